@@ -1,0 +1,464 @@
+"""NumPy restatement of the OpenCV (opencv-python-headless 4.13.0.92) numerics that the
+reference's distortion / blend path delegates to.  TEST INFRASTRUCTURE ONLY: imported by
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline leg; never by `vkit_b200/`.
+
+The reference (vkit-x/vkit @ 98ada2d) holds no arithmetic of its own for these steps; it calls
+cv2, an un-vendored dependency pinned only by minimum version (`setup.cfg:21-25`).  Each
+function below names the reference call site it stands in for and is pinned bit-exactly (or to
+the stated tolerance) against the real cv2 wheel in `tests/test_oracle_cv2_model.py` (which
+runs wherever cv2 is importable) and against fixtures in `tests/golden/`.
+
+Reference call sites:
+  remap_linear              vkit/mechanism/distortion/geometric/grid_rendering/grid_blender.py:60,70,80
+  warp_affine               vkit/mechanism/distortion/geometric/affine.py:40
+  warp_perspective          vkit/mechanism/distortion/geometric/affine.py:43
+  get_perspective_transform vkit/mechanism/distortion/geometric/grid_rendering/type.py:172,189; affine.py:326,386
+  fill_poly                 vkit/element/polygon.py:75
+  gaussian_blur_u8          vkit/mechanism/distortion/photometric/blur.py:65
+  cvt_*                     vkit/element/image.py:794,800,808
+  rodrigues/project_points  vkit/mechanism/distortion/geometric/camera.py:96,189
+"""
+import numpy as np
+
+INTER_BITS = 5
+INTER_TAB_SIZE = 1 << INTER_BITS  # 32 sub-pixel positions per axis
+REMAP_COEF_BITS = 15
+
+
+# --------------------------------------------------------------------------------------------
+# Bilinear sampling shared by remap / warpAffine / warpPerspective (BORDER_CONSTANT, value 0).
+# --------------------------------------------------------------------------------------------
+def _tap(src, yy, xx):
+    """src[yy, xx] with zeros outside the image. yy/xx int arrays of equal shape."""
+    h, w = src.shape[:2]
+    inside = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+    yc = np.clip(yy, 0, h - 1)
+    xc = np.clip(xx, 0, w - 1)
+    val = src[yc, xc]
+    if src.ndim == 3:
+        inside = inside[..., None]
+    return np.where(inside, val, np.zeros((), dtype=src.dtype))
+
+
+def bilinear_fixed(src, X, Y):
+    """Sample `src` at 1/32-pixel fixed-point coordinates (X, Y) the way cv::remap does.
+
+    uint8: integer weights that sum to 2^15, result (acc + 2^14) >> 15.
+    float32: float32 weights ((32-f)/32 products), float32 multiply/adds in tap order.
+    """
+    X = np.asarray(X, dtype=np.int64)
+    Y = np.asarray(Y, dtype=np.int64)
+    # cv::remap stores integer coordinates as int16 (saturate_cast<short>).
+    x0 = np.clip(X >> INTER_BITS, -32768, 32767)
+    y0 = np.clip(Y >> INTER_BITS, -32768, 32767)
+    fx = X & (INTER_TAB_SIZE - 1)
+    fy = Y & (INTER_TAB_SIZE - 1)
+
+    p00 = _tap(src, y0, x0)
+    p01 = _tap(src, y0, x0 + 1)
+    p10 = _tap(src, y0 + 1, x0)
+    p11 = _tap(src, y0 + 1, x0 + 1)
+
+    if src.dtype == np.uint8:
+        w00 = (32 - fy) * (32 - fx) * 32
+        w01 = (32 - fy) * fx * 32
+        w10 = fy * (32 - fx) * 32
+        w11 = fy * fx * 32
+        if src.ndim == 3:
+            w00, w01, w10, w11 = (w[..., None] for w in (w00, w01, w10, w11))
+        acc = (p00.astype(np.int64) * w00 + p01.astype(np.int64) * w01
+               + p10.astype(np.int64) * w10 + p11.astype(np.int64) * w11)
+        return ((acc + (1 << (REMAP_COEF_BITS - 1))) >> REMAP_COEF_BITS).astype(np.uint8)
+
+    if src.dtype == np.float32:
+        one = np.float32(1.0)
+        scale = np.float32(1.0 / INTER_TAB_SIZE)
+        ax = fx.astype(np.float32) * scale
+        ay = fy.astype(np.float32) * scale
+        w00 = (one - ay) * (one - ax)
+        w01 = (one - ay) * ax
+        w10 = ay * (one - ax)
+        w11 = ay * ax
+        if src.ndim == 3:
+            w00, w01, w10, w11 = (w[..., None] for w in (w00, w01, w10, w11))
+        out = p00 * w00
+        out = out + p01 * w01
+        out = out + p10 * w10
+        out = out + p11 * w11
+        return out.astype(np.float32)
+
+    raise NotImplementedError(src.dtype)
+
+
+def cv_round(x):
+    """cvRound: round-half-to-even on a double, to int64."""
+    return np.rint(np.asarray(x, dtype=np.float64)).astype(np.int64)
+
+
+def remap_linear(src, map_x, map_y):
+    """cv.remap(src, map_x, map_y, cv.INTER_LINEAR) with BORDER_CONSTANT(0)."""
+    assert map_x.dtype == np.float32 and map_y.dtype == np.float32
+    # float32 * 32 is exact; saturate to int32 like saturate_cast<int>.
+    X = np.clip(cv_round(map_x.astype(np.float64) * INTER_TAB_SIZE), -2**31, 2**31 - 1)
+    Y = np.clip(cv_round(map_y.astype(np.float64) * INTER_TAB_SIZE), -2**31, 2**31 - 1)
+    return bilinear_fixed(src, X, Y)
+
+
+def invert_affine(M):
+    """Inverse of a 2x3 affine map exactly as cv::warpAffine computes it (double)."""
+    M = np.asarray(M, dtype=np.float64).copy()
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    A11 = M[1, 1] * D
+    A22 = M[0, 0] * D
+    M[0, 0] = A11
+    M[0, 1] *= -D
+    M[1, 0] *= -D
+    M[1, 1] = A22
+    b1 = -M[0, 0] * M[0, 2] - M[0, 1] * M[1, 2]
+    b2 = -M[1, 0] * M[0, 2] - M[1, 1] * M[1, 2]
+    M[0, 2] = b1
+    M[1, 2] = b2
+    return M
+
+
+def affine_fixed_coords(M, dsize):
+    """1/32-pixel source coordinates for every dst pixel of cv.warpAffine(src, M, dsize)."""
+    width, height = dsize
+    Mi = invert_affine(M)
+    AB_BITS = 10
+    AB_SCALE = 1 << AB_BITS
+    round_delta = AB_SCALE // INTER_TAB_SIZE // 2  # 16
+    xs = np.arange(width, dtype=np.float64)
+    ys = np.arange(height, dtype=np.float64)
+    adelta = cv_round(Mi[0, 0] * xs * AB_SCALE)
+    bdelta = cv_round(Mi[1, 0] * xs * AB_SCALE)
+    X0 = cv_round((Mi[0, 1] * ys + Mi[0, 2]) * AB_SCALE) + round_delta
+    Y0 = cv_round((Mi[1, 1] * ys + Mi[1, 2]) * AB_SCALE) + round_delta
+    X = (X0[:, None] + adelta[None, :]) >> (AB_BITS - INTER_BITS)
+    Y = (Y0[:, None] + bdelta[None, :]) >> (AB_BITS - INTER_BITS)
+    return X, Y
+
+
+def warp_affine(src, M, dsize):
+    """cv.warpAffine(src, M, dsize) (INTER_LINEAR, BORDER_CONSTANT 0)."""
+    X, Y = affine_fixed_coords(M, dsize)
+    return bilinear_fixed(src, X, Y)
+
+
+def perspective_fixed_coords(M, dsize):
+    width, height = dsize
+    Mi = np.linalg.inv(np.asarray(M, dtype=np.float64))
+    xs = np.arange(width, dtype=np.float64)[None, :]
+    ys = np.arange(height, dtype=np.float64)[:, None]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        W = Mi[2, 0] * xs + Mi[2, 1] * ys + Mi[2, 2]
+        W = np.where(W != 0, INTER_TAB_SIZE / W, 0.0)
+        fX = np.clip((Mi[0, 0] * xs + Mi[0, 1] * ys + Mi[0, 2]) * W, -2.0**31, 2.0**31 - 1)
+        fY = np.clip((Mi[1, 0] * xs + Mi[1, 1] * ys + Mi[1, 2]) * W, -2.0**31, 2.0**31 - 1)
+    return cv_round(fX), cv_round(fY)
+
+
+def warp_perspective(src, M, dsize):
+    """cv.warpPerspective(src, M, dsize) (INTER_LINEAR, BORDER_CONSTANT 0)."""
+    X, Y = perspective_fixed_coords(M, dsize)
+    return bilinear_fixed(src, X, Y)
+
+
+# --------------------------------------------------------------------------------------------
+# Homography from 4 point pairs.
+# --------------------------------------------------------------------------------------------
+def get_perspective_transform(src, dst):
+    """cv.getPerspectiveTransform(src, dst, cv.DECOMP_SVD): 8x8 system solved in double."""
+    src = np.asarray(src, dtype=np.float64)
+    dst = np.asarray(dst, dtype=np.float64)
+    A = np.zeros((8, 8), dtype=np.float64)
+    b = np.zeros(8, dtype=np.float64)
+    for i in range(4):
+        sx, sy = src[i]
+        dx, dy = dst[i]
+        A[i] = [sx, sy, 1, 0, 0, 0, -sx * dx, -sy * dx]
+        A[i + 4] = [0, 0, 0, sx, sy, 1, -sx * dy, -sy * dy]
+        b[i] = dx
+        b[i + 4] = dy
+    U, w, Vt = np.linalg.svd(A)
+    x = Vt.T @ ((U.T @ b) / w)
+    return np.append(x, 1.0).reshape(3, 3)
+
+
+# --------------------------------------------------------------------------------------------
+# cv.fillPoly(img, [pts int32], 1) for one polygon, lineType 8, shift 0.
+# --------------------------------------------------------------------------------------------
+def _line8(mask, x0, y0, x1, y1):
+    """cv::LineIterator(connectivity=8, leftToRight=true); both endpoints inside the canvas."""
+    h, w = mask.shape
+    if x0 > x1:
+        x0, y0, x1, y1 = x1, y1, x0, y0
+    dx = x1 - x0
+    dy = y1 - y0
+    sy = 1 if dy >= 0 else -1
+    dy = abs(dy)
+    steep = dy > dx
+    if steep:
+        dx, dy = dy, dx
+    err = dx - 2 * dy
+    x, y = x0, y0
+    for _ in range(dx + 1):
+        if 0 <= x < w and 0 <= y < h:
+            mask[y, x] = 1
+        m = err < 0
+        err += -2 * dy + (2 * dx if m else 0)
+        if steep:
+            y += sy
+            if m:
+                x += 1
+        else:
+            x += 1
+            if m:
+                y += sy
+
+
+def fill_poly(shape, pts):
+    """Coverage (uint8 0/1) of cv.fillPoly on a zero canvas of `shape` for one polygon.
+
+    outline (8-connected Bresenham per edge) UNION scan-line fill with 16.16 fixed-point edges,
+    spans [ceil(xl), floor(xr)], edges active on [ymin, ymax).  Polygon assumed inside canvas
+    (the reference always rasterises on the polygon's own bounding box, polygon.py:70-77).
+    """
+    h, w = shape
+    mask = np.zeros((h, w), dtype=np.uint8)
+    pts = [(int(p[0]), int(p[1])) for p in pts]
+    n = len(pts)
+    edges = []
+    for i in range(n):
+        x0, y0 = pts[i - 1]
+        x1, y1 = pts[i]
+        _line8(mask, x0, y0, x1, y1)
+        if y0 == y1:
+            continue
+        num = (x1 - x0) << 16
+        den = y1 - y0
+        dxf = abs(num) // abs(den)
+        if (num < 0) != (den < 0):
+            dxf = -dxf  # C truncating division
+        if y0 < y1:
+            edges.append((y0, y1, x0 << 16, dxf))
+        else:
+            edges.append((y1, y0, x1 << 16, dxf))
+    if not edges:
+        return mask
+    y_lo = min(e[0] for e in edges)
+    y_hi = max(e[1] for e in edges)
+    for y in range(max(y_lo, 0), min(y_hi, h)):
+        xs = sorted(x + d * (y - ya) for (ya, yb, x, d) in edges if ya <= y < yb)
+        for k in range(0, len(xs) - 1, 2):
+            xl = (xs[k] + 65535) >> 16
+            xr = xs[k + 1] >> 16
+            xl = max(xl, 0)
+            xr = min(xr, w - 1)
+            if xl <= xr:
+                mask[y, xl:xr + 1] = 1
+    return mask
+
+
+# --------------------------------------------------------------------------------------------
+# cv.GaussianBlur(uint8, (k, k), sigma), BORDER_REFLECT_101: 8.8 fixed-point separable filter.
+# --------------------------------------------------------------------------------------------
+def gaussian_kernel_u8(ksize, sigma):
+    """Integer (sum 256) kernel cv::getGaussianKernelBitExact builds for uint8 images."""
+    r = ksize // 2
+    xs = np.arange(ksize, dtype=np.float64) - r
+    k = np.exp(-(xs * xs) / (2.0 * sigma * sigma))
+    k = k / k.sum()
+    out = np.zeros(ksize, dtype=np.int64)
+    err = 0.0
+    for i in range(r):
+        adj = k[i] * 256.0 + err
+        v = np.rint(adj)
+        err = adj - v
+        out[i] = out[ksize - 1 - i] = int(v)
+    out[r] = 256 - out.sum()
+    return out
+
+
+def _reflect101(idx, n):
+    if n == 1:
+        return np.zeros_like(idx)
+    period = 2 * (n - 1)
+    idx = np.abs(idx) % period
+    return np.where(idx >= n, period - idx, idx)
+
+
+def gaussian_blur_u8(src, ksize, sigma):
+    assert src.dtype == np.uint8
+    K = gaussian_kernel_u8(ksize, sigma)
+    r = ksize // 2
+    h, w = src.shape[:2]
+    s = src.astype(np.int64)
+    cols = _reflect101(np.arange(-r, w + r), w)
+    rows = _reflect101(np.arange(-r, h + r), h)
+    sp = s[:, cols]
+    acc = np.zeros_like(s)
+    for i in range(ksize):
+        acc += sp[:, i:i + w] * K[i]
+    acc = np.minimum(acc, 65535)
+    ap = acc[rows]
+    out = np.zeros_like(s)
+    for i in range(ksize):
+        out += ap[i:i + h] * K[i]
+    out = np.minimum((out + (1 << 15)) >> 16, 255)
+    return out.astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# Colour conversions (uint8).
+# --------------------------------------------------------------------------------------------
+def _div_table(scale):
+    t = np.zeros(256, dtype=np.int64)
+    i = np.arange(1, 256, dtype=np.float64)
+    t[1:] = np.rint(scale / i).astype(np.int64)
+    return t
+
+
+_SDIV = _div_table(255 << 12)
+_HDIV256 = _div_table((256 << 12) / 6.0)
+
+
+def cvt_rgb2hsv_full(rgb):
+    """cv.cvtColor(uint8, COLOR_RGB2HSV_FULL): integer tables, hue range 256."""
+    r = rgb[..., 0].astype(np.int64)
+    g = rgb[..., 1].astype(np.int64)
+    b = rgb[..., 2].astype(np.int64)
+    v = np.maximum(np.maximum(r, g), b)
+    vmin = np.minimum(np.minimum(r, g), b)
+    diff = v - vmin
+    vr = v == r
+    vg = v == g
+    h = np.where(vr, g - b, np.where(vg, b - r + 2 * diff, r - g + 4 * diff))
+    s = (diff * _SDIV[v] + (1 << 11)) >> 12
+    h = (h * _HDIV256[diff] + (1 << 11)) >> 12
+    h = h + np.where(h < 0, 256, 0)
+    out = np.stack([np.clip(h, 0, 255), s, v], axis=-1)
+    return out.astype(np.uint8)
+
+
+_SECTOR = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+
+
+def _sector_pick(tab, sector):
+    """tab: (..., 4) float32, sector: (...) int in [0, 6). Returns (b, g, r) picks."""
+    idx = _SECTOR[sector]  # (..., 3)
+    return np.take_along_axis(tab, idx, axis=-1)
+
+
+def cvt_hsv2rgb_full(hsv):
+    """cv.cvtColor(uint8, COLOR_HSV2RGB_FULL): float32 path, hue scale 6/255 (+-1 vs cv2 on
+    <= 78 of 2^24 inputs; cv2 itself is backend dependent here)."""
+    f32 = np.float32
+    h = hsv[..., 0].astype(f32) * f32(6.0 / 255.0)
+    s = hsv[..., 1].astype(f32) * f32(1.0 / 255.0)
+    v = hsv[..., 2].astype(f32) * f32(1.0 / 255.0)
+    sector = np.floor(h).astype(np.int64)
+    frac = h - sector.astype(f32)
+    sector = sector % 6
+    one = f32(1.0)
+    tab = np.stack([v, v * (one - s), v * (one - s * frac), v * (one - s * (one - frac))],
+                   axis=-1).astype(f32)
+    bgr = _sector_pick(tab, sector)
+    gray = np.stack([v, v, v], axis=-1)
+    bgr = np.where((hsv[..., 1] == 0)[..., None], gray, bgr)
+    rgb = bgr[..., ::-1]
+    return np.clip(np.rint(rgb * f32(255.0)), 0, 255).astype(np.uint8)
+
+
+def cvt_rgb2hls_full(rgb):
+    """cv.cvtColor(uint8, COLOR_RGB2HLS_FULL): float32 path, hue scale 255/360. L is exact,
+    H/S within +-1 of cv2 (backend dependent inside cv2, appendix A.6)."""
+    f32 = np.float32
+    x = rgb.astype(f32) * f32(1.0 / 255.0)
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    vmax = np.maximum(np.maximum(r, g), b)
+    vmin = np.minimum(np.minimum(r, g), b)
+    diff = vmax - vmin
+    l = (vmax + vmin) * f32(0.5)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        s = np.where(l < f32(0.5), diff / (vmax + vmin), diff / (f32(2.0) - vmax - vmin))
+        d = f32(60.0) / diff
+        h = np.where(vmax == r, (g - b) * d,
+                     np.where(vmax == g, (b - r) * d + f32(120.0), (r - g) * d + f32(240.0)))
+    h = np.where(h < 0, h + f32(360.0), h)
+    zero = diff <= np.finfo(f32).eps
+    h = np.where(zero, f32(0), h)
+    s = np.where(zero, f32(0), s)
+    out = np.stack([h * f32(255.0 / 360.0), l * f32(255.0), s * f32(255.0)], axis=-1)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def cvt_hls2rgb_full(hls):
+    """cv.cvtColor(uint8, COLOR_HLS2RGB_FULL): float32 path, hue scale 6/255."""
+    f32 = np.float32
+    h = hls[..., 0].astype(f32) * f32(6.0 / 255.0)
+    l = hls[..., 1].astype(f32) * f32(1.0 / 255.0)
+    s = hls[..., 2].astype(f32) * f32(1.0 / 255.0)
+    one = f32(1.0)
+    p2 = np.where(l <= f32(0.5), l * (one + s), l + s - l * s)
+    p1 = f32(2.0) * l - p2
+    sector = np.floor(h).astype(np.int64)
+    frac = h - sector.astype(f32)
+    sector = sector % 6
+    tab = np.stack([p2, p1, p1 + (p2 - p1) * (one - frac), p1 + (p2 - p1) * frac],
+                   axis=-1).astype(f32)
+    bgr = _sector_pick(tab, sector)
+    gray = np.stack([l, l, l], axis=-1)
+    bgr = np.where((hls[..., 2] == 0)[..., None], gray, bgr)
+    rgb = bgr[..., ::-1]
+    return np.clip(np.rint(rgb * f32(255.0)), 0, 255).astype(np.uint8)
+
+
+def cvt_rgb2gray(rgb):
+    """cv.cvtColor(uint8, COLOR_RGB2GRAY): (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+    (pinned over all 2^24 colours against cv2 4.13.0)."""
+    r = rgb[..., 0].astype(np.int64)
+    g = rgb[..., 1].astype(np.int64)
+    b = rgb[..., 2].astype(np.int64)
+    return ((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def cvt_gray2rgb(gray):
+    return np.repeat(gray[..., None], 3, axis=-1)
+
+
+# --------------------------------------------------------------------------------------------
+# Pin-hole camera helpers (double precision, as inside cv2).
+# --------------------------------------------------------------------------------------------
+def rodrigues(rvec):
+    """cv.Rodrigues(rvec) -> 3x3 rotation matrix, computed in double."""
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    theta = np.sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2])
+    if theta < np.finfo(np.float64).eps:
+        return np.eye(3)
+    c = np.cos(theta)
+    s = np.sin(theta)
+    c1 = 1.0 - c
+    x, y, z = r / theta
+    rrt = np.array([[x * x, x * y, x * z], [x * y, y * y, y * z], [x * z, y * z, z * z]])
+    rx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+    return c * np.eye(3) + c1 * rrt + s * rx
+
+
+def project_points(pts3d, rvec, tvec, K):
+    """cv.projectPoints(pts3d, rvec, tvec, K, zeros(5)) -> (N, 2), output dtype = input dtype."""
+    out_dtype = pts3d.dtype
+    P = np.asarray(pts3d, dtype=np.float64)
+    R = rodrigues(np.asarray(rvec, dtype=np.float64))
+    t = np.asarray(tvec, dtype=np.float64).reshape(3)
+    K = np.asarray(K, dtype=np.float64)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    X, Y, Z = P[:, 0], P[:, 1], P[:, 2]
+    x = R[0, 0] * X + R[0, 1] * Y + R[0, 2] * Z + t[0]
+    y = R[1, 0] * X + R[1, 1] * Y + R[1, 2] * Z + t[1]
+    z = R[2, 0] * X + R[2, 1] * Y + R[2, 2] * Z + t[2]
+    z = np.where(z != 0, 1.0 / np.where(z != 0, z, 1.0), 1.0)
+    x = x * z
+    y = y * z
+    return np.stack([x * fx + cx, y * fy + cy], axis=-1).astype(out_dtype)
