@@ -1,0 +1,186 @@
+/* vkit_b200.h -- C ABI of libvkit_b200.so (sm_100a).
+ *
+ * The reference (vkit-x/vkit @ 98ada2d) has no FFI: its plugin boundary is the Python
+ * `Distortion(config_cls, state_cls, func_image, func_mask, func_score_map, ...)` object
+ * (vkit/mechanism/distortion/interface.py:141-248).  The entry points below are what the
+ * `func_*` callables and `state_cls` constructors of that object bind to once the NumPy/cv2
+ * arithmetic underneath them is replaced; each one cites the reference code it stands in for.
+ * INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all memory (outputs and workspaces are allocated by the caller);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, negative = error; `vkb_last_error()` gives the message
+ *     (thread local);
+ *   - images are dense HWC uint8 (C = 1, 3 or 4), masks dense HW uint8, score maps dense HW
+ *     float32 -- the layouts of `Image.mat`, `Mask.mat`, `ScoreMap.mat`
+ *     (vkit/element/image.py:217-258, mask.py:71-88, score_map.py:86-108).
+ */
+#ifndef VKIT_B200_H_
+#define VKIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKB_OK 0
+#define VKB_ERR_INVALID (-1)
+#define VKB_ERR_CUDA (-2)
+
+int vkb_version(void);
+const char* vkb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Containers that travel together through one geometric op (Image + Mask + ScoreMap of one
+ * page).  Absent containers have NULL pointers / image_channels == 0.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vkb_planes {
+    const uint8_t* src_image;
+    uint8_t* dst_image;
+    const uint8_t* src_mask;
+    uint8_t* dst_mask;
+    const float* src_score;
+    float* dst_score;
+    int32_t image_channels;
+    int32_t src_h, src_w;
+    int32_t dst_h, dst_w;
+    int32_t _pad;
+} vkb_planes;
+
+/* ---------------------------------------------------------------------------------------
+ * Affine family: rotate / shear_hori / shear_vert (2x3, cv.warpAffine) and skew_hori /
+ * skew_vert (3x3, cv.warpPerspective).  Replaces affine_mat + affine_trait_func_image /
+ * _mask / _score_map (vkit/mechanism/distortion/geometric/affine.py:38-43, 416-456).
+ * `inv` is the INVERSE map (dst -> src) in double, row major; for kind 0 only inv[0..5]
+ * are used.  One launch warps all present containers of all pages.
+ * ------------------------------------------------------------------------------------- */
+#define VKB_WARP_AFFINE 0
+#define VKB_WARP_PERSPECTIVE 1
+
+typedef struct vkb_warp_page {
+    vkb_planes planes;
+    double inv[9];
+    int32_t kind;
+    int32_t _pad;
+} vkb_warp_page;
+
+int vkb_warp_fused(const vkb_warp_page* pages, int32_t n_pages, int32_t max_dst_h,
+                   int32_t max_dst_w, void* stream);
+
+/* Points through a 2x3 / 3x3 forward matrix (affine_np_points, affine.py:46-64).
+ * xy_in / xy_out: n x 2 float64 (x, y). mat: 6 or 9 doubles (host pointer, copied by value).
+ * `f32_math` != 0 evaluates in float32 like the reference does for the 2x3 ops. */
+int vkb_affine_points(const double* mat_host, int32_t rows, const double* xy_in, double* xy_out,
+                      int32_t n, int32_t f32_math, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Grid-based ops: camera_* and similarity_mls.
+ * Replaces create_dst_image_grid_and_shift_amounts_and_resize_ratios (grid_creator.py:44-115),
+ * the point projectors (camera.py:188-212, 276-282, 375-398, 464-480; mls.py:52-135),
+ * ImageGrid.get_inv_trans_mat / generate_remap_params (type.py:182-261) and
+ * blend_src_to_dst_* (grid_blender.py:54-81).
+ * ------------------------------------------------------------------------------------- */
+#define VKB_PROJ_CAMERA 0
+#define VKB_PROJ_MLS 1
+#define VKB_PROJ_GIVEN 2 /* lattice_f already holds the projected lattice (tests, plugins) */
+
+#define VKB_CAM_PLANE 0
+#define VKB_CAM_CUBIC 1
+#define VKB_CAM_LINE_FOLD 2
+#define VKB_CAM_LINE_CURVE 3
+
+typedef struct vkb_grid_page {
+    int32_t src_h, src_w;
+    int32_t grid_size;
+    int32_t rows, cols; /* lattice points per column / row (grid_creator.py:22-41) */
+    int32_t projector;
+    int32_t strategy;
+    int32_t resize_as_src;
+    /* camera model (camera.py:58-196): Rodrigues matrix, translation, focal length */
+    double R[9];
+    double t[3];
+    double focal;
+    /* cubic curve (camera.py:313-398) */
+    double poly[4];
+    double curve_scale;
+    float rot2[4];
+    float proj_min, proj_range;
+    /* plane line fold / curve (camera.py:432-480) */
+    double line_c;
+    double dist_max;
+    double line_alpha;
+    float line_ab[2];
+    float perturb[3];
+    int32_t n_handles;
+    /* similarity MLS (mls.py:38-135): n_handles x 2 float32 (x, y) each */
+    const float* handles_src;
+    const float* handles_dst;
+} vkb_grid_page;
+
+typedef struct vkb_grid_meta {
+    int32_t dst_h, dst_w;     /* result shape (type.py:41-50) */
+    int32_t shift_y, shift_x; /* grid_creator.py:61-81 */
+    double resize_ratio_y, resize_ratio_x;
+    int32_t status; /* bit 0: some tile candidate list overflowed (slow path used) */
+    int32_t n_flagged_cells;
+} vkb_grid_meta;
+
+/* Fixed per-cell budget of coverage-mask words; cells that need more are rasterised on the
+ * fly by the remap kernel. */
+#define VKB_CELL_MASK_WORDS 32
+#define VKB_TILE 32     /* dst tile edge of the remap kernel */
+#define VKB_TILE_CAP 64 /* candidate cells kept per tile before the slow path is used */
+
+/* Phase 1: project the source lattice (p_max >= rows*cols of every page).
+ * lattice_f: n_pages x p_max x 2 doubles (x, y), un-shifted projected coordinates. */
+int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
+                     double* lattice_f, void* stream);
+
+/* Phase 1b: round (half to even), shift to the origin, optional resize_as_src, result shape.
+ * lattice_i: n_pages x p_max x 2 int32 (x, y). */
+int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
+                      const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
+                      void* stream);
+
+/* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage masks; per dst
+ * tile the list of candidate cells.  c_max >= (rows-1)*(cols-1); t_max >= tiles per page.
+ *   hinv:       n_pages x c_max x 9 doubles
+ *   hfwd:       n_pages x c_max x 9 doubles or NULL (forward maps, needed by vkb_grid_points)
+ *   cell_box:   n_pages x c_max x 4 int32 (x0, y0, x1, y1); bit 30 of x1 set = coverage of
+ *               this cell exceeds the mask budget and is rasterised on the fly by the remap
+ *   cell_masks: n_pages x c_max x VKB_CELL_MASK_WORDS uint32
+ *   tile_count: n_pages x t_max int32 (zeroed by this call)
+ *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16 */
+int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
+                   int32_t t_max, const int32_t* lattice_i, vkb_grid_meta* meta, double* hinv,
+                   double* hfwd, int32_t* cell_box, uint32_t* cell_masks, int32_t* tile_count,
+                   uint16_t* tile_cells, void* stream);
+
+/* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
+ * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
+ * value, 1/32 px quantisation, bilinear gather of Image + Mask + ScoreMap in one pass. */
+int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
+                   int32_t p_max, int32_t c_max, int32_t t_max, const int32_t* lattice_i,
+                   const vkb_grid_meta* meta, const double* hinv, const int32_t* cell_box,
+                   const uint32_t* cell_masks,
+                   const int32_t* tile_count, const uint16_t* tile_cells, int32_t max_dst_h,
+                   int32_t max_dst_w, void* stream);
+
+/* Points through the forward homography of the source cell that contains the ROUNDED point
+ * (FuncImageGridBased.func_point, grid_rendering/interface.py:194-216).
+ * xy_in: n x 2 doubles (smooth x, y); cell_rc: n x 2 int32 (polygon_row, polygon_col). */
+int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double* xy_in,
+                    const int32_t* cell_rc, double* xy_out, int32_t n, void* stream);
+
+/* Active mask: cv.fillPoly of one polygon (the dst lattice border, interface.py:177-192)
+ * on a zeroed uint8 canvas.  poly_xy: n_pts x 2 int32 (x, y). */
+int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32_t* poly_xy, int32_t n_pts,
+                     uint8_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKIT_B200_H_ */

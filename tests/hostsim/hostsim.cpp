@@ -1,0 +1,158 @@
+// hostsim.cpp -- TEST HARNESS ONLY.  Compiles vkit_b200/csrc/vkb_math.cuh and vkb_lattice.cuh
+// (the per-element numerics the CUDA kernels call) with g++ and walks them sequentially over a
+// page, so the arithmetic can be compared with the oracle on a machine that has no GPU.
+// Nothing in vkit_b200/ links or loads this file.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "../../vkit_b200/csrc/vkb_math.cuh"
+#include "../../vkit_b200/csrc/vkb_lattice.cuh"
+
+using namespace vkb;
+
+static void sample_and_store(const vkb_planes& pl, int x, int y, int X, int Y) {
+    const long long di = (long long)y * pl.dst_w + x;
+    if (pl.image_channels == 3) bilinear_u8<3>(pl.src_image, pl.src_h, pl.src_w, (long long)pl.src_w * 3, X, Y, pl.dst_image + di * 3);
+    else if (pl.image_channels == 1) bilinear_u8<1>(pl.src_image, pl.src_h, pl.src_w, pl.src_w, X, Y, pl.dst_image + di);
+    else if (pl.image_channels == 4) bilinear_u8<4>(pl.src_image, pl.src_h, pl.src_w, (long long)pl.src_w * 4, X, Y, pl.dst_image + di * 4);
+    if (pl.src_mask) bilinear_u8<1>(pl.src_mask, pl.src_h, pl.src_w, pl.src_w, X, Y, pl.dst_mask + di);
+    if (pl.src_score) pl.dst_score[di] = bilinear_f32(pl.src_score, pl.src_h, pl.src_w, pl.src_w, X, Y);
+}
+
+extern "C" void hs_warp(const vkb_warp_page* pg) {
+    const vkb_planes& pl = pg->planes;
+    for (int y = 0; y < pl.dst_h; ++y)
+        for (int x = 0; x < pl.dst_w; ++x) {
+            int X, Y;
+            if (pg->kind == VKB_WARP_AFFINE) affine_coord(pg->inv, x, y, X, Y);
+            else perspective_coord(pg->inv, x, y, X, Y);
+            sample_and_store(pl, x, y, X, Y);
+        }
+}
+
+// lattice_f: P x 2 doubles (x, y)
+extern "C" void hs_grid_project(const vkb_grid_page* pg, double* out) {
+    const int P = pg->rows * pg->cols;
+    auto cx = [&](int i) { return lattice_coord(i % pg->cols, pg->src_w, pg->grid_size); };
+    auto cy = [&](int i) { return lattice_coord(i / pg->cols, pg->src_h, pg->grid_size); };
+    if (pg->projector == VKB_PROJ_MLS) {
+        for (int i = 0; i < P; ++i)
+            mls_point_seq(pg->handles_src, pg->handles_dst, pg->n_handles, (float)cx(i), (float)cy(i), out[2 * i], out[2 * i + 1]);
+        return;
+    }
+    if (pg->projector != VKB_PROJ_CAMERA) return;
+    if (pg->strategy == VKB_CAM_PLANE) {
+        for (int i = 0; i < P; ++i) {
+            double u, v;
+            project_point(pg->R, pg->t, pg->focal, cx(i), cy(i), 0.0, u, v);
+            out[2 * i] = (double)(float)u;
+            out[2 * i + 1] = (double)(float)v;
+        }
+    } else if (pg->strategy == VKB_CAM_CUBIC) {
+        std::vector<double> z(P);
+        double sum = 0;
+        for (int i = 0; i < P; ++i) { z[i] = cubic_z(*pg, (float)cx(i), (float)cy(i)); sum += z[i]; }
+        const double mean = sum / P;
+        for (int i = 0; i < P; ++i)
+            project_point(pg->R, pg->t, pg->focal, cx(i), cy(i), z[i] - mean, out[2 * i], out[2 * i + 1]);
+    } else {
+        std::vector<double> w(P);
+        double s[3] = {0, 0, 0};
+        for (int i = 0; i < P; ++i) {
+            w[i] = line_weight(*pg, (float)cx(i), (float)cy(i));
+            for (int k = 0; k < 3; ++k) s[k] += w[i] * (double)pg->perturb[k];
+        }
+        for (int k = 0; k < 3; ++k) s[k] /= P;
+        for (int i = 0; i < P; ++i) {
+            const float X = (float)((double)cx(i) + (w[i] * (double)pg->perturb[0] - s[0]));
+            const float Y = (float)((double)cy(i) + (w[i] * (double)pg->perturb[1] - s[1]));
+            const float Z = (float)(0.0 + (w[i] * (double)pg->perturb[2] - s[2]));
+            double u, v;
+            project_point(pg->R, pg->t, pg->focal, X, Y, Z, u, v);
+            out[2 * i] = (double)(float)u;
+            out[2 * i + 1] = (double)(float)v;
+        }
+    }
+}
+
+extern "C" void hs_grid_finalize(const vkb_grid_page* pg, const double* in, int32_t* out, vkb_grid_meta* m) {
+    const int P = pg->rows * pg->cols;
+    int mnx = INT32_MAX, mny = INT32_MAX;
+    for (int i = 0; i < P; ++i) { mnx = std::min(mnx, cv_round_d(in[2 * i])); mny = std::min(mny, cv_round_d(in[2 * i + 1])); }
+    int mxx = INT32_MIN, mxy = INT32_MIN;
+    for (int i = 0; i < P; ++i) {
+        out[2 * i] = cv_round_d(in[2 * i] - (double)mnx);
+        out[2 * i + 1] = cv_round_d(in[2 * i + 1] - (double)mny);
+        mxx = std::max(mxx, out[2 * i]); mxy = std::max(mxy, out[2 * i + 1]);
+    }
+    m->dst_w = mxx + 1; m->dst_h = mxy + 1; m->shift_x = mnx; m->shift_y = mny;
+    m->resize_ratio_x = m->resize_ratio_y = 1.0; m->status = 0; m->n_flagged_cells = 0;
+    if (pg->resize_as_src) {
+        const int raw_w = m->dst_w, raw_h = m->dst_h;
+        m->resize_ratio_y = (double)pg->src_h / raw_h; m->resize_ratio_x = (double)pg->src_w / raw_w;
+        for (int i = 0; i < P; ++i) {
+            double sx = (in[2 * i] - (double)mnx) * (double)pg->src_w / (double)raw_w;
+            double sy = (in[2 * i + 1] - (double)mny) * (double)pg->src_h / (double)raw_h;
+            sx = std::max(0.0, std::min(sx, (double)(pg->src_w - 1)));
+            sy = std::max(0.0, std::min(sy, (double)(pg->src_h - 1)));
+            out[2 * i] = cv_round_d(sx); out[2 * i + 1] = cv_round_d(sy);
+        }
+        m->dst_h = pg->src_h; m->dst_w = pg->src_w;
+    }
+}
+
+// owner map (int32, -1 = uncovered) + inverse homographies + remap of the planes
+extern "C" void hs_grid_remap(const vkb_grid_page* pg, const int32_t* lat, const vkb_planes* pl,
+                              int32_t* owner, double* hinv_out) {
+    const int ccols = pg->cols - 1, C = (pg->rows - 1) * ccols;
+    const int W = pl->dst_w, Hh = pl->dst_h;
+    std::fill(owner, owner + (size_t)W * Hh, -1);
+    std::vector<double> hinv((size_t)C * 9);
+    for (int cell = 0; cell < C; ++cell) {
+        const int r = cell / ccols, c = cell % ccols;
+        const int i00 = r * pg->cols + c, i01 = i00 + 1, i11 = i00 + pg->cols + 1, i10 = i00 + pg->cols;
+        const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
+        const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
+        const double sx0 = lattice_coord(c, pg->src_w, pg->grid_size), sx1 = lattice_coord(c + 1, pg->src_w, pg->grid_size);
+        const double sy0 = lattice_coord(r, pg->src_h, pg->grid_size), sy1 = lattice_coord(r + 1, pg->src_h, pg->grid_size);
+        const double sq[8] = {sx0, sy0, sx1, sy0, sx1, sy1, sx0, sy1};
+        const double dq[8] = {(double)px[0], (double)py[0], (double)px[1], (double)py[1], (double)px[2], (double)py[2], (double)px[3], (double)py[3]};
+        homography_4pt(dq, sq, &hinv[(size_t)cell * 9]);
+        const int x0 = *std::min_element(px, px + 4), x1 = *std::max_element(px, px + 4);
+        const int y0 = *std::min_element(py, py + 4), y1 = *std::max_element(py, py + 4);
+        const int nwords = (x1 - x0 + 32) / 32;
+        std::vector<uint32_t> words(nwords);
+        for (int y = y0; y <= y1; ++y) {
+            std::fill(words.begin(), words.end(), 0u);
+            poly_row_mask<4>(px, py, y, x0, words.data(), nwords);
+            for (int x = x0; x <= x1; ++x)
+                if ((words[(x - x0) >> 5] >> ((x - x0) & 31)) & 1u)
+                    if (y >= 0 && y < Hh && x >= 0 && x < W) owner[(size_t)y * W + x] = std::max(owner[(size_t)y * W + x], cell);
+        }
+    }
+    if (hinv_out) std::memcpy(hinv_out, hinv.data(), sizeof(double) * hinv.size());
+    for (int y = 0; y < Hh; ++y)
+        for (int x = 0; x < W; ++x) {
+            int X = 0, Y = 0;
+            const int o = owner[(size_t)y * W + x];
+            if (o >= 0) cell_coord(&hinv[(size_t)o * 9], x, y, X, Y);
+            sample_and_store(*pl, x, y, X, Y);
+        }
+}
+
+extern "C" void hs_fill_poly4(const int32_t* pts, int h, int w, uint8_t* out) {
+    const int px[4] = {pts[0], pts[2], pts[4], pts[6]}, py[4] = {pts[1], pts[3], pts[5], pts[7]};
+    const int nwords = (w + 31) / 32;
+    std::vector<uint32_t> words(nwords);
+    for (int y = 0; y < h; ++y) {
+        std::fill(words.begin(), words.end(), 0u);
+        poly_row_mask<4>(px, py, y, 0, words.data(), nwords);
+        for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = (words[x >> 5] >> (x & 31)) & 1u;
+    }
+}
+
+extern "C" void hs_homography(const double* src_quad, const double* dst_quad, double* H) { homography_4pt(src_quad, dst_quad, H); }
+extern "C" int hs_sizeof_grid_page() { return (int)sizeof(vkb_grid_page); }
+extern "C" int hs_sizeof_warp_page() { return (int)sizeof(vkb_warp_page); }
+extern "C" int hs_sizeof_planes() { return (int)sizeof(vkb_planes); }
+extern "C" int hs_sizeof_grid_meta() { return (int)sizeof(vkb_grid_meta); }

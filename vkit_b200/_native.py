@@ -1,0 +1,138 @@
+"""ctypes binding of libvkit_b200.so (the C ABI declared in include/vkit_b200.h).
+
+There is no CPU fallback: if the shared library is missing or CUDA is unavailable every op
+raises.  Struct layouts are mirrored both as `ctypes.Structure` (single records) and as NumPy
+structured dtypes (batched parameter blocks that are uploaded in one copy).
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_double, c_float, c_int32, c_uint8, c_uint16, c_uint32, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libvkit_b200.so')
+
+CELL_MASK_WORDS = 32
+TILE = 32
+TILE_CAP = 64
+
+WARP_AFFINE = 0
+WARP_PERSPECTIVE = 1
+PROJ_CAMERA = 0
+PROJ_MLS = 1
+PROJ_GIVEN = 2
+CAM_PLANE = 0
+CAM_CUBIC = 1
+CAM_LINE_FOLD = 2
+CAM_LINE_CURVE = 3
+
+
+class Planes(ctypes.Structure):
+    _fields_ = [
+        ('src_image', c_void_p), ('dst_image', c_void_p),
+        ('src_mask', c_void_p), ('dst_mask', c_void_p),
+        ('src_score', c_void_p), ('dst_score', c_void_p),
+        ('image_channels', c_int32),
+        ('src_h', c_int32), ('src_w', c_int32),
+        ('dst_h', c_int32), ('dst_w', c_int32),
+        ('_pad', c_int32),
+    ]
+
+
+class WarpPage(ctypes.Structure):
+    _fields_ = [('planes', Planes), ('inv', c_double * 9), ('kind', c_int32), ('_pad', c_int32)]
+
+
+class GridPage(ctypes.Structure):
+    _fields_ = [
+        ('src_h', c_int32), ('src_w', c_int32), ('grid_size', c_int32),
+        ('rows', c_int32), ('cols', c_int32),
+        ('projector', c_int32), ('strategy', c_int32), ('resize_as_src', c_int32),
+        ('R', c_double * 9), ('t', c_double * 3), ('focal', c_double),
+        ('poly', c_double * 4), ('curve_scale', c_double),
+        ('rot2', c_float * 4), ('proj_min', c_float), ('proj_range', c_float),
+        ('line_c', c_double), ('dist_max', c_double), ('line_alpha', c_double),
+        ('line_ab', c_float * 2), ('perturb', c_float * 3),
+        ('n_handles', c_int32),
+        ('handles_src', c_void_p), ('handles_dst', c_void_p),
+    ]
+
+
+class GridMeta(ctypes.Structure):
+    _fields_ = [
+        ('dst_h', c_int32), ('dst_w', c_int32), ('shift_y', c_int32), ('shift_x', c_int32),
+        ('resize_ratio_y', c_double), ('resize_ratio_x', c_double),
+        ('status', c_int32), ('n_flagged_cells', c_int32),
+    ]
+
+
+def _np_dtype(struct_cls):
+    """NumPy structured dtype with the exact layout (offsets, padding) of a ctypes struct."""
+    names, formats, offsets = [], [], []
+    for name, ctype in struct_cls._fields_:
+        field = getattr(struct_cls, name)
+        names.append(name)
+        offsets.append(field.offset)
+        if isinstance(ctype, type) and issubclass(ctype, ctypes.Structure):
+            formats.append(_np_dtype(ctype))
+        elif isinstance(ctype, type) and issubclass(ctype, ctypes.Array):
+            formats.append((np.dtype(ctype._type_), (ctype._length_,)))
+        elif ctype is c_void_p:
+            formats.append(np.uint64)
+        else:
+            formats.append(np.dtype(ctype))
+    return np.dtype({'names': names, 'formats': formats, 'offsets': offsets,
+                     'itemsize': ctypes.sizeof(struct_cls)})
+
+
+PLANES_DTYPE = _np_dtype(Planes)
+WARP_PAGE_DTYPE = _np_dtype(WarpPage)
+GRID_PAGE_DTYPE = _np_dtype(GridPage)
+GRID_META_DTYPE = _np_dtype(GridMeta)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _declare(lib):
+    lib.vkb_version.restype = c_int32
+    lib.vkb_last_error.restype = ctypes.c_char_p
+    i32 = c_int32
+    vp = c_void_p
+    lib.vkb_warp_fused.argtypes = [vp, i32, i32, i32, vp]
+    lib.vkb_affine_points.argtypes = [POINTER(c_double), i32, vp, vp, i32, i32, vp]
+    lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, vp]
+    lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32,
+                                   i32, vp]
+    lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
+    for name in ('vkb_warp_fused', 'vkb_affine_points', 'vkb_grid_project', 'vkb_grid_finalize',
+                 'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon'):
+        getattr(lib, name).restype = c_int32
+
+
+def lib():
+    """The loaded shared library; raises NativeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f'{LIB_PATH} not found: build it with `python -m vkit_b200.build` '
+                '(there is no CPU fallback for the distortion path).')
+        loaded = ctypes.CDLL(LIB_PATH)
+        _declare(loaded)
+        _lib = loaded
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().vkb_last_error().decode('utf-8', 'replace')
+        raise NativeError(f'{what} failed (rc={rc}): {msg}')

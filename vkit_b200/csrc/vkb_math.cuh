@@ -1,0 +1,332 @@
+// vkb_math.cuh -- per-element numerics of the distortion / blend path.
+//
+// Every function here is `__host__ __device__`: the CUDA kernels in this directory call them
+// per pixel / per lattice point / per cell-row, and `tests/hostsim/` compiles the very same
+// header with g++ so the arithmetic can be checked against the oracle on a machine without a
+// GPU.  The host build is a test harness only; nothing in the product path runs on the CPU.
+//
+// The arithmetic restates what the reference (vkit-x/vkit @ 98ada2d) obtains from OpenCV
+// 4.13: 1/32-pixel coordinate quantisation, uint8 bilinear with integer
+// weights summing to 2^15, float32 bilinear without FMA contraction, the fixed-point affine
+// coordinate pipeline of cv::warpAffine, cv::fillPoly coverage (8-connected Bresenham outline
+// plus 16.16 scan fill) and closed-form 4-point homographies.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define VKB_HD __host__ __device__ __forceinline__
+#else
+#define VKB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define VKB_FMUL(a, b) __fmul_rn((a), (b))
+#define VKB_FADD(a, b) __fadd_rn((a), (b))
+#define VKB_FSUB(a, b) __fsub_rn((a), (b))
+#define VKB_DMUL(a, b) __dmul_rn((a), (b))
+#define VKB_DADD(a, b) __dadd_rn((a), (b))
+#else
+#define VKB_FMUL(a, b) ((a) * (b))
+#define VKB_FADD(a, b) ((a) + (b))
+#define VKB_FSUB(a, b) ((a) - (b))
+#define VKB_DMUL(a, b) ((a) * (b))
+#define VKB_DADD(a, b) ((a) + (b))
+#endif
+
+namespace vkb {
+
+constexpr int kInterBits = 5;
+constexpr int kInterTab = 32;
+
+// ---------------------------------------------------------------------------------------
+// Rounding helpers.
+// ---------------------------------------------------------------------------------------
+// cvRound / saturate_cast<int>(double): round half to even, out-of-range and NaN -> INT_MIN
+// (what cvtsd2si returns), which lands outside every image and therefore samples the border.
+VKB_HD int cv_round_d(double v) {
+    if (!(v == v)) return INT32_MIN;
+    double r = rint(v);
+    if (r >= 2147483648.0 || r < -2147483648.0) return INT32_MIN;
+    return (int)r;
+}
+
+// float map value -> 1/32 px fixed point exactly like cv::remap (value * 32 is exact in float).
+VKB_HD int map_to_fixed(float m) {
+    return cv_round_d((double)m * 32.0);
+}
+
+VKB_HD int clamp_short(int v) {
+    return v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+}
+
+// ---------------------------------------------------------------------------------------
+// Bilinear taps, BORDER_CONSTANT(0).  X, Y are 1/32 px fixed point source coordinates.
+// ---------------------------------------------------------------------------------------
+template <int C>
+VKB_HD void bilinear_u8(const uint8_t* __restrict__ src, int h, int w, long long pitch, int X,
+                        int Y, uint8_t* out) {
+    const int x0 = clamp_short(X >> kInterBits);
+    const int y0 = clamp_short(Y >> kInterBits);
+    const int fx = X & (kInterTab - 1);
+    const int fy = Y & (kInterTab - 1);
+    const bool in_x0 = (unsigned)x0 < (unsigned)w;
+    const bool in_x1 = (unsigned)(x0 + 1) < (unsigned)w;
+    const bool in_y0 = (unsigned)y0 < (unsigned)h;
+    const bool in_y1 = (unsigned)(y0 + 1) < (unsigned)h;
+    const uint8_t* r0 = src + (long long)y0 * pitch + (long long)x0 * C;
+    const uint8_t* r1 = r0 + pitch;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int p00 = (in_y0 && in_x0) ? r0[c] : 0;
+        const int p01 = (in_y0 && in_x1) ? r0[C + c] : 0;
+        const int p10 = (in_y1 && in_x0) ? r1[c] : 0;
+        const int p11 = (in_y1 && in_x1) ? r1[C + c] : 0;
+        // Weights (32-fy)(32-fx)*32 ... share the factor 32, so
+        // (sum p*w + 2^14) >> 15 == (t + 512) >> 10 with t below (max 255 * 1024).
+        const int a = (kInterTab - fx) * p00 + fx * p01;
+        const int b = (kInterTab - fx) * p10 + fx * p11;
+        const int t = (kInterTab - fy) * a + fy * b;
+        out[c] = (uint8_t)((t + 512) >> 10);
+    }
+}
+
+VKB_HD float bilinear_f32(const float* __restrict__ src, int h, int w, long long pitch_elems,
+                          int X, int Y) {
+    const int x0 = clamp_short(X >> kInterBits);
+    const int y0 = clamp_short(Y >> kInterBits);
+    const int fx = X & (kInterTab - 1);
+    const int fy = Y & (kInterTab - 1);
+    const bool in_x0 = (unsigned)x0 < (unsigned)w;
+    const bool in_x1 = (unsigned)(x0 + 1) < (unsigned)w;
+    const bool in_y0 = (unsigned)y0 < (unsigned)h;
+    const bool in_y1 = (unsigned)(y0 + 1) < (unsigned)h;
+    const float* r0 = src + (long long)y0 * pitch_elems + x0;
+    const float* r1 = r0 + pitch_elems;
+    const float p00 = (in_y0 && in_x0) ? r0[0] : 0.f;
+    const float p01 = (in_y0 && in_x1) ? r0[1] : 0.f;
+    const float p10 = (in_y1 && in_x0) ? r1[0] : 0.f;
+    const float p11 = (in_y1 && in_x1) ? r1[1] : 0.f;
+    const float ax = (float)fx * 0.03125f;  // exact
+    const float ay = (float)fy * 0.03125f;
+    const float bx = 1.0f - ax;  // exact
+    const float by = 1.0f - ay;
+    const float w00 = VKB_FMUL(by, bx);
+    const float w01 = VKB_FMUL(by, ax);
+    const float w10 = VKB_FMUL(ay, bx);
+    const float w11 = VKB_FMUL(ay, ax);
+    float acc = VKB_FMUL(p00, w00);
+    acc = VKB_FADD(acc, VKB_FMUL(p01, w01));
+    acc = VKB_FADD(acc, VKB_FMUL(p10, w10));
+    acc = VKB_FADD(acc, VKB_FMUL(p11, w11));
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Coordinate pipelines.
+// ---------------------------------------------------------------------------------------
+// cv::warpAffine: Mi = inverse map (2x3, double, row major).  AB_BITS = 10 fixed point.
+VKB_HD void affine_coord(const double* __restrict__ Mi, int x, int y, int& X, int& Y) {
+    const int adelta = cv_round_d(VKB_DMUL(VKB_DMUL(Mi[0], (double)x), 1024.0));
+    const int bdelta = cv_round_d(VKB_DMUL(VKB_DMUL(Mi[3], (double)x), 1024.0));
+    const int X0 = cv_round_d(VKB_DMUL(VKB_DADD(VKB_DMUL(Mi[1], (double)y), Mi[2]), 1024.0)) + 16;
+    const int Y0 = cv_round_d(VKB_DMUL(VKB_DADD(VKB_DMUL(Mi[4], (double)y), Mi[5]), 1024.0)) + 16;
+    X = (X0 + adelta) >> 5;
+    Y = (Y0 + bdelta) >> 5;
+}
+
+// cv::warpPerspective: Mi = inverse map (3x3, double).
+VKB_HD void perspective_coord(const double* __restrict__ Mi, int x, int y, int& X, int& Y) {
+    const double xd = (double)x, yd = (double)y;
+    double W = VKB_DADD(VKB_DADD(VKB_DMUL(Mi[6], xd), VKB_DMUL(Mi[7], yd)), Mi[8]);
+    W = (W != 0.0) ? 32.0 / W : 0.0;
+    double fX = VKB_DMUL(VKB_DADD(VKB_DADD(VKB_DMUL(Mi[0], xd), VKB_DMUL(Mi[1], yd)), Mi[2]), W);
+    double fY = VKB_DMUL(VKB_DADD(VKB_DADD(VKB_DMUL(Mi[3], xd), VKB_DMUL(Mi[4], yd)), Mi[5]), W);
+    fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+    fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+    X = cv_round_d(fX);
+    Y = cv_round_d(fY);
+}
+
+// Grid remap: source coordinate of dst pixel (x, y) under a cell's inverse homography H
+// (double), stored as float32 like the reference's map_x/map_y, then quantised like cv::remap.
+// (vkit grid_rendering/type.py:231-256 followed by grid_blender.py:60.)
+VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& Y) {
+    const double xd = (double)x, yd = (double)y;
+    const double den = fma(H[6], xd, fma(H[7], yd, H[8]));
+    const double nx = fma(H[0], xd, fma(H[1], yd, H[2]));
+    const double ny = fma(H[3], xd, fma(H[4], yd, H[5]));
+    if (den == 0.0) {  // the reference skips such pixels; they keep map value 0
+        X = 0;
+        Y = 0;
+        return;
+    }
+    const float mx = (float)(nx / den);
+    const float my = (float)(ny / den);
+    X = map_to_fixed(mx);
+    Y = map_to_fixed(my);
+}
+
+// ---------------------------------------------------------------------------------------
+// Homography through 4 point pairs, closed form (Heckbert), double precision.
+// q = [x0,y0,x1,y1,x2,y2,x3,y3].  Result maps src quad -> dst quad, H[8] = 1.
+// Stands in for cv.getPerspectiveTransform(src, dst, DECOMP_SVD) (type.py:172,189).
+// ---------------------------------------------------------------------------------------
+VKB_HD void unit_square_to_quad(const double* q, double* A) {
+    const double x0 = q[0], y0 = q[1], x1 = q[2], y1 = q[3], x2 = q[4], y2 = q[5], x3 = q[6],
+                 y3 = q[7];
+    const double dx1 = x1 - x2, dx2 = x3 - x2, sx = x0 - x1 + x2 - x3;
+    const double dy1 = y1 - y2, dy2 = y3 - y2, sy = y0 - y1 + y2 - y3;
+    const double den = dx1 * dy2 - dx2 * dy1;
+    const double g = (sx * dy2 - dx2 * sy) / den;
+    const double h = (dx1 * sy - sx * dy1) / den;
+    A[0] = x1 - x0 + g * x1;
+    A[1] = x3 - x0 + h * x3;
+    A[2] = x0;
+    A[3] = y1 - y0 + g * y1;
+    A[4] = y3 - y0 + h * y3;
+    A[5] = y0;
+    A[6] = g;
+    A[7] = h;
+    A[8] = 1.0;
+}
+
+VKB_HD void homography_4pt(const double* src_quad, const double* dst_quad, double* H) {
+    double A[9], B[9], J[9];
+    unit_square_to_quad(src_quad, A);
+    unit_square_to_quad(dst_quad, B);
+    // adj(A): maps src quad -> unit square up to scale.
+    J[0] = A[4] * A[8] - A[5] * A[7];
+    J[1] = A[2] * A[7] - A[1] * A[8];
+    J[2] = A[1] * A[5] - A[2] * A[4];
+    J[3] = A[5] * A[6] - A[3] * A[8];
+    J[4] = A[0] * A[8] - A[2] * A[6];
+    J[5] = A[2] * A[3] - A[0] * A[5];
+    J[6] = A[3] * A[7] - A[4] * A[6];
+    J[7] = A[1] * A[6] - A[0] * A[7];
+    J[8] = A[0] * A[4] - A[1] * A[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            H[r * 3 + c] = B[r * 3 + 0] * J[0 * 3 + c] + B[r * 3 + 1] * J[1 * 3 + c]
+                           + B[r * 3 + 2] * J[2 * 3 + c];
+        }
+    }
+    const double inv = 1.0 / H[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) H[i] *= inv;
+    H[8] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// cv::fillPoly coverage of one polygon restricted to one row, as a bit mask.
+//
+// Coverage = outline (cv::LineIterator, 8-connected, left-to-right) UNION scan fill
+// (16.16 fixed-point edges active on [ymin, ymax), spans [ceil(xl), floor(xr)]).
+// The Bresenham walk is evaluated in closed form per row: with major extent D, minor extent d,
+// the minor coordinate after j major steps is  floor((2*d*j + D - 1) / (2*D)).
+// Bit i of the mask = pixel (bx0 + i, y).  `words` must hold nwords zero-initialised words.
+// ---------------------------------------------------------------------------------------
+VKB_HD void set_bits(uint32_t* words, int nwords, int lo, int hi) {
+    // set bits [lo, hi] (inclusive), clipped to [0, 32*nwords)
+    if (lo < 0) lo = 0;
+    const int top = nwords * 32 - 1;
+    if (hi > top) hi = top;
+    if (lo > hi) return;
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        const int a = (w == w0) ? (lo & 31) : 0;
+        const int b = (w == w1) ? (hi & 31) : 31;
+        const uint32_t m = (b == 31 ? 0xFFFFFFFFu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+        words[w] |= m;
+    }
+}
+
+VKB_HD int ceil_div_pos(int num, int den) {  // den > 0, any num; ceil(num/den)
+    return (num >= 0) ? (num + den - 1) / den : -((-num) / den);
+}
+
+// pixels of the Bresenham line (ax,ay)-(bx,by) that lie on row y: [xlo, xhi] or empty.
+VKB_HD bool line_row_run(int ax, int ay, int bx, int by, int y, int& xlo, int& xhi) {
+    if (ax > bx) {  // left to right
+        int t = ax; ax = bx; bx = t;
+        t = ay; ay = by; by = t;
+    }
+    const int dx = bx - ax;
+    const int dys = by - ay;
+    const int sy = dys >= 0 ? 1 : -1;
+    const int dy = dys >= 0 ? dys : -dys;
+    const int k = (y - ay) * sy;  // rows travelled from the start point
+    if (k < 0 || k > dy) return false;
+    if (dy > dx) {  // steep: one pixel per row
+        const int kx = (2 * dx * k + dy - 1) / (2 * dy);
+        xlo = xhi = ax + kx;
+        return true;
+    }
+    if (dy == 0) {  // horizontal (or a single point)
+        xlo = ax;
+        xhi = bx;
+        return true;
+    }
+    int jlo = (k == 0) ? 0 : ceil_div_pos(2 * dx * k - dx + 1, 2 * dy);
+    int jhi = ceil_div_pos(2 * dx * (k + 1) - dx + 1, 2 * dy) - 1;
+    if (jlo < 0) jlo = 0;
+    if (jhi > dx) jhi = dx;
+    if (jlo > jhi) return false;
+    xlo = ax + jlo;
+    xhi = ax + jhi;
+    return true;
+}
+
+template <int N>
+VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t* words,
+                          int nwords) {
+    long long cross[N];
+    int ncross = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int j = (i + N - 1) % N;
+        const int x0 = px[j], y0 = py[j], x1 = px[i], y1 = py[i];
+        int lo, hi;
+        if (line_row_run(x0, y0, x1, y1, y, lo, hi)) set_bits(words, nwords, lo - bx0, hi - bx0);
+        if (y0 == y1) continue;
+        const long long dxf = ((long long)(x1 - x0) * 65536) / (long long)(y1 - y0);  // trunc
+        int ya, yb;
+        long long xa;
+        if (y0 < y1) { ya = y0; yb = y1; xa = (long long)x0 * 65536; }
+        else { ya = y1; yb = y0; xa = (long long)x1 * 65536; }
+        if (ya <= y && y < yb) cross[ncross++] = xa + dxf * (long long)(y - ya);
+    }
+    // insertion sort (N is 4 for lattice cells)
+    for (int i = 1; i < ncross; ++i) {
+        const long long v = cross[i];
+        int j = i - 1;
+        while (j >= 0 && cross[j] > v) { cross[j + 1] = cross[j]; --j; }
+        cross[j + 1] = v;
+    }
+    for (int k = 0; k + 1 < ncross; k += 2) {
+        const long long xl = (cross[k] + 65535) >> 16;
+        const long long xr = cross[k + 1] >> 16;
+        if (xl <= xr) set_bits(words, nwords, (int)xl - bx0, (int)xr - bx0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera lattice projection (cv.projectPoints with zero distortion, camera.py:188-196).
+// R row major, t, f: all double.  Returns image coordinates in double; caller casts to the
+// strategy's dtype (float32 for plane/line strategies, float64 for cubic curve).
+// ---------------------------------------------------------------------------------------
+VKB_HD void project_point(const double* R, const double* t, double f, double X, double Y,
+                          double Z, double& u, double& v) {
+    double x = VKB_DADD(VKB_DADD(VKB_DADD(VKB_DMUL(R[0], X), VKB_DMUL(R[1], Y)), VKB_DMUL(R[2], Z)), t[0]);
+    double y = VKB_DADD(VKB_DADD(VKB_DADD(VKB_DMUL(R[3], X), VKB_DMUL(R[4], Y)), VKB_DMUL(R[5], Z)), t[1]);
+    double z = VKB_DADD(VKB_DADD(VKB_DADD(VKB_DMUL(R[6], X), VKB_DMUL(R[7], Y)), VKB_DMUL(R[8], Z)), t[2]);
+    z = (z != 0.0) ? 1.0 / z : 1.0;
+    x = VKB_DMUL(x, z);
+    y = VKB_DMUL(y, z);
+    u = VKB_DADD(VKB_DMUL(x, f), 0.0);
+    v = VKB_DADD(VKB_DMUL(y, f), 0.0);
+}
+
+}  // namespace vkb
