@@ -180,6 +180,113 @@ int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double*
 int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32_t* poly_xy, int32_t n_pts,
                      uint8_t value, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Blend: the device form of fill_np_array (vkit/element/opt.py:118-209) as reached through
+ * Box / Mask / ScoreMap / Polygon .fill_image / .fill_mask / .fill_score_map
+ * (box.py:311-416, score_map.py:678-687) -- glyph -> text line -> page compositing
+ * (engine/font/freetype.py:314-380, pipeline/text_detection/page_assembler.py:152-236,
+ * page_distortion.py:146-161).
+ *   active pixel : mask != 0, else alpha_arr > 0 when alpha is an array, else every pixel
+ *   alpha array  : out = trunc((1 - a) * f32(dst) + a * f32(value))   (float32, no FMA)
+ *   alpha scalar : 1 -> assign (or keep max / keep min), (0,1) -> same blend with a = f32(alpha)
+ * ------------------------------------------------------------------------------------- */
+typedef struct vkb_blend_item {
+    void* dst;             /* full destination plane, HWC uint8 or HW float32 */
+    const void* value_arr; /* NULL: value_const; else same dtype as dst, origin at region */
+    const uint8_t* mask;   /* NULL or region shaped */
+    const float* alpha_arr; /* NULL or region shaped */
+    int32_t dst_f32;
+    int32_t channels;
+    int32_t dst_w; /* pixels per destination row */
+    int32_t box_y, box_x, box_h, box_w;
+    int32_t value_pitch; /* pixels per row of value_arr */
+    int32_t mask_pitch;
+    int32_t alpha_pitch;
+    int32_t keep_mode; /* 0 none, 1 keep max, 2 keep min */
+    float alpha;
+    float value_const[4];
+} vkb_blend_item;
+
+int vkb_blend_fill(const vkb_blend_item* item_host, void* stream);
+/* Ordered draw list: items (device array) are applied in order; overlapping items see each
+ * other's result exactly as successive fill_image calls would. All items share one dst. */
+int vkb_blend_draw_list(const vkb_blend_item* items, int32_t n_items, int32_t dst_h,
+                        int32_t dst_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Colour-mode conversion: Image.to_target_mode_image (vkit/element/image.py:771-814).
+ * uint8 in/out; HSL is stored H,S,L (the reference slices cv2's HLS with [0,2,1]).
+ * ------------------------------------------------------------------------------------- */
+#define VKB_CVT_RGB2HSV 0
+#define VKB_CVT_HSV2RGB 1
+#define VKB_CVT_RGB2HSL 2
+#define VKB_CVT_HSL2RGB 3
+#define VKB_CVT_RGB2GRAY 4
+#define VKB_CVT_GRAY2RGB 5
+#define VKB_CVT_RGBA2RGB 6
+#define VKB_CVT_RGB2RGBA 7
+#define VKB_CVT_GRAY2RGBA 8
+#define VKB_CVT_RGBA2GRAY 9
+int vkb_cvt_color(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t code, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pixel photometric ops, fused: an op list interpreted per pixel in one pass
+ * (vkit/mechanism/distortion/photometric/color.py:32-439, opt.py:24-85).
+ * ------------------------------------------------------------------------------------- */
+#define VKB_OP_MEAN_SHIFT 0       /* i0 delta, i1 threshold (-1 none), i2 channel bits, i3 cycle */
+#define VKB_OP_HUE_SHIFT_RGB 1    /* i0 delta: RGB -> HSV_FULL, H += delta (mod 256), -> RGB */
+#define VKB_OP_LIGHT_SHIFT_RGB 2  /* i0 delta, i1 0: via HSL (L), 1: via HSV (V); clipped */
+#define VKB_OP_STD_SHIFT 3        /* f0 scale, f1..f3 mean*(scale-1) per channel, i2 channel bits */
+#define VKB_OP_COMPLEMENT 4       /* i1 threshold (-1 none), i3 lte flag, i2 channel bits */
+#define VKB_OP_POSTERIZE 5        /* i0 bit mask, i2 channel bits */
+#define VKB_OP_COLOR_BALANCE 6    /* f0 ratio */
+#define VKB_OP_PERMUTE 7          /* i0 packed permutation (4 bits per channel) */
+#define VKB_OP_BOUNDARY_EQ 8      /* f0..f2 min per channel, g0..g2 scale per channel, i2 bits */
+typedef struct vkb_color_op {
+    int32_t kind;
+    int32_t i0, i1, i2, i3;
+    float f0, f1, f2, f3;
+    float g0, g1, g2;
+} vkb_color_op;
+#define VKB_MAX_COLOR_OPS 8
+int vkb_color_ops(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                  const vkb_color_op* ops_host, int32_t n_ops, void* stream);
+
+/* Per-channel sum / min / max of a uint8 image (std_shift mean, boundary_equalization).
+ * out: 3 x uint64 sums, then 3 x uint32 mins, 3 x uint32 maxs (device, 48 bytes). */
+int vkb_channel_stats(const uint8_t* src, int64_t n_pixels, int32_t channels, void* out,
+                      void* stream);
+
+/* cv.GaussianBlur(uint8, (k,k), sigma) with BORDER_REFLECT_101: separable 8.8 fixed-point
+ * stencil staged through shared memory (photometric/blur.py:49-76). kernel_host: k integer
+ * taps summing to 256 (k odd, k <= 17). */
+int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                         const int32_t* kernel_host, int32_t ksize, void* stream);
+
+/* Noise (photometric/noise.py:25-190).  kind: 0 gaussian (p0 = std), 1 poisson, 2 impulse
+ * (p0 = prob_salt, p1 = prob_pepper), 3 speckle (p0 = std).
+ * Philox variant: counter-based device RNG keyed by (seed, element index); distributional
+ * parity.  Field variant: the host supplies the random field the reference would draw
+ * (gaussian: int16 rounded noise; poisson: int64 samples; impulse: int64 categories 0/1/2 per
+ * PIXEL; speckle: float64 normal) and the result is bit-exact. */
+int vkb_noise_philox(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                     int32_t kind, double p0, double p1, uint64_t seed, void* stream);
+int vkb_noise_field(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                    int32_t kind, const void* field, void* stream);
+
+/* Streaks (photometric/streak.py:44-337).  line: analytic periodic masks; rect: the masks are
+ * rasterised from the host-computed bar lists; both blend `color` with `alpha`, vertical mask
+ * first, horizontal second (crossings get alpha twice, streak.py:96-98). In place on `image`. */
+typedef struct vkb_rect { int32_t up, down, left, right; } vkb_rect;
+int vkb_streak_line(uint8_t* image, int32_t h, int32_t w, int32_t channels, int32_t thickness,
+                    int32_t gap, int32_t dash_thickness, int32_t dash_gap, int32_t enable_vert,
+                    int32_t enable_hori, const float* color_host, float alpha, void* stream);
+int vkb_fill_rects(uint8_t* mask, int32_t h, int32_t w, const vkb_rect* rects, int32_t n_rects,
+                   void* stream);
+int vkb_streak_masks(uint8_t* image, int32_t h, int32_t w, int32_t channels,
+                     const uint8_t* mask_vert, const uint8_t* mask_hori, int32_t dash_thickness,
+                     int32_t dash_gap, const float* color_host, float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

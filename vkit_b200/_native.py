@@ -67,6 +67,36 @@ class GridMeta(ctypes.Structure):
     ]
 
 
+class BlendItem(ctypes.Structure):
+    _fields_ = [
+        ('dst', c_void_p), ('value_arr', c_void_p), ('mask', c_void_p), ('alpha_arr', c_void_p),
+        ('dst_f32', c_int32), ('channels', c_int32), ('dst_w', c_int32),
+        ('box_y', c_int32), ('box_x', c_int32), ('box_h', c_int32), ('box_w', c_int32),
+        ('value_pitch', c_int32), ('mask_pitch', c_int32), ('alpha_pitch', c_int32),
+        ('keep_mode', c_int32), ('alpha', c_float), ('value_const', c_float * 4),
+    ]
+
+
+class ColorOp(ctypes.Structure):
+    _fields_ = [
+        ('kind', c_int32), ('i0', c_int32), ('i1', c_int32), ('i2', c_int32), ('i3', c_int32),
+        ('f0', c_float), ('f1', c_float), ('f2', c_float), ('f3', c_float),
+        ('g0', c_float), ('g1', c_float), ('g2', c_float),
+    ]
+
+
+class Rect(ctypes.Structure):
+    _fields_ = [('up', c_int32), ('down', c_int32), ('left', c_int32), ('right', c_int32)]
+
+
+(CVT_RGB2HSV, CVT_HSV2RGB, CVT_RGB2HSL, CVT_HSL2RGB, CVT_RGB2GRAY, CVT_GRAY2RGB, CVT_RGBA2RGB,
+ CVT_RGB2RGBA, CVT_GRAY2RGBA, CVT_RGBA2GRAY) = range(10)
+(OP_MEAN_SHIFT, OP_HUE_SHIFT_RGB, OP_LIGHT_SHIFT_RGB, OP_STD_SHIFT, OP_COMPLEMENT, OP_POSTERIZE,
+ OP_COLOR_BALANCE, OP_PERMUTE, OP_BOUNDARY_EQ) = range(9)
+MAX_COLOR_OPS = 8
+NOISE_GAUSSIAN, NOISE_POISSON, NOISE_IMPULSE, NOISE_SPECKLE = range(4)
+
+
 def _np_dtype(struct_cls):
     """NumPy structured dtype with the exact layout (offsets, padding) of a ctypes struct."""
     names, formats, offsets = [], [], []
@@ -87,6 +117,8 @@ def _np_dtype(struct_cls):
 
 
 PLANES_DTYPE = _np_dtype(Planes)
+BLEND_ITEM_DTYPE = _np_dtype(BlendItem)
+RECT_DTYPE = _np_dtype(Rect)
 WARP_PAGE_DTYPE = _np_dtype(WarpPage)
 GRID_PAGE_DTYPE = _np_dtype(GridPage)
 GRID_META_DTYPE = _np_dtype(GridMeta)
@@ -113,9 +145,31 @@ def _declare(lib):
                                    i32, vp]
     lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
-    for name in ('vkb_warp_fused', 'vkb_affine_points', 'vkb_grid_project', 'vkb_grid_finalize',
-                 'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon'):
+    i64 = ctypes.c_int64
+    lib.vkb_blend_fill.argtypes = [POINTER(BlendItem), vp]
+    lib.vkb_blend_draw_list.argtypes = [vp, i32, i32, i32, vp]
+    lib.vkb_cvt_color.argtypes = [vp, vp, i64, i32, vp]
+    lib.vkb_color_ops.argtypes = [vp, vp, i64, i32, POINTER(ColorOp), i32, vp]
+    lib.vkb_channel_stats.argtypes = [vp, i64, i32, vp, vp]
+    lib.vkb_gaussian_blur_u8.argtypes = [vp, vp, i32, i32, i32, POINTER(c_int32), i32, vp]
+    lib.vkb_noise_philox.argtypes = [vp, vp, i64, i32, i32, c_double, c_double, ctypes.c_uint64, vp]
+    lib.vkb_noise_field.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    lib.vkb_streak_line.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                    POINTER(c_float), c_float, vp]
+    lib.vkb_fill_rects.argtypes = [vp, i32, i32, vp, i32, vp]
+    lib.vkb_streak_masks.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, POINTER(c_float),
+                                     c_float, vp]
+    for name in EXPORTS:
         getattr(lib, name).restype = c_int32
+
+
+EXPORTS = (
+    'vkb_warp_fused', 'vkb_affine_points', 'vkb_grid_project', 'vkb_grid_finalize',
+    'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon',
+    'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
+    'vkb_channel_stats', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
+    'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks',
+)
 
 
 def lib():

@@ -1,0 +1,627 @@
+// photometric.cu -- sm_100a kernels + C ABI for blends, colour conversion, the fused per-pixel
+// photometric ops, the 8.8 fixed-point Gaussian, noise and streaks.
+//
+//   blend_*            element/opt.py:118-209 through box.py:311-416
+//   cvt_color_kernel   element/image.py:771-814
+//   color_ops_kernel   photometric/color.py:32-439
+//   gaussian_blur_*    photometric/blur.py:49-76   (cv.GaussianBlur uint8)
+//   noise_*            photometric/noise.py:25-190
+//   streak_*           photometric/streak.py:44-279
+//
+// All of it is byte-stream work bound by HBM bandwidth: one read and one write per pixel,
+// no tensor cores.
+#include <curand_kernel.h>
+#include "common.cuh"
+#include "vkb_color.cuh"
+
+namespace vkb {
+
+__constant__ HsvTables c_hsv;
+static bool g_hsv_ready = false;
+
+static int ensure_tables(cudaStream_t st) {
+    if (!g_hsv_ready) {
+        static HsvTables host;
+        fill_hsv_tables(host);
+        VKB_CUDA(cudaMemcpyToSymbolAsync(c_hsv, &host, sizeof(host), 0, cudaMemcpyHostToDevice, st));
+        VKB_CUDA(cudaStreamSynchronize(st));
+        g_hsv_ready = true;
+    }
+    return VKB_OK;
+}
+
+// ============================================================================================
+// Blend
+// ============================================================================================
+__device__ __forceinline__ void blend_pixel(const vkb_blend_item& it, int ry, int rx) {
+    bool active = true;
+    float a = it.alpha;
+    if (it.alpha_arr) {
+        a = it.alpha_arr[(long long)ry * it.alpha_pitch + rx];
+        active = a > 0.f;
+    }
+    if (it.mask) active = it.mask[(long long)ry * it.mask_pitch + rx] != 0;
+    if (!active) return;
+    const long long di = ((long long)(it.box_y + ry) * it.dst_w + (it.box_x + rx)) * it.channels;
+    const long long vi = ((long long)ry * it.value_pitch + rx) * it.channels;
+    const bool do_blend = it.alpha_arr != nullptr || a < 1.0f;
+    for (int c = 0; c < it.channels; ++c) {
+        if (it.dst_f32) {
+            float* d = reinterpret_cast<float*>(it.dst) + di + c;
+            const float v = it.value_arr ? reinterpret_cast<const float*>(it.value_arr)[vi + c]
+                                         : it.value_const[c];
+            if (do_blend) *d = blend_f32(*d, v, a);
+            else if (it.keep_mode == 1) { if (*d < v) *d = v; }
+            else if (it.keep_mode == 2) { if (*d > v) *d = v; }
+            else *d = v;
+        } else {
+            uint8_t* d = reinterpret_cast<uint8_t*>(it.dst) + di + c;
+            const int v = it.value_arr ? (int)reinterpret_cast<const uint8_t*>(it.value_arr)[vi + c]
+                                       : (int)it.value_const[c];
+            if (do_blend) *d = (uint8_t)(int)blend_f32((float)*d, (float)v, a);  // truncation
+            else if (it.keep_mode == 1) { if (*d < v) *d = (uint8_t)v; }
+            else if (it.keep_mode == 2) { if (*d > v) *d = (uint8_t)v; }
+            else *d = (uint8_t)v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) blend_fill_kernel(const vkb_blend_item it) {
+    const int rx = blockIdx.x * 32 + threadIdx.x;
+    const int ry0 = blockIdx.y * 32 + threadIdx.y;
+    if (rx >= it.box_w) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ry = ry0 + 8 * k;
+        if (ry < it.box_h) blend_pixel(it, ry, rx);
+    }
+}
+
+// Ordered draw list: every thread owns one destination pixel and walks the items in order,
+// so overlapping items compose exactly like successive fill calls.
+__global__ void __launch_bounds__(256) blend_draw_list_kernel(const vkb_blend_item* __restrict__ items,
+                                                              int n_items, int dst_h, int dst_w) {
+    extern __shared__ unsigned char smem_raw[];
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y0 = blockIdx.y * 32 + threadIdx.y;
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
+    for (int i = 0; i < n_items; ++i) {
+        const vkb_blend_item& it = items[i];
+        // tile / box rejection is block uniform
+        if (it.box_x > tx0 + 31 || it.box_x + it.box_w <= tx0 || it.box_y > ty0 + 31
+            || it.box_y + it.box_h <= ty0)
+            continue;
+        const int rx = x - it.box_x;
+        if (rx < 0 || rx >= it.box_w || x >= dst_w) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y = y0 + 8 * k;
+            const int ry = y - it.box_y;
+            if (y < dst_h && ry >= 0 && ry < it.box_h) blend_pixel(it, ry, rx);
+        }
+    }
+    (void)smem_raw;
+}
+
+// ============================================================================================
+// Colour conversion
+// ============================================================================================
+__global__ void __launch_bounds__(256) cvt_color_kernel(const uint8_t* __restrict__ src,
+                                                        uint8_t* __restrict__ dst, long long n, int code) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a, b, c;
+    switch (code) {
+        case VKB_CVT_RGB2HSV: {
+            rgb2hsv_full(c_hsv, src[3 * i], src[3 * i + 1], src[3 * i + 2], a, b, c);
+            dst[3 * i] = a; dst[3 * i + 1] = b; dst[3 * i + 2] = c;
+        } break;
+        case VKB_CVT_HSV2RGB: {
+            hsv2rgb_full(src[3 * i], src[3 * i + 1], src[3 * i + 2], a, b, c);
+            dst[3 * i] = a; dst[3 * i + 1] = b; dst[3 * i + 2] = c;
+        } break;
+        case VKB_CVT_RGB2HSL: {
+            int h, l, s;
+            rgb2hls_full(src[3 * i], src[3 * i + 1], src[3 * i + 2], h, l, s);
+            dst[3 * i] = h; dst[3 * i + 1] = s; dst[3 * i + 2] = l;  // stored H, S, L
+        } break;
+        case VKB_CVT_HSL2RGB: {
+            hls2rgb_full(src[3 * i], src[3 * i + 2], src[3 * i + 1], a, b, c);
+            dst[3 * i] = a; dst[3 * i + 1] = b; dst[3 * i + 2] = c;
+        } break;
+        case VKB_CVT_RGB2GRAY:
+            dst[i] = rgb2gray(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+            break;
+        case VKB_CVT_GRAY2RGB:
+            dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = src[i];
+            break;
+        case VKB_CVT_RGBA2RGB:
+            dst[3 * i] = src[4 * i]; dst[3 * i + 1] = src[4 * i + 1]; dst[3 * i + 2] = src[4 * i + 2];
+            break;
+        case VKB_CVT_RGB2RGBA:
+            dst[4 * i] = src[3 * i]; dst[4 * i + 1] = src[3 * i + 1]; dst[4 * i + 2] = src[3 * i + 2];
+            dst[4 * i + 3] = 255;
+            break;
+        case VKB_CVT_GRAY2RGBA:
+            dst[4 * i] = dst[4 * i + 1] = dst[4 * i + 2] = src[i];
+            dst[4 * i + 3] = 255;
+            break;
+        case VKB_CVT_RGBA2GRAY:
+            dst[i] = rgb2gray(src[4 * i], src[4 * i + 1], src[4 * i + 2]);
+            break;
+        default: break;
+    }
+}
+
+// ============================================================================================
+// Fused per-pixel photometric ops.
+// ============================================================================================
+struct ColorOpList {
+    vkb_color_op ops[VKB_MAX_COLOR_OPS];
+    int n;
+};
+
+__device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, int channels) {
+    switch (op.kind) {
+        case VKB_OP_MEAN_SHIFT: {
+            for (int c = 0; c < channels; ++c) {
+                if (!((op.i2 >> c) & 1)) continue;
+                int v = px[c];
+                bool hit = true;
+                if (op.i1 >= 0) hit = op.i0 > 0 ? (v <= op.i1) : (op.i1 <= v);
+                if (hit) v += op.i0;
+                px[c] = op.i3 ? floor_mod_256(v) : clip_u8(v);
+            }
+        } break;
+        case VKB_OP_HUE_SHIFT_RGB: {
+            int h, s, v;
+            rgb2hsv_full(c_hsv, px[0], px[1], px[2], h, s, v);
+            h = floor_mod_256(h + op.i0);
+            hsv2rgb_full(h, s, v, px[0], px[1], px[2]);
+        } break;
+        case VKB_OP_LIGHT_SHIFT_RGB: {
+            if (op.i1 == 0) {
+                int h, l, s;
+                rgb2hls_full(px[0], px[1], px[2], h, l, s);
+                l = clip_u8(l + op.i0);
+                hls2rgb_full(h, l, s, px[0], px[1], px[2]);
+            } else {
+                int h, s, v;
+                rgb2hsv_full(c_hsv, px[0], px[1], px[2], h, s, v);
+                v = clip_u8(v + op.i0);
+                hsv2rgb_full(h, s, v, px[0], px[1], px[2]);
+            }
+        } break;
+        case VKB_OP_STD_SHIFT: {
+            const float sub[3] = {op.f1, op.f2, op.f3};
+            for (int c = 0; c < channels; ++c) {
+                if (!((op.i2 >> c) & 1)) continue;
+                const float v = __fsub_rn(__fmul_rn((float)px[c], op.f0), sub[c]);
+                px[c] = round_u8(v);
+            }
+        } break;
+        case VKB_OP_COMPLEMENT: {
+            for (int c = 0; c < channels; ++c) {
+                if (!((op.i2 >> c) & 1)) continue;
+                bool hit = true;
+                if (op.i1 >= 0) hit = op.i3 ? (px[c] <= op.i1) : (op.i1 <= px[c]);
+                if (hit) px[c] = 255 - px[c];
+            }
+        } break;
+        case VKB_OP_POSTERIZE: {
+            for (int c = 0; c < channels; ++c)
+                if ((op.i2 >> c) & 1) px[c] &= op.i0;
+        } break;
+        case VKB_OP_COLOR_BALANCE: {
+            if (channels >= 3) {
+                const float gray = (float)rgb2gray(px[0], px[1], px[2]);
+                for (int c = 0; c < 3; ++c) {
+                    const float v = __fadd_rn(__fmul_rn(op.f1, gray), __fmul_rn(op.f0, (float)px[c]));
+                    px[c] = clip_u8((int)fminf(fmaxf(v, 0.f), 255.f));  // clip, then truncate
+                }
+            }
+        } break;
+        case VKB_OP_PERMUTE: {
+            int t[4] = {px[0], px[1], px[2], px[3]};
+            for (int c = 0; c < channels; ++c) px[c] = t[(op.i0 >> (4 * c)) & 0xF];
+        } break;
+        case VKB_OP_BOUNDARY_EQ: {
+            const float mn[3] = {op.f0, op.f1, op.f2};
+            const float sc[3] = {op.g0, op.g1, op.g2};
+            for (int c = 0; c < channels; ++c) {
+                if (!((op.i2 >> c) & 1)) continue;
+                px[c] = round_u8(__fmul_rn(__fsub_rn((float)px[c], mn[c]), sc[c]));
+            }
+        } break;
+        default: break;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) color_ops_kernel(const uint8_t* __restrict__ src,
+                                                        uint8_t* __restrict__ dst, long long n,
+                                                        const ColorOpList list) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int px[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < C; ++c) px[c] = src[i * C + c];
+    for (int k = 0; k < list.n; ++k) apply_color_op(list.ops[k], px, C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
+}
+
+// per-channel sum/min/max
+__global__ void __launch_bounds__(256) channel_stats_kernel(const uint8_t* __restrict__ src, long long n,
+                                                            int channels, unsigned long long* sums,
+                                                            unsigned int* mins, unsigned int* maxs) {
+    unsigned long long s[3] = {0, 0, 0};
+    unsigned int mn[3] = {255, 255, 255}, mx[3] = {0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < channels; ++c) {
+            const unsigned int v = src[i * channels + c];
+            s[c] += v;
+            mn[c] = min(mn[c], v);
+            mx[c] = max(mx[c], v);
+        }
+    }
+    for (int c = 0; c < channels; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&sums[c], s[c]);
+            atomicMin(&mins[c], mn[c]);
+            atomicMax(&maxs[c], mx[c]);
+        }
+    }
+}
+
+__global__ void channel_stats_init_kernel(unsigned long long* sums, unsigned int* mins, unsigned int* maxs) {
+    if (threadIdx.x < 3) {
+        sums[threadIdx.x] = 0;
+        mins[threadIdx.x] = 255;
+        maxs[threadIdx.x] = 0;
+    }
+}
+
+// ============================================================================================
+// Gaussian blur, uint8, 8.8 fixed point, BORDER_REFLECT_101.  Block = 32 x 8 threads on a
+// 32 x 32 output tile; the tile plus halo is staged in shared memory, the horizontal pass keeps
+// its saturated 16-bit rows in shared memory, the vertical pass writes the result.
+// ============================================================================================
+constexpr int kGaussMaxR = 8;
+struct GaussKernel {
+    int k[2 * kGaussMaxR + 1];
+    int r;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t* __restrict__ src,
+                                                            uint8_t* __restrict__ dst, int h, int w,
+                                                            const GaussKernel gk) {
+    extern __shared__ unsigned char smem[];
+    const int r = gk.r;
+    const int TW = 32 + 2 * r, TH = 32 + 2 * r;
+    uint8_t* tile = smem;                                                  // TH x TW x C
+    unsigned short* rows = reinterpret_cast<unsigned short*>(smem + ((TH * TW * C + 3) & ~3));  // TH x 32 x C
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int sy = reflect101(y0 + ty - r, h), sx = reflect101(x0 + tx - r, w);
+        const uint8_t* p = src + ((long long)sy * w + sx) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) tile[i * C + c] = p[c];
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * 32; i += 256) {
+        const int ty = i >> 5, tx = i & 31;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k) acc += (int)tile[(ty * TW + tx + k) * C + c] * gk.k[k];
+            rows[i * C + c] = (unsigned short)min(acc, 65535);
+        }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= w) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ly = threadIdx.y + 8 * j;
+        const int y = y0 + ly;
+        if (y >= h) break;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k) acc += (int)rows[((ly + k) * 32 + threadIdx.x) * C + c] * gk.k[k];
+            dst[((long long)y * w + x) * C + c] = (uint8_t)min((acc + (1 << 15)) >> 16, 255);
+        }
+    }
+}
+
+// ============================================================================================
+// Noise
+// ============================================================================================
+__global__ void __launch_bounds__(256) noise_philox_kernel(const uint8_t* __restrict__ src,
+                                                           uint8_t* __restrict__ dst, long long n_pixels,
+                                                           int channels, int kind, double p0, double p1,
+                                                           unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)i, 0, &st);
+    if (kind == 2) {  // impulse: one categorical per pixel, all channels (noise.py:132-142)
+        const double u = curand_uniform_double(&st);
+        const double presv = 1.0 - p0 - p1;
+        for (int c = 0; c < channels; ++c) {
+            const uint8_t v = src[i * channels + c];
+            dst[i * channels + c] = u < presv ? v : (u < presv + p0 ? 255 : 0);
+        }
+        return;
+    }
+    for (int c = 0; c < channels; ++c) {
+        const int v = src[i * channels + c];
+        int out;
+        if (kind == 0) {
+            const double nz = rint((double)curand_normal(&st) * p0);
+            out = clip_u8(v + (int)nz);
+        } else if (kind == 1) {
+            out = clip_u8((int)curand_poisson(&st, (double)v));
+        } else {
+            const double nz = (double)curand_normal(&st) * p0;
+            const double r = (double)v + (double)v * nz;
+            out = (int)fmin(fmax(r, 0.0), 255.0);  // clip then truncate (noise.py:182)
+        }
+        dst[i * channels + c] = (uint8_t)out;
+    }
+}
+
+__global__ void __launch_bounds__(256) noise_field_kernel(const uint8_t* __restrict__ src,
+                                                          uint8_t* __restrict__ dst, long long n_pixels,
+                                                          int channels, int kind,
+                                                          const void* __restrict__ field) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    for (int c = 0; c < channels; ++c) {
+        const long long e = i * channels + c;
+        const int v = src[e];
+        int out;
+        if (kind == 0) {
+            out = clip_u8(v + (int)reinterpret_cast<const short*>(field)[e]);
+        } else if (kind == 1) {
+            const long long s = reinterpret_cast<const long long*>(field)[e];
+            out = s < 0 ? 0 : (s > 255 ? 255 : (int)s);
+        } else if (kind == 2) {
+            const long long cat = reinterpret_cast<const long long*>(field)[i];
+            out = cat == 1 ? 255 : (cat == 2 ? 0 : v);
+        } else {
+            // float32 mat + float32 mat * float64 noise -> float64 (noise.py:181-182)
+            const double nz = reinterpret_cast<const double*>(field)[e];
+            const double r = __dadd_rn((double)v, __dmul_rn((double)v, nz));
+            out = (int)fmin(fmax(r, 0.0), 255.0);
+        }
+        dst[e] = (uint8_t)out;
+    }
+}
+
+// ============================================================================================
+// Streaks
+// ============================================================================================
+struct StreakColor {
+    float c[4];
+};
+
+__device__ __forceinline__ void streak_blend(uint8_t* p, int channels, const StreakColor& col, float alpha) {
+    for (int c = 0; c < channels; ++c) {
+        if (alpha >= 1.0f) p[c] = (uint8_t)(int)col.c[c];
+        else p[c] = (uint8_t)(int)blend_f32((float)p[c], col.c[c], alpha);
+    }
+}
+
+__device__ __forceinline__ bool dash_off(int coord, int dash_thickness, int dash_gap) {
+    // fill_*_dash_gap (streak.py:24-41): positions with coord % (thickness + gap) < gap are cleared
+    if (dash_thickness <= 0 || dash_gap <= 0) return false;
+    return (coord % (dash_thickness + dash_gap)) < dash_gap;
+}
+
+__global__ void __launch_bounds__(256) streak_line_kernel(uint8_t* image, int h, int w, int channels,
+                                                          int thickness, int gap, int dash_thickness,
+                                                          int dash_gap, int enable_vert, int enable_hori,
+                                                          StreakColor col, float alpha) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int step = thickness + gap;
+    const bool vert = enable_vert && (x % step) < thickness && !dash_off(y, dash_thickness, dash_gap);
+    const bool hori = enable_hori && (y % step) < thickness && !dash_off(x, dash_thickness, dash_gap);
+    uint8_t* p = image + ((long long)y * w + x) * channels;
+    if (vert) streak_blend(p, channels, col, alpha);
+    if (hori) streak_blend(p, channels, col, alpha);
+}
+
+__global__ void __launch_bounds__(256) fill_rects_kernel(uint8_t* mask, int h, int w,
+                                                         const vkb_rect* __restrict__ rects) {
+    const vkb_rect rc = rects[blockIdx.x];
+    const int up = max(rc.up, 0), down = min(rc.down, h - 1);
+    const int left = max(rc.left, 0), right = min(rc.right, w - 1);
+    const int rw = right - left + 1, rh = down - up + 1;
+    if (rw <= 0 || rh <= 0) return;
+    for (long long i = threadIdx.x; i < (long long)rw * rh; i += blockDim.x) {
+        const int yy = (int)(i / rw), xx = (int)(i - (long long)yy * rw);
+        mask[(long long)(up + yy) * w + left + xx] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) streak_masks_kernel(uint8_t* image, int h, int w, int channels,
+                                                           const uint8_t* __restrict__ mask_vert,
+                                                           const uint8_t* __restrict__ mask_hori,
+                                                           int dash_thickness, int dash_gap,
+                                                           StreakColor col, float alpha) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const long long i = (long long)y * w + x;
+    const bool vert = mask_vert && mask_vert[i] && !dash_off(y, dash_thickness, dash_gap);
+    const bool hori = mask_hori && mask_hori[i] && !dash_off(x, dash_thickness, dash_gap);
+    uint8_t* p = image + i * channels;
+    if (vert) streak_blend(p, channels, col, alpha);
+    if (hori) streak_blend(p, channels, col, alpha);
+}
+
+}  // namespace vkb
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+using namespace vkb;
+
+extern "C" int vkb_blend_fill(const vkb_blend_item* item_host, void* stream) {
+    VKB_REQUIRE(item_host && item_host->dst, "no destination");
+    const vkb_blend_item& it = *item_host;
+    VKB_REQUIRE(it.channels >= 1 && it.channels <= 4, "channels must be 1..4");
+    if (it.box_h <= 0 || it.box_w <= 0) return VKB_OK;
+    dim3 grid((it.box_w + 31) / 32, (it.box_h + 31) / 32);
+    blend_fill_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(it);
+    return check_launch("blend_fill_kernel");
+}
+
+extern "C" int vkb_blend_draw_list(const vkb_blend_item* items, int32_t n_items, int32_t dst_h,
+                                   int32_t dst_w, void* stream) {
+    VKB_REQUIRE(items && n_items >= 0 && dst_h > 0 && dst_w > 0, "bad arguments");
+    if (n_items == 0) return VKB_OK;
+    dim3 grid((dst_w + 31) / 32, (dst_h + 31) / 32);
+    blend_draw_list_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(items, n_items, dst_h, dst_w);
+    return check_launch("blend_draw_list_kernel");
+}
+
+extern "C" int vkb_cvt_color(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t code,
+                             void* stream) {
+    VKB_REQUIRE(src && dst && code >= 0 && code <= VKB_CVT_RGBA2GRAY, "bad arguments");
+    if (n_pixels <= 0) return VKB_OK;
+    int rc = ensure_tables((cudaStream_t)stream);
+    if (rc) return rc;
+    const long long blocks = (n_pixels + 255) / 256;
+    cvt_color_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n_pixels, code);
+    return check_launch("cvt_color_kernel");
+}
+
+extern "C" int vkb_color_ops(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                             const vkb_color_op* ops_host, int32_t n_ops, void* stream) {
+    VKB_REQUIRE(src && dst && ops_host, "bad arguments");
+    VKB_REQUIRE(n_ops >= 0 && n_ops <= VKB_MAX_COLOR_OPS, "too many ops");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    if (n_pixels <= 0) return VKB_OK;
+    int rc = ensure_tables((cudaStream_t)stream);
+    if (rc) return rc;
+    ColorOpList list;
+    list.n = n_ops;
+    for (int i = 0; i < n_ops; ++i) list.ops[i] = ops_host[i];
+    const unsigned blocks = (unsigned)((n_pixels + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) color_ops_kernel<1><<<blocks, 256, 0, st>>>(src, dst, n_pixels, list);
+    else if (channels == 3) color_ops_kernel<3><<<blocks, 256, 0, st>>>(src, dst, n_pixels, list);
+    else color_ops_kernel<4><<<blocks, 256, 0, st>>>(src, dst, n_pixels, list);
+    return check_launch("color_ops_kernel");
+}
+
+extern "C" int vkb_channel_stats(const uint8_t* src, int64_t n_pixels, int32_t channels, void* out,
+                                 void* stream) {
+    VKB_REQUIRE(src && out && channels >= 1 && channels <= 3, "bad arguments");
+    unsigned long long* sums = reinterpret_cast<unsigned long long*>(out);
+    unsigned int* mins = reinterpret_cast<unsigned int*>(sums + 3);
+    unsigned int* maxs = mins + 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    channel_stats_init_kernel<<<1, 32, 0, st>>>(sums, mins, maxs);
+    if (n_pixels > 0) {
+        const long long want = (n_pixels + 255) / 256;
+        const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+        channel_stats_kernel<<<blocks, 256, 0, st>>>(src, n_pixels, channels, sums, mins, maxs);
+    }
+    return check_launch("channel_stats_kernel");
+}
+
+extern "C" int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
+                                    int32_t channels, const int32_t* kernel_host, int32_t ksize,
+                                    void* stream) {
+    VKB_REQUIRE(src && dst && kernel_host && h > 0 && w > 0, "bad arguments");
+    VKB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 2 * kGaussMaxR + 1, "ksize must be odd and <= 17");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    GaussKernel gk;
+    gk.r = ksize / 2;
+    for (int i = 0; i < ksize; ++i) gk.k[i] = kernel_host[i];
+    const int TW = 32 + 2 * gk.r;
+    const size_t smem = ((size_t)(TW * TW * channels + 3) & ~(size_t)3) + (size_t)TW * 32 * channels * 2;
+    dim3 grid((w + 31) / 32, (h + 31) / 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) gaussian_blur_kernel<1><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
+    else if (channels == 3) gaussian_blur_kernel<3><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
+    else gaussian_blur_kernel<4><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
+    return check_launch("gaussian_blur_kernel");
+}
+
+extern "C" int vkb_noise_philox(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                                int32_t kind, double p0, double p1, uint64_t seed, void* stream) {
+    VKB_REQUIRE(src && dst && kind >= 0 && kind <= 3 && channels >= 1 && channels <= 4, "bad arguments");
+    if (n_pixels <= 0) return VKB_OK;
+    noise_philox_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, n_pixels, channels, kind, p0, p1, seed);
+    return check_launch("noise_philox_kernel");
+}
+
+extern "C" int vkb_noise_field(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                               int32_t kind, const void* field, void* stream) {
+    VKB_REQUIRE(src && dst && field && kind >= 0 && kind <= 3 && channels >= 1 && channels <= 4,
+                "bad arguments");
+    if (n_pixels <= 0) return VKB_OK;
+    noise_field_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, n_pixels, channels, kind, field);
+    return check_launch("noise_field_kernel");
+}
+
+extern "C" int vkb_streak_line(uint8_t* image, int32_t h, int32_t w, int32_t channels,
+                               int32_t thickness, int32_t gap, int32_t dash_thickness,
+                               int32_t dash_gap, int32_t enable_vert, int32_t enable_hori,
+                               const float* color_host, float alpha, void* stream) {
+    VKB_REQUIRE(image && color_host && h > 0 && w > 0 && thickness + gap > 0, "bad arguments");
+    StreakColor col;
+    for (int c = 0; c < 4; ++c) col.c[c] = c < channels ? color_host[c] : 0.f;
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    streak_line_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        image, h, w, channels, thickness, gap, dash_thickness, dash_gap, enable_vert, enable_hori, col, alpha);
+    return check_launch("streak_line_kernel");
+}
+
+extern "C" int vkb_fill_rects(uint8_t* mask, int32_t h, int32_t w, const vkb_rect* rects,
+                              int32_t n_rects, void* stream) {
+    VKB_REQUIRE(mask && h > 0 && w > 0, "bad arguments");
+    if (n_rects <= 0) return VKB_OK;
+    fill_rects_kernel<<<n_rects, 256, 0, (cudaStream_t)stream>>>(mask, h, w, rects);
+    return check_launch("fill_rects_kernel");
+}
+
+extern "C" int vkb_streak_masks(uint8_t* image, int32_t h, int32_t w, int32_t channels,
+                                const uint8_t* mask_vert, const uint8_t* mask_hori,
+                                int32_t dash_thickness, int32_t dash_gap, const float* color_host,
+                                float alpha, void* stream) {
+    VKB_REQUIRE(image && color_host && h > 0 && w > 0, "bad arguments");
+    StreakColor col;
+    for (int c = 0; c < 4; ++c) col.c[c] = c < channels ? color_host[c] : 0.f;
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    streak_masks_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        image, h, w, channels, mask_vert, mask_hori, dash_thickness, dash_gap, col, alpha);
+    return check_launch("streak_masks_kernel");
+}
