@@ -1,0 +1,145 @@
+"""Device plan of the grid-based ops for a BATCH of pages (batch = 1 for `Distortion.distort`).
+
+Phase 1  project lattice -> finalise (round, shift, result shape)     [shapes come back]
+Phase 2a per-cell homographies, coverage masks, tile candidate lists
+Phase 2b fused remap of Image + Mask + ScoreMap
+
+Replaces DistortionStateImageGridBased.initialize_image_grid_based and
+ImageGrid.generate_remap_params + cv.remap (grid_rendering/interface.py:98-114,
+type.py:209-261, grid_blender.py:54-81).
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from vkit_b200 import _native as nv
+from vkit_b200 import device as dv
+
+from ._hostmath import lattice_axis
+
+
+def new_grid_page(height: int, width: int, grid_size: int):
+    rec = np.zeros((), dtype=nv.GRID_PAGE_DTYPE)
+    rec['src_h'] = height
+    rec['src_w'] = width
+    rec['grid_size'] = grid_size
+    rec['rows'] = len(lattice_axis(height, grid_size))
+    rec['cols'] = len(lattice_axis(width, grid_size))
+    return rec
+
+
+class GridBatch:
+
+    def __init__(self, pages: np.ndarray, keepalive: Sequence = (),
+                 given_lattice: Optional[np.ndarray] = None):
+        dv.require_cuda()
+        self.lib = nv.lib()
+        self.pages = np.ascontiguousarray(pages, dtype=nv.GRID_PAGE_DTYPE).reshape(-1)
+        self.n = int(self.pages.shape[0])
+        self.keepalive = list(keepalive)
+        self.p_max = int((self.pages['rows'] * self.pages['cols']).max())
+        self.c_max = int(((self.pages['rows'] - 1) * (self.pages['cols'] - 1)).max())
+        self.pages_dev = dv.upload_structs(self.pages)
+        self.lattice_f = dv.empty((self.n, self.p_max, 2), np.float64)
+        self.lattice_i = dv.empty((self.n, self.p_max, 2), np.int32)
+        self.meta_dev = dv.empty((self.n * nv.GRID_META_DTYPE.itemsize,), np.uint8)
+        stream = dv.stream_ptr()
+        if given_lattice is not None:
+            lat = np.zeros((self.n, self.p_max, 2), dtype=np.float64)
+            lat[:, :given_lattice.shape[1]] = given_lattice
+            self.lattice_f.copy_(dv.to_device(lat))
+        nv.check(self.lib.vkb_grid_project(dv.ptr(self.pages_dev), self.n, self.p_max,
+                                           dv.ptr(self.lattice_f), stream), 'vkb_grid_project')
+        nv.check(self.lib.vkb_grid_finalize(dv.ptr(self.pages_dev), self.n, self.p_max,
+                                            dv.ptr(self.lattice_f), dv.ptr(self.lattice_i),
+                                            dv.ptr(self.meta_dev), stream), 'vkb_grid_finalize')
+        # result shapes are needed on the host to allocate outputs: one small D2H per batch
+        self.meta = np.frombuffer(dv.to_host(self.meta_dev).tobytes(), dtype=nv.GRID_META_DTYPE)
+        self.max_dst_h = int(self.meta['dst_h'].max())
+        self.max_dst_w = int(self.meta['dst_w'].max())
+        self.tiles_x = (self.max_dst_w + nv.TILE - 1) // nv.TILE
+        self.tiles_y = (self.max_dst_h + nv.TILE - 1) // nv.TILE
+        self.t_max = self.tiles_x * self.tiles_y
+        self.hinv = None
+        self.hfwd = None
+
+    def result_shape(self, i: int = 0):
+        return int(self.meta['dst_h'][i]), int(self.meta['dst_w'][i])
+
+    def build(self, need_forward: bool = False):
+        if self.hinv is not None and (self.hfwd is not None or not need_forward):
+            return
+        self.hinv = dv.empty((self.n, self.c_max, 9), np.float64)
+        if need_forward:
+            self.hfwd = dv.empty((self.n, self.c_max, 9), np.float64)
+        self.cell_box = dv.empty((self.n, self.c_max, 4), np.int32)
+        self.cell_masks = dv.empty((self.n, self.c_max, nv.CELL_MASK_WORDS), np.uint32)
+        self.tile_count = dv.empty((self.n, self.t_max), np.int32)
+        self.tile_cells = dv.empty((self.n, self.t_max, nv.TILE_CAP), np.uint16)
+        nv.check(self.lib.vkb_grid_build(
+            dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max,
+            dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv), dv.ptr(self.hfwd),
+            dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
+            dv.ptr(self.tile_cells), dv.stream_ptr()), 'vkb_grid_build')
+
+    def remap(self, planes: np.ndarray):
+        """planes: structured array (PLANES_DTYPE), one record per page, device pointers."""
+        self.build()
+        planes_dev = dv.upload_structs(np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE))
+        nv.check(self.lib.vkb_grid_remap(
+            dv.ptr(self.pages_dev), dv.ptr(planes_dev), self.n, self.p_max, self.c_max, self.t_max,
+            dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv),
+            dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
+            dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, dv.stream_ptr()),
+            'vkb_grid_remap')
+        return planes_dev
+
+    def transform_points(self, page: int, xy: np.ndarray, cell_rc: np.ndarray) -> np.ndarray:
+        """xy: n x 2 float64 smooth (x, y); cell_rc: n x 2 int32 (polygon_row, polygon_col)."""
+        self.build(need_forward=True)
+        n = int(xy.shape[0])
+        if n == 0:
+            return np.zeros((0, 2), dtype=np.float64)
+        ccols = int(self.pages['cols'][page]) - 1
+        xy_dev = dv.to_device(np.ascontiguousarray(xy, dtype=np.float64))
+        rc_dev = dv.to_device(np.ascontiguousarray(cell_rc, dtype=np.int32))
+        out = dv.empty((n, 2), np.float64)
+        nv.check(self.lib.vkb_grid_points(dv.ptr(self.hfwd[page]), ccols, dv.ptr(xy_dev),
+                                          dv.ptr(rc_dev), dv.ptr(out), n, dv.stream_ptr()),
+                 'vkb_grid_points')
+        return dv.to_host(out)
+
+    def lattice_points(self, page: int = 0) -> np.ndarray:
+        """Integer dst lattice (rows, cols, 2) as (x, y), on the host."""
+        rows, cols = int(self.pages['rows'][page]), int(self.pages['cols'][page])
+        return dv.to_host(self.lattice_i[page, :rows * cols]).reshape(rows, cols, 2)
+
+
+def planes_record(image=None, mask=None, score_map=None, dst_shape=None):
+    """Allocate outputs for one page and describe the fused launch.  Inputs are elements;
+    returns (record, out_image_tensor, out_mask_tensor, out_score_tensor)."""
+    rec = np.zeros((), dtype=nv.PLANES_DTYPE)
+    first = image or mask or score_map
+    src_h, src_w = first.shape
+    dst_h, dst_w = dst_shape
+    rec['src_h'], rec['src_w'], rec['dst_h'], rec['dst_w'] = src_h, src_w, dst_h, dst_w
+    out_image = out_mask = out_score = None
+    if image is not None:
+        channels = image.num_channels or 1
+        if image.mat_dtype != np.uint8 or channels not in (1, 3, 4):
+            raise NotImplementedError('geometric ops support uint8 images with 1, 3 or 4 channels')
+        shape = (dst_h, dst_w) if image.num_channels == 0 else (dst_h, dst_w, channels)
+        out_image = dv.empty(shape, np.uint8)
+        rec['src_image'] = image.dev.data_ptr()
+        rec['dst_image'] = out_image.data_ptr()
+        rec['image_channels'] = channels
+    if mask is not None:
+        out_mask = dv.empty((dst_h, dst_w), np.uint8)
+        rec['src_mask'] = mask.dev.data_ptr()
+        rec['dst_mask'] = out_mask.data_ptr()
+    if score_map is not None:
+        out_score = dv.empty((dst_h, dst_w), np.float32)
+        rec['src_score'] = score_map.dev.data_ptr()
+        rec['dst_score'] = out_score.data_ptr()
+    return rec, out_image, out_mask, out_score
