@@ -372,9 +372,19 @@ def cvt_hsv2rgb_full(hsv):
 
 
 def cvt_rgb2hls_full(rgb):
-    """cv.cvtColor(uint8, COLOR_RGB2HLS_FULL): float32 path, hue scale 255/360. L is exact,
-    H/S within +-1 of cv2 (backend dependent inside cv2, appendix A.6)."""
+    """cv.cvtColor(uint8, COLOR_RGB2HLS_FULL) as the default (IPP) backend of the 4.13 wheel
+    computes it: hue scale 255/360; L = round_half_even((max + min) / 2) EXACTLY (all 32 896
+    (max, min) pairs); H and S through float32, within +-1 of cv2 (whose own result depends on
+    the IPP / SIMD / scalar backend)."""
     f32 = np.float32
+    ri = rgb[..., 0].astype(np.int64)
+    gi = rgb[..., 1].astype(np.int64)
+    bi = rgb[..., 2].astype(np.int64)
+    imax = np.maximum(np.maximum(ri, gi), bi)
+    imin = np.minimum(np.minimum(ri, gi), bi)
+    isum = imax + imin
+    half = isum >> 1
+    l_int = np.where((isum & 1) == 0, half, half + (half & 1))
     x = rgb.astype(f32) * f32(1.0 / 255.0)
     r, g, b = x[..., 0], x[..., 1], x[..., 2]
     vmax = np.maximum(np.maximum(r, g), b)
@@ -390,8 +400,9 @@ def cvt_rgb2hls_full(rgb):
     zero = diff <= np.finfo(f32).eps
     h = np.where(zero, f32(0), h)
     s = np.where(zero, f32(0), s)
-    out = np.stack([h * f32(255.0 / 360.0), l * f32(255.0), s * f32(255.0)], axis=-1)
-    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+    hs = np.stack([h * f32(255.0 / 360.0), s * f32(255.0)], axis=-1)
+    hs = np.clip(np.rint(hs), 0, 255).astype(np.int64)
+    return np.stack([hs[..., 0], l_int, hs[..., 1]], axis=-1).astype(np.uint8)
 
 
 def cvt_hls2rgb_full(hls):

@@ -1,0 +1,111 @@
+"""Shared test helpers: seeded synthetic inputs, golden fixtures."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+TESTS_DIR = os.path.dirname(os.path.abspath(__file__))
+GOLDEN_DIR = os.path.join(TESTS_DIR, 'golden')
+
+
+def make_inputs(seed: int, shape):
+    """image uint8 HxWx3, mask uint8 HxW (0/1), score_map float32 HxW in [0, 1)."""
+    height, width = shape
+    rng = np.random.default_rng(seed)
+    image = rng.integers(0, 256, (height, width, 3), dtype=np.uint8)
+    mask = (rng.random((height, width)) > 0.5).astype(np.uint8)
+    score_map = rng.random((height, width)).astype(np.float32)
+    return image, mask, score_map
+
+
+def make_points(seed: int, shape, n: int):
+    """n smooth (x, y) points strictly inside the page."""
+    height, width = shape
+    rng = np.random.default_rng(seed + 100000)
+    xs = rng.uniform(0, width - 2, n)
+    ys = rng.uniform(0, height - 2, n)
+    return [(float(x), float(y)) for x, y in zip(xs, ys)]
+
+
+def make_polygons(seed: int, shape, n: int):
+    """n axis-aligned quads as lists of (x, y)."""
+    height, width = shape
+    rng = np.random.default_rng(seed + 200000)
+    polys = []
+    for _ in range(n):
+        x0 = int(rng.integers(0, width - 12))
+        y0 = int(rng.integers(0, height - 12))
+        x1 = int(rng.integers(x0 + 4, min(width - 1, x0 + 60)))
+        y1 = int(rng.integers(y0 + 4, min(height - 1, y0 + 40)))
+        polys.append([(x0, y0), (x1, y0), (x1, y1), (x0, y1)])
+    return polys
+
+
+def sha(arr: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+_GOLDEN = None
+
+
+def golden():
+    """(cases list, arrays NpzFile) from tests/golden."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        with open(os.path.join(GOLDEN_DIR, 'cases.json')) as fin:
+            meta = json.load(fin)
+        arrays = np.load(os.path.join(GOLDEN_DIR, 'arrays.npz'))
+        _GOLDEN = (meta['cases'], arrays)
+    return _GOLDEN
+
+
+def golden_cases(kind=None, **filters):
+    cases, _ = golden()
+    out = []
+    for case in cases:
+        if kind and case['kind'] != kind:
+            continue
+        if any(case.get(k) != v for k, v in filters.items()):
+            continue
+        out.append(case)
+    return out
+
+
+def golden_array(case, key):
+    _, arrays = golden()
+    name = f"{case['id']}/{key}"
+    return arrays[name] if name in arrays.files else None
+
+
+# ---------------------------------------------------------------------------------------------
+# Golden case -> oracle run / product config
+# ---------------------------------------------------------------------------------------------
+AFFINE_OPS = ('rotate', 'shear_hori', 'shear_vert', 'skew_hori', 'skew_vert')
+
+
+def oracle_geometric(case, port, want=('image', 'mask', 'score_map'), given_lattice=None):
+    """Run the oracle on a golden geometric case -> dict of arrays."""
+    shape = tuple(case['shape'])
+    image, mask, score_map = make_inputs(case['seed'], shape)
+    name, cfg = case['op'], case['config']
+    mats = {'image': image, 'mask': mask, 'score_map': score_map}
+    if name in AFFINE_OPS:
+        trans_mat, dsize = port.affine_state(name, cfg, shape)
+        out = {k: port.affine_apply(mats[k], trans_mat, dsize) for k in want}
+        out['shape'] = (dsize[1], dsize[0]) if dsize else shape
+        out['trans_mat'] = trans_mat
+        return out
+    res = port.grid_distort(name, cfg, shape, **{k: mats[k] for k in want},
+                            given_lattice=given_lattice)
+    return res
+
+
+def product_config(case):
+    """Config argument for vkit_b200.mechanism.distortion.<op>.distort from a golden case."""
+    cfg = dict(case['config'])
+    if case['op'] == 'similarity_mls':
+        from vkit_b200.element import PointTuple
+        cfg['src_handle_points'] = PointTuple.from_xy_pairs(cfg['src_handle_points'])
+        cfg['dst_handle_points'] = PointTuple.from_xy_pairs(cfg['dst_handle_points'])
+    return cfg

@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures of the live
+reference and against the oracle.  Needs a B200: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from common import (AFFINE_OPS, golden_array, golden_cases, make_inputs, make_points,
+                    make_polygons, oracle_geometric, product_config, sha)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def vk():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from vkit_b200 import _native
+    _native.lib()  # fails loudly if the extension is missing
+    import vkit_b200.element as element
+    from vkit_b200.mechanism import distortion
+    return element, distortion
+
+
+GEOMETRIC = golden_cases('geometric')
+
+
+def _run_product(vk, case, device_inputs=False, given_lattice=None):
+    element, distortion = vk
+    shape = tuple(case['shape'])
+    image, mask, score_map = make_inputs(case['seed'], shape)
+    kwargs = {}
+    if case['labels']:
+        kwargs['points'] = element.PointList(
+            element.Point.create(y=y, x=x) for x, y in make_points(case['seed'], shape, 24))
+        kwargs['polygons'] = [element.Polygon.from_xy_pairs(p)
+                              for p in make_polygons(case['seed'], shape, 6)]
+    op = getattr(distortion, case['op'])
+    if device_inputs:
+        import torch
+        image, mask, score_map = (torch.from_numpy(a).cuda() for a in (image, mask, score_map))
+    return op.distort(product_config(case), image=element.Image(mat=image),
+                      mask=element.Mask(mat=mask), score_map=element.ScoreMap(mat=score_map),
+                      get_active_mask=True, get_state=True, disable_clip_result_elements=True,
+                      **kwargs)
+
+
+def _diff_report(got, ref):
+    d = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    if d.ndim == 3:
+        d = d.max(axis=-1)
+    return f'{int((d > 0).sum())}/{d.size} px differ, max abs {d.max():.4g}'
+
+
+@pytest.mark.parametrize('case', GEOMETRIC, ids=lambda c: f"{c['id']}-{c['op']}-{c['shape'][0]}")
+def test_geometric_vs_golden(vk, case):
+    r = _run_product(vk, case)
+    assert tuple(r.shape) == tuple(case['result_shape'])
+    grid_op = case['op'] not in AFFINE_OPS
+    flips = 0
+    if grid_op:
+        lattice = golden_array(case, 'lattice')
+        mine = r.state.plan.lattice_points(0).reshape(-1, 2)
+        flips = int((mine != lattice).any(axis=1).sum())
+        if case['op'] == 'similarity_mls':
+            # float32 MLS through BLAS on the host cannot be reproduced op for op: a handful of
+            # lattice points may round differently.
+            assert flips <= 4, f'{flips} lattice flips'
+        else:
+            assert flips == 0, f'{flips} lattice flips'
+    got = {'image': r.image.mat, 'mask': r.mask.mat, 'score_map': r.score_map.mat,
+           'active_mask': r.active_mask.mat}
+    if case['op'].startswith('skew'):
+        ref = golden_array(case, 'image')
+        diff = np.abs(got['image'].astype(int) - ref.astype(int)).max(axis=-1)
+        assert (diff > 0).mean() <= 0.005 and diff.max() <= 16, _diff_report(got['image'], ref)
+    elif flips == 0:
+        for key in ('image', 'mask', 'score_map', 'active_mask'):
+            if sha(got[key]) != case['sha'][key]:
+                from oracle import vkit_port as port
+                port.use_cv2(False)
+                ref = oracle_geometric(case, port, want=(key,) if key != 'active_mask' else ())
+                detail = _diff_report(got[key], ref[key]) if key in ref and ref[key] is not None else ''
+                raise AssertionError(f'{key} differs from the reference: {detail}')
+    if case['labels']:
+        pts = np.asarray([(p.smooth_x, p.smooth_y) for p in r.points])
+        polys = np.asarray([[(p.smooth_x, p.smooth_y) for p in poly.points] for poly in r.polygons])
+        if flips == 0:
+            np.testing.assert_allclose(pts, golden_array(case, 'points'), rtol=0, atol=2e-4)
+            np.testing.assert_allclose(polys, golden_array(case, 'polygons'), rtol=0, atol=2e-4)
+            ref_int = np.rint(golden_array(case, 'points'))
+            assert (np.rint(pts) != ref_int).sum() <= 1  # rounded twins (ties aside)
+
+
+@pytest.mark.parametrize('case', [c for c in GEOMETRIC if c['op'] == 'similarity_mls'],
+                         ids=lambda c: f"{c['id']}-{c['shape'][0]}")
+def test_mls_kernel_exact_given_reference_lattice(vk, case):
+    """With the reference's own lattice injected, the fused remap is bit-exact."""
+    element, distortion = vk
+    from vkit_b200 import _native as nv
+    from vkit_b200.mechanism.distortion.geometric import mls as mls_mod
+    from vkit_b200.mechanism.distortion.geometric._gridcore import GridBatch, planes_record
+    shape = tuple(case['shape'])
+    image, mask, score_map = make_inputs(case['seed'], shape)
+    cfg = product_config(case)
+    config = mls_mod.SimilarityMlsConfig(**{k: v for k, v in cfg.items()})
+    rec, handles = mls_mod.similarity_mls_page(config, shape)
+    rec['projector'] = nv.PROJ_GIVEN
+    rec['resize_as_src'] = 0
+    lattice = golden_array(case, 'lattice').astype(np.float64)[None]
+    plan = GridBatch(rec.reshape(1), keepalive=[handles], given_lattice=lattice)
+    assert plan.result_shape(0) == tuple(case['result_shape'])
+    planes, oi, om, os_ = planes_record(element.Image(mat=image), element.Mask(mat=mask),
+                                        element.ScoreMap(mat=score_map), plan.result_shape(0))
+    plan.remap(planes.reshape(1))
+    assert sha(oi.cpu().numpy()) == case['sha']['image']
+    assert sha(om.cpu().numpy()) == case['sha']['mask']
+    assert sha(os_.cpu().numpy()) == case['sha']['score_map']
+
+
+def test_device_resident_inputs_and_chaining(vk):
+    """Tensor-backed containers: no host round trip between ops, same bits as host inputs."""
+    case = [c for c in GEOMETRIC if c['op'] == 'camera_cubic_curve' and c['shape'][0] < 400][0]
+    a = _run_product(vk, case, device_inputs=False)
+    b = _run_product(vk, case, device_inputs=True)
+    assert b.image.on_device and b.mask.on_device and b.score_map.on_device
+    assert sha(a.image.mat) == sha(b.image.mat) == case['sha']['image']
+    element, distortion = vk
+    c = distortion.rotate.distort({'angle': 33}, image=b.image, mask=b.mask, score_map=b.score_map)
+    assert c.image.on_device
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    trans_mat, dsize = port.affine_state('rotate', {'angle': 33}, b.image.shape)
+    assert sha(c.image.mat) == sha(port.affine_apply(b.image.mat, trans_mat, dsize))
+    assert sha(c.score_map.mat) == sha(port.affine_apply(b.score_map.mat, trans_mat, dsize))
+
+
+def test_separate_calls_match_fused(vk):
+    element, distortion = vk
+    case = [c for c in GEOMETRIC if c['op'] == 'camera_plane_line_fold'][0]
+    shape = tuple(case['shape'])
+    image, mask, score_map = make_inputs(case['seed'], shape)
+    cfg = product_config(case)
+    op = distortion.camera_plane_line_fold
+    state = op.generate_state(cfg, shape)
+    img = op.distort_image(cfg, element.Image(mat=image), state=state)
+    msk = op.distort_mask(cfg, element.Mask(mat=mask), state=state)
+    scm = op.distort_score_map(cfg, element.ScoreMap(mat=score_map), state=state)
+    assert sha(img.mat) == case['sha']['image']
+    assert sha(msk.mat) == case['sha']['mask']
+    assert sha(scm.mat) == case['sha']['score_map']
+    assert img.mode == element.ImageMode.RGB
+
+
+def test_grayscale_and_rgba_images(vk):
+    element, distortion = vk
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    rng = np.random.default_rng(3)
+    gray = rng.integers(0, 256, (90, 121), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (90, 121, 4), dtype=np.uint8)
+    for mat in (gray, rgba):
+        r = distortion.rotate.distort({'angle': 77}, image=element.Image(mat=mat))
+        trans_mat, dsize = port.affine_state('rotate', {'angle': 77}, mat.shape[:2])
+        assert sha(r.image.mat) == sha(port.affine_apply(mat, trans_mat, dsize))
+    case = [c for c in GEOMETRIC if c['op'] == 'camera_plane_only'][0]
+    shape = tuple(case['shape'])
+    mat = rng.integers(0, 256, shape + (4,), dtype=np.uint8)
+    r = distortion.camera_plane_only.distort(product_config(case), image=element.Image(mat=mat))
+    ref = port.grid_distort(case['op'], case['config'], shape, image=mat)
+    assert sha(r.image.mat) == sha(ref['image'])
+
+
+def test_nop_and_edge_shapes(vk):
+    element, distortion = vk
+    rng = np.random.default_rng(4)
+    mat = rng.integers(0, 256, (33, 47, 3), dtype=np.uint8)
+    r = distortion.rotate.distort({'angle': 0}, image=element.Image(mat=mat))
+    assert r.shape == (33, 47) and sha(r.image.mat) == sha(mat)
+    r = distortion.rotate.distort({'angle': 360}, image=element.Image(mat=mat))
+    assert sha(r.image.mat) == sha(mat)  # angle % 360 == 0 still warps with the identity
+    r = distortion.rotate.distort({'angle': 90}, image=element.Image(mat=mat))
+    from oracle import vkit_port as port
+    trans_mat, dsize = port.affine_state('rotate', {'angle': 90}, (33, 47))
+    assert sha(r.image.mat) == sha(port.affine_apply(mat, trans_mat, dsize))
+    # page smaller than one grid cell in one direction
+    tiny = rng.integers(0, 256, (16, 40, 3), dtype=np.uint8)
+    cfg = {'camera_model_config': {'rotation_unit_vec': [1.0, 0.5, 0.1], 'rotation_theta': 20},
+           'grid_size': 15}
+    r = distortion.camera_plane_only.distort(cfg, image=element.Image(mat=tiny))
+    ref = port.grid_distort('camera_plane_only', cfg, (16, 40), image=tiny)
+    assert r.shape == tuple(ref['shape']) and sha(r.image.mat) == sha(ref['image'])
+
+
+# ---------------------------------------------------------------------------------------------
+# photometric + blend
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', golden_cases('photometric'),
+                         ids=lambda c: f"{c['id']}-{c['op']}-{c['shape'][0]}")
+def test_photometric_vs_golden(vk, case):
+    element, distortion = vk
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    img = element.Image(mat=image)
+    if case['mode']:
+        img = img.to_target_mode_image(element.ImageMode(case['mode']))
+    rng = np.random.default_rng(case['rng_seed']) if case['rng_seed'] is not None else None
+    op = getattr(distortion, case['op'])
+    is_noise = case['op'].endswith('_noise')
+    noise_mod.use_host_field(is_noise)  # bit-exact mode: the host draws the reference's field
+    try:
+        r = op.distort(dict(case['config']), image=img, rng=rng)
+    finally:
+        noise_mod.use_host_field(False)
+    got = r.image.mat
+    assert r.image.mode.value == case['result_mode']
+    if case['op'] in ('color_shift', 'brightness_shift'):
+        ref = golden_array(case, 'image')
+        diff = np.abs(got.astype(int) - ref.astype(int))
+        if case['op'] == 'brightness_shift' and case['config']['intermediate_image_mode'] == 'hsl':
+            assert (diff > 0).mean() <= 0.03 and (diff > 1).mean() <= 0.006 and diff.max() <= 8
+        else:
+            assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3
+    elif case['op'] == 'std_shift':
+        ref = golden_array(case, 'image')
+        diff = np.abs(got.astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4  # exact mean vs float32 running mean
+    else:
+        assert sha(got) == case['sha']['image'], case['op']
+
+
+def test_noise_philox_distribution(vk):
+    """Default (device RNG) noise mode: distributional parity."""
+    element, distortion = vk
+    base = np.full((512, 512, 3), 128, dtype=np.uint8)
+    rng = np.random.default_rng(0)
+    out = distortion.gaussion_noise.distort({'std': 10.0}, image=element.Image(mat=base), rng=rng)
+    res = out.image.mat.astype(np.float64) - 128
+    assert abs(res.mean()) < 0.05 and abs(res.std() - np.sqrt(100 + 1 / 12)) < 0.1
+    out = distortion.poisson_noise.distort({}, image=element.Image(mat=base), rng=rng)
+    res = out.image.mat.astype(np.float64)
+    assert abs(res.mean() - 128) < 0.1 and abs(res.var() - 128) < 2.0
+    out = distortion.impulse_noise.distort({'prob_salt': 0.03, 'prob_pepper': 0.02},
+                                           image=element.Image(mat=base), rng=rng)
+    m = out.image.mat
+    assert abs((m[..., 0] == 255).mean() - 0.03) < 2e-3 and abs((m[..., 0] == 0).mean() - 0.02) < 2e-3
+    assert ((m[..., 0] == m[..., 1]) & (m[..., 1] == m[..., 2])).all()  # one draw per pixel
+    out = distortion.speckle_noise.distort({'std': 0.1}, image=element.Image(mat=base), rng=rng)
+    res = out.image.mat.astype(np.float64) - 128
+    assert abs(res.mean() + 0.5) < 0.1 and abs(res.std() - 12.8) < 0.2  # truncation bias -0.5
+
+
+@pytest.mark.parametrize('case', golden_cases('blend'), ids=lambda c: f"{c['id']}-{c['op']}")
+def test_blend_vs_golden(vk, case):
+    element, _ = vk
+    shape = tuple(case['shape'])
+    image, mask, score_map = make_inputs(case['seed'], shape)
+    up, down, left, right = case['box']
+    box = element.Box(up=up, down=down, left=left, right=right)
+    img = element.Image(mat=image.copy())
+    kind = case['op']
+    if kind == 'score_map_color':
+        element.ScoreMap(mat=golden_array(case, 'alpha'), box=box).fill_image(img, (17, 99, 201))
+    elif kind == 'box_alpha_scalar':
+        box.fill_image(img, (250, 3, 77), alpha=case['alpha'])
+    elif kind == 'box_value_image_alpha':
+        box.fill_image(img, golden_array(case, 'value'), alpha=case['alpha'])
+    elif kind == 'mask_assign':
+        element.Mask(mat=golden_array(case, 'm'), box=box).fill_image(img, (1, 2, 3))
+    elif kind == 'score_keep_max':
+        base = element.ScoreMap(mat=score_map.copy())
+        box.fill_score_map(base, golden_array(case, 'value'), keep_max_value=True)
+        assert sha(base.mat) == case['sha']['out_score']
+        return
+    elif kind == 'inactive_fill':
+        element.Mask(mat=mask.copy()).to_inverted_mask().fill_image(
+            img, element.Image(mat=golden_array(case, 'bottom')))
+    assert sha(img.mat) == case['sha']['out_image']
+
+
+def test_photometric_properties(vk):
+    """Property assertions of the reference's own tests, on synthetic images
+    (tests/mechanism/test_photometric_distortion.py:21-278)."""
+    element, distortion = vk
+    image, _, _ = make_inputs(7, (96, 128))
+    img = element.Image(mat=image)
+    out = distortion.complement.distort({}, image=img).image.mat
+    assert (out.astype(int) + image.astype(int) == 255).all()
+    out = distortion.posterization.distort({'num_bits': 4}, image=img).image.mat
+    assert (out & 0x0F == 0).all() and ((out | 0x0F) == (image | 0x0F)).all()
+    out = distortion.mean_shift.distort({'delta': 255}, image=img).image.mat
+    assert (out == 255).all()
+    out = distortion.mean_shift.distort({'delta': 256, 'oob_behavior': 'cycle'}, image=img).image.mat
+    assert (out == image).all()
+    out = distortion.boundary_equalization.distort({}, image=img).image.mat
+    assert out.reshape(-1, 3).min(axis=0).tolist() == [0, 0, 0]
+    assert out.reshape(-1, 3).max(axis=0).tolist() == [255, 255, 255]
+    out = distortion.channel_permutation.distort({}, image=img, rng=np.random.default_rng(0))
+    assert (out.image.mat == image[:, :, [2, 0, 1]]).all()  # known answer of the reference test
+    out = distortion.std_shift.distort({'scale': 1.5}, image=element.Image(
+        mat=np.clip(image // 2 + 64, 0, 255).astype(np.uint8))).image.mat
+    src = np.clip(image // 2 + 64, 0, 255).astype(np.float64)
+    assert abs(out.std() / src.std() - 1.5) < 0.1 and abs(out.mean() - src.mean()) < 2
+
+
+def test_random_distortion_chain_runs(vk):
+    element, _ = vk
+    from vkit_b200.mechanism.distortion_policy import random_distortion_factory
+    not_yet = ['defocus_blur', 'zoom_in_blur', 'motion_blur', 'glass_blur', 'jpeg_quality',
+               'pixelation', 'fog', 'ellipse_streak', 'histogram_equalization']
+    rd = random_distortion_factory.create({'disabled_policy_names': not_yet,
+                                           'force_post_rotate': True})
+    image, mask, _ = make_inputs(9, (200, 260))
+    pts = [element.Point.create(y=y, x=x) for x, y in make_points(9, (200, 260), 16)]
+    polys = [element.Polygon.from_xy_pairs(p) for p in make_polygons(9, (200, 260), 4)]
+    for seed in range(12):
+        rng = np.random.default_rng(seed)
+        r = rd.distort(rng, image=element.Image(mat=image), mask=element.Mask(mat=mask),
+                       points=pts, polygons=polys)
+        assert r.image.shape == r.mask.shape == tuple(r.shape) or r.image.shape == r.mask.shape
+        assert len(r.points) == 16 and len(r.polygons) == 4
+        assert r.image.mat.dtype == np.uint8
+
+
+def test_batched_engine_matches_single_page(vk):
+    element, distortion = vk
+    import torch
+    from vkit_b200.batch import GeometricBatch
+    cases = [c for c in GEOMETRIC if c['op'] not in AFFINE_OPS and tuple(c['shape']) == (136, 176)]
+    shape = (136, 176)
+    images = np.stack([make_inputs(c['seed'], shape)[0] for c in cases])
+    masks = np.stack([make_inputs(c['seed'], shape)[1] for c in cases])
+    scores = np.stack([make_inputs(c['seed'], shape)[2] for c in cases])
+    engine = GeometricBatch([c['op'] for c in cases], [product_config(c) for c in cases], shape)
+    out = engine.run(torch.from_numpy(images).cuda(), torch.from_numpy(masks).cuda(),
+                     torch.from_numpy(scores).cuda())
+    for i, case in enumerate(cases):
+        assert out.shapes[i] == tuple(case['result_shape'])
+        lattice = golden_array(case, 'lattice')
+        mine = engine.plan.lattice_points(i).reshape(-1, 2)
+        if (mine != lattice).any():
+            assert case['op'] == 'similarity_mls'
+            continue
+        assert sha(out.image(i).cpu().numpy()) == case['sha']['image'], case['id']
+        assert sha(out.mask(i).cpu().numpy()) == case['sha']['mask'], case['id']
+        assert sha(out.score_map(i).cpu().numpy()) == case['sha']['score_map'], case['id']

@@ -74,8 +74,9 @@ VKB_HD void hsv2rgb_full(int H, int S, int V, int& r, int& g, int& b) {
     b = round_u8(VKB_FMUL(fb, 255.f));
 }
 
-// COLOR_RGB2HLS_FULL, uint8 through float32, hue scale 255/360. L exact; H, S within +-1 of cv2,
-// whose own result depends on the SIMD / IPP backend (appendix A.6).
+// COLOR_RGB2HLS_FULL, uint8, hue scale 255/360 (the wheel's default IPP backend).
+// L = round_half_even((max + min) / 2): exact.  H, S through float32: within +-1 of cv2, whose
+// own result depends on the IPP / SIMD / scalar backend (appendix A.6).
 VKB_HD void rgb2hls_full(int R, int G, int B, int& h, int& l, int& s) {
     const float k = (float)(1.0 / 255.0);
     const float r = VKB_FMUL((float)R, k), g = VKB_FMUL((float)G, k), b = VKB_FMUL((float)B, k);
@@ -94,7 +95,10 @@ VKB_HD void rgb2hls_full(int R, int G, int B, int& h, int& l, int& s) {
         if (hf < 0.f) hf = VKB_FADD(hf, 360.f);
     }
     h = round_u8(VKB_FMUL(hf, (float)(255.0 / 360.0)));
-    l = round_u8(VKB_FMUL(lf, 255.f));
+    const int imax = R > G ? (R > B ? R : B) : (G > B ? G : B);
+    const int imin = R < G ? (R < B ? R : B) : (G < B ? G : B);
+    const int isum = imax + imin, half = isum >> 1;
+    l = (isum & 1) ? half + (half & 1) : half;
     s = round_u8(VKB_FMUL(sf, 255.f));
 }
 
