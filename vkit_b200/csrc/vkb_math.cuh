@@ -213,10 +213,22 @@ VKB_HD void homography_4pt(const double* src_quad, const double* dst_quad, doubl
                            + B[r * 3 + 2] * J[2 * 3 + c];
         }
     }
-    const double inv = 1.0 / H[8];
+    // cv2 fixes H[8] = 1.  When the cell's vanishing line passes (numerically) through the
+    // canvas origin H[8] is ~0 and that normalisation blows up, so fall back to the largest
+    // entry; a homography is scale free, N/D per pixel is unaffected.
+    double big = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) H[i] *= inv;
-    H[8] = 1.0;
+    for (int i = 0; i < 9; ++i) big = fmax(big, fabs(H[i]));
+    if (fabs(H[8]) > 1e-9 * big) {
+        const double inv = 1.0 / H[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) H[i] *= inv;
+        H[8] = 1.0;
+    } else if (big > 0.0) {
+        const double inv = 1.0 / big;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] *= inv;
+    }
 }
 
 // ---------------------------------------------------------------------------------------

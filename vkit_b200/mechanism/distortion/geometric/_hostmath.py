@@ -71,7 +71,10 @@ def homography_4pt(src_quad, dst_quad) -> np.ndarray:
          a[0, 0] * a[1, 1] - a[0, 1] * a[1, 0]],
     ])
     h = b @ adj
-    return h / h[2, 2]
+    big = np.abs(h).max()
+    if abs(h[2, 2]) > 1e-9 * big:
+        return h / h[2, 2]
+    return h / big
 
 
 def lattice_axis(size: int, grid_size: int):
