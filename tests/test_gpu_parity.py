@@ -108,8 +108,8 @@ def test_mls_kernel_exact_given_reference_lattice(vk, case):
     lattice = golden_array(case, 'lattice').astype(np.float64)[None]
     plan = GridBatch(rec.reshape(1), keepalive=[handles], given_lattice=lattice)
     assert plan.result_shape(0) == tuple(case['result_shape'])
-    planes, oi, om, os_ = planes_record(element.Image(mat=image), element.Mask(mat=mask),
-                                        element.ScoreMap(mat=score_map), plan.result_shape(0))
+    src = (element.Image(mat=image), element.Mask(mat=mask), element.ScoreMap(mat=score_map))
+    planes, oi, om, os_ = planes_record(*src, plan.result_shape(0))  # src keeps the inputs alive
     plan.remap(planes.reshape(1))
     assert sha(oi.cpu().numpy()) == case['sha']['image']
     assert sha(om.cpu().numpy()) == case['sha']['mask']
