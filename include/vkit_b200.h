@@ -161,13 +161,15 @@ int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, i
 
 /* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
  * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
- * value, 1/32 px quantisation, bilinear gather of Image + Mask + ScoreMap in one pass. */
+ * value, 1/32 px quantisation, bilinear gather of Image + Mask + ScoreMap in one pass.
+ * The kernel is specialised at compile time on the containers present, so every page of one
+ * call carries the same set: image_channels (0 = no image), has_mask, has_score. */
 int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
                    int32_t p_max, int32_t c_max, int32_t t_max, const int32_t* lattice_i,
                    const vkb_grid_meta* meta, const double* hinv, const int32_t* cell_box,
-                   const uint32_t* cell_masks,
-                   const int32_t* tile_count, const uint16_t* tile_cells, int32_t max_dst_h,
-                   int32_t max_dst_w, void* stream);
+                   const uint32_t* cell_masks, const int32_t* tile_count,
+                   const uint16_t* tile_cells, int32_t max_dst_h, int32_t max_dst_w,
+                   int32_t image_channels, int32_t has_mask, int32_t has_score, void* stream);
 
 /* Points through the forward homography of the source cell that contains the ROUNDED point
  * (FuncImageGridBased.func_point, grid_rendering/interface.py:194-216).

@@ -156,3 +156,51 @@ extern "C" int hs_sizeof_grid_page() { return (int)sizeof(vkb_grid_page); }
 extern "C" int hs_sizeof_warp_page() { return (int)sizeof(vkb_warp_page); }
 extern "C" int hs_sizeof_planes() { return (int)sizeof(vkb_planes); }
 extern "C" int hs_sizeof_grid_meta() { return (int)sizeof(vkb_grid_meta); }
+
+// Fast-path audit: for every covered pixel compare the float32 fast path with the float64 path.
+// stats[0] pixels, [1] fast ok, [2] ok but X/Y differ from exact (must be 0),
+// [3] max |32*du_fast - 32*du_exact| * 1e9 (x or y), over pixels of covered cells.
+extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, int W, int Hh,
+                                   const int32_t* owner, long long* stats) {
+    const int ccols = pg->cols - 1, C = (pg->rows - 1) * ccols;
+    std::vector<double> hinv((size_t)C * 9);
+    std::vector<CellLocal> loc(C);
+    for (int cell = 0; cell < C; ++cell) {
+        const int r = cell / ccols, c = cell % ccols;
+        const int i00 = r * pg->cols + c, i01 = i00 + 1, i11 = i00 + pg->cols + 1, i10 = i00 + pg->cols;
+        const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
+        const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
+        const int sx0 = lattice_coord(c, pg->src_w, pg->grid_size), sx1 = lattice_coord(c + 1, pg->src_w, pg->grid_size);
+        const int sy0 = lattice_coord(r, pg->src_h, pg->grid_size), sy1 = lattice_coord(r + 1, pg->src_h, pg->grid_size);
+        const double sq[8] = {(double)sx0, (double)sy0, (double)sx1, (double)sy0, (double)sx1, (double)sy1, (double)sx0, (double)sy1};
+        const double dq[8] = {(double)px[0], (double)py[0], (double)px[1], (double)py[1], (double)px[2], (double)py[2], (double)px[3], (double)py[3]};
+        homography_4pt(dq, sq, &hinv[(size_t)cell * 9]);
+        const int x0 = *std::min_element(px, px + 4), y0 = *std::min_element(py, py + 4);
+        make_cell_local(&hinv[(size_t)cell * 9], sx0, sy0, x0, y0, loc[cell]);
+    }
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (int y = 0; y < Hh; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int o = owner[(size_t)y * W + x];
+            if (o < 0) continue;
+            stats[0]++;
+            int Xe, Ye, Xf, Yf;
+            cell_coord(&hinv[(size_t)o * 9], x, y, Xe, Ye);
+            const bool ok = cell_coord_fast(loc[o], x, y, Xf, Yf);
+            if (ok) { stats[1]++; if (Xf != Xe || Yf != Ye) stats[2]++; }
+            // error of the float32 evaluation itself
+            const double* H = &hinv[(size_t)o * 9];
+            const double den = H[6] * x + H[7] * y + H[8];
+            const double ux = (H[0] * x + H[1] * y + H[2]) / den, uy = (H[3] * x + H[4] * y + H[5]) / den;
+            const CellLocal& L = loc[o];
+            const float xf = (float)(x - L.cx), yf = (float)(y - L.cy);
+            const float d = (float)((double)L.g * xf + ((double)L.h * yf + 1.0));
+            const float nx = (float)((double)L.a0 * xf + ((double)L.a1 * yf + (double)L.a2));
+            const float ny = (float)((double)L.b0 * xf + ((double)L.b1 * yf + (double)L.b2));
+            const float r32 = 32.0f / d;
+            const double ex = fabs((double)(nx * r32) - 32.0 * (ux - L.sx0));
+            const double ey = fabs((double)(ny * r32) - 32.0 * (uy - L.sy0));
+            const long long e = (long long)(fmax(ex, ey) * 1e9);
+            if (e > stats[3]) stats[3] = e;
+        }
+}

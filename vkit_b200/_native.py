@@ -142,7 +142,7 @@ def _declare(lib):
     lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32,
-                                   i32, vp]
+                                   i32, i32, i32, i32, vp]
     lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
     i64 = ctypes.c_int64

@@ -459,9 +459,84 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
 
 // ============================================================================================
 // Fused remap.  Block = 256 threads = 8 warps on one 32 x 32 dst tile; warp w owns rows
-// 4w..4w+3, lane = column.  Per row the owner cell is the maximum cell index among the tile's
-// candidate cells whose coverage bit for this pixel is set.
+// 4w..4w+3, lane = column.
+//
+//   prologue  the tile's candidate cells (<= VKB_TILE_CAP) are staged in shared memory: bbox,
+//             float64 inverse homography, and its float32 re-centred form (CellLocal);
+//   owner     lane-parallel: lane i fetches candidate i's coverage words for the warp's 4 rows
+//             (shifted to the tile's columns), a ballot keeps the candidates that touch the
+//             band, and each survivor is broadcast with shuffles; every pixel keeps the
+//             maximum cell index whose coverage bit is set (= last writer in row-major order);
+//   coords    float32 fast path with a proven error band, float64 path for the <1% of pixels
+//             that sit next to a rounding boundary (vkb_math.cuh);
+//   gather    cv::remap's fixed-point bilinear for Image (C channels), Mask and ScoreMap.
 // ============================================================================================
+template <int C>
+__device__ __forceinline__ void sample_u8(const uint8_t* __restrict__ src, int h, int w, int X, int Y,
+                                          uint8_t* __restrict__ dst) {
+    const int x0 = clamp_short(X >> kInterBits);
+    const int y0 = clamp_short(Y >> kInterBits);
+    const int fx = X & (kInterTab - 1);
+    const int fy = Y & (kInterTab - 1);
+    const long long pitch = (long long)w * C;
+    const uint8_t* r0 = src + (long long)y0 * pitch + (long long)x0 * C;
+    const uint8_t* r1 = r0 + pitch;
+    int p00[C], p01[C], p10[C], p11[C];
+    if ((unsigned)x0 < (unsigned)(w - 1) && (unsigned)y0 < (unsigned)(h - 1)) {  // interior
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            p00[c] = __ldg(r0 + c);
+            p01[c] = __ldg(r0 + C + c);
+            p10[c] = __ldg(r1 + c);
+            p11[c] = __ldg(r1 + C + c);
+        }
+    } else {
+        const bool in_x0 = (unsigned)x0 < (unsigned)w, in_x1 = (unsigned)(x0 + 1) < (unsigned)w;
+        const bool in_y0 = (unsigned)y0 < (unsigned)h, in_y1 = (unsigned)(y0 + 1) < (unsigned)h;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            p00[c] = (in_y0 && in_x0) ? r0[c] : 0;
+            p01[c] = (in_y0 && in_x1) ? r0[C + c] : 0;
+            p10[c] = (in_y1 && in_x0) ? r1[c] : 0;
+            p11[c] = (in_y1 && in_x1) ? r1[C + c] : 0;
+        }
+    }
+    const int gx = kInterTab - fx, gy = kInterTab - fy;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int a = gx * p00[c] + fx * p01[c];
+        const int b = gx * p10[c] + fx * p11[c];
+        dst[c] = (uint8_t)((gy * a + fy * b + 512) >> 10);
+    }
+}
+
+struct RemapShared {
+    double H[VKB_TILE_CAP][9];
+    CellLocal loc[VKB_TILE_CAP];
+    int box[VKB_TILE_CAP][4];
+    int cell[VKB_TILE_CAP];
+};
+
+// coverage of one cell on row y, restricted to the 32 columns starting at tx0
+__device__ __forceinline__ uint32_t cell_row_window(const uint32_t* __restrict__ cell_masks,
+                                                    const int32_t* __restrict__ lat, int cols,
+                                                    int ccols, int cell, bool flagged, int bx0,
+                                                    int by0, int y, int tx0) {
+    if (!flagged) {
+        const uint32_t w = cell_masks[(size_t)cell * VKB_CELL_MASK_WORDS + (y - by0)];
+        const int rel = tx0 - bx0;  // in (-32, 32) because the boxes overlap
+        return rel >= 0 ? (w >> rel) : (w << (-rel));
+    }
+    const int r = cell / ccols, c = cell - r * ccols;
+    const int i00 = r * cols + c, i01 = i00 + 1, i11 = i00 + cols + 1, i10 = i00 + cols;
+    const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
+    const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
+    uint32_t bits = 0;
+    poly_row_mask<4>(px, py, y, tx0, &bits, 1);
+    return bits;
+}
+
+template <int C, bool MASK, bool SCORE>
 __global__ void __launch_bounds__(256) grid_remap_kernel(
     const vkb_grid_page* __restrict__ pages, const vkb_planes* __restrict__ planes,
     int c_max, int t_max, const vkb_grid_meta* __restrict__ meta, const double* __restrict__ hinv,
@@ -469,105 +544,124 @@ __global__ void __launch_bounds__(256) grid_remap_kernel(
     const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
     const int32_t* __restrict__ lattice_i, int p_max) {
     const int page = blockIdx.z;
-    const vkb_grid_meta mt = meta[page];
-    const int tiles_x = (mt.dst_w + VKB_TILE - 1) / VKB_TILE;
-    const int tiles_y = (mt.dst_h + VKB_TILE - 1) / VKB_TILE;
+    const int dst_h = meta[page].dst_h, dst_w = meta[page].dst_w;
+    const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
+    const int tiles_y = (dst_h + VKB_TILE - 1) / VKB_TILE;
     if ((int)blockIdx.x >= tiles_x || (int)blockIdx.y >= tiles_y) return;
 
-    __shared__ vkb_planes pl;
-    __shared__ double sH[VKB_TILE_CAP][9];
-    __shared__ int sBox[VKB_TILE_CAP][4];
-    __shared__ int sCell[VKB_TILE_CAP];
-
+    __shared__ RemapShared sm;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
     const int count = tile_count[(size_t)page * t_max + tile];
     const bool fast = count <= VKB_TILE_CAP;
-    {
-        const int* src = reinterpret_cast<const int*>(planes + page);
-        int* dst = reinterpret_cast<int*>(&pl);
-        for (int i = tid; i < (int)(sizeof(vkb_planes) / 4); i += 256) dst[i] = src[i];
-    }
-    const vkb_grid_page& pg = pages[page];
-    const int ccols = pg.cols - 1;
-    const int C = (pg.rows - 1) * ccols;
-    if (fast) {
-        for (int i = tid; i < count * 9; i += 256) {
-            const int s = i / 9, k = i - s * 9;
-            const int cell = tile_cells[((size_t)page * t_max + tile) * VKB_TILE_CAP + s];
-            sH[s][k] = hinv[((size_t)page * c_max + cell) * 9 + k];
-        }
-        for (int i = tid; i < count * 4; i += 256) {
-            const int s = i >> 2, k = i & 3;
-            const int cell = tile_cells[((size_t)page * t_max + tile) * VKB_TILE_CAP + s];
-            sBox[s][k] = cell_box[((size_t)page * c_max + cell) * 4 + k];
-            if (k == 0) sCell[s] = cell;
-        }
+    const vkb_planes pl = planes[page];
+    const int cols = pages[page].cols, rows = pages[page].rows;
+    const int src_h = pl.src_h, src_w = pl.src_w, grid = pages[page].grid_size;
+    const int ccols = cols - 1;
+    const int n_cells = (rows - 1) * ccols;
+    const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
+    const uint32_t* page_masks = cell_masks + (size_t)page * c_max * VKB_CELL_MASK_WORDS;
+    const int32_t* page_box = cell_box + (size_t)page * c_max * 4;
+    const double* page_hinv = hinv + (size_t)page * c_max * 9;
+
+    if (fast && tid < count) {
+        const int cell = tile_cells[((size_t)page * t_max + tile) * VKB_TILE_CAP + tid];
+        const int4 b = *reinterpret_cast<const int4*>(page_box + (size_t)cell * 4);
+        sm.box[tid][0] = b.x; sm.box[tid][1] = b.y; sm.box[tid][2] = b.z; sm.box[tid][3] = b.w;
+        sm.cell[tid] = cell;
+        double H[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H[k] = page_hinv[(size_t)cell * 9 + k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sm.H[tid][k] = H[k];
+        const int r = cell / ccols, c = cell - r * ccols;
+        make_cell_local(H, lattice_coord(c, src_w, grid), lattice_coord(r, src_h, grid), b.x, b.y,
+                        sm.loc[tid]);
     }
     __syncthreads();
 
-    const int warp = tid >> 5, lane = tid & 31;
     const int tx0 = blockIdx.x * VKB_TILE;
     const int x = tx0 + lane;
-    const int ry0 = blockIdx.y * VKB_TILE + warp * 4;  // first of this warp's 4 rows
-    const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
+    const int ry0 = blockIdx.y * VKB_TILE + warp * 4;
+    if (ry0 >= dst_h) return;
 
+    // ---- owner ---------------------------------------------------------------------------
     int key[4] = {-1, -1, -1, -1};
-    const int n_cand = fast ? count : C;
-    for (int s = 0; s < n_cand; ++s) {
-        int bx0, by0, bx1, by1, cell;
-        if (fast) {
-            bx0 = sBox[s][0]; by0 = sBox[s][1]; bx1 = sBox[s][2]; by1 = sBox[s][3];
-            cell = sCell[s];
-        } else {
-            cell = s;
-            const int32_t* b = cell_box + ((size_t)page * c_max + cell) * 4;
-            bx0 = b[0]; by0 = b[1]; bx1 = b[2]; by1 = b[3];
-        }
-        const bool flagged = (bx1 & 0x40000000) != 0;
-        bx1 &= 0x3FFFFFFF;
-        if (by1 < ry0 || by0 > ry0 + 3 || bx1 < tx0 || bx0 > tx0 + 31) continue;  // warp uniform
-        const int k = fast ? ((cell << 6) | s) : (cell << 6);
-        if (!flagged) {
-            const uint32_t* mw = cell_masks + ((size_t)page * c_max + cell) * VKB_CELL_MASK_WORDS;
-            const int rel = tx0 - bx0;  // in (-32, 32)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int y = ry0 + j;
-                if (y < by0 || y > by1) continue;
-                const uint32_t w = mw[y - by0];
-                const uint32_t bits = rel >= 0 ? (w >> rel) : (w << (-rel));
-                if ((bits >> lane) & 1u) key[j] = max(key[j], k);
+    const int n_cand = fast ? count : n_cells;
+    for (int base = 0; base < n_cand; base += 32) {
+        const int s = base + lane;
+        uint32_t win[4] = {0u, 0u, 0u, 0u};
+        int my_key = -1;
+        if (s < n_cand) {
+            int bx0, by0, bx1, by1, cell;
+            if (fast) {
+                bx0 = sm.box[s][0]; by0 = sm.box[s][1]; bx1 = sm.box[s][2]; by1 = sm.box[s][3];
+                cell = sm.cell[s];
+            } else {
+                const int4 b = *reinterpret_cast<const int4*>(page_box + (size_t)s * 4);
+                bx0 = b.x; by0 = b.y; bx1 = b.z; by1 = b.w;
+                cell = s;
             }
-        } else {
-            const int r = cell / ccols, c = cell - r * ccols;
-            const int i00 = r * pg.cols + c, i01 = i00 + 1, i11 = i00 + pg.cols + 1, i10 = i00 + pg.cols;
-            const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
-            const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
+            const bool flagged = (bx1 & 0x40000000) != 0;
+            bx1 &= 0x3FFFFFFF;
+            if (!(by1 < ry0 || by0 > ry0 + 3 || bx1 < tx0 || bx0 > tx0 + 31)) {
+                my_key = fast ? ((cell << 6) | s) : (cell << 6);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int y = ry0 + j;
+                    if (y >= by0 && y <= by1)
+                        win[j] = cell_row_window(page_masks, lat, cols, ccols, cell, flagged, bx0,
+                                                 by0, y, tx0);
+                }
+            }
+        }
+        unsigned active = __ballot_sync(0xffffffffu, (win[0] | win[1] | win[2] | win[3]) != 0u);
+        while (active) {
+            const int src_lane = __ffs(active) - 1;
+            active &= active - 1;
+            const int k = __shfl_sync(0xffffffffu, my_key, src_lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int y = ry0 + j;
-                if (y < by0 || y > by1) continue;
-                uint32_t bits = 0;
-                poly_row_mask<4>(px, py, y, tx0, &bits, 1);
-                if ((bits >> lane) & 1u) key[j] = max(key[j], k);
+                const uint32_t w = __shfl_sync(0xffffffffu, win[j], src_lane);
+                key[j] = max(key[j], ((w >> lane) & 1u) ? k : -1);
             }
         }
     }
+    if (x >= dst_w) return;
 
+    // ---- coordinates + gather ------------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int y = ry0 + j;
-        if (y >= mt.dst_h || x >= mt.dst_w) continue;
+        if (y >= dst_h) break;
         int X = 0, Y = 0;
         if (key[j] >= 0) {
             if (fast) {
-                cell_coord(sH[key[j] & 63], x, y, X, Y);
+                const int slot = key[j] & 63;
+                if (!cell_coord_fast(sm.loc[slot], x, y, X, Y)) cell_coord(sm.H[slot], x, y, X, Y);
             } else {
-                cell_coord(hinv + ((size_t)page * c_max + (key[j] >> 6)) * 9, x, y, X, Y);
+                cell_coord(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, X, Y);
             }
         }
-        sample_and_store(pl, x, y, X, Y);
+        const long long di = (long long)y * dst_w + x;
+        if (C > 0) {
+            uint8_t px[C > 0 ? C : 1];
+            sample_u8<(C > 0 ? C : 1)>(pl.src_image, src_h, src_w, X, Y, px);
+            uint8_t* d = pl.dst_image + di * C;
+            if (C == 4) {
+                *reinterpret_cast<uchar4*>(d) = make_uchar4(px[0], px[1], px[2], px[3 % (C > 0 ? C : 1)]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = px[c];
+            }
+        }
+        if (MASK) {
+            uint8_t m[1];
+            sample_u8<1>(pl.src_mask, src_h, src_w, X, Y, m);
+            pl.dst_mask[di] = m[0];
+        }
+        if (SCORE) pl.dst_score[di] = bilinear_f32(pl.src_score, src_h, src_w, src_w, X, Y);
     }
 }
 
@@ -764,16 +858,42 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               const double* hinv, const int32_t* cell_box,
                               const uint32_t* cell_masks, const int32_t* tile_count,
                               const uint16_t* tile_cells, int32_t max_dst_h, int32_t max_dst_w,
+                              int32_t image_channels, int32_t has_mask, int32_t has_score,
                               void* stream) {
     VKB_REQUIRE(pages && planes && lattice_i && meta && hinv && cell_box && cell_masks
                     && tile_count && tile_cells, "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(max_dst_h > 0 && max_dst_w > 0, "empty destination");
+    VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
+                    || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
+    VKB_REQUIRE(image_channels || has_mask || has_score, "nothing to remap");
     dim3 grid((max_dst_w + VKB_TILE - 1) / VKB_TILE, (max_dst_h + VKB_TILE - 1) / VKB_TILE, n_pages);
     VKB_REQUIRE((long long)grid.x * grid.y <= t_max, "t_max smaller than the tile grid");
-    grid_remap_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        pages, planes, c_max, t_max, meta, hinv, cell_box, cell_masks, tile_count, tile_cells,
-        lattice_i, p_max);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
+    grid_remap_kernel<CH, M, S><<<grid, 256, 0, st>>>(pages, planes, c_max, t_max, meta, hinv, \
+                                                      cell_box, cell_masks, tile_count,        \
+                                                      tile_cells, lattice_i, p_max)
+    const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
+    switch (key) {
+        case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;
+        case 0 * 4 + 2: VKB_LAUNCH_REMAP(0, true, false); break;
+        case 0 * 4 + 3: VKB_LAUNCH_REMAP(0, true, true); break;
+        case 1 * 4 + 0: VKB_LAUNCH_REMAP(1, false, false); break;
+        case 1 * 4 + 1: VKB_LAUNCH_REMAP(1, false, true); break;
+        case 1 * 4 + 2: VKB_LAUNCH_REMAP(1, true, false); break;
+        case 1 * 4 + 3: VKB_LAUNCH_REMAP(1, true, true); break;
+        case 3 * 4 + 0: VKB_LAUNCH_REMAP(3, false, false); break;
+        case 3 * 4 + 1: VKB_LAUNCH_REMAP(3, false, true); break;
+        case 3 * 4 + 2: VKB_LAUNCH_REMAP(3, true, false); break;
+        case 3 * 4 + 3: VKB_LAUNCH_REMAP(3, true, true); break;
+        case 4 * 4 + 0: VKB_LAUNCH_REMAP(4, false, false); break;
+        case 4 * 4 + 1: VKB_LAUNCH_REMAP(4, false, true); break;
+        case 4 * 4 + 2: VKB_LAUNCH_REMAP(4, true, false); break;
+        case 4 * 4 + 3: VKB_LAUNCH_REMAP(4, true, true); break;
+        default: VKB_REQUIRE(false, "unsupported container combination");
+    }
+#undef VKB_LAUNCH_REMAP
     return check_launch("grid_remap_kernel");
 }
 

@@ -151,6 +151,14 @@ VKB_HD void perspective_coord(const double* __restrict__ Mi, int x, int y, int& 
 // Grid remap: source coordinate of dst pixel (x, y) under a cell's inverse homography H
 // (double), stored as float32 like the reference's map_x/map_y, then quantised like cv::remap.
 // (vkit grid_rendering/type.py:231-256 followed by grid_blender.py:60.)
+VKB_HD int map_to_fixed_f(float m) {
+    // float * 32 is exact (or overflows to inf); round half to even; NaN / out of range ->
+    // a coordinate far outside every image, like cvRound's INT_MIN.
+    const float t = m * 32.0f;
+    if (!(fabsf(t) < 2.0e9f)) return INT32_MIN;
+    return (int)rintf(t);
+}
+
 VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& Y) {
     const double xd = (double)x, yd = (double)y;
     const double den = fma(H[6], xd, fma(H[7], yd, H[8]));
@@ -163,8 +171,88 @@ VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& 
     }
     const float mx = (float)(nx / den);
     const float my = (float)(ny / den);
-    X = map_to_fixed(mx);
-    Y = map_to_fixed(my);
+    X = map_to_fixed_f(mx);
+    Y = map_to_fixed_f(my);
+}
+
+// ---------------------------------------------------------------------------------------
+// Error-bounded float32 evaluation of cell_coord.
+//
+// The source lattice is integer, so inside a cell the source coordinate is  u = sx0 + du  with
+// du in roughly [-2, g+2].  du is evaluated in float32 from the homography re-centred on the
+// cell (dst bbox corner -> offset from the src corner): magnitudes stay below ~64, so the
+// absolute error of 32*du is far below the 1/32 px quantum.  The reference rounds twice
+// (float64 -> float32 map value, then round(32 * map)); both roundings can only change the
+// result when 32*u lies within  32*halfulp_f32(u) + slack  of a half integer.  Outside that
+// band the float32 result is provably the reference's; inside it the caller falls back to the
+// float64 path.  kFastSlack bounds the float32 evaluation error of 32*du (validated in
+// tests/test_hostsim.py: observed max error is > 8x smaller).
+// ---------------------------------------------------------------------------------------
+struct CellLocal {
+    float a0, a1, a2;  // numerator of du_x
+    float b0, b1, b2;  // numerator of du_y
+    float g, h;        // denominator g*x' + h*y' + 1
+    int sx0, sy0;      // src corner of the cell
+    int cx, cy;        // dst reference point (bbox corner): x' = x - cx
+};
+
+constexpr float kFastSlack = 2.0e-3f;  // in units of 1/32 px
+
+VKB_HD void make_cell_local(const double* __restrict__ H, int sx0, int sy0, int cx, int cy,
+                            CellLocal& L) {
+    const double ax0 = H[0] - sx0 * H[6], ax1 = H[1] - sx0 * H[7], ax2 = H[2] - sx0 * H[8];
+    const double ay0 = H[3] - sy0 * H[6], ay1 = H[4] - sy0 * H[7], ay2 = H[5] - sy0 * H[8];
+    const double d0 = H[6] * cx + H[7] * cy + H[8];
+    const double inv = 1.0 / d0;  // inf / nan when degenerate: the fast path then always fails
+    L.a0 = (float)(ax0 * inv);
+    L.a1 = (float)(ax1 * inv);
+    L.a2 = (float)((ax0 * cx + ax1 * cy + ax2) * inv);
+    L.b0 = (float)(ay0 * inv);
+    L.b1 = (float)(ay1 * inv);
+    L.b2 = (float)((ay0 * cx + ay1 * cy + ay2) * inv);
+    L.g = (float)(H[6] * inv);
+    L.h = (float)(H[7] * inv);
+    L.sx0 = sx0;
+    L.sy0 = sy0;
+    L.cx = cx;
+    L.cy = cy;
+}
+
+// 2^(e-19) for |u| in [2^e, 2^(e+1)): 32 * half ulp of float32(u); ~0 for |u| < 2^-100.
+VKB_HD float half_ulp_times_32(float u) {
+    union { float f; uint32_t i; } v;
+    v.f = u;
+    const uint32_t e = v.i & 0x7f800000u;
+    v.i = e > (19u << 23) ? e - (19u << 23) : 0u;
+    return v.f;
+}
+
+VKB_HD bool fast_axis(float num, float r32, int s0, int& X) {
+    const float f = VKB_FMUL(num, r32);  // 32 * du
+    const float fl = floorf(f);
+    const float frac = f - fl;  // exact
+    const float u = (float)s0 + f * 0.03125f;
+    const float margin = half_ulp_times_32(u) + kFastSlack;
+    X = s0 * 32 + (int)fl + (frac > 0.5f ? 1 : 0);
+    return fabsf(frac - 0.5f) > margin && fabsf(f) < 1.0e6f;
+}
+
+VKB_HD bool cell_coord_fast(const CellLocal& L, int x, int y, int& X, int& Y) {
+    const float xf = (float)(x - L.cx), yf = (float)(y - L.cy);
+#if defined(__CUDA_ARCH__)
+    const float d = __fmaf_rn(L.g, xf, __fmaf_rn(L.h, yf, 1.0f));
+    const float nx = __fmaf_rn(L.a0, xf, __fmaf_rn(L.a1, yf, L.a2));
+    const float ny = __fmaf_rn(L.b0, xf, __fmaf_rn(L.b1, yf, L.b2));
+    const float r32 = __fdividef(32.0f, d);
+#else
+    const float d = (float)((double)L.g * xf + ((double)L.h * yf + 1.0));
+    const float nx = (float)((double)L.a0 * xf + ((double)L.a1 * yf + (double)L.a2));
+    const float ny = (float)((double)L.b0 * xf + ((double)L.b1 * yf + (double)L.b2));
+    const float r32 = 32.0f / d;
+#endif
+    const bool okx = fast_axis(nx, r32, L.sx0, X);
+    const bool oky = fast_axis(ny, r32, L.sy0, Y);
+    return okx && oky;  // NaN / inf anywhere -> false
 }
 
 // ---------------------------------------------------------------------------------------

@@ -86,13 +86,21 @@ class GridBatch:
     def remap(self, planes: np.ndarray):
         """planes: structured array (PLANES_DTYPE), one record per page, device pointers."""
         self.build()
-        planes_dev = dv.upload_structs(np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE))
+        planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
+        channels = int(planes['image_channels'][0])
+        has_mask = int(planes['src_mask'][0] != 0)
+        has_score = int(planes['src_score'][0] != 0)
+        if ((planes['image_channels'] != channels).any()
+                or ((planes['src_mask'] != 0) != bool(has_mask)).any()
+                or ((planes['src_score'] != 0) != bool(has_score)).any()):
+            raise ValueError('all pages of one remap call must carry the same containers')
+        planes_dev = dv.upload_structs(planes)
         nv.check(self.lib.vkb_grid_remap(
             dv.ptr(self.pages_dev), dv.ptr(planes_dev), self.n, self.p_max, self.c_max, self.t_max,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv),
             dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
-            dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, dv.stream_ptr()),
-            'vkb_grid_remap')
+            dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, channels, has_mask,
+            has_score, dv.stream_ptr()), 'vkb_grid_remap')
         return planes_dev
 
     def transform_points(self, page: int, xy: np.ndarray, cell_rc: np.ndarray) -> np.ndarray:
