@@ -347,7 +347,19 @@ VKB_HD int ceil_div_pos(int num, int den) {  // den > 0, any num; ceil(num/den)
     return (num >= 0) ? (num + den - 1) / den : -((-num) / den);
 }
 
+// floor(num / den) for 0 <= num < 2^23, 0 < den < 2^23 through a float reciprocal and one
+// correction step (exact; an integer division costs ~5x more issue slots on the GPU).
+VKB_HD int floor_div_small(int num, int den, float rcp) {
+    int q = (int)((float)num * rcp);
+    const int r = num - q * den;
+    q += (r >= den) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
 // pixels of the Bresenham line (ax,ay)-(bx,by) that lie on row y: [xlo, xhi] or empty.
+// cv::LineIterator, 8-connected, left to right: after j major steps the minor coordinate is
+// floor((2*minor*j + major - 1) / (2*major)).
 VKB_HD bool line_row_run(int ax, int ay, int bx, int by, int y, int& xlo, int& xhi) {
     if (ax > bx) {  // left to right
         int t = ax; ax = bx; bx = t;
@@ -359,19 +371,28 @@ VKB_HD bool line_row_run(int ax, int ay, int bx, int by, int y, int& xlo, int& x
     const int dy = dys >= 0 ? dys : -dys;
     const int k = (y - ay) * sy;  // rows travelled from the start point
     if (k < 0 || k > dy) return false;
-    if (dy > dx) {  // steep: one pixel per row
-        const int kx = (2 * dx * k + dy - 1) / (2 * dy);
-        xlo = xhi = ax + kx;
-        return true;
-    }
     if (dy == 0) {  // horizontal (or a single point)
         xlo = ax;
         xhi = bx;
         return true;
     }
-    int jlo = (k == 0) ? 0 : ceil_div_pos(2 * dx * k - dx + 1, 2 * dy);
-    int jhi = ceil_div_pos(2 * dx * (k + 1) - dx + 1, 2 * dy) - 1;
-    if (jlo < 0) jlo = 0;
+    const int den = 2 * dy;
+    const bool small = dx < 2048 && dy < 2048;  // numerators below 2^23
+    const float rcp = 1.0f / (float)den;
+    if (dy > dx) {  // steep: one pixel per row
+        const int num = 2 * dx * k + dy - 1;
+        const int kx = small ? floor_div_small(num, den, rcp) : num / den;
+        xlo = xhi = ax + kx;
+        return true;
+    }
+    // shallow: ceil(n / den) = floor((n + den - 1) / den) for n >= 0
+    int jlo = 0;
+    if (k > 0) {
+        const int n = 2 * dx * k - dx + 1;  // > 0 because dx >= dy >= 1 and k >= 1
+        jlo = small ? floor_div_small(n + den - 1, den, rcp) : ceil_div_pos(n, den);
+    }
+    const int n2 = 2 * dx * (k + 1) - dx + 1;
+    int jhi = (small ? floor_div_small(n2 + den - 1, den, rcp) : ceil_div_pos(n2, den)) - 1;
     if (jhi > dx) jhi = dx;
     if (jlo > jhi) return false;
     xlo = ax + jlo;
@@ -391,12 +412,20 @@ VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t
         int lo, hi;
         if (line_row_run(x0, y0, x1, y1, y, lo, hi)) set_bits(words, nwords, lo - bx0, hi - bx0);
         if (y0 == y1) continue;
-        const long long dxf = ((long long)(x1 - x0) * 65536) / (long long)(y1 - y0);  // trunc
-        int ya, yb;
-        long long xa;
-        if (y0 < y1) { ya = y0; yb = y1; xa = (long long)x0 * 65536; }
-        else { ya = y1; yb = y0; xa = (long long)x1 * 65536; }
-        if (ya <= y && y < yb) cross[ncross++] = xa + dxf * (long long)(y - ya);
+        const int ya = y0 < y1 ? y0 : y1, yb = y0 < y1 ? y1 : y0;
+        if (!(ya <= y && y < yb)) continue;
+        const int xs = y0 < y1 ? x0 : x1;
+        const int ddx = x1 - x0, ddy = y1 - y0;
+        long long c;
+        if (ddx > -16384 && ddx < 16384) {
+            // (ddx << 16) / ddy truncating, all in 32 bits; |dxf * (y - ya)| <= |ddx| << 16
+            const int dxf = (ddx * 65536) / ddy;
+            c = (long long)xs * 65536 + (long long)(dxf * (y - ya));
+        } else {
+            const long long dxf = ((long long)ddx * 65536) / (long long)ddy;
+            c = (long long)xs * 65536 + dxf * (long long)(y - ya);
+        }
+        cross[ncross++] = c;
     }
     // insertion sort (N is 4 for lattice cells)
     for (int i = 1; i < ncross; ++i) {
