@@ -131,6 +131,7 @@ typedef struct vkb_grid_meta {
 /* Fixed per-cell budget of coverage-mask words; cells that need more are rasterised on the
  * fly by the remap kernel. */
 #define VKB_CELL_MASK_WORDS 32
+#define VKB_CELL_LOCAL_BYTES 48
 #define VKB_TILE 32     /* dst tile edge of the remap kernel */
 #define VKB_TILE_CAP 64 /* candidate cells kept per tile before the slow path is used */
 
@@ -151,13 +152,15 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
  *   hfwd:       n_pages x c_max x 9 doubles or NULL (forward maps, needed by vkb_grid_points)
  *   cell_box:   n_pages x c_max x 4 int32 (x0, y0, x1, y1); bit 30 of x1 set = coverage of
  *               this cell exceeds the mask budget and is rasterised on the fly by the remap
+ *   cell_local: n_pages x c_max x VKB_CELL_LOCAL_BYTES bytes (float32 re-centred inverse maps
+ *               for the remap kernel's error-bounded fast path, opaque to the caller)
  *   cell_masks: n_pages x c_max x VKB_CELL_MASK_WORDS uint32
  *   tile_count: n_pages x t_max int32 (zeroed by this call)
  *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16 */
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
                    int32_t t_max, const int32_t* lattice_i, vkb_grid_meta* meta, double* hinv,
-                   double* hfwd, int32_t* cell_box, uint32_t* cell_masks, int32_t* tile_count,
-                   uint16_t* tile_cells, void* stream);
+                   double* hfwd, int32_t* cell_box, void* cell_local, uint32_t* cell_masks,
+                   int32_t* tile_count, uint16_t* tile_cells, void* stream);
 
 /* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
  * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
@@ -167,7 +170,7 @@ int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, i
 int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
                    int32_t p_max, int32_t c_max, int32_t t_max, const int32_t* lattice_i,
                    const vkb_grid_meta* meta, const double* hinv, const int32_t* cell_box,
-                   const uint32_t* cell_masks, const int32_t* tile_count,
+                   const void* cell_local, const uint32_t* cell_masks, const int32_t* tile_count,
                    const uint16_t* tile_cells, int32_t max_dst_h, int32_t max_dst_w,
                    int32_t image_channels, int32_t has_mask, int32_t has_score, void* stream);
 

@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max, int t_max,
     const int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta,
     double* __restrict__ hinv, double* __restrict__ hfwd, int32_t* __restrict__ cell_box,
-    int32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_cells) {
+    CellLocal* __restrict__ cell_local, int32_t* __restrict__ tile_count,
+    uint16_t* __restrict__ tile_cells) {
     const int page = blockIdx.y;
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
@@ -403,6 +404,15 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     box[1] = y0;
     box[2] = x1;
     box[3] = y1;
+    // float32 re-centred form of the inverse map for the remap kernel's fast path
+    {
+        double Hi[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Hi[i] = ho[i];
+        CellLocal L;
+        make_cell_local(Hi, (int)sx0, (int)sy0, x0, y0, L);
+        cell_local[(size_t)page * c_max + cell] = L;
+    }
 
     // bin into dst tiles
     const int tiles_x = (meta[page].dst_w + VKB_TILE - 1) / VKB_TILE;
@@ -433,7 +443,8 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (cell >= C) return;
     const int lane = threadIdx.x & 31;
-    const int r = cell / ccols, c = cell - r * ccols;
+    const int r = floor_div_small(cell, ccols, __fdividef(1.0f, (float)ccols));
+    const int c = cell - r * ccols;
     const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
     const int i00 = r * pg.cols + c, i01 = i00 + 1, i11 = i00 + pg.cols + 1, i10 = i00 + pg.cols;
     const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
@@ -478,11 +489,11 @@ __device__ __forceinline__ void sample_u8(const uint8_t* __restrict__ src, int h
     const int y0 = clamp_short(Y >> kInterBits);
     const int fx = X & (kInterTab - 1);
     const int fy = Y & (kInterTab - 1);
-    const long long pitch = (long long)w * C;
-    const uint8_t* r0 = src + (long long)y0 * pitch + (long long)x0 * C;
-    const uint8_t* r1 = r0 + pitch;
+    const int pitch = w * C;  // a page plane is < 2 GiB (checked by the launcher)
     int p00[C], p01[C], p10[C], p11[C];
     if ((unsigned)x0 < (unsigned)(w - 1) && (unsigned)y0 < (unsigned)(h - 1)) {  // interior
+        const uint8_t* r0 = src + (y0 * pitch + x0 * C);
+        const uint8_t* r1 = r0 + pitch;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             p00[c] = __ldg(r0 + c);
@@ -493,6 +504,8 @@ __device__ __forceinline__ void sample_u8(const uint8_t* __restrict__ src, int h
     } else {
         const bool in_x0 = (unsigned)x0 < (unsigned)w, in_x1 = (unsigned)(x0 + 1) < (unsigned)w;
         const bool in_y0 = (unsigned)y0 < (unsigned)h, in_y1 = (unsigned)(y0 + 1) < (unsigned)h;
+        const uint8_t* r0 = src + ((long long)y0 * pitch + (long long)x0 * C);
+        const uint8_t* r1 = r0 + pitch;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             p00[c] = (in_y0 && in_x0) ? r0[c] : 0;
@@ -510,23 +523,23 @@ __device__ __forceinline__ void sample_u8(const uint8_t* __restrict__ src, int h
     }
 }
 
+static_assert(sizeof(CellLocal) == VKB_CELL_LOCAL_BYTES, "CellLocal layout is part of the ABI");
+
 struct RemapShared {
-    double H[VKB_TILE_CAP][9];
     CellLocal loc[VKB_TILE_CAP];
     int box[VKB_TILE_CAP][4];
     int cell[VKB_TILE_CAP];
 };
 
-// coverage of one cell on row y, restricted to the 32 columns starting at tx0
-__device__ __forceinline__ uint32_t cell_row_window(const uint32_t* __restrict__ cell_masks,
-                                                    const int32_t* __restrict__ lat, int cols,
-                                                    int ccols, int cell, bool flagged, int bx0,
-                                                    int by0, int y, int tx0) {
-    if (!flagged) {
-        const uint32_t w = cell_masks[(size_t)cell * VKB_CELL_MASK_WORDS + (y - by0)];
-        const int rel = tx0 - bx0;  // in (-32, 32) because the boxes overlap
-        return rel >= 0 ? (w >> rel) : (w << (-rel));
-    }
+// Rare paths are kept out of line so the hot loop stays small (instruction cache).
+__device__ __noinline__ void cell_coord_exact(const double* __restrict__ H, int x, int y, int* X,
+                                              int* Y) {
+    cell_coord(H, x, y, *X, *Y);
+}
+
+// coverage of one over-budget cell on row y, restricted to the 32 columns starting at tx0
+__device__ __noinline__ uint32_t cell_row_window_slow(const int32_t* __restrict__ lat, int cols,
+                                                      int ccols, int cell, int y, int tx0) {
     const int r = cell / ccols, c = cell - r * ccols;
     const int i00 = r * cols + c, i01 = i00 + 1, i11 = i00 + cols + 1, i10 = i00 + cols;
     const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
@@ -536,11 +549,22 @@ __device__ __forceinline__ uint32_t cell_row_window(const uint32_t* __restrict__
     return bits;
 }
 
+__device__ __forceinline__ uint32_t cell_row_window(const uint32_t* __restrict__ cell_masks,
+                                                    const int32_t* __restrict__ lat, int cols,
+                                                    int ccols, int cell, bool flagged, int bx0,
+                                                    int by0, int y, int tx0) {
+    if (flagged) return cell_row_window_slow(lat, cols, ccols, cell, y, tx0);
+    const uint32_t w = cell_masks[cell * VKB_CELL_MASK_WORDS + (y - by0)];
+    const int rel = tx0 - bx0;  // in (-32, 32) because the boxes overlap
+    return rel >= 0 ? (w >> rel) : (w << (-rel));
+}
+
 template <int C, bool MASK, bool SCORE>
-__global__ void __launch_bounds__(256) grid_remap_kernel(
+__global__ void __launch_bounds__(256, (C == 3 && !MASK && !SCORE) ? 5 : 4) grid_remap_kernel(
     const vkb_grid_page* __restrict__ pages, const vkb_planes* __restrict__ planes,
     int c_max, int t_max, const vkb_grid_meta* __restrict__ meta, const double* __restrict__ hinv,
-    const int32_t* __restrict__ cell_box, const uint32_t* __restrict__ cell_masks,
+    const int32_t* __restrict__ cell_box, const CellLocal* __restrict__ cell_local,
+    const uint32_t* __restrict__ cell_masks,
     const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
     const int32_t* __restrict__ lattice_i, int p_max) {
     const int page = blockIdx.z;
@@ -557,7 +581,7 @@ __global__ void __launch_bounds__(256) grid_remap_kernel(
     const bool fast = count <= VKB_TILE_CAP;
     const vkb_planes pl = planes[page];
     const int cols = pages[page].cols, rows = pages[page].rows;
-    const int src_h = pl.src_h, src_w = pl.src_w, grid = pages[page].grid_size;
+    const int src_h = pl.src_h, src_w = pl.src_w;
     const int ccols = cols - 1;
     const int n_cells = (rows - 1) * ccols;
     const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
@@ -570,14 +594,11 @@ __global__ void __launch_bounds__(256) grid_remap_kernel(
         const int4 b = *reinterpret_cast<const int4*>(page_box + (size_t)cell * 4);
         sm.box[tid][0] = b.x; sm.box[tid][1] = b.y; sm.box[tid][2] = b.z; sm.box[tid][3] = b.w;
         sm.cell[tid] = cell;
-        double H[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) H[k] = page_hinv[(size_t)cell * 9 + k];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) sm.H[tid][k] = H[k];
-        const int r = cell / ccols, c = cell - r * ccols;
-        make_cell_local(H, lattice_coord(c, src_w, grid), lattice_coord(r, src_h, grid), b.x, b.y,
-                        sm.loc[tid]);
+        const int4* lsrc = reinterpret_cast<const int4*>(cell_local + (size_t)page * c_max + cell);
+        int4* ldst = reinterpret_cast<int4*>(&sm.loc[tid]);
+        ldst[0] = lsrc[0];
+        ldst[1] = lsrc[1];
+        ldst[2] = lsrc[2];
     }
     __syncthreads();
 
@@ -639,12 +660,13 @@ __global__ void __launch_bounds__(256) grid_remap_kernel(
         if (key[j] >= 0) {
             if (fast) {
                 const int slot = key[j] & 63;
-                if (!cell_coord_fast(sm.loc[slot], x, y, X, Y)) cell_coord(sm.H[slot], x, y, X, Y);
+                if (!cell_coord_fast(sm.loc[slot], x, y, X, Y))
+                    cell_coord_exact(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, &X, &Y);
             } else {
-                cell_coord(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, X, Y);
+                cell_coord_exact(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, &X, &Y);
             }
         }
-        const long long di = (long long)y * dst_w + x;
+        const int di = y * dst_w + x;
         if (C > 0) {
             uint8_t px[C > 0 ? C : 1];
             sample_u8<(C > 0 ? C : 1)>(pl.src_image, src_h, src_w, X, Y, px);
@@ -835,16 +857,17 @@ extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, in
 extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                               int32_t c_max, int32_t t_max, const int32_t* lattice_i,
                               vkb_grid_meta* meta, double* hinv, double* hfwd, int32_t* cell_box,
-                              uint32_t* cell_masks, int32_t* tile_count, uint16_t* tile_cells,
-                              void* stream) {
-    VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_masks && tile_count
-                    && tile_cells, "bad arguments");
+                              void* cell_local, uint32_t* cell_masks, int32_t* tile_count,
+                              uint16_t* tile_cells, void* stream) {
+    VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_local && cell_masks
+                    && tile_count && tile_cells, "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(c_max > 0 && c_max <= 65535, "at most 65535 cells per page");
     cudaStream_t st = (cudaStream_t)stream;
     VKB_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)n_pages * t_max, st));
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
-        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
+        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box,
+        reinterpret_cast<CellLocal*>(cell_local), tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
     grid_masks_kernel<<<dim3((c_max + 3) / 4, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
@@ -856,11 +879,11 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               int32_t p_max, int32_t c_max, int32_t t_max,
                               const int32_t* lattice_i, const vkb_grid_meta* meta,
                               const double* hinv, const int32_t* cell_box,
-                              const uint32_t* cell_masks, const int32_t* tile_count,
-                              const uint16_t* tile_cells, int32_t max_dst_h, int32_t max_dst_w,
-                              int32_t image_channels, int32_t has_mask, int32_t has_score,
-                              void* stream) {
-    VKB_REQUIRE(pages && planes && lattice_i && meta && hinv && cell_box && cell_masks
+                              const void* cell_local, const uint32_t* cell_masks,
+                              const int32_t* tile_count, const uint16_t* tile_cells,
+                              int32_t max_dst_h, int32_t max_dst_w, int32_t image_channels,
+                              int32_t has_mask, int32_t has_score, void* stream) {
+    VKB_REQUIRE(pages && planes && lattice_i && meta && hinv && cell_box && cell_local && cell_masks
                     && tile_count && tile_cells, "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(max_dst_h > 0 && max_dst_w > 0, "empty destination");
@@ -871,9 +894,10 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     VKB_REQUIRE((long long)grid.x * grid.y <= t_max, "t_max smaller than the tile grid");
     cudaStream_t st = (cudaStream_t)stream;
 #define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
-    grid_remap_kernel<CH, M, S><<<grid, 256, 0, st>>>(pages, planes, c_max, t_max, meta, hinv, \
-                                                      cell_box, cell_masks, tile_count,        \
-                                                      tile_cells, lattice_i, p_max)
+    grid_remap_kernel<CH, M, S><<<grid, 256, 0, st>>>(                                         \
+        pages, planes, c_max, t_max, meta, hinv, cell_box,                                     \
+        reinterpret_cast<const CellLocal*>(cell_local), cell_masks, tile_count, tile_cells,    \
+        lattice_i, p_max)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
     switch (key) {
         case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;

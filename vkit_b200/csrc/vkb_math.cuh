@@ -26,12 +26,14 @@
 #define VKB_FSUB(a, b) __fsub_rn((a), (b))
 #define VKB_DMUL(a, b) __dmul_rn((a), (b))
 #define VKB_DADD(a, b) __dadd_rn((a), (b))
+#define VKB_FRCP_APPROX(x) __fdividef(1.0f, (x))
 #else
 #define VKB_FMUL(a, b) ((a) * (b))
 #define VKB_FADD(a, b) ((a) + (b))
 #define VKB_FSUB(a, b) ((a) - (b))
 #define VKB_DMUL(a, b) ((a) * (b))
 #define VKB_DADD(a, b) ((a) + (b))
+#define VKB_FRCP_APPROX(x) (1.0f / (x))
 #endif
 
 namespace vkb {
@@ -343,12 +345,21 @@ VKB_HD void set_bits(uint32_t* words, int nwords, int lo, int hi) {
     }
 }
 
+VKB_HD void set_bits1(uint32_t& word, int lo, int hi) {  // bits [lo, hi] of ONE word
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 31 ? 31 : hi;
+    if (lo > hi) return;
+    word |= (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+
 VKB_HD int ceil_div_pos(int num, int den) {  // den > 0, any num; ceil(num/den)
     return (num >= 0) ? (num + den - 1) / den : -((-num) / den);
 }
 
-// floor(num / den) for 0 <= num < 2^23, 0 < den < 2^23 through a float reciprocal and one
-// correction step (exact; an integer division costs ~5x more issue slots on the GPU).
+// floor(num / den) for 0 <= num < 2^23, 0 < den, QUOTIENT < 2^15, through an (approximate)
+// float reciprocal and one correction step: the estimate is off by at most one, so the result
+// is exact whatever the reciprocal's last bits are (an integer division costs ~5x more issue
+// slots on the GPU).
 VKB_HD int floor_div_small(int num, int den, float rcp) {
     int q = (int)((float)num * rcp);
     const int r = num - q * den;
@@ -378,7 +389,7 @@ VKB_HD bool line_row_run(int ax, int ay, int bx, int by, int y, int& xlo, int& x
     }
     const int den = 2 * dy;
     const bool small = dx < 2048 && dy < 2048;  // numerators below 2^23
-    const float rcp = 1.0f / (float)den;
+    const float rcp = VKB_FRCP_APPROX((float)den);
     if (dy > dx) {  // steep: one pixel per row
         const int num = 2 * dx * k + dy - 1;
         const int kx = small ? floor_div_small(num, den, rcp) : num / den;
@@ -400,6 +411,30 @@ VKB_HD bool line_row_run(int ax, int ay, int bx, int by, int y, int& xlo, int& x
     return true;
 }
 
+// 16.16 fixed-point x of the scan edge (x0,y0)-(x1,y1) at row y (cv::FillEdgeCollection):
+// x_at_ymin << 16 plus trunc(((x1 - x0) << 16) / (y1 - y0)) per row.
+VKB_HD long long scan_edge_x(int x0, int y0, int x1, int y1, int y) {
+    const int ya = y0 < y1 ? y0 : y1;
+    const int xs = y0 < y1 ? x0 : x1;
+    const int ddx = x1 - x0, ddy = y1 - y0;
+    const int adx = ddx < 0 ? -ddx : ddx, ady = ddy < 0 ? -ddy : ddy;
+    if (adx < 128 && ady < 128) {
+        // trunc((adx << 16) / ady) in two 8-bit steps so every partial quotient stays < 2^15
+        const float rcp = VKB_FRCP_APPROX((float)ady);
+        const int q1 = floor_div_small(adx * 256, ady, rcp);
+        const int r1 = adx * 256 - q1 * ady;
+        const int q = q1 * 256 + floor_div_small(r1 * 256, ady, rcp);
+        const int dxf = ((ddx < 0) != (ddy < 0)) ? -q : q;
+        return (long long)xs * 65536 + (long long)(dxf * (y - ya));
+    }
+    if (adx < 16384) {
+        const int dxf = (ddx * 65536) / ddy;  // 32-bit; |dxf * (y - ya)| <= |ddx| << 16
+        return (long long)xs * 65536 + (long long)(dxf * (y - ya));
+    }
+    const long long dxf = ((long long)ddx * 65536) / (long long)ddy;
+    return (long long)xs * 65536 + dxf * (long long)(y - ya);
+}
+
 template <int N>
 VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t* words,
                           int nwords) {
@@ -410,22 +445,13 @@ VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t
         const int j = (i + N - 1) % N;
         const int x0 = px[j], y0 = py[j], x1 = px[i], y1 = py[i];
         int lo, hi;
-        if (line_row_run(x0, y0, x1, y1, y, lo, hi)) set_bits(words, nwords, lo - bx0, hi - bx0);
+        if (line_row_run(x0, y0, x1, y1, y, lo, hi)) {
+            if (nwords == 1) set_bits1(words[0], lo - bx0, hi - bx0);
+            else set_bits(words, nwords, lo - bx0, hi - bx0);
+        }
         if (y0 == y1) continue;
         const int ya = y0 < y1 ? y0 : y1, yb = y0 < y1 ? y1 : y0;
-        if (!(ya <= y && y < yb)) continue;
-        const int xs = y0 < y1 ? x0 : x1;
-        const int ddx = x1 - x0, ddy = y1 - y0;
-        long long c;
-        if (ddx > -16384 && ddx < 16384) {
-            // (ddx << 16) / ddy truncating, all in 32 bits; |dxf * (y - ya)| <= |ddx| << 16
-            const int dxf = (ddx * 65536) / ddy;
-            c = (long long)xs * 65536 + (long long)(dxf * (y - ya));
-        } else {
-            const long long dxf = ((long long)ddx * 65536) / (long long)ddy;
-            c = (long long)xs * 65536 + dxf * (long long)(y - ya);
-        }
-        cross[ncross++] = c;
+        if (ya <= y && y < yb) cross[ncross++] = scan_edge_x(x0, y0, x1, y1, y);
     }
     // insertion sort (N is 4 for lattice cells)
     for (int i = 1; i < ncross; ++i) {
@@ -437,7 +463,13 @@ VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t
     for (int k = 0; k + 1 < ncross; k += 2) {
         const long long xl = (cross[k] + 65535) >> 16;
         const long long xr = cross[k + 1] >> 16;
-        if (xl <= xr) set_bits(words, nwords, (int)xl - bx0, (int)xr - bx0);
+        if (xl <= xr) {
+            const long long lo = xl - bx0, hi = xr - bx0;
+            const int lo_i = lo < -1 ? -1 : (lo > 1 << 20 ? 1 << 20 : (int)lo);
+            const int hi_i = hi < -1 ? -1 : (hi > 1 << 20 ? 1 << 20 : (int)hi);
+            if (nwords == 1) set_bits1(words[0], lo_i, hi_i);
+            else set_bits(words, nwords, lo_i, hi_i);
+        }
     }
 }
 

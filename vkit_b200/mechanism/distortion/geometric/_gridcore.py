@@ -74,14 +74,15 @@ class GridBatch:
         if need_forward:
             self.hfwd = dv.empty((self.n, self.c_max, 9), np.float64)
         self.cell_box = dv.empty((self.n, self.c_max, 4), np.int32)
+        self.cell_local = dv.empty((self.n, self.c_max, nv.CELL_LOCAL_BYTES), np.uint8)
         self.cell_masks = dv.empty((self.n, self.c_max, nv.CELL_MASK_WORDS), np.uint32)
         self.tile_count = dv.empty((self.n, self.t_max), np.int32)
         self.tile_cells = dv.empty((self.n, self.t_max, nv.TILE_CAP), np.uint16)
         nv.check(self.lib.vkb_grid_build(
             dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv), dv.ptr(self.hfwd),
-            dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
-            dv.ptr(self.tile_cells), dv.stream_ptr()), 'vkb_grid_build')
+            dv.ptr(self.cell_box), dv.ptr(self.cell_local), dv.ptr(self.cell_masks),
+            dv.ptr(self.tile_count), dv.ptr(self.tile_cells), dv.stream_ptr()), 'vkb_grid_build')
 
     def remap(self, planes: np.ndarray):
         """planes: structured array (PLANES_DTYPE), one record per page, device pointers."""
@@ -98,8 +99,8 @@ class GridBatch:
         nv.check(self.lib.vkb_grid_remap(
             dv.ptr(self.pages_dev), dv.ptr(planes_dev), self.n, self.p_max, self.c_max, self.t_max,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv),
-            dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
-            dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, channels, has_mask,
+            dv.ptr(self.cell_box), dv.ptr(self.cell_local), dv.ptr(self.cell_masks),
+            dv.ptr(self.tile_count), dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, channels, has_mask,
             has_score, dv.stream_ptr()), 'vkb_grid_remap')
         return planes_dev
 
