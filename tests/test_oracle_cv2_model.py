@@ -1,0 +1,113 @@
+"""oracle/cv2_model.py against the real cv2 wheel (skipped when cv2 is not importable).
+Pins the NumPy restatement of every cv2 function on the path to the installed OpenCV."""
+import math
+
+import numpy as np
+import pytest
+
+cv = pytest.importorskip('cv2')
+from oracle import cv2_model as cm  # noqa: E402
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.fixture(scope='module')
+def rng():
+    return np.random.default_rng(1)
+
+
+@pytest.mark.parametrize('channels', [None, 3, 4])
+def test_remap_u8(rng, channels):
+    shape = (97, 131) if channels is None else (97, 131, channels)
+    src = rng.integers(0, 256, shape, dtype=np.uint8)
+    map_x = rng.uniform(-5, 136, (120, 150)).astype(np.float32)
+    map_y = rng.uniform(-5, 102, (120, 150)).astype(np.float32)
+    map_x[:10, :10] = np.arange(10, dtype=np.float32)[None, :]  # exact integer coordinates
+    map_y[:10, :10] = np.arange(10, dtype=np.float32)[:, None]
+    map_x[20:30, :20] = (np.arange(20, dtype=np.float32) / 2)[None, :]  # exact half pixels
+    map_y[20:30, :20] = 7.5
+    assert _same(cm.remap_linear(src, map_x, map_y), cv.remap(src, map_x, map_y, cv.INTER_LINEAR))
+
+
+def test_remap_f32(rng):
+    src = rng.random((97, 131)).astype(np.float32)
+    map_x = rng.uniform(-5, 136, (120, 150)).astype(np.float32)
+    map_y = rng.uniform(-5, 102, (120, 150)).astype(np.float32)
+    assert _same(cm.remap_linear(src, map_x, map_y), cv.remap(src, map_x, map_y, cv.INTER_LINEAR))
+
+
+@pytest.mark.parametrize('angle', [30, 77, 200, 0.5])
+def test_warp_affine(rng, angle):
+    rad = math.radians(angle)
+    M = np.asarray([[math.cos(rad), -math.sin(rad), 40], [math.sin(rad), math.cos(rad), -10.3]],
+                   dtype=np.float32)
+    for src in (rng.integers(0, 256, (211, 173, 3), dtype=np.uint8),
+                rng.integers(0, 2, (211, 173), dtype=np.uint8),
+                rng.random((211, 173)).astype(np.float32)):
+        assert _same(cm.warp_affine(src, M, (300, 260)), cv.warpAffine(src, M, (300, 260)))
+
+
+def test_warp_perspective_and_homography(rng):
+    src_q = np.asarray([[0, 0], [172, 0], [172, 210], [0, 210]], dtype=np.float32)
+    dst_q = np.asarray([[0, 23], [172, 0], [172, 210], [0, 181]], dtype=np.float32)
+    M = cv.getPerspectiveTransform(src_q, dst_q, cv.DECOMP_SVD)
+    np.testing.assert_allclose(cm.get_perspective_transform(src_q, dst_q), M, rtol=0, atol=1e-9)
+    src = rng.integers(0, 256, (211, 173, 3), dtype=np.uint8)
+    got, ref = cm.warp_perspective(src, M, (173, 211)), cv.warpPerspective(src, M, (173, 211))
+    assert (got != ref).any(axis=-1).mean() <= 0.005  # exact but for 1/64 px ties (block order)
+    srcf = rng.random((211, 173)).astype(np.float32)
+    got, ref = cm.warp_perspective(srcf, M, (173, 211)), cv.warpPerspective(srcf, M, (173, 211))
+    assert (got != ref).mean() <= 0.005
+
+
+def test_fill_poly(rng):
+    for it in range(600):
+        side = int(rng.integers(3, 40))
+        quad = np.array([[0, 0], [side, 0], [side, side], [0, side]]) + rng.integers(-4, 5, (4, 2))
+        if it % 9 == 0:
+            quad = rng.integers(0, 60, (4, 2))
+        quad -= quad.min(axis=0)
+        w, h = int(quad[:, 0].max() + 1), int(quad[:, 1].max() + 1)
+        ref = np.zeros((h, w), np.uint8)
+        cv.fillPoly(ref, [quad.astype(np.int32)], 1)
+        assert _same(cm.fill_poly((h, w), quad), ref), quad.tolist()
+
+
+@pytest.mark.parametrize('sigma', [0.5, 0.62, 0.75, 0.9, 1.0, 2.0])
+def test_gaussian_blur(rng, sigma):
+    k = max(3, round(3 * sigma) + 1)
+    k += (k % 2 == 0)
+    for shape in ((77, 91, 3), (40, 33)):
+        src = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert _same(cm.gaussian_blur_u8(src, k, sigma), cv.GaussianBlur(src, (k, k), sigma))
+
+
+def test_colour_conversions_all_colours():
+    grid = np.stack(np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij'),
+                    -1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert _same(cm.cvt_rgb2hsv_full(grid), cv.cvtColor(grid, cv.COLOR_RGB2HSV_FULL))
+    assert _same(cm.cvt_rgb2gray(grid), cv.cvtColor(grid, cv.COLOR_RGB2GRAY))
+    for model, code, max_bad in ((cm.cvt_hsv2rgb_full, cv.COLOR_HSV2RGB_FULL, 200),
+                                 (cm.cvt_hls2rgb_full, cv.COLOR_HLS2RGB_FULL, 200)):
+        diff = np.abs(model(grid).astype(int) - cv.cvtColor(grid, code).astype(int))
+        assert diff.max() <= 1 and (diff > 0).any(axis=-1).sum() <= max_bad
+    got = cm.cvt_rgb2hls_full(grid).astype(int)
+    ref = cv.cvtColor(grid, cv.COLOR_RGB2HLS_FULL).astype(int)
+    assert np.array_equal(got[..., 1], ref[..., 1])  # L exact
+    assert np.abs(got - ref).max() <= 1  # H, S within 1 (IPP backend)
+
+
+def test_camera_functions(rng):
+    rvec = (np.asarray([0.6, 0.7, 0.3], np.float32) / np.float32(np.linalg.norm([0.6, 0.7, 0.3]))
+            ) * np.float32(0.25)
+    R, _ = cv.Rodrigues(rvec.astype(np.float64))
+    assert _same(cm.rodrigues(rvec), R)
+    pts = np.hstack([rng.uniform(0, 1024, (500, 2)), rng.uniform(-100, 100, (500, 1))])
+    tvec = np.asarray([[-500.], [-510.], [1024.]], np.float32)
+    K = np.asarray([[1024, 0, 0], [0, 1024, 0], [0, 0, 1]], np.float32)
+    for dtype in (np.float32, np.float64):
+        p = pts.astype(dtype)
+        ref, _ = cv.projectPoints(p, rvec, tvec, K, np.zeros(5))
+        assert _same(cm.project_points(p, rvec, tvec, K), ref.reshape(-1, 2))
