@@ -79,51 +79,100 @@ def config_to_plain(config):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every ~5 ms; falls back
+    to `nvidia-smi -lms 100` when pynvml is unavailable)."""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.samples = []
-        self.proc = None
+        self.sm = []
+        self.max_mhz = None
+        self.reasons = set()
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.proc = None
+        self.smi_samples = []
+
+    def _visible_index(self):
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if visible:
+            ids = [v.strip() for v in visible.split(',') if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
+
+    def _poll_nvml(self, nvml, handle):
+        bits = {
+            'hw_slowdown': nvml.nvmlClocksThrottleReasonHwSlowdown,
+            'hw_thermal_slowdown': nvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+            'sw_thermal_slowdown': nvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+            'sw_power_cap': nvml.nvmlClocksThrottleReasonSwPowerCap,
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)))
+                mask = nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as nvml
+            nvml.nvmlInit()
+            handle = nvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
+                ['nvidia-smi', f'--id={self._visible_index()}', f'--query-gpu={self.QUERY}',
                  '--format=csv,noheader,nounits', '-lms', '100'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump_smi, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
-            return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
-        self.thread.start()
 
-    def _pump(self):
+    def _pump_smi(self):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                self.smi_samples.append(parts)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '', 1).isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '', 1).isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for s in self.samples for i in range(4)
-                          if s[2 + i].lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.samples)}
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            for s in self.smi_samples:
+                if s[0].replace('.', '', 1).isdigit():
+                    self.sm.append(float(s[0]))
+                if s[1].replace('.', '', 1).isdigit():
+                    self.max_mhz = max(self.max_mhz or 0.0, float(s[1]))
+                for i in range(4):
+                    if s[2 + i].lower().startswith('active'):
+                        self.reasons.add(names[i])
+        elif self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+        else:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable']}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.sm)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -216,7 +265,7 @@ def workload_config(world: int):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=10)
+    parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     parser.add_argument('--batch', type=int, default=BATCH)
@@ -312,14 +361,14 @@ def main():
     # ---- end to end: host buffers, public batch API -----------------------------------------
     host_out = torch.empty((out_bytes,), dtype=torch.uint8).pin_memory()
 
+    from vkit_b200.batch import distort_pages_host
+
     def e2e_step():
-        eng = GeometricBatch(names, configs, PAGE_SHAPE)  # config -> parameter blocks (host)
-        dev_in = host_pages.cuda(non_blocking=True)      # H2D of this step's pages
-        res = eng.run(dev_in)
-        n = int(res.image_arena.numel())
-        host_out[:n].copy_(res.image_arena, non_blocking=True)  # D2H of the distorted pages
-        torch.cuda.synchronize()
-        return n
+        # configs -> parameter blocks (host), H2D of this step's pages, kernels, D2H of the
+        # distorted pages; chunked over two streams so the three overlap
+        _, _, offsets = distort_pages_host(names, configs, PAGE_SHAPE, host_pages, host_out,
+                                           chunk_pages=32)
+        return int(offsets[-1])
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -360,8 +409,9 @@ def main():
             'e2e': {'value': batch * world / (e2e_ms * 1e-3), 'unit': 'pages/s',
                     'h2d_bytes_per_step': int(host_pages.numel()),
                     'd2h_bytes_per_step': int(d2h),
-                    'note': 'GeometricBatch(configs).run(host pages) incl. parameter-block build, '
-                            'H2D, kernels, D2H; per GPU batch, wall clock'},
+                    'note': 'vkit_b200.batch.distort_pages_host(configs, pinned host pages) incl. '
+                            'parameter-block build, H2D, kernels, D2H (32-page chunks on two '
+                            'streams); wall clock, max over ranks'},
             'gpu_launches': KERNELS_PER_STEP * args.steps,
             'roofline': {
                 'bound': 'hbm', 'kernel': 'grid_remap_kernel', 'achieved': achieved, 'peak': peak,

@@ -342,3 +342,22 @@ def test_batched_engine_matches_single_page(vk):
         assert sha(out.image(i).cpu().numpy()) == case['sha']['image'], case['id']
         assert sha(out.mask(i).cpu().numpy()) == case['sha']['mask'], case['id']
         assert sha(out.score_map(i).cpu().numpy()) == case['sha']['score_map'], case['id']
+
+
+def test_host_to_host_pipeline_matches_device_batch(vk):
+    import torch
+    from vkit_b200.batch import GeometricBatch, distort_pages_host
+    cases = [c for c in GEOMETRIC if c['op'].startswith('camera') and tuple(c['shape']) == (136, 176)]
+    cases = cases * 3  # 24 pages -> several chunks
+    shape = (136, 176)
+    images = np.stack([make_inputs(c['seed'], shape)[0] for c in cases])
+    names = [c['op'] for c in cases]
+    configs = [product_config(c) for c in cases]
+    host_in = torch.from_numpy(images).pin_memory()
+    host_out, shapes, offsets = distort_pages_host(names, configs, shape, host_in, chunk_pages=5)
+    assert len(shapes) == len(cases) and len(offsets) == len(cases) + 1
+    for i, case in enumerate(cases):
+        h, w = shapes[i]
+        assert (h, w) == tuple(case['result_shape'])
+        page = host_out[offsets[i]:offsets[i + 1]].numpy().reshape(h, w, 3)
+        assert sha(page) == case['sha']['image'], (i, case['id'])

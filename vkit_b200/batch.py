@@ -140,3 +140,63 @@ class GeometricBatch:
         height, width = self.shape
         dst = sum(h * w for h, w in (self.plan.result_shape(i) for i in range(self.n)))
         return per_px * (self.n * height * width + dst)
+
+
+def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int],
+                       host_images, host_out=None, chunk_pages: int = 64):
+    """Host buffers in, host buffers out -- the end-to-end form of the batch engine.
+
+    `host_images`: pinned (B, H, W, C) uint8 CPU tensor; the distorted pages land back to back in
+    the pinned flat uint8 tensor `host_out` (allocated when None).  The batch is cut into chunks
+    that alternate between two CUDA streams, so the H2D copy of chunk i+1, the kernels of chunk i
+    and the D2H copy of chunk i-1 overlap, while a helper thread turns the configs of the next
+    chunk into parameter blocks (Rodrigues, translation, curve / line constants).
+    Returns (host_out, shapes, byte_offsets)."""
+    import queue
+    import threading
+    t = dv.require_cuda()
+    n = len(op_names)
+    bounds = [(a, min(a + chunk_pages, n)) for a in range(0, n, chunk_pages)]
+    ready: 'queue.Queue' = queue.Queue(maxsize=2)
+
+    def producer():
+        try:
+            for a, b in bounds:
+                ready.put(GeometricBatch(op_names[a:b], configs[a:b], shape))
+        except BaseException as exc:  # surface errors in the consumer
+            ready.put(exc)
+
+    channels = 1 if host_images.dim() == 3 else int(host_images.shape[3])
+    if host_out is None:
+        bound = int(n * shape[0] * shape[1] * channels * 2.25)
+        host_out = t.empty((bound,), dtype=t.uint8).pin_memory()
+    thread = threading.Thread(target=producer, daemon=True)
+    thread.start()
+    streams = [t.cuda.Stream(), t.cuda.Stream()]
+    shapes, offsets = [], [0]
+    keep = []
+    for i, (a, b) in enumerate(bounds):
+        sub = ready.get()
+        if isinstance(sub, BaseException):
+            raise sub
+        with t.cuda.stream(streams[i % 2]):
+            dev_in = host_images[a:b].to(dv.device(), non_blocking=True)
+            out = sub.run(dev_in)
+            n_bytes = int(out.image_arena.numel())
+            start = offsets[-1]
+            if start + n_bytes > host_out.numel():
+                raise ValueError('host_out is too small for the distorted pages')
+            host_out[start:start + n_bytes].copy_(out.image_arena, non_blocking=True)
+            for k, (h, w) in enumerate(out.shapes):
+                shapes.append((h, w))
+                offsets.append(start + int(out.pixel_offsets[k + 1]) * channels)
+            keep.append((dev_in, out, sub))
+        if len(keep) > 2:
+            # chunk i-2 ran on this stream's sibling two iterations ago: its buffers may be
+            # recycled once that stream has drained
+            streams[(i + 1) % 2].synchronize()
+            keep.pop(0)
+    for s in streams:
+        s.synchronize()
+    thread.join()
+    return host_out, shapes, offsets

@@ -11,19 +11,23 @@ import numpy as np
 
 def rodrigues(rvec) -> np.ndarray:
     """cv.Rodrigues(rvec) in double (3x3).  Used by camera.py:96 (float32 out) and inside
-    cv.projectPoints (camera.py:189, double)."""
-    r = np.asarray(rvec, dtype=np.float64).reshape(3)
-    theta = math.sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2])
-    if theta < np.finfo(np.float64).eps:
+    cv.projectPoints (camera.py:189, double).  Plain Python floats: same IEEE operations as the
+    NumPy expression c*I + c1*rrt + s*r_x, without the small-array overhead."""
+    r0, r1, r2 = float(rvec[0]), float(rvec[1]), float(rvec[2])
+    theta = math.sqrt(r0 * r0 + r1 * r1 + r2 * r2)
+    if theta < 2.220446049250313e-16:
         return np.eye(3, dtype=np.float64)
     c = math.cos(theta)
     s = math.sin(theta)
     c1 = 1.0 - c
     itheta = 1.0 / theta
-    x, y, z = r[0] * itheta, r[1] * itheta, r[2] * itheta
-    rrt = np.array([[x * x, x * y, x * z], [x * y, y * y, y * z], [x * z, y * z, z * z]])
-    r_x = np.array([[0.0, -z, y], [z, 0.0, -x], [-y, x, 0.0]])
-    return c * np.eye(3) + c1 * rrt + s * r_x
+    x, y, z = r0 * itheta, r1 * itheta, r2 * itheta
+    # element (i, j): c*I + c1*r_i*r_j + s*[r]x, summed left to right like the matrix expression
+    return np.array([
+        [c * 1.0 + c1 * (x * x) + s * 0.0, c * 0.0 + c1 * (x * y) + s * -z, c * 0.0 + c1 * (x * z) + s * y],
+        [c * 0.0 + c1 * (x * y) + s * z, c * 1.0 + c1 * (y * y) + s * 0.0, c * 0.0 + c1 * (y * z) + s * -x],
+        [c * 0.0 + c1 * (x * z) + s * -y, c * 0.0 + c1 * (y * z) + s * x, c * 1.0 + c1 * (z * z) + s * 0.0],
+    ], dtype=np.float64)
 
 
 def invert_affine(trans_mat) -> np.ndarray:

@@ -49,7 +49,7 @@ def fill_camera_model(rec: np.ndarray, config: CameraModelConfig):
     length = np.linalg.norm(unit_vec)
     if length != 1.0:
         unit_vec /= length
-    theta = float(np.clip(config.rotation_theta, -89, 89) / 180 * np.pi)
+    theta = float(min(max(config.rotation_theta, -89), 89) / 180 * np.pi)
     rotation_vec = unit_vec * theta  # float32
 
     principal_point = list(config.principal_point)
