@@ -142,8 +142,22 @@ class GeometricBatch:
         return per_px * (self.n * height * width + dst)
 
 
+_PIPELINE_STREAMS = {}
+
+
+def _pipeline_streams():
+    """Two long-lived side streams per device (the caching allocator keeps one pool per stream,
+    so fresh streams per call would mean fresh cudaMallocs per call)."""
+    t = dv.require_cuda()
+    key = t.cuda.current_device()
+    if key not in _PIPELINE_STREAMS:
+        _PIPELINE_STREAMS[key] = [t.cuda.Stream(), t.cuda.Stream()]
+    return _PIPELINE_STREAMS[key]
+
+
 def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int],
-                       host_images, host_out=None, chunk_pages: int = 64):
+                       host_images, host_out=None, chunk_pages: int = 64,
+                       use_thread: bool = True):
     """Host buffers in, host buffers out -- the end-to-end form of the batch engine.
 
     `host_images`: pinned (B, H, W, C) uint8 CPU tensor; the distorted pages land back to back in
@@ -170,13 +184,16 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     if host_out is None:
         bound = int(n * shape[0] * shape[1] * channels * 2.25)
         host_out = t.empty((bound,), dtype=t.uint8).pin_memory()
-    thread = threading.Thread(target=producer, daemon=True)
-    thread.start()
-    streams = [t.cuda.Stream(), t.cuda.Stream()]
+    if use_thread:
+        thread = threading.Thread(target=producer, daemon=True)
+        thread.start()
+    streams = _pipeline_streams()
+    for s in streams:
+        s.wait_stream(t.cuda.current_stream())
     shapes, offsets = [], [0]
     keep = []
     for i, (a, b) in enumerate(bounds):
-        sub = ready.get()
+        sub = ready.get() if use_thread else GeometricBatch(op_names[a:b], configs[a:b], shape)
         if isinstance(sub, BaseException):
             raise sub
         with t.cuda.stream(streams[i % 2]):
@@ -198,5 +215,6 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
             keep.pop(0)
     for s in streams:
         s.synchronize()
-    thread.join()
+    if use_thread:
+        thread.join()
     return host_out, shapes, offsets
