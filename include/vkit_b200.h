@@ -262,6 +262,14 @@ int vkb_color_ops(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t ch
 int vkb_channel_stats(const uint8_t* src, int64_t n_pixels, int32_t channels, void* out,
                       void* stream);
 
+/* cv.equalizeHist building blocks (photometric/color.py:264-298): per-channel 256-bin
+ * histogram (out: 3 x 256 uint32, device) and a per-channel 256-entry LUT (3 x 256 uint8,
+ * device) applied to the channels selected by channel_bits. */
+int vkb_histogram_u8(const uint8_t* src, int64_t n_pixels, int32_t channels, uint32_t* out,
+                     void* stream);
+int vkb_apply_lut(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                  const uint8_t* lut, int32_t channel_bits, void* stream);
+
 /* cv.GaussianBlur(uint8, (k,k), sigma) with BORDER_REFLECT_101: separable 8.8 fixed-point
  * stencil staged through shared memory (photometric/blur.py:49-76). kernel_host: k integer
  * taps summing to 256 (k odd, k <= 17). */

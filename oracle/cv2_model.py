@@ -435,6 +435,20 @@ def cvt_rgb2gray(rgb):
     return ((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15).astype(np.uint8)
 
 
+def equalize_hist(gray):
+    """cv.equalizeHist(uint8 HxW) (vkit/mechanism/distortion/photometric/color.py:284)."""
+    hist = np.bincount(gray.reshape(-1), minlength=256)
+    total = int(hist.sum())
+    first = int(np.nonzero(hist)[0][0])
+    if int(hist[first]) == total:
+        return np.full_like(gray, first)
+    scale = np.float32(255.0) / np.float32(total - int(hist[first]))
+    lut = np.zeros(256, dtype=np.uint8)
+    cumulative = np.cumsum(hist[first + 1:].astype(np.int64))
+    lut[first + 1:] = np.clip(np.rint(cumulative.astype(np.float32) * scale), 0, 255).astype(np.uint8)
+    return lut[gray]
+
+
 def cvt_gray2rgb(gray):
     return np.repeat(gray[..., None], 3, axis=-1)
 

@@ -275,6 +275,13 @@ def main():
 
     blend_cases()
 
+    # appended later (keeps the ids / seeds of the cases above stable)
+    photometric_case('histogram_equalization', {}, (64, 96), 601, keep_arrays=False)
+    photometric_case('histogram_equalization', {'channels': [1]}, (64, 96), 602, keep_arrays=False)
+    photometric_case('histogram_equalization', {}, (1024, 1024), 603, keep_arrays=False)
+    photometric_case('histogram_equalization', {}, (64, 96), 604, keep_arrays=False,
+                     mode='grayscale')
+
     with open(os.path.join(HERE, 'cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)

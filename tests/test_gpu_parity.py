@@ -361,3 +361,77 @@ def test_host_to_host_pipeline_matches_device_batch(vk):
         assert (h, w) == tuple(case['result_shape'])
         page = host_out[offsets[i]:offsets[i + 1]].numpy().reshape(h, w, 3)
         assert sha(page) == case['sha']['image'], (i, case['id'])
+
+
+def test_draw_list_text_layer_compositing(vk):
+    """BASELINE config 4 shape: background + 64 text lines of float32 coverage blended in one
+    launch == the same fills through the oracle's fill_np_array, one by one, in order."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    from vkit_b200.compositing import (DrawList, assemble_text_lines, fill_page_inactive_region,
+                                       render_char_glyphs_in_text_line)
+    rng = np.random.default_rng(11)
+    height, width = 512, 640
+    background = rng.integers(0, 256, (height, width, 3), dtype=np.uint8)
+    lines, colors, boxes = [], [], []
+    for i in range(40):
+        lh, lw = int(rng.integers(8, 25)), int(rng.integers(60, 400))
+        up, left = int(rng.integers(0, height - lh)), int(rng.integers(0, width - lw))
+        alpha = np.clip(rng.normal(0.8, 0.3, (lh, lw)), 0, 1).astype(np.float32)
+        alpha[rng.random((lh, lw)) > 0.4] = 0.0
+        box = element.Box(up=up, down=up + lh - 1, left=left, right=left + lw - 1)
+        lines.append(element.ScoreMap(mat=alpha, box=box))
+        colors.append(tuple(int(v) for v in rng.integers(0, 256, 3)))
+        boxes.append(box)
+    got = assemble_text_lines(element.Image(mat=background), lines, colors).mat
+    ref = background.copy()
+    for line, color, box in zip(lines, colors, boxes):  # overlapping boxes: order matters
+        port.fill_np_array(ref[box.up:box.down + 1, box.left:box.right + 1], color, alpha=line.mat)
+    assert sha(got) == sha(ref)
+    # the same through the per-call element API
+    seq = element.Image(mat=background.copy())
+    for line, color in zip(lines, colors):
+        line.fill_image(seq, color)
+    assert sha(seq.mat) == sha(ref)
+    # scalar alpha + mask + image value + keep_max in one list
+    target = element.Image(mat=background.copy())
+    dl = DrawList(target)
+    value = rng.integers(0, 256, (100, 200, 3), dtype=np.uint8)
+    m = (rng.random((100, 200)) > 0.5)
+    dl.fill(element.Box(up=10, down=109, left=20, right=219), value, alpha=0.35)
+    dl.fill(element.Box(up=50, down=149, left=100, right=299), (9, 8, 7), mask=m)
+    dl.flush()
+    ref2 = background.copy()
+    port.fill_np_array(ref2[10:110, 20:220], value, alpha=0.35)
+    port.fill_np_array(ref2[50:150, 100:300], (9, 8, 7), np_mask=m)
+    assert sha(target.mat) == sha(ref2)
+    # glyph -> text line
+    glyph_images, glyph_scores, char_boxes = [], [], []
+    x = 2
+    for _ in range(12):
+        gh, gw = int(rng.integers(10, 24)), int(rng.integers(6, 20))
+        bitmap = (rng.random((gh, gw)) > 0.5) * rng.integers(1, 256, (gh, gw))
+        glyph_images.append(bitmap.astype(np.uint8))
+        glyph_scores.append(np.power(bitmap / 255.0, 1.3).astype(np.float32))
+        char_boxes.append(element.Box(up=1, down=gh, left=x, right=x + gw - 1))
+        x += gw - 2  # neighbouring glyphs overlap by two columns
+    image, mask, score_map = render_char_glyphs_in_text_line((30, 60, 90), 26, x + 24,
+                                                             glyph_images, glyph_scores, char_boxes)
+    ref_image = np.full((26, x + 24, 3), 255, np.uint8)
+    ref_mask = np.zeros((26, x + 24), np.uint8)
+    ref_score = np.zeros((26, x + 24), np.float32)
+    for gi, gs, box in zip(glyph_images, glyph_scores, char_boxes):
+        region = (slice(box.up, box.down + 1), slice(box.left, box.right + 1))
+        port.fill_np_array(ref_image[region], (30, 60, 90), np_mask=gi > 0)
+        port.fill_np_array(ref_mask[region], 1, np_mask=gi > 0)
+        port.fill_np_array(ref_score[region], gs, keep_max_value=True)
+    assert sha(image.mat) == sha(ref_image) and sha(mask.mat) == sha(ref_mask)
+    assert sha(score_map.mat) == sha(ref_score)
+    # inactive-region fill
+    page = element.Image(mat=background.copy())
+    active = element.Mask(mat=(rng.random((height, width)) > 0.1).astype(np.uint8))
+    bottom = rng.integers(0, 256, (height, width, 3), dtype=np.uint8)
+    fill_page_inactive_region(page, active, element.Image(mat=bottom))
+    ref3 = background.copy()
+    port.fill_np_array(ref3, bottom, np_mask=active.mat == 0)
+    assert sha(page.mat) == sha(ref3)

@@ -239,11 +239,19 @@ assert float(stats[0]) == float(world)
 assert names[0] == bench.CAMERA_OPS[(rank * batch) %% 4]
 print('rank', rank, 'ok')
 ''' % ROOT)
+    import socket
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
-    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
-                          '--nproc-per-node=2', '--master-addr', '127.0.0.1', '--master-port',
-                          '29517', str(script)], capture_output=True, text=True, env=env,
-                         timeout=300)
+    out = None
+    for _ in range(3):  # a freshly released port can still be refused; pick another one
+        with socket.socket() as sock:
+            sock.bind(('127.0.0.1', 0))
+            port = sock.getsockname()[1]
+        out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                              '--nproc-per-node=2', '--master-addr', '127.0.0.1', '--master-port',
+                              str(port), str(script)], capture_output=True, text=True, env=env,
+                             timeout=300)
+        if out.returncode == 0:
+            break
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout
 

@@ -117,6 +117,8 @@ def _oracle_photometric(case):
         return port.std_shift(image, cfg['scale'], cfg['channels'])
     if name == 'boundary_equalization':
         return port.boundary_equalization(image, cfg['channels'])
+    if name == 'histogram_equalization':
+        return port.histogram_equalization(image, cfg['channels'])
     if name == 'complement':
         return port.complement(image, cfg['threshold'], cfg['enable_threshold_lte'],
                                cfg['channels'])

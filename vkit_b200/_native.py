@@ -152,6 +152,8 @@ def _declare(lib):
     lib.vkb_cvt_color.argtypes = [vp, vp, i64, i32, vp]
     lib.vkb_color_ops.argtypes = [vp, vp, i64, i32, POINTER(ColorOp), i32, vp]
     lib.vkb_channel_stats.argtypes = [vp, i64, i32, vp, vp]
+    lib.vkb_histogram_u8.argtypes = [vp, i64, i32, vp, vp]
+    lib.vkb_apply_lut.argtypes = [vp, vp, i64, i32, vp, i32, vp]
     lib.vkb_gaussian_blur_u8.argtypes = [vp, vp, i32, i32, i32, POINTER(c_int32), i32, vp]
     lib.vkb_noise_philox.argtypes = [vp, vp, i64, i32, i32, c_double, c_double, ctypes.c_uint64, vp]
     lib.vkb_noise_field.argtypes = [vp, vp, i64, i32, i32, vp, vp]
@@ -168,7 +170,7 @@ EXPORTS = (
     'vkb_warp_fused', 'vkb_affine_points', 'vkb_grid_project', 'vkb_grid_finalize',
     'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon',
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
-    'vkb_channel_stats', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
+    'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks',
 )
 

@@ -288,6 +288,37 @@ __global__ void channel_stats_init_kernel(unsigned long long* sums, unsigned int
     }
 }
 
+// per-channel 256-bin histogram (cv.equalizeHist, photometric/color.py:264-298) and LUT apply
+__global__ void __launch_bounds__(256) histogram_kernel(const uint8_t* __restrict__ src, long long n,
+                                                        int channels, unsigned int* __restrict__ out) {
+    __shared__ unsigned int sh[3 * 256];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < channels; ++c) atomicAdd(&sh[c * 256 + src[i * channels + c]], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < channels * 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&out[i], sh[i]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) apply_lut_kernel(const uint8_t* __restrict__ src,
+                                                        uint8_t* __restrict__ dst, long long n,
+                                                        const uint8_t* __restrict__ lut, int bits) {
+    __shared__ uint8_t sl[3 * 256];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) sl[i] = lut[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint8_t v = src[i * C + c];
+        dst[i * C + c] = ((bits >> c) & 1) && c < 3 ? sl[c * 256 + v] : v;
+    }
+}
+
 // ============================================================================================
 // Gaussian blur, uint8, 8.8 fixed point, BORDER_REFLECT_101.  Block = 32 x 8 threads on a
 // 32 x 32 output tile; the tile plus halo is staged in shared memory, the horizontal pass keeps
@@ -552,6 +583,32 @@ extern "C" int vkb_channel_stats(const uint8_t* src, int64_t n_pixels, int32_t c
         channel_stats_kernel<<<blocks, 256, 0, st>>>(src, n_pixels, channels, sums, mins, maxs);
     }
     return check_launch("channel_stats_kernel");
+}
+
+extern "C" int vkb_histogram_u8(const uint8_t* src, int64_t n_pixels, int32_t channels,
+                                uint32_t* out, void* stream) {
+    VKB_REQUIRE(src && out && channels >= 1 && channels <= 3, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    VKB_CUDA(cudaMemsetAsync(out, 0, sizeof(uint32_t) * 3 * 256, st));
+    if (n_pixels > 0) {
+        const long long want = (n_pixels + 255) / 256;
+        const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+        histogram_kernel<<<blocks, 256, 0, st>>>(src, n_pixels, channels, out);
+    }
+    return check_launch("histogram_kernel");
+}
+
+extern "C" int vkb_apply_lut(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
+                             const uint8_t* lut, int32_t channel_bits, void* stream) {
+    VKB_REQUIRE(src && dst && lut, "bad arguments");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    if (n_pixels <= 0) return VKB_OK;
+    const unsigned blocks = (unsigned)((n_pixels + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) apply_lut_kernel<1><<<blocks, 256, 0, st>>>(src, dst, n_pixels, lut, channel_bits);
+    else if (channels == 3) apply_lut_kernel<3><<<blocks, 256, 0, st>>>(src, dst, n_pixels, lut, channel_bits);
+    else apply_lut_kernel<4><<<blocks, 256, 0, st>>>(src, dst, n_pixels, lut, channel_bits);
+    return check_launch("apply_lut_kernel");
 }
 
 extern "C" int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,

@@ -157,11 +157,42 @@ class HistogramEqualizationConfig(DistortionConfig):
     channels: Optional[Sequence[int]] = None
 
 
+def equalize_hist_lut(hist: np.ndarray) -> np.ndarray:
+    """cv.equalizeHist's LUT from a 256-bin histogram: lut[first] = 0, then
+    saturate_cast<uchar>(cumulative * scale) with float32 scale = 255 / (total - hist[first])."""
+    total = int(hist.sum())
+    first = int(np.nonzero(hist)[0][0])
+    if int(hist[first]) == total:
+        return np.full(256, first, dtype=np.uint8)
+    scale = np.float32(255.0) / np.float32(total - int(hist[first]))
+    lut = np.zeros(256, dtype=np.uint8)
+    cumulative = np.cumsum(hist[first + 1:].astype(np.int64))
+    values = np.rint(cumulative.astype(np.float32) * scale)
+    lut[first + 1:] = np.clip(values, 0, 255).astype(np.uint8)
+    return lut
+
+
 def histogram_equalization_image(config: HistogramEqualizationConfig, state, image: Image,
                                  rng: Optional[RandomGenerator]):
-    raise NotImplementedError(
-        'histogram_equalization (cv.equalizeHist) is a "next" row of the scope table and has '
-        'no device kernel yet.')
+    from vkit_b200 import device as dv
+    if image.mat_dtype != np.uint8:
+        raise NotImplementedError('photometric ops expect uint8 images')
+    channels = image.num_channels or 1
+    n_pixels = image.height * image.width
+    hist_dev = dv.empty((3, 256), np.uint32)
+    nv.check(nv.lib().vkb_histogram_u8(dv.ptr(image.dev), n_pixels, min(channels, 3),
+                                       dv.ptr(hist_dev), dv.stream_ptr()), 'vkb_histogram_u8')
+    hist = dv.to_host(hist_dev)
+    bits = channel_bits(image, config.channels)
+    lut = np.zeros((3, 256), dtype=np.uint8)
+    for c in range(min(channels, 3)):
+        if (bits >> c) & 1:
+            lut[c] = equalize_hist_lut(hist[c])
+    lut_dev = dv.to_device(lut)
+    dst = dv.empty(tuple(image.dev.shape), np.uint8)
+    nv.check(nv.lib().vkb_apply_lut(dv.ptr(image.dev), dv.ptr(dst), n_pixels, channels,
+                                    dv.ptr(lut_dev), bits, dv.stream_ptr()), 'vkb_apply_lut')
+    return attrs.evolve(image, mat=dst)
 
 
 histogram_equalization = Distortion(config_cls=HistogramEqualizationConfig,
