@@ -131,7 +131,6 @@ typedef struct vkb_grid_meta {
 /* Fixed per-cell budget of coverage-mask words; cells that need more are rasterised on the
  * fly by the remap kernel. */
 #define VKB_CELL_MASK_WORDS 32
-#define VKB_CELL_LOCAL_BYTES 48
 #define VKB_TILE 32     /* dst tile edge of the remap kernel */
 #define VKB_TILE_CAP 64 /* candidate cells kept per tile before the slow path is used */
 
@@ -147,31 +146,40 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
                       void* stream);
 
 /* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage masks; per dst
- * tile the list of candidate cells.  c_max >= (rows-1)*(cols-1); t_max >= tiles per page.
+ * tile the candidate cells and their records for the remap kernel.
+ * c_max >= (rows-1)*(cols-1); t_max >= 32x32 tiles per page; s_cap = candidate records kept
+ * per page (16 * t_max is ample; tiles that do not fit are handled by a slow exact path).
  *   hinv:       n_pages x c_max x 9 doubles
  *   hfwd:       n_pages x c_max x 9 doubles or NULL (forward maps, needed by vkb_grid_points)
  *   cell_box:   n_pages x c_max x 4 int32 (x0, y0, x1, y1); bit 30 of x1 set = coverage of
  *               this cell exceeds the mask budget and is rasterised on the fly by the remap
- *   cell_local: n_pages x c_max x VKB_CELL_LOCAL_BYTES bytes (float32 re-centred inverse maps
- *               for the remap kernel's error-bounded fast path, opaque to the caller)
  *   cell_masks: n_pages x c_max x VKB_CELL_MASK_WORDS uint32
  *   tile_count: n_pages x t_max int32 (zeroed by this call)
- *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16 */
+ *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16
+ *   tile_off:   n_pages x t_max int32, first record of each tile within its page
+ *   tile_base:  n_pages + 1 int32, prefix sum of tiles per page (the remap's flat work list)
+ *   tile_slots: n_pages x s_cap x VKB_TILE_SLOT_BYTES bytes, opaque (bbox, cell id and the
+ *               float32 tile-centred inverse map of every candidate, ascending cell order) */
+#define VKB_TILE_SLOT_BYTES 64
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
-                   int32_t t_max, const int32_t* lattice_i, vkb_grid_meta* meta, double* hinv,
-                   double* hfwd, int32_t* cell_box, void* cell_local, uint32_t* cell_masks,
-                   int32_t* tile_count, uint16_t* tile_cells, void* stream);
+                   int32_t t_max, int32_t s_cap, const int32_t* lattice_i, vkb_grid_meta* meta,
+                   double* hinv, double* hfwd, int32_t* cell_box, uint32_t* cell_masks,
+                   int32_t* tile_count, uint16_t* tile_cells, int32_t* tile_off,
+                   int32_t* tile_base, void* tile_slots, void* stream);
 
 /* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
  * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
  * value, 1/32 px quantisation, bilinear gather of Image + Mask + ScoreMap in one pass.
+ * A persistent kernel: every block walks a contiguous share of the flat tile list and
+ * prefetches the next tile's records while it works on the current one.
  * The kernel is specialised at compile time on the containers present, so every page of one
- * call carries the same set: image_channels (0 = no image), has_mask, has_score. */
+ * call carries the same set: image_channels (0 = no image), has_mask, has_score.
+ * planes[i].dst_h / dst_w must be the result shape in meta[i]; src planes below 32768 px. */
 int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
-                   int32_t p_max, int32_t c_max, int32_t t_max, const int32_t* lattice_i,
-                   const vkb_grid_meta* meta, const double* hinv, const int32_t* cell_box,
-                   const void* cell_local, const uint32_t* cell_masks, const int32_t* tile_count,
-                   const uint16_t* tile_cells, int32_t max_dst_h, int32_t max_dst_w,
+                   int32_t p_max, int32_t c_max, int32_t t_max, int32_t s_cap,
+                   const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
+                   const uint32_t* cell_masks, const int32_t* tile_count,
+                   const int32_t* tile_off, const int32_t* tile_base, const void* tile_slots,
                    int32_t image_channels, int32_t has_mask, int32_t has_score, void* stream);
 
 /* Points through the forward homography of the source cell that contains the ROUNDED point

@@ -164,7 +164,7 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
                                    const int32_t* owner, long long* stats) {
     const int ccols = pg->cols - 1, C = (pg->rows - 1) * ccols;
     std::vector<double> hinv((size_t)C * 9);
-    std::vector<CellLocal> loc(C);
+    std::vector<int> sx(C), sy(C);
     for (int cell = 0; cell < C; ++cell) {
         const int r = cell / ccols, c = cell % ccols;
         const int i00 = r * pg->cols + c, i01 = i00 + 1, i11 = i00 + pg->cols + 1, i10 = i00 + pg->cols;
@@ -175,31 +175,38 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
         const double sq[8] = {(double)sx0, (double)sy0, (double)sx1, (double)sy0, (double)sx1, (double)sy1, (double)sx0, (double)sy1};
         const double dq[8] = {(double)px[0], (double)py[0], (double)px[1], (double)py[1], (double)px[2], (double)py[2], (double)px[3], (double)py[3]};
         homography_4pt(dq, sq, &hinv[(size_t)cell * 9]);
-        const int x0 = *std::min_element(px, px + 4), y0 = *std::min_element(py, py + 4);
-        make_cell_local(&hinv[(size_t)cell * 9], sx0, sy0, x0, y0, loc[cell]);
+        sx[cell] = sx0;
+        sy[cell] = sy0;
     }
+    float t_odd, t_even;
+    fast_thresholds(pg->src_w > pg->src_h ? pg->src_w : pg->src_h, t_odd, t_even);
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
     for (int y = 0; y < Hh; ++y)
         for (int x = 0; x < W; ++x) {
             const int o = owner[(size_t)y * W + x];
             if (o < 0) continue;
             stats[0]++;
+            // the kernel's form: re-centred on the origin of the pixel's 32 x 32 tile
+            const int ox = x & ~31, oy = y & ~31;
+            CellLocal L;
+            make_cell_local(&hinv[(size_t)o * 9], sx[o], sy[o], ox, oy, L);
             int Xe, Ye, Xf, Yf;
             cell_coord(&hinv[(size_t)o * 9], x, y, Xe, Ye);
-            const bool ok = cell_coord_fast(loc[o], x, y, Xf, Yf);
+            const float xr = (float)(x - ox), yr = (float)(y - oy);
+            const bool ok = cell_coord_fast(L, xr, yr, sx[o] * 32 - kRoundMagicBits,
+                                            sy[o] * 32 - kRoundMagicBits, t_odd, t_even, Xf, Yf);
             if (ok) { stats[1]++; if (Xf != Xe || Yf != Ye) stats[2]++; }
             // error of the float32 evaluation itself
             const double* H = &hinv[(size_t)o * 9];
             const double den = H[6] * x + H[7] * y + H[8];
             const double ux = (H[0] * x + H[1] * y + H[2]) / den, uy = (H[3] * x + H[4] * y + H[5]) / den;
-            const CellLocal& L = loc[o];
-            const float xf = (float)(x - L.cx), yf = (float)(y - L.cy);
-            const float d = (float)((double)L.g * xf + ((double)L.h * yf + 1.0));
-            const float nx = (float)((double)L.a0 * xf + ((double)L.a1 * yf + (double)L.a2));
-            const float ny = (float)((double)L.b0 * xf + ((double)L.b1 * yf + (double)L.b2));
-            const float r32 = 32.0f / d;
-            const double ex = fabs((double)(nx * r32) - 32.0 * (ux - L.sx0));
-            const double ey = fabs((double)(ny * r32) - 32.0 * (uy - L.sy0));
+            const float d = (float)((double)L.g * xr + ((double)L.h * yr + 1.0));
+            const float nx = (float)((double)L.a0 * xr + ((double)L.a1 * yr + (double)L.a2));
+            const float ny = (float)((double)L.b0 * xr + ((double)L.b1 * yr + (double)L.b2));
+            const float r = 1.0f / d;
+            const double ex = fabs((double)(nx * r) - 32.0 * (ux - sx[o]));
+            const double ey = fabs((double)(ny * r) - 32.0 * (uy - sy[o]));
+            if (fmax(fabs((double)(nx * r)), fabs((double)(ny * r))) >= kFastRange) continue;
             const long long e = (long long)(fmax(ex, ey) * 1e9);
             if (e > stats[3]) stats[3] = e;
         }

@@ -139,8 +139,9 @@ def test_remap_numerics_given_reference_lattice(hs, case):
                           owner.ctypes.data, stats)
     pixels, ok, wrong, max_err = list(stats)
     assert wrong == 0
-    assert ok / pixels > 0.97
-    assert max_err / 1e9 < 2.0e-3 / 4  # kFastSlack with a 4x margin
+    assert ok / pixels > 0.99
+    assert max_err / 1e9 < 1.0e-3 / 4  # kFastSlack with a 4x margin
+    print(f'fast path: {ok / pixels:.5f} accepted, max error {max_err / 1e9:.2e}')
 
 
 def test_fill_poly_rows_random_quads(hs):

@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libvkit_b200.so')
 
 CELL_MASK_WORDS = 32
-CELL_LOCAL_BYTES = 48
 TILE = 32
 TILE_CAP = 64
+TILE_SLOT_BYTES = 64
 
 WARP_AFFINE = 0
 WARP_PERSPECTIVE = 1
@@ -141,9 +141,10 @@ def _declare(lib):
     lib.vkb_affine_points.argtypes = [POINTER(c_double), i32, vp, vp, i32, i32, vp]
     lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, vp]
     lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp]
-    lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                   i32, i32, i32, i32, i32, vp]
+    lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   vp, vp, vp]
+    lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   i32, i32, i32, vp]
     lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
     i64 = ctypes.c_int64

@@ -10,6 +10,7 @@
 // All kernels are HBM/issue bound integer + fp64 work; no tensor cores (no contraction here).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "vkb_math.cuh"
 #include "vkb_lattice.cuh"
@@ -363,8 +364,7 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max, int t_max,
     const int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta,
     double* __restrict__ hinv, double* __restrict__ hfwd, int32_t* __restrict__ cell_box,
-    CellLocal* __restrict__ cell_local, int32_t* __restrict__ tile_count,
-    uint16_t* __restrict__ tile_cells) {
+    int32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_cells) {
     const int page = blockIdx.y;
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
@@ -404,16 +404,6 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     box[1] = y0;
     box[2] = x1;
     box[3] = y1;
-    // float32 re-centred form of the inverse map for the remap kernel's fast path
-    {
-        double Hi[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Hi[i] = ho[i];
-        CellLocal L;
-        make_cell_local(Hi, (int)sx0, (int)sy0, x0, y0, L);
-        cell_local[(size_t)page * c_max + cell] = L;
-    }
-
     // bin into dst tiles
     const int tiles_x = (meta[page].dst_w + VKB_TILE - 1) / VKB_TILE;
     const int tx0 = x0 / VKB_TILE, tx1 = x1 / VKB_TILE, ty0 = y0 / VKB_TILE, ty1 = y1 / VKB_TILE;
@@ -469,77 +459,199 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
 }
 
 // ============================================================================================
-// Fused remap.  Block = 256 threads = 8 warps on one 32 x 32 dst tile; warp w owns rows
-// 4w..4w+3, lane = column.
+// Per-tile candidate records for the remap kernel.
 //
-//   prologue  the tile's candidate cells (<= VKB_TILE_CAP) are staged in shared memory: bbox,
-//             float64 inverse homography, and its float32 re-centred form (CellLocal);
-//   owner     lane-parallel: lane i fetches candidate i's coverage words for the warp's 4 rows
-//             (shifted to the tile's columns), a ballot keeps the candidates that touch the
-//             band, and each survivor is broadcast with shuffles; every pixel keeps the
-//             maximum cell index whose coverage bit is set (= last writer in row-major order);
-//   coords    float32 fast path with a proven error band, float64 path for the <1% of pixels
-//             that sit next to a rounding boundary (vkb_math.cuh);
-//   gather    cv::remap's fixed-point bilinear for Image (C channels), Mask and ScoreMap.
+//   grid_tile_base_kernel     prefix sum over pages of the number of 32 x 32 dst tiles: the
+//                             remap's flat work list (tile_base[n_pages] = all tiles);
+//   grid_tile_offsets_kernel  block per page: exclusive scan of the candidate counts of the
+//                             page's tiles -> where each tile's records start;
+//   grid_tile_records_kernel  warp per tile, lane per candidate: rank the candidates by cell
+//                             index (the remap resolves "last writer wins" by letting later
+//                             records overwrite earlier ones) and write one 64-byte record per
+//                             candidate: bbox, packed (slot, cell column, cell row) and the
+//                             float32 form of the cell's inverse homography re-centred on the
+//                             tile origin (CellLocal, built here from the float64 matrix).
 // ============================================================================================
-template <int C>
-__device__ __forceinline__ void sample_u8(const uint8_t* __restrict__ src, int h, int w, int X, int Y,
-                                          uint8_t* __restrict__ dst) {
-    const int x0 = clamp_short(X >> kInterBits);
-    const int y0 = clamp_short(Y >> kInterBits);
-    const int fx = X & (kInterTab - 1);
-    const int fy = Y & (kInterTab - 1);
-    const int pitch = w * C;  // a page plane is < 2 GiB (checked by the launcher)
-    int p00[C], p01[C], p10[C], p11[C];
-    if ((unsigned)x0 < (unsigned)(w - 1) && (unsigned)y0 < (unsigned)(h - 1)) {  // interior
-        const uint8_t* r0 = src + (y0 * pitch + x0 * C);
-        const uint8_t* r1 = r0 + pitch;
+struct __align__(16) TileSlot {
+    CellLocal loc;
+    int x0, y0, nr, cellf;  // bbox origin, rows - 1, cell | (over mask budget ? 1 << 31 : 0)
+    int info;               // slot | cell column << 6 | cell row << 16
+    int pad[3];
+};
+static_assert(sizeof(TileSlot) == VKB_TILE_SLOT_BYTES, "TileSlot layout is part of the ABI");
+
+__device__ __forceinline__ int page_tiles(const vkb_grid_meta& m) {
+    return ((m.dst_w + VKB_TILE - 1) / VKB_TILE) * ((m.dst_h + VKB_TILE - 1) / VKB_TILE);
+}
+
+// exclusive scan of v over the block (1024 threads); returns the exclusive prefix, adds the
+// block total to `carry` (shared).
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* warp_sums, int* carry) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            p00[c] = __ldg(r0 + c);
-            p01[c] = __ldg(r0 + C + c);
-            p10[c] = __ldg(r1 + c);
-            p11[c] = __ldg(r1 + C + c);
-        }
-    } else {
-        const bool in_x0 = (unsigned)x0 < (unsigned)w, in_x1 = (unsigned)(x0 + 1) < (unsigned)w;
-        const bool in_y0 = (unsigned)y0 < (unsigned)h, in_y1 = (unsigned)(y0 + 1) < (unsigned)h;
-        const uint8_t* r0 = src + ((long long)y0 * pitch + (long long)x0 * C);
-        const uint8_t* r1 = r0 + pitch;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            p00[c] = (in_y0 && in_x0) ? r0[c] : 0;
-            p01[c] = (in_y0 && in_x1) ? r0[C + c] : 0;
-            p10[c] = (in_y1 && in_x0) ? r1[c] : 0;
-            p11[c] = (in_y1 && in_x1) ? r1[C + c] : 0;
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
     }
-    const int gx = kInterTab - fx, gy = kInterTab - fy;
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int ws = warp_sums[lane];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const int a = gx * p00[c] + fx * p01[c];
-        const int b = gx * p10[c] + fx * p11[c];
-        dst[c] = (uint8_t)((gy * a + fy * b + 512) >> 10);
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, ws, d);
+            if (lane >= d) ws += o;
+        }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int base = *carry + (warp > 0 ? warp_sums[warp - 1] : 0);
+    const int total = warp_sums[31];
+    __syncthreads();
+    if (threadIdx.x == 0) *carry += total;
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) grid_tile_base_kernel(const vkb_grid_meta* __restrict__ meta,
+                                                              int n_pages, int32_t* __restrict__ tile_base) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_pages; base += 1024) {
+        const int page = base + threadIdx.x;
+        const int v = page < n_pages ? page_tiles(meta[page]) : 0;
+        const int ex = block_exclusive_scan_1024(v, warp_sums, &carry);
+        if (page < n_pages) tile_base[page] = ex;
+    }
+    if (threadIdx.x == 0) tile_base[n_pages] = carry;
+}
+
+__global__ void __launch_bounds__(1024) grid_tile_offsets_kernel(
+    const vkb_grid_meta* __restrict__ meta, int t_max, const int32_t* __restrict__ tile_count,
+    int32_t* __restrict__ tile_off) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int page = blockIdx.x;
+    const int tiles = min(page_tiles(meta[page]), t_max);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        int v = 0;
+        if (t < tiles) {
+            v = tile_count[(size_t)page * t_max + t];
+            if (v > VKB_TILE_CAP) v = 0;  // overflowing tiles keep no records (slow path)
+        }
+        const int ex = block_exclusive_scan_1024(v, warp_sums, &carry);
+        if (t < tiles) tile_off[(size_t)page * t_max + t] = ex;
     }
 }
 
-static_assert(sizeof(CellLocal) == VKB_CELL_LOCAL_BYTES, "CellLocal layout is part of the ABI");
+__global__ void __launch_bounds__(128) grid_tile_records_kernel(
+    const vkb_grid_page* __restrict__ pages, const vkb_grid_meta* __restrict__ meta, int c_max,
+    int t_max, int s_cap, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
+    const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
+    const int32_t* __restrict__ tile_off, TileSlot* __restrict__ slots) {
+    const int page = blockIdx.y;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int dst_w = meta[page].dst_w;
+    const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
+    if (t >= min(page_tiles(meta[page]), t_max)) return;
+    const size_t pt = (size_t)page * t_max + t;
+    const int count = tile_count[pt];
+    const int off = tile_off[pt];
+    if (count > VKB_TILE_CAP || off + count > s_cap) return;  // the remap takes its slow path
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
+    const int ca = lane < count ? (int)cells[lane] : 0x7fffffff;
+    const int cb = lane + 32 < count ? (int)cells[lane + 32] : 0x7fffffff;
+    int rank_a = 0, rank_b = 0;
+    const int na = min(count, 32), nb = max(count - 32, 0);
+    for (int i = 0; i < na; ++i) {
+        const int o = __shfl_sync(0xffffffffu, ca, i);
+        rank_a += o < ca;
+        rank_b += o < cb;
+    }
+    for (int i = 0; i < nb; ++i) {
+        const int o = __shfl_sync(0xffffffffu, cb, i);
+        rank_a += o < ca;
+        rank_b += o < cb;
+    }
+    const int ccols = pages[page].cols - 1;
+    const int gs = pages[page].grid_size;
+    const size_t page_cell0 = (size_t)page * c_max;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int s = lane + 32 * half;
+        if (s >= count) break;
+        const int cell = half ? cb : ca;
+        const int rank = half ? rank_b : rank_a;
+        const int4 b = cell_box[page_cell0 + cell];
+        const int r = cell / ccols, c = cell - r * ccols;
+        double H[9];
+        const double* __restrict__ hp = hinv + (page_cell0 + cell) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = hp[i];
+        TileSlot rec;
+        make_cell_local(H, c * gs, r * gs, tx * VKB_TILE, ty * VKB_TILE, rec.loc);
+        rec.x0 = b.x;
+        rec.y0 = b.y;
+        rec.nr = b.w - b.y;
+        rec.cellf = cell | ((b.z & 0x40000000) ? (int)0x80000000 : 0);
+        rec.info = rank | (c << 6) | (r << 16);
+        rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+        int4* __restrict__ dst = reinterpret_cast<int4*>(slots + ((size_t)page * s_cap + off + rank));
+        const int4* src = reinterpret_cast<const int4*>(&rec);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+        dst[3] = src[3];
+    }
+}
 
-struct RemapShared {
-    CellLocal loc[VKB_TILE_CAP];
-    int box[VKB_TILE_CAP][4];
-    int cell[VKB_TILE_CAP];
+// ============================================================================================
+// Fused remap.  Block = 32 x (32 / R) threads on one 32 x 32 dst tile; warp w owns rows
+// R*w .. R*w + R-1, lane = column.
+//
+//   prologue  the tile's candidate cells (<= VKB_TILE_CAP, ascending cell order) are staged in
+//             shared memory: bbox + packed (slot, cell column, cell row), and the float32 form
+//             of the cell's inverse homography re-centred on the tile origin (CellLocal, built
+//             here from the float64 matrix);
+//   owner     lane-parallel: lane i fetches candidate i's coverage words for the warp's R rows
+//             (shifted to the tile's columns), a ballot keeps the candidates that touch the
+//             band, and each survivor is broadcast with shuffles in ascending order; a pixel
+//             whose coverage bit is set takes the survivor's key, so the last (= largest) cell
+//             wins, exactly like the reference's cell-by-cell map writes;
+//   coords    float32 fast path with a proven acceptance test, float64 path for the pixels that
+//             sit next to a rounding boundary (vkb_math.cuh);
+//   gather    cv::remap's fixed-point bilinear for Image (C channels), Mask and ScoreMap.  The
+//             L1 data pipe is the scarce resource here, so the RGB taps of a row (6 contiguous
+//             bytes at any alignment) come in as 2-3 aligned 32-bit loads, are aligned with
+//             PRMT and blended horizontally with IDP.4A (byte weights) instead of 6 byte loads.
+// ============================================================================================
+#ifndef VKB_REMAP_ROWS
+#define VKB_REMAP_ROWS 4  // dst rows per thread of the remap kernel (4 or 8)
+#endif
+
+struct __align__(16) RemapShared {
+    TileSlot slot[VKB_TILE_CAP];
 };
 
 // Rare paths are kept out of line so the hot loop stays small (instruction cache).
-__device__ __noinline__ void cell_coord_exact(const double* __restrict__ H, int x, int y, int* X,
-                                              int* Y) {
-    cell_coord(H, x, y, *X, *Y);
+__device__ __noinline__ int2 cell_coord_exact(const double* __restrict__ H, int x, int y) {
+    int X, Y;
+    cell_coord(H, x, y, X, Y);
+    return make_int2(X, Y);
 }
 
 // coverage of one over-budget cell on row y, restricted to the 32 columns starting at tx0
 __device__ __noinline__ uint32_t cell_row_window_slow(const int32_t* __restrict__ lat, int cols,
-                                                      int ccols, int cell, int y, int tx0) {
+                                                      int cell, int y, int tx0) {
+    const int ccols = cols - 1;
     const int r = cell / ccols, c = cell - r * ccols;
     const int i00 = r * cols + c, i01 = i00 + 1, i11 = i00 + cols + 1, i10 = i00 + cols;
     const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
@@ -549,141 +661,403 @@ __device__ __noinline__ uint32_t cell_row_window_slow(const int32_t* __restrict_
     return bits;
 }
 
-__device__ __forceinline__ uint32_t cell_row_window(const uint32_t* __restrict__ cell_masks,
-                                                    const int32_t* __restrict__ lat, int cols,
-                                                    int ccols, int cell, bool flagged, int bx0,
-                                                    int by0, int y, int tx0) {
-    if (flagged) return cell_row_window_slow(lat, cols, ccols, cell, y, tx0);
-    const uint32_t w = cell_masks[cell * VKB_CELL_MASK_WORDS + (y - by0)];
-    const int rel = tx0 - bx0;  // in (-32, 32) because the boxes overlap
-    return rel >= 0 ? (w >> rel) : (w << (-rel));
+// ---- bilinear taps ---------------------------------------------------------------------------
+// (sum p*w + 2^14) >> 15 with w = (32-fy)(32-fx)*32 ...: all weights share the factor 32, so it
+// equals (gy*a + fy*b + 512) >> 10 with a, b the horizontally blended rows (gx*p0 + fx*p1).
+
+// One row of an RGB pixel pair: the 6 bytes at `p` (any alignment) as two words
+// lo = R0 G0 B0 R1, hi = G1 B1 . .  (2 aligned 32-bit loads, a third when the bytes straddle).
+struct RowRgb {
+    uint32_t w0, w1, w2, off;
+};
+
+__device__ __forceinline__ RowRgb row_rgb_load(const uint8_t* __restrict__ p) {
+    RowRgb r;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    r.off = (uint32_t)addr & 3u;
+    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(addr - r.off);
+    r.w0 = __ldg(q);
+    r.w1 = __ldg(q + 1);
+    r.w2 = 0;
+    if (r.off == 3u) r.w2 = __ldg(q + 2);  // only then do the 6 bytes reach into a third word
+    return r;
 }
 
-template <int C, bool MASK, bool SCORE>
-__global__ void __launch_bounds__(256, (C == 3 && !MASK && !SCORE) ? 5 : 4) grid_remap_kernel(
-    const vkb_grid_page* __restrict__ pages, const vkb_planes* __restrict__ planes,
-    int c_max, int t_max, const vkb_grid_meta* __restrict__ meta, const double* __restrict__ hinv,
-    const int32_t* __restrict__ cell_box, const CellLocal* __restrict__ cell_local,
-    const uint32_t* __restrict__ cell_masks,
-    const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
-    const int32_t* __restrict__ lattice_i, int p_max) {
-    const int page = blockIdx.z;
-    const int dst_h = meta[page].dst_h, dst_w = meta[page].dst_w;
-    const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
-    const int tiles_y = (dst_h + VKB_TILE - 1) / VKB_TILE;
-    if ((int)blockIdx.x >= tiles_x || (int)blockIdx.y >= tiles_y) return;
+// horizontal blend with IDP.4A: wr / wg0,wg1 / wb0,wb1 are byte-weight words on (lo, hi)
+__device__ __forceinline__ void row_rgb_blend(const RowRgb& row, uint32_t wr, uint32_t wg0,
+                                              uint32_t wg1, uint32_t wb0, uint32_t wb1, int& r,
+                                              int& g, int& b) {
+    const uint32_t sel = 0x3210u + row.off * 0x1111u;
+    const uint32_t lo = __byte_perm(row.w0, row.w1, sel);
+    const uint32_t hi = __byte_perm(row.w1, row.w2, sel);
+    r = (int)__dp4a(lo, wr, 0u);
+    g = (int)__dp4a(hi, wg1, __dp4a(lo, wg0, 0u));
+    b = (int)__dp4a(hi, wb1, __dp4a(lo, wb0, 0u));
+}
 
-    __shared__ RemapShared sm;
+// Branch-free taps.  The 2 x 2 footprint at (x0, y0) is read from the in-image window that
+// starts at xs = clamp(x0, 0, w-2), ys = clamp(y0, 0, h-2); taps that fall outside the image
+// (BORDER_CONSTANT 0) get weight 0 and the surviving tap keeps its own weight:
+//   x0 == xs: (32-fx, fx)   x0 == xs-1: (fx, 0)   x0 == xs+1: (0, 32-fx)   otherwise (0, 0).
+// No divergent border branch, so the loads of all pixels of a thread can be in flight together.
+// Needs w >= 2 and h >= 2 (the kernel routes smaller planes to sample_u8_small).
+struct TapWeights {
+    int xs, ys;
+    int wx0, wx1, wy0, wy1;
+};
+
+__device__ __forceinline__ TapWeights tap_weights(int X, int Y, int h, int w) {
+    // sizes are below 32768 (checked by the caller), so cv's saturate_cast<short> of the
+    // integer coordinates cannot turn an outside tap into an inside one
+    const int x0 = X >> kInterBits, y0 = Y >> kInterBits;
+    const int fx = X & (kInterTab - 1), fy = Y & (kInterTab - 1);
+    TapWeights t;
+    t.xs = min(max(x0, 0), w - 2);
+    t.ys = min(max(y0, 0), h - 2);
+    const int dx = x0 - t.xs, dy = y0 - t.ys;
+    t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
+    t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
+    t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
+    t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
+    return t;
+}
+
+// Taps of one pixel, requested now and blended later (so a thread keeps the loads of all its
+// pixels in flight).
+template <int C>
+struct Taps {
+    TapWeights t;
+    RowRgb rgb[2];                // C == 3
+    int p[C == 3 ? 1 : 4 * C];    // C != 3: p00, p01, p10, p11 per channel
+};
+
+template <int C>
+__device__ __forceinline__ void taps_load(const uint8_t* __restrict__ src, int h, int w, int X,
+                                          int Y, Taps<C>& k) {
+    k.t = tap_weights(X, Y, h, w);
+    const int pitch = w * C;  // a page plane is < 2 GiB (checked by the caller)
+    const uint8_t* r0 = src + (k.t.ys * pitch + k.t.xs * C);
+    const uint8_t* r1 = r0 + pitch;
+    if (C == 3) {
+        k.rgb[0] = row_rgb_load(r0);
+        k.rgb[1] = row_rgb_load(r1);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            k.p[(4 * c + 0) % (C == 3 ? 1 : 4 * C)] = __ldg(r0 + c);
+            k.p[(4 * c + 1) % (C == 3 ? 1 : 4 * C)] = __ldg(r0 + C + c);
+            k.p[(4 * c + 2) % (C == 3 ? 1 : 4 * C)] = __ldg(r1 + c);
+            k.p[(4 * c + 3) % (C == 3 ? 1 : 4 * C)] = __ldg(r1 + C + c);
+        }
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void taps_blend(const Taps<C>& k, uint8_t* __restrict__ out) {
+    const TapWeights& t = k.t;
+    if (C == 3) {
+        const uint32_t wr = (uint32_t)t.wx0 | ((uint32_t)t.wx1 << 24);
+        const uint32_t wg0 = (uint32_t)t.wx0 << 8, wg1 = (uint32_t)t.wx1;
+        const uint32_t wb0 = (uint32_t)t.wx0 << 16, wb1 = (uint32_t)t.wx1 << 8;
+        int a[3], b[3];
+        row_rgb_blend(k.rgb[0], wr, wg0, wg1, wb0, wb1, a[0], a[1], a[2]);
+        row_rgb_blend(k.rgb[1], wr, wg0, wg1, wb0, wb1, b[0], b[1], b[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c % C] = (uint8_t)((t.wy0 * a[c] + t.wy1 * b[c] + 512) >> 10);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            constexpr int M = C == 3 ? 1 : 4 * C;
+            const int a = t.wx0 * k.p[(4 * c + 0) % M] + t.wx1 * k.p[(4 * c + 1) % M];
+            const int b = t.wx0 * k.p[(4 * c + 2) % M] + t.wx1 * k.p[(4 * c + 3) % M];
+            out[c] = (uint8_t)((t.wy0 * a + t.wy1 * b + 512) >> 10);
+        }
+    }
+}
+
+// planes narrower or shorter than 2 px: plain per-tap bounds checks
+template <int C>
+__device__ __noinline__ uint32_t sample_u8_small(const uint8_t* __restrict__ src, int h, int w,
+                                                 int X, int Y) {
+    uint8_t out[4] = {0, 0, 0, 0};
+    bilinear_u8<C>(src, h, w, (long long)w * C, X, Y, out);
+    return out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+}
+
+// One work item of the persistent remap kernel (uniform across the block).
+struct RemapTile {
+    int page, tx0, ty0, count, off;
+};
+
+__device__ __forceinline__ RemapTile remap_tile_header(int w, int page, const vkb_planes* __restrict__ planes,
+                                                       const int32_t* __restrict__ tile_base, int t_max,
+                                                       const int32_t* __restrict__ tile_count,
+                                                       const int32_t* __restrict__ tile_off) {
+    RemapTile t;
+    while (w >= tile_base[page + 1]) ++page;  // work items are handed out in order
+    const int local = w - tile_base[page];
+    const int tiles_x = (planes[page].dst_w + VKB_TILE - 1) / VKB_TILE;
+    const int ty = local / tiles_x;
+    t.page = page;
+    t.tx0 = (local - ty * tiles_x) * VKB_TILE;
+    t.ty0 = ty * VKB_TILE;
+    const size_t idx = (size_t)page * t_max + local;
+    t.count = tile_count[idx];
+    t.off = tile_off[idx];
+    return t;
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
+template <int C, bool MASK, bool SCORE, int R>
+__global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_remap_kernel(
+    const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
+    int c_max, int t_max, int p_max, int s_cap, const double* __restrict__ hinv,
+    const int4* __restrict__ cell_box, const uint32_t* __restrict__ cell_masks,
+    const int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_off,
+    const int32_t* __restrict__ tile_base, const TileSlot* __restrict__ slots,
+    const int32_t* __restrict__ lattice_i, const int dbg) {
+    constexpr int kThreads = 32 * (VKB_TILE / R);
+    __shared__ RemapShared sm[2];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.y * tiles_x + blockIdx.x;
-    const int count = tile_count[(size_t)page * t_max + tile];
-    const bool fast = count <= VKB_TILE_CAP;
-    const vkb_planes pl = planes[page];
-    const int cols = pages[page].cols, rows = pages[page].rows;
-    const int src_h = pl.src_h, src_w = pl.src_w;
-    const int ccols = cols - 1;
-    const int n_cells = (rows - 1) * ccols;
-    const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
-    const uint32_t* page_masks = cell_masks + (size_t)page * c_max * VKB_CELL_MASK_WORDS;
-    const int32_t* page_box = cell_box + (size_t)page * c_max * 4;
-    const double* page_hinv = hinv + (size_t)page * c_max * 9;
 
-    if (fast && tid < count) {
-        const int cell = tile_cells[((size_t)page * t_max + tile) * VKB_TILE_CAP + tid];
-        const int4 b = *reinterpret_cast<const int4*>(page_box + (size_t)cell * 4);
-        sm.box[tid][0] = b.x; sm.box[tid][1] = b.y; sm.box[tid][2] = b.z; sm.box[tid][3] = b.w;
-        sm.cell[tid] = cell;
-        const int4* lsrc = reinterpret_cast<const int4*>(cell_local + (size_t)page * c_max + cell);
-        int4* ldst = reinterpret_cast<int4*>(&sm.loc[tid]);
-        ldst[0] = lsrc[0];
-        ldst[1] = lsrc[1];
-        ldst[2] = lsrc[2];
-    }
+    // contiguous share of the flat tile list
+    const int total = tile_base[n_pages];
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int w_begin = blockIdx.x * per;
+    const int w_end = min(total, w_begin + per);
+    if (w_begin >= w_end) return;
+
+    auto usable = [&](const RemapTile& t) { return t.count <= VKB_TILE_CAP && t.off + t.count <= s_cap; };
+    auto prefetch = [&](const RemapTile& t, int buf) {
+        if (usable(t)) {
+            const char* g = reinterpret_cast<const char*>(slots + ((size_t)t.page * s_cap + t.off));
+            char* d = reinterpret_cast<char*>(sm[buf].slot);
+            for (int i = tid; i < t.count * (VKB_TILE_SLOT_BYTES / 16); i += kThreads)
+                cp_async_16(d + i * 16, g + i * 16);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    RemapTile cur = remap_tile_header(w_begin, 0, planes, tile_base, t_max, tile_count, tile_off);
+    RemapTile nxt = cur;
+    if (w_begin + 1 < w_end)
+        nxt = remap_tile_header(w_begin + 1, cur.page, planes, tile_base, t_max, tile_count, tile_off);
+    prefetch(cur, 0);
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
 
-    const int tx0 = blockIdx.x * VKB_TILE;
-    const int x = tx0 + lane;
-    const int ry0 = blockIdx.y * VKB_TILE + warp * 4;
-    if (ry0 >= dst_h) return;
+    // per-page state, reloaded when the page changes
+    int ctx_page = -1;
+    int dst_h = 0, dst_w = 0, src_h = 0, src_w = 0, cols = 0, grid32 = 0;
+    float t_odd = 0.f, t_even = 0.f;
+    const uint8_t* __restrict__ src_image = nullptr;
+    uint8_t* __restrict__ dst_image = nullptr;
+    const uint8_t* __restrict__ src_mask = nullptr;
+    uint8_t* __restrict__ dst_mask = nullptr;
+    const float* __restrict__ src_score = nullptr;
+    float* __restrict__ dst_score = nullptr;
 
-    // ---- owner ---------------------------------------------------------------------------
-    int key[4] = {-1, -1, -1, -1};
-    const int n_cand = fast ? count : n_cells;
-    for (int base = 0; base < n_cand; base += 32) {
-        const int s = base + lane;
-        uint32_t win[4] = {0u, 0u, 0u, 0u};
-        int my_key = -1;
-        if (s < n_cand) {
-            int bx0, by0, bx1, by1, cell;
-            if (fast) {
-                bx0 = sm.box[s][0]; by0 = sm.box[s][1]; bx1 = sm.box[s][2]; by1 = sm.box[s][3];
-                cell = sm.cell[s];
-            } else {
-                const int4 b = *reinterpret_cast<const int4*>(page_box + (size_t)s * 4);
-                bx0 = b.x; by0 = b.y; bx1 = b.z; by1 = b.w;
-                cell = s;
-            }
-            const bool flagged = (bx1 & 0x40000000) != 0;
-            bx1 &= 0x3FFFFFFF;
-            if (!(by1 < ry0 || by0 > ry0 + 3 || bx1 < tx0 || bx0 > tx0 + 31)) {
-                my_key = fast ? ((cell << 6) | s) : (cell << 6);
+    for (int w = w_begin; w < w_end; ++w) {
+        const int buf = (w - w_begin) & 1;
+        // records of the next tile start moving now; the header of the one after is requested
+        // so its loads are in flight while this tile is processed
+        RemapTile nn = nxt;
+        if (w + 1 < w_end) prefetch(nxt, buf ^ 1);
+        if (w + 2 < w_end)
+            nn = remap_tile_header(w + 2, nxt.page, planes, tile_base, t_max, tile_count, tile_off);
+
+        const int page = cur.page;
+        if (page != ctx_page) {
+            const vkb_planes* __restrict__ pl = planes + page;
+            dst_h = pl->dst_h; dst_w = pl->dst_w; src_h = pl->src_h; src_w = pl->src_w;
+            src_image = pl->src_image; dst_image = pl->dst_image;
+            src_mask = pl->src_mask; dst_mask = pl->dst_mask;
+            src_score = pl->src_score; dst_score = pl->dst_score;
+            cols = pages[page].cols;
+            grid32 = pages[page].grid_size * 32;
+            fast_thresholds(max(src_h, src_w), t_odd, t_even);
+            ctx_page = page;
+        }
+        const TileSlot* __restrict__ S = sm[buf].slot;
+        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
+        const bool fast = usable(cur);
+        const size_t page_cell0 = (size_t)page * c_max;
+        const int x = tx0 + lane;
+        const int ry0 = ty0 + warp * R;
+
+        if (ry0 < dst_h) {
+            const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
+            // ---- owner ---------------------------------------------------------------------
+            // key: fast mode -> info of the owning slot; overflow mode -> cell index; -1 = none
+            int key[R];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int y = ry0 + j;
-                    if (y >= by0 && y <= by1)
-                        win[j] = cell_row_window(page_masks, lat, cols, ccols, cell, flagged, bx0,
-                                                 by0, y, tx0);
+            for (int j = 0; j < R; ++j) key[j] = -1;
+            int n_cand = fast ? count : (pages[page].rows - 1) * (cols - 1);
+            if (dbg & 4) {
+                n_cand = 0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) key[j] = (fast && count > 0) ? S[0].info : -1;
+            }
+            for (int base = 0; base < n_cand; base += 32) {
+                const int s = base + lane;
+                uint32_t win[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) win[j] = 0u;
+                int my_key = s;
+                if (s < n_cand) {
+                    int4 b;
+                    if (fast) {
+                        b = *reinterpret_cast<const int4*>(&S[s].x0);
+                        my_key = S[s].info;
+                    } else {
+                        const int4 g = cell_box[page_cell0 + s];
+                        b = make_int4(g.x, g.y, g.w - g.y, s | ((g.z & 0x40000000) ? (int)0x80000000 : 0));
+                    }
+                    const int r = ry0 - b.y;    // band row 0 relative to the bbox
+                    const int rel = tx0 - b.x;  // tile column 0 relative to the bbox
+                    if (r + (R - 1) >= 0 && r <= b.z) {
+                        if (b.w >= 0) {
+                            if (fast || (rel > -32 && rel < 32)) {
+                                const uint32_t* __restrict__ m = page_masks + (b.w * VKB_CELL_MASK_WORDS + r);
+#pragma unroll
+                                for (int j = 0; j < R; ++j) {
+                                    if ((unsigned)(r + j) <= (unsigned)b.z) {
+                                        const uint32_t wd = __ldg(m + j);
+                                        win[j] = rel >= 0 ? (wd >> rel) : (wd << (-rel));
+                                    }
+                                }
+                            }
+                        } else {
+                            const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
+#pragma unroll
+                            for (int j = 0; j < R; ++j)
+                                win[j] = cell_row_window_slow(lat, cols, b.w & 0x7FFFFFFF, ry0 + j, tx0);
+                        }
+                    }
+                }
+                uint32_t any = win[0];
+#pragma unroll
+                for (int j = 1; j < R; ++j) any |= win[j];
+                unsigned active = __ballot_sync(0xffffffffu, any != 0u);
+                while (active) {
+                    const int src_lane = __ffs(active) - 1;
+                    active &= active - 1;
+                    const int k = __shfl_sync(0xffffffffu, my_key, src_lane);
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const uint32_t wd = __shfl_sync(0xffffffffu, win[j], src_lane);
+                        if ((wd >> lane) & 1u) key[j] = k;
+                    }
+                }
+            }
+
+            if (x < dst_w) {
+                // ---- coordinates -----------------------------------------------------------
+                const float xr = (float)lane;
+                const float yr0 = (float)(warp * R);
+                int X[R], Y[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    X[j] = 0;
+                    Y[j] = 0;
+                    if (dbg & 8) {
+                        X[j] = (x * 29) & 32767;
+                        Y[j] = ((ry0 + j) * 29) & 32767;
+                    } else if (key[j] >= 0) {
+                        int cell = key[j];
+                        bool done = false;
+                        if (fast) {
+                            const int slot = key[j] & 63;
+                            const int c = (key[j] >> 6) & 1023, r = key[j] >> 16;
+                            done = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j,
+                                                   c * grid32 - kRoundMagicBits,
+                                                   r * grid32 - kRoundMagicBits, t_odd, t_even, X[j], Y[j]);
+                            if (!done) cell = S[slot].cellf & 0x7FFFFFFF;
+                        }
+                        if (!done) {
+                            const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
+                            X[j] = e.x;
+                            Y[j] = e.y;
+                        }
+                    }
+                }
+
+                // ---- gather ----------------------------------------------------------------
+                const int di0 = ry0 * dst_w + x;
+                const bool tiny = src_h < 2 || src_w < 2;
+                if (C > 0) {
+                    constexpr int CC = C > 0 ? C : 1;
+                    uint8_t px[R][CC];
+                    if (dbg & 2) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j)
+#pragma unroll
+                            for (int c = 0; c < CC; ++c) px[j][c] = (uint8_t)((X[j] >> (c * 3)) ^ Y[j]);
+                    } else if (tiny) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j) {
+                            const uint32_t v = sample_u8_small<CC>(src_image, src_h, src_w, X[j], Y[j]);
+#pragma unroll
+                            for (int c = 0; c < CC; ++c) px[j][c] = (uint8_t)(v >> (8 * c));
+                        }
+                    } else {
+                        Taps<CC> taps[R];
+#pragma unroll
+                        for (int j = 0; j < R; ++j) taps_load<CC>(src_image, src_h, src_w, X[j], Y[j], taps[j]);
+#pragma unroll
+                        for (int j = 0; j < R; ++j) taps_blend<CC>(taps[j], px[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        if (ry0 + j < dst_h && (!(dbg & 1) || (px[j][0] == 77 && X[j] == 123457))) {
+                            uint8_t* d = dst_image + (di0 + j * dst_w) * CC;
+                            if (CC == 4) {
+                                *reinterpret_cast<uchar4*>(d) =
+                                    make_uchar4(px[j][0], px[j][1 % CC], px[j][2 % CC], px[j][3 % CC]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CC; ++c) d[c] = px[j][c];
+                            }
+                        }
+                    }
+                }
+                if (MASK) {
+                    uint8_t m[R][1];
+                    if (tiny) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            m[j][0] = (uint8_t)sample_u8_small<1>(src_mask, src_h, src_w, X[j], Y[j]);
+                    } else {
+                        Taps<1> taps[R];
+#pragma unroll
+                        for (int j = 0; j < R; ++j) taps_load<1>(src_mask, src_h, src_w, X[j], Y[j], taps[j]);
+#pragma unroll
+                        for (int j = 0; j < R; ++j) taps_blend<1>(taps[j], m[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (ry0 + j < dst_h) dst_mask[di0 + j * dst_w] = m[j][0];
+                }
+                if (SCORE) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const float v = bilinear_f32(src_score, src_h, src_w, src_w, X[j], Y[j]);
+                        if (ry0 + j < dst_h) dst_score[di0 + j * dst_w] = v;
+                    }
                 }
             }
         }
-        unsigned active = __ballot_sync(0xffffffffu, (win[0] | win[1] | win[2] | win[3]) != 0u);
-        while (active) {
-            const int src_lane = __ffs(active) - 1;
-            active &= active - 1;
-            const int k = __shfl_sync(0xffffffffu, my_key, src_lane);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t w = __shfl_sync(0xffffffffu, win[j], src_lane);
-                key[j] = max(key[j], ((w >> lane) & 1u) ? k : -1);
-            }
-        }
-    }
-    if (x >= dst_w) return;
 
-    // ---- coordinates + gather ------------------------------------------------------------
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int y = ry0 + j;
-        if (y >= dst_h) break;
-        int X = 0, Y = 0;
-        if (key[j] >= 0) {
-            if (fast) {
-                const int slot = key[j] & 63;
-                if (!cell_coord_fast(sm.loc[slot], x, y, X, Y))
-                    cell_coord_exact(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, &X, &Y);
-            } else {
-                cell_coord_exact(page_hinv + (size_t)(key[j] >> 6) * 9, x, y, &X, &Y);
-            }
-        }
-        const int di = y * dst_w + x;
-        if (C > 0) {
-            uint8_t px[C > 0 ? C : 1];
-            sample_u8<(C > 0 ? C : 1)>(pl.src_image, src_h, src_w, X, Y, px);
-            uint8_t* d = pl.dst_image + di * C;
-            if (C == 4) {
-                *reinterpret_cast<uchar4*>(d) = make_uchar4(px[0], px[1], px[2], px[3 % (C > 0 ? C : 1)]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) d[c] = px[c];
-            }
-        }
-        if (MASK) {
-            uint8_t m[1];
-            sample_u8<1>(pl.src_mask, src_h, src_w, X, Y, m);
-            pl.dst_mask[di] = m[0];
-        }
-        if (SCORE) pl.dst_score[di] = bilinear_f32(pl.src_score, src_h, src_w, src_w, X, Y);
+        // the next tile's records have landed and nobody reads this tile's any more
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        cur = nxt;
+        nxt = nn;
     }
 }
 
@@ -855,49 +1229,73 @@ extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, in
 }
 
 extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
-                              int32_t c_max, int32_t t_max, const int32_t* lattice_i,
+                              int32_t c_max, int32_t t_max, int32_t s_cap, const int32_t* lattice_i,
                               vkb_grid_meta* meta, double* hinv, double* hfwd, int32_t* cell_box,
-                              void* cell_local, uint32_t* cell_masks, int32_t* tile_count,
-                              uint16_t* tile_cells, void* stream) {
-    VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_local && cell_masks
-                    && tile_count && tile_cells, "bad arguments");
+                              uint32_t* cell_masks, int32_t* tile_count, uint16_t* tile_cells,
+                              int32_t* tile_off, int32_t* tile_base, void* tile_slots,
+                              void* stream) {
+    VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_masks && tile_count
+                    && tile_cells && tile_off && tile_base && tile_slots, "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(c_max > 0 && c_max <= 65535, "at most 65535 cells per page");
+    VKB_REQUIRE(t_max > 0 && s_cap > 0, "empty tile workspace");
+    VKB_REQUIRE((long long)n_pages * t_max < (1ll << 31), "too many tiles in one launch");
     cudaStream_t st = (cudaStream_t)stream;
     VKB_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)n_pages * t_max, st));
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
-        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box,
-        reinterpret_cast<CellLocal*>(cell_local), tile_count, tile_cells);
+        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
     grid_masks_kernel<<<dim3((c_max + 3) / 4, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
                                                                      cell_box, cell_masks);
-    return check_launch("grid_masks_kernel");
+    rc = check_launch("grid_masks_kernel");
+    if (rc) return rc;
+    grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);
+    grid_tile_offsets_kernel<<<n_pages, 1024, 0, st>>>(meta, t_max, tile_count, tile_off);
+    rc = check_launch("grid_tile_offsets_kernel");
+    if (rc) return rc;
+    grid_tile_records_kernel<<<dim3((t_max + 3) / 4, n_pages), 128, 0, st>>>(
+        pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
+        tile_cells, tile_off, reinterpret_cast<TileSlot*>(tile_slots));
+    return check_launch("grid_tile_records_kernel");
+}
+
+static int remap_grid_blocks(int blocks_per_sm) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess
+            || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess
+            || sm_count <= 0)
+            sm_count = 148;
+    }
+    return sm_count * blocks_per_sm;
 }
 
 extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
-                              int32_t p_max, int32_t c_max, int32_t t_max,
-                              const int32_t* lattice_i, const vkb_grid_meta* meta,
-                              const double* hinv, const int32_t* cell_box,
-                              const void* cell_local, const uint32_t* cell_masks,
-                              const int32_t* tile_count, const uint16_t* tile_cells,
-                              int32_t max_dst_h, int32_t max_dst_w, int32_t image_channels,
-                              int32_t has_mask, int32_t has_score, void* stream) {
-    VKB_REQUIRE(pages && planes && lattice_i && meta && hinv && cell_box && cell_local && cell_masks
-                    && tile_count && tile_cells, "bad arguments");
+                              int32_t p_max, int32_t c_max, int32_t t_max, int32_t s_cap,
+                              const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
+                              const uint32_t* cell_masks, const int32_t* tile_count,
+                              const int32_t* tile_off, const int32_t* tile_base,
+                              const void* tile_slots, int32_t image_channels, int32_t has_mask,
+                              int32_t has_score, void* stream) {
+    VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
+                    && tile_off && tile_base && tile_slots, "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
-    VKB_REQUIRE(max_dst_h > 0 && max_dst_w > 0, "empty destination");
     VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
                     || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
     VKB_REQUIRE(image_channels || has_mask || has_score, "nothing to remap");
-    dim3 grid((max_dst_w + VKB_TILE - 1) / VKB_TILE, (max_dst_h + VKB_TILE - 1) / VKB_TILE, n_pages);
-    VKB_REQUIRE((long long)grid.x * grid.y <= t_max, "t_max smaller than the tile grid");
     cudaStream_t st = (cudaStream_t)stream;
+    constexpr int R = VKB_REMAP_ROWS;
+    constexpr int kBlocksPerSm = (R == 4) ? 4 : 8;
+    const int grid = remap_grid_blocks(kBlocksPerSm);
+    const char* dbg_env = getenv("VKB_REMAP_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
 #define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
-    grid_remap_kernel<CH, M, S><<<grid, 256, 0, st>>>(                                         \
-        pages, planes, c_max, t_max, meta, hinv, cell_box,                                     \
-        reinterpret_cast<const CellLocal*>(cell_local), cell_masks, tile_count, tile_cells,    \
-        lattice_i, p_max)
+    grid_remap_kernel<CH, M, S, R><<<grid, 32 * (VKB_TILE / R), 0, st>>>(                      \
+        planes, pages, n_pages, c_max, t_max, p_max, s_cap, hinv,                              \
+        reinterpret_cast<const int4*>(cell_box), cell_masks, tile_count, tile_off, tile_base,  \
+        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, dbg)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
     switch (key) {
         case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;

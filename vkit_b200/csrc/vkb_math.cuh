@@ -181,46 +181,35 @@ VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& 
 // Error-bounded float32 evaluation of cell_coord.
 //
 // The source lattice is integer, so inside a cell the source coordinate is  u = sx0 + du  with
-// du in roughly [-2, g+2].  du is evaluated in float32 from the homography re-centred on the
-// cell (dst bbox corner -> offset from the src corner): magnitudes stay below ~64, so the
-// absolute error of 32*du is far below the 1/32 px quantum.  The reference rounds twice
-// (float64 -> float32 map value, then round(32 * map)); both roundings can only change the
-// result when 32*u lies within  32*halfulp_f32(u) + slack  of a half integer.  Outside that
-// band the float32 result is provably the reference's; inside it the caller falls back to the
-// float64 path.  kFastSlack bounds the float32 evaluation error of 32*du (validated in
-// tests/test_hostsim.py: observed max error is > 8x smaller).
+// du in roughly [-2, g+2].  f = 32*du is evaluated in float32 from the homography re-centred on
+// the origin of the 32 x 32 dst tile the pixel lies in (tile origin -> offset from the cell's
+// src corner, numerators pre-scaled by 32): magnitudes stay in the low thousands, so the
+// absolute error of f is far below the 1/32 px quantum.
+//
+// The reference rounds twice: u (float64) -> float32 map value m, then X = rint(32 * m), half
+// to even.  With t = 32 * u, K an integer and T = K + 0.5: every t within h = 32 * halfulp32(u)
+// of T rounds to the float32 value T itself, which rint() then sends to the EVEN neighbour.
+// So the set of t that produce an odd X is (X - 0.5 + h, X + 0.5 - h) and the set that produce
+// an even X is [X - 0.5 - h, X + 0.5 + h].  With Xi = nearest integer of the float32 estimate
+// and d = f - Xi, the estimate therefore IS the reference's result whenever
+//     |d| < 0.5 - h - eps   (Xi odd)        |d| < 0.5 + h - eps   (Xi even)
+// where eps (kFastSlack) bounds the float32 evaluation error of f; otherwise the caller takes
+// the float64 path.  The kernel uses one pair of thresholds per page: h_max of the largest
+// source coordinate for odd results, h = 0 for even ones (both conservative).
+// tests/test_hostsim.py audits all of this on every golden grid case (observed evaluation
+// error is > 4x below kFastSlack; 0 wrong results among accepted pixels).
 // ---------------------------------------------------------------------------------------
 struct CellLocal {
-    float a0, a1, a2;  // numerator of du_x
-    float b0, b1, b2;  // numerator of du_y
-    float g, h;        // denominator g*x' + h*y' + 1
-    int sx0, sy0;      // src corner of the cell
-    int cx, cy;        // dst reference point (bbox corner): x' = x - cx
+    float a0, a1, a2, g;  // 32 * numerator of du_x = a0*x' + a1*y' + a2 ; denominator g*x' + h*y' + 1
+    float b0, b1, b2, h;  // 32 * numerator of du_y          (x', y') = pixel - tile origin
 };
 
-constexpr float kFastSlack = 2.0e-3f;  // in units of 1/32 px
+constexpr float kFastSlack = 1.0e-3f;          // in units of 1/32 px
+constexpr float kFastRange = 1024.0f;          // |32*du| accepted by the fast path (32 px)
+constexpr float kRoundMagic = 12582912.0f;     // 1.5 * 2^23: (v + magic) rounds v half to even
+constexpr int kRoundMagicBits = 0x4B400000;    // bit pattern of kRoundMagic
 
-VKB_HD void make_cell_local(const double* __restrict__ H, int sx0, int sy0, int cx, int cy,
-                            CellLocal& L) {
-    const double ax0 = H[0] - sx0 * H[6], ax1 = H[1] - sx0 * H[7], ax2 = H[2] - sx0 * H[8];
-    const double ay0 = H[3] - sy0 * H[6], ay1 = H[4] - sy0 * H[7], ay2 = H[5] - sy0 * H[8];
-    const double d0 = H[6] * cx + H[7] * cy + H[8];
-    const double inv = 1.0 / d0;  // inf / nan when degenerate: the fast path then always fails
-    L.a0 = (float)(ax0 * inv);
-    L.a1 = (float)(ax1 * inv);
-    L.a2 = (float)((ax0 * cx + ax1 * cy + ax2) * inv);
-    L.b0 = (float)(ay0 * inv);
-    L.b1 = (float)(ay1 * inv);
-    L.b2 = (float)((ay0 * cx + ay1 * cy + ay2) * inv);
-    L.g = (float)(H[6] * inv);
-    L.h = (float)(H[7] * inv);
-    L.sx0 = sx0;
-    L.sy0 = sy0;
-    L.cx = cx;
-    L.cy = cy;
-}
-
-// 2^(e-19) for |u| in [2^e, 2^(e+1)): 32 * half ulp of float32(u); ~0 for |u| < 2^-100.
+// 2^(e-19) for |u| in [2^e, 2^(e+1)): 32 * half ulp of float32(u); 0 for tiny |u|.
 VKB_HD float half_ulp_times_32(float u) {
     union { float f; uint32_t i; } v;
     v.f = u;
@@ -229,32 +218,61 @@ VKB_HD float half_ulp_times_32(float u) {
     return v.f;
 }
 
-VKB_HD bool fast_axis(float num, float r32, int s0, int& X) {
-    const float f = VKB_FMUL(num, r32);  // 32 * du
-    const float fl = floorf(f);
-    const float frac = f - fl;  // exact
-    const float u = (float)s0 + f * 0.03125f;
-    const float margin = half_ulp_times_32(u) + kFastSlack;
-    X = s0 * 32 + (int)fl + (frac > 0.5f ? 1 : 0);
-    return fabsf(frac - 0.5f) > margin && fabsf(f) < 1.0e6f;
+// acceptance thresholds for a page whose source coordinates stay below `extent` pixels
+VKB_HD void fast_thresholds(int extent, float& t_odd, float& t_even) {
+    const float reach = (float)extent + kFastRange / 32.0f + 1.0f;
+    t_odd = 0.5f - half_ulp_times_32(reach) - kFastSlack;
+    t_even = 0.5f - kFastSlack;
 }
 
-VKB_HD bool cell_coord_fast(const CellLocal& L, int x, int y, int& X, int& Y) {
-    const float xf = (float)(x - L.cx), yf = (float)(y - L.cy);
+// H: inverse homography of the cell (dst -> src); (sx0, sy0): its src corner; (ox, oy): origin
+// of the dst tile the form is valid for.
+VKB_HD void make_cell_local(const double* __restrict__ H, int sx0, int sy0, int ox, int oy,
+                            CellLocal& L) {
+    const double ax0 = H[0] - sx0 * H[6], ax1 = H[1] - sx0 * H[7], ax2 = H[2] - sx0 * H[8];
+    const double ay0 = H[3] - sy0 * H[6], ay1 = H[4] - sy0 * H[7], ay2 = H[5] - sy0 * H[8];
+    const double d0 = H[6] * ox + H[7] * oy + H[8];
+    const double inv = 1.0 / d0;  // inf / nan when degenerate: the fast path then always fails
+    const double inv32 = 32.0 * inv;
+    L.a0 = (float)(ax0 * inv32);
+    L.a1 = (float)(ax1 * inv32);
+    L.a2 = (float)((ax0 * ox + ax1 * oy + ax2) * inv32);
+    L.b0 = (float)(ay0 * inv32);
+    L.b1 = (float)(ay1 * inv32);
+    L.b2 = (float)((ay0 * ox + ay1 * oy + ay2) * inv32);
+    L.g = (float)(H[6] * inv);
+    L.h = (float)(H[7] * inv);
+}
+
+// one axis: f = float32 estimate of 32*du, base_m = 32*s0 - kRoundMagicBits.
+// Returns the acceptance test; X = 32*s0 + rint(f).
+VKB_HD bool fast_axis(float f, int base_m, float t_odd, float t_even, int& X) {
+    union { float f; int i; } v;
+    v.f = VKB_FADD(f, kRoundMagic);                 // low mantissa bits = rint(f), half to even
+    const float d = VKB_FSUB(f, VKB_FSUB(v.f, kRoundMagic));  // exact
+    X = base_m + v.i;
+    return fabsf(d) < ((v.i & 1) ? t_odd : t_even);
+}
+
+// (xr, yr): pixel - tile origin as floats (exact small integers).
+VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int x0m, int y0m, float t_odd,
+                            float t_even, int& X, int& Y) {
 #if defined(__CUDA_ARCH__)
-    const float d = __fmaf_rn(L.g, xf, __fmaf_rn(L.h, yf, 1.0f));
-    const float nx = __fmaf_rn(L.a0, xf, __fmaf_rn(L.a1, yf, L.a2));
-    const float ny = __fmaf_rn(L.b0, xf, __fmaf_rn(L.b1, yf, L.b2));
-    const float r32 = __fdividef(32.0f, d);
+    const float d = __fmaf_rn(L.g, xr, __fmaf_rn(L.h, yr, 1.0f));
+    const float nx = __fmaf_rn(L.a0, xr, __fmaf_rn(L.a1, yr, L.a2));
+    const float ny = __fmaf_rn(L.b0, xr, __fmaf_rn(L.b1, yr, L.b2));
+    const float r = __fdividef(1.0f, d);
 #else
-    const float d = (float)((double)L.g * xf + ((double)L.h * yf + 1.0));
-    const float nx = (float)((double)L.a0 * xf + ((double)L.a1 * yf + (double)L.a2));
-    const float ny = (float)((double)L.b0 * xf + ((double)L.b1 * yf + (double)L.b2));
-    const float r32 = 32.0f / d;
+    const float d = (float)((double)L.g * xr + ((double)L.h * yr + 1.0));
+    const float nx = (float)((double)L.a0 * xr + ((double)L.a1 * yr + (double)L.a2));
+    const float ny = (float)((double)L.b0 * xr + ((double)L.b1 * yr + (double)L.b2));
+    const float r = 1.0f / d;
 #endif
-    const bool okx = fast_axis(nx, r32, L.sx0, X);
-    const bool oky = fast_axis(ny, r32, L.sy0, Y);
-    return okx && oky;  // NaN / inf anywhere -> false
+    const float fx = VKB_FMUL(nx, r), fy = VKB_FMUL(ny, r);
+    const bool okx = fast_axis(fx, x0m, t_odd, t_even, X);
+    const bool oky = fast_axis(fy, y0m, t_odd, t_even, Y);
+    // NaN / inf anywhere -> false (every comparison fails)
+    return okx && oky && fmaxf(fabsf(fx), fabsf(fy)) < kFastRange;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -74,15 +74,21 @@ class GridBatch:
         if need_forward:
             self.hfwd = dv.empty((self.n, self.c_max, 9), np.float64)
         self.cell_box = dv.empty((self.n, self.c_max, 4), np.int32)
-        self.cell_local = dv.empty((self.n, self.c_max, nv.CELL_LOCAL_BYTES), np.uint8)
         self.cell_masks = dv.empty((self.n, self.c_max, nv.CELL_MASK_WORDS), np.uint32)
         self.tile_count = dv.empty((self.n, self.t_max), np.int32)
         self.tile_cells = dv.empty((self.n, self.t_max, nv.TILE_CAP), np.uint16)
+        # candidate records of the remap kernel: 16 per tile on average is ample (typical 8-10);
+        # a page that needs more falls back to the kernel's slow exact path for the excess tiles
+        self.s_cap = 16 * self.t_max
+        self.tile_off = dv.empty((self.n, self.t_max), np.int32)
+        self.tile_base = dv.empty((self.n + 1,), np.int32)
+        self.tile_slots = dv.empty((self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
         nv.check(self.lib.vkb_grid_build(
-            dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max,
+            dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max, self.s_cap,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv), dv.ptr(self.hfwd),
-            dv.ptr(self.cell_box), dv.ptr(self.cell_local), dv.ptr(self.cell_masks),
-            dv.ptr(self.tile_count), dv.ptr(self.tile_cells), dv.stream_ptr()), 'vkb_grid_build')
+            dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
+            dv.ptr(self.tile_cells), dv.ptr(self.tile_off), dv.ptr(self.tile_base),
+            dv.ptr(self.tile_slots), dv.stream_ptr()), 'vkb_grid_build')
 
     def remap(self, planes: np.ndarray):
         """planes: structured array (PLANES_DTYPE), one record per page, device pointers."""
@@ -95,13 +101,17 @@ class GridBatch:
                 or ((planes['src_mask'] != 0) != bool(has_mask)).any()
                 or ((planes['src_score'] != 0) != bool(has_score)).any()):
             raise ValueError('all pages of one remap call must carry the same containers')
+        if int(planes['src_h'].max()) >= 32768 or int(planes['src_w'].max()) >= 32768:
+            raise ValueError('source planes larger than 32767 px are not supported (cv.remap limit)')
         planes_dev = dv.upload_structs(planes)
+        if (planes['dst_h'] != self.meta['dst_h']).any() or (planes['dst_w'] != self.meta['dst_w']).any():
+            raise ValueError('planes.dst_h / dst_w must be the result shapes of the plan')
         nv.check(self.lib.vkb_grid_remap(
             dv.ptr(self.pages_dev), dv.ptr(planes_dev), self.n, self.p_max, self.c_max, self.t_max,
-            dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv),
-            dv.ptr(self.cell_box), dv.ptr(self.cell_local), dv.ptr(self.cell_masks),
-            dv.ptr(self.tile_count), dv.ptr(self.tile_cells), self.max_dst_h, self.max_dst_w, channels, has_mask,
-            has_score, dv.stream_ptr()), 'vkb_grid_remap')
+            self.s_cap, dv.ptr(self.lattice_i), dv.ptr(self.hinv), dv.ptr(self.cell_box),
+            dv.ptr(self.cell_masks), dv.ptr(self.tile_count), dv.ptr(self.tile_off),
+            dv.ptr(self.tile_base), dv.ptr(self.tile_slots), channels, has_mask, has_score,
+            dv.stream_ptr()), 'vkb_grid_remap')
         return planes_dev
 
     def transform_points(self, page: int, xy: np.ndarray, cell_rc: np.ndarray) -> np.ndarray:
