@@ -9,8 +9,8 @@ from the reference's policy generators with the per-page generator
 default_rng(SeedSequence(133700).spawn(N)[i]).
 
 One step = one pass of the hot path over the batch: lattice projection -> finalise -> per-cell
-homographies + coverage masks + tile bins -> fused remap.  `value` times it with the inputs
-already in HBM; `e2e` times the same thing through the public batch API with HOST buffers
+homographies + coverage masks + tile bins + per-tile candidate records -> fused remap.  `value`
+times it with the inputs already in HBM; `e2e` times the same thing through the public batch API with HOST buffers
 (config -> parameter blocks, H2D of the pages, kernels, D2H of the distorted pages).
 `--impl reference` times the reference's own CPU algorithm (oracle port, cv2-backed when cv2
 is importable) on the host cores.
@@ -37,7 +37,12 @@ PAGE_SHAPE = (1024, 1024)
 BATCH = 256
 CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold',
               'camera_plane_line_curve')
-KERNELS_PER_STEP = 6  # project_camera, project_mls, finalize, cells, masks, remap
+# project_camera, project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records, remap
+KERNELS_PER_STEP = 9
+# dram__bytes_read.sum + dram__bytes_write.sum of grid_remap_kernel, one 32-page launch under
+# `ncu --set full` (profiles/r01_ncu_summary.md): 254.5 MB / 32 pages
+TRAFFIC_PER_PAGE = 254.5e6 / 32
+CPU_PAGES_PER_WORKER = 6  # bounded sample of the CPU arm: ~20 s of CPU work in total
 
 
 def page_rngs(first: int, count: int, total: int):
@@ -222,7 +227,7 @@ def run_reference(args, rank: int, world: int):
         return
     cores = os.cpu_count() or 1
     cores = max(1, min(cores, 64))
-    pages_per_step = cores  # one page per worker per step: a bounded sample of the workload
+    pages_per_step = cores * 2  # two pages per worker per step: a bounded sample of the workload
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_throughput(pages_per_step, cores)
     walls = []
@@ -324,21 +329,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- kernel-only: inputs resident -----------------------------------------------------
-    remap_ms = []
+    remap_events = []
 
     def step(timed: bool):
-        plan = engine.plan_batch()
-        if timed:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-        out = engine.run(pages_dev, replan=False)
-        if timed:
-            e1.record()
-            remap_events.append((e0, e1))
-        return out
+        engine.plan_batch()
+        return engine.run(pages_dev, replan=False, launch_events=remap_events if timed else None)
 
-    remap_events = []
     for _ in range(warmup):
         out = step(False)
     barrier()
@@ -354,6 +350,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     elapsed_ms = start.elapsed_time(stop)
+    # CUDA events recorded immediately around the remap launch, on the launching stream
     remap_ms = [a.elapsed_time(b) for a, b in remap_events]
     algorithmic_bytes = engine.algorithmic_bytes(channels=3)
     out_bytes = int(out.image_arena.numel())
@@ -410,25 +407,27 @@ def main():
                     'h2d_bytes_per_step': int(host_pages.numel()),
                     'd2h_bytes_per_step': int(d2h),
                     'note': 'vkit_b200.batch.distort_pages_host(configs, pinned host pages) incl. '
-                            'parameter-block build, H2D, kernels, D2H (32-page chunks on two '
-                            'streams); wall clock, max over ranks'},
+                            'parameter-block build, H2D, kernels, D2H (32-page chunks; copy-in, '
+                            'two work and copy-out streams); wall clock, max over ranks'},
             'gpu_launches': KERNELS_PER_STEP * args.steps,
             'roofline': {
                 'bound': 'hbm', 'kernel': 'grid_remap_kernel', 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAFFIC_PER_PAGE * batch, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': algorithmic_bytes,
                 'launch_ms': remap_mean_ms,
-                'note': '3 B x (src pixels + dst pixels) of the batch / mean remap launch time '
-                        '(CUDA events on the launch stream)',
+                'note': '3 B x (src pixels + dst pixels) of the batch / mean duration of the '
+                        'grid_remap_kernel launch (CUDA events recorded around the launch on its '
+                        'stream); traffic = ncu dram bytes of one 32-page launch scaled to the '
+                        'batch, see profiles/',
             },
         }
         if not args.skip_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, 64))
-            n_pages = cores
+            n_pages = cores * CPU_PAGES_PER_WORKER
             cpu_value, cpu_wall, per_page = cpu_reference_throughput(n_pages, cores)
             line['cpu_baseline'] = {
                 'value': cpu_value, 'unit': 'pages/s', 'cores': cores, 'kind': 'port',
-                'sample': f'{n_pages} pages of the same workload, one per worker process '
+                'sample': f'{n_pages} pages of the same workload, {CPU_PAGES_PER_WORKER} per worker process '
                           f'({per_page:.2f} s/page/core, wall {cpu_wall:.1f} s); '
                           + cpu_backend_name(),
             }

@@ -159,13 +159,17 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
  *   tile_off:   n_pages x t_max int32, first record of each tile within its page
  *   tile_base:  n_pages + 1 int32, prefix sum of tiles per page (the remap's flat work list)
  *   tile_slots: n_pages x s_cap x VKB_TILE_SLOT_BYTES bytes, opaque (bbox, cell id and the
- *               float32 tile-centred inverse map of every candidate, ascending cell order) */
+ *               float32 tile-centred inverse map of every candidate, ascending cell order)
+ *   tile_headers: (sum of tiles of all pages) x VKB_TILE_HEADER_BYTES bytes, opaque: the flat
+ *               work list of the remap (page, tile origin, record count, first record);
+ *               n_pages x t_max entries are always enough */
 #define VKB_TILE_SLOT_BYTES 64
+#define VKB_TILE_HEADER_BYTES 32
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
                    int32_t t_max, int32_t s_cap, const int32_t* lattice_i, vkb_grid_meta* meta,
                    double* hinv, double* hfwd, int32_t* cell_box, uint32_t* cell_masks,
                    int32_t* tile_count, uint16_t* tile_cells, int32_t* tile_off,
-                   int32_t* tile_base, void* tile_slots, void* stream);
+                   int32_t* tile_base, void* tile_slots, void* tile_headers, void* stream);
 
 /* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
  * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
@@ -180,7 +184,8 @@ int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t
                    const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
                    const uint32_t* cell_masks, const int32_t* tile_count,
                    const int32_t* tile_off, const int32_t* tile_base, const void* tile_slots,
-                   int32_t image_channels, int32_t has_mask, int32_t has_score, void* stream);
+                   const void* tile_headers, int32_t image_channels, int32_t has_mask,
+                   int32_t has_score, void* stream);
 
 /* Points through the forward homography of the source cell that contains the ROUNDED point
  * (FuncImageGridBased.func_point, grid_rendering/interface.py:194-216).

@@ -33,7 +33,8 @@ def launch():
         dv.ptr(plan.pages_dev), dv.ptr(planes_dev), plan.n, plan.p_max, plan.c_max, plan.t_max,
         plan.s_cap, dv.ptr(plan.lattice_i), dv.ptr(plan.hinv), dv.ptr(plan.cell_box),
         dv.ptr(plan.cell_masks), dv.ptr(plan.tile_count), dv.ptr(plan.tile_off),
-        dv.ptr(plan.tile_base), dv.ptr(plan.tile_slots), 3, 0, 0, dv.stream_ptr()), 'remap')
+        dv.ptr(plan.tile_base), dv.ptr(plan.tile_slots), dv.ptr(plan.tile_headers), 3, 0, 0,
+        dv.stream_ptr()), 'remap')
 
 
 px = float(offsets[-1])

@@ -17,6 +17,7 @@ CELL_MASK_WORDS = 32
 TILE = 32
 TILE_CAP = 64
 TILE_SLOT_BYTES = 64
+TILE_HEADER_BYTES = 32
 
 WARP_AFFINE = 0
 WARP_PERSPECTIVE = 1
@@ -142,9 +143,9 @@ def _declare(lib):
     lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, vp]
     lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                   vp, vp, vp]
+                                   vp, vp, vp, vp]
     lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                   i32, i32, i32, vp]
+                                   vp, i32, i32, i32, vp]
     lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
     i64 = ctypes.c_int64

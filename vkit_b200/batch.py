@@ -93,9 +93,12 @@ class GeometricBatch:
         self.plan.build()
         return self.plan
 
-    def run(self, images=None, masks=None, score_maps=None, replan: bool = True) -> BatchOutput:
+    def run(self, images=None, masks=None, score_maps=None, replan: bool = True,
+            launch_events=None) -> BatchOutput:
         """images: (B, H, W, C) uint8, masks: (B, H, W) uint8, score_maps: (B, H, W) float32 --
-        CUDA tensors (any subset).  Returns ragged outputs in fresh arenas."""
+        CUDA tensors (any subset).  Returns ragged outputs in fresh arenas.
+        `launch_events`: optional list; a (start, end) pair of CUDA events recorded immediately
+        around the fused remap launch is appended (kernel time without host work)."""
         if replan or self.plan is None:
             self.plan_batch()
         plan = self.plan
@@ -129,7 +132,7 @@ class GeometricBatch:
             planes['src_score'] = score_maps.data_ptr() + np.arange(
                 self.n, dtype=np.uint64) * np.uint64(height * width * 4)
             planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
-        plan.remap(planes)
+        plan.remap(planes, launch_events=launch_events)
         return BatchOutput(shapes, channels, image_arena, mask_arena, score_arena, offsets)
 
     def algorithmic_bytes(self, channels: int = 3, with_mask: bool = False,
@@ -142,36 +145,44 @@ class GeometricBatch:
         return per_px * (self.n * height * width + dst)
 
 
-_PIPELINE_STREAMS = {}
+_PIPELINE_STATE = {}
 
 
-def _pipeline_streams():
-    """Two long-lived side streams per device (the caching allocator keeps one pool per stream,
-    so fresh streams per call would mean fresh cudaMallocs per call)."""
+def _pipeline_state():
+    """Long-lived side streams per device (the caching allocator keeps one pool per stream, so
+    fresh streams per call would mean fresh cudaMallocs per call): one for the H2D copies, two
+    alternating work streams (plan + remap), one for the D2H copies."""
     t = dv.require_cuda()
     key = t.cuda.current_device()
-    if key not in _PIPELINE_STREAMS:
-        _PIPELINE_STREAMS[key] = [t.cuda.Stream(), t.cuda.Stream()]
-    return _PIPELINE_STREAMS[key]
+    if key not in _PIPELINE_STATE:
+        _PIPELINE_STATE[key] = {'h2d': t.cuda.Stream(), 'work': [t.cuda.Stream(), t.cuda.Stream()],
+                                'd2h': t.cuda.Stream(), 'staging': None}
+    return _PIPELINE_STATE[key]
 
 
 def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int],
-                       host_images, host_out=None, chunk_pages: int = 64,
-                       use_thread: bool = True):
+                       host_images, host_out=None, chunk_pages: int = 32,
+                       use_thread: bool = False):
     """Host buffers in, host buffers out -- the end-to-end form of the batch engine.
 
     `host_images`: pinned (B, H, W, C) uint8 CPU tensor; the distorted pages land back to back in
-    the pinned flat uint8 tensor `host_out` (allocated when None).  The batch is cut into chunks
-    that alternate between two CUDA streams, so the H2D copy of chunk i+1, the kernels of chunk i
-    and the D2H copy of chunk i-1 overlap, while a helper thread turns the configs of the next
-    chunk into parameter blocks (Rodrigues, translation, curve / line constants).
+    the pinned flat uint8 tensor `host_out` (allocated when None).  Four streams keep both copy
+    engines and the SMs busy at once:
+      * every chunk's H2D copy is queued up front on the copy-in stream (pixels do not depend on
+        the configs), one event per chunk;
+      * per chunk the host turns the configs into parameter blocks (Rodrigues, translation,
+        curve / line constants), plans it -- lattice, result shapes (the only host sync, on a
+        work stream that never carries pixel copies), cells, masks, records -- and launches its
+        remap behind the chunk's H2D event (`use_thread` moves the parameter blocks to a helper
+        thread; measured slower under the GIL);
+      * the D2H copy of a finished chunk runs on the copy-out stream.
     Returns (host_out, shapes, byte_offsets)."""
     import queue
     import threading
     t = dv.require_cuda()
     n = len(op_names)
     bounds = [(a, min(a + chunk_pages, n)) for a in range(0, n, chunk_pages)]
-    ready: 'queue.Queue' = queue.Queue(maxsize=2)
+    ready: 'queue.Queue' = queue.Queue(maxsize=3)
 
     def producer():
         try:
@@ -187,34 +198,54 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     if use_thread:
         thread = threading.Thread(target=producer, daemon=True)
         thread.start()
-    streams = _pipeline_streams()
-    for s in streams:
-        s.wait_stream(t.cuda.current_stream())
+    state = _pipeline_state()
+    current = t.cuda.current_stream()
+    for s in [state['h2d'], state['d2h']] + state['work']:
+        s.wait_stream(current)
+
+    # 1. all H2D copies, back to back
+    staging = state['staging']
+    if staging is None or staging.shape != host_images.shape:
+        with t.cuda.stream(state['h2d']):
+            staging = t.empty(host_images.shape, dtype=t.uint8, device=dv.device())
+        state['staging'] = staging
+    copied = []
+    with t.cuda.stream(state['h2d']):
+        for a, b in bounds:
+            staging[a:b].copy_(host_images[a:b], non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record()
+            copied.append(ev)
+
+    # 2. plan + remap per chunk on alternating work streams, D2H behind each
     shapes, offsets = [], [0]
     keep = []
     for i, (a, b) in enumerate(bounds):
         sub = ready.get() if use_thread else GeometricBatch(op_names[a:b], configs[a:b], shape)
         if isinstance(sub, BaseException):
             raise sub
-        with t.cuda.stream(streams[i % 2]):
-            dev_in = host_images[a:b].to(dv.device(), non_blocking=True)
-            out = sub.run(dev_in)
-            n_bytes = int(out.image_arena.numel())
-            start = offsets[-1]
-            if start + n_bytes > host_out.numel():
-                raise ValueError('host_out is too small for the distorted pages')
+        work = state['work'][i % 2]
+        with t.cuda.stream(work):
+            sub.plan_batch()
+            work.wait_event(copied[i])
+            out = sub.run(staging[a:b], replan=False)
+            done = t.cuda.Event()
+            done.record()
+        n_bytes = int(out.image_arena.numel())
+        start = offsets[-1]
+        if start + n_bytes > host_out.numel():
+            raise ValueError('host_out is too small for the distorted pages')
+        with t.cuda.stream(state['d2h']):
+            state['d2h'].wait_event(done)
             host_out[start:start + n_bytes].copy_(out.image_arena, non_blocking=True)
-            for k, (h, w) in enumerate(out.shapes):
-                shapes.append((h, w))
-                offsets.append(start + int(out.pixel_offsets[k + 1]) * channels)
-            keep.append((dev_in, out, sub))
-        if len(keep) > 2:
-            # chunk i-2 ran on this stream's sibling two iterations ago: its buffers may be
-            # recycled once that stream has drained
-            streams[(i + 1) % 2].synchronize()
-            keep.pop(0)
-    for s in streams:
+        for k, (h, w) in enumerate(out.shapes):
+            shapes.append((h, w))
+            offsets.append(start + int(out.pixel_offsets[k + 1]) * channels)
+        keep.append((out, sub))
+    state['d2h'].synchronize()
+    for s in state['work']:
         s.synchronize()
+    current.wait_stream(state['h2d'])
     if use_thread:
         thread.join()
     return host_out, shapes, offsets

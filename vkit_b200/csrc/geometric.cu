@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
 }
 
 // ============================================================================================
-// Coverage masks: warp per cell, lane per row of the cell's bounding box.
+// Coverage masks: half a warp per cell, lane per row of the cell's bounding box (a typical
+// cell spans 16-17 rows; rows 16.. of taller cells are done in a second pass).
 // ============================================================================================
 __global__ void __launch_bounds__(128) grid_masks_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max,
@@ -430,9 +431,9 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
     const int C = (pg.rows - 1) * ccols;
-    const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int cell = blockIdx.x * 8 + (threadIdx.x >> 4);
     if (cell >= C) return;
-    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x & 15;
     const int r = floor_div_small(cell, ccols, __fdividef(1.0f, (float)ccols));
     const int c = cell - r * ccols;
     const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
@@ -448,13 +449,13 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     uint32_t* out = cell_masks + ((size_t)page * c_max + cell) * VKB_CELL_MASK_WORDS;
     if (nwords != 1 || nrows > VKB_CELL_MASK_WORDS) {
         // too large for the fixed budget: the remap kernel rasterises this cell on the fly.
-        if (lane == 0) cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
+        if (sub == 0) cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
         return;
     }
-    if (lane < nrows) {
+    for (int row = sub; row < nrows; row += 16) {
         uint32_t word = 0;
-        poly_row_mask<4>(px, py, y0 + lane, x0, &word, 1);
-        out[lane] = word;
+        poly_row_mask<4>(px, py, y0 + row, x0, &word, 1);
+        out[row] = word;
     }
 }
 
@@ -479,6 +480,15 @@ struct __align__(16) TileSlot {
     int pad[3];
 };
 static_assert(sizeof(TileSlot) == VKB_TILE_SLOT_BYTES, "TileSlot layout is part of the ABI");
+
+// One work item of the persistent remap kernel: a 32 x 32 dst tile (uniform across a warp).
+struct __align__(16) RemapTile {
+    int page, tx0, ty0;
+    int count;  // candidate records; -1: the tile takes the slow exact path
+    int rec;    // index of the first record
+    int pad[3];
+};
+static_assert(sizeof(RemapTile) == VKB_TILE_HEADER_BYTES, "RemapTile layout is part of the ABI");
 
 __device__ __forceinline__ int page_tiles(const vkb_grid_meta& m) {
     return ((m.dst_w + VKB_TILE - 1) / VKB_TILE) * ((m.dst_h + VKB_TILE - 1) / VKB_TILE);
@@ -554,7 +564,8 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     const vkb_grid_page* __restrict__ pages, const vkb_grid_meta* __restrict__ meta, int c_max,
     int t_max, int s_cap, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
     const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
-    const int32_t* __restrict__ tile_off, TileSlot* __restrict__ slots) {
+    const int32_t* __restrict__ tile_off, const int32_t* __restrict__ tile_base,
+    TileSlot* __restrict__ slots, RemapTile* __restrict__ headers) {
     const int page = blockIdx.y;
     const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -564,8 +575,22 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     const size_t pt = (size_t)page * t_max + t;
     const int count = tile_count[pt];
     const int off = tile_off[pt];
-    if (count > VKB_TILE_CAP || off + count > s_cap) return;  // the remap takes its slow path
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const bool usable = count <= VKB_TILE_CAP && off + count <= s_cap;
+    if (lane == 0) {
+        RemapTile h;
+        h.page = page;
+        h.tx0 = tx * VKB_TILE;
+        h.ty0 = ty * VKB_TILE;
+        h.count = usable ? count : -1;
+        h.rec = page * s_cap + off;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        int4* __restrict__ dst = reinterpret_cast<int4*>(headers + (tile_base[page] + t));
+        const int4* src = reinterpret_cast<const int4*>(&h);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+    if (!usable) return;  // the remap takes its slow path
     const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
     const int ca = lane < count ? (int)cells[lane] : 0x7fffffff;
     const int cb = lane + 32 < count ? (int)cells[lane + 32] : 0x7fffffff;
@@ -675,7 +700,7 @@ __device__ __forceinline__ RowRgb row_rgb_load(const uint8_t* __restrict__ p) {
     RowRgb r;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
     r.off = (uint32_t)addr & 3u;
-    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(addr - r.off);
+    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
     r.w0 = __ldg(q);
     r.w1 = __ldg(q + 1);
     r.w2 = 0;
@@ -712,13 +737,22 @@ __device__ __forceinline__ TapWeights tap_weights(int X, int Y, int h, int w) {
     const int x0 = X >> kInterBits, y0 = Y >> kInterBits;
     const int fx = X & (kInterTab - 1), fy = Y & (kInterTab - 1);
     TapWeights t;
-    t.xs = min(max(x0, 0), w - 2);
-    t.ys = min(max(y0, 0), h - 2);
-    const int dx = x0 - t.xs, dy = y0 - t.ys;
-    t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
-    t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
-    t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
-    t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
+    t.xs = x0;
+    t.ys = y0;
+    t.wx0 = kInterTab - fx;
+    t.wx1 = fx;
+    t.wy0 = kInterTab - fy;
+    t.wy1 = fy;
+    if ((unsigned)x0 > (unsigned)(w - 2) || (unsigned)y0 > (unsigned)(h - 2)) {
+        // the footprint touches the border (rare)
+        t.xs = min(max(x0, 0), w - 2);
+        t.ys = min(max(y0, 0), h - 2);
+        const int dx = x0 - t.xs, dy = y0 - t.ys;
+        t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
+        t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
+        t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
+        t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
+    }
     return t;
 }
 
@@ -784,44 +818,52 @@ __device__ __noinline__ uint32_t sample_u8_small(const uint8_t* __restrict__ src
     return out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
 }
 
-// One work item of the persistent remap kernel (uniform across the block).
-struct RemapTile {
-    int page, tx0, ty0, count, off;
-};
-
-__device__ __forceinline__ RemapTile remap_tile_header(int w, int page, const vkb_planes* __restrict__ planes,
-                                                       const int32_t* __restrict__ tile_base, int t_max,
-                                                       const int32_t* __restrict__ tile_count,
-                                                       const int32_t* __restrict__ tile_off) {
-    RemapTile t;
-    while (w >= tile_base[page + 1]) ++page;  // work items are handed out in order
-    const int local = w - tile_base[page];
-    const int tiles_x = (planes[page].dst_w + VKB_TILE - 1) / VKB_TILE;
-    const int ty = local / tiles_x;
-    t.page = page;
-    t.tx0 = (local - ty * tiles_x) * VKB_TILE;
-    t.ty0 = ty * VKB_TILE;
-    const size_t idx = (size_t)page * t_max + local;
-    t.count = tile_count[idx];
-    t.off = tile_off[idx];
-    return t;
+// ---- mbarrier / cp.async plumbing of the persistent remap kernel ----------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
 }
-
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// arrival that fires when this thread's earlier cp.async copies have landed
+__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
+
+// Persistent kernel.  Every block owns a contiguous share of the flat tile list; its warps run
+// the tiles in the same order but are NOT kept in lock step: the records of tile k+2 are
+// requested (cp.async) when a warp starts tile k, `land[k % 4]` completes when all threads'
+// copies for tile k have arrived, `done[k % 4]` when all warps have finished reading them, so a
+// warp only ever waits for a warp that is more than a tile behind.
+constexpr int kRemapBuffers = 4;
 
 template <int C, bool MASK, bool SCORE, int R>
 __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_remap_kernel(
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
-    int c_max, int t_max, int p_max, int s_cap, const double* __restrict__ hinv,
-    const int4* __restrict__ cell_box, const uint32_t* __restrict__ cell_masks,
-    const int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_off,
-    const int32_t* __restrict__ tile_base, const TileSlot* __restrict__ slots,
-    const int32_t* __restrict__ lattice_i, const int dbg) {
+    int c_max, int p_max, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
+    const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
+    const RemapTile* __restrict__ headers, const TileSlot* __restrict__ slots,
+    const int32_t* __restrict__ lattice_i) {
     constexpr int kThreads = 32 * (VKB_TILE / R);
-    __shared__ RemapShared sm[2];
+    constexpr int kWarps = VKB_TILE / R;
+    __shared__ RemapShared sm[kRemapBuffers];
+    __shared__ uint64_t land[kRemapBuffers], done[kRemapBuffers];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
@@ -829,27 +871,37 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
     const int total = tile_base[n_pages];
     const int per = (total + gridDim.x - 1) / gridDim.x;
     const int w_begin = blockIdx.x * per;
-    const int w_end = min(total, w_begin + per);
-    if (w_begin >= w_end) return;
-
-    auto usable = [&](const RemapTile& t) { return t.count <= VKB_TILE_CAP && t.off + t.count <= s_cap; };
-    auto prefetch = [&](const RemapTile& t, int buf) {
-        if (usable(t)) {
-            const char* g = reinterpret_cast<const char*>(slots + ((size_t)t.page * s_cap + t.off));
-            char* d = reinterpret_cast<char*>(sm[buf].slot);
-            for (int i = tid; i < t.count * (VKB_TILE_SLOT_BYTES / 16); i += kThreads)
-                cp_async_16(d + i * 16, g + i * 16);
+    const int n_tiles = min(total, w_begin + per) - w_begin;
+    if (n_tiles <= 0) return;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kRemapBuffers; ++i) {
+            mbar_init(&land[i], kThreads);
+            mbar_init(&done[i], kWarps);
         }
-        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    __syncthreads();
+
+    auto load_header = [&](int k) {
+        RemapTile t;
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + (w_begin + min(k, n_tiles - 1)));
+        const int4 a = __ldg(src), b = __ldg(src + 1);
+        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
+        return t;
+    };
+    auto prefetch = [&](const RemapTile& t, int k) {
+        const int chunks = t.count * (VKB_TILE_SLOT_BYTES / 16);  // <= 256; negative on the slow path
+        if (tid < chunks) {
+            const char* g = reinterpret_cast<const char*>(slots + t.rec);
+            char* d = reinterpret_cast<char*>(sm[k % kRemapBuffers].slot);
+            for (int i = tid; i < chunks; i += kThreads) cp_async_16(d + i * 16, g + i * 16);
+        }
+        mbar_arrive_on_copies(&land[k % kRemapBuffers]);
     };
 
-    RemapTile cur = remap_tile_header(w_begin, 0, planes, tile_base, t_max, tile_count, tile_off);
-    RemapTile nxt = cur;
-    if (w_begin + 1 < w_end)
-        nxt = remap_tile_header(w_begin + 1, cur.page, planes, tile_base, t_max, tile_count, tile_off);
-    prefetch(cur, 0);
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
+    RemapTile h0 = load_header(0), h1 = load_header(1), h2 = load_header(2);
+    prefetch(h0, 0);
+    if (n_tiles > 1) prefetch(h1, 1);
 
     // per-page state, reloaded when the page changes
     int ctx_page = -1;
@@ -862,14 +914,15 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
     const float* __restrict__ src_score = nullptr;
     float* __restrict__ dst_score = nullptr;
 
-    for (int w = w_begin; w < w_end; ++w) {
-        const int buf = (w - w_begin) & 1;
-        // records of the next tile start moving now; the header of the one after is requested
-        // so its loads are in flight while this tile is processed
-        RemapTile nn = nxt;
-        if (w + 1 < w_end) prefetch(nxt, buf ^ 1);
-        if (w + 2 < w_end)
-            nn = remap_tile_header(w + 2, nxt.page, planes, tile_base, t_max, tile_count, tile_off);
+    for (int k = 0; k < n_tiles; ++k) {
+        const RemapTile cur = h0;
+        const RemapTile h3 = load_header(k + 3);  // in flight while this tile is processed
+        if (k + 2 < n_tiles) {
+            // buffer (k + 2) % 4 last held tile k - 2: wait until every warp is done with it
+            if (k >= 2) mbar_wait(&done[(k - 2) % kRemapBuffers], ((k - 2) / kRemapBuffers) & 1);
+            prefetch(h2, k + 2);
+        }
+        mbar_wait(&land[k % kRemapBuffers], (k / kRemapBuffers) & 1);
 
         const int page = cur.page;
         if (page != ctx_page) {
@@ -883,13 +936,14 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
             fast_thresholds(max(src_h, src_w), t_odd, t_even);
             ctx_page = page;
         }
-        const TileSlot* __restrict__ S = sm[buf].slot;
+        const TileSlot* __restrict__ S = sm[k % kRemapBuffers].slot;
         const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
-        const bool fast = usable(cur);
+        const bool fast = count >= 0;
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
         const int ry0 = ty0 + warp * R;
 
+        int X[R], Y[R];
         if (ry0 < dst_h) {
             const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
             // ---- owner ---------------------------------------------------------------------
@@ -897,12 +951,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
             int key[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) key[j] = -1;
-            int n_cand = fast ? count : (pages[page].rows - 1) * (cols - 1);
-            if (dbg & 4) {
-                n_cand = 0;
-#pragma unroll
-                for (int j = 0; j < R; ++j) key[j] = (fast && count > 0) ? S[0].info : -1;
-            }
+            const int n_cand = fast ? count : (pages[page].rows - 1) * (cols - 1);
             for (int base = 0; base < n_cand; base += 32) {
                 const int s = base + lane;
                 uint32_t win[R];
@@ -947,58 +996,62 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                 while (active) {
                     const int src_lane = __ffs(active) - 1;
                     active &= active - 1;
-                    const int k = __shfl_sync(0xffffffffu, my_key, src_lane);
+                    const int kk = __shfl_sync(0xffffffffu, my_key, src_lane);
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
                         const uint32_t wd = __shfl_sync(0xffffffffu, win[j], src_lane);
-                        if ((wd >> lane) & 1u) key[j] = k;
+                        if ((wd >> lane) & 1u) key[j] = kk;
                     }
                 }
             }
 
-            if (x < dst_w) {
+            {
                 // ---- coordinates -----------------------------------------------------------
+                // uncovered pixels keep map value (0, 0); the fast path is evaluated for every
+                // pixel (slot 0 for uncovered ones) and the result selected afterwards
                 const float xr = (float)lane;
                 const float yr0 = (float)(warp * R);
-                int X[R], Y[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    X[j] = 0;
-                    Y[j] = 0;
-                    if (dbg & 8) {
-                        X[j] = (x * 29) & 32767;
-                        Y[j] = ((ry0 + j) * 29) & 32767;
-                    } else if (key[j] >= 0) {
-                        int cell = key[j];
-                        bool done = false;
-                        if (fast) {
-                            const int slot = key[j] & 63;
-                            const int c = (key[j] >> 6) & 1023, r = key[j] >> 16;
-                            done = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j,
-                                                   c * grid32 - kRoundMagicBits,
-                                                   r * grid32 - kRoundMagicBits, t_odd, t_even, X[j], Y[j]);
-                            if (!done) cell = S[slot].cellf & 0x7FFFFFFF;
-                        }
-                        if (!done) {
+                    const bool covered = key[j] >= 0;
+                    if (fast) {
+                        const int kj = covered ? key[j] : 0;
+                        const int slot = kj & 63;
+                        const int c = (kj >> 6) & 1023, r = kj >> 16;
+                        const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j,
+                                                        c * grid32 - kRoundMagicBits,
+                                                        r * grid32 - kRoundMagicBits, t_odd, t_even, X[j], Y[j]);
+                        if (covered && !ok) {
+                            const int cell = S[slot].cellf & 0x7FFFFFFF;
                             const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
                             X[j] = e.x;
                             Y[j] = e.y;
                         }
+                    } else if (covered) {
+                        const int2 e = cell_coord_exact(hinv + (page_cell0 + key[j]) * 9, x, ry0 + j);
+                        X[j] = e.x;
+                        Y[j] = e.y;
+                    }
+                    if (!covered) {
+                        X[j] = 0;
+                        Y[j] = 0;
                     }
                 }
+            }
+        }
+        // last read of this tile's records: let the buffer go before the gather
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[k % kRemapBuffers]);
 
+        if (ry0 < dst_h) {
+            if (x < dst_w) {
                 // ---- gather ----------------------------------------------------------------
                 const int di0 = ry0 * dst_w + x;
                 const bool tiny = src_h < 2 || src_w < 2;
                 if (C > 0) {
                     constexpr int CC = C > 0 ? C : 1;
                     uint8_t px[R][CC];
-                    if (dbg & 2) {
-#pragma unroll
-                        for (int j = 0; j < R; ++j)
-#pragma unroll
-                            for (int c = 0; c < CC; ++c) px[j][c] = (uint8_t)((X[j] >> (c * 3)) ^ Y[j]);
-                    } else if (tiny) {
+                    if (tiny) {
 #pragma unroll
                         for (int j = 0; j < R; ++j) {
                             const uint32_t v = sample_u8_small<CC>(src_image, src_h, src_w, X[j], Y[j]);
@@ -1014,7 +1067,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                     }
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        if (ry0 + j < dst_h && (!(dbg & 1) || (px[j][0] == 77 && X[j] == 123457))) {
+                        if (ry0 + j < dst_h) {
                             uint8_t* d = dst_image + (di0 + j * dst_w) * CC;
                             if (CC == 4) {
                                 *reinterpret_cast<uchar4*>(d) =
@@ -1052,12 +1105,9 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                 }
             }
         }
-
-        // the next tile's records have landed and nobody reads this tile's any more
-        asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();
-        cur = nxt;
-        nxt = nn;
+        h0 = h1;
+        h1 = h2;
+        h2 = h3;
     }
 }
 
@@ -1233,20 +1283,22 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
                               vkb_grid_meta* meta, double* hinv, double* hfwd, int32_t* cell_box,
                               uint32_t* cell_masks, int32_t* tile_count, uint16_t* tile_cells,
                               int32_t* tile_off, int32_t* tile_base, void* tile_slots,
-                              void* stream) {
+                              void* tile_headers, void* stream) {
     VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_masks && tile_count
-                    && tile_cells && tile_off && tile_base && tile_slots, "bad arguments");
+                    && tile_cells && tile_off && tile_base && tile_slots && tile_headers,
+                "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(c_max > 0 && c_max <= 65535, "at most 65535 cells per page");
     VKB_REQUIRE(t_max > 0 && s_cap > 0, "empty tile workspace");
     VKB_REQUIRE((long long)n_pages * t_max < (1ll << 31), "too many tiles in one launch");
+    VKB_REQUIRE((long long)n_pages * s_cap < (1ll << 31), "too many tile records in one launch");
     cudaStream_t st = (cudaStream_t)stream;
     VKB_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)n_pages * t_max, st));
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
-    grid_masks_kernel<<<dim3((c_max + 3) / 4, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
+    grid_masks_kernel<<<dim3((c_max + 7) / 8, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
                                                                      cell_box, cell_masks);
     rc = check_launch("grid_masks_kernel");
     if (rc) return rc;
@@ -1256,7 +1308,8 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     if (rc) return rc;
     grid_tile_records_kernel<<<dim3((t_max + 3) / 4, n_pages), 128, 0, st>>>(
         pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
-        tile_cells, tile_off, reinterpret_cast<TileSlot*>(tile_slots));
+        tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
+        reinterpret_cast<RemapTile*>(tile_headers));
     return check_launch("grid_tile_records_kernel");
 }
 
@@ -1277,10 +1330,13 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
                               const uint32_t* cell_masks, const int32_t* tile_count,
                               const int32_t* tile_off, const int32_t* tile_base,
-                              const void* tile_slots, int32_t image_channels, int32_t has_mask,
-                              int32_t has_score, void* stream) {
+                              const void* tile_slots, const void* tile_headers,
+                              int32_t image_channels, int32_t has_mask, int32_t has_score,
+                              void* stream) {
     VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
-                    && tile_off && tile_base && tile_slots, "bad arguments");
+                    && tile_off && tile_base && tile_slots && tile_headers, "bad arguments");
+    (void)t_max;
+    (void)s_cap;
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
                     || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
@@ -1289,13 +1345,11 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     constexpr int R = VKB_REMAP_ROWS;
     constexpr int kBlocksPerSm = (R == 4) ? 4 : 8;
     const int grid = remap_grid_blocks(kBlocksPerSm);
-    const char* dbg_env = getenv("VKB_REMAP_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
 #define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
     grid_remap_kernel<CH, M, S, R><<<grid, 32 * (VKB_TILE / R), 0, st>>>(                      \
-        planes, pages, n_pages, c_max, t_max, p_max, s_cap, hinv,                              \
-        reinterpret_cast<const int4*>(cell_box), cell_masks, tile_count, tile_off, tile_base,  \
-        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, dbg)
+        planes, pages, n_pages, c_max, p_max, hinv, reinterpret_cast<const int4*>(cell_box),   \
+        cell_masks, tile_base, reinterpret_cast<const RemapTile*>(tile_headers),               \
+        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
     switch (key) {
         case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;

@@ -83,15 +83,18 @@ class GridBatch:
         self.tile_off = dv.empty((self.n, self.t_max), np.int32)
         self.tile_base = dv.empty((self.n + 1,), np.int32)
         self.tile_slots = dv.empty((self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
+        self.tile_headers = dv.empty((self.n * self.t_max, nv.TILE_HEADER_BYTES), np.uint8)
         nv.check(self.lib.vkb_grid_build(
             dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max, self.s_cap,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv), dv.ptr(self.hfwd),
             dv.ptr(self.cell_box), dv.ptr(self.cell_masks), dv.ptr(self.tile_count),
             dv.ptr(self.tile_cells), dv.ptr(self.tile_off), dv.ptr(self.tile_base),
-            dv.ptr(self.tile_slots), dv.stream_ptr()), 'vkb_grid_build')
+            dv.ptr(self.tile_slots), dv.ptr(self.tile_headers), dv.stream_ptr()), 'vkb_grid_build')
 
-    def remap(self, planes: np.ndarray):
-        """planes: structured array (PLANES_DTYPE), one record per page, device pointers."""
+    def remap(self, planes: np.ndarray, launch_events=None):
+        """planes: structured array (PLANES_DTYPE), one record per page, device pointers.
+        `launch_events`: optional list that receives a (start, end) CUDA event pair recorded
+        immediately around the kernel launch."""
         self.build()
         planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
         channels = int(planes['image_channels'][0])
@@ -106,12 +109,19 @@ class GridBatch:
         planes_dev = dv.upload_structs(planes)
         if (planes['dst_h'] != self.meta['dst_h']).any() or (planes['dst_w'] != self.meta['dst_w']).any():
             raise ValueError('planes.dst_h / dst_w must be the result shapes of the plan')
+        if launch_events is not None:
+            t = dv.torch()
+            ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            ev0.record()
         nv.check(self.lib.vkb_grid_remap(
             dv.ptr(self.pages_dev), dv.ptr(planes_dev), self.n, self.p_max, self.c_max, self.t_max,
             self.s_cap, dv.ptr(self.lattice_i), dv.ptr(self.hinv), dv.ptr(self.cell_box),
             dv.ptr(self.cell_masks), dv.ptr(self.tile_count), dv.ptr(self.tile_off),
-            dv.ptr(self.tile_base), dv.ptr(self.tile_slots), channels, has_mask, has_score,
-            dv.stream_ptr()), 'vkb_grid_remap')
+            dv.ptr(self.tile_base), dv.ptr(self.tile_slots), dv.ptr(self.tile_headers), channels,
+            has_mask, has_score, dv.stream_ptr()), 'vkb_grid_remap')
+        if launch_events is not None:
+            ev1.record()
+            launch_events.append((ev0, ev1))
         return planes_dev
 
     def transform_points(self, page: int, xy: np.ndarray, cell_rc: np.ndarray) -> np.ndarray:
