@@ -28,15 +28,16 @@ _PAGE_BUILDERS = {
 }
 
 
-def grid_page_record(op_name: str, config, shape: Tuple[int, int]):
-    """(page record, keepalive) for one page of a grid-based op."""
+def grid_page_record(op_name: str, config, shape: Tuple[int, int], out=None):
+    """(page record, keepalive) for one page of a grid-based op.  `out`: zeroed element of a
+    GRID_PAGE_DTYPE array to fill in place."""
     height, width = shape
     if op_name == 'similarity_mls':
         config = dyn_structure(config, _mls.SimilarityMlsConfig)
-        return _mls.similarity_mls_page(config, shape)
+        return _mls.similarity_mls_page(config, shape, out)
     config_cls, builder = _PAGE_BUILDERS[op_name]
     config = dyn_structure(config, config_cls)
-    rec = builder(config, shape)
+    rec = builder(config, shape, out)
     camera_model_config = _camera.complete_camera_model_config(height, width,
                                                                config.camera_model_config)
     _camera.fill_camera_model(rec, camera_model_config)
@@ -75,16 +76,14 @@ class GeometricBatch:
 
     def __init__(self, op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int]):
         self.shape = tuple(shape)
-        records = []
         keepalive = []
-        for op_name, config in zip(op_names, configs):
-            rec, keep = grid_page_record(op_name, config, self.shape)
-            records.append(rec)
+        self.n = len(op_names)
+        self.pages = np.zeros(self.n, dtype=nv.GRID_PAGE_DTYPE)
+        for i, (op_name, config) in enumerate(zip(op_names, configs)):
+            _, keep = grid_page_record(op_name, config, self.shape, out=self.pages[i])
             if keep is not None:
                 keepalive.append(keep)
-        self.pages = np.stack(records).astype(nv.GRID_PAGE_DTYPE)
         self.keepalive = keepalive
-        self.n = len(records)
         self.plan: Optional[GridBatch] = None
 
     def plan_batch(self):
@@ -181,7 +180,10 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     import threading
     t = dv.require_cuda()
     n = len(op_names)
-    bounds = [(a, min(a + chunk_pages, n)) for a in range(0, n, chunk_pages)]
+    # a short first chunk gets the D2H engine going early (the pipeline is PCIe-bound: the fill
+    # time before the first copy-out is pure loss)
+    first = min(n, max(1, chunk_pages // 4))
+    bounds = [(0, first)] + [(a, min(a + chunk_pages, n)) for a in range(first, n, chunk_pages)]
     ready: 'queue.Queue' = queue.Queue(maxsize=3)
 
     def producer():

@@ -19,13 +19,23 @@ from vkit_b200 import device as dv
 from ._hostmath import lattice_axis
 
 
-def new_grid_page(height: int, width: int, grid_size: int):
-    rec = np.zeros((), dtype=nv.GRID_PAGE_DTYPE)
+_LATTICE_DIMS = {}
+
+
+def new_grid_page(height: int, width: int, grid_size: int, out=None):
+    """A zeroed page record with the source shape and lattice dimensions filled in.  `out`: a
+    zeroed element of a GRID_PAGE_DTYPE array to fill in place (batch builders)."""
+    rec = np.zeros((), dtype=nv.GRID_PAGE_DTYPE) if out is None else out
+    key = (height, width, grid_size)
+    dims = _LATTICE_DIMS.get(key)
+    if dims is None:
+        dims = (len(lattice_axis(height, grid_size)), len(lattice_axis(width, grid_size)))
+        if len(_LATTICE_DIMS) < 1024:
+            _LATTICE_DIMS[key] = dims
     rec['src_h'] = height
     rec['src_w'] = width
     rec['grid_size'] = grid_size
-    rec['rows'] = len(lattice_axis(height, grid_size))
-    rec['cols'] = len(lattice_axis(width, grid_size))
+    rec['rows'], rec['cols'] = dims
     return rec
 
 

@@ -33,41 +33,46 @@ def complete_camera_model_config(height: int, width: int, config: CameraModelCon
     # camera.py:220-241 (principal point default is [height // 2, width // 2], consumed as x, y)
     if config.principal_point and config.focal_length and config.camera_distance:
         return config
-    config = attrs.evolve(config)
-    if not config.principal_point:
-        config.principal_point = [height // 2, width // 2]
-    if not config.focal_length or not config.camera_distance:
-        config.focal_length = max(height, width)
-        config.camera_distance = config.focal_length
-    return config
+    principal_point = config.principal_point or [height // 2, width // 2]
+    focal_length, camera_distance = config.focal_length, config.camera_distance
+    if not focal_length or not camera_distance:
+        focal_length = max(height, width)
+        camera_distance = focal_length
+    return CameraModelConfig(rotation_unit_vec=config.rotation_unit_vec,
+                             rotation_theta=config.rotation_theta, focal_length=focal_length,
+                             principal_point=principal_point, camera_distance=camera_distance)
+
+
+_F32 = np.float32
 
 
 def fill_camera_model(rec: np.ndarray, config: CameraModelConfig):
-    """CameraModel.__init__ (camera.py:157-175) -> R (double), t, focal in the page record."""
+    """CameraModel.__init__ (camera.py:157-175) -> R (double), t, focal in the page record.
+
+    Same NumPy float32 operations as the reference line by line (the lattice these constants
+    feed is rounded to integers, so the last bit matters); only the call overhead is trimmed:
+    `norm` is its own definition sqrt(x.dot(x)), and R^T . (0, 0, d) is the third row of R times
+    d (the other products are exact zeros), which leaves one real float32 matmul."""
     assert config.focal_length and config.camera_distance and config.principal_point
-    unit_vec = np.asarray(config.rotation_unit_vec, dtype=np.float32)
-    length = np.linalg.norm(unit_vec)
+    unit_vec = np.array(config.rotation_unit_vec, dtype=_F32)
+    length = np.sqrt(unit_vec.dot(unit_vec))  # np.linalg.norm of a 1-D float32 vector
     if length != 1.0:
         unit_vec /= length
     theta = float(min(max(config.rotation_theta, -89), 89) / 180 * np.pi)
     rotation_vec = unit_vec * theta  # float32
 
-    principal_point = list(config.principal_point)
-    if len(principal_point) == 2:
-        principal_point.append(0)
-    principal_point = np.asarray(principal_point, dtype=np.float32).reshape(-1, 1)
+    pp = config.principal_point
+    principal_point = np.array((pp[0], pp[1], pp[2] if len(pp) > 2 else 0), dtype=_F32)
 
-    rotation_mat = rodrigues(rotation_vec).astype(np.float32)  # cv.Rodrigues(float32) -> float32
-    cc_principal_point_vec = np.asarray([0, 0, config.camera_distance],
-                                        dtype=np.float32).reshape(-1, 1)
-    wc_shifted_original_vec = np.matmul(rotation_mat.transpose(), cc_principal_point_vec)
+    rotation_mat = rodrigues(rotation_vec).astype(_F32)  # cv.Rodrigues(float32) -> float32
+    wc_shifted_original_vec = rotation_mat[2] * _F32(config.camera_distance)
     wc_shifted_principal_point_vec = wc_shifted_original_vec - principal_point
-    translation_vec = np.matmul(rotation_mat, wc_shifted_principal_point_vec.reshape(-1, 1))
+    translation_vec = np.matmul(rotation_mat, wc_shifted_principal_point_vec.reshape(3, 1))
 
     # cv.projectPoints converts rvec / tvec / K to double and recomputes Rodrigues in double
-    rec['R'] = rodrigues(rotation_vec.astype(np.float64)).reshape(-1)
-    rec['t'] = translation_vec.astype(np.float64).reshape(-1)
-    rec['focal'] = float(np.float32(config.focal_length))
+    rec['R'] = rodrigues(rotation_vec).reshape(-1)
+    rec['t'] = translation_vec.reshape(-1)
+    rec['focal'] = float(_F32(config.focal_length))
     rec['projector'] = nv.PROJ_CAMERA
 
 
@@ -89,9 +94,9 @@ class CameraPlaneOnlyConfig(DistortionConfig):
     grid_size: int
 
 
-def plane_only_page(config: CameraPlaneOnlyConfig, shape: Tuple[int, int]):
+def plane_only_page(config: CameraPlaneOnlyConfig, shape: Tuple[int, int], out=None):
     height, width = shape
-    rec = new_grid_page(height, width, config.grid_size)
+    rec = new_grid_page(height, width, config.grid_size, out)
     rec['strategy'] = nv.CAM_PLANE
     return rec
 
@@ -122,13 +127,13 @@ class CameraCubicCurveConfig(DistortionConfig):
     grid_size: int
 
 
-def cubic_curve_page(config: CameraCubicCurveConfig, shape: Tuple[int, int]):
+def cubic_curve_page(config: CameraCubicCurveConfig, shape: Tuple[int, int], out=None):
     # CameraCubicCurvePoint2dTo3dStrategy.__init__ (camera.py:325-373)
     height, width = shape
-    rec = new_grid_page(height, width, config.grid_size)
+    rec = new_grid_page(height, width, config.grid_size, out)
     rec['strategy'] = nv.CAM_CUBIC
-    alpha = math.tan(np.clip(config.curve_alpha, -80, 80) / 180 * np.pi)
-    beta = math.tan(np.clip(config.curve_beta, -80, 80) / 180 * np.pi)
+    alpha = math.tan(min(max(config.curve_alpha, -80), 80) / 180 * np.pi)
+    beta = math.tan(min(max(config.curve_beta, -80), 80) / 180 * np.pi)
     direction = (config.curve_direction % 180) / 180 * np.pi
     rotation_mat = np.asarray(
         [[math.cos(direction), math.sin(direction)], [-math.sin(direction), math.cos(direction)]],
@@ -162,10 +167,10 @@ camera_cubic_curve = DistortionImageGridBased(config_cls=CameraCubicCurveConfig,
 
 # ---- plane line fold / curve -------------------------------------------------------------
 def plane_line_page(shape: Tuple[int, int], grid_size: int, point, direction: float, perturb_vec,
-                    alpha: float, strategy: int):
+                    alpha: float, strategy: int, out=None):
     # CameraPlaneLinePoint2dTo3dStrategy.__init__ (camera.py:434-462)
     height, width = shape
-    rec = new_grid_page(height, width, grid_size)
+    rec = new_grid_page(height, width, grid_size, out)
     rec['strategy'] = strategy
     point = np.asarray(point, dtype=np.float32)
     direction = (direction % 180) / 180 * np.pi
@@ -190,9 +195,9 @@ class CameraPlaneLineFoldConfig(DistortionConfig):
     grid_size: int
 
 
-def plane_line_fold_page(config: CameraPlaneLineFoldConfig, shape: Tuple[int, int]):
+def plane_line_fold_page(config: CameraPlaneLineFoldConfig, shape: Tuple[int, int], out=None):
     return plane_line_page(shape, config.grid_size, config.fold_point, config.fold_direction,
-                           config.fold_perturb_vec, config.fold_alpha, nv.CAM_LINE_FOLD)
+                           config.fold_perturb_vec, config.fold_alpha, nv.CAM_LINE_FOLD, out)
 
 
 class CameraPlaneLineFoldState(DistortionStateCameraOperation):
@@ -220,9 +225,9 @@ class CameraPlaneLineCurveConfig(DistortionConfig):
     grid_size: int
 
 
-def plane_line_curve_page(config: CameraPlaneLineCurveConfig, shape: Tuple[int, int]):
+def plane_line_curve_page(config: CameraPlaneLineCurveConfig, shape: Tuple[int, int], out=None):
     return plane_line_page(shape, config.grid_size, config.curve_point, config.curve_direction,
-                           config.curve_perturb_vec, config.curve_alpha, nv.CAM_LINE_CURVE)
+                           config.curve_perturb_vec, config.curve_alpha, nv.CAM_LINE_CURVE, out)
 
 
 class CameraPlaneLineCurveState(DistortionStateCameraOperation):

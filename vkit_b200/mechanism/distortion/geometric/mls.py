@@ -28,10 +28,10 @@ class SimilarityMlsConfig(DistortionConfig):
     resize_as_src: bool = False
 
 
-def similarity_mls_page(config: SimilarityMlsConfig, shape: Tuple[int, int]):
+def similarity_mls_page(config: SimilarityMlsConfig, shape: Tuple[int, int], out=None):
     """Page record + the device tensors it points to (kept alive by the caller)."""
     height, width = shape
-    rec = new_grid_page(height, width, config.grid_size)
+    rec = new_grid_page(height, width, config.grid_size, out)
     rec['projector'] = nv.PROJ_MLS
     rec['resize_as_src'] = int(config.resize_as_src)
     # PointTuple.to_smooth_np_array: rounded coordinates as float32 (mls.py:49-50)
