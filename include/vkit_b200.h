@@ -313,6 +313,30 @@ int vkb_streak_masks(uint8_t* image, int32_t h, int32_t w, int32_t channels,
                      const uint8_t* mask_vert, const uint8_t* mask_hori, int32_t dash_thickness,
                      int32_t dash_gap, const float* color_host, float alpha, void* stream);
 
+/* Batched photometric chain over a ragged batch of pages: optional cv.GaussianBlur (uint8,
+ * 8.8 fixed point, BORDER_REFLECT_101; photometric/blur.py:49-76) followed by a per-pixel op
+ * list (photometric/color.py:32-439) in ONE pass, per-page shapes / taps / ops.  The batched
+ * form of vkb_gaussian_blur_u8 + vkb_color_ops for chains such as
+ * similarity_mls -> gaussian_blur -> color_shift (random_distortion.py:350-392).
+ * `pages`: device array, `pages_host`: the same records on the host (validation and launch
+ * shape).  src != dst when blur_radius > 0.  blur_taps: 2*radius+1 integers summing to 256. */
+typedef struct vkb_photo_page {
+    const uint8_t* src;
+    uint8_t* dst;
+    int32_t h, w;
+    int32_t blur_radius; /* 0: no blur */
+    int32_t n_ops;
+    int32_t blur_taps[17];
+    int32_t pad_;
+    vkb_color_op ops[VKB_MAX_COLOR_OPS];
+} vkb_photo_page;
+int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_photo_page* pages_host,
+                            int32_t n_pages, int32_t channels, void* stream);
+/* Per-page channel statistics of the `src` planes of a ragged batch.
+ * out (device): per page 3 x uint64 sums, then 3 x uint32 mins, 3 x uint32 maxs (48 bytes). */
+int vkb_channel_stats_batched(const vkb_photo_page* pages, int32_t n_pages, int32_t channels,
+                              void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -435,3 +435,121 @@ def test_draw_list_text_layer_compositing(vk):
     ref3 = background.copy()
     port.fill_np_array(ref3, bottom, np_mask=active.mat == 0)
     assert sha(page.mat) == sha(ref3)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 3 shape: similarity_mls -> gaussian_blur -> colour op, batched and ragged
+# ---------------------------------------------------------------------------------------------
+def _mls_batch_cases():
+    return [c for c in GEOMETRIC if c['op'] in ('similarity_mls', 'camera_cubic_curve',
+                                                 'camera_plane_line_fold')
+            and tuple(c['shape']) == (136, 176)]
+
+
+def test_batched_chain_matches_oracle_exact_ops(vk):
+    """grid op -> gaussian_blur -> mean_shift -> complement through the fused batched kernel;
+    every stage is integer arithmetic, so the result must equal the oracle bit for bit."""
+    import torch
+    from oracle import vkit_port as port
+    from vkit_b200.batch import GeometricBatch, distort_chain
+    cases = _mls_batch_cases() * 2
+    shape = (136, 176)
+    n = len(cases)
+    rng = np.random.default_rng(7)
+    sigmas = [float(s) for s in rng.uniform(0.5, 2.2, n)]  # 3, 5 and 7 tap kernels
+    deltas = [int(d) for d in rng.integers(-60, 60, n)]
+    thresholds = [None if i % 3 == 0 else int(rng.integers(0, 255)) for i in range(n)]
+    images = np.stack([make_inputs(c['seed'], shape)[0] for c in cases])
+    stages = [
+        ('gaussian_blur', [{'sigma': s} for s in sigmas]),
+        ('mean_shift', [{'delta': d} for d in deltas]),
+        ('complement', [{'threshold': t, 'enable_threshold_lte': bool(i & 1)}
+                        for i, t in enumerate(thresholds)]),
+    ]
+    out, photo = distort_chain([c['op'] for c in cases], [product_config(c) for c in cases], shape,
+                               torch.from_numpy(images).cuda(), stages)
+    assert photo.launches == 1  # blur + both ops fused into one pass
+    geo = GeometricBatch([c['op'] for c in cases], [product_config(c) for c in cases], shape)
+    plain = geo.run(torch.from_numpy(images).cuda())
+    port.use_cv2(False)
+    for i, case in enumerate(cases):
+        assert out.shapes[i] == tuple(case['result_shape'])
+        base = plain.image(i).cpu().numpy()  # the remap itself is covered by the golden tests
+        ref = port.gaussian_blur(base, sigmas[i])
+        ref = port.mean_shift(ref, deltas[i])
+        ref = port.complement(ref, thresholds[i], bool(i & 1))
+        got = out.image(i).cpu().numpy()
+        assert np.array_equal(got, ref), (i, case['id'], _diff_report(got, ref))
+
+
+def test_batched_chain_matches_single_page_ops(vk):
+    """similarity_mls -> gaussian_blur -> color_shift -> std_shift (config 3 and its variants):
+    the batched chain must equal the per-page Distortion calls bit for bit, and stay within the
+    colour tolerances of the oracle."""
+    import torch
+    from oracle import vkit_port as port
+    from vkit_b200.batch import distort_chain
+    element, distortion = vk
+    cases = _mls_batch_cases()
+    shape = (136, 176)
+    n = len(cases)
+    rng = np.random.default_rng(11)
+    sigmas = [float(s) for s in rng.uniform(0.5, 1.0, n)]
+    hue = [int(d) for d in rng.integers(1, 255, n)]
+    scales = [float(s) for s in rng.uniform(0.6, 1.6, n)]
+    light = [int(d) for d in rng.integers(-80, 80, n)]
+    images = np.stack([make_inputs(c['seed'], shape)[0] for c in cases])
+    stages = [
+        ('gaussian_blur', [{'sigma': s} for s in sigmas]),
+        ('color_shift', [{'delta': d} for d in hue]),
+        ('std_shift', [{'scale': s} for s in scales]),
+        ('brightness_shift', [{'delta': d, 'intermediate_image_mode': 'hsv'} for d in light]),
+    ]
+    out, photo = distort_chain([c['op'] for c in cases], [product_config(c) for c in cases], shape,
+                               torch.from_numpy(images).cuda(), stages)
+    assert photo.launches == 4  # blur+hue | stats (2 launches) | std+light
+    port.use_cv2(False)
+    for i, case in enumerate(cases):
+        op = getattr(distortion, case['op'])
+        single = op.distort(product_config(case), image=element.Image(mat=images[i])).image
+        geo_image = single.mat.copy()
+        single = distortion.gaussian_blur.distort({'sigma': sigmas[i]}, image=single).image
+        single = distortion.color_shift.distort({'delta': hue[i]}, image=single).image
+        single = distortion.std_shift.distort({'scale': scales[i]}, image=single).image
+        single = distortion.brightness_shift.distort(
+            {'delta': light[i], 'intermediate_image_mode': 'hsv'}, image=single).image
+        got = out.image(i).cpu().numpy()
+        assert np.array_equal(got, single.mat), (i, case['id'], _diff_report(got, single.mat))
+        # oracle for the first two stages (colour conversions are +-1 inside cv2 itself)
+        ref = port.color_shift(port.gaussian_blur(geo_image, sigmas[i]), hue[i])
+        two, _ = distort_chain([case['op']], [product_config(case)], shape,
+                               torch.from_numpy(images[i:i + 1]).cuda(),
+                               [('gaussian_blur', [{'sigma': sigmas[i]}]),
+                                ('color_shift', [{'delta': hue[i]}])])
+        diff = np.abs(two.image(0).cpu().numpy().astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3, (i, case['id'])
+
+
+def test_photometric_batch_ragged_edges(vk):
+    """Ragged shapes incl. pages smaller than the blur halo, 1-pixel pages, grayscale."""
+    import torch
+    from oracle import vkit_port as port
+    from vkit_b200.batch import PhotometricBatch
+    port.use_cv2(False)
+    for channels in (3, 1):
+        shapes = [(1, 1), (2, 3), (5, 70), (33, 31), (64, 64), (97, 130), (3, 200)]
+        rng = np.random.default_rng(3)
+        pages = [rng.integers(0, 256, s + ((3,) if channels == 3 else ()), dtype=np.uint8)
+                 for s in shapes]
+        sigmas = [0.5, 0.9, 1.3, 2.0, 2.4, 0.7, 1.1]
+        arena = torch.from_numpy(np.concatenate([p.reshape(-1) for p in pages])).cuda()
+        photo = PhotometricBatch(shapes, channels, [
+            ('gaussian_blur', [{'sigma': s} for s in sigmas]),
+            ('posterization', [{'num_bits': i % 5} for i in range(len(shapes))]),
+        ])
+        result = photo.run(arena).cpu().numpy()
+        for i, page in enumerate(pages):
+            ref = port.posterization(port.gaussian_blur(page, sigmas[i]), i % 5)
+            a = int(photo.pixel_offsets[i]) * channels
+            got = result[a:a + page.size].reshape(page.shape)
+            assert np.array_equal(got, ref), (channels, shapes[i], _diff_report(got, ref))

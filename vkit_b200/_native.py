@@ -87,6 +87,14 @@ class ColorOp(ctypes.Structure):
     ]
 
 
+class PhotoPage(ctypes.Structure):
+    _fields_ = [
+        ('src', c_void_p), ('dst', c_void_p), ('h', c_int32), ('w', c_int32),
+        ('blur_radius', c_int32), ('n_ops', c_int32), ('blur_taps', c_int32 * 17),
+        ('pad_', c_int32), ('ops', ColorOp * 8),
+    ]
+
+
 class Rect(ctypes.Structure):
     _fields_ = [('up', c_int32), ('down', c_int32), ('left', c_int32), ('right', c_int32)]
 
@@ -121,6 +129,8 @@ def _np_dtype(struct_cls):
 PLANES_DTYPE = _np_dtype(Planes)
 BLEND_ITEM_DTYPE = _np_dtype(BlendItem)
 RECT_DTYPE = _np_dtype(Rect)
+PHOTO_PAGE_DTYPE = _np_dtype(PhotoPage)
+COLOR_OP_DTYPE = _np_dtype(ColorOp)
 WARP_PAGE_DTYPE = _np_dtype(WarpPage)
 GRID_PAGE_DTYPE = _np_dtype(GridPage)
 GRID_META_DTYPE = _np_dtype(GridMeta)
@@ -164,6 +174,8 @@ def _declare(lib):
     lib.vkb_fill_rects.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.vkb_streak_masks.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, POINTER(c_float),
                                      c_float, vp]
+    lib.vkb_photo_chain_batched.argtypes = [vp, vp, i32, i32, vp]
+    lib.vkb_channel_stats_batched.argtypes = [vp, i32, i32, vp, vp]
     for name in EXPORTS:
         getattr(lib, name).restype = c_int32
 
@@ -173,7 +185,8 @@ EXPORTS = (
     'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon',
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
-    'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks',
+    'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks', 'vkb_photo_chain_batched',
+    'vkb_channel_stats_batched',
 )
 
 

@@ -9,6 +9,7 @@ arena, one small D2H per batch for the result shapes.
     out = engine.run(images_dev)          # images_dev: (B, H, W, 3) uint8 CUDA tensor
     out.image(i)                          # (H'_i, W'_i, 3) view into the output arena
 """
+import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -28,13 +29,13 @@ _PAGE_BUILDERS = {
 }
 
 
-def grid_page_record(op_name: str, config, shape: Tuple[int, int], out=None):
+def grid_page_record(op_name: str, config, shape: Tuple[int, int], out=None, handle_sink=None):
     """(page record, keepalive) for one page of a grid-based op.  `out`: zeroed element of a
-    GRID_PAGE_DTYPE array to fill in place."""
+    GRID_PAGE_DTYPE array to fill in place; `handle_sink`: see similarity_mls_page."""
     height, width = shape
     if op_name == 'similarity_mls':
         config = dyn_structure(config, _mls.SimilarityMlsConfig)
-        return _mls.similarity_mls_page(config, shape, out)
+        return _mls.similarity_mls_page(config, shape, out, handle_sink)
     config_cls, builder = _PAGE_BUILDERS[op_name]
     config = dyn_structure(config, config_cls)
     rec = builder(config, shape, out)
@@ -79,10 +80,15 @@ class GeometricBatch:
         keepalive = []
         self.n = len(op_names)
         self.pages = np.zeros(self.n, dtype=nv.GRID_PAGE_DTYPE)
+        handle_sink = []
         for i, (op_name, config) in enumerate(zip(op_names, configs)):
-            _, keep = grid_page_record(op_name, config, self.shape, out=self.pages[i])
+            _, keep = grid_page_record(op_name, config, self.shape, out=self.pages[i],
+                                       handle_sink=handle_sink)
             if keep is not None:
                 keepalive.append(keep)
+        handles = _mls.upload_handles(handle_sink) if handle_sink else None
+        if handles is not None:
+            keepalive.append(handles)
         self.keepalive = keepalive
         self.plan: Optional[GridBatch] = None
 
@@ -251,3 +257,215 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     if use_thread:
         thread.join()
     return host_out, shapes, offsets
+
+
+# =============================================================================================
+# Photometric chain over a ragged batch
+# =============================================================================================
+from .mechanism.distortion.photometric import blur as _blur  # noqa: E402
+from .mechanism.distortion.photometric import color as _color  # noqa: E402
+from .mechanism.distortion.photometric.opt import OutOfBoundBehavior, make_op  # noqa: E402
+
+_ALL_BITS = {1: 0b1, 3: 0b111, 4: 0b1111}
+
+
+def _bits(channels: int, selected):
+    if not selected:
+        return _ALL_BITS[channels]
+    bits = 0
+    for c in selected:
+        if c < 0 or c >= channels:
+            raise IndexError(f'channel {c} out of range')
+        bits |= 1 << c
+    return bits
+
+
+def _stage_ops(name: str, config, channels: int, stats):
+    """Op list of one photometric stage for one RGB / GRAYSCALE uint8 page (the per-page half of
+    photometric/color.py); `stats` = (sums, mins, maxs, n_pixels) of the stage's input when the
+    stage needs them.  Returns [] for a NOP."""
+    if name == 'mean_shift':
+        config = dyn_structure(config, _color.MeanShiftConfig)
+        if config.delta == 0:
+            return []
+        return [make_op(nv.OP_MEAN_SHIFT, i0=config.delta,
+                        i1=-1 if config.threshold is None else config.threshold,
+                        i2=_bits(channels, config.channels),
+                        i3=1 if config.oob_behavior == OutOfBoundBehavior.CYCLE else 0)]
+    if name == 'color_shift':
+        config = dyn_structure(config, _color.ColorShiftConfig)
+        return [make_op(nv.OP_HUE_SHIFT_RGB, i0=config.delta)]
+    if name == 'brightness_shift':
+        config = dyn_structure(config, _color.BrightnessShiftConfig)
+        from .element import ImageMode
+        via_hsv = 1 if config.intermediate_image_mode == ImageMode.HSV else 0
+        return [make_op(nv.OP_LIGHT_SHIFT_RGB, i0=config.delta, i1=via_hsv)]
+    if name == 'complement':
+        config = dyn_structure(config, _color.ComplementConfig)
+        return [make_op(nv.OP_COMPLEMENT, i1=-1 if config.threshold is None else config.threshold,
+                        i2=_bits(channels, config.channels), i3=int(config.enable_threshold_lte))]
+    if name == 'posterization':
+        config = dyn_structure(config, _color.PosterizationConfig)
+        if config.num_bits == 0:
+            return []
+        return [make_op(nv.OP_POSTERIZE, i0=(0xFF >> config.num_bits) << config.num_bits,
+                        i2=_bits(channels, config.channels))]
+    if name == 'color_balance':
+        config = dyn_structure(config, _color.ColorBalanceConfig)
+        if channels == 1:
+            return []
+        return [make_op(nv.OP_COLOR_BALANCE, f0=np.float32(config.ratio),
+                        f1=np.float32(1 - config.ratio))]
+    if name == 'std_shift':
+        config = dyn_structure(config, _color.StdShiftConfig)
+        sums, _, _, count = stats
+        means = [np.float32(float(s) / count) for s in sums[:min(channels, 3)]]
+        sub = [np.float32(m) * np.float32(config.scale - 1) for m in means] + [0.0, 0.0]
+        return [make_op(nv.OP_STD_SHIFT, i2=_bits(channels, config.channels),
+                        f0=np.float32(config.scale), f1=sub[0], f2=sub[1] if channels > 1 else 0.0,
+                        f3=sub[2] if channels > 2 else 0.0)]
+    if name == 'boundary_equalization':
+        config = dyn_structure(config, _color.BoundaryEqualizationConfig)
+        _, mins, maxs, _ = stats
+        bits = _bits(channels, config.channels)
+        mn, sc, active = [0.0] * 3, [0.0] * 3, 0
+        for c in range(min(channels, 3)):
+            if not (bits >> c) & 1:
+                continue
+            delta = np.float32(maxs[c]) - np.float32(mins[c])
+            if delta > 0:
+                active |= 1 << c
+                mn[c] = float(mins[c])
+                sc[c] = np.float32(255.0) / delta
+        if not active:
+            return []
+        return [make_op(nv.OP_BOUNDARY_EQ, i2=active, f0=mn[0], f1=mn[1], f2=mn[2], g0=sc[0],
+                        g1=sc[1], g2=sc[2])]
+    raise NotImplementedError(f'{name} has no batched form')
+
+
+_STATS_STAGES = ('std_shift', 'boundary_equalization')
+
+
+class PhotometricBatch:
+    """A chain of photometric stages over a ragged batch of uint8 pages (RGB or GRAYSCALE), every
+    page with its own configs: `stages` = [(name, configs)], name one of gaussian_blur,
+    mean_shift, color_shift, brightness_shift, std_shift, boundary_equalization, complement,
+    posterization, color_balance.
+
+    Consecutive stages are folded into passes of the fused kernel (`vkb_photo_chain_batched`):
+    a pass is an optional Gaussian blur followed by up to 8 per-pixel ops; a new pass starts at
+    every blur and at every stage that needs statistics of its input."""
+
+    def __init__(self, shapes: Sequence[Tuple[int, int]], channels: int, stages):
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.n = len(self.shapes)
+        self.channels = channels
+        self.stages = [(name, list(configs)) for name, configs in stages]
+        for name, configs in self.stages:
+            if len(configs) != self.n:
+                raise ValueError(f'stage {name}: one config per page expected')
+        sizes = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
+        self.pixel_offsets = np.concatenate([[0], np.cumsum(sizes)])
+        self.launches = 0
+
+    def _new_pass(self):
+        rec = np.zeros(self.n, dtype=nv.PHOTO_PAGE_DTYPE)
+        rec['h'] = [s[0] for s in self.shapes]
+        rec['w'] = [s[1] for s in self.shapes]
+        return rec
+
+    def _launch(self, rec, src, dst):
+        base = self.pixel_offsets[:-1].astype(np.uint64) * np.uint64(self.channels)
+        rec['src'] = np.uint64(src.data_ptr()) + base
+        rec['dst'] = np.uint64(dst.data_ptr()) + base
+        rec_dev = dv.upload_structs(rec)
+        nv.check(nv.lib().vkb_photo_chain_batched(dv.ptr(rec_dev), rec.ctypes.data_as(ctypes.c_void_p),
+                                                  self.n, self.channels, dv.stream_ptr()),
+                 'vkb_photo_chain_batched')
+        self.launches += 1
+        return rec_dev
+
+    def _stats(self, arena):
+        rec = self._new_pass()
+        base = self.pixel_offsets[:-1].astype(np.uint64) * np.uint64(self.channels)
+        rec['src'] = np.uint64(arena.data_ptr()) + base
+        rec['dst'] = rec['src']
+        rec_dev = dv.upload_structs(rec)
+        out = dv.empty((self.n, 48), np.uint8)
+        nv.check(nv.lib().vkb_channel_stats_batched(dv.ptr(rec_dev), self.n, min(self.channels, 3),
+                                                    dv.ptr(out), dv.stream_ptr()),
+                 'vkb_channel_stats_batched')
+        self.launches += 2
+        raw = dv.to_host(out)
+        sums = raw[:, :24].copy().view(np.uint64)
+        mins = raw[:, 24:36].copy().view(np.uint32)
+        maxs = raw[:, 36:48].copy().view(np.uint32)
+        return sums, mins, maxs
+
+    def run(self, arena, scratch=None):
+        """arena: flat uint8 CUDA tensor holding the pages back to back (pixel_offsets order).
+        Returns the tensor that holds the result (arena itself or `scratch`)."""
+        t = dv.require_cuda()
+        cur = arena
+        other = scratch
+        rec = self._new_pass()
+        dirty = False
+
+        def flush():
+            nonlocal cur, other, rec, dirty
+            if not dirty:
+                return
+            if (rec['blur_radius'] > 0).any():
+                if other is None:
+                    other = t.empty_like(cur)
+                self._launch(rec, cur, other)
+                cur, other = other, cur
+            else:
+                self._launch(rec, cur, cur)
+            rec = self._new_pass()
+            dirty = False
+
+        for name, configs in self.stages:
+            if name == 'gaussian_blur':
+                flush()
+                for i, config in enumerate(configs):
+                    config = dyn_structure(config, _blur.GaussianBlurConfig)
+                    ksize = _blur._estimate_gaussian_kernel_size(config.sigma)
+                    if ksize > 17:
+                        raise NotImplementedError('gaussian_blur kernels wider than 17 taps')
+                    taps = _blur.gaussian_kernel_u8(ksize, config.sigma)
+                    rec['blur_radius'][i] = ksize // 2
+                    rec['blur_taps'][i, :ksize] = taps
+                dirty = True
+                continue
+            stats = None
+            if name in _STATS_STAGES:
+                flush()
+                stats = self._stats(cur)
+            elif int(rec['n_ops'].max()) >= nv.MAX_COLOR_OPS:
+                flush()
+            for i, config in enumerate(configs):
+                page_stats = None
+                if stats is not None:
+                    h, w = self.shapes[i]
+                    page_stats = (stats[0][i], stats[1][i], stats[2][i], h * w)
+                for op in _stage_ops(name, config, self.channels, page_stats):
+                    k = int(rec['n_ops'][i])
+                    rec['ops'][i, k] = np.frombuffer(bytes(op), dtype=nv.COLOR_OP_DTYPE)[0]
+                    rec['n_ops'][i] = k + 1
+                    dirty = True
+        flush()
+        return cur
+
+
+def distort_chain(op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int], images,
+                  photometric_stages):
+    """Geometric grid op per page followed by a photometric chain, all batched:
+    e.g. similarity_mls -> gaussian_blur -> color_shift (BASELINE config 3).
+    images: (B, H, W, C) uint8 CUDA tensor.  Returns (BatchOutput, PhotometricBatch)."""
+    engine = GeometricBatch(op_names, configs, shape)
+    out = engine.run(images)
+    photo = PhotometricBatch(out.shapes, out.channels, photometric_stages)
+    out.image_arena = photo.run(out.image_arena)
+    return out, photo

@@ -513,6 +513,178 @@ __global__ void __launch_bounds__(256) streak_masks_kernel(uint8_t* image, int h
     if (hori) streak_blend(p, channels, col, alpha);
 }
 
+// ============================================================================================
+// Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
+// over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
+// gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
+// them (distortion_policy/random_distortion.py:350-392), without the intermediate image.
+//
+// Block = 32 x 8 threads on a 32 x 32 output tile.  The tile plus halo is staged in shared
+// memory (interior tiles: aligned 32-bit loads of the row span, each row keeps its own byte
+// misalignment; border tiles: byte loads with BORDER_REFLECT_101), blurred horizontally into
+// saturated 16-bit rows, then vertically; the op list runs on the blurred pixel in registers.
+// ============================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* __restrict__ pages,
+                                                          int max_r) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const vkb_photo_page& pg = pages[blockIdx.z];
+    const int h = pg.h, w = pg.w;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (x0 >= w || y0 >= h) return;
+    const uint8_t* __restrict__ src = pg.src;
+    uint8_t* __restrict__ dst = pg.dst;
+    const int r = pg.blur_radius;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int n_ops = pg.n_ops;
+    const int x = x0 + threadIdx.x;
+
+    if (r == 0) {
+        if (x >= w) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = y0 + threadIdx.y + 8 * j;
+            if (y >= h) break;
+            const long long i = (long long)y * w + x;
+            int px[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < C; ++c) px[c] = src[i * C + c];
+            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C);
+#pragma unroll
+            for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
+        }
+        return;
+    }
+
+    // shared layout (sized by the host for the largest radius of the batch)
+    const int TWm = 32 + 2 * max_r;
+    const int row_stride = ((TWm * C + 3) & ~3) + 4;  // bytes; room for the row's misalignment
+    uint8_t* tile = smem;                               // TH rows of row_stride bytes
+    unsigned short* rows =
+        reinterpret_cast<unsigned short*>(smem + (size_t)TWm * row_stride);  // TH x 32 x C
+    __shared__ int taps[2 * 8 + 1];
+    if (tid <= 2 * r) taps[tid] = pg.blur_taps[tid];
+
+    const int TW = 32 + 2 * r, TH = 32 + 2 * r;
+    const bool interior = x0 - r >= 0 && y0 - r >= 0 && x0 + 32 + r <= w && y0 + 32 + r <= h;
+    if (interior) {
+        // aligned words of every row span; the last word of the last row must stay inside the
+        // plane, which holds whenever another row follows (always true unless y0+32+r == h and
+        // the span ends in the plane's final word: reading it is still in bounds).
+        const int words_max = (TW * C + 3 + 3) >> 2;
+        for (int i = tid; i < TH * words_max; i += 256) {
+            const int ty = i / words_max, k = i - ty * words_max;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(src)
+                                + ((size_t)(y0 - r + ty) * w + (x0 - r)) * C;
+            const uintptr_t a0 = a & ~(uintptr_t)3;
+            const int span_words = (int)(((a - a0) + TW * C + 3) >> 2);
+            if (k < span_words) {
+                const uintptr_t wa = a0 + 4u * k;
+                // the final word of the final row of the plane may poke past the allocation
+                uint32_t v;
+                const uintptr_t end = reinterpret_cast<uintptr_t>(src) + (size_t)h * w * C;
+                if (wa + 4 <= end) {
+                    v = __ldg(reinterpret_cast<const uint32_t*>(wa));
+                } else {
+                    v = 0;
+                    for (int b = 0; b < 4; ++b)
+                        if (wa + b < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(wa + b)) << (8 * b);
+                }
+                *reinterpret_cast<uint32_t*>(tile + ty * row_stride + 4 * k) = v;
+            }
+        }
+    } else {
+        for (int i = tid; i < TH * TW; i += 256) {
+            const int ty = i / TW, tx = i - ty * TW;
+            const int sy = reflect101(y0 + ty - r, h), sx = reflect101(x0 + tx - r, w);
+            const uint8_t* p = src + ((long long)sy * w + sx) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) tile[ty * row_stride + tx * C + c] = p[c];
+        }
+    }
+    __syncthreads();
+    // horizontal pass
+    for (int i = tid; i < TH * 32; i += 256) {
+        const int ty = i >> 5, tx = i & 31;
+        int mis = 0;
+        if (interior)
+            mis = (int)((reinterpret_cast<uintptr_t>(src) + ((size_t)(y0 - r + ty) * w + (x0 - r)) * C) & 3);
+        const uint8_t* __restrict__ p = tile + ty * row_stride + mis + tx * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k) acc += (int)p[k * C + c] * taps[k];
+            rows[i * C + c] = (unsigned short)min(acc, 65535);
+        }
+    }
+    __syncthreads();
+    if (x >= w) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ly = threadIdx.y + 8 * j;
+        const int y = y0 + ly;
+        if (y >= h) break;
+        int px[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k)
+                acc += (int)rows[((ly + k) * 32 + threadIdx.x) * C + c] * taps[k];
+            px[c] = min((acc + (1 << 15)) >> 16, 255);
+        }
+        for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C);
+        const long long i = (long long)y * w + x;
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
+    }
+}
+
+// per-page channel sums / mins / maxs of a ragged batch (std_shift, boundary_equalization)
+__global__ void __launch_bounds__(256) channel_stats_batched_kernel(
+    const vkb_photo_page* __restrict__ pages, int channels, unsigned long long* __restrict__ out) {
+    const vkb_photo_page& pg = pages[blockIdx.y];
+    const long long n = (long long)pg.h * pg.w;
+    unsigned long long s[3] = {0, 0, 0};
+    unsigned int mn[3] = {255, 255, 255}, mx[3] = {0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < channels; ++c) {
+            const unsigned int v = pg.src[i * channels + c];
+            s[c] += v;
+            mn[c] = min(mn[c], v);
+            mx[c] = max(mx[c], v);
+        }
+    }
+    // out per page: 3 sums (u64), then 3 mins and 3 maxs packed as u32 pairs in 3 more u64 slots
+    unsigned long long* o = out + (size_t)blockIdx.y * 6;
+    unsigned int* o32 = reinterpret_cast<unsigned int*>(o + 3);
+    for (int c = 0; c < channels; ++c) {
+        unsigned long long v = s[c];
+        unsigned int a = mn[c], b = mx[c];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, d);
+            a = min(a, __shfl_xor_sync(0xffffffffu, a, d));
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, d));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(o + c, v);
+            atomicMin(o32 + c, a);
+            atomicMax(o32 + 3 + c, b);
+        }
+    }
+}
+
+__global__ void channel_stats_batched_init_kernel(unsigned long long* out, int n_pages) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pages) return;
+    unsigned long long* o = out + (size_t)i * 6;
+    unsigned int* o32 = reinterpret_cast<unsigned int*>(o + 3);
+    o[0] = o[1] = o[2] = 0;
+    o32[0] = o32[1] = o32[2] = 0xffffffffu;
+    o32[3] = o32[4] = o32[5] = 0;
+}
+
 }  // namespace vkb
 
 // ============================================================================================
@@ -681,4 +853,44 @@ extern "C" int vkb_streak_masks(uint8_t* image, int32_t h, int32_t w, int32_t ch
     streak_masks_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
         image, h, w, channels, mask_vert, mask_hori, dash_thickness, dash_gap, col, alpha);
     return check_launch("streak_masks_kernel");
+}
+
+extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_photo_page* pages_host,
+                                       int32_t n_pages, int32_t channels, void* stream) {
+    VKB_REQUIRE(pages && pages_host && n_pages > 0 && n_pages <= 65535, "bad arguments");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    int max_h = 0, max_w = 0, max_r = 0;
+    for (int i = 0; i < n_pages; ++i) {
+        const vkb_photo_page& p = pages_host[i];
+        VKB_REQUIRE(p.src && p.dst && p.h > 0 && p.w > 0, "page without planes");
+        VKB_REQUIRE(p.blur_radius >= 0 && p.blur_radius <= 8, "blur radius must be 0..8");
+        VKB_REQUIRE(p.n_ops >= 0 && p.n_ops <= VKB_MAX_COLOR_OPS, "too many ops");
+        VKB_REQUIRE(p.blur_radius == 0 || p.src != p.dst, "blur cannot run in place");
+        max_h = p.h > max_h ? p.h : max_h;
+        max_w = p.w > max_w ? p.w : max_w;
+        max_r = p.blur_radius > max_r ? p.blur_radius : max_r;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_tables(st);
+    if (rc) return rc;
+    const int TW = 32 + 2 * max_r;
+    const int row_stride = ((TW * channels + 3) & ~3) + 4;
+    const size_t smem = max_r ? (size_t)TW * row_stride + (size_t)TW * 32 * channels * 2 : 0;
+    dim3 grid((max_w + 31) / 32, (max_h + 31) / 32, n_pages);
+    VKB_REQUIRE(grid.y <= 65535, "page too tall");
+    if (channels == 1) photo_chain_kernel<1><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
+    else if (channels == 3) photo_chain_kernel<3><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
+    else photo_chain_kernel<4><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
+    return check_launch("photo_chain_kernel");
+}
+
+extern "C" int vkb_channel_stats_batched(const vkb_photo_page* pages, int32_t n_pages,
+                                         int32_t channels, void* out, void* stream) {
+    VKB_REQUIRE(pages && out && n_pages > 0 && n_pages <= 65535, "bad arguments");
+    VKB_REQUIRE(channels >= 1 && channels <= 3, "channels must be 1..3");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+    channel_stats_batched_init_kernel<<<(n_pages + 255) / 256, 256, 0, st>>>(o, n_pages);
+    channel_stats_batched_kernel<<<dim3(64, n_pages), 256, 0, st>>>(pages, channels, o);
+    return check_launch("channel_stats_batched_kernel");
 }

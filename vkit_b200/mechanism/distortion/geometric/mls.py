@@ -28,8 +28,12 @@ class SimilarityMlsConfig(DistortionConfig):
     resize_as_src: bool = False
 
 
-def similarity_mls_page(config: SimilarityMlsConfig, shape: Tuple[int, int], out=None):
-    """Page record + the device tensors it points to (kept alive by the caller)."""
+def similarity_mls_page(config: SimilarityMlsConfig, shape: Tuple[int, int], out=None,
+                        handle_sink=None):
+    """Page record + the device tensors it points to (kept alive by the caller).
+    `handle_sink`: a list; when given the handle arrays are appended as (record, src, dst) and
+    NOT uploaded -- the batch engine uploads all pages' handles in one copy and patches the
+    pointers (`upload_handles`)."""
     height, width = shape
     rec = new_grid_page(height, width, config.grid_size, out)
     rec['projector'] = nv.PROJ_MLS
@@ -38,11 +42,31 @@ def similarity_mls_page(config: SimilarityMlsConfig, shape: Tuple[int, int], out
     src = np.ascontiguousarray(PointTuple(config.src_handle_points).to_smooth_np_array())
     dst = np.ascontiguousarray(PointTuple(config.dst_handle_points).to_smooth_np_array())
     assert src.shape == dst.shape and src.ndim == 2
-    handles = dv.to_device(np.stack([src, dst]))
     rec['n_handles'] = src.shape[0]
+    if handle_sink is not None:
+        handle_sink.append((rec, src, dst))
+        return rec, None
+    handles = dv.to_device(np.stack([src, dst]))
     rec['handles_src'] = handles[0].data_ptr()
     rec['handles_dst'] = handles[1].data_ptr()
     return rec, handles
+
+
+def upload_handles(handle_sink):
+    """One H2D copy for the handles of every page in `handle_sink`; returns the device tensor the
+    page records now point into."""
+    if not handle_sink:
+        return None
+    flat = np.concatenate([np.concatenate([src.reshape(-1), dst.reshape(-1)])
+                           for _, src, dst in handle_sink]).astype(np.float32)
+    dev = dv.to_device(flat)
+    base = dev.data_ptr()
+    offset = 0
+    for rec, src, dst in handle_sink:
+        rec['handles_src'] = base + offset * 4
+        rec['handles_dst'] = base + (offset + src.size) * 4
+        offset += src.size + dst.size
+    return dev
 
 
 class SimilarityMlsState(DistortionStateImageGridBased):
