@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
 }
 
 // ============================================================================================
-// Coverage masks: half a warp per cell, lane per row of the cell's bounding box (a typical
-// cell spans 16-17 rows; rows 16.. of taller cells are done in a second pass).
+// Coverage masks: warp per cell, lane per row of the cell's bounding box.  (Half a warp per
+// cell was measured 1.5x SLOWER: two cells per warp diverge in poly_row_mask.)
 // ============================================================================================
 __global__ void __launch_bounds__(128) grid_masks_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max,
@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
     const int C = (pg.rows - 1) * ccols;
-    const int cell = blockIdx.x * 8 + (threadIdx.x >> 4);
+    const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (cell >= C) return;
-    const int sub = threadIdx.x & 15;
+    const int lane = threadIdx.x & 31;
     const int r = floor_div_small(cell, ccols, __fdividef(1.0f, (float)ccols));
     const int c = cell - r * ccols;
     const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
@@ -449,13 +449,13 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     uint32_t* out = cell_masks + ((size_t)page * c_max + cell) * VKB_CELL_MASK_WORDS;
     if (nwords != 1 || nrows > VKB_CELL_MASK_WORDS) {
         // too large for the fixed budget: the remap kernel rasterises this cell on the fly.
-        if (sub == 0) cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
+        if (lane == 0) cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
         return;
     }
-    for (int row = sub; row < nrows; row += 16) {
+    if (lane < nrows) {
         uint32_t word = 0;
-        poly_row_mask<4>(px, py, y0 + row, x0, &word, 1);
-        out[row] = word;
+        poly_row_mask<4>(px, py, y0 + lane, x0, &word, 1);
+        out[lane] = word;
     }
 }
 
@@ -1298,7 +1298,7 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
-    grid_masks_kernel<<<dim3((c_max + 7) / 8, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
+    grid_masks_kernel<<<dim3((c_max + 3) / 4, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
                                                                      cell_box, cell_masks);
     rc = check_launch("grid_masks_kernel");
     if (rc) return rc;
