@@ -42,15 +42,19 @@ def main():
     pages = torch.randint(0, 256, (n,) + bench.PAGE_SHAPE + (3,), dtype=torch.uint8, device='cuda')
     names = ['similarity_mls'] * n
     scratch = [None]
+    kernel_events = []
+    remap_events = []
 
     def step(events=None):
         engine = GeometricBatch(names, mls_cfg, bench.PAGE_SHAPE)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        out = engine.run(pages)
+        out = engine.run(pages, launch_events=remap_events if events is not None else None)
         e[1].record()
         photo = PhotometricBatch(out.shapes, 3, [('gaussian_blur', blur_cfg),
                                                   ('color_shift', color_cfg)])
+        if events is not None:
+            photo.launch_events = kernel_events
         if scratch[0] is None or scratch[0].numel() != out.image_arena.numel():
             scratch[0] = torch.empty_like(out.image_arena)
         res = photo.run(out.image_arena, scratch[0])
@@ -72,6 +76,8 @@ def main():
     ms = start.elapsed_time(stop) / args.steps
     geo_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
     photo_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    photo_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    remap_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in remap_events]))
     dst_px = int(res.numel()) // 3
     src_px = n * bench.PAGE_SHAPE[0] * bench.PAGE_SHAPE[1]
     peak = bench.measured_peak()[0] if hasattr(bench, 'measured_peak') else 6552.3
@@ -80,7 +86,8 @@ def main():
                     f'batch {n}, inputs resident, configs from the policy generators',
         'pages_per_s': n / ms * 1e3, 'ms_per_step': ms,
         'geometric_ms': geo_ms, 'photometric_ms': photo_ms,
-        'fused_photo_GBps': 6.0 * dst_px / photo_ms / 1e6,
+        'remap_kernel_ms': remap_kernel_ms, 'photo_kernel_ms': photo_kernel_ms,
+        'fused_photo_GBps': 6.0 * dst_px / photo_kernel_ms / 1e6,
         'chain_algorithmic_GBps': 3.0 * (src_px + dst_px) / ms / 1e6,
         'hbm_peak_GBps': peak,
     }))

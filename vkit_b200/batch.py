@@ -368,6 +368,7 @@ class PhotometricBatch:
         sizes = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
         self.pixel_offsets = np.concatenate([[0], np.cumsum(sizes)])
         self.launches = 0
+        self.launch_events = None  # set to a list to collect (start, end) CUDA events per pass
 
     def _new_pass(self):
         rec = np.zeros(self.n, dtype=nv.PHOTO_PAGE_DTYPE)
@@ -380,9 +381,16 @@ class PhotometricBatch:
         rec['src'] = np.uint64(src.data_ptr()) + base
         rec['dst'] = np.uint64(dst.data_ptr()) + base
         rec_dev = dv.upload_structs(rec)
+        if self.launch_events is not None:
+            t = dv.torch()
+            ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            ev0.record()
         nv.check(nv.lib().vkb_photo_chain_batched(dv.ptr(rec_dev), rec.ctypes.data_as(ctypes.c_void_p),
                                                   self.n, self.channels, dv.stream_ptr()),
                  'vkb_photo_chain_batched')
+        if self.launch_events is not None:
+            ev1.record()
+            self.launch_events.append((ev0, ev1))
         self.launches += 1
         return rec_dev
 

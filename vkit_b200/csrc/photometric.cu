@@ -161,7 +161,17 @@ struct ColorOpList {
     int n;
 };
 
-__device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, int channels) {
+// The division tables are looked up with per-pixel indices: constant memory would serialise the
+// lanes of a warp, so every block works from a shared-memory copy.
+__device__ __forceinline__ void stage_hsv_tables(HsvTables& sm, int tid, int n_threads) {
+    const int* src = c_hsv.sdiv;
+    int* dst = sm.sdiv;
+    for (int i = tid; i < 512; i += n_threads) dst[i] = src[i];
+}
+static_assert(sizeof(HsvTables) == 512 * sizeof(int), "HsvTables: two 256-entry tables");
+
+__device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, int channels,
+                                               const HsvTables& tables) {
     switch (op.kind) {
         case VKB_OP_MEAN_SHIFT: {
             for (int c = 0; c < channels; ++c) {
@@ -175,7 +185,7 @@ __device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, 
         } break;
         case VKB_OP_HUE_SHIFT_RGB: {
             int h, s, v;
-            rgb2hsv_full(c_hsv, px[0], px[1], px[2], h, s, v);
+            rgb2hsv_full(tables, px[0], px[1], px[2], h, s, v);
             h = floor_mod_256(h + op.i0);
             hsv2rgb_full(h, s, v, px[0], px[1], px[2]);
         } break;
@@ -187,7 +197,7 @@ __device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, 
                 hls2rgb_full(h, l, s, px[0], px[1], px[2]);
             } else {
                 int h, s, v;
-                rgb2hsv_full(c_hsv, px[0], px[1], px[2], h, s, v);
+                rgb2hsv_full(tables, px[0], px[1], px[2], h, s, v);
                 v = clip_u8(v + op.i0);
                 hsv2rgb_full(h, s, v, px[0], px[1], px[2]);
             }
@@ -241,12 +251,15 @@ template <int C>
 __global__ void __launch_bounds__(256) color_ops_kernel(const uint8_t* __restrict__ src,
                                                         uint8_t* __restrict__ dst, long long n,
                                                         const ColorOpList list) {
+    __shared__ HsvTables tables;
+    stage_hsv_tables(tables, threadIdx.x, 256);
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int px[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < C; ++c) px[c] = src[i * C + c];
-    for (int k = 0; k < list.n; ++k) apply_color_op(list.ops[k], px, C);
+    for (int k = 0; k < list.n; ++k) apply_color_op(list.ops[k], px, C, tables);
 #pragma unroll
     for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
 }
@@ -519,27 +532,176 @@ __global__ void __launch_bounds__(256) streak_masks_kernel(uint8_t* image, int h
 // gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
 // them (distortion_policy/random_distortion.py:350-392), without the intermediate image.
 //
-// Block = 32 x 8 threads on a 32 x 32 output tile.  The tile plus halo is staged in shared
-// memory (interior tiles: aligned 32-bit loads of the row span, each row keeps its own byte
-// misalignment; border tiles: byte loads with BORDER_REFLECT_101), blurred horizontally into
-// saturated 16-bit rows, then vertically; the op list runs on the blurred pixel in registers.
+// Block = 256 threads on a 32 x 32 output tile; the interleaved channels are treated as a byte
+// stream (a horizontal tap is C bytes away).
+//   load   tile + halo -> shared memory, rows re-aligned to the tile's first byte (interior
+//          tiles: aligned 32-bit loads + funnel shift; border tiles: BORDER_REFLECT_101 bytes);
+//   horiz  a thread blurs 4 consecutive bytes of two vertically adjacent rows: per tap one
+//          funnel shift + two PRMT unpack the bytes into 16-bit lane pairs and one IMAD per pair
+//          accumulates both lanes at once (the taps sum to 256, so a lane never exceeds
+//          255 * 256 and cannot carry into its neighbour); results are re-paired vertically
+//          (row 2t, row 2t+1) per byte and stored as 32-bit words;
+//   vert   a thread owns one pixel of two adjacent output rows: per channel R+1 word loads and
+//          IDP.2A (16-bit pair x byte weights) per row, + 2^15, >> 16;
+//   ops    the op list runs on the blurred pixel in registers; bytes are stored.
 // ============================================================================================
+template <int C, int R>
+struct ChainGeom {
+    static constexpr int TH = 32 + 2 * R;                    // tile rows incl. halo (even)
+    static constexpr int TWB = (32 + 2 * R) * C;             // tile row bytes incl. halo
+    static constexpr int ROW_WORDS = (TWB + 3) / 4 + 1;      // + 1: the horizontal pass may read one word past
+    static constexpr int NB = 32 * C;                        // output bytes per tile row
+    static constexpr int TILE_BYTES = (TH * ROW_WORDS * 4 + 15) & ~15;  // V stays 16-byte aligned
+    static constexpr int V_BYTES = (TH / 2) * NB * 4;
+    static constexpr int SMEM = TILE_BYTES + V_BYTES;
+};
+
+template <int C, int R>
+__device__ __forceinline__ void hblur4(const uint32_t* __restrict__ w, const int* __restrict__ taps,
+                                       uint32_t& lo, uint32_t& hi) {
+    lo = 0;
+    hi = 0;
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) {
+        const int o = C * k, wi = o >> 2, sh = o & 3;
+        const uint32_t win = sh ? __funnelshift_r(w[wi], w[wi + 1], 8 * sh) : w[wi];
+        lo += (uint32_t)taps[k] * __byte_perm(win, 0u, 0x4140);
+        hi += (uint32_t)taps[k] * __byte_perm(win, 0u, 0x4342);
+    }
+}
+
+template <int C, int R>
+__device__ __forceinline__ void chain_tile(const vkb_photo_page& pg, unsigned char* smem,
+                                           const int* __restrict__ taps,
+                                           const uint32_t* __restrict__ wev,
+                                           const uint32_t* __restrict__ wod,
+                                           const HsvTables& tables) {
+    using G = ChainGeom<C, R>;
+    const int h = pg.h, w = pg.w;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const uint8_t* __restrict__ src = pg.src;
+    uint8_t* __restrict__ dst = pg.dst;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);                        // TH x ROW_WORDS
+    uint32_t* V = reinterpret_cast<uint32_t*>(smem + G::TILE_BYTES);           // TH/2 x NB
+
+    // ---- load ---------------------------------------------------------------------------
+    const bool interior = x0 - R >= 0 && y0 - R >= 0 && x0 + 32 + R <= w && y0 + 32 + R <= h;
+    if (interior) {
+        // Every word that is read holds at least one byte of the span, so the reads stay inside
+        // the plane's allocation (device allocations are sized in multiples of >= 16 bytes).
+        const uintptr_t base = reinterpret_cast<uintptr_t>(src) + ((size_t)(y0 - R) * w + (x0 - R)) * C;
+        const size_t pitch = (size_t)w * C;
+        for (int ty = warp; ty < G::TH; ty += 8) {
+            const uintptr_t a = base + ty * pitch;
+            const uint32_t* __restrict__ a0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            const int mis = (int)(a & 3);
+            const int last = (mis + G::TWB - 1) >> 2;  // last word with span bytes
+            for (int k = lane; k < G::ROW_WORDS - 1; k += 32) {
+                uint32_t v = __ldg(a0 + k);
+                if (mis) {
+                    const uint32_t nxt = k < last ? __ldg(a0 + k + 1) : 0u;
+                    v = __funnelshift_r(v, nxt, 8 * mis);
+                }
+                tile[ty * G::ROW_WORDS + k] = v;
+            }
+        }
+    } else {
+        uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+        constexpr int TW = 32 + 2 * R;
+        for (int i = tid; i < G::TH * TW; i += 256) {
+            const int ty = i / TW, tx = i - ty * TW;
+            const int sy = reflect101(y0 + ty - R, h), sx = reflect101(x0 + tx - R, w);
+            const uint8_t* p = src + ((long long)sy * w + sx) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) tb[ty * (G::ROW_WORDS * 4) + tx * C + c] = p[c];
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal: (row pair t, 4-byte group q) ------------------------------------------
+    constexpr int NQ = G::NB / 4;
+    constexpr int NW = 1 + (2 * R * C + 3) / 4;  // words a 4-byte group reads per row
+    for (int i = tid; i < (G::TH / 2) * NQ; i += 256) {
+        const int t = i / NQ, q = i - t * NQ;
+        uint32_t w0[NW + 1], w1[NW + 1];
+        const uint32_t* r0 = tile + (2 * t) * G::ROW_WORDS + q;
+        const uint32_t* r1 = r0 + G::ROW_WORDS;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            w0[j] = r0[j];
+            w1[j] = r1[j];
+        }
+        w0[NW] = 0;
+        w1[NW] = 0;
+        uint32_t lo0, hi0, lo1, hi1;
+        hblur4<C, R>(w0, taps, lo0, hi0);
+        hblur4<C, R>(w1, taps, lo1, hi1);
+        uint4 out;
+        out.x = __byte_perm(lo0, lo1, 0x5410);  // byte 0: (row 2t, row 2t+1)
+        out.y = __byte_perm(lo0, lo1, 0x7632);
+        out.z = __byte_perm(hi0, hi1, 0x5410);
+        out.w = __byte_perm(hi0, hi1, 0x7632);
+        *reinterpret_cast<uint4*>(V + t * G::NB + 4 * q) = out;
+    }
+    __syncthreads();
+
+    // ---- vertical + ops + store: (pixel x, output row pair) --------------------------------
+    const int n_ops = pg.n_ops;
+    const int x = x0 + lane;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int op_ = warp + 8 * it;  // output row pair 0..15
+        const int ya = y0 + 2 * op_;
+        int pa[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            uint32_t acc_a = 1u << 15, acc_b = 1u << 15;
+#pragma unroll
+            for (int m = 0; m <= R; ++m) {
+                const uint32_t v = V[(op_ + m) * G::NB + lane * C + c];
+                acc_a = __dp2a_lo(v, wev[m], acc_a);
+                acc_b = __dp2a_lo(v, wod[m], acc_b);
+            }
+            pa[c] = (int)(acc_a >> 16);
+            pb[c] = (int)(acc_b >> 16);
+        }
+        if (x < w && ya < h) {
+            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], pa, C, tables);
+            uint8_t* d = dst + ((long long)ya * w + x) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) d[c] = (uint8_t)pa[c];
+            if (ya + 1 < h) {
+                for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], pb, C, tables);
+                d += (long long)w * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = (uint8_t)pb[c];
+            }
+        }
+    }
+}
+
 template <int C>
-__global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* __restrict__ pages,
-                                                          int max_r) {
+__global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* __restrict__ pages) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int taps[17];
+    __shared__ uint32_t wev[9], wod[9];
+    __shared__ HsvTables tables;
     const vkb_photo_page& pg = pages[blockIdx.z];
     const int h = pg.h, w = pg.w;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     if (x0 >= w || y0 >= h) return;
-    const uint8_t* __restrict__ src = pg.src;
-    uint8_t* __restrict__ dst = pg.dst;
     const int r = pg.blur_radius;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const int n_ops = pg.n_ops;
-    const int x = x0 + threadIdx.x;
+    if (pg.n_ops > 0) stage_hsv_tables(tables, tid, 256);
+    if (r == 0) __syncthreads();
 
     if (r == 0) {
+        const uint8_t* __restrict__ src = pg.src;
+        uint8_t* __restrict__ dst = pg.dst;
+        const int n_ops = pg.n_ops;
+        const int x = x0 + threadIdx.x;
         if (x >= w) return;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -549,93 +711,46 @@ __global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* 
             int px[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < C; ++c) px[c] = src[i * C + c];
-            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C);
+            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C, tables);
 #pragma unroll
             for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
         }
         return;
     }
-
-    // shared layout (sized by the host for the largest radius of the batch)
-    const int TWm = 32 + 2 * max_r;
-    const int row_stride = ((TWm * C + 3) & ~3) + 4;  // bytes; room for the row's misalignment
-    uint8_t* tile = smem;                               // TH rows of row_stride bytes
-    unsigned short* rows =
-        reinterpret_cast<unsigned short*>(smem + (size_t)TWm * row_stride);  // TH x 32 x C
-    __shared__ int taps[2 * 8 + 1];
+    // taps, and the byte-weight pairs of the vertical pass: output row 2o reads row pairs
+    // m = 0..R with weights (w[2m], w[2m+1]); output row 2o+1 with (w[2m-1], w[2m]).
     if (tid <= 2 * r) taps[tid] = pg.blur_taps[tid];
+    if (tid >= 32 && tid < 32 + 9) {
+        const int m = tid - 32;
+        auto tap = [&](int k) { return (k >= 0 && k <= 2 * r) ? (uint32_t)pg.blur_taps[k] : 0u; };
+        wev[m] = tap(2 * m) | (tap(2 * m + 1) << 8);
+        wod[m] = tap(2 * m - 1) | (tap(2 * m) << 8);
+    }
+    __syncthreads();
+    switch (r) {
+        case 1: chain_tile<C, 1>(pg, smem, taps, wev, wod, tables); break;
+        case 2: chain_tile<C, 2>(pg, smem, taps, wev, wod, tables); break;
+        case 3: chain_tile<C, 3>(pg, smem, taps, wev, wod, tables); break;
+        case 4: chain_tile<C, 4>(pg, smem, taps, wev, wod, tables); break;
+        case 5: chain_tile<C, 5>(pg, smem, taps, wev, wod, tables); break;
+        case 6: chain_tile<C, 6>(pg, smem, taps, wev, wod, tables); break;
+        case 7: chain_tile<C, 7>(pg, smem, taps, wev, wod, tables); break;
+        default: chain_tile<C, 8>(pg, smem, taps, wev, wod, tables); break;
+    }
+}
 
-    const int TW = 32 + 2 * r, TH = 32 + 2 * r;
-    const bool interior = x0 - r >= 0 && y0 - r >= 0 && x0 + 32 + r <= w && y0 + 32 + r <= h;
-    if (interior) {
-        // aligned words of every row span; the last word of the last row must stay inside the
-        // plane, which holds whenever another row follows (always true unless y0+32+r == h and
-        // the span ends in the plane's final word: reading it is still in bounds).
-        const int words_max = (TW * C + 3 + 3) >> 2;
-        for (int i = tid; i < TH * words_max; i += 256) {
-            const int ty = i / words_max, k = i - ty * words_max;
-            const uintptr_t a = reinterpret_cast<uintptr_t>(src)
-                                + ((size_t)(y0 - r + ty) * w + (x0 - r)) * C;
-            const uintptr_t a0 = a & ~(uintptr_t)3;
-            const int span_words = (int)(((a - a0) + TW * C + 3) >> 2);
-            if (k < span_words) {
-                const uintptr_t wa = a0 + 4u * k;
-                // the final word of the final row of the plane may poke past the allocation
-                uint32_t v;
-                const uintptr_t end = reinterpret_cast<uintptr_t>(src) + (size_t)h * w * C;
-                if (wa + 4 <= end) {
-                    v = __ldg(reinterpret_cast<const uint32_t*>(wa));
-                } else {
-                    v = 0;
-                    for (int b = 0; b < 4; ++b)
-                        if (wa + b < end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(wa + b)) << (8 * b);
-                }
-                *reinterpret_cast<uint32_t*>(tile + ty * row_stride + 4 * k) = v;
-            }
-        }
-    } else {
-        for (int i = tid; i < TH * TW; i += 256) {
-            const int ty = i / TW, tx = i - ty * TW;
-            const int sy = reflect101(y0 + ty - r, h), sx = reflect101(x0 + tx - r, w);
-            const uint8_t* p = src + ((long long)sy * w + sx) * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) tile[ty * row_stride + tx * C + c] = p[c];
-        }
-    }
-    __syncthreads();
-    // horizontal pass
-    for (int i = tid; i < TH * 32; i += 256) {
-        const int ty = i >> 5, tx = i & 31;
-        int mis = 0;
-        if (interior)
-            mis = (int)((reinterpret_cast<uintptr_t>(src) + ((size_t)(y0 - r + ty) * w + (x0 - r)) * C) & 3);
-        const uint8_t* __restrict__ p = tile + ty * row_stride + mis + tx * C;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            int acc = 0;
-            for (int k = 0; k <= 2 * r; ++k) acc += (int)p[k * C + c] * taps[k];
-            rows[i * C + c] = (unsigned short)min(acc, 65535);
-        }
-    }
-    __syncthreads();
-    if (x >= w) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ly = threadIdx.y + 8 * j;
-        const int y = y0 + ly;
-        if (y >= h) break;
-        int px[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            int acc = 0;
-            for (int k = 0; k <= 2 * r; ++k)
-                acc += (int)rows[((ly + k) * 32 + threadIdx.x) * C + c] * taps[k];
-            px[c] = min((acc + (1 << 15)) >> 16, 255);
-        }
-        for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C);
-        const long long i = (long long)y * w + x;
-#pragma unroll
-        for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
+template <int C>
+static size_t chain_smem_bytes(int r) {
+    switch (r) {
+        case 0: return 0;
+        case 1: return ChainGeom<C, 1>::SMEM;
+        case 2: return ChainGeom<C, 2>::SMEM;
+        case 3: return ChainGeom<C, 3>::SMEM;
+        case 4: return ChainGeom<C, 4>::SMEM;
+        case 5: return ChainGeom<C, 5>::SMEM;
+        case 6: return ChainGeom<C, 6>::SMEM;
+        case 7: return ChainGeom<C, 7>::SMEM;
+        default: return ChainGeom<C, 8>::SMEM;
     }
 }
 
@@ -866,6 +981,9 @@ extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_ph
         VKB_REQUIRE(p.blur_radius >= 0 && p.blur_radius <= 8, "blur radius must be 0..8");
         VKB_REQUIRE(p.n_ops >= 0 && p.n_ops <= VKB_MAX_COLOR_OPS, "too many ops");
         VKB_REQUIRE(p.blur_radius == 0 || p.src != p.dst, "blur cannot run in place");
+        for (int k = 0; k <= 2 * p.blur_radius && p.blur_radius > 0; ++k)
+            VKB_REQUIRE(p.blur_taps[k] >= 0 && p.blur_taps[k] <= 255,
+                        "blur taps must be 0..255 (a 256 centre tap is the identity: use radius 0)");
         max_h = p.h > max_h ? p.h : max_h;
         max_w = p.w > max_w ? p.w : max_w;
         max_r = p.blur_radius > max_r ? p.blur_radius : max_r;
@@ -873,14 +991,14 @@ extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_ph
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(st);
     if (rc) return rc;
-    const int TW = 32 + 2 * max_r;
-    const int row_stride = ((TW * channels + 3) & ~3) + 4;
-    const size_t smem = max_r ? (size_t)TW * row_stride + (size_t)TW * 32 * channels * 2 : 0;
     dim3 grid((max_w + 31) / 32, (max_h + 31) / 32, n_pages);
     VKB_REQUIRE(grid.y <= 65535, "page too tall");
-    if (channels == 1) photo_chain_kernel<1><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
-    else if (channels == 3) photo_chain_kernel<3><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
-    else photo_chain_kernel<4><<<grid, dim3(32, 8), smem, st>>>(pages, max_r);
+    if (channels == 1)
+        photo_chain_kernel<1><<<grid, dim3(32, 8), chain_smem_bytes<1>(max_r), st>>>(pages);
+    else if (channels == 3)
+        photo_chain_kernel<3><<<grid, dim3(32, 8), chain_smem_bytes<3>(max_r), st>>>(pages);
+    else
+        photo_chain_kernel<4><<<grid, dim3(32, 8), chain_smem_bytes<4>(max_r), st>>>(pages);
     return check_launch("photo_chain_kernel");
 }
 

@@ -36,21 +36,28 @@ VKB_HD void rgb2hsv_full(const HsvTables& t, int r, int g, int b, int& h, int& s
 }
 
 VKB_HD int round_u8(float x) {
+#if defined(__CUDA_ARCH__)
+    return min(max(__float2int_rn(x), 0), 255);  // F2I rounds half to even and saturates
+#else
     const float r = rintf(x);
     return r < 0.f ? 0 : (r > 255.f ? 255 : (int)r);
+#endif
 }
 
 // sector tables of cv::HSV2RGB_native / HLS2RGB_native: which of tab[0..3] goes to b, g, r.
+VKB_HD float tab_pick(const float* tab, int idx) {
+    const float lo = (idx & 1) ? tab[1] : tab[0];
+    const float hi = (idx & 1) ? tab[3] : tab[2];
+    return (idx & 2) ? hi : lo;
+}
+
 VKB_HD void sector_pick(const float* tab, int sector, float& r, float& g, float& b) {
-    // {b, g, r} = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}[sector]
-    switch (sector) {
-        case 0: b = tab[1]; g = tab[3]; r = tab[0]; break;
-        case 1: b = tab[1]; g = tab[0]; r = tab[2]; break;
-        case 2: b = tab[3]; g = tab[0]; r = tab[1]; break;
-        case 3: b = tab[0]; g = tab[2]; r = tab[1]; break;
-        case 4: b = tab[0]; g = tab[1]; r = tab[3]; break;
-        default: b = tab[2]; g = tab[1]; r = tab[0]; break;
-    }
+    // {b, g, r} = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}[sector], two bits per entry;
+    // selects instead of a switch: the sectors of neighbouring pixels differ (no divergence).
+    const int sh = 2 * sector;
+    r = tab_pick(tab, (0x358 >> sh) & 3);
+    g = tab_pick(tab, (0x583 >> sh) & 3);
+    b = tab_pick(tab, (0x835 >> sh) & 3);
 }
 
 // COLOR_HSV2RGB_FULL, uint8 through the float32 path, hue scale 6/255.
@@ -58,10 +65,9 @@ VKB_HD void hsv2rgb_full(int H, int S, int V, int& r, int& g, int& b) {
     const float h = VKB_FMUL((float)H, (float)(6.0 / 255.0));
     const float s = VKB_FMUL((float)S, (float)(1.0 / 255.0));
     const float v = VKB_FMUL((float)V, (float)(1.0 / 255.0));
-    int sector = (int)floorf(h);
+    int sector = (int)floorf(h);  // 0..6 for H in 0..255
     const float frac = VKB_FSUB(h, (float)sector);
-    sector %= 6;
-    if (sector < 0) sector += 6;
+    sector = sector >= 6 ? sector - 6 : sector;
     float tab[4];
     tab[0] = v;
     tab[1] = VKB_FMUL(v, VKB_FSUB(1.f, s));
@@ -112,10 +118,9 @@ VKB_HD void hls2rgb_full(int H, int L, int S, int& r, int& g, int& b) {
         const float p2 = l <= 0.5f ? VKB_FMUL(l, VKB_FADD(1.f, s))
                                    : VKB_FSUB(VKB_FADD(l, s), VKB_FMUL(l, s));
         const float p1 = VKB_FSUB(VKB_FMUL(2.f, l), p2);
-        int sector = (int)floorf(h);
+        int sector = (int)floorf(h);  // 0..6 for H in 0..255
         const float frac = VKB_FSUB(h, (float)sector);
-        sector %= 6;
-        if (sector < 0) sector += 6;
+        sector = sector >= 6 ? sector - 6 : sector;
         float tab[4];
         tab[0] = p2;
         tab[1] = p1;
@@ -139,7 +144,7 @@ VKB_HD float blend_f32(float dst, float value, float a) {
     return VKB_FADD(VKB_FMUL(wm, dst), VKB_FMUL(a, value));
 }
 
-VKB_HD int floor_mod_256(int v) { return ((v % 256) + 256) % 256; }
+VKB_HD int floor_mod_256(int v) { return v & 255; }  // two's complement: floor modulo
 VKB_HD int clip_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 }  // namespace vkb
