@@ -109,3 +109,55 @@ def product_config(case):
         cfg['src_handle_points'] = PointTuple.from_xy_pairs(cfg['src_handle_points'])
         cfg['dst_handle_points'] = PointTuple.from_xy_pairs(cfg['dst_handle_points'])
     return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# Chained fixtures (tests/golden/make_golden_chain.py)
+# ---------------------------------------------------------------------------------------------
+_CHAIN = None
+
+
+def chain_golden():
+    global _CHAIN
+    if _CHAIN is None:
+        with open(os.path.join(GOLDEN_DIR, 'chain_cases.json')) as fin:
+            meta = json.load(fin)
+        _CHAIN = (meta['cases'], np.load(os.path.join(GOLDEN_DIR, 'chain_arrays.npz')))
+    return _CHAIN
+
+
+def chain_cases(kind):
+    return [c for c in chain_golden()[0] if c['kind'] == kind]
+
+
+def chain_array(case, key):
+    arrays = chain_golden()[1]
+    name = f"{case['id']}/{key}"
+    return arrays[name] if name in arrays.files else None
+
+
+def plain_config(obj):
+    """Product config (attrs) -> the JSON-able structure make_golden.plain produces."""
+    import attrs
+    if hasattr(obj, 'smooth_x') and hasattr(obj, 'smooth_y'):
+        return [obj.smooth_x, obj.smooth_y]
+    if attrs.has(type(obj)):
+        out = {}
+        for field in attrs.fields(type(obj)):
+            if field.name == '_rng_state':
+                continue
+            out[field.name.lstrip('_')] = plain_config(getattr(obj, field.name))
+        return out
+    if isinstance(obj, (list, tuple)):
+        return [plain_config(x) for x in obj]
+    if hasattr(obj, 'value') and type(obj).__module__.startswith('vkit_b200'):
+        return obj.value
+    if isinstance(obj, np.integer):
+        return int(obj)
+    if isinstance(obj, np.floating):
+        return float(obj)
+    return obj
+
+
+def product_config_for(op, config):
+    return product_config({'op': op, 'config': config})

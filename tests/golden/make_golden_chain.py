@@ -1,0 +1,115 @@
+"""Golden fixtures for the CHAINED configurations, from the LIVE reference (vkit-x/vkit @ 98ada2d
+under /root/reference, cv2 4.13.0.92, numpy 2.3.5).  Run in the build container only:
+
+    PYTHONPATH=/root/repo python tests/golden/make_golden_chain.py
+
+  random_distortion   BASELINE config 4's distortion stage: random_distortion_factory with the
+                      pipeline's flags (page_distortion.py:53-64 minus the ops that are "next"
+                      rows), image + mask + points + polygons, one case per rng seed: the chosen
+                      policy names / levels / configs, the result shape, hashes and arrays.
+  fixed_chain         BASELINE config 5's 10-op chain at several page sizes: per-stage hashes,
+                      final arrays for the smallest size.
+Inputs are regenerated from the seed by tests/common.py, never stored.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+import make_golden as mg  # noqa: E402  (loads the reference through oracle/refshim)
+
+from vkit.element import Image, Mask, Point, PointList, Polygon  # noqa: E402
+from vkit.mechanism import distortion  # noqa: E402
+from vkit.mechanism.distortion_policy.random_distortion import (  # noqa: E402
+    RandomDistortionDebug, random_distortion_factory)
+
+from common import make_inputs, make_points, make_polygons  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NOT_YET = ['defocus_blur', 'zoom_in_blur', 'motion_blur', 'glass_blur', 'jpeg_quality',
+           'pixelation', 'fog', 'ellipse_streak']
+CHAIN_OPS = ['mean_shift', 'color_shift', 'brightness_shift', 'std_shift', 'gaussian_blur',
+             'gaussion_noise', 'line_streak', 'camera_cubic_curve', 'similarity_mls', 'rotate']
+
+CASES, ARRAYS = [], {}
+
+
+def xy(points):
+    return np.asarray([(p.smooth_x, p.smooth_y) for p in points], dtype=np.float64)
+
+
+def random_distortion_cases():
+    shape = (160, 208)
+    rd = random_distortion_factory.create({'disabled_policy_names': NOT_YET,
+                                           'force_post_rotate': True})
+    for seed in range(24):
+        image, mask, _ = make_inputs(1000 + seed, shape)
+        pts = PointList(Point.create(y=y, x=x) for x, y in make_points(1000 + seed, shape, 16))
+        polys = [Polygon.from_xy_pairs(p) for p in make_polygons(1000 + seed, shape, 4)]
+        debug = RandomDistortionDebug()
+        rng = np.random.default_rng(seed)
+        r = rd.distort(rng, image=Image(mat=image), mask=Mask(mat=mask), points=pts,
+                       polygons=polys, debug=debug)
+        cid = f'rd{seed:02d}'
+        case = {
+            'id': cid, 'kind': 'random_distortion', 'shape': list(shape), 'seed': 1000 + seed,
+            'rng_seed': seed, 'names': list(debug.distortion_names),
+            'levels': [int(v) for v in debug.distortion_levels],
+            'configs': [mg.plain(c) for c in debug.distortion_configs],
+            'result_shape': list(r.image.shape),
+            'stage_sha': [mg.sha(im.mat) for im in debug.distortion_images],
+            'sha': {'image': mg.sha(r.image.mat), 'mask': mg.sha(r.mask.mat)},
+            'rng_after': float(rng.random()),
+        }
+        ARRAYS[f'{cid}/image'] = r.image.mat
+        ARRAYS[f'{cid}/mask'] = r.mask.mat
+        ARRAYS[f'{cid}/points'] = xy(r.points)
+        ARRAYS[f'{cid}/polygons'] = np.asarray([xy(p.points) for p in r.polygons])
+        CASES.append(case)
+
+
+def fixed_chain_cases():
+    for size, keep in ((256, True), (512, False), (1024, False)):
+        shape = (size, size)
+        seed = 5000 + size
+        image, _, _ = make_inputs(seed, shape)
+        rng = np.random.default_rng(seed)
+        cur = Image(mat=image)
+        stage_sha, configs, shapes = [], [], []
+        for name in CHAIN_OPS:
+            config = mg.policy_config(name, 6, cur.shape, int(rng.integers(0, 2**31)))
+            op_rng = np.random.default_rng(int(rng.integers(0, 2**31)))
+            r = getattr(distortion, name).distort(config, image=cur, rng=op_rng, get_config=True)
+            cur = r.image
+            configs.append(mg.plain(r.config))
+            stage_sha.append(mg.sha(cur.mat))
+            shapes.append(list(cur.shape))
+        cid = f'fc{size}'
+        case = {'id': cid, 'kind': 'fixed_chain', 'shape': list(shape), 'seed': seed,
+                'ops': CHAIN_OPS, 'configs': configs, 'stage_sha': stage_sha,
+                'stage_shapes': shapes, 'sha': {'image': mg.sha(cur.mat)}}
+        if keep:
+            ARRAYS[f'{cid}/image'] = cur.mat
+        CASES.append(case)
+
+
+def main():
+    random_distortion_cases()
+    fixed_chain_cases()
+    with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
+        json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
+                   'numpy': np.__version__, 'cases': CASES}, fout, indent=1)
+    np.savez_compressed(os.path.join(HERE, 'chain_arrays.npz'), **ARRAYS)
+    print(len(CASES), 'cases;', sum(v.nbytes for v in ARRAYS.values()) / 1e6, 'MB raw arrays')
+    for c in CASES:
+        print(c['id'], c.get('names', c.get('ops')), c['result_shape'] if 'result_shape' in c else c['stage_shapes'][-1])
+
+
+if __name__ == '__main__':
+    main()

@@ -553,3 +553,104 @@ def test_photometric_batch_ragged_edges(vk):
             a = int(photo.pixel_offsets[i]) * channels
             got = result[a:a + page.size].reshape(page.shape)
             assert np.array_equal(got, ref), (channels, shapes[i], _diff_report(got, ref))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4 / 5: RandomDistortion and the fixed 10-op chain vs the live reference
+# ---------------------------------------------------------------------------------------------
+from common import chain_array, chain_cases, plain_config, product_config_for  # noqa: E402
+
+NOT_YET = ['defocus_blur', 'zoom_in_blur', 'motion_blur', 'glass_blur', 'jpeg_quality',
+           'pixelation', 'fog', 'ellipse_streak']
+# ops whose result is not bit-exact by construction
+INEXACT = {'color_shift', 'brightness_shift', 'std_shift', 'skew_hori', 'skew_vert',
+           'similarity_mls'}
+
+
+def _json_round(obj):
+    import json
+    return json.loads(json.dumps(obj))
+
+
+@pytest.mark.parametrize('case', chain_cases('random_distortion'), ids=lambda c: c['id'])
+def test_random_distortion_vs_reference(vk, case):
+    """Same rng seed -> the same policies, levels and configs as the reference (the generators
+    consume the NumPy stream identically), the same result shape, and the same pixels: bit-exact
+    when every chosen op is exact, within the documented colour / tie tolerances otherwise."""
+    element, _ = vk
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    from vkit_b200.mechanism.distortion_policy import random_distortion_factory
+    from vkit_b200.mechanism.distortion_policy.random_distortion import RandomDistortionDebug
+    shape = tuple(case['shape'])
+    rd = random_distortion_factory.create({'disabled_policy_names': NOT_YET,
+                                           'force_post_rotate': True})
+    image, mask, _ = make_inputs(case['seed'], shape)
+    pts = element.PointList(element.Point.create(y=y, x=x)
+                            for x, y in make_points(case['seed'], shape, 16))
+    polys = [element.Polygon.from_xy_pairs(p) for p in make_polygons(case['seed'], shape, 4)]
+    debug = RandomDistortionDebug()
+    rng = np.random.default_rng(case['rng_seed'])
+    noise_mod.use_host_field(True)
+    try:
+        r = rd.distort(rng, image=element.Image(mat=image), mask=element.Mask(mat=mask),
+                       points=pts, polygons=polys, debug=debug)
+    finally:
+        noise_mod.use_host_field(False)
+    assert list(debug.distortion_names) == case['names']
+    assert [int(v) for v in debug.distortion_levels] == case['levels']
+    assert _json_round([plain_config(c) for c in debug.distortion_configs]) == case['configs']
+    assert float(rng.random()) == case['rng_after']  # the stream was consumed identically
+    assert list(r.image.shape) == case['result_shape']
+    got, ref = r.image.mat, chain_array(case, 'image')
+    got_mask, ref_mask = r.mask.mat, chain_array(case, 'mask')
+    report = (case['id'], case['names'], _diff_report(got, ref), _diff_report(got_mask, ref_mask))
+    if not (set(case['names']) & INEXACT):
+        assert sha(got) == case['sha']['image'], report
+        assert sha(got_mask) == case['sha']['mask'], report
+    else:
+        diff = np.abs(got.astype(int) - ref.astype(int))
+        # an equalisation after a +-1 colour op stretches the difference on the few pixels whose
+        # histogram bin moved: bound the count there, not the magnitude
+        stretched = {'histogram_equalization', 'boundary_equalization'} & set(case['names'])
+        assert (diff > 0).mean() <= 0.03 and (stretched or diff.max() <= 16), report
+        if not ({'skew_hori', 'skew_vert', 'similarity_mls'} & set(case['names'])):
+            assert sha(got_mask) == case['sha']['mask'], report
+        else:
+            assert (got_mask != ref_mask).mean() <= 0.01, report
+    pts_ref = chain_array(case, 'points')
+    pts_got = np.asarray([(p.smooth_x, p.smooth_y) for p in r.points])
+    assert np.abs(pts_got - pts_ref).max() <= 1e-3, report
+    poly_ref = chain_array(case, 'polygons')
+    poly_got = np.asarray([[(p.smooth_x, p.smooth_y) for p in poly.points] for poly in r.polygons])
+    assert np.abs(poly_got - poly_ref).max() <= 1e-3, report
+
+
+@pytest.mark.parametrize('case', chain_cases('fixed_chain'), ids=lambda c: c['id'])
+def test_fixed_ten_op_chain_vs_reference(vk, case):
+    """BASELINE config 5's chain at 256 / 512 / 1024 px: every stage's result shape equals the
+    reference's, stages are bit-exact up to the first colour-space op, and the final image stays
+    within the accumulated colour tolerance (arrays kept for 256 px)."""
+    element, distortion = vk
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    shape = tuple(case['shape'])
+    image, _, _ = make_inputs(case['seed'], shape)
+    rng = np.random.default_rng(case['seed'])
+    cur = element.Image(mat=image)
+    exact_so_far = True
+    noise_mod.use_host_field(True)
+    try:
+        for k, name in enumerate(case['ops']):
+            rng.integers(0, 2**31)  # the generator's config seed (configs are stored)
+            op_rng = np.random.default_rng(int(rng.integers(0, 2**31)))
+            config = product_config_for(name, case['configs'][k])
+            cur = getattr(distortion, name).distort(config, image=cur, rng=op_rng).image
+            assert list(cur.shape) == case['stage_shapes'][k], (name, cur.shape)
+            exact_so_far = exact_so_far and name not in INEXACT
+            if exact_so_far:
+                assert sha(cur.mat) == case['stage_sha'][k], name
+    finally:
+        noise_mod.use_host_field(False)
+    ref = chain_array(case, 'image')
+    if ref is not None:
+        diff = np.abs(cur.mat.astype(int) - ref.astype(int))
+        assert (diff > 0).mean() <= 0.05 and diff.max() <= 16, _diff_report(cur.mat, ref)
