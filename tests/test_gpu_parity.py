@@ -654,3 +654,47 @@ def test_fixed_ten_op_chain_vs_reference(vk, case):
     if ref is not None:
         diff = np.abs(cur.mat.astype(int) - ref.astype(int))
         assert (diff > 0).mean() <= 0.05 and diff.max() <= 16, _diff_report(cur.mat, ref)
+
+
+def test_full_size_batch_properties(vk):
+    """BASELINE config 2 at its full size (256 pages of 1024x1024 RGB, the bench's configs):
+    size-independent properties instead of an oracle run --
+      * a page's result does not depend on the batch it travels in: pages of the 256-page launch
+        equal the same page distorted alone through Distortion.distort (itself pinned to the
+        reference by the 1024^2 golden cases);
+      * theta = 0 camera_plane_only is the identity;
+      * every output pixel is either a bilinear mix of source values (bounded by the source
+        range) and uncovered pixels carry src[0, 0]."""
+    import torch
+    import bench
+    from vkit_b200.batch import GeometricBatch
+    element, distortion = vk
+    n = 256
+    names, configs = bench.sample_page_configs(0, n, n)
+    # page 3 becomes the identity: rotation 0 on a flat plane
+    import attrs
+    ident = attrs.evolve(configs[0], camera_model_config=attrs.evolve(
+        configs[0].camera_model_config, rotation_theta=0.0))
+    names[3], configs[3] = 'camera_plane_only', ident
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    pages = torch.randint(0, 256, (n, 1024, 1024, 3), dtype=torch.uint8, device='cuda',
+                          generator=gen)
+    pages[7] = torch.randint(40, 200, (1024, 1024, 3), dtype=torch.uint8, device='cuda',
+                             generator=gen)
+    engine = GeometricBatch(names, configs, (1024, 1024))
+    out = engine.run(pages)
+    assert len(out.shapes) == n
+    assert out.shapes[3] == (1024, 1024)
+    assert torch.equal(out.image(3), pages[3])
+    for i in (0, 37, 101, 255):
+        single = getattr(distortion, names[i]).distort(
+            configs[i], image=element.Image(mat=pages[i])).image
+        assert tuple(single.shape) == out.shapes[i]
+        assert torch.equal(single.dev, out.image(i)), (i, names[i])
+    img7 = out.image(7)
+    corner = pages[7, 0, 0]
+    inside = ((img7 >= 40) & (img7 < 200)).all(dim=-1)
+    is_corner = (img7 == corner).all(dim=-1)
+    is_border_mix = (img7 < 200).all(dim=-1)  # BORDER_CONSTANT 0 can only darken
+    assert bool((inside | is_corner | is_border_mix).all())
+    assert float(inside.float().mean()) > 0.5

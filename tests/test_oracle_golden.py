@@ -191,3 +191,62 @@ def test_blend(case):
     elif kind == 'inactive_fill':
         port.fill_np_array(out, golden_array(case, 'bottom'), np_mask=~(mask > 0))
     assert sha(out) == case['sha']['out_image']
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5's fixed 10-op chain (tests/golden/make_golden_chain.py): the oracle, stage by
+# stage, against the live reference's per-stage hashes
+# ---------------------------------------------------------------------------------------------
+from common import chain_array, chain_cases  # noqa: E402
+
+
+@pytest.mark.skipif(not _cv2_available(), reason='the cv2-backed oracle needs opencv')
+@pytest.mark.parametrize('case', [c for c in chain_cases('fixed_chain') if c['shape'][0] <= 512],
+                         ids=lambda c: c['id'])
+def test_fixed_chain_oracle_cv2_backend(case):
+    """cv2-backed oracle (the arithmetic the CPU baseline times): every stage of the chain is
+    bit-identical to the reference."""
+    port.use_cv2(True)
+    try:
+        shape = tuple(case['shape'])
+        image, _, _ = make_inputs(case['seed'], shape)
+        rng = np.random.default_rng(case['seed'])
+        cur = image
+        for k, name in enumerate(case['ops']):
+            rng.integers(0, 2**31)
+            op_rng = np.random.default_rng(int(rng.integers(0, 2**31)))
+            cfg = case['configs'][k]
+            if name in ('camera_cubic_curve', 'similarity_mls'):
+                cur = port.grid_distort(name, cfg, cur.shape[:2], image=cur)['image']
+            elif name == 'rotate':
+                trans_mat, dsize = port.affine_state(name, cfg, cur.shape[:2])
+                cur = port.affine_apply(cur, trans_mat, dsize)
+            else:
+                h, w = cur.shape[:2]
+                fake = {'seed': 0, 'shape': [h, w], 'config': cfg, 'op': name, 'mode': None,
+                        'rng_seed': None}
+                cur = _oracle_photometric_on(cur, fake, op_rng)
+            assert list(cur.shape[:2]) == case['stage_shapes'][k], name
+            assert sha(cur) == case['stage_sha'][k], (case['id'], k, name)
+    finally:
+        port.use_cv2(False)
+
+
+def _oracle_photometric_on(image, case, rng):
+    cfg, name = case['config'], case['op']
+    if name == 'mean_shift':
+        return port.mean_shift(image, cfg['delta'], cfg['threshold'], cfg['channels'],
+                               cfg['oob_behavior'] == 'cycle')
+    if name == 'color_shift':
+        return port.color_shift(image, cfg['delta'])
+    if name == 'brightness_shift':
+        return port.brightness_shift(image, cfg['delta'], cfg['intermediate_image_mode'] == 'hsv')
+    if name == 'std_shift':
+        return port.std_shift(image, cfg['scale'], cfg['channels'])
+    if name == 'gaussian_blur':
+        return port.gaussian_blur(image, cfg['sigma'])
+    if name == 'gaussion_noise':
+        return port.gaussion_noise(image, cfg['std'], rng)
+    if name == 'line_streak':
+        return port.line_streak(image, **cfg)
+    raise KeyError(name)
