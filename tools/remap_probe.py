@@ -38,19 +38,17 @@ def launch():
 
 
 px = float(offsets[-1])
-for dbg in [int(v) for v in (sys.argv[2].split(',') if len(sys.argv) > 2 else '0,1,2,4,8,3,12,14,15'.split(','))]:
-    os.environ['VKB_REMAP_DEBUG'] = str(dbg)
-    for _ in range(3):
-        launch()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(7):
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); launch(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    t = min(ts)
-    print(f'dbg={dbg:2d} (1 nostore 2 notaps 4 noowner 8 nocoords): {t*1e3/n:7.2f} us/page, '
-          f'{3 * (n * 1024 * 1024 + px) / t / 1e6:7.1f} GB/s algorithmic  (median {sorted(ts)[3]*1e3/n:.2f} us/page)')
+for _ in range(3):
+    launch()
+torch.cuda.synchronize()
+ts = []
+for _ in range(9):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); launch(); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+t = min(ts)
+print(f'{os.environ.get("VKB_LIB", "in-tree")}: remap {t*1e3/n:7.2f} us/page, '
+      f'{3 * (n * 1024 * 1024 + px) / t / 1e6:7.1f} GB/s algorithmic  (median {sorted(ts)[4]*1e3/n:.2f} us/page)')
 # the plan itself
 for _ in range(2):
     eng.plan_batch()

@@ -11,7 +11,8 @@ from ctypes import POINTER, c_double, c_float, c_int32, c_uint8, c_uint16, c_uin
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libvkit_b200.so')
+# VKB_LIB: alternative build of the same ABI (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get('VKB_LIB') or os.path.join(_HERE, 'csrc', 'libvkit_b200.so')
 
 CELL_MASK_WORDS = 32
 TILE = 32

@@ -476,8 +476,9 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
 struct __align__(16) TileSlot {
     CellLocal loc;
     int x0, y0, nr, cellf;  // bbox origin, rows - 1, cell | (over mask budget ? 1 << 31 : 0)
+    int xm, ym;             // 32 * (src corner of the cell) - kRoundMagicBits: base of the fast path
     int info;               // slot | cell column << 6 | cell row << 16
-    int pad[3];
+    int pad;
 };
 static_assert(sizeof(TileSlot) == VKB_TILE_SLOT_BYTES, "TileSlot layout is part of the ABI");
 
@@ -627,8 +628,10 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         rec.y0 = b.y;
         rec.nr = b.w - b.y;
         rec.cellf = cell | ((b.z & 0x40000000) ? (int)0x80000000 : 0);
+        rec.xm = c * gs * 32 - kRoundMagicBits;
+        rec.ym = r * gs * 32 - kRoundMagicBits;
         rec.info = rank | (c << 6) | (r << 16);
-        rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+        rec.pad = 0;
         int4* __restrict__ dst = reinterpret_cast<int4*>(slots + ((size_t)page * s_cap + off + rank));
         const int4* src = reinterpret_cast<const int4*>(&rec);
         dst[0] = src[0];
@@ -660,6 +663,9 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
 // ============================================================================================
 #ifndef VKB_REMAP_ROWS
 #define VKB_REMAP_ROWS 4  // dst rows per thread of the remap kernel (4 or 8)
+#endif
+#ifndef VKB_REMAP_BLOCKS
+#define VKB_REMAP_BLOCKS ((VKB_REMAP_ROWS == 4) ? 4 : 8)  // resident blocks per SM (register cap)
 #endif
 
 struct __align__(16) RemapShared {
@@ -731,30 +737,35 @@ struct TapWeights {
     int wx0, wx1, wy0, wy1;
 };
 
-__device__ __forceinline__ TapWeights tap_weights(int X, int Y, int h, int w) {
-    // sizes are below 32768 (checked by the caller), so cv's saturate_cast<short> of the
-    // integer coordinates cannot turn an outside tap into an inside one
-    const int x0 = X >> kInterBits, y0 = Y >> kInterBits;
-    const int fx = X & (kInterTab - 1), fy = Y & (kInterTab - 1);
+__device__ __forceinline__ TapWeights tap_weights_plain(int X, int Y) {
     TapWeights t;
-    t.xs = x0;
-    t.ys = y0;
-    t.wx0 = kInterTab - fx;
-    t.wx1 = fx;
-    t.wy0 = kInterTab - fy;
-    t.wy1 = fy;
-    if ((unsigned)x0 > (unsigned)(w - 2) || (unsigned)y0 > (unsigned)(h - 2)) {
-        // the footprint touches the border (rare)
-        t.xs = min(max(x0, 0), w - 2);
-        t.ys = min(max(y0, 0), h - 2);
-        const int dx = x0 - t.xs, dy = y0 - t.ys;
-        t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
-        t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
-        t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
-        t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
-    }
+    t.xs = X >> kInterBits;
+    t.ys = Y >> kInterBits;
+    t.wx1 = X & (kInterTab - 1);
+    t.wy1 = Y & (kInterTab - 1);
+    t.wx0 = kInterTab - t.wx1;
+    t.wy0 = kInterTab - t.wy1;
     return t;
 }
+
+// true when the 2 x 2 footprint leaves the image (sizes are below 32768, checked by the caller,
+// so cv's saturate_cast<short> of the integer coordinates cannot turn an outside tap into an
+// inside one)
+__device__ __forceinline__ bool tap_outside(const TapWeights& t, int h, int w) {
+    return (unsigned)t.xs > (unsigned)(w - 2) || (unsigned)t.ys > (unsigned)(h - 2);
+}
+
+__device__ __forceinline__ void tap_border_fix(TapWeights& t, int h, int w) {
+    const int x0 = t.xs, y0 = t.ys, fx = t.wx1, fy = t.wy1;
+    t.xs = min(max(x0, 0), w - 2);
+    t.ys = min(max(y0, 0), h - 2);
+    const int dx = x0 - t.xs, dy = y0 - t.ys;
+    t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
+    t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
+    t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
+    t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
+}
+
 
 // Taps of one pixel, requested now and blended later (so a thread keeps the loads of all its
 // pixels in flight).
@@ -766,9 +777,7 @@ struct Taps {
 };
 
 template <int C>
-__device__ __forceinline__ void taps_load(const uint8_t* __restrict__ src, int h, int w, int X,
-                                          int Y, Taps<C>& k) {
-    k.t = tap_weights(X, Y, h, w);
+__device__ __forceinline__ void taps_load(const uint8_t* __restrict__ src, int w, Taps<C>& k) {
     const int pitch = w * C;  // a page plane is < 2 GiB (checked by the caller)
     const uint8_t* r0 = src + (k.t.ys * pitch + k.t.xs * C);
     const uint8_t* r1 = r0 + pitch;
@@ -854,7 +863,7 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
 constexpr int kRemapBuffers = 4;
 
 template <int C, bool MASK, bool SCORE, int R>
-__global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_remap_kernel(
+__global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_remap_kernel(
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
     int c_max, int p_max, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
     const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
@@ -905,7 +914,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
 
     // per-page state, reloaded when the page changes
     int ctx_page = -1;
-    int dst_h = 0, dst_w = 0, src_h = 0, src_w = 0, cols = 0, grid32 = 0;
+    int dst_h = 0, dst_w = 0, src_h = 0, src_w = 0, cols = 0;
     float t_odd = 0.f, t_even = 0.f;
     const uint8_t* __restrict__ src_image = nullptr;
     uint8_t* __restrict__ dst_image = nullptr;
@@ -932,7 +941,6 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
             src_mask = pl->src_mask; dst_mask = pl->dst_mask;
             src_score = pl->src_score; dst_score = pl->dst_score;
             cols = pages[page].cols;
-            grid32 = pages[page].grid_size * 32;
             fast_thresholds(max(src_h, src_w), t_odd, t_even);
             ctx_page = page;
         }
@@ -961,8 +969,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                 if (s < n_cand) {
                     int4 b;
                     if (fast) {
-                        b = *reinterpret_cast<const int4*>(&S[s].x0);
-                        my_key = S[s].info;
+                        b = *reinterpret_cast<const int4*>(&S[s].x0);  // records sit in rank order: key = s
                     } else {
                         const int4 g = cell_box[page_cell0 + s];
                         b = make_int4(g.x, g.y, g.w - g.y, s | ((g.z & 0x40000000) ? (int)0x80000000 : 0));
@@ -1015,12 +1022,10 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                 for (int j = 0; j < R; ++j) {
                     const bool covered = key[j] >= 0;
                     if (fast) {
-                        const int kj = covered ? key[j] : 0;
-                        const int slot = kj & 63;
-                        const int c = (kj >> 6) & 1023, r = kj >> 16;
-                        const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j,
-                                                        c * grid32 - kRoundMagicBits,
-                                                        r * grid32 - kRoundMagicBits, t_odd, t_even, X[j], Y[j]);
+                        const int slot = covered ? key[j] : 0;
+                        const int2 base = *reinterpret_cast<const int2*>(&S[slot].xm);
+                        const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j, base.x, base.y,
+                                                        t_odd, t_even, X[j], Y[j]);
                         if (covered && !ok) {
                             const int cell = S[slot].cellf & 0x7FFFFFFF;
                             const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
@@ -1048,6 +1053,20 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                 // ---- gather ----------------------------------------------------------------
                 const int di0 = ry0 * dst_w + x;
                 const bool tiny = src_h < 2 || src_w < 2;
+                // tap weights of the R pixels, shared by Image and Mask; footprints that leave
+                // the image are rare, so all of them are fixed up behind ONE branch
+                TapWeights tw[R];
+                bool outside = false;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    tw[j] = tap_weights_plain(X[j], Y[j]);
+                    outside |= tap_outside(tw[j], src_h, src_w);
+                }
+                if (outside && !tiny) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (tap_outside(tw[j], src_h, src_w)) tap_border_fix(tw[j], src_h, src_w);
+                }
                 if (C > 0) {
                     constexpr int CC = C > 0 ? C : 1;
                     uint8_t px[R][CC];
@@ -1061,7 +1080,10 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                     } else {
                         Taps<CC> taps[R];
 #pragma unroll
-                        for (int j = 0; j < R; ++j) taps_load<CC>(src_image, src_h, src_w, X[j], Y[j], taps[j]);
+                        for (int j = 0; j < R; ++j) {
+                            taps[j].t = tw[j];
+                            taps_load<CC>(src_image, src_w, taps[j]);
+                        }
 #pragma unroll
                         for (int j = 0; j < R; ++j) taps_blend<CC>(taps[j], px[j]);
                     }
@@ -1088,7 +1110,10 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), (R == 4) ? 4 : 8) grid_re
                     } else {
                         Taps<1> taps[R];
 #pragma unroll
-                        for (int j = 0; j < R; ++j) taps_load<1>(src_mask, src_h, src_w, X[j], Y[j], taps[j]);
+                        for (int j = 0; j < R; ++j) {
+                            taps[j].t = tw[j];
+                            taps_load<1>(src_mask, src_w, taps[j]);
+                        }
 #pragma unroll
                         for (int j = 0; j < R; ++j) taps_blend<1>(taps[j], m[j]);
                     }
@@ -1343,7 +1368,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     VKB_REQUIRE(image_channels || has_mask || has_score, "nothing to remap");
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int R = VKB_REMAP_ROWS;
-    constexpr int kBlocksPerSm = (R == 4) ? 4 : 8;
+    constexpr int kBlocksPerSm = VKB_REMAP_BLOCKS;
     const int grid = remap_grid_blocks(kBlocksPerSm);
 #define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
     grid_remap_kernel<CH, M, S, R><<<grid, 32 * (VKB_TILE / R), 0, st>>>(                      \
