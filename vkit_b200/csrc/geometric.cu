@@ -665,12 +665,11 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
 #define VKB_REMAP_ROWS 4  // dst rows per thread of the remap kernel (4 or 8)
 #endif
 #ifndef VKB_REMAP_BLOCKS
-#define VKB_REMAP_BLOCKS ((VKB_REMAP_ROWS == 4) ? 4 : 8)  // resident blocks per SM (register cap)
+// resident blocks per SM = the register cap: 3 x 256 threads leaves 85 registers (78 used, no
+// spills); 4 blocks spill and measured 2 % slower, 2 blocks 19 % slower
+#define VKB_REMAP_BLOCKS ((VKB_REMAP_ROWS == 4) ? 3 : 4)
 #endif
 
-struct __align__(16) RemapShared {
-    TileSlot slot[VKB_TILE_CAP];
-};
 
 // Rare paths are kept out of line so the hot loop stays small (instruction cache).
 __device__ __noinline__ int2 cell_coord_exact(const double* __restrict__ H, int x, int y) {
@@ -827,40 +826,27 @@ __device__ __noinline__ uint32_t sample_u8_small(const uint8_t* __restrict__ src
     return out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
 }
 
-// ---- mbarrier / cp.async plumbing of the persistent remap kernel ----------------------------
+// ---- cp.async plumbing of the persistent remap kernel -----------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
     return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// arrival that fires when this thread's earlier cp.async copies have landed
-__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
-// Persistent kernel.  Every block owns a contiguous share of the flat tile list; its warps run
-// the tiles in the same order but are NOT kept in lock step: the records of tile k+2 are
-// requested (cp.async) when a warp starts tile k, `land[k % 4]` completes when all threads'
-// copies for tile k have arrived, `done[k % 4]` when all warps have finished reading them, so a
-// warp only ever waits for a warp that is more than a tile behind.
-constexpr int kRemapBuffers = 4;
+// Persistent kernel, WARP-private work items: a block owns a contiguous share of the flat tile
+// list and its warps take the tiles of that share round robin (neighbouring tiles at the same
+// time, so their source rows meet in L1); a warp walks the R-row bands of its 32 x 32 tile by
+// itself.  No block-level synchronisation exists: every warp stages the candidate records of its
+// next tile with cp.async into its own half of a 2 x 32-record shared-memory buffer while it
+// works on the current one (a tile with 33..64 records takes both halves and is loaded when it
+// starts), so a warp never waits for another warp.
+constexpr int kWarpSlots = 64;
 
 template <int C, bool MASK, bool SCORE, int R>
 __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_remap_kernel(
@@ -869,48 +855,39 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
     const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
     const RemapTile* __restrict__ headers, const TileSlot* __restrict__ slots,
     const int32_t* __restrict__ lattice_i) {
-    constexpr int kThreads = 32 * (VKB_TILE / R);
     constexpr int kWarps = VKB_TILE / R;
-    __shared__ RemapShared sm[kRemapBuffers];
-    __shared__ uint64_t land[kRemapBuffers], done[kRemapBuffers];
+    __shared__ __align__(16) TileSlot sm_all[kWarps][kWarpSlots];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    TileSlot* __restrict__ sm = sm_all[warp];
 
-    // contiguous share of the flat tile list
+    // contiguous share of the flat tile list per block, round robin over its warps
     const int total = tile_base[n_pages];
     const int per = (total + gridDim.x - 1) / gridDim.x;
     const int w_begin = blockIdx.x * per;
-    const int n_tiles = min(total, w_begin + per) - w_begin;
+    const int n_block = min(total, w_begin + per) - w_begin;
+    const int n_tiles = n_block > warp ? (n_block - warp + kWarps - 1) / kWarps : 0;  // of this warp
     if (n_tiles <= 0) return;
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < kRemapBuffers; ++i) {
-            mbar_init(&land[i], kThreads);
-            mbar_init(&done[i], kWarps);
-        }
-    }
-    __syncthreads();
 
     auto load_header = [&](int k) {
         RemapTile t;
-        const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + (w_begin + min(k, n_tiles - 1)));
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(
+            headers + (w_begin + warp + kWarps * min(k, n_tiles - 1)));
         const int4 a = __ldg(src), b = __ldg(src + 1);
         t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
         return t;
     };
-    auto prefetch = [&](const RemapTile& t, int k) {
+    auto stage = [&](const RemapTile& t, int base) {  // this warp's copies of one tile's records
         const int chunks = t.count * (VKB_TILE_SLOT_BYTES / 16);  // <= 256; negative on the slow path
-        if (tid < chunks) {
-            const char* g = reinterpret_cast<const char*>(slots + t.rec);
-            char* d = reinterpret_cast<char*>(sm[k % kRemapBuffers].slot);
-            for (int i = tid; i < chunks; i += kThreads) cp_async_16(d + i * 16, g + i * 16);
-        }
-        mbar_arrive_on_copies(&land[k % kRemapBuffers]);
+        const char* g = reinterpret_cast<const char*>(slots + t.rec);
+        char* d = reinterpret_cast<char*>(sm + base);
+        for (int i = lane; i < chunks; i += 32) cp_async_16(d + i * 16, g + i * 16);
+        cp_async_commit();
     };
 
-    RemapTile h0 = load_header(0), h1 = load_header(1), h2 = load_header(2);
-    prefetch(h0, 0);
-    if (n_tiles > 1) prefetch(h1, 1);
+    RemapTile h0 = load_header(0), h1 = load_header(1);
+    int cur_base = 0;
+    bool cur_staged = false;
 
     // per-page state, reloaded when the page changes
     int ctx_page = -1;
@@ -925,13 +902,20 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 
     for (int k = 0; k < n_tiles; ++k) {
         const RemapTile cur = h0;
-        const RemapTile h3 = load_header(k + 3);  // in flight while this tile is processed
-        if (k + 2 < n_tiles) {
-            // buffer (k + 2) % 4 last held tile k - 2: wait until every warp is done with it
-            if (k >= 2) mbar_wait(&done[(k - 2) % kRemapBuffers], ((k - 2) / kRemapBuffers) & 1);
-            prefetch(h2, k + 2);
+        if (!cur_staged) {
+            cur_base = 0;
+            stage(cur, 0);
         }
-        mbar_wait(&land[k % kRemapBuffers], (k / kRemapBuffers) & 1);
+        // the next tile's records go to the other half when both tiles fit a half
+        const bool ahead = k + 1 < n_tiles && cur.count <= kWarpSlots / 2 && h1.count <= kWarpSlots / 2;
+        const int next_base = cur_base ? 0 : kWarpSlots / 2;
+        if (ahead) {
+            stage(h1, next_base);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
 
         const int page = cur.page;
         if (page != ctx_page) {
@@ -944,12 +928,15 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
             fast_thresholds(max(src_h, src_w), t_odd, t_even);
             ctx_page = page;
         }
-        const TileSlot* __restrict__ S = sm[k % kRemapBuffers].slot;
+        const TileSlot* __restrict__ S = sm + cur_base;
         const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
         const bool fast = count >= 0;
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
-        const int ry0 = ty0 + warp * R;
+#pragma unroll 1
+        for (int band = 0; band < kWarps; ++band) {
+        const int ry0 = ty0 + band * R;
+        if (ry0 >= dst_h) break;
 
         int X[R], Y[R];
         if (ry0 < dst_h) {
@@ -1017,7 +1004,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                 // uncovered pixels keep map value (0, 0); the fast path is evaluated for every
                 // pixel (slot 0 for uncovered ones) and the result selected afterwards
                 const float xr = (float)lane;
-                const float yr0 = (float)(warp * R);
+                const float yr0 = (float)(band * R);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const bool covered = key[j] >= 0;
@@ -1044,10 +1031,6 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                 }
             }
         }
-        // last read of this tile's records: let the buffer go before the gather
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&done[k % kRemapBuffers]);
-
         if (ry0 < dst_h) {
             if (x < dst_w) {
                 // ---- gather ----------------------------------------------------------------
@@ -1130,9 +1113,12 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                 }
             }
         }
+        }  // band
+        __syncwarp();  // every lane is done with this tile's records before their half is reused
+        cur_staged = ahead;
+        cur_base = next_base;
         h0 = h1;
-        h1 = h2;
-        h2 = h3;
+        h1 = load_header(k + 2);  // one exposed L2 latency per tile (~1 % of a tile's time)
     }
 }
 
