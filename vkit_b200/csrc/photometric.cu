@@ -16,7 +16,10 @@
 
 namespace vkb {
 
-__constant__ HsvTables c_hsv;
+// Division tables of RGB2HSV: looked up with per-pixel indices, so they live in global memory
+// (coalesced staging into shared memory per block), not in the constant bank, whose reads
+// serialise when the lanes of a warp use different addresses.
+__device__ HsvTables c_hsv;
 static bool g_hsv_ready = false;
 
 static int ensure_tables(cudaStream_t st) {
@@ -164,9 +167,9 @@ struct ColorOpList {
 // The division tables are looked up with per-pixel indices: constant memory would serialise the
 // lanes of a warp, so every block works from a shared-memory copy.
 __device__ __forceinline__ void stage_hsv_tables(HsvTables& sm, int tid, int n_threads) {
-    const int* src = c_hsv.sdiv;
+    const int* __restrict__ src = c_hsv.sdiv;
     int* dst = sm.sdiv;
-    for (int i = tid; i < 512; i += n_threads) dst[i] = src[i];
+    for (int i = tid; i < 512; i += n_threads) dst[i] = __ldg(src + i);
 }
 static_assert(sizeof(HsvTables) == 512 * sizeof(int), "HsvTables: two 256-entry tables");
 
@@ -591,10 +594,10 @@ __device__ __forceinline__ void chain_tile(const vkb_photo_page& pg, unsigned ch
     if (interior) {
         // Every word that is read holds at least one byte of the span, so the reads stay inside
         // the plane's allocation (device allocations are sized in multiples of >= 16 bytes).
-        const uintptr_t base = reinterpret_cast<uintptr_t>(src) + ((size_t)(y0 - R) * w + (x0 - R)) * C;
         const size_t pitch = (size_t)w * C;
-        for (int ty = warp; ty < G::TH; ty += 8) {
-            const uintptr_t a = base + ty * pitch;
+        uintptr_t a = reinterpret_cast<uintptr_t>(src) + ((size_t)(y0 - R) * w + (x0 - R)) * C
+                      + warp * pitch;
+        for (int ty = warp; ty < G::TH; ty += 8, a += 8 * pitch) {
             const uint32_t* __restrict__ a0 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
             const int mis = (int)(a & 3);
             const int last = (mis + G::TWB - 1) >> 2;  // last word with span bytes
