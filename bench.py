@@ -40,8 +40,8 @@ CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold
 # project_camera, project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records, remap
 KERNELS_PER_STEP = 9
 # dram__bytes_read.sum + dram__bytes_write.sum of grid_remap_kernel, one 32-page launch under
-# `ncu --set full` (profiles/r01_ncu_summary.md): 254.5 MB / 32 pages
-TRAFFIC_PER_PAGE = 254.5e6 / 32
+# `ncu --set full` (profiles/r01_ncu_summary.md): 166.7 MB read + 81.9 MB written / 32 pages
+TRAFFIC_PER_PAGE = 248.5e6 / 32
 CPU_PAGES_PER_WORKER = 6  # bounded sample of the CPU arm: ~20 s of CPU work in total
 
 
