@@ -198,6 +198,24 @@ int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double*
 int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32_t* poly_xy, int32_t n_pts,
                      uint8_t value, void* stream);
 
+/* Ordered polygon fills -- label rasterisation after distortion (text-line / char masks and
+ * height score maps: pipeline/text_detection/page_distortion.py:163-314, Polygon.fill_mask /
+ * fill_score_map element/polygon.py:458-487, engine/char_mask/default.py:44-56).
+ * Every polygon is rasterised with cv.fillPoly semantics and applied in list order:
+ *   mode 0: assign (later polygons overwrite earlier ones)   mode 1: keep max   mode 2: keep min
+ * dst: h x w uint8 (dst_f32 = 0) or float32 plane, updated in place; pts_xy: all vertices
+ * (x, y) int32, device; items: device array (items_host: the same records on the host);
+ * keys: h x w int32 device workspace. */
+typedef struct vkb_poly_item {
+    int32_t first_pt, n_pts; /* slice of pts_xy */
+    int32_t y_min, y_max;    /* vertical extent of the polygon */
+    float value;
+    int32_t pad_;
+} vkb_poly_item;
+int vkb_fill_polygons(void* dst, int32_t dst_f32, int32_t h, int32_t w, const int32_t* pts_xy,
+                      const vkb_poly_item* items, const vkb_poly_item* items_host,
+                      int32_t n_items, int32_t mode, int32_t* keys, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Blend: the device form of fill_np_array (vkit/element/opt.py:118-209) as reached through
  * Box / Mask / ScoreMap / Polygon .fill_image / .fill_mask / .fill_score_map

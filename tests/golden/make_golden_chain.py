@@ -99,16 +99,69 @@ def fixed_chain_cases():
         CASES.append(case)
 
 
+def label_polygons(seed, shape, n, max_side):
+    """n rotated boxes (as the distorted char / text-line polygons look), overlapping freely."""
+    rng = np.random.default_rng(seed)
+    height, width = shape
+    polys = []
+    for _ in range(n):
+        cx, cy = rng.uniform(8, width - 8), rng.uniform(8, height - 8)
+        hw, hh = rng.uniform(2, max_side), rng.uniform(2, max_side / 2)
+        theta = rng.uniform(-0.6, 0.6)
+        c, s = np.cos(theta), np.sin(theta)
+        corners = [(-hw, -hh), (hw, -hh), (hw, hh), (-hw, hh)]
+        xy = [(np.clip(cx + c * x - s * y, 0, width - 1), np.clip(cy + s * x + c * y, 0, height - 1))
+              for x, y in corners]
+        polys.append([(float(x), float(y)) for x, y in xy])
+    return polys
+
+
+def label_cases():
+    """Label rasterisation after distortion (page_distortion.py:163-314): text-line mask, height
+    score map in list order, combined char mask (keep max), char heights from tall to small."""
+    from vkit.element import ScoreMap
+    for cid, shape, n, max_side, seed in (('lb0', (160, 208), 40, 30, 70),
+                                          ('lb1', (512, 640), 600, 14, 71),
+                                          ('lb2', (300, 333), 25, 120, 72)):
+        xy_lists = label_polygons(seed, shape, n, max_side)
+        polys = [Polygon.from_xy_pairs(p) for p in xy_lists]
+        rng = np.random.default_rng(seed + 1)
+        heights = [float(v) for v in rng.uniform(4, 60, n).astype(np.float32)]
+        mask = Mask.from_shape(shape)
+        for poly in polys:
+            poly.fill_mask(mask)
+        height_map = ScoreMap.from_shape(shape, is_prob=False)
+        for poly, hv in zip(polys, heights):
+            poly.fill_score_map(score_map=height_map, value=hv)
+        char_mask = Mask.from_shape(shape)
+        for poly in polys:
+            poly.fill_mask(char_mask, keep_max_value=True)
+        order = list(reversed(np.asarray(heights).argsort()))
+        char_heights = ScoreMap.from_shape(shape, is_prob=False)
+        for idx in order:
+            polys[idx].fill_score_map(score_map=char_heights, value=heights[idx])
+        case = {'id': cid, 'kind': 'labels', 'shape': list(shape), 'seed': seed,
+                'polygons': xy_lists, 'heights': heights,
+                'sha': {'mask': mg.sha(mask.mat), 'height_map': mg.sha(height_map.mat),
+                        'char_mask': mg.sha(char_mask.mat),
+                        'char_heights': mg.sha(char_heights.mat)}}
+        if cid == 'lb0':
+            ARRAYS[f'{cid}/mask'] = mask.mat
+            ARRAYS[f'{cid}/height_map'] = height_map.mat
+        CASES.append(case)
+
+
 def main():
     random_distortion_cases()
     fixed_chain_cases()
+    label_cases()
     with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)
     np.savez_compressed(os.path.join(HERE, 'chain_arrays.npz'), **ARRAYS)
     print(len(CASES), 'cases;', sum(v.nbytes for v in ARRAYS.values()) / 1e6, 'MB raw arrays')
     for c in CASES:
-        print(c['id'], c.get('names', c.get('ops')), c['result_shape'] if 'result_shape' in c else c['stage_shapes'][-1])
+        print(c['id'], c.get('names', c.get('ops', c['kind'])), c.get('result_shape') or (c.get('stage_shapes') or [c['shape']])[-1])
 
 
 if __name__ == '__main__':

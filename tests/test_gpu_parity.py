@@ -698,3 +698,30 @@ def test_full_size_batch_properties(vk):
     is_border_mix = (img7 < 200).all(dim=-1)  # BORDER_CONSTANT 0 can only darken
     assert bool((inside | is_corner | is_border_mix).all())
     assert float(inside.float().mean()) > 0.5
+
+
+@pytest.mark.parametrize('case', chain_cases('labels'), ids=lambda c: c['id'])
+def test_label_rasterisation_vs_reference(vk, case):
+    """Ordered polygon fills (text-line mask, height score map, combined char mask, char heights
+    from tall to small) in one device pass each == the reference's per-polygon loops."""
+    element, _ = vk
+    from vkit_b200.compositing import fill_polygons
+    shape = tuple(case['shape'])
+    polys = [element.Polygon.from_xy_pairs(p) for p in case['polygons']]
+    heights = case['heights']
+    mask = fill_polygons(element.Mask.from_shape(shape), polys, 1)
+    assert sha(mask.mat) == case['sha']['mask']
+    height_map = fill_polygons(element.ScoreMap.from_shape(shape, is_prob=False), polys, heights)
+    assert sha(height_map.mat) == case['sha']['height_map']
+    char_mask = fill_polygons(element.Mask.from_shape(shape), polys, 1, keep_max_value=True)
+    assert sha(char_mask.mat) == case['sha']['char_mask']
+    order = list(reversed(np.asarray(heights).argsort()))
+    char_heights = fill_polygons(element.ScoreMap.from_shape(shape, is_prob=False),
+                                 [polys[i] for i in order], [heights[i] for i in order])
+    assert sha(char_heights.mat) == case['sha']['char_heights']
+    # the same through the per-polygon element API (one launch pair per polygon)
+    if case['id'] == 'lb0':
+        seq = element.Mask.from_shape(shape)
+        for poly in polys:
+            poly.fill_mask(seq)
+        assert sha(seq.mat) == case['sha']['mask']

@@ -250,3 +250,27 @@ def _oracle_photometric_on(image, case, rng):
     if name == 'line_streak':
         return port.line_streak(image, **cfg)
     raise KeyError(name)
+
+
+# ---------------------------------------------------------------------------------------------
+# Label rasterisation after distortion (ordered polygon fills)
+# ---------------------------------------------------------------------------------------------
+def _label_oracle(case):
+    shape = tuple(case['shape'])
+    polys, heights = case['polygons'], case['heights']
+    mask = port.fill_polygons(np.zeros(shape, np.uint8), polys, 1)
+    height_map = port.fill_polygons(np.zeros(shape, np.float32), polys, heights)
+    char_mask = port.fill_polygons(np.zeros(shape, np.uint8), polys, 1, keep_max_value=True)
+    order = list(reversed(np.asarray(heights).argsort()))
+    char_heights = port.fill_polygons(np.zeros(shape, np.float32), [polys[i] for i in order],
+                                      [heights[i] for i in order])
+    return {'mask': mask, 'height_map': height_map, 'char_mask': char_mask,
+            'char_heights': char_heights}
+
+
+@pytest.mark.parametrize('case', chain_cases('labels'), ids=lambda c: c['id'])
+def test_label_rasterisation_oracle(case):
+    port.use_cv2(False)
+    got = _label_oracle(case)
+    for key, value in got.items():
+        assert sha(value) == case['sha'][key], (case['id'], key)

@@ -96,6 +96,11 @@ class PhotoPage(ctypes.Structure):
     ]
 
 
+class PolyItem(ctypes.Structure):
+    _fields_ = [('first_pt', c_int32), ('n_pts', c_int32), ('y_min', c_int32), ('y_max', c_int32),
+                ('value', c_float), ('pad_', c_int32)]
+
+
 class Rect(ctypes.Structure):
     _fields_ = [('up', c_int32), ('down', c_int32), ('left', c_int32), ('right', c_int32)]
 
@@ -130,6 +135,7 @@ def _np_dtype(struct_cls):
 PLANES_DTYPE = _np_dtype(Planes)
 BLEND_ITEM_DTYPE = _np_dtype(BlendItem)
 RECT_DTYPE = _np_dtype(Rect)
+POLY_ITEM_DTYPE = _np_dtype(PolyItem)
 PHOTO_PAGE_DTYPE = _np_dtype(PhotoPage)
 COLOR_OP_DTYPE = _np_dtype(ColorOp)
 WARP_PAGE_DTYPE = _np_dtype(WarpPage)
@@ -175,6 +181,7 @@ def _declare(lib):
     lib.vkb_fill_rects.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.vkb_streak_masks.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, POINTER(c_float),
                                      c_float, vp]
+    lib.vkb_fill_polygons.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]
     lib.vkb_photo_chain_batched.argtypes = [vp, vp, i32, i32, vp]
     lib.vkb_channel_stats_batched.argtypes = [vp, i32, i32, vp, vp]
     for name in EXPORTS:
@@ -187,7 +194,7 @@ EXPORTS = (
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks', 'vkb_photo_chain_batched',
-    'vkb_channel_stats_batched',
+    'vkb_channel_stats_batched', 'vkb_fill_polygons',
 )
 
 

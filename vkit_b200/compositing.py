@@ -187,3 +187,54 @@ def fill_page_inactive_region(page_image: Image, page_active_mask: Mask,
     if page_bottom_layer_image.shape != page_image.shape:
         raise NotImplementedError('resizing the bottom layer (cv.resize) is a "next" row')
     page_active_mask.to_inverted_mask().fill_image(page_image, page_bottom_layer_image)
+
+
+# =============================================================================================
+# Label rasterisation after distortion
+# =============================================================================================
+def fill_polygons(target: Union[Mask, ScoreMap], polygons, value=1, keep_max_value: bool = False,
+                  keep_min_value: bool = False):
+    """`for polygon, v in zip(polygons, values): polygon.fill_mask(target, v, keep_max_value=...)`
+    (or `fill_score_map`) as ONE ordered device pass: every polygon is rasterised with cv.fillPoly
+    semantics and later polygons overwrite earlier ones (vkit/element/polygon.py:458-487 as looped
+    by pipeline/text_detection/page_distortion.py:163-314 and engine/char_mask/default.py:44-56).
+    `value`: one number for all polygons or one per polygon.  The target is updated in place."""
+    polygons = list(polygons)
+    if not polygons:
+        return target
+    if target.box is not None:
+        raise NotImplementedError('fill_polygons expects a target without an attached box')
+    values = list(value) if isinstance(value, (list, tuple, np.ndarray)) else [value] * len(polygons)
+    if len(values) != len(polygons):
+        raise ValueError('one value per polygon expected')
+    mode = 1 if keep_max_value else (2 if keep_min_value else 0)
+    items = np.zeros(len(polygons), dtype=nv.POLY_ITEM_DTYPE)
+    pts = []
+    first = 0
+    for i, (polygon, v) in enumerate(zip(polygons, values)):
+        xy = np.asarray(polygon.to_np_array(), dtype=np.int32).reshape(-1, 2)
+        items['first_pt'][i] = first
+        items['n_pts'][i] = xy.shape[0]
+        items['y_min'][i] = int(xy[:, 1].min())
+        items['y_max'][i] = int(xy[:, 1].max())
+        items['value'][i] = v
+        first += xy.shape[0]
+        pts.append(xy)
+    dst_f32 = target.mat_dtype == np.float32
+    pts_dev = dv.to_device(np.ascontiguousarray(np.concatenate(pts)))
+    items_dev = dv.upload_structs(items)
+    height, width = target.shape
+    keys = dv.empty((height, width), np.int32)
+    dst = target.dev
+    lib = nv.lib()
+    # at most 65535 polygons per launch; ordering across launches is the list order
+    for a in range(0, len(polygons), 65535):
+        b = min(a + 65535, len(polygons))
+        offset = a * nv.POLY_ITEM_DTYPE.itemsize
+        nv.check(lib.vkb_fill_polygons(
+            dv.ptr(dst), int(dst_f32), height, width, dv.ptr(pts_dev),
+            ctypes.c_void_p(items_dev.data_ptr() + offset),
+            ctypes.c_void_p(items.ctypes.data + offset), b - a, mode, dv.ptr(keys),
+            dv.stream_ptr()), 'vkb_fill_polygons')
+    target._after_device_write()
+    return target

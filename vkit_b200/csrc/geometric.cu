@@ -1237,6 +1237,114 @@ __global__ void fill_polygon_edges_kernel(uint8_t* __restrict__ mask, int h, int
     }
 }
 
+// ============================================================================================
+// Ordered polygon fills (label rasterisation after distortion): N polygons, each cv.fillPoly
+// exact (scan fill with 16.16 edges + 8-connected outline), applied in list order like the
+// reference's loops of Polygon.fill_mask / fill_score_map (page_distortion.py:163-314,
+// engine/char_mask/default.py:44-56).  Pass 1 marks every covered pixel with atomicMax of an
+// order key into an int32 canvas (assign: the polygon's list position, so the LAST polygon wins;
+// keep max / keep min: an order-preserving image of the value); pass 2 resolves the keys.
+// ============================================================================================
+__device__ __forceinline__ void poly_mark(int32_t* __restrict__ keys, int h, int w, int x, int y, int key) {
+    if ((unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h) atomicMax(keys + (size_t)y * w + x, key);
+}
+
+__device__ __forceinline__ int poly_item_key(const vkb_poly_item& it, int index, int mode) {
+    if (mode == 0) return index + 1;
+    const int bits = __float_as_int(it.value);  // values are >= 0: the bit pattern is monotonic
+    return mode == 1 ? bits + 1 : 0x7fffffff - bits;
+}
+
+__global__ void __launch_bounds__(128) poly_rows_kernel(int32_t* __restrict__ keys, int h, int w,
+                                                        const int32_t* __restrict__ pts,
+                                                        const vkb_poly_item* __restrict__ items,
+                                                        int mode) {
+    const vkb_poly_item it = items[blockIdx.y];
+    const int y = it.y_min + blockIdx.x * blockDim.x + threadIdx.x;
+    if (y > it.y_max || y < 0 || y >= h) return;
+    const int32_t* __restrict__ poly = pts + 2 * (size_t)it.first_pt;
+    const int n = it.n_pts;
+    long long cross[kMaxCross];
+    int nc = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = i == 0 ? n - 1 : i - 1;
+        const int x0 = poly[2 * j], y0 = poly[2 * j + 1], x1 = poly[2 * i], y1 = poly[2 * i + 1];
+        if (y0 == y1) continue;
+        int ya, yb;
+        long long xa;
+        if (y0 < y1) { ya = y0; yb = y1; xa = (long long)x0 * 65536; }
+        else { ya = y1; yb = y0; xa = (long long)x1 * 65536; }
+        if (ya <= y && y < yb) {
+            const long long dxf = ((long long)(x1 - x0) * 65536) / (long long)(y1 - y0);
+            if (nc < kMaxCross) cross[nc] = xa + dxf * (long long)(y - ya);
+            ++nc;
+        }
+    }
+    if (nc > kMaxCross) nc = kMaxCross;  // pathological polygons only
+    for (int i = 1; i < nc; ++i) {
+        const long long v = cross[i];
+        int j = i - 1;
+        while (j >= 0 && cross[j] > v) { cross[j + 1] = cross[j]; --j; }
+        cross[j + 1] = v;
+    }
+    const int key = poly_item_key(it, blockIdx.y, mode);
+    int32_t* __restrict__ row = keys + (size_t)y * w;
+    for (int k = 0; k + 1 < nc; k += 2) {
+        long long xl = (cross[k] + 65535) >> 16;
+        long long xr = cross[k + 1] >> 16;
+        if (xl < 0) xl = 0;
+        if (xr > w - 1) xr = w - 1;
+        for (long long xx = xl; xx <= xr; ++xx) atomicMax(row + xx, key);
+    }
+}
+
+__global__ void __launch_bounds__(128) poly_edges_kernel(int32_t* __restrict__ keys, int h, int w,
+                                                         const int32_t* __restrict__ pts,
+                                                         const vkb_poly_item* __restrict__ items,
+                                                         int mode) {
+    const vkb_poly_item it = items[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = it.n_pts;
+    if (i >= n) return;
+    const int32_t* __restrict__ poly = pts + 2 * (size_t)it.first_pt;
+    const int j = i == 0 ? n - 1 : i - 1;
+    int ax = poly[2 * j], ay = poly[2 * j + 1], bx = poly[2 * i], by = poly[2 * i + 1];
+    if (ax > bx) { int t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
+    int dx = bx - ax, dy = by - ay;
+    const int sy = dy >= 0 ? 1 : -1;
+    dy = dy >= 0 ? dy : -dy;
+    const bool steep = dy > dx;
+    if (steep) { const int t = dx; dx = dy; dy = t; }
+    int err = dx - 2 * dy;
+    int x = ax, y = ay;
+    const int key = poly_item_key(it, blockIdx.y, mode);
+    for (int s = 0; s <= dx; ++s) {
+        poly_mark(keys, h, w, x, y, key);
+        const bool m = err < 0;
+        err += -2 * dy + (m ? 2 * dx : 0);
+        if (steep) { y += sy; if (m) x += 1; }
+        else { x += 1; if (m) y += sy; }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) poly_resolve_kernel(T* __restrict__ dst, const int32_t* __restrict__ keys,
+                                                           long long n, const vkb_poly_item* __restrict__ items,
+                                                           int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = keys[i];
+    if (key <= 0) return;
+    float v;
+    if (mode == 0) v = items[key - 1].value;
+    else if (mode == 1) v = __int_as_float(key - 1);
+    else v = __int_as_float(0x7fffffff - key);
+    const float old = (float)dst[i];
+    if (mode == 1) v = fmaxf(old, v);
+    if (mode == 2) v = fminf(old, v);
+    dst[i] = (T)v;
+}
+
 }  // namespace vkb
 
 // ============================================================================================
@@ -1402,4 +1510,40 @@ extern "C" int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32
     if (rc) return rc;
     fill_polygon_edges_kernel<<<(n_pts + 127) / 128, 128, 0, st>>>(mask, h, w, poly_xy, n_pts, value);
     return check_launch("fill_polygon_edges_kernel");
+}
+
+extern "C" int vkb_fill_polygons(void* dst, int32_t dst_f32, int32_t h, int32_t w,
+                                 const int32_t* pts_xy, const vkb_poly_item* items,
+                                 const vkb_poly_item* items_host, int32_t n_items, int32_t mode,
+                                 int32_t* keys, void* stream) {
+    VKB_REQUIRE(dst && pts_xy && items && items_host && keys && h > 0 && w > 0, "bad arguments");
+    VKB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (assign), 1 (keep max) or 2 (keep min)");
+    VKB_REQUIRE(n_items >= 0 && n_items <= 65535, "at most 65535 polygons per launch");
+    if (n_items == 0) return VKB_OK;
+    int max_rows = 1, max_pts = 1;
+    for (int i = 0; i < n_items; ++i) {
+        const vkb_poly_item& it = items_host[i];
+        VKB_REQUIRE(it.n_pts >= 1 && it.first_pt >= 0, "empty polygon");
+        VKB_REQUIRE(mode == 0 || it.value >= 0.f, "keep max / keep min need values >= 0");
+        VKB_REQUIRE(dst_f32 || (it.value >= 0.f && it.value <= 255.f && it.value == (float)(int)it.value),
+                    "uint8 destinations take integer values 0..255");
+        const int rows = it.y_max - it.y_min + 1;
+        max_rows = rows > max_rows ? rows : max_rows;
+        max_pts = it.n_pts > max_pts ? it.n_pts : max_pts;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)h * w;
+    VKB_CUDA(cudaMemsetAsync(keys, 0, sizeof(int32_t) * (size_t)n, st));
+    poly_rows_kernel<<<dim3((max_rows + 127) / 128, n_items), 128, 0, st>>>(keys, h, w, pts_xy, items, mode);
+    int rc = check_launch("poly_rows_kernel");
+    if (rc) return rc;
+    poly_edges_kernel<<<dim3((max_pts + 127) / 128, n_items), 128, 0, st>>>(keys, h, w, pts_xy, items, mode);
+    rc = check_launch("poly_edges_kernel");
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (dst_f32)
+        poly_resolve_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<float*>(dst), keys, n, items, mode);
+    else
+        poly_resolve_kernel<uint8_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint8_t*>(dst), keys, n, items, mode);
+    return check_launch("poly_resolve_kernel");
 }
