@@ -307,6 +307,13 @@ int vkb_apply_lut(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t ch
 int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
                          const int32_t* kernel_host, int32_t ksize, void* stream);
 
+/* cv.filter2D(uint8, -1, float32 kernel) with BORDER_REFLECT_101 and the anchor at the kernel
+ * centre: float32 accumulation in row-major tap order, round half to even, saturate
+ * (defocus_blur / motion_blur, photometric/blur.py:79-192).  taps_dev: kh x kw float32 on the
+ * device, kh and kw odd and <= 63.  src != dst. */
+int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                    const float* taps_dev, int32_t kh, int32_t kw, void* stream);
+
 /* Noise (photometric/noise.py:25-190).  kind: 0 gaussian (p0 = std), 1 poisson, 2 impulse
  * (p0 = prob_salt, p1 = prob_pepper), 3 speckle (p0 = std).
  * Philox variant: counter-based device RNG keyed by (seed, element index); distributional

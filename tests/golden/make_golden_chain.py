@@ -151,10 +151,40 @@ def label_cases():
         CASES.append(case)
 
 
+def filter_blur_cases():
+    """defocus_blur / motion_blur (cv.filter2D with a host-built float32 kernel)."""
+    shape = (64, 96)
+    specs = [('defocus_blur', {'radius': 1}), ('defocus_blur', {'radius': 2}),
+             ('defocus_blur', {'radius': 3}), ('defocus_blur', {'radius': 4, 'anti_aliasing_sigma': 0.9}),
+             ('defocus_blur', {'radius': 7}),  # 17 x 17 taps: cv2 switches to its DFT path
+             ('motion_blur', {'radius': 2, 'angle': 30}), ('motion_blur', {'radius': 4, 'angle': 135}),
+             ('motion_blur', {'radius': 3, 'angle': 300}), ('motion_blur', {'radius': 5, 'angle': 0}),
+             ('motion_blur', {'radius': 1, 'angle': 77, 'anti_aliasing_sigma': 0.8})]
+    for k, (name, cfg) in enumerate(specs):
+        seed = 8000 + k
+        image, _, _ = make_inputs(seed, shape)
+        r = getattr(distortion, name).distort(cfg, image=Image(mat=image), get_config=True)
+        cid = f'fb{k:02d}'
+        CASES.append({'id': cid, 'kind': 'filter_blur', 'op': name, 'config': mg.plain(r.config),
+                      'shape': list(shape), 'seed': seed, 'sha': {'image': mg.sha(r.image.mat)}})
+        ARRAYS[f'{cid}/image'] = r.image.mat
+    # one full-size page per op (hash only)
+    for k, (name, cfg) in enumerate([('defocus_blur', {'radius': 3}),
+                                     ('motion_blur', {'radius': 4, 'angle': 200})]):
+        seed = 8100 + k
+        image, _, _ = make_inputs(seed, (1024, 1024))
+        r = getattr(distortion, name).distort(cfg, image=Image(mat=image), get_config=True)
+        CASES.append({'id': f'fbL{k}', 'kind': 'filter_blur', 'op': name,
+                      'config': mg.plain(r.config), 'shape': [1024, 1024], 'seed': seed,
+                      'sha': {'image': mg.sha(r.image.mat)},
+                      'sum': int(r.image.mat.astype(np.int64).sum())})
+
+
 def main():
     random_distortion_cases()
     fixed_chain_cases()
     label_cases()
+    filter_blur_cases()
     with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)

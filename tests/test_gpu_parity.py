@@ -725,3 +725,22 @@ def test_label_rasterisation_vs_reference(vk, case):
         for poly in polys:
             poly.fill_mask(seq)
         assert sha(seq.mat) == case['sha']['mask']
+
+
+@pytest.mark.parametrize('case', chain_cases('filter_blur'), ids=lambda c: f"{c['id']}-{c['op']}")
+def test_filter_blur_vs_reference(vk, case):
+    """defocus_blur / motion_blur: host-built float32 kernel (1 ulp from cv2's) + device filter2D in
+    float32; cv2 itself switches to a DFT for >= 130 taps.  Tolerance: +-1 grey level on <= 0.2 % of
+    the pixels (0 differences observed for the small kernels)."""
+    element, distortion = vk
+    shape = tuple(case['shape'])
+    image, _, _ = make_inputs(case['seed'], shape)
+    got = getattr(distortion, case['op']).distort(dict(case['config']),
+                                                  image=element.Image(mat=image)).image.mat
+    ref = chain_array(case, 'image')
+    if ref is None:  # full-size page: hash, else the checksum within the tolerance
+        if sha(got) != case['sha']['image']:
+            assert abs(int(got.astype(np.int64).sum()) - case['sum']) <= 2e-3 * got.size
+        return
+    diff = np.abs(got.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3, (case['id'], _diff_report(got, ref))

@@ -530,6 +530,60 @@ __global__ void __launch_bounds__(256) streak_masks_kernel(uint8_t* image, int h
 }
 
 // ============================================================================================
+// cv.filter2D(uint8, -1, float32 kernel), BORDER_REFLECT_101, anchor at the kernel centre:
+// float32 accumulation over the taps in row-major order, round half to even, saturate
+// (defocus_blur / motion_blur, photometric/blur.py:79-192).  32 x 32 tile + halo in shared
+// memory, taps in shared memory, 4 rows per thread.
+// ============================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) filter2d_kernel(const uint8_t* __restrict__ src,
+                                                       uint8_t* __restrict__ dst, int h, int w,
+                                                       const float* __restrict__ taps, int kh, int kw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* ktaps = reinterpret_cast<float*>(smem);
+    uint8_t* tile = smem + (((size_t)kh * kw * 4 + 15) & ~(size_t)15);
+    const int ay = kh / 2, ax = kw / 2;
+    const int TW = 32 + kw - 1, TH = 32 + kh - 1;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < kh * kw; i += 256) ktaps[i] = taps[i];
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int sy = reflect101(y0 + ty - ay, h), sx = reflect101(x0 + tx - ax, w);
+        const uint8_t* p = src + ((long long)sy * w + sx) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) tile[i * C + c] = p[c];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    float acc[4][C];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[j][c] = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+        for (int kx = 0; kx < kw; ++kx) {
+            const float f = ktaps[ky * kw + kx];
+            if (f == 0.f) continue;  // cv keeps only the non-zero taps
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t* p = tile + ((threadIdx.y + 8 * j + ky) * TW + threadIdx.x + kx) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[j][c] = __fmaf_rn(f, (float)p[c], acc[j][c]);
+            }
+        }
+    }
+    if (x >= w) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int y = y0 + threadIdx.y + 8 * j;
+        if (y >= h) break;
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[((long long)y * w + x) * C + c] = (uint8_t)round_u8(acc[j][c]);
+    }
+}
+
+// ============================================================================================
 // Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
 // over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
 // gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
@@ -1014,4 +1068,29 @@ extern "C" int vkb_channel_stats_batched(const vkb_photo_page* pages, int32_t n_
     channel_stats_batched_init_kernel<<<(n_pages + 255) / 256, 256, 0, st>>>(o, n_pages);
     channel_stats_batched_kernel<<<dim3(64, n_pages), 256, 0, st>>>(pages, channels, o);
     return check_launch("channel_stats_batched_kernel");
+}
+
+extern "C" int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
+                               int32_t channels, const float* taps_dev, int32_t kh, int32_t kw,
+                               void* stream) {
+    VKB_REQUIRE(src && dst && taps_dev && h > 0 && w > 0 && src != dst, "bad arguments");
+    VKB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1) && kh <= 63 && kw <= 63,
+                "kernel sides must be odd and <= 63");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    const size_t smem = (((size_t)kh * kw * 4 + 15) & ~(size_t)15)
+                        + (size_t)(32 + kw - 1) * (32 + kh - 1) * channels;
+    dim3 grid((w + 31) / 32, (h + 31) / 32);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VKB_LAUNCH_F2D(CH)                                                                       \
+    do {                                                                                         \
+        if (smem > 48 * 1024)                                                                    \
+            VKB_CUDA(cudaFuncSetAttribute(filter2d_kernel<CH>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        filter2d_kernel<CH><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, taps_dev, kh, kw);  \
+    } while (0)
+    if (channels == 1) VKB_LAUNCH_F2D(1);
+    else if (channels == 3) VKB_LAUNCH_F2D(3);
+    else VKB_LAUNCH_F2D(4);
+#undef VKB_LAUNCH_F2D
+    return check_launch("filter2d_kernel");
 }

@@ -80,15 +80,112 @@ def _next_row(name):
     return func
 
 
+# ---- defocus / motion blur: a small float32 kernel built on the host, cv.filter2D on the device ---
+def _get_anti_aliasing_kernel_size_and_padding(anti_aliasing_sigma: float):
+    kernel_size = _estimate_gaussian_kernel_size(anti_aliasing_sigma)
+    return kernel_size, kernel_size // 2 * 2
+
+
+def gaussian_taps_f32(ksize: int, sigma: float) -> np.ndarray:
+    """cv.getGaussianKernel(ksize, sigma, CV_32F): double taps, normalised, cast to float32."""
+    xs = np.arange(ksize, dtype=np.float64) - ksize // 2
+    taps = np.exp(-(xs * xs) / (2.0 * sigma * sigma))
+    return (taps / taps.sum()).astype(np.float32)
+
+
+def _reflect101(index: int, size: int) -> int:
+    if size == 1:
+        return 0
+    while index < 0 or index >= size:
+        index = -index if index < 0 else 2 * (size - 1) - index
+    return index
+
+
+def gaussian_blur_f32(mat: np.ndarray, ksize: int, sigma: float) -> np.ndarray:
+    """cv.GaussianBlur on a small float32 array (BORDER_REFLECT_101), separable, float32 sums in
+    the symmetric order centre*k0 + (left + right)*k1 + ...  Matches cv2 to 1 ulp of float32 (cv2's
+    own summation order depends on its SIMD / IPP backend); the array is a blur kernel whose taps
+    feed a uint8-rounded convolution."""
+    taps = gaussian_taps_f32(ksize, sigma)
+    r = ksize // 2
+    f32 = np.float32
+
+    def one_axis(src: np.ndarray, axis: int) -> np.ndarray:
+        n = src.shape[axis]
+        out = np.zeros_like(src)
+        for pos in range(n):
+            centre = np.take(src, pos, axis=axis)
+            acc = (centre * taps[r]).astype(f32)
+            for d in range(1, r + 1):
+                pair = (np.take(src, _reflect101(pos - d, n), axis=axis)
+                        + np.take(src, _reflect101(pos + d, n), axis=axis)).astype(f32)
+                acc = (acc + (pair * taps[r + d]).astype(f32)).astype(f32)
+            if axis == 0:
+                out[pos, :] = acc
+            else:
+                out[:, pos] = acc
+        return out
+
+    return one_axis(one_axis(np.asarray(mat, dtype=f32), 1), 0)
+
+
+def rotation_matrix_2d(center, angle: float, scale: float) -> np.ndarray:
+    """cv.getRotationMatrix2D (double)."""
+    import math
+    angle = angle * (np.pi / 180)
+    alpha = scale * math.cos(angle)
+    beta = scale * math.sin(angle)
+    cx, cy = center
+    return np.asarray([[alpha, beta, (1 - alpha) * cx - beta * cy],
+                       [-beta, alpha, beta * cx + (1 - alpha) * cy]], dtype=np.float64)
+
+
+def filter2d_device(image: Image, kernel: np.ndarray) -> Image:
+    """cv.filter2D(image.mat, -1, kernel) on the device (uint8, BORDER_REFLECT_101)."""
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    kh, kw = kernel.shape
+    if kh > 63 or kw > 63:
+        raise NotImplementedError('filter kernels larger than 63 x 63 are not provided')
+    src = image.dev
+    dst = dv.empty(tuple(src.shape), np.uint8)
+    taps = dv.to_device(kernel)
+    nv.check(nv.lib().vkb_filter2d_u8(dv.ptr(src), dv.ptr(dst), image.height, image.width,
+                                      image.num_channels or 1, dv.ptr(taps), kh, kw,
+                                      dv.stream_ptr()), 'vkb_filter2d_u8')
+    return attrs.evolve(image, mat=dst)
+
+
 @attrs.define
 class DefocusBlurConfig(DistortionConfig):
     radius: int
     anti_aliasing_sigma: float = 0.5
 
 
+def defocus_blur_kernel(radius: int, anti_aliasing_sigma: float) -> np.ndarray:
+    # blur.py:91-112: disc of ones / its sum, then anti-aliased with a Gaussian
+    assert 0 < radius
+    aa_ksize, aa_padding = _get_anti_aliasing_kernel_size_and_padding(anti_aliasing_sigma)
+    kernel_size = 2 * radius + 1 + aa_padding
+    begin = -(kernel_size // 2)
+    coords = np.arange(begin, begin + kernel_size)
+    x, y = np.meshgrid(coords, coords)
+    kernel = ((x**2 + y**2) <= radius**2).astype(np.float32)
+    kernel /= kernel.sum()
+    return gaussian_blur_f32(kernel, aa_ksize, anti_aliasing_sigma)
+
+
+def defocus_blur_image(config: DefocusBlurConfig, state, image: Image,
+                       rng: Optional[RandomGenerator]):
+    kernel = defocus_blur_kernel(config.radius, config.anti_aliasing_sigma)
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    image = filter2d_device(image, kernel)
+    return to_original_image(image, mode)
+
+
 defocus_blur = Distortion(config_cls=DefocusBlurConfig,
                           state_cls=DistortionNopState[DefocusBlurConfig],
-                          func_image=_next_row('defocus_blur'))
+                          func_image=defocus_blur_image)
 
 
 @attrs.define
@@ -98,9 +195,40 @@ class MotionBlurConfig(DistortionConfig):
     anti_aliasing_sigma: float = 0.5
 
 
+def motion_blur_kernel(radius: int, angle: int, anti_aliasing_sigma: float) -> np.ndarray:
+    # blur.py:145-177: a horizontal line of ones, rotated with cv.warpAffine (float32, bilinear;
+    # here through the device warp that reproduces it bit for bit), / its sum, anti-aliased
+    from vkit_b200.element import ScoreMap
+    from ..geometric.affine import warp_planes
+    kernel_size = 2 * radius + 1
+    aa_ksize, aa_padding = _get_anti_aliasing_kernel_size_and_padding(anti_aliasing_sigma)
+    half = aa_padding // 2
+    center = radius + half
+    left = half
+    right = left + kernel_size - 1
+    kernel_size += aa_padding
+    kernel = np.zeros((kernel_size, kernel_size), dtype=np.float32)
+    kernel[center, left:right + 1] = 1.0
+    trans_mat = rotation_matrix_2d((center, center), 360 - (angle % 360), 1.0)
+    _, _, rotated = warp_planes(trans_mat, (kernel_size, kernel_size),
+                                score_map=ScoreMap(mat=kernel, is_prob=False))
+    kernel = dv.to_host(rotated).astype(np.float32).reshape(kernel_size, kernel_size).copy()
+    kernel /= kernel.sum()
+    return gaussian_blur_f32(kernel, aa_ksize, anti_aliasing_sigma)
+
+
+def motion_blur_image(config: MotionBlurConfig, state, image: Image,
+                      rng: Optional[RandomGenerator]):
+    kernel = motion_blur_kernel(config.radius, config.angle, config.anti_aliasing_sigma)
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    image = filter2d_device(image, kernel)
+    return to_original_image(image, mode)
+
+
 motion_blur = Distortion(config_cls=MotionBlurConfig,
                          state_cls=DistortionNopState[MotionBlurConfig],
-                         func_image=_next_row('motion_blur'))
+                         func_image=motion_blur_image)
 
 
 @attrs.define
