@@ -314,6 +314,14 @@ int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
 int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
                     const float* taps_dev, int32_t kh, int32_t kw, void* stream);
 
+/* cv.resize(uint8) for INTER_NEAREST and INTER_LINEAR (pixelation, photometric/effect.py:58-79;
+ * Image.to_resized_image with those interpolations, element/image.py:836-852): bit exact
+ * (11-bit fixed-point coefficients and cv2's 8-bit vertical pass). */
+#define VKB_INTER_NEAREST 0
+#define VKB_INTER_LINEAR 1
+int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
+                  int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
+
 /* Noise (photometric/noise.py:25-190).  kind: 0 gaussian (p0 = std), 1 poisson, 2 impulse
  * (p0 = prob_salt, p1 = prob_pepper), 3 speckle (p0 = std).
  * Philox variant: counter-based device RNG keyed by (seed, element index); distributional

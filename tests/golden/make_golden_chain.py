@@ -180,11 +180,31 @@ def filter_blur_cases():
                       'sum': int(r.image.mat.astype(np.int64).sum())})
 
 
+def effect_cases():
+    """pixelation (cv.resize linear down + nearest up) and fog (diamond-square field + blend)."""
+    specs = [('pixelation', {'ratio': 0.13}, (64, 96)), ('pixelation', {'ratio': 0.5}, (64, 96)),
+             ('pixelation', {'ratio': 0.37}, (100, 133)), ('pixelation', {'ratio': 0.93}, (77, 50)),
+             ('pixelation', {'ratio': 0.25}, (1024, 1024)),
+             ('fog', {'roughness': 0.5}, (64, 96)), ('fog', {'roughness': 0.2, 'ratio_max': 0.7,
+                                                               'ratio_min': 0.1}, (100, 133)),
+             ('fog', {'roughness': 0.9, 'fog_rgb': [10, 20, 250]}, (257, 300)),
+             ('fog', {'roughness': 0.6}, (1024, 1024))]
+    for k, (name, cfg, shape) in enumerate(specs):
+        seed = 8200 + k
+        image, _, _ = make_inputs(seed, shape)
+        rng = np.random.default_rng(seed + 1) if name == 'fog' else None
+        r = getattr(distortion, name).distort(cfg, image=Image(mat=image), rng=rng, get_config=True)
+        CASES.append({'id': f'ef{k:02d}', 'kind': 'effect', 'op': name, 'config': mg.plain(r.config),
+                      'shape': list(shape), 'seed': seed, 'rng_seed': seed + 1 if rng else None,
+                      'sha': {'image': mg.sha(r.image.mat)}})
+
+
 def main():
     random_distortion_cases()
     fixed_chain_cases()
     label_cases()
     filter_blur_cases()
+    effect_cases()
     with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)

@@ -744,3 +744,15 @@ def test_filter_blur_vs_reference(vk, case):
         return
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3, (case['id'], _diff_report(got, ref))
+
+
+@pytest.mark.parametrize('case', chain_cases('effect'), ids=lambda c: f"{c['id']}-{c['op']}")
+def test_effect_vs_reference(vk, case):
+    """pixelation (both cv.resize passes bit exact) and fog (host-drawn diamond-square field from
+    the caller's rng, device blend): sha256 equal to the reference."""
+    element, distortion = vk
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    rng = np.random.default_rng(case['rng_seed']) if case['rng_seed'] is not None else None
+    got = getattr(distortion, case['op']).distort(dict(case['config']),
+                                                  image=element.Image(mat=image), rng=rng).image.mat
+    assert sha(got) == case['sha']['image'], case['id']

@@ -304,3 +304,20 @@ def test_filter_blur_oracle(case):
             assert sha(_filter_blur_oracle(case)) == case['sha']['image']
         finally:
             port.use_cv2(False)
+
+
+# ---------------------------------------------------------------------------------------------
+# pixelation / fog
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', [c for c in chain_cases('effect') if c['shape'][0] <= 300],
+                         ids=lambda c: f"{c['id']}-{c['op']}")
+def test_effect_oracle(case):
+    port.use_cv2(False)
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    cfg = case['config']
+    if case['op'] == 'pixelation':
+        got = port.pixelation(image, cfg['ratio'])
+    else:
+        got = port.fog(image, cfg['roughness'], np.random.default_rng(case['rng_seed']),
+                       tuple(cfg['fog_rgb']), cfg['ratio_max'], cfg['ratio_min'])
+    assert sha(got) == case['sha']['image'], case['id']

@@ -584,6 +584,54 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const uint8_t* __restrict
 }
 
 // ============================================================================================
+// cv.resize(uint8): INTER_LINEAR (11-bit fixed-point coefficients, the 8-bit vertical pass
+// ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2) and INTER_NEAREST (floor(x / scale)).
+// pixelation (photometric/effect.py:58-79) = linear down + nearest up.  Thread per dst pixel.
+// ============================================================================================
+__device__ __forceinline__ void resize_lin_coef(int d, double scale, int sn, int& s0, int& s1,
+                                                int& a0, int& a1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int si = (int)floorf(f);
+    f -= (float)si;
+    if (si < 0) { si = 0; f = 0.f; }
+    if (si >= sn - 1) { si = sn - 1; f = 0.f; }
+    s0 = si;
+    s1 = min(si + 1, sn - 1);
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw,
+                                                        uint8_t* __restrict__ dst, int dh, int dw,
+                                                        double scale_x, double scale_y, int nearest) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    uint8_t* d = dst + ((long long)y * dw + x) * C;
+    if (nearest) {
+        const int sx = min((int)floor((double)x * scale_x), sw - 1);
+        const int sy = min((int)floor((double)y * scale_y), sh - 1);
+        const uint8_t* p = src + ((long long)sy * sw + sx) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) d[c] = p[c];
+        return;
+    }
+    int x0, x1, ax0, ax1, y0, y1, by0, by1;
+    resize_lin_coef(x, scale_x, sw, x0, x1, ax0, ax1);
+    resize_lin_coef(y, scale_y, sh, y0, y1, by0, by1);
+    const uint8_t* r0 = src + (long long)y0 * sw * C;
+    const uint8_t* r1 = src + (long long)y1 * sw * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int s0 = (int)r0[x0 * C + c] * ax0 + (int)r0[x1 * C + c] * ax1;
+        const int s1 = (int)r1[x0 * C + c] * ax0 + (int)r1[x1 * C + c] * ax1;
+        const int v = (((by0 * (s0 >> 4)) >> 16) + ((by1 * (s1 >> 4)) >> 16) + 2) >> 2;
+        d[c] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// ============================================================================================
 // Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
 // over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
 // gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
@@ -1093,4 +1141,26 @@ extern "C" int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int3
     else VKB_LAUNCH_F2D(4);
 #undef VKB_LAUNCH_F2D
     return check_launch("filter2d_kernel");
+}
+
+extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst,
+                             int32_t dst_h, int32_t dst_w, int32_t channels, int32_t interpolation,
+                             void* stream) {
+    VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR,
+                "interpolation must be VKB_INTER_NEAREST or VKB_INTER_LINEAR");
+    // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
+    const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
+    const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
+    dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nearest = interpolation == VKB_INTER_NEAREST;
+    if (channels == 1)
+        resize_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
+    else if (channels == 3)
+        resize_u8_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
+    else
+        resize_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
+    return check_launch("resize_u8_kernel");
 }

@@ -1,13 +1,23 @@
 """Effect ops (vkit/mechanism/distortion/photometric/effect.py): jpeg_quality, pixelation, fog.
-All three are "next" rows of the scope table (libjpeg codec, cv.resize models, sequential
-diamond-square RNG recursion); the config classes exist so policies / configs stay
-interchangeable with the reference."""
+
+pixelation: cv.resize INTER_LINEAR down + INTER_NEAREST up, both bit exact on the device.
+fog: the diamond-square field is drawn on the host from the caller's NumPy generator (it is the
+random field the reference would draw, a few vector operations per level), the blend runs on the
+device.  jpeg_quality stays a "next" row (libjpeg codec)."""
+import ctypes
 from typing import Any, Mapping, Optional, Tuple
 
 import attrs
+import numpy as np
+from numpy.random import Generator as RandomGenerator
+
+from vkit_b200 import _native as nv
+from vkit_b200 import device as dv
+from vkit_b200.element import Image, ImageMode
 
 from ..interface import Distortion, DistortionConfig, DistortionNopState
 from .blur import _next_row
+from .opt import to_original_image, to_rgb_image
 
 
 @attrs.define
@@ -25,9 +35,80 @@ class PixelationConfig(DistortionConfig):
     ratio: float
 
 
+def resize_device(image: Image, resized_height: int, resized_width: int, interpolation: int) -> Image:
+    """cv.resize(image.mat, (w, h), interpolation) for uint8 images, NEAREST / LINEAR."""
+    if image.mat_dtype != np.uint8:
+        raise NotImplementedError('resize is provided for uint8 images')
+    src = image.dev
+    channels = image.num_channels or 1
+    shape = (resized_height, resized_width) + ((channels,) if image.num_channels else ())
+    dst = dv.empty(shape, np.uint8)
+    nv.check(nv.lib().vkb_resize_u8(dv.ptr(src), image.height, image.width, dv.ptr(dst),
+                                    resized_height, resized_width, channels, interpolation,
+                                    dv.stream_ptr()), 'vkb_resize_u8')
+    return attrs.evolve(image, mat=dst)
+
+
+def pixelation_image(config: PixelationConfig, state, image: Image,
+                     rng: Optional[RandomGenerator]):
+    # effect.py:58-79
+    assert 0 < config.ratio < 1
+    small = resize_device(image, round(image.height * config.ratio),
+                          round(image.width * config.ratio), nv.INTER_LINEAR)
+    return resize_device(small, image.height, image.width, nv.INTER_NEAREST)
+
+
 pixelation = Distortion(config_cls=PixelationConfig,
                         state_cls=DistortionNopState[PixelationConfig],
-                        func_image=_next_row('pixelation'))
+                        func_image=pixelation_image)
+
+
+def _midpoint_level(sums: np.ndarray, weight: float, rng: RandomGenerator) -> np.ndarray:
+    """One displacement level: mean of the four neighbours damped by (1 - weight) plus
+    weight * U(0, 1).  The dtype sequence is the reference's (float32 sums, float64 draws)."""
+    return (1 - weight) * sums / 4 + weight * rng.uniform(0, 1, sums.shape)
+
+
+def generate_diamond_square_mask(shape: Tuple[int, int], roughness: float, rng: RandomGenerator):
+    """Diamond-square plasma field cropped to `shape` (effect.py:89-146); consumes `rng` exactly
+    like the reference: 4 corner draws, then per level the diamond draw, the two square draws,
+    and finally the crop offsets."""
+    assert 0.0 <= roughness <= 1.0
+    height, width = shape
+    size = int(2**np.ceil(np.log2(max(height, width))) + 1)
+    field = np.zeros((size, size), dtype=np.float32)
+    for corner in ((0, 0), (0, -1), (-1, -1), (-1, 0)):
+        field[corner] = rng.uniform(0.0, 1.0)
+
+    step, level = size - 1, 0
+    while step >= 2:
+        weight = roughness**level
+        half = step // 2
+        corners = field[0:size:step, 0:size:step]
+        down_pairs = corners + np.roll(corners, shift=-1, axis=0)
+        right_pairs = corners + np.roll(corners, shift=-1, axis=1)
+
+        # centres of the squares
+        centres = _midpoint_level((down_pairs + right_pairs)[:-1, :-1], weight, rng)
+        field[half:size:step, half:size:step] = centres
+
+        # edge midpoints on the corner rows: left/right corners + centres above/below (wrapping)
+        above_below = centres + np.roll(centres, shift=1, axis=0)
+        above_below = np.vstack([above_below, above_below[0]])
+        field[0:size:step, half:size:step] = _midpoint_level(right_pairs[:, :-1] + above_below,
+                                                             weight, rng)
+
+        # edge midpoints on the corner columns
+        left_right = centres + np.roll(centres, shift=1, axis=1)
+        left_right = np.hstack([left_right, left_right[0].reshape(-1, 1)])
+        field[half:size:step, 0:size:step] = _midpoint_level(down_pairs[:-1] + left_right, weight,
+                                                             rng)
+        level += 1
+        step = half
+
+    up = rng.integers(0, size - height + 1)
+    left = rng.integers(0, size - width + 1)
+    return field[up:up + height, left:left + width]
 
 
 @attrs.define
@@ -52,5 +133,49 @@ class FogConfig(DistortionConfig):
         self._rng_state = val
 
 
+def fog_image(config: FogConfig, state, image: Image, rng: Optional[RandomGenerator]):
+    # effect.py:169-208
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    assert rng is not None
+    mask = generate_diamond_square_mask(image.shape, config.roughness, rng)
+    mask -= mask.min()
+    mask /= mask.max()
+    assert config.ratio_min < config.ratio_max
+    if config.ratio_min < 0.0 or config.ratio_max > 1.0:
+        raise NotImplementedError('fog ratios outside [0, 1] are not provided')
+    mask *= (config.ratio_max - config.ratio_min)
+    mask += config.ratio_min
+
+    channels = image.num_channels or 1
+    if image.mode == ImageMode.GRAYSCALE:
+        fog_value = [np.float32(0.2126 * config.fog_rgb[0] + 0.7152 * config.fog_rgb[1]
+                                + 0.0722 * config.fog_rgb[2])]
+    else:
+        assert image.mode == ImageMode.RGB
+        fog_value = [np.float32(v) for v in config.fog_rgb]
+
+    # (1 - mask) * mat + mask * fog in float32, clipped and truncated: the device blend
+    dst = image.dev.clone()
+    alpha = dv.to_device(np.ascontiguousarray(mask, dtype=np.float32))
+    item = nv.BlendItem()
+    item.dst = dst.data_ptr()
+    item.dst_f32 = 0
+    item.channels = channels
+    item.dst_w = image.width
+    item.box_y, item.box_x, item.box_h, item.box_w = 0, 0, image.height, image.width
+    item.value_arr = None
+    for i, v in enumerate(fog_value):
+        item.value_const[i] = float(v)
+    item.mask = None
+    item.alpha_arr = alpha.data_ptr()
+    item.alpha_pitch = image.width
+    item.keep_mode = 0
+    item.alpha = 1.0
+    nv.check(nv.lib().vkb_blend_fill(ctypes.byref(item), dv.stream_ptr()), 'vkb_blend_fill')
+    image = attrs.evolve(image, mat=dst)
+    return to_original_image(image, mode)
+
+
 fog = Distortion(config_cls=FogConfig, state_cls=DistortionNopState[FogConfig],
-                 func_image=_next_row('fog'))
+                 func_image=fog_image)
