@@ -322,6 +322,11 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
 
+/* dst[y, x] = src[pos_y[y, x], pos_x[y, x]] (uint8 HWC): the pixel permutation of glass_blur
+ * (photometric/blur.py:216-264); the index maps are the host-drawn random field. */
+int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                         const int32_t* pos_y, const int32_t* pos_x, void* stream);
+
 /* Noise (photometric/noise.py:25-190).  kind: 0 gaussian (p0 = std), 1 poisson, 2 impulse
  * (p0 = prob_salt, p1 = prob_pepper), 3 speckle (p0 = std).
  * Philox variant: counter-based device RNG keyed by (seed, element index); distributional

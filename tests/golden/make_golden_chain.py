@@ -188,11 +188,15 @@ def effect_cases():
              ('fog', {'roughness': 0.5}, (64, 96)), ('fog', {'roughness': 0.2, 'ratio_max': 0.7,
                                                                'ratio_min': 0.1}, (100, 133)),
              ('fog', {'roughness': 0.9, 'fog_rgb': [10, 20, 250]}, (257, 300)),
-             ('fog', {'roughness': 0.6}, (1024, 1024))]
+             ('fog', {'roughness': 0.6}, (1024, 1024)),
+             ('glass_blur', {'sigma': 0.7}, (64, 96)),
+             ('glass_blur', {'sigma': 1.2, 'delta': 2, 'loop': 3}, (100, 133)),
+             ('glass_blur', {'sigma': 0.9, 'delta': 3, 'loop': 7}, (33, 47)),
+             ('glass_blur', {'sigma': 0.8}, (1024, 1024))]
     for k, (name, cfg, shape) in enumerate(specs):
         seed = 8200 + k
         image, _, _ = make_inputs(seed, shape)
-        rng = np.random.default_rng(seed + 1) if name == 'fog' else None
+        rng = np.random.default_rng(seed + 1) if name in ('fog', 'glass_blur') else None
         r = getattr(distortion, name).distort(cfg, image=Image(mat=image), rng=rng, get_config=True)
         CASES.append({'id': f'ef{k:02d}', 'kind': 'effect', 'op': name, 'config': mg.plain(r.config),
                       'shape': list(shape), 'seed': seed, 'rng_seed': seed + 1 if rng else None,

@@ -748,8 +748,9 @@ def test_filter_blur_vs_reference(vk, case):
 
 @pytest.mark.parametrize('case', chain_cases('effect'), ids=lambda c: f"{c['id']}-{c['op']}")
 def test_effect_vs_reference(vk, case):
-    """pixelation (both cv.resize passes bit exact) and fog (host-drawn diamond-square field from
-    the caller's rng, device blend): sha256 equal to the reference."""
+    """pixelation (both cv.resize passes bit exact), fog (host-drawn diamond-square field from the
+    caller's rng, device blend) and glass_blur (device Gaussian, host-drawn swap maps, device
+    gather): sha256 equal to the reference."""
     element, distortion = vk
     image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
     rng = np.random.default_rng(case['rng_seed']) if case['rng_seed'] is not None else None

@@ -317,6 +317,9 @@ def test_effect_oracle(case):
     cfg = case['config']
     if case['op'] == 'pixelation':
         got = port.pixelation(image, cfg['ratio'])
+    elif case['op'] == 'glass_blur':
+        got = port.glass_blur(image, cfg['sigma'], np.random.default_rng(case['rng_seed']),
+                              cfg['delta'], cfg['loop'])
     else:
         got = port.fog(image, cfg['roughness'], np.random.default_rng(case['rng_seed']),
                        tuple(cfg['fog_rgb']), cfg['ratio_max'], cfg['ratio_min'])

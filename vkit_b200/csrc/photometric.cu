@@ -632,6 +632,21 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
 }
 
 // ============================================================================================
+// mat[pos_y, pos_x]: the pixel permutation of glass_blur (photometric/blur.py:216-264).
+// ============================================================================================
+template <int C>
+__global__ void __launch_bounds__(256) gather_pixels_kernel(const uint8_t* __restrict__ src,
+                                                            uint8_t* __restrict__ dst, long long n, int w,
+                                                            const int32_t* __restrict__ pos_y,
+                                                            const int32_t* __restrict__ pos_x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = src + ((long long)pos_y[i] * w + pos_x[i]) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[i * C + c] = p[c];
+}
+
+// ============================================================================================
 // Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
 // over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
 // gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
@@ -1163,4 +1178,18 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     else
         resize_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
     return check_launch("resize_u8_kernel");
+}
+
+extern "C" int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
+                                    int32_t channels, const int32_t* pos_y, const int32_t* pos_x,
+                                    void* stream) {
+    VKB_REQUIRE(src && dst && pos_y && pos_x && h > 0 && w > 0 && src != dst, "bad arguments");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    const long long n = (long long)h * w;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) gather_pixels_kernel<1><<<blocks, 256, 0, st>>>(src, dst, n, w, pos_y, pos_x);
+    else if (channels == 3) gather_pixels_kernel<3><<<blocks, 256, 0, st>>>(src, dst, n, w, pos_y, pos_x);
+    else gather_pixels_kernel<4><<<blocks, 256, 0, st>>>(src, dst, n, w, pos_y, pos_x);
+    return check_launch("gather_pixels_kernel");
 }

@@ -252,9 +252,50 @@ class GlassBlurConfig(DistortionConfig):
         self._rng_state = val
 
 
+def glass_swap_maps(shape, delta: int, loop: int, rng: RandomGenerator):
+    """The pixel permutation of glass_blur as two index maps (blur.py:232-262): `loop` rounds in
+    which every (2*delta+1)-th pixel trades places with a random neighbour.  Drawn on the host from
+    the caller's generator -- it is the random field of the op; duplicates among the targets
+    resolve like NumPy's fancy assignment (the last writer in C order wins)."""
+    height, width = shape
+    pos_x, pos_y = np.meshgrid(np.arange(width), np.arange(height))
+    period = 2 * delta + 1
+    for _ in range(loop):
+        rows = np.arange(rng.integers(0, period), height - delta, period).reshape(-1, 1)
+        cols = np.arange(rng.integers(0, period), width - delta, period).reshape(1, -1)
+        grid_shape = (rows.shape[0], cols.shape[1])
+        shift_y = rng.integers(-delta, delta + 1, grid_shape)
+        shift_x = rng.integers(-delta, delta + 1, grid_shape)
+        target_y = np.clip(pos_y[rows, cols] + shift_y, 0, height - 1)
+        target_x = np.clip(pos_x[rows, cols] + shift_x, 0, width - 1)
+        for pos in (pos_y, pos_x):
+            at_centre, at_target = pos[rows, cols], pos[target_y, target_x]
+            pos[rows, cols] = at_target
+            pos[target_y, target_x] = at_centre
+    return pos_y, pos_x
+
+
+def glass_blur_image(config: GlassBlurConfig, state, image: Image,
+                     rng: Optional[RandomGenerator]):
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    image = gaussian_blur_device(image, config.sigma)
+    assert rng is not None
+    pos_y, pos_x = glass_swap_maps(image.shape, config.delta, config.loop, rng)
+    src = image.dev
+    dst = dv.empty(tuple(src.shape), np.uint8)
+    py = dv.to_device(np.ascontiguousarray(pos_y, dtype=np.int32))
+    px = dv.to_device(np.ascontiguousarray(pos_x, dtype=np.int32))
+    nv.check(nv.lib().vkb_gather_pixels_u8(dv.ptr(src), dv.ptr(dst), image.height, image.width,
+                                           image.num_channels or 1, dv.ptr(py), dv.ptr(px),
+                                           dv.stream_ptr()), 'vkb_gather_pixels_u8')
+    image = attrs.evolve(image, mat=dst)
+    return to_original_image(image, mode)
+
+
 glass_blur = Distortion(config_cls=GlassBlurConfig,
                         state_cls=DistortionNopState[GlassBlurConfig],
-                        func_image=_next_row('glass_blur'))
+                        func_image=glass_blur_image)
 
 
 @attrs.define
