@@ -44,11 +44,14 @@ def xy(points):
     return np.asarray([(p.smooth_x, p.smooth_y) for p in points], dtype=np.float64)
 
 
-def random_distortion_cases():
+NOT_YET_2 = ['zoom_in_blur', 'jpeg_quality', 'ellipse_streak']
+
+
+def random_distortion_cases(prefix='rd', disabled=NOT_YET, seeds=range(24)):
     shape = (160, 208)
-    rd = random_distortion_factory.create({'disabled_policy_names': NOT_YET,
+    rd = random_distortion_factory.create({'disabled_policy_names': disabled,
                                            'force_post_rotate': True})
-    for seed in range(24):
+    for seed in seeds:
         image, mask, _ = make_inputs(1000 + seed, shape)
         pts = PointList(Point.create(y=y, x=x) for x, y in make_points(1000 + seed, shape, 16))
         polys = [Polygon.from_xy_pairs(p) for p in make_polygons(1000 + seed, shape, 4)]
@@ -56,9 +59,9 @@ def random_distortion_cases():
         rng = np.random.default_rng(seed)
         r = rd.distort(rng, image=Image(mat=image), mask=Mask(mat=mask), points=pts,
                        polygons=polys, debug=debug)
-        cid = f'rd{seed:02d}'
+        cid = f'{prefix}{seed:02d}'
         case = {
-            'id': cid, 'kind': 'random_distortion', 'shape': list(shape), 'seed': 1000 + seed,
+            'id': cid, 'kind': 'random_distortion', 'disabled': list(disabled), 'shape': list(shape), 'seed': 1000 + seed,
             'rng_seed': seed, 'names': list(debug.distortion_names),
             'levels': [int(v) for v in debug.distortion_levels],
             'configs': [mg.plain(c) for c in debug.distortion_configs],
@@ -209,6 +212,7 @@ def main():
     label_cases()
     filter_blur_cases()
     effect_cases()
+    random_distortion_cases('rx', NOT_YET_2, range(100, 124))
     with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)
