@@ -37,8 +37,9 @@ PAGE_SHAPE = (1024, 1024)
 BATCH = 256
 CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold',
               'camera_plane_line_curve')
-# project_camera, project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records, remap
-KERNELS_PER_STEP = 9
+# project_camera, project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records,
+# remap (small-tile launch + large-tile launch)
+KERNELS_PER_STEP = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of grid_remap_kernel, one 32-page launch under
 # `ncu --set full` (profiles/r01_ncu_summary.md): 166.7 MB read + 81.9 MB written / 32 pages
 TRAFFIC_PER_PAGE = 248.5e6 / 32

@@ -160,9 +160,10 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
  *   tile_base:  n_pages + 1 int32, prefix sum of tiles per page (the remap's flat work list)
  *   tile_slots: n_pages x s_cap x VKB_TILE_SLOT_BYTES bytes, opaque (bbox, cell id and the
  *               float32 tile-centred inverse map of every candidate, ascending cell order)
- *   tile_headers: (sum of tiles of all pages) x VKB_TILE_HEADER_BYTES bytes, opaque: the flat
- *               work list of the remap (page, tile origin, record count, first record);
- *               n_pages x t_max entries are always enough */
+ *   tile_headers: n_pages x t_max x VKB_TILE_HEADER_BYTES bytes (the flat work list of the
+ *               remap: page, tile origin, record count, first record) followed by
+ *               (n_pages x t_max + 1) int32 (the list of tiles that take the remap's second
+ *               launch: more than 15 candidates or the exact slow path); opaque */
 #define VKB_TILE_SLOT_BYTES 64
 #define VKB_TILE_HEADER_BYTES 32
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,

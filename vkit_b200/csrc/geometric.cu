@@ -11,6 +11,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
 #include "common.cuh"
 #include "vkb_math.cuh"
 #include "vkb_lattice.cuh"
@@ -482,6 +483,10 @@ struct __align__(16) TileSlot {
 };
 static_assert(sizeof(TileSlot) == VKB_TILE_SLOT_BYTES, "TileSlot layout is part of the ABI");
 
+// Tiles with at most this many candidates resolve their owners once per tile (lane = row, four
+// bit planes); the others go on a separate work list.
+constexpr int kPlaneCands = 15;
+
 // One work item of the persistent remap kernel: a 32 x 32 dst tile (uniform across a warp).
 struct __align__(16) RemapTile {
     int page, tx0, ty0;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     int t_max, int s_cap, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
     const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
     const int32_t* __restrict__ tile_off, const int32_t* __restrict__ tile_base,
-    TileSlot* __restrict__ slots, RemapTile* __restrict__ headers) {
+    TileSlot* __restrict__ slots, RemapTile* __restrict__ headers, int32_t* __restrict__ large) {
     const int page = blockIdx.y;
     const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -586,10 +591,13 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         h.count = usable ? count : -1;
         h.rec = page * s_cap + off;
         h.pad[0] = h.pad[1] = h.pad[2] = 0;
-        int4* __restrict__ dst = reinterpret_cast<int4*>(headers + (tile_base[page] + t));
+        const int index = tile_base[page] + t;
+        int4* __restrict__ dst = reinterpret_cast<int4*>(headers + index);
         const int4* src = reinterpret_cast<const int4*>(&h);
         dst[0] = src[0];
         dst[1] = src[1];
+        // tiles outside the lane-per-row owner path go on the second launch's work list
+        if ((unsigned)h.count > (unsigned)kPlaneCands) large[1 + atomicAdd(large, 1)] = index;
     }
     if (!usable) return;  // the remap takes its slow path
     const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
@@ -848,31 +856,39 @@ __device__ __forceinline__ void cp_async_wait() {
 // starts), so a warp never waits for another warp.
 constexpr int kWarpSlots = 64;
 
-template <int C, bool MASK, bool SCORE, int R>
+// LARGE = false: the tiles with at most kPlaneCands candidates (99.8 % of them), owners resolved
+// once per tile with lane = row; LARGE = true: the remaining tiles (more candidates, or the exact
+// slow path), owners resolved band by band.  Two launches over the same tile list, each skipping
+// the other's tiles, keep both kernels inside the register budget.
+template <int C, bool MASK, bool SCORE, int R, bool LARGE>
 __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_remap_kernel(
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
     int c_max, int p_max, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
     const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
     const RemapTile* __restrict__ headers, const TileSlot* __restrict__ slots,
-    const int32_t* __restrict__ lattice_i) {
+    const int32_t* __restrict__ lattice_i, const int32_t* __restrict__ large) {
     constexpr int kWarps = VKB_TILE / R;
     __shared__ __align__(16) TileSlot sm_all[kWarps][kWarpSlots];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     TileSlot* __restrict__ sm = sm_all[warp];
 
-    // contiguous share of the flat tile list per block, round robin over its warps
-    const int total = tile_base[n_pages];
+    // LARGE = false: contiguous share of the flat tile list per block, round robin over its
+    // warps.  LARGE = true: the (short, clustered) list of large tiles, strided over all warps.
+    const int total = LARGE ? large[0] : tile_base[n_pages];
     const int per = (total + gridDim.x - 1) / gridDim.x;
-    const int w_begin = blockIdx.x * per;
-    const int n_block = min(total, w_begin + per) - w_begin;
-    const int n_tiles = n_block > warp ? (n_block - warp + kWarps - 1) / kWarps : 0;  // of this warp
+    const int w_begin = LARGE ? 0 : blockIdx.x * per;
+    const int n_block = LARGE ? total : min(total, w_begin + per) - w_begin;
+    const int first = LARGE ? blockIdx.x * kWarps + warp : warp;
+    const int stride = LARGE ? gridDim.x * kWarps : kWarps;
+    const int n_tiles = n_block > first ? (n_block - first + stride - 1) / stride : 0;  // of this warp
     if (n_tiles <= 0) return;
 
     auto load_header = [&](int k) {
         RemapTile t;
-        const int4* __restrict__ src = reinterpret_cast<const int4*>(
-            headers + (w_begin + warp + kWarps * min(k, n_tiles - 1)));
+        int index = w_begin + first + stride * min(k, n_tiles - 1);
+        if (LARGE) index = large[1 + index];
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
         t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
         return t;
@@ -900,14 +916,23 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
     const float* __restrict__ src_score = nullptr;
     float* __restrict__ dst_score = nullptr;
 
+    auto mine = [](const RemapTile& t) {
+        return ((unsigned)t.count <= (unsigned)kPlaneCands) != LARGE;
+    };
     for (int k = 0; k < n_tiles; ++k) {
         const RemapTile cur = h0;
+        if (!mine(cur)) {  // the other launch's tile (never staged ahead)
+            h0 = h1;
+            h1 = load_header(k + 2);
+            continue;
+        }
         if (!cur_staged) {
             cur_base = 0;
             stage(cur, 0);
         }
         // the next tile's records go to the other half when both tiles fit a half
-        const bool ahead = k + 1 < n_tiles && cur.count <= kWarpSlots / 2 && h1.count <= kWarpSlots / 2;
+        const bool ahead = k + 1 < n_tiles && mine(h1) && cur.count <= kWarpSlots / 2
+                           && h1.count <= kWarpSlots / 2;
         const int next_base = cur_base ? 0 : kWarpSlots / 2;
         if (ahead) {
             stage(h1, next_base);
@@ -933,6 +958,39 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
         const bool fast = count >= 0;
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
+
+        // ---- owner, whole tile at once: lane = dst row ------------------------------------
+        // Bit plane b of a row holds bit b of (slot + 1) of every pixel's owner (0 = uncovered).
+        // Candidates come in ascending cell order and later ones overwrite earlier ones, exactly
+        // like the reference's cell-by-cell map writes; one coverage word per candidate and row.
+        // Four planes cover tiles with up to 15 candidates (mean 8.7).
+        uint32_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0;
+        constexpr bool planes_ok = !LARGE;
+        if (planes_ok) {
+            const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
+            const int row_y = ty0 + lane;
+            for (int s = 0; s < count; ++s) {
+                const int4 b = *reinterpret_cast<const int4*>(&S[s].x0);  // same for all lanes
+                const int r = row_y - b.y;
+                uint32_t win = 0u;
+                if ((unsigned)r <= (unsigned)b.z) {
+                    if (b.w >= 0) {
+                        const uint32_t wd = __ldg(page_masks + (b.w * VKB_CELL_MASK_WORDS + r));
+                        const int rel = tx0 - b.x;  // |rel| < 32: the bbox overlaps the tile
+                        win = rel >= 0 ? (wd >> rel) : (wd << (-rel));
+                    } else {
+                        win = cell_row_window_slow(lattice_i + (size_t)page * p_max * 2, cols,
+                                                   b.w & 0x7FFFFFFF, row_y, tx0);
+                    }
+                }
+                const uint32_t id = (uint32_t)s + 1u;
+                pl0 = (pl0 & ~win) | (win & (0u - (id & 1u)));
+                pl1 = (pl1 & ~win) | (win & (0u - ((id >> 1) & 1u)));
+                pl2 = (pl2 & ~win) | (win & (0u - ((id >> 2) & 1u)));
+                pl3 = (pl3 & ~win) | (win & (0u - ((id >> 3) & 1u)));
+            }
+        }
+
 #pragma unroll 1
         for (int band = 0; band < kWarps; ++band) {
         const int ry0 = ty0 + band * R;
@@ -946,7 +1004,18 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
             int key[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) key[j] = -1;
-            const int n_cand = fast ? count : (pages[page].rows - 1) * (cols - 1);
+            if (planes_ok) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int row = band * R + j;
+                    uint32_t id = (__shfl_sync(0xffffffffu, pl0, row) >> lane) & 1u;
+                    id |= ((__shfl_sync(0xffffffffu, pl1, row) >> lane) & 1u) << 1;
+                    id |= ((__shfl_sync(0xffffffffu, pl2, row) >> lane) & 1u) << 2;
+                    id |= ((__shfl_sync(0xffffffffu, pl3, row) >> lane) & 1u) << 3;
+                    key[j] = (int)id - 1;
+                }
+            }
+            const int n_cand = planes_ok ? 0 : (fast ? count : (pages[page].rows - 1) * (cols - 1));
             for (int base = 0; base < n_cand; base += 32) {
                 const int s = base + lane;
                 uint32_t win[R];
@@ -1413,6 +1482,10 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     VKB_REQUIRE((long long)n_pages * s_cap < (1ll << 31), "too many tile records in one launch");
     cudaStream_t st = (cudaStream_t)stream;
     VKB_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)n_pages * t_max, st));
+    // the list of large tiles lives behind the headers: [count, tile index ...]
+    int32_t* large = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(tile_headers)
+                                                + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
+    VKB_CUDA(cudaMemsetAsync(large, 0, sizeof(int32_t), st));
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
@@ -1428,7 +1501,7 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     grid_tile_records_kernel<<<dim3((t_max + 3) / 4, n_pages), 128, 0, st>>>(
         pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
         tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
-        reinterpret_cast<RemapTile*>(tile_headers));
+        reinterpret_cast<RemapTile*>(tile_headers), large);
     return check_launch("grid_tile_records_kernel");
 }
 
@@ -1444,6 +1517,29 @@ static int remap_grid_blocks(int blocks_per_sm) {
     return sm_count * blocks_per_sm;
 }
 
+// One side stream + fork / join events per device, created on first use (the only state the
+// library keeps besides the colour tables; work submitted through it is ordered with the
+// caller's stream by the two events, so the call stays stream-ordered for the caller).
+struct RemapSide {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static RemapSide* remap_side() {
+    static RemapSide sides[64];
+    static bool ready[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ready[dev]) {
+        RemapSide s;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sides[dev] = s;
+        ready[dev] = true;
+    }
+    return &sides[dev];
+}
+
 extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
                               int32_t p_max, int32_t c_max, int32_t t_max, int32_t s_cap,
                               const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
@@ -1454,8 +1550,9 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               void* stream) {
     VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
                     && tile_off && tile_base && tile_slots && tile_headers, "bad arguments");
-    (void)t_max;
     (void)s_cap;
+    const int32_t* large = reinterpret_cast<const int32_t*>(
+        reinterpret_cast<const char*>(tile_headers) + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
                     || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
@@ -1464,11 +1561,29 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     constexpr int R = VKB_REMAP_ROWS;
     constexpr int kBlocksPerSm = VKB_REMAP_BLOCKS;
     const int grid = remap_grid_blocks(kBlocksPerSm);
-#define VKB_LAUNCH_REMAP(CH, M, S)                                                             \
-    grid_remap_kernel<CH, M, S, R><<<grid, 32 * (VKB_TILE / R), 0, st>>>(                      \
+#define VKB_LAUNCH_REMAP_1(CH, M, S, LARGE)                                                     \
+    grid_remap_kernel<CH, M, S, R, LARGE><<<grid, 32 * (VKB_TILE / R), 0, st>>>(               \
         planes, pages, n_pages, c_max, p_max, hinv, reinterpret_cast<const int4*>(cell_box),   \
         cell_masks, tile_base, reinterpret_cast<const RemapTile*>(tile_headers),               \
-        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i)
+        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, large)
+    // The few large tiles run on a side stream next to the main launch (disjoint dst tiles):
+    // alone they are a latency-bound tail of ~30 us.
+    RemapSide* side = remap_side();
+    cudaStream_t main_st = st;
+    // fork / launch / join are issued under a lock: the events are shared by all callers
+    static std::mutex side_mutex;
+    std::lock_guard<std::mutex> side_lock(side_mutex);
+    if (side) {
+        VKB_CUDA(cudaEventRecord(side->fork, main_st));
+        VKB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
+#define VKB_LAUNCH_REMAP(CH, M, S)                \
+    do {                                          \
+        st = side ? side->stream : main_st;       \
+        VKB_LAUNCH_REMAP_1(CH, M, S, true);       \
+        st = main_st;                             \
+        VKB_LAUNCH_REMAP_1(CH, M, S, false);      \
+    } while (0)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
     switch (key) {
         case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;
@@ -1489,6 +1604,11 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
         default: VKB_REQUIRE(false, "unsupported container combination");
     }
 #undef VKB_LAUNCH_REMAP
+#undef VKB_LAUNCH_REMAP_1
+    if (side) {
+        VKB_CUDA(cudaEventRecord(side->join, side->stream));
+        VKB_CUDA(cudaStreamWaitEvent(main_st, side->join, 0));
+    }
     return check_launch("grid_remap_kernel");
 }
 
