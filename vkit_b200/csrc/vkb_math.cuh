@@ -454,23 +454,116 @@ VKB_HD long long scan_edge_x(int x0, int y0, int x1, int y1, int y) {
     return (long long)xs * 65536 + dxf * (long long)(y - ya);
 }
 
+// ---------------------------------------------------------------------------------------
+// The same two edge walks split into a per-edge setup and a per-row evaluation, so that code
+// which visits many rows of one edge (grid_masks_kernel: lane = row) pays the divisions and the
+// endpoint bookkeeping once per edge.  edge_row_run == line_row_run and edge_row_cross ==
+// scan_edge_x for every input (tests/test_hostsim.py exercises both through poly_row_mask).
+// ---------------------------------------------------------------------------------------
+struct alignas(16) EdgeConst {
+    int ax, ay, dx, dy;   // left end point, |dx|, |dy| of the outline (left to right)
+    int sy;               // row direction of the outline walk (+1 / -1)
+    int small;            // both deltas below 2048: divisions go through floor_div_small
+    float rcp;            // ~ 1 / (2 * dy)
+    int scan;             // the edge takes part in the scan fill (not horizontal)
+    int ya, yb;           // scan edge active on rows [ya, yb)
+    int pad0, pad1;       // pad0: the slope arithmetic fits 32 bits
+    long long base, dxf;  // 16.16 x at row ya, increment per row
+};
+
+VKB_HD void edge_setup(int x0, int y0, int x1, int y1, EdgeConst& E) {
+    // scan part (direction independent): start at the upper end point; the slope is
+    // trunc(((x1 - x0) << 16) / (y1 - y0)), through the cheapest exact route (see scan_edge_x)
+    E.scan = y0 != y1;
+    E.ya = y0 < y1 ? y0 : y1;
+    E.yb = y0 < y1 ? y1 : y0;
+    const int xs = y0 < y1 ? x0 : x1;
+    E.base = (long long)xs * 65536;
+    {
+        const int ddx = x1 - x0, ddy = y1 - y0;
+        const int adx = ddx < 0 ? -ddx : ddx, ady = ddy < 0 ? -ddy : ddy;
+        E.pad0 = adx < 16384;  // slope and slope * rows fit 32 bits
+        if (!E.scan) {
+            E.dxf = 0;
+        } else if (adx < 128 && ady < 128) {
+            const float rcp = VKB_FRCP_APPROX((float)ady);
+            const int q1 = floor_div_small(adx * 256, ady, rcp);
+            const int r1 = adx * 256 - q1 * ady;
+            const int q = q1 * 256 + floor_div_small(r1 * 256, ady, rcp);
+            E.dxf = ((ddx < 0) != (ddy < 0)) ? -q : q;
+        } else if (adx < 16384) {
+            E.dxf = (ddx * 65536) / ddy;
+        } else {
+            E.dxf = ((long long)ddx * 65536) / (long long)ddy;
+        }
+    }
+    // outline part: cv::LineIterator walks from the left end point
+    if (x0 > x1) {
+        int t = x0; x0 = x1; x1 = t;
+        t = y0; y0 = y1; y1 = t;
+    }
+    E.ax = x0;
+    E.ay = y0;
+    E.dx = x1 - x0;
+    const int dys = y1 - y0;
+    E.sy = dys >= 0 ? 1 : -1;
+    E.dy = dys >= 0 ? dys : -dys;
+    E.small = E.dx < 2048 && E.dy < 2048;
+    E.rcp = E.dy ? VKB_FRCP_APPROX((float)(2 * E.dy)) : 0.f;
+    E.pad1 = 0;
+}
+
+VKB_HD bool edge_row_run(const EdgeConst& E, int y, int& xlo, int& xhi) {
+    const int dx = E.dx, dy = E.dy;
+    const int k = (y - E.ay) * E.sy;  // rows travelled from the start point
+    if (k < 0 || k > dy) return false;
+    if (dy == 0) {  // horizontal (or a single point)
+        xlo = E.ax;
+        xhi = E.ax + dx;
+        return true;
+    }
+    const int den = 2 * dy;
+    if (dy > dx) {  // steep: one pixel per row
+        const int num = 2 * dx * k + dy - 1;
+        const int kx = E.small ? floor_div_small(num, den, E.rcp) : num / den;
+        xlo = xhi = E.ax + kx;
+        return true;
+    }
+    int jlo = 0;
+    if (k > 0) {
+        const int n = 2 * dx * k - dx + 1;
+        jlo = E.small ? floor_div_small(n + den - 1, den, E.rcp) : ceil_div_pos(n, den);
+    }
+    const int n2 = 2 * dx * (k + 1) - dx + 1;
+    int jhi = (E.small ? floor_div_small(n2 + den - 1, den, E.rcp) : ceil_div_pos(n2, den)) - 1;
+    if (jhi > dx) jhi = dx;
+    if (jlo > jhi) return false;
+    xlo = E.ax + jlo;
+    xhi = E.ax + jhi;
+    return true;
+}
+
+VKB_HD bool edge_row_cross(const EdgeConst& E, int y, long long& x) {
+    if (!E.scan || y < E.ya || y >= E.yb) return false;
+    if (E.pad0) x = E.base + (long long)((int)E.dxf * (y - E.ya));
+    else x = E.base + E.dxf * (long long)(y - E.ya);
+    return true;
+}
+
+// coverage of row y from prepared edges; N edges, bits relative to column bx0
 template <int N>
-VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t* words,
-                          int nwords) {
+VKB_HD void poly_row_mask_edges(const EdgeConst* E, int y, int bx0, uint32_t* words, int nwords) {
     long long cross[N];
     int ncross = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const int j = (i + N - 1) % N;
-        const int x0 = px[j], y0 = py[j], x1 = px[i], y1 = py[i];
         int lo, hi;
-        if (line_row_run(x0, y0, x1, y1, y, lo, hi)) {
+        if (edge_row_run(E[i], y, lo, hi)) {
             if (nwords == 1) set_bits1(words[0], lo - bx0, hi - bx0);
             else set_bits(words, nwords, lo - bx0, hi - bx0);
         }
-        if (y0 == y1) continue;
-        const int ya = y0 < y1 ? y0 : y1, yb = y0 < y1 ? y1 : y0;
-        if (ya <= y && y < yb) cross[ncross++] = scan_edge_x(x0, y0, x1, y1, y);
+        long long cx;
+        if (edge_row_cross(E[i], y, cx)) cross[ncross++] = cx;
     }
     // insertion sort (N is 4 for lattice cells)
     for (int i = 1; i < ncross; ++i) {
@@ -490,6 +583,18 @@ VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t
             else set_bits(words, nwords, lo_i, hi_i);
         }
     }
+}
+
+template <int N>
+VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t* words,
+                          int nwords) {
+    EdgeConst E[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int j = (i + N - 1) % N;
+        edge_setup(px[j], py[j], px[i], py[i], E[i]);
+    }
+    poly_row_mask_edges<N>(E, y, bx0, words, nwords);
 }
 
 // ---------------------------------------------------------------------------------------
