@@ -140,10 +140,14 @@ int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                      double* lattice_f, void* stream);
 
 /* Phase 1b: round (half to even), shift to the origin, optional resize_as_src, result shape.
- * lattice_i: n_pages x p_max x 2 int32 (x, y). */
+ * lattice_i: n_pages x p_max x 2 int32 (x, y).
+ * meta_mirror: NULL, or a second copy of `meta` in device-accessible (mapped, pinned) HOST
+ * memory: the host needs the result shapes to allocate the outputs, and a mirror written by the
+ * kernel is readable after a stream synchronise without a D2H copy (which would queue behind
+ * bulk copies on the copy engine). */
 int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                       const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
-                      void* stream);
+                      vkb_grid_meta* meta_mirror, void* stream);
 
 /* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage masks; per dst
  * tile the candidate cells and their records for the remap kernel.

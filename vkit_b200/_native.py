@@ -159,7 +159,7 @@ def _declare(lib):
     lib.vkb_warp_fused.argtypes = [vp, i32, i32, i32, vp]
     lib.vkb_affine_points.argtypes = [POINTER(c_double), i32, vp, vp, i32, i32, vp]
     lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, vp]
-    lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                    vp, vp, vp, vp]
     lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -190,6 +190,10 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     # time before the first copy-out is pure loss)
     first = min(n, max(1, chunk_pages // 4))
     bounds = [(0, first)] + [(a, min(a + chunk_pages, n)) for a in range(first, n, chunk_pages)]
+    # ... and a short last chunk keeps the drain (its kernels + its D2H, nothing to overlap) short
+    a, b = bounds[-1]
+    if b - a > first:
+        bounds[-1:] = [(a, b - first), (b - first, b)]
     ready: 'queue.Queue' = queue.Queue(maxsize=3)
 
     def producer():

@@ -297,7 +297,8 @@ __device__ __forceinline__ int block_reduce_int(int v, int* scratch, bool is_min
 
 __global__ void __launch_bounds__(1024) grid_finalize_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, const double* __restrict__ lattice_f,
-    int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta) {
+    int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta,
+    vkb_grid_meta* __restrict__ meta_mirror) {
     __shared__ int scratch[32];
     const vkb_grid_page& pg = pages[blockIdx.x];
     const int P = pg.rows * pg.cols;
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(1024) grid_finalize_kernel(
         m.status = 0;
         m.n_flagged_cells = 0;
         meta[blockIdx.x] = m;
+        if (meta_mirror) meta_mirror[blockIdx.x] = m;  // mapped pinned host memory: no D2H copy
     }
 }
 
@@ -1472,10 +1474,10 @@ extern "C" int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int
 
 extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                                  const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
-                                 void* stream) {
+                                 vkb_grid_meta* meta_mirror, void* stream) {
     VKB_REQUIRE(pages && lattice_f && lattice_i && meta && n_pages > 0, "bad arguments");
     grid_finalize_kernel<<<n_pages, 1024, 0, (cudaStream_t)stream>>>(pages, p_max, lattice_f,
-                                                                    lattice_i, meta);
+                                                                    lattice_i, meta, meta_mirror);
     return check_launch("grid_finalize_kernel");
 }
 

@@ -61,11 +61,19 @@ class GridBatch:
             self.lattice_f.copy_(dv.to_device(lat))
         nv.check(self.lib.vkb_grid_project(dv.ptr(self.pages_dev), self.n, self.p_max,
                                            dv.ptr(self.lattice_f), stream), 'vkb_grid_project')
+        # result shapes are needed on the host to allocate the outputs: the kernel mirrors them
+        # into pinned host memory (device accessible under UVA), so one stream synchronise is
+        # enough -- a D2H copy would wait behind bulk copies queued on the copy engine
+        t = dv.torch()
+        meta_host = t.empty((self.n * nv.GRID_META_DTYPE.itemsize,), dtype=t.uint8,
+                            pin_memory=True)
         nv.check(self.lib.vkb_grid_finalize(dv.ptr(self.pages_dev), self.n, self.p_max,
                                             dv.ptr(self.lattice_f), dv.ptr(self.lattice_i),
-                                            dv.ptr(self.meta_dev), stream), 'vkb_grid_finalize')
-        # result shapes are needed on the host to allocate outputs: one small D2H per batch
-        self.meta = np.frombuffer(dv.to_host(self.meta_dev).tobytes(), dtype=nv.GRID_META_DTYPE)
+                                            dv.ptr(self.meta_dev),
+                                            ctypes.c_void_p(meta_host.data_ptr()), stream),
+                 'vkb_grid_finalize')
+        t.cuda.current_stream().synchronize()
+        self.meta = np.frombuffer(meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
         self.max_dst_h = int(self.meta['dst_h'].max())
         self.max_dst_w = int(self.meta['dst_w'].max())
         self.tiles_x = (self.max_dst_w + nv.TILE - 1) // nv.TILE
