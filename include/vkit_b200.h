@@ -283,6 +283,10 @@ int vkb_cvt_color(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t co
 #define VKB_OP_COLOR_BALANCE 6    /* f0 ratio */
 #define VKB_OP_PERMUTE 7          /* i0 packed permutation (4 bits per channel) */
 #define VKB_OP_BOUNDARY_EQ 8      /* f0..f2 min per channel, g0..g2 scale per channel, i2 bits */
+/* position dependent ops: LINE_STREAK only through vkb_photo_chain_batched, NOISE only through
+ * vkb_noise_philox_batched */
+#define VKB_OP_NOISE 9            /* i0 kind (vkb_noise_philox), i1 / i2 seed low / high word, f0 p0, f1 p1 */
+#define VKB_OP_LINE_STREAK 10     /* i0 thickness, i1 gap, i2 dash_thickness | dash_gap << 16, i3 bit 0 vert / bit 1 hori, f0 alpha, f1 f2 f3 g0 colour */
 typedef struct vkb_color_op {
     int32_t kind;
     int32_t i0, i1, i2, i3;
@@ -375,6 +379,11 @@ typedef struct vkb_photo_page {
 } vkb_photo_page;
 int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_photo_page* pages_host,
                             int32_t n_pages, int32_t channels, void* stream);
+/* Philox noise over a ragged batch (the batched form of vkb_noise_philox): ops[0] of every page
+ * is a VKB_OP_NOISE record (pages without one are skipped); keyed by (seed, pixel index of the
+ * page), so a page gives the same result alone or in a batch.  In place allowed. */
+int vkb_noise_philox_batched(const vkb_photo_page* pages, int32_t n_pages, int32_t channels,
+                             int32_t blocks_per_page, void* stream);
 /* Per-page channel statistics of the `src` planes of a ragged batch.
  * out (device): per page 3 x uint64 sums, then 3 x uint32 mins, 3 x uint32 maxs (48 bytes). */
 int vkb_channel_stats_batched(const vkb_photo_page* pages, int32_t n_pages, int32_t channels,

@@ -756,3 +756,62 @@ def test_effect_vs_reference(vk, case):
     got = getattr(distortion, case['op']).distort(dict(case['config']),
                                                   image=element.Image(mat=image), rng=rng).image.mat
     assert sha(got) == case['sha']['image'], case['id']
+
+
+def test_batched_chain_noise_and_streak_match_single_page_ops(vk):
+    """Config 5's photometric half as batched passes: mean_shift -> color_shift -> brightness_shift
+    | std_shift | gaussian_blur -> gaussion_noise -> line_streak.  Philox noise is keyed by (seed,
+    pixel index of the page), so the batch equals the per-page Distortion calls bit for bit."""
+    import torch
+    from vkit_b200.batch import PhotometricBatch
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    element, distortion = vk
+    shapes = [(64, 96), (33, 47), (100, 133), (70, 70)]
+    n = len(shapes)
+    rng = np.random.default_rng(21)
+    pages = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in shapes]
+    deltas = [int(v) for v in rng.integers(-50, 50, n)]
+    hues = [int(v) for v in rng.integers(1, 255, n)]
+    lights = [int(v) for v in rng.integers(-60, 60, n)]
+    scales = [float(v) for v in rng.uniform(0.7, 1.4, n)]
+    sigmas = [float(v) for v in rng.uniform(0.5, 1.6, n)]
+    stds = [float(v) for v in rng.uniform(2, 30, n)]
+    seeds = [int(v) for v in rng.integers(0, 2**63 - 1, n)]
+    streaks = [{'thickness': 1 + i % 3, 'gap': 4 + i, 'dash_thickness': 3 * (i % 2),
+                'dash_gap': 2 * (i % 2), 'alpha': 0.3 + 0.2 * i, 'color': [10 * i, 200, 30],
+                'enable_hori': i != 1} for i in range(n)]
+    stages = [
+        ('mean_shift', [{'delta': d} for d in deltas]),
+        ('color_shift', [{'delta': d} for d in hues]),
+        ('brightness_shift', [{'delta': d, 'intermediate_image_mode': 'hsv'} for d in lights]),
+        ('std_shift', [{'scale': s} for s in scales]),
+        ('gaussian_blur', [{'sigma': s} for s in sigmas]),
+        ('gaussion_noise', [{'std': s} for s in stds], seeds),
+        ('line_streak', streaks),
+    ]
+    arena = torch.from_numpy(np.concatenate([p.reshape(-1) for p in pages])).cuda()
+    photo = PhotometricBatch(shapes, 3, stages)
+    result = photo.run(arena).cpu().numpy()
+
+    class _FixedSeed:
+        def __init__(self, seed):
+            self.seed = seed
+
+        def integers(self, *args, **kwargs):
+            return self.seed
+
+    noise_mod.use_host_field(False)
+    for i, page in enumerate(pages):
+        img = element.Image(mat=page)
+        img = distortion.mean_shift.distort({'delta': deltas[i]}, image=img).image
+        img = distortion.color_shift.distort({'delta': hues[i]}, image=img).image
+        img = distortion.brightness_shift.distort(
+            {'delta': lights[i], 'intermediate_image_mode': 'hsv'}, image=img).image
+        img = distortion.std_shift.distort({'scale': scales[i]}, image=img).image
+        img = distortion.gaussian_blur.distort({'sigma': sigmas[i]}, image=img).image
+        img = noise_mod.gaussion_noise_image(noise_mod.GaussionNoiseConfig(std=stds[i]), None, img,
+                                             _FixedSeed(seeds[i]))
+        img = distortion.line_streak.distort(streaks[i], image=element.Image(mat=img.mat)).image
+        a = int(photo.pixel_offsets[i]) * 3
+        got = result[a:a + page.size].reshape(page.shape)
+        assert np.array_equal(got, img.mat), (i, shapes[i], _diff_report(got, img.mat))

@@ -108,7 +108,7 @@ class Rect(ctypes.Structure):
 (CVT_RGB2HSV, CVT_HSV2RGB, CVT_RGB2HSL, CVT_HSL2RGB, CVT_RGB2GRAY, CVT_GRAY2RGB, CVT_RGBA2RGB,
  CVT_RGB2RGBA, CVT_GRAY2RGBA, CVT_RGBA2GRAY) = range(10)
 (OP_MEAN_SHIFT, OP_HUE_SHIFT_RGB, OP_LIGHT_SHIFT_RGB, OP_STD_SHIFT, OP_COMPLEMENT, OP_POSTERIZE,
- OP_COLOR_BALANCE, OP_PERMUTE, OP_BOUNDARY_EQ) = range(9)
+ OP_COLOR_BALANCE, OP_PERMUTE, OP_BOUNDARY_EQ, OP_NOISE, OP_LINE_STREAK) = range(11)
 MAX_COLOR_OPS = 8
 INTER_NEAREST, INTER_LINEAR = 0, 1
 NOISE_GAUSSIAN, NOISE_POISSON, NOISE_IMPULSE, NOISE_SPECKLE = range(4)
@@ -188,6 +188,7 @@ def _declare(lib):
     lib.vkb_fill_polygons.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]
     lib.vkb_photo_chain_batched.argtypes = [vp, vp, i32, i32, vp]
     lib.vkb_channel_stats_batched.argtypes = [vp, i32, i32, vp, vp]
+    lib.vkb_noise_philox_batched.argtypes = [vp, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name).restype = c_int32
 
@@ -198,7 +199,7 @@ EXPORTS = (
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks', 'vkb_photo_chain_batched',
-    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_gather_pixels_u8',
+    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched',
 )
 
 

@@ -345,17 +345,51 @@ def _stage_ops(name: str, config, channels: int, stats):
             return []
         return [make_op(nv.OP_BOUNDARY_EQ, i2=active, f0=mn[0], f1=mn[1], f2=mn[2], g0=sc[0],
                         g1=sc[1], g2=sc[2])]
+    if name == 'line_streak':
+        from .mechanism.distortion.photometric import streak as _streak
+        config = dyn_structure(config, _streak.LineStreakConfig)
+        alpha = _streak._check_alpha(config.alpha)
+        if alpha == 0.0 or not (config.enable_vert or config.enable_hori):
+            return []
+        color = list(config.color) if channels > 1 else [config.color[0]]
+        color = [float(np.uint8(c)) for c in color] + [0.0] * 4
+        return [make_op(nv.OP_LINE_STREAK, i0=config.thickness, i1=config.gap,
+                        i2=(config.dash_thickness & 0xFFFF) | ((config.dash_gap & 0xFFFF) << 16),
+                        i3=int(config.enable_vert) | (int(config.enable_hori) << 1), f0=alpha,
+                        f1=color[0], f2=color[1], f3=color[2], g0=color[3])]
     raise NotImplementedError(f'{name} has no batched form')
 
 
+def _noise_op(name: str, config, seed: int):
+    """VKB_OP_NOISE record of one page (photometric/noise.py), Philox mode."""
+    from .mechanism.distortion.photometric import noise as _noise
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    lo, hi = seed & 0xFFFFFFFF, seed >> 32
+    lo = lo - (1 << 32) if lo >= (1 << 31) else lo
+    hi = hi - (1 << 32) if hi >= (1 << 31) else hi
+    if name == 'gaussion_noise':
+        config = dyn_structure(config, _noise.GaussionNoiseConfig)
+        return make_op(nv.OP_NOISE, i0=nv.NOISE_GAUSSIAN, i1=lo, i2=hi, f0=config.std)
+    if name == 'poisson_noise':
+        return make_op(nv.OP_NOISE, i0=nv.NOISE_POISSON, i1=lo, i2=hi)
+    if name == 'impulse_noise':
+        config = dyn_structure(config, _noise.ImpulseNoiseConfig)
+        return make_op(nv.OP_NOISE, i0=nv.NOISE_IMPULSE, i1=lo, i2=hi, f0=config.prob_salt,
+                       f1=config.prob_pepper)
+    config = dyn_structure(config, _noise.SpeckleNoiseConfig)
+    return make_op(nv.OP_NOISE, i0=nv.NOISE_SPECKLE, i1=lo, i2=hi, f0=config.std)
+
+
 _STATS_STAGES = ('std_shift', 'boundary_equalization')
+_NOISE_STAGES = ('gaussion_noise', 'poisson_noise', 'impulse_noise', 'speckle_noise')
 
 
 class PhotometricBatch:
     """A chain of photometric stages over a ragged batch of uint8 pages (RGB or GRAYSCALE), every
     page with its own configs: `stages` = [(name, configs)], name one of gaussian_blur,
     mean_shift, color_shift, brightness_shift, std_shift, boundary_equalization, complement,
-    posterization, color_balance.
+    posterization, color_balance, line_streak, and the four noises as (name, configs, seeds) with
+    one Philox seed per page (what the per-page op draws from its rng).
 
     Consecutive stages are folded into passes of the fused kernel (`vkb_photo_chain_batched`):
     a pass is an optional Gaussian blur followed by up to 8 per-pixel ops; a new pass starts at
@@ -365,10 +399,15 @@ class PhotometricBatch:
         self.shapes = [(int(h), int(w)) for h, w in shapes]
         self.n = len(self.shapes)
         self.channels = channels
-        self.stages = [(name, list(configs)) for name, configs in stages]
-        for name, configs in self.stages:
-            if len(configs) != self.n:
-                raise ValueError(f'stage {name}: one config per page expected')
+        self.stages = []
+        for stage in stages:
+            name, configs = stage[0], list(stage[1])
+            seeds = list(stage[2]) if len(stage) > 2 else None
+            if len(configs) != self.n or (seeds is not None and len(seeds) != self.n):
+                raise ValueError(f'stage {name}: one config (and seed) per page expected')
+            if name in _NOISE_STAGES and seeds is None:
+                raise ValueError(f'stage {name}: (name, configs, seeds) expected')
+            self.stages.append((name, configs, seeds))
         sizes = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
         self.pixel_offsets = np.concatenate([[0], np.cumsum(sizes)])
         self.launches = 0
@@ -438,7 +477,23 @@ class PhotometricBatch:
             rec = self._new_pass()
             dirty = False
 
-        for name, configs in self.stages:
+        for name, configs, seeds in self.stages:
+            if name in _NOISE_STAGES:
+                flush()
+                for i, (config, seed) in enumerate(zip(configs, seeds)):
+                    op = _noise_op(name, config, seed)
+                    rec['ops'][i, 0] = np.frombuffer(bytes(op), dtype=nv.COLOR_OP_DTYPE)[0]
+                    rec['n_ops'][i] = 1
+                base = self.pixel_offsets[:-1].astype(np.uint64) * np.uint64(self.channels)
+                rec['src'] = np.uint64(cur.data_ptr()) + base
+                rec['dst'] = rec['src']
+                rec_dev = dv.upload_structs(rec)
+                nv.check(nv.lib().vkb_noise_philox_batched(dv.ptr(rec_dev), self.n, self.channels,
+                                                           64, dv.stream_ptr()),
+                         'vkb_noise_philox_batched')
+                self.launches += 1
+                rec = self._new_pass()
+                continue
             if name == 'gaussian_blur':
                 flush()
                 for i, config in enumerate(configs):

@@ -173,8 +173,66 @@ __device__ __forceinline__ void stage_hsv_tables(HsvTables& sm, int tid, int n_t
 }
 static_assert(sizeof(HsvTables) == 512 * sizeof(int), "HsvTables: two 256-entry tables");
 
+// photometric/noise.py:25-190 with the counter-based generator of vkb_noise_philox: keyed by
+// (seed, pixel index), so a page gives the same result alone or in a batch.  Out of line: the
+// Philox state and the double arithmetic stay out of the fused chain kernel (registers): noise
+// is its own batched pass (noise_philox_batched_kernel).
+__device__ __forceinline__ void noise_op(const vkb_color_op& op, int* px, int channels, long long i) {
+    const unsigned long long seed =
+        (unsigned long long)(unsigned)op.i1 | ((unsigned long long)(unsigned)op.i2 << 32);
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)i, 0, &st);
+    const double p0 = (double)op.f0, p1 = (double)op.f1;
+    if (op.i0 == 2) {
+        const double u = curand_uniform_double(&st);
+        const double presv = 1.0 - p0 - p1;
+        for (int c = 0; c < channels; ++c) px[c] = u < presv ? px[c] : (u < presv + p0 ? 255 : 0);
+        return;
+    }
+    for (int c = 0; c < channels; ++c) {
+        const int v = px[c];
+        if (op.i0 == 0) {
+            px[c] = clip_u8(v + (int)rint((double)curand_normal(&st) * p0));
+        } else if (op.i0 == 1) {
+            px[c] = clip_u8((int)curand_poisson(&st, (double)v));
+        } else {
+            const double r = (double)v + (double)v * ((double)curand_normal(&st) * p0);
+            px[c] = (int)fmin(fmax(r, 0.0), 255.0);
+        }
+    }
+}
+
+// photometric/streak.py:44-106: periodic lines with dashes, vertical mask blended first,
+// horizontal second (crossings get alpha twice).  Only compiled into the POS variant of the chain
+// kernel, so the common chains keep their register budget.
+__device__ __forceinline__ void line_streak_op(const vkb_color_op& op, int* px, int channels, int x,
+                                               int y) {
+    const int thickness = op.i0, step = op.i0 + op.i1;
+    const int dash_t = op.i2 & 0xFFFF, dash_g = (op.i2 >> 16) & 0xFFFF;
+    const bool dashed = dash_t > 0 && dash_g > 0;
+    const bool vert = (op.i3 & 1) && (x % step) < thickness
+                      && !(dashed && (y % (dash_t + dash_g)) < dash_g);
+    const bool hori = (op.i3 & 2) && (y % step) < thickness
+                      && !(dashed && (x % (dash_t + dash_g)) < dash_g);
+    const float col[4] = {op.f1, op.f2, op.f3, op.g0};
+    for (int rep = 0; rep < 2; ++rep) {
+        if (!(rep == 0 ? vert : hori)) continue;
+        for (int c = 0; c < channels; ++c) {
+            if (op.f0 >= 1.0f) px[c] = (int)col[c];
+            else px[c] = (int)blend_f32((float)px[c], col[c], op.f0);
+        }
+    }
+}
+
+// (x, y): position inside the page, i: linear pixel index of the page (position dependent ops)
+template <bool POS = false>
 __device__ __forceinline__ void apply_color_op(const vkb_color_op& op, int* px, int channels,
-                                               const HsvTables& tables) {
+                                               const HsvTables& tables, int x = 0, int y = 0,
+                                               long long i = 0) {
+    if (POS && op.kind == VKB_OP_LINE_STREAK) {
+        line_streak_op(op, px, channels, x, y);
+        return;
+    }
     switch (op.kind) {
         case VKB_OP_MEAN_SHIFT: {
             for (int c = 0; c < channels; ++c) {
@@ -690,7 +748,7 @@ __device__ __forceinline__ void hblur4(const uint32_t* __restrict__ w, const int
     }
 }
 
-template <int C, int R>
+template <int C, int R, bool POS>
 __device__ __forceinline__ void chain_tile(const vkb_photo_page& pg, unsigned char* smem,
                                            const int* __restrict__ taps,
                                            const uint32_t* __restrict__ wev,
@@ -788,12 +846,14 @@ __device__ __forceinline__ void chain_tile(const vkb_photo_page& pg, unsigned ch
             pb[c] = (int)(acc_b >> 16);
         }
         if (x < w && ya < h) {
-            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], pa, C, tables);
+            for (int k = 0; k < n_ops; ++k)
+                apply_color_op<POS>(pg.ops[k], pa, C, tables, x, ya, (long long)ya * w + x);
             uint8_t* d = dst + ((long long)ya * w + x) * C;
 #pragma unroll
             for (int c = 0; c < C; ++c) d[c] = (uint8_t)pa[c];
             if (ya + 1 < h) {
-                for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], pb, C, tables);
+                for (int k = 0; k < n_ops; ++k)
+                    apply_color_op<POS>(pg.ops[k], pb, C, tables, x, ya + 1, (long long)(ya + 1) * w + x);
                 d += (long long)w * C;
 #pragma unroll
                 for (int c = 0; c < C; ++c) d[c] = (uint8_t)pb[c];
@@ -802,7 +862,7 @@ __device__ __forceinline__ void chain_tile(const vkb_photo_page& pg, unsigned ch
     }
 }
 
-template <int C>
+template <int C, bool POS>
 __global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* __restrict__ pages) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int taps[17];
@@ -831,7 +891,7 @@ __global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* 
             int px[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < C; ++c) px[c] = src[i * C + c];
-            for (int k = 0; k < n_ops; ++k) apply_color_op(pg.ops[k], px, C, tables);
+            for (int k = 0; k < n_ops; ++k) apply_color_op<POS>(pg.ops[k], px, C, tables, x, y, i);
 #pragma unroll
             for (int c = 0; c < C; ++c) dst[i * C + c] = (uint8_t)px[c];
         }
@@ -848,14 +908,14 @@ __global__ void __launch_bounds__(256) photo_chain_kernel(const vkb_photo_page* 
     }
     __syncthreads();
     switch (r) {
-        case 1: chain_tile<C, 1>(pg, smem, taps, wev, wod, tables); break;
-        case 2: chain_tile<C, 2>(pg, smem, taps, wev, wod, tables); break;
-        case 3: chain_tile<C, 3>(pg, smem, taps, wev, wod, tables); break;
-        case 4: chain_tile<C, 4>(pg, smem, taps, wev, wod, tables); break;
-        case 5: chain_tile<C, 5>(pg, smem, taps, wev, wod, tables); break;
-        case 6: chain_tile<C, 6>(pg, smem, taps, wev, wod, tables); break;
-        case 7: chain_tile<C, 7>(pg, smem, taps, wev, wod, tables); break;
-        default: chain_tile<C, 8>(pg, smem, taps, wev, wod, tables); break;
+        case 1: chain_tile<C, 1, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 2: chain_tile<C, 2, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 3: chain_tile<C, 3, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 4: chain_tile<C, 4, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 5: chain_tile<C, 5, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 6: chain_tile<C, 6, POS>(pg, smem, taps, wev, wod, tables); break;
+        case 7: chain_tile<C, 7, POS>(pg, smem, taps, wev, wod, tables); break;
+        default: chain_tile<C, 8, POS>(pg, smem, taps, wev, wod, tables); break;
     }
 }
 
@@ -871,6 +931,21 @@ static size_t chain_smem_bytes(int r) {
         case 6: return ChainGeom<C, 6>::SMEM;
         case 7: return ChainGeom<C, 7>::SMEM;
         default: return ChainGeom<C, 8>::SMEM;
+    }
+}
+
+// noise over a ragged batch: ops[0] of every page carries VKB_OP_NOISE (or the page is skipped)
+__global__ void __launch_bounds__(256) noise_philox_batched_kernel(const vkb_photo_page* __restrict__ pages,
+                                                                   int channels) {
+    const vkb_photo_page& pg = pages[blockIdx.y];
+    if (pg.n_ops < 1 || pg.ops[0].kind != VKB_OP_NOISE) return;
+    const long long n = (long long)pg.h * pg.w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        int px[4] = {0, 0, 0, 0};
+        for (int c = 0; c < channels; ++c) px[c] = pg.src[i * channels + c];
+        noise_op(pg.ops[0], px, channels, i);
+        for (int c = 0; c < channels; ++c) pg.dst[i * channels + c] = (uint8_t)px[c];
     }
 }
 
@@ -1041,6 +1116,10 @@ extern "C" int vkb_noise_philox(const uint8_t* src, uint8_t* dst, int64_t n_pixe
                                 int32_t kind, double p0, double p1, uint64_t seed, void* stream) {
     VKB_REQUIRE(src && dst && kind >= 0 && kind <= 3 && channels >= 1 && channels <= 4, "bad arguments");
     if (n_pixels <= 0) return VKB_OK;
+    // parameters in float32 precision, like the op records of the batched form: a page gets the
+    // same noise alone or in a batch
+    p0 = (double)(float)p0;
+    p1 = (double)(float)p1;
     noise_philox_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         src, dst, n_pixels, channels, kind, p0, p1, seed);
     return check_launch("noise_philox_kernel");
@@ -1095,6 +1174,7 @@ extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_ph
     VKB_REQUIRE(pages && pages_host && n_pages > 0 && n_pages <= 65535, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     int max_h = 0, max_w = 0, max_r = 0;
+    bool pos = false;  // some page carries a position dependent op
     for (int i = 0; i < n_pages; ++i) {
         const vkb_photo_page& p = pages_host[i];
         VKB_REQUIRE(p.src && p.dst && p.h > 0 && p.w > 0, "page without planes");
@@ -1107,18 +1187,25 @@ extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_ph
         max_h = p.h > max_h ? p.h : max_h;
         max_w = p.w > max_w ? p.w : max_w;
         max_r = p.blur_radius > max_r ? p.blur_radius : max_r;
+        for (int k = 0; k < p.n_ops; ++k) {
+            VKB_REQUIRE(p.ops[k].kind != VKB_OP_NOISE, "noise runs through vkb_noise_philox_batched");
+            pos = pos || p.ops[k].kind == VKB_OP_LINE_STREAK;
+        }
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(st);
     if (rc) return rc;
     dim3 grid((max_w + 31) / 32, (max_h + 31) / 32, n_pages);
     VKB_REQUIRE(grid.y <= 65535, "page too tall");
-    if (channels == 1)
-        photo_chain_kernel<1><<<grid, dim3(32, 8), chain_smem_bytes<1>(max_r), st>>>(pages);
-    else if (channels == 3)
-        photo_chain_kernel<3><<<grid, dim3(32, 8), chain_smem_bytes<3>(max_r), st>>>(pages);
-    else
-        photo_chain_kernel<4><<<grid, dim3(32, 8), chain_smem_bytes<4>(max_r), st>>>(pages);
+#define VKB_LAUNCH_CHAIN(CH)                                                                          \
+    do {                                                                                              \
+        if (pos) photo_chain_kernel<CH, true><<<grid, dim3(32, 8), chain_smem_bytes<CH>(max_r), st>>>(pages); \
+        else photo_chain_kernel<CH, false><<<grid, dim3(32, 8), chain_smem_bytes<CH>(max_r), st>>>(pages);    \
+    } while (0)
+    if (channels == 1) VKB_LAUNCH_CHAIN(1);
+    else if (channels == 3) VKB_LAUNCH_CHAIN(3);
+    else VKB_LAUNCH_CHAIN(4);
+#undef VKB_LAUNCH_CHAIN
     return check_launch("photo_chain_kernel");
 }
 
@@ -1192,4 +1279,13 @@ extern "C" int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h,
     else if (channels == 3) gather_pixels_kernel<3><<<blocks, 256, 0, st>>>(src, dst, n, w, pos_y, pos_x);
     else gather_pixels_kernel<4><<<blocks, 256, 0, st>>>(src, dst, n, w, pos_y, pos_x);
     return check_launch("gather_pixels_kernel");
+}
+
+extern "C" int vkb_noise_philox_batched(const vkb_photo_page* pages, int32_t n_pages,
+                                        int32_t channels, int32_t blocks_per_page, void* stream) {
+    VKB_REQUIRE(pages && n_pages > 0 && n_pages <= 65535, "bad arguments");
+    VKB_REQUIRE(channels >= 1 && channels <= 4 && blocks_per_page > 0, "bad arguments");
+    noise_philox_batched_kernel<<<dim3(blocks_per_page, n_pages), 256, 0, (cudaStream_t)stream>>>(
+        pages, channels);
+    return check_launch("noise_philox_batched_kernel");
 }
