@@ -815,3 +815,57 @@ def test_batched_chain_noise_and_streak_match_single_page_ops(vk):
         a = int(photo.pixel_offsets[i]) * 3
         got = result[a:a + page.size].reshape(page.shape)
         assert np.array_equal(got, img.mat), (i, shapes[i], _diff_report(got, img.mat))
+
+
+def test_config5_chain_fully_batched_mixed_resolution(vk):
+    """BASELINE config 5's 10-op chain over a MIXED-RESOLUTION batch (256 / 512 / 1024 px pages with
+    the golden configs) as batched passes only -- PhotometricBatch (ragged), GeometricBatch twice
+    (the second on ragged inputs), AffineBatch -- equals the per-page Distortion calls bit for bit
+    (Philox noise with the same seeds on both sides)."""
+    import torch
+    from vkit_b200.batch import AffineBatch, GeometricBatch, PhotometricBatch
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    element, distortion = vk
+    cases = chain_cases('fixed_chain')
+    shapes = [tuple(c['shape']) for c in cases]
+    pages = [make_inputs(c['seed'], tuple(c['shape']))[0] for c in cases]
+    ops = cases[0]['ops']
+    cfg = {name: [product_config_for(name, c['configs'][k]) for c in cases]
+           for k, name in enumerate(ops)}
+    seeds = [1234567 + 17 * i for i in range(len(cases))]
+
+    arena = torch.from_numpy(np.concatenate([p.reshape(-1) for p in pages])).cuda()
+    photo = PhotometricBatch(shapes, 3, [
+        ('mean_shift', cfg['mean_shift']), ('color_shift', cfg['color_shift']),
+        ('brightness_shift', cfg['brightness_shift']), ('std_shift', cfg['std_shift']),
+        ('gaussian_blur', cfg['gaussian_blur']), ('gaussion_noise', cfg['gaussion_noise'], seeds),
+        ('line_streak', cfg['line_streak'])])
+    arena = photo.run(arena)
+    out = GeometricBatch(['camera_cubic_curve'] * len(cases), cfg['camera_cubic_curve'],
+                         shapes).run(arena, channels=3)
+    out = GeometricBatch(['similarity_mls'] * len(cases), cfg['similarity_mls'],
+                         out.shapes).run(out.image_arena, channels=3)
+    out = AffineBatch(['rotate'] * len(cases), cfg['rotate'], out.shapes).run(out.image_arena,
+                                                                              channels=3)
+
+    class _FixedSeed:
+        def __init__(self, seed):
+            self.seed = seed
+
+        def integers(self, *args, **kwargs):
+            return self.seed
+
+    noise_mod.use_host_field(False)
+    for i, case in enumerate(cases):
+        img = element.Image(mat=pages[i])
+        for name in ops:
+            if name == 'gaussion_noise':
+                img = noise_mod.gaussion_noise_image(
+                    noise_mod.GaussionNoiseConfig(**cfg[name][i]), None, img, _FixedSeed(seeds[i]))
+                img = element.Image(mat=img.mat)
+            else:
+                img = getattr(distortion, name).distort(cfg[name][i], image=img).image
+        assert out.shapes[i] == tuple(img.shape), (case['id'], out.shapes[i], img.shape)
+        assert list(out.shapes[i]) == case['stage_shapes'][-1]
+        got = out.image(i).cpu().numpy()
+        assert np.array_equal(got, img.mat), (case['id'], _diff_report(got, img.mat))

@@ -75,14 +75,22 @@ class BatchOutput:
 class GeometricBatch:
     """A batch of same-size pages, each with its own grid-op config."""
 
-    def __init__(self, op_names: Sequence[str], configs: Sequence, shape: Tuple[int, int]):
-        self.shape = tuple(shape)
-        keepalive = []
+    def __init__(self, op_names: Sequence[str], configs: Sequence, shape):
+        """`shape`: (H, W) shared by all pages, or one (H, W) per page (ragged input, e.g. the
+        output of a previous geometric batch)."""
         self.n = len(op_names)
+        if len(shape) == 2 and not isinstance(shape[0], (tuple, list)):
+            self.shapes = [(int(shape[0]), int(shape[1]))] * self.n
+        else:
+            self.shapes = [(int(h), int(w)) for h, w in shape]
+            if len(self.shapes) != self.n:
+                raise ValueError('one shape per page expected')
+        self.shape = self.shapes[0]
+        keepalive = []
         self.pages = np.zeros(self.n, dtype=nv.GRID_PAGE_DTYPE)
         handle_sink = []
         for i, (op_name, config) in enumerate(zip(op_names, configs)):
-            _, keep = grid_page_record(op_name, config, self.shape, out=self.pages[i],
+            _, keep = grid_page_record(op_name, config, self.shapes[i], out=self.pages[i],
                                        handle_sink=handle_sink)
             if keep is not None:
                 keepalive.append(keep)
@@ -99,43 +107,50 @@ class GeometricBatch:
         return self.plan
 
     def run(self, images=None, masks=None, score_maps=None, replan: bool = True,
-            launch_events=None) -> BatchOutput:
+            launch_events=None, channels: Optional[int] = None) -> BatchOutput:
         """images: (B, H, W, C) uint8, masks: (B, H, W) uint8, score_maps: (B, H, W) float32 --
-        CUDA tensors (any subset).  Returns ragged outputs in fresh arenas.
+        CUDA tensors (any subset); or, for ragged pages, flat arenas that hold the pages back to
+        back in page order (`channels` then names the image's channel count).  Returns ragged
+        outputs in fresh arenas.
         `launch_events`: optional list; a (start, end) pair of CUDA events recorded immediately
         around the fused remap launch is appended (kernel time without host work)."""
         if replan or self.plan is None:
             self.plan_batch()
         plan = self.plan
-        height, width = self.shape
         shapes = [plan.result_shape(i) for i in range(self.n)]
         pixels = np.asarray([h * w for h, w in shapes], dtype=np.int64)
         offsets = np.concatenate([[0], np.cumsum(pixels)])
         total = int(offsets[-1])
+        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
+        src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
         planes = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
-        planes['src_h'], planes['src_w'] = height, width
+        planes['src_h'] = [s[0] for s in self.shapes]
+        planes['src_w'] = [s[1] for s in self.shapes]
         planes['dst_h'] = [s[0] for s in shapes]
         planes['dst_w'] = [s[1] for s in shapes]
         image_arena = mask_arena = score_arena = None
-        channels = 0
         if images is not None:
-            channels = 1 if images.dim() == 3 else int(images.shape[3])
+            if channels is None:
+                channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
+                                                        else None)
+            if channels is None:
+                raise ValueError('flat image arenas need `channels`')
+            if int(images.numel()) != int(src_pixels.sum()) * channels:
+                raise ValueError('images do not hold the pages of this batch')
             image_arena = dv.empty((total * channels,), np.uint8)
-            base = images.data_ptr()
-            planes['src_image'] = base + np.arange(self.n, dtype=np.uint64) * np.uint64(
-                height * width * channels)
+            planes['src_image'] = np.uint64(images.data_ptr()) + src_offsets * np.uint64(channels)
             planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
                 np.uint64)
             planes['image_channels'] = channels
+        else:
+            channels = 0
         if masks is not None:
             mask_arena = dv.empty((total,), np.uint8)
-            planes['src_mask'] = masks.data_ptr() + np.arange(self.n, dtype=np.uint64) * np.uint64(
-                height * width)
+            planes['src_mask'] = np.uint64(masks.data_ptr()) + src_offsets
             planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
         if score_maps is not None:
             score_arena = dv.empty((total,), np.float32)
-            planes['src_score'] = score_maps.data_ptr() + np.arange(
-                self.n, dtype=np.uint64) * np.uint64(height * width * 4)
+            planes['src_score'] = np.uint64(score_maps.data_ptr()) + src_offsets * np.uint64(4)
             planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
         plan.remap(planes, launch_events=launch_events)
         return BatchOutput(shapes, channels, image_arena, mask_arena, score_arena, offsets)
@@ -145,9 +160,105 @@ class GeometricBatch:
         """Compulsory traffic of the batch: every source pixel read once, every destination
         pixel written once."""
         per_px = channels + (1 if with_mask else 0) + (4 if with_score else 0)
-        height, width = self.shape
+        src = sum(h * w for h, w in self.shapes)
         dst = sum(h * w for h, w in (self.plan.result_shape(i) for i in range(self.n)))
-        return per_px * (self.n * height * width + dst)
+        return per_px * (src + dst)
+
+
+_AFFINE_STATES = None
+
+
+def _affine_states():
+    global _AFFINE_STATES
+    if _AFFINE_STATES is None:
+        from .mechanism.distortion.geometric import affine as _affine
+        _AFFINE_STATES = {
+            'shear_hori': (_affine.ShearHoriConfig, _affine.ShearHoriState),
+            'shear_vert': (_affine.ShearVertConfig, _affine.ShearVertState),
+            'rotate': (_affine.RotateConfig, _affine.RotateState),
+            'skew_hori': (_affine.SkewHoriConfig, _affine.SkewHoriState),
+            'skew_vert': (_affine.SkewVertConfig, _affine.SkewVertState),
+        }
+    return _AFFINE_STATES
+
+
+class AffineBatch:
+    """rotate / shear_* / skew_* over a (possibly ragged) batch of pages in ONE launch of
+    `vkb_warp_fused`: per-page forward matrix and dsize from the reference's state classes
+    (geometric/affine.py:92-395), per-page inverse in the parameter block, ragged output arena."""
+
+    def __init__(self, op_names: Sequence[str], configs: Sequence, shape):
+        from .mechanism.distortion.geometric._hostmath import invert_affine
+        self.n = len(op_names)
+        if len(shape) == 2 and not isinstance(shape[0], (tuple, list)):
+            self.shapes = [(int(shape[0]), int(shape[1]))] * self.n
+        else:
+            self.shapes = [(int(h), int(w)) for h, w in shape]
+        self.records = np.zeros(self.n, dtype=nv.WARP_PAGE_DTYPE)
+        self.result_shapes = []
+        self.identity = []
+        for i, (name, config) in enumerate(zip(op_names, configs)):
+            config_cls, state_cls = _affine_states()[name]
+            config = dyn_structure(config, config_cls)
+            state = state_cls(config, self.shapes[i], None)
+            trans_mat, dsize = state.trans_mat, state.dsize
+            if trans_mat is None or getattr(config, 'is_nop', False):
+                self.identity.append(True)
+                self.result_shapes.append(self.shapes[i])
+                self.records['kind'][i] = nv.WARP_AFFINE
+                self.records['inv'][i, :6] = [1, 0, 0, 0, 1, 0]
+                continue
+            self.identity.append(False)
+            self.result_shapes.append((int(dsize[1]), int(dsize[0])))
+            if trans_mat.shape[0] == 2:
+                self.records['kind'][i] = nv.WARP_AFFINE
+                self.records['inv'][i, :6] = invert_affine(trans_mat).reshape(-1)
+            else:
+                self.records['kind'][i] = nv.WARP_PERSPECTIVE
+                self.records['inv'][i] = np.linalg.inv(
+                    np.asarray(trans_mat, dtype=np.float64)).reshape(-1)
+
+    def run(self, images=None, masks=None, score_maps=None, channels: Optional[int] = None):
+        """Same input conventions as GeometricBatch.run (4-D batch or flat arenas)."""
+        shapes = self.result_shapes
+        pixels = np.asarray([h * w for h, w in shapes], dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(pixels)])
+        total = int(offsets[-1])
+        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
+        src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
+        planes = self.records['planes']
+        planes['src_h'] = [s[0] for s in self.shapes]
+        planes['src_w'] = [s[1] for s in self.shapes]
+        planes['dst_h'] = [s[0] for s in shapes]
+        planes['dst_w'] = [s[1] for s in shapes]
+        image_arena = mask_arena = score_arena = None
+        if images is not None:
+            if channels is None:
+                channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
+                                                        else None)
+            if channels is None:
+                raise ValueError('flat image arenas need `channels`')
+            image_arena = dv.empty((total * channels,), np.uint8)
+            planes['src_image'] = np.uint64(images.data_ptr()) + src_offsets * np.uint64(channels)
+            planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
+                np.uint64)
+            planes['image_channels'] = channels
+        else:
+            channels = 0
+        if masks is not None:
+            mask_arena = dv.empty((total,), np.uint8)
+            planes['src_mask'] = np.uint64(masks.data_ptr()) + src_offsets
+            planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
+        if score_maps is not None:
+            score_arena = dv.empty((total,), np.float32)
+            planes['src_score'] = np.uint64(score_maps.data_ptr()) + src_offsets * np.uint64(4)
+            planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
+        self.records['planes'] = planes
+        pages_dev = dv.upload_structs(self.records)
+        nv.check(nv.lib().vkb_warp_fused(dv.ptr(pages_dev), self.n,
+                                         max(s[0] for s in shapes), max(s[1] for s in shapes),
+                                         dv.stream_ptr()), 'vkb_warp_fused')
+        return BatchOutput(shapes, channels, image_arena, mask_arena, score_arena, offsets)
 
 
 _PIPELINE_STATE = {}
