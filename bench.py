@@ -82,6 +82,44 @@ def config_to_plain(config):
 
 
 # ---------------------------------------------------------------------------------------------
+# NUMA placement of the rank (e2e leg: pinned host buffers next to the GPU's PCIe root)
+# ---------------------------------------------------------------------------------------------
+_ALL_CPUS = None
+
+
+def bind_to_gpu_cpus(gpu_index: int):
+    """Restrict this process to the CPUs NVML names as local to the GPU, so the pinned host
+    buffers of the e2e leg (first touch) and the copy-issuing thread sit on the GPU's NUMA node.
+    Returns the number of CPUs in the mask, or None when NVML cannot tell."""
+    global _ALL_CPUS
+    if os.environ.get('VKB_BENCH_NO_AFFINITY'):
+        return None
+    try:
+        import pynvml as nvml
+        _ALL_CPUS = os.sched_getaffinity(0)
+        nvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = gpu_index
+        if visible:
+            ids = [v.strip() for v in visible.split(',') if v.strip()]
+            if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                index = int(ids[gpu_index])
+        nvml.nvmlDeviceSetCpuAffinity(nvml.nvmlDeviceGetHandleByIndex(index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def unbind_cpus():
+    """Back to the full CPU set (the CPU baseline leg uses every core)."""
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except OSError:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -294,6 +332,7 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     _native.lib()
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_cpus(local_rank)  # pinned buffers land on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -422,7 +461,9 @@ def main():
                         'batch, see profiles/',
             },
         }
+        line['config']['numa_local_cpus'] = numa_cpus
         if not args.skip_cpu_baseline:
+            unbind_cpus()
             cores = max(1, min(os.cpu_count() or 1, 64))
             n_pages = cores * CPU_PAGES_PER_WORKER
             cpu_value, cpu_wall, per_page = cpu_reference_throughput(n_pages, cores)
