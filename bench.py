@@ -41,8 +41,9 @@ CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold
 # remap (small-tile launch + large-tile launch)
 KERNELS_PER_STEP = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of grid_remap_kernel, one 32-page launch under
-# `ncu --set full` (profiles/r01_ncu_summary.md): 166.7 MB read + 81.9 MB written / 32 pages
-TRAFFIC_PER_PAGE = 248.5e6 / 32
+# `ncu --set full` (profiles/r01_ncu_summary.md): both launches, 176.5 MB read + 85.8 MB written
+# per 32 pages
+TRAFFIC_PER_PAGE = 262.3e6 / 32
 CPU_PAGES_PER_WORKER = 6  # bounded sample of the CPU arm: ~20 s of CPU work in total
 
 
