@@ -214,3 +214,24 @@ class DistortionImageGridBased(Distortion[_T_CONFIG, _T_STATE]):
         return PointTuple(self._func_points_batched(internals.config, internals.state,
                                                     internals.shape, PointList(points),
                                                     internals.rng))
+
+    def distort_polygons_based_on_internals(self, internals, polygons):
+        # the vertices of ALL polygons through one launch (the reference falls back to one
+        # func_point call per vertex, interface.py:694-715)
+        from vkit_b200.element import Polygon, PointTuple
+        internals.restore_rng_if_supported()
+        polygons = list(polygons)
+        flat = PointList()
+        for polygon in polygons:
+            flat.extend(polygon.points)
+        moved = self._func_points_batched(internals.config, internals.state, internals.shape, flat,
+                                          internals.rng)
+        out, begin = [], 0
+        for polygon in polygons:
+            end = begin + polygon.num_points
+            out.append(Polygon.create(points=moved[begin:end]))
+            begin = end
+        return out
+
+    def distort_polygon_based_on_internals(self, internals, polygon):
+        return self.distort_polygons_based_on_internals(internals, [polygon])[0]
