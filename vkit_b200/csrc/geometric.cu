@@ -28,78 +28,6 @@ void set_error(const char* fmt, ...) {
 }
 
 // ============================================================================================
-// Shared per-pixel output stage: sample every present container at (X, Y) and store.
-// ============================================================================================
-__device__ __forceinline__ void sample_and_store(const vkb_planes& pl, int x, int y, int X, int Y) {
-    const long long dst_idx = (long long)y * pl.dst_w + x;
-    if (pl.image_channels == 3) {
-        uint8_t px[3];
-        bilinear_u8<3>(pl.src_image, pl.src_h, pl.src_w, (long long)pl.src_w * 3, X, Y, px);
-        uint8_t* d = pl.dst_image + dst_idx * 3;
-        d[0] = px[0];
-        d[1] = px[1];
-        d[2] = px[2];
-    } else if (pl.image_channels == 1) {
-        uint8_t px[1];
-        bilinear_u8<1>(pl.src_image, pl.src_h, pl.src_w, (long long)pl.src_w, X, Y, px);
-        pl.dst_image[dst_idx] = px[0];
-    } else if (pl.image_channels == 4) {
-        uint8_t px[4];
-        bilinear_u8<4>(pl.src_image, pl.src_h, pl.src_w, (long long)pl.src_w * 4, X, Y, px);
-        *reinterpret_cast<uchar4*>(pl.dst_image + dst_idx * 4) =
-            make_uchar4(px[0], px[1], px[2], px[3]);
-    }
-    if (pl.src_mask) {
-        uint8_t m[1];
-        bilinear_u8<1>(pl.src_mask, pl.src_h, pl.src_w, (long long)pl.src_w, X, Y, m);
-        pl.dst_mask[dst_idx] = m[0];
-    }
-    if (pl.src_score) {
-        pl.dst_score[dst_idx] = bilinear_f32(pl.src_score, pl.src_h, pl.src_w, pl.src_w, X, Y);
-    }
-}
-
-// ============================================================================================
-// Affine / perspective warp.  Block (32, 8) covers a 32 x 32 dst tile, 4 rows per thread.
-// ============================================================================================
-__global__ void __launch_bounds__(256) warp_fused_kernel(const vkb_warp_page* __restrict__ pages) {
-    __shared__ vkb_warp_page pg;
-    {
-        const int tid = threadIdx.y * 32 + threadIdx.x;
-        const int* src = reinterpret_cast<const int*>(pages + blockIdx.z);
-        int* dst = reinterpret_cast<int*>(&pg);
-        for (int i = tid; i < (int)(sizeof(vkb_warp_page) / 4); i += 256) dst[i] = src[i];
-    }
-    __syncthreads();
-    const vkb_planes& pl = pg.planes;
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y_base = blockIdx.y * 32 + threadIdx.y;
-    if (x >= pl.dst_w || y_base >= pl.dst_h) return;
-
-    if (pg.kind == VKB_WARP_AFFINE) {
-        const int adelta = cv_round_d(__dmul_rn(__dmul_rn(pg.inv[0], (double)x), 1024.0));
-        const int bdelta = cv_round_d(__dmul_rn(__dmul_rn(pg.inv[3], (double)x), 1024.0));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int y = y_base + 8 * k;
-            if (y >= pl.dst_h) break;
-            const int X0 = cv_round_d(__dmul_rn(__dadd_rn(__dmul_rn(pg.inv[1], (double)y), pg.inv[2]), 1024.0)) + 16;
-            const int Y0 = cv_round_d(__dmul_rn(__dadd_rn(__dmul_rn(pg.inv[4], (double)y), pg.inv[5]), 1024.0)) + 16;
-            sample_and_store(pl, x, y, (X0 + adelta) >> 5, (Y0 + bdelta) >> 5);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int y = y_base + 8 * k;
-            if (y >= pl.dst_h) break;
-            int X, Y;
-            perspective_coord(pg.inv, x, y, X, Y);
-            sample_and_store(pl, x, y, X, Y);
-        }
-    }
-}
-
-// ============================================================================================
 // Lattice projection.
 // ============================================================================================
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
@@ -847,6 +775,141 @@ __device__ __noinline__ uint32_t sample_u8_small(const uint8_t* __restrict__ src
     uint8_t out[4] = {0, 0, 0, 0};
     bilinear_u8<C>(src, h, w, (long long)w * C, X, Y, out);
     return out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+}
+
+// ============================================================================================
+// Affine / perspective warp (rotate / shear / skew: affine.py:38-43, 416-456).  Block (32, 8)
+// covers a 32 x 32 dst tile, 4 rows per thread.  The coordinates follow cv::warpAffine /
+// cv::warpPerspective (double arithmetic, 10-bit / 5-bit fixed point); the gather is the remap's:
+// all four pixels' aligned row loads in flight, PRMT + IDP.4A blend for RGB, tap weights shared by
+// Image and Mask, out-of-image footprints fixed behind one branch per thread.
+// ============================================================================================
+__global__ void __launch_bounds__(256) warp_fused_kernel(const vkb_warp_page* __restrict__ pages) {
+    __shared__ vkb_warp_page pg;
+    {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        const int* src = reinterpret_cast<const int*>(pages + blockIdx.z);
+        int* dst = reinterpret_cast<int*>(&pg);
+        for (int i = tid; i < (int)(sizeof(vkb_warp_page) / 4); i += 256) dst[i] = src[i];
+    }
+    __syncthreads();
+    const vkb_planes& pl = pg.planes;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y_base = blockIdx.y * 32 + threadIdx.y;
+    if (x >= pl.dst_w || y_base >= pl.dst_h) return;
+    constexpr int R = 4;
+    const int src_h = pl.src_h, src_w = pl.src_w;
+
+    int X[R], Y[R];
+    if (pg.kind == VKB_WARP_AFFINE) {
+        const int adelta = cv_round_d(__dmul_rn(__dmul_rn(pg.inv[0], (double)x), 1024.0));
+        const int bdelta = cv_round_d(__dmul_rn(__dmul_rn(pg.inv[3], (double)x), 1024.0));
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int y = y_base + 8 * k;
+            const int X0 = cv_round_d(__dmul_rn(__dadd_rn(__dmul_rn(pg.inv[1], (double)y), pg.inv[2]), 1024.0)) + 16;
+            const int Y0 = cv_round_d(__dmul_rn(__dadd_rn(__dmul_rn(pg.inv[4], (double)y), pg.inv[5]), 1024.0)) + 16;
+            X[k] = (X0 + adelta) >> 5;
+            Y[k] = (Y0 + bdelta) >> 5;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) perspective_coord(pg.inv, x, y_base + 8 * k, X[k], Y[k]);
+    }
+
+    const bool tiny = src_h < 2 || src_w < 2;
+    TapWeights tw[R];
+    bool outside = false;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        tw[k] = tap_weights_plain(X[k], Y[k]);
+        outside |= tap_outside(tw[k], src_h, src_w);
+    }
+    if (outside && !tiny) {
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (tap_outside(tw[k], src_h, src_w)) tap_border_fix(tw[k], src_h, src_w);
+    }
+    const int channels = pl.image_channels;
+    if (channels == 3 && !tiny) {
+        Taps<3> taps[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            taps[k].t = tw[k];
+            taps_load<3>(pl.src_image, src_w, taps[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int y = y_base + 8 * k;
+            uint8_t px[3];
+            taps_blend<3>(taps[k], px);
+            if (y < pl.dst_h) {
+                uint8_t* d = pl.dst_image + ((long long)y * pl.dst_w + x) * 3;
+                d[0] = px[0];
+                d[1] = px[1];
+                d[2] = px[2];
+            }
+        }
+    } else if (channels) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int y = y_base + 8 * k;
+            if (y >= pl.dst_h) break;
+            const long long dst_idx = (long long)y * pl.dst_w + x;
+            if (channels == 3) {
+                uint8_t px[3];
+                bilinear_u8<3>(pl.src_image, src_h, src_w, (long long)src_w * 3, X[k], Y[k], px);
+                uint8_t* d = pl.dst_image + dst_idx * 3;
+                d[0] = px[0];
+                d[1] = px[1];
+                d[2] = px[2];
+            } else if (channels == 1) {
+                uint8_t px[1];
+                bilinear_u8<1>(pl.src_image, src_h, src_w, (long long)src_w, X[k], Y[k], px);
+                pl.dst_image[dst_idx] = px[0];
+            } else {
+                uint8_t px[4];
+                bilinear_u8<4>(pl.src_image, src_h, src_w, (long long)src_w * 4, X[k], Y[k], px);
+                *reinterpret_cast<uchar4*>(pl.dst_image + dst_idx * 4) =
+                    make_uchar4(px[0], px[1], px[2], px[3]);
+            }
+        }
+    }
+    if (pl.src_mask) {
+        if (!tiny) {
+            Taps<1> taps[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                taps[k].t = tw[k];
+                taps_load<1>(pl.src_mask, src_w, taps[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int y = y_base + 8 * k;
+                uint8_t m[1];
+                taps_blend<1>(taps[k], m);
+                if (y < pl.dst_h) pl.dst_mask[(long long)y * pl.dst_w + x] = m[0];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int y = y_base + 8 * k;
+                if (y >= pl.dst_h) break;
+                uint8_t m[1];
+                bilinear_u8<1>(pl.src_mask, src_h, src_w, (long long)src_w, X[k], Y[k], m);
+                pl.dst_mask[(long long)y * pl.dst_w + x] = m[0];
+            }
+        }
+    }
+    if (pl.src_score) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int y = y_base + 8 * k;
+            if (y >= pl.dst_h) break;
+            pl.dst_score[(long long)y * pl.dst_w + x] =
+                bilinear_f32(pl.src_score, src_h, src_w, src_w, X[k], Y[k]);
+        }
+    }
 }
 
 // ---- cp.async plumbing of the persistent remap kernel -----------------------------------------
