@@ -869,3 +869,28 @@ def test_config5_chain_fully_batched_mixed_resolution(vk):
         assert list(out.shapes[i]) == case['stage_shapes'][-1]
         got = out.image(i).cpu().numpy()
         assert np.array_equal(got, img.mat), (case['id'], _diff_report(got, img.mat))
+
+
+def test_affine_batch_matches_golden(vk):
+    """rotate / shear / skew over a batch in ONE launch (image + mask + score_map, ragged results)
+    against the golden hashes of the per-page reference runs."""
+    import torch
+    from vkit_b200.batch import AffineBatch
+    cases = [c for c in GEOMETRIC if c['op'] in AFFINE_OPS and tuple(c['shape']) == (136, 176)]
+    shape = (136, 176)
+    images = np.stack([make_inputs(c['seed'], shape)[0] for c in cases])
+    masks = np.stack([make_inputs(c['seed'], shape)[1] for c in cases])
+    scores = np.stack([make_inputs(c['seed'], shape)[2] for c in cases])
+    out = AffineBatch([c['op'] for c in cases], [product_config(c) for c in cases], shape).run(
+        torch.from_numpy(images).cuda(), torch.from_numpy(masks).cuda(),
+        torch.from_numpy(scores).cuda())
+    for i, case in enumerate(cases):
+        assert out.shapes[i] == tuple(case['result_shape']), case['id']
+        if case['op'].startswith('skew'):
+            ref = golden_array(case, 'image')  # tie tolerance, see DESIGN.md
+            got = out.image(i).cpu().numpy()
+            assert (np.abs(got.astype(int) - ref.astype(int)) > 0).mean() <= 5e-3, case['id']
+            continue
+        assert sha(out.image(i).cpu().numpy()) == case['sha']['image'], case['id']
+        assert sha(out.mask(i).cpu().numpy()) == case['sha']['mask'], case['id']
+        assert sha(out.score_map(i).cpu().numpy()) == case['sha']['score_map'], case['id']
