@@ -143,11 +143,20 @@ extern "C" void hs_grid_remap(const vkb_grid_page* pg, const int32_t* lat, const
 extern "C" void hs_fill_poly4(const int32_t* pts, int h, int w, uint8_t* out) {
     const int px[4] = {pts[0], pts[2], pts[4], pts[6]}, py[4] = {pts[1], pts[3], pts[5], pts[7]};
     const int nwords = (w + 31) / 32;
-    std::vector<uint32_t> words(nwords);
+    std::vector<uint32_t> words(nwords), words2(nwords);
+    // both forms of the row coverage: the direct one and the per-edge setup + row evaluation the
+    // masks kernel uses; a pixel on which they disagree is reported as 7
+    EdgeConst E[4];
+    for (int i = 0; i < 4; ++i) edge_setup(px[(i + 3) & 3], py[(i + 3) & 3], px[i], py[i], E[i]);
     for (int y = 0; y < h; ++y) {
         std::fill(words.begin(), words.end(), 0u);
+        std::fill(words2.begin(), words2.end(), 0u);
         poly_row_mask<4>(px, py, y, 0, words.data(), nwords);
-        for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = (words[x >> 5] >> (x & 31)) & 1u;
+        poly_row_mask_edges<4>(E, y, 0, words2.data(), nwords);
+        for (int x = 0; x < w; ++x) {
+            const uint32_t a = (words[x >> 5] >> (x & 31)) & 1u, b = (words2[x >> 5] >> (x & 31)) & 1u;
+            out[(size_t)y * w + x] = a == b ? a : 7;
+        }
     }
 }
 

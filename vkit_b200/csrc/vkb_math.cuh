@@ -585,16 +585,44 @@ VKB_HD void poly_row_mask_edges(const EdgeConst* E, int y, int bx0, uint32_t* wo
     }
 }
 
+// Direct form (no per-edge state): used where a single row of a polygon is needed once
+// (over-budget cells in the remap's slow path); same results as poly_row_mask_edges.
 template <int N>
 VKB_HD void poly_row_mask(const int* px, const int* py, int y, int bx0, uint32_t* words,
                           int nwords) {
-    EdgeConst E[N];
+    long long cross[N];
+    int ncross = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const int j = (i + N - 1) % N;
-        edge_setup(px[j], py[j], px[i], py[i], E[i]);
+        const int x0 = px[j], y0 = py[j], x1 = px[i], y1 = py[i];
+        int lo, hi;
+        if (line_row_run(x0, y0, x1, y1, y, lo, hi)) {
+            if (nwords == 1) set_bits1(words[0], lo - bx0, hi - bx0);
+            else set_bits(words, nwords, lo - bx0, hi - bx0);
+        }
+        if (y0 == y1) continue;
+        const int ya = y0 < y1 ? y0 : y1, yb = y0 < y1 ? y1 : y0;
+        if (ya <= y && y < yb) cross[ncross++] = scan_edge_x(x0, y0, x1, y1, y);
     }
-    poly_row_mask_edges<N>(E, y, bx0, words, nwords);
+    // insertion sort (N is 4 for lattice cells)
+    for (int i = 1; i < ncross; ++i) {
+        const long long v = cross[i];
+        int j = i - 1;
+        while (j >= 0 && cross[j] > v) { cross[j + 1] = cross[j]; --j; }
+        cross[j + 1] = v;
+    }
+    for (int k = 0; k + 1 < ncross; k += 2) {
+        const long long xl = (cross[k] + 65535) >> 16;
+        const long long xr = cross[k + 1] >> 16;
+        if (xl <= xr) {
+            const long long lo = xl - bx0, hi = xr - bx0;
+            const int lo_i = lo < -1 ? -1 : (lo > 1 << 20 ? 1 << 20 : (int)lo);
+            const int hi_i = hi < -1 ? -1 : (hi > 1 << 20 ? 1 << 20 : (int)hi);
+            if (nwords == 1) set_bits1(words[0], lo_i, hi_i);
+            else set_bits(words, nwords, lo_i, hi_i);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
