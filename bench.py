@@ -37,9 +37,9 @@ PAGE_SHAPE = (1024, 1024)
 BATCH = 256
 CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold',
               'camera_plane_line_curve')
-# project_camera, project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records,
-# remap (small-tile launch + large-tile launch)
-KERNELS_PER_STEP = 10
+# project_camera (no page uses the MLS projector, so that kernel is not launched), finalize, cells,
+# masks, tile_base, tile_offsets, tile_records, remap (small-tile launch + large-tile launch)
+KERNELS_PER_STEP = 9
 # dram__bytes_read.sum + dram__bytes_write.sum of grid_remap_kernel, one 32-page launch under
 # `ncu --set full` (profiles/r01_ncu_summary.md): both launches, 176.5 MB read + 85.8 MB written
 # per 32 pages

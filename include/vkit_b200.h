@@ -135,9 +135,11 @@ typedef struct vkb_grid_meta {
 #define VKB_TILE_CAP 64 /* candidate cells kept per tile before the slow path is used */
 
 /* Phase 1: project the source lattice (p_max >= rows*cols of every page).
- * lattice_f: n_pages x p_max x 2 doubles (x, y), un-shifted projected coordinates. */
+ * lattice_f: n_pages x p_max x 2 doubles (x, y), un-shifted projected coordinates.
+ * projectors: bit (1 << VKB_PROJ_*) set for every projector some page uses (the pages live in
+ * device memory; a projector nobody uses costs no launch). */
 int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
-                     double* lattice_f, void* stream);
+                     double* lattice_f, int32_t projectors, void* stream);
 
 /* Phase 1b: round (half to even), shift to the origin, optional resize_as_src, result shape.
  * lattice_i: n_pages x p_max x 2 int32 (x, y).

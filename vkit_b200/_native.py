@@ -158,7 +158,7 @@ def _declare(lib):
     vp = c_void_p
     lib.vkb_warp_fused.argtypes = [vp, i32, i32, i32, vp]
     lib.vkb_affine_points.argtypes = [POINTER(c_double), i32, vp, vp, i32, i32, vp]
-    lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, vp]
+    lib.vkb_grid_project.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.vkb_grid_finalize.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.vkb_grid_build.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                    vp, vp, vp, vp]

@@ -1524,15 +1524,21 @@ extern "C" int vkb_affine_points(const double* mat_host, int32_t rows, const dou
 }
 
 extern "C" int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
-                                double* lattice_f, void* stream) {
+                                double* lattice_f, int32_t projectors, void* stream) {
     VKB_REQUIRE(pages && lattice_f && n_pages > 0 && p_max > 0, "bad arguments");
     VKB_REQUIRE(n_pages <= 65535, "at most 65535 pages per launch");
-    grid_project_camera_kernel<<<n_pages, 1024, 0, (cudaStream_t)stream>>>(pages, p_max, lattice_f);
-    int rc = check_launch("grid_project_camera_kernel");
-    if (rc) return rc;
-    grid_project_mls_kernel<<<dim3((p_max + 7) / 8, n_pages), 256, 0, (cudaStream_t)stream>>>(
-        pages, p_max, lattice_f);
-    return check_launch("grid_project_mls_kernel");
+    // every kernel skips the pages of the other projector; a kernel no page needs is not launched
+    if (projectors & (1 << VKB_PROJ_CAMERA)) {
+        grid_project_camera_kernel<<<n_pages, 1024, 0, (cudaStream_t)stream>>>(pages, p_max, lattice_f);
+        int rc = check_launch("grid_project_camera_kernel");
+        if (rc) return rc;
+    }
+    if (projectors & (1 << VKB_PROJ_MLS)) {
+        grid_project_mls_kernel<<<dim3((p_max + 7) / 8, n_pages), 256, 0, (cudaStream_t)stream>>>(
+            pages, p_max, lattice_f);
+        return check_launch("grid_project_mls_kernel");
+    }
+    return VKB_OK;
 }
 
 extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,

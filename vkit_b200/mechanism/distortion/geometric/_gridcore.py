@@ -59,8 +59,12 @@ class GridBatch:
             lat = np.zeros((self.n, self.p_max, 2), dtype=np.float64)
             lat[:, :given_lattice.shape[1]] = given_lattice
             self.lattice_f.copy_(dv.to_device(lat))
+        projectors = 0
+        for kind in np.unique(self.pages['projector']):
+            projectors |= 1 << int(kind)
         nv.check(self.lib.vkb_grid_project(dv.ptr(self.pages_dev), self.n, self.p_max,
-                                           dv.ptr(self.lattice_f), stream), 'vkb_grid_project')
+                                           dv.ptr(self.lattice_f), projectors, stream),
+                 'vkb_grid_project')
         # result shapes are needed on the host to allocate the outputs: the kernel mirrors them
         # into pinned host memory (device accessible under UVA), so one stream synchronise is
         # enough -- a D2H copy would wait behind bulk copies queued on the copy engine
