@@ -894,3 +894,64 @@ def test_affine_batch_matches_golden(vk):
         assert sha(out.image(i).cpu().numpy()) == case['sha']['image'], case['id']
         assert sha(out.mask(i).cpu().numpy()) == case['sha']['mask'], case['id']
         assert sha(out.score_map(i).cpu().numpy()) == case['sha']['score_map'], case['id']
+
+
+# ---------------------------------------------------------------------------------------------
+# Seeded fuzz: policy-generated camera configs at random shapes, levels and grid sizes (small
+# grids give cells wider than the 32-bit coverage budget, strong levels give folded lattices and
+# tiles with many candidate cells) -- CUDA path vs the oracle, bit for bit
+# ---------------------------------------------------------------------------------------------
+def _fuzz_cases():
+    rng = np.random.default_rng(20261017)
+    ops = ['camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold',
+           'camera_plane_line_curve']
+    cases = []
+    for k in range(28):
+        shape = (int(rng.integers(40, 330)), int(rng.integers(40, 330)))
+        cases.append((k, ops[k % 4], int(rng.integers(1, 11)), shape,
+                      [None, None, 8, 23, 45][k % 5], int(rng.integers(0, 2**31))))
+    return cases
+
+
+@pytest.mark.parametrize('case', _fuzz_cases(), ids=lambda c: f'{c[0]}-{c[1]}-L{c[2]}-{c[3][0]}x{c[3][1]}-g{c[4]}')
+def test_fuzz_camera_ops_vs_oracle(vk, case):
+    import attrs
+    from oracle import vkit_port as port
+    from vkit_b200.mechanism.distortion_policy.geometric import camera as cam_policy
+    element, distortion = vk
+    _, name, level, shape, grid_size, seed = case
+    factory = getattr(cam_policy, f'{name}_policy_factory')
+    policy = factory.create()
+    generator = policy.config_generator_cls(policy.config_for_config_generator, level)
+    config = generator(shape, np.random.default_rng(seed))
+    if grid_size is not None:
+        config = attrs.evolve(config, grid_size=grid_size)
+    image, mask, score_map = make_inputs(seed % 100000, shape)
+    r = getattr(distortion, name).distort(config, image=element.Image(mat=image),
+                                          mask=element.Mask(mat=mask),
+                                          score_map=element.ScoreMap(mat=score_map))
+
+    def plain(obj):
+        if attrs.has(type(obj)):
+            return {f.name: plain(getattr(obj, f.name)) for f in attrs.fields(type(obj))}
+        if isinstance(obj, (list, tuple)):
+            return [plain(v) for v in obj]
+        return obj
+
+    port.use_cv2(False)
+    ref = port.grid_distort(name, plain(config), shape, image=image, mask=mask,
+                            score_map=score_map)
+    assert tuple(r.shape) == tuple(ref['shape']), (r.shape, ref['shape'])
+    if level <= 2:
+        # Nearly undistorted pages: the cells stay axis-aligned 15 x 15 squares, so thousands of
+        # source coordinates land EXACTLY on 1/64-px ties, where the last bit of the float64
+        # homography (cv2 solves it by SVD) and the summation order of the reference's BLAS
+        # matmul decide the rounding -- the live reference differs from this oracle on a few of
+        # them too ("ties").  Each flip moves one coordinate by 1/32 px.
+        wrong = (r.image.mat != ref['image']).any(axis=-1).mean()
+        assert wrong <= 5e-3, _diff_report(r.image.mat, ref['image'])
+        assert (r.mask.mat != ref['mask']).mean() <= 5e-3
+        return
+    assert np.array_equal(r.image.mat, ref['image']), _diff_report(r.image.mat, ref['image'])
+    assert np.array_equal(r.mask.mat, ref['mask']), _diff_report(r.mask.mat, ref['mask'])
+    assert np.array_equal(r.score_map.mat, ref['score_map'])
