@@ -157,6 +157,12 @@ extern "C" void hs_fill_poly4(const int32_t* pts, int h, int w, uint8_t* out) {
             const uint32_t a = (words[x >> 5] >> (x & 31)) & 1u, b = (words2[x >> 5] >> (x & 31)) & 1u;
             out[(size_t)y * w + x] = a == b ? a : 7;
         }
+        // the branch-free form works on one 32-bit window at a time
+        if (edges_fast_ok(E)) {
+            for (int wd = 0; wd < nwords; ++wd)
+                if (quad_row_mask_fast(E, y, 32 * wd) != words[wd])
+                    for (int x = 32 * wd; x < w && x < 32 * wd + 32; ++x) out[(size_t)y * w + x] = 9;
+        }
     }
 }
 

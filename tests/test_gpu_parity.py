@@ -955,3 +955,20 @@ def test_fuzz_camera_ops_vs_oracle(vk, case):
     assert np.array_equal(r.image.mat, ref['image']), _diff_report(r.image.mat, ref['image'])
     assert np.array_equal(r.mask.mat, ref['mask']), _diff_report(r.mask.mat, ref['mask'])
     assert np.array_equal(r.score_map.mat, ref['score_map'])
+
+
+def test_image_to_resized_image_linear_and_nearest(vk):
+    """Image.to_resized_image with cv.INTER_LINEAR / INTER_NEAREST == the oracle's cv.resize model
+    (pinned to cv2 by the pixelation goldens); the default INTER_CUBIC says where it stands."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    image, _, _ = make_inputs(77, (100, 133))
+    img = element.Image(mat=image)
+    for (h, w) in ((37, 200), (150, 61), (100, 133)):
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=1).mat
+        assert np.array_equal(got, port.resize_u8(image, (w, h)))
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=0).mat
+        assert np.array_equal(got, port.resize_u8(image, (w, h), nearest=True))
+    with pytest.raises(NotImplementedError):
+        img.to_resized_image(resized_height=50)

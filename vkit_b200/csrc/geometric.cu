@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
     __syncwarp();
     if (lane < nrows) {
         uint32_t word = 0;
-        poly_row_mask_edges<4>(E, y0 + lane, x0, &word, 1);
+        if (edges_fast_ok(E)) word = quad_row_mask_fast(E, y0 + lane, x0);  // branch-free form
+        else poly_row_mask_edges<4>(E, y0 + lane, x0, &word, 1);
         out[lane] = word;
     }
 }

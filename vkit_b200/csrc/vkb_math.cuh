@@ -585,6 +585,82 @@ VKB_HD void poly_row_mask_edges(const EdgeConst* E, int y, int bx0, uint32_t* wo
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Branch-free row coverage of a QUAD whose edges are all "small" (deltas below 2048, slope
+// arithmetic in 32 bits, coordinates in [0, 32768)) -- every lattice cell.  Same results as
+// poly_row_mask_edges<4> (cross-checked on the host); no early returns, no divergent loops:
+// invalid runs / crossings are carried as empty masks / sentinels, the four crossings go through
+// a 5-exchange sorting network on 32-bit keys.
+// ---------------------------------------------------------------------------------------
+VKB_HD bool edges_fast_ok(const EdgeConst* E) {
+    return E[0].small && E[1].small && E[2].small && E[3].small && E[0].pad0 && E[1].pad0
+           && E[2].pad0 && E[3].pad0;
+}
+
+VKB_HD uint32_t bits_lo_hi(int lo, int hi) {  // bits [lo, hi] clipped to one word; empty if lo > hi
+    const int l = lo < 0 ? 0 : lo, h = hi > 31 ? 31 : hi;
+    const uint32_t m = (0xFFFFFFFFu >> (31 - (h & 31))) & (0xFFFFFFFFu << (l & 31));
+    return (l <= h) ? m : 0u;
+}
+
+VKB_HD uint32_t edge_row_bits_fast(const EdgeConst& E, int y, int bx0) {
+    const int dx = E.dx, dy = E.dy;
+    const int k = (y - E.ay) * E.sy;
+    bool valid = (unsigned)k <= (unsigned)dy;
+    const int kk = k < 0 ? 0 : (k > dy ? dy : k);
+    int lo, hi;
+    if (dy == 0) {  // uniform per edge
+        lo = E.ax;
+        hi = E.ax + dx;
+    } else {
+        const int den = 2 * dy;
+        if (dy > dx) {
+            lo = hi = E.ax + floor_div_small(2 * dx * kk + dy - 1, den, E.rcp);
+        } else {
+            const int n = 2 * dx * kk - dx + den;  // (2*dx*k - dx + 1) + den - 1
+            const int jl = floor_div_small(n < 0 ? 0 : n, den, E.rcp);
+            const int jlo = kk > 0 ? jl : 0;
+            int jhi = floor_div_small(2 * dx * (kk + 1) - dx + den, den, E.rcp) - 1;
+            jhi = jhi > dx ? dx : jhi;
+            valid = valid && jlo <= jhi;
+            lo = E.ax + jlo;
+            hi = E.ax + jhi;
+        }
+    }
+    const uint32_t m = bits_lo_hi(lo - bx0, hi - bx0);
+    return valid ? m : 0u;
+}
+
+constexpr int kNoCross = 0x7fffffff;
+
+VKB_HD int edge_row_cross_fast(const EdgeConst& E, int y) {
+    const bool valid = E.scan && y >= E.ya && y < E.yb;
+    const int x = (int)E.base + (int)E.dxf * (y - E.ya);
+    return valid ? x : kNoCross;
+}
+
+VKB_HD uint32_t quad_row_mask_fast(const EdgeConst* E, int y, int bx0) {
+    uint32_t word = edge_row_bits_fast(E[0], y, bx0) | edge_row_bits_fast(E[1], y, bx0)
+                    | edge_row_bits_fast(E[2], y, bx0) | edge_row_bits_fast(E[3], y, bx0);
+    int c0 = edge_row_cross_fast(E[0], y), c1 = edge_row_cross_fast(E[1], y);
+    int c2 = edge_row_cross_fast(E[2], y), c3 = edge_row_cross_fast(E[3], y);
+#define VKB_CSWAP(a, b) { const int lo_ = a < b ? a : b, hi_ = a < b ? b : a; a = lo_; b = hi_; }
+    VKB_CSWAP(c0, c1) VKB_CSWAP(c2, c3) VKB_CSWAP(c0, c2) VKB_CSWAP(c1, c3) VKB_CSWAP(c1, c2)
+#undef VKB_CSWAP
+    // crossings come in pairs; sentinels sort last
+    {
+        const int xl = (int)(((long long)c0 + 65535) >> 16), xr = c1 >> 16;
+        const uint32_t m = bits_lo_hi(xl - bx0, xr - bx0);
+        word |= (c1 != kNoCross && xl <= xr) ? m : 0u;
+    }
+    {
+        const int xl = (int)(((long long)c2 + 65535) >> 16), xr = c3 >> 16;
+        const uint32_t m = bits_lo_hi(xl - bx0, xr - bx0);
+        word |= (c3 != kNoCross && xl <= xr) ? m : 0u;
+    }
+    return word;
+}
+
 // Direct form (no per-edge state): used where a single row of a polygon is needed once
 // (over-budget cells in the remap's slow path); same results as poly_row_mask_edges.
 template <int N>

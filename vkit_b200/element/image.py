@@ -279,6 +279,33 @@ class Image(DualStorage, Shapable):
         return attrs.evolve(self, mat=self._crop_storage(up, down, left, right))
 
 
+    # cv2 interpolation codes (cv.INTER_NEAREST / INTER_LINEAR / INTER_CUBIC)
+    _CV_INTER = {0: _native.INTER_NEAREST, 1: _native.INTER_LINEAR}
+
+    def to_resized_image(self, resized_height: Optional[int] = None,
+                         resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
+        """element/image.py:836-852.  The device resize reproduces cv.resize bit for bit for
+        INTER_NEAREST (0) and INTER_LINEAR (1); the reference's default INTER_CUBIC (2) runs in
+        Intel IPP inside the cv2 wheel and is a "next" row."""
+        from .opt import generate_shape_and_resized_shape
+        _, _, resized_height, resized_width = generate_shape_and_resized_shape(
+            self, resized_height, resized_width)
+        if cv_resize_interpolation not in self._CV_INTER:
+            raise NotImplementedError(
+                'to_resized_image: only cv.INTER_NEAREST and cv.INTER_LINEAR have device kernels; '
+                'pass cv_resize_interpolation=0 or 1')
+        if self.mat_dtype != np.uint8:
+            raise NotImplementedError('to_resized_image is provided for uint8 images')
+        src = self.dev
+        channels = self.num_channels or 1
+        shape = (resized_height, resized_width) + ((channels,) if self.num_channels else ())
+        dst = dv.empty(shape, np.uint8)
+        _native.check(_native.lib().vkb_resize_u8(
+            dv.ptr(src), self.height, self.width, dv.ptr(dst), resized_height, resized_width,
+            channels, self._CV_INTER[cv_resize_interpolation], dv.stream_ptr()), 'vkb_resize_u8')
+        return attrs.evolve(self, mat=dst)
+
+
 from .box import Box, generate_fill_by_boxes_mask  # noqa: E402
 from .polygon import Polygon, generate_fill_by_polygons_mask  # noqa: E402
 from .mask import Mask, generate_fill_by_masks_mask  # noqa: E402
