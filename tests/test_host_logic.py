@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_c_abi_exports_every_declared_symbol():
     from vkit_b200 import _native
+    from vkit_b200 import build as vk_build
+    if vk_build.needs_build():  # stale or missing in-tree library: nvcc cross-compiles without a GPU
+        vk_build.build()
     header = open(os.path.join(ROOT, 'include', 'vkit_b200.h')).read()
     declared = set(re.findall(r'^(?:int|const char\*)\s+(vkb_\w+)\s*\(', header, flags=re.M))
     assert declared, 'no declarations found'
@@ -28,7 +31,8 @@ def test_struct_layouts_match_numpy_dtypes():
     from vkit_b200 import _native as nv
     for struct, dtype in ((nv.Planes, nv.PLANES_DTYPE), (nv.WarpPage, nv.WARP_PAGE_DTYPE),
                           (nv.GridPage, nv.GRID_PAGE_DTYPE), (nv.GridMeta, nv.GRID_META_DTYPE),
-                          (nv.BlendItem, nv.BLEND_ITEM_DTYPE)):
+                          (nv.BlendItem, nv.BLEND_ITEM_DTYPE), (nv.PhotoPage, nv.PHOTO_PAGE_DTYPE),
+                          (nv.PolyItem, nv.POLY_ITEM_DTYPE), (nv.ColorOp, nv.COLOR_OP_DTYPE)):
         assert ctypes.sizeof(struct) == dtype.itemsize
         for name, _ in struct._fields_:
             assert getattr(struct, name).offset == dtype.fields[name][1]
