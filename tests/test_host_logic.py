@@ -241,8 +241,8 @@ assert int(counters[0]) == batch * world
 assert int(counters[1]) == int(seeds.sum())
 assert float(stats[0]) == float(world)
 assert names[0] == bench.CAMERA_OPS[(rank * batch) %% 4]
-print('rank', rank, 'ok')
-''' % ROOT)
+open(os.path.join(%r, 'rank%%d.ok' %% rank), 'w').write('ok')
+''' % (ROOT, str(tmp_path)))
     import socket
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     out = None
@@ -257,7 +257,8 @@ print('rank', rank, 'ok')
         if out.returncode == 0:
             break
     assert out.returncode == 0, out.stdout + out.stderr
-    assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout
+    # one marker file per rank (the ranks' stdout interleaves)
+    assert (tmp_path / 'rank0.ok').exists() and (tmp_path / 'rank1.ok').exists(), out.stdout
 
 
 def test_reference_arm_runs_on_cpu():
