@@ -330,8 +330,20 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
  * (11-bit fixed-point coefficients and cv2's 8-bit vertical pass). */
 #define VKB_INTER_NEAREST 0
 #define VKB_INTER_LINEAR 1
+#define VKB_INTER_CUBIC 2 /* cv2's own fixed-point path; the wheel's IPP default differs by +-1 on ~5 % of pixels */
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
+
+/* zoom_in_blur (photometric/blur.py:278-330): the page averaged with n_levels cubic enlargements
+ * of itself (centre crops), blended with the page by alpha.  levels: device array; the level's
+ * enlargement has (src dims / scale) pixels and the crop starts at (up, left). */
+typedef struct vkb_zoom_level {
+    double scale_x, scale_y; /* 1 / (resized / original), as cv::resize computes it */
+    int32_t up, left;
+} vkb_zoom_level;
+int vkb_zoom_in_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                        const vkb_zoom_level* levels_dev, int32_t n_levels, double alpha,
+                        void* stream);
 
 /* dst[y, x] = src[pos_y[y, x], pos_x[y, x]] (uint8 HWC): the pixel permutation of glass_blur
  * (photometric/blur.py:216-264); the index maps are the host-drawn random field. */

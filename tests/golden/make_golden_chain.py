@@ -206,6 +206,30 @@ def effect_cases():
                       'sha': {'image': mg.sha(r.image.mat)}})
 
 
+def cubic_cases():
+    """zoom_in_blur and Image.to_resized_image (default INTER_CUBIC): cv2 runs cubic in Intel IPP,
+    so these are tolerance cases (+-1); arrays are kept."""
+    for k, (cfg, shape) in enumerate([({}, (64, 96)), ({'ratio': 0.05, 'step': 0.02, 'alpha': 0.7},
+                                                       (100, 133)), ({'ratio': 0.2, 'step': 0.05},
+                                                                     (77, 50))]):
+        seed = 8300 + k
+        image, _, _ = make_inputs(seed, shape)
+        r = distortion.zoom_in_blur.distort(cfg, image=Image(mat=image), get_config=True)
+        cid = f'zb{k}'
+        CASES.append({'id': cid, 'kind': 'cubic', 'op': 'zoom_in_blur', 'config': mg.plain(r.config),
+                      'shape': list(shape), 'seed': seed, 'sha': {'image': mg.sha(r.image.mat)}})
+        ARRAYS[f'{cid}/image'] = r.image.mat
+    for k, (shape, dsize) in enumerate([((64, 96), (70, 101)), ((100, 133), (61, 200)),
+                                        ((77, 50), (150, 33))]):
+        seed = 8400 + k
+        image, _, _ = make_inputs(seed, shape)
+        out = Image(mat=image).to_resized_image(resized_height=dsize[0], resized_width=dsize[1])
+        cid = f'rc{k}'
+        CASES.append({'id': cid, 'kind': 'cubic', 'op': 'to_resized_image', 'shape': list(shape),
+                      'resized': list(dsize), 'seed': seed, 'sha': {'image': mg.sha(out.mat)}})
+        ARRAYS[f'{cid}/image'] = out.mat
+
+
 def main():
     random_distortion_cases()
     fixed_chain_cases()
@@ -213,6 +237,7 @@ def main():
     filter_blur_cases()
     effect_cases()
     random_distortion_cases('rx', NOT_YET_2, range(100, 124))
+    cubic_cases()
     with open(os.path.join(HERE, 'chain_cases.json'), 'w') as fout:
         json.dump({'reference': 'vkit-x/vkit@98ada2d', 'cv2': __import__('cv2').__version__,
                    'numpy': np.__version__, 'cases': CASES}, fout, indent=1)

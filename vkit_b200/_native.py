@@ -101,6 +101,10 @@ class PolyItem(ctypes.Structure):
                 ('value', c_float), ('pad_', c_int32)]
 
 
+class ZoomLevel(ctypes.Structure):
+    _fields_ = [('scale_x', c_double), ('scale_y', c_double), ('up', c_int32), ('left', c_int32)]
+
+
 class Rect(ctypes.Structure):
     _fields_ = [('up', c_int32), ('down', c_int32), ('left', c_int32), ('right', c_int32)]
 
@@ -110,7 +114,7 @@ class Rect(ctypes.Structure):
 (OP_MEAN_SHIFT, OP_HUE_SHIFT_RGB, OP_LIGHT_SHIFT_RGB, OP_STD_SHIFT, OP_COMPLEMENT, OP_POSTERIZE,
  OP_COLOR_BALANCE, OP_PERMUTE, OP_BOUNDARY_EQ, OP_NOISE, OP_LINE_STREAK) = range(11)
 MAX_COLOR_OPS = 8
-INTER_NEAREST, INTER_LINEAR = 0, 1
+INTER_NEAREST, INTER_LINEAR, INTER_CUBIC = 0, 1, 2
 NOISE_GAUSSIAN, NOISE_POISSON, NOISE_IMPULSE, NOISE_SPECKLE = range(4)
 
 
@@ -136,6 +140,7 @@ def _np_dtype(struct_cls):
 PLANES_DTYPE = _np_dtype(Planes)
 BLEND_ITEM_DTYPE = _np_dtype(BlendItem)
 RECT_DTYPE = _np_dtype(Rect)
+ZOOM_LEVEL_DTYPE = _np_dtype(ZoomLevel)
 POLY_ITEM_DTYPE = _np_dtype(PolyItem)
 PHOTO_PAGE_DTYPE = _np_dtype(PhotoPage)
 COLOR_OP_DTYPE = _np_dtype(ColorOp)
@@ -182,6 +187,7 @@ def _declare(lib):
     lib.vkb_fill_rects.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.vkb_streak_masks.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, POINTER(c_float),
                                      c_float, vp]
+    lib.vkb_zoom_in_blur_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, c_double, vp]
     lib.vkb_gather_pixels_u8.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.vkb_resize_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_filter2d_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
@@ -199,7 +205,7 @@ EXPORTS = (
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks', 'vkb_photo_chain_batched',
-    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched',
+    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8',
 )
 
 

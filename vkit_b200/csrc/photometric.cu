@@ -705,6 +705,103 @@ __global__ void __launch_bounds__(256) gather_pixels_kernel(const uint8_t* __res
 }
 
 // ============================================================================================
+// cv.resize(uint8, INTER_CUBIC) -- cv2's own (non-IPP) fixed-point path: float32 coefficients
+// (A = -0.75) rounded to 11 bits, integer horizontal pass, vertical pass (sum + 2^21) >> 22,
+// replicated borders.  The cv2 wheel routes cubic through Intel IPP by default, which differs
+// from this by +-1 on ~5 % of the pixels of a random image (measured; cv.ipp.setUseIPP(False)
+// gives this path).  Used by Image.to_resized_image and zoom_in_blur
+// (photometric/blur.py:278-330).
+// ============================================================================================
+__device__ __forceinline__ void resize_cubic_coef(int d, double scale, int& s0, int* a) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    const int si = (int)floorf(f);
+    f = __fsub_rn(f, (float)si);
+    s0 = si;
+    const float A = -0.75f;
+    const float f1 = __fadd_rn(f, 1.f), g = __fsub_rn(1.f, f);
+    float c[4];
+    c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, f1), 5.f * A), f1), 8.f * A), f1), 4.f * A);
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, f), A + 3.f), f), f), 1.f);
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, g), A + 3.f), g), g), 1.f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = min(max(__float2int_rn(__fmul_rn(c[k], 2048.f)), -32768), 32767);
+}
+
+template <int C>
+__device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ src, int sh, int sw,
+                                                   int x, int y, double scale_x, double scale_y,
+                                                   int* out) {
+    int sx, sy, ax[4], ay[4];
+    resize_cubic_coef(x, scale_x, sx, ax);
+    resize_cubic_coef(y, scale_y, sy, ay);
+    int acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 1 << 21;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int yy = min(max(sy - 1 + j, 0), sh - 1);
+        const uint8_t* row = src + (long long)yy * sw * C;
+        int hsum[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) hsum[c] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = min(max(sx - 1 + k, 0), sw - 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) hsum[c] += (int)row[xx * C + c] * ax[k];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += hsum[c] * ay[j];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = min(max(acc[c] >> 22, 0), 255);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) resize_cubic_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw,
+                                                              uint8_t* __restrict__ dst, int dh, int dw,
+                                                              double scale_x, double scale_y) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    int px[C];
+    resize_cubic_pixel<C>(src, sh, sw, x, y, scale_x, scale_y, px);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[((long long)y * dw + x) * C + c] = (uint8_t)px[c];
+}
+
+// zoom_in_blur (photometric/blur.py:278-330): the page plus its cubic enlargements (centre
+// crops), averaged (uint16 sum / count, rounded half to even), blended with the page in float64
+// and truncated.  The enlargements are sampled on the fly, never materialised.
+template <int C>
+__global__ void __launch_bounds__(256) zoom_in_blur_kernel(const uint8_t* __restrict__ src,
+                                                           uint8_t* __restrict__ dst, int h, int w,
+                                                           const vkb_zoom_level* __restrict__ levels,
+                                                           int n_levels, double alpha) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int acc[C], base[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = base[c] = src[((long long)y * w + x) * C + c];
+    for (int l = 0; l < n_levels; ++l) {
+        const vkb_zoom_level lv = levels[l];
+        int px[C];
+        resize_cubic_pixel<C>(src, h, w, x + lv.left, y + lv.up, lv.scale_x, lv.scale_y, px);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += px[c];
+    }
+    const double count = (double)(n_levels + 1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double mean = rint(__ddiv_rn((double)acc[c], count));
+        const double v = __dadd_rn(__dmul_rn(1.0 - alpha, (double)base[c]), __dmul_rn(alpha, mean));
+        dst[((long long)y * w + x) * C + c] = (uint8_t)(int)fmin(fmax(v, 0.0), 255.0);
+    }
+}
+
+// ============================================================================================
 // Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
 // over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
 // gaussian_blur -> color_shift / brightness_shift / mean_shift / ... as RandomDistortion applies
@@ -1250,13 +1347,23 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
                              void* stream) {
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
-    VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR,
-                "interpolation must be VKB_INTER_NEAREST or VKB_INTER_LINEAR");
+    VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
+                    || interpolation == VKB_INTER_CUBIC,
+                "interpolation must be VKB_INTER_NEAREST, VKB_INTER_LINEAR or VKB_INTER_CUBIC");
     // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
     const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
     dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    if (interpolation == VKB_INTER_CUBIC) {
+        if (channels == 1)
+            resize_cubic_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
+        else if (channels == 3)
+            resize_cubic_u8_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
+        else
+            resize_cubic_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
+        return check_launch("resize_cubic_u8_kernel");
+    }
     const int nearest = interpolation == VKB_INTER_NEAREST;
     if (channels == 1)
         resize_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
@@ -1288,4 +1395,19 @@ extern "C" int vkb_noise_philox_batched(const vkb_photo_page* pages, int32_t n_p
     noise_philox_batched_kernel<<<dim3(blocks_per_page, n_pages), 256, 0, (cudaStream_t)stream>>>(
         pages, channels);
     return check_launch("noise_philox_batched_kernel");
+}
+
+extern "C" int vkb_zoom_in_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
+                                   int32_t channels, const vkb_zoom_level* levels_dev,
+                                   int32_t n_levels, double alpha, void* stream) {
+    VKB_REQUIRE(src && dst && src != dst && h > 0 && w > 0 && n_levels >= 0, "bad arguments");
+    VKB_REQUIRE(n_levels == 0 || levels_dev, "levels missing");
+    VKB_REQUIRE(n_levels < 255, "at most 254 enlargements (the reference sums in uint16)");
+    VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 1) zoom_in_blur_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, dst, h, w, levels_dev, n_levels, alpha);
+    else if (channels == 3) zoom_in_blur_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, dst, h, w, levels_dev, n_levels, alpha);
+    else zoom_in_blur_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, dst, h, w, levels_dev, n_levels, alpha);
+    return check_launch("zoom_in_blur_kernel");
 }

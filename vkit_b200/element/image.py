@@ -280,20 +280,21 @@ class Image(DualStorage, Shapable):
 
 
     # cv2 interpolation codes (cv.INTER_NEAREST / INTER_LINEAR / INTER_CUBIC)
-    _CV_INTER = {0: _native.INTER_NEAREST, 1: _native.INTER_LINEAR}
+    _CV_INTER = {0: _native.INTER_NEAREST, 1: _native.INTER_LINEAR, 2: _native.INTER_CUBIC}
 
     def to_resized_image(self, resized_height: Optional[int] = None,
                          resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
         """element/image.py:836-852.  The device resize reproduces cv.resize bit for bit for
-        INTER_NEAREST (0) and INTER_LINEAR (1); the reference's default INTER_CUBIC (2) runs in
-        Intel IPP inside the cv2 wheel and is a "next" row."""
+        INTER_NEAREST (0) and INTER_LINEAR (1).  INTER_CUBIC (2, the reference's default) follows
+        cv2's own fixed-point path; the cv2 wheel routes cubic through Intel IPP, whose result
+        differs from it by +-1 on about 5 % of the pixels."""
         from .opt import generate_shape_and_resized_shape
         _, _, resized_height, resized_width = generate_shape_and_resized_shape(
             self, resized_height, resized_width)
         if cv_resize_interpolation not in self._CV_INTER:
             raise NotImplementedError(
-                'to_resized_image: only cv.INTER_NEAREST and cv.INTER_LINEAR have device kernels; '
-                'pass cv_resize_interpolation=0 or 1')
+                'to_resized_image: cv.INTER_NEAREST, INTER_LINEAR and INTER_CUBIC have device '
+                'kernels (AREA / LANCZOS4 / *_EXACT are "next" rows)')
         if self.mat_dtype != np.uint8:
             raise NotImplementedError('to_resized_image is provided for uint8 images')
         src = self.dev

@@ -305,6 +305,33 @@ class ZoomInBlurConfig(DistortionConfig):
     alpha: float = 0.5
 
 
+def zoom_in_blur_image(config: ZoomInBlurConfig, state, image: Image,
+                       rng: Optional[RandomGenerator]):
+    # blur.py:285-323: the page + its enlargements by 1+step .. 1+ratio (cubic, centre crops),
+    # averaged and blended; one launch samples every enlargement on the fly
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    height, width = image.shape
+    levels = []
+    for ratio in np.arange(1 + config.step, 1 + config.ratio + config.step, config.step):
+        resized_height = round(height * ratio)
+        resized_width = round(width * ratio)
+        levels.append((1.0 / (resized_width / width), 1.0 / (resized_height / height),
+                       (resized_height - height) // 2, (resized_width - width) // 2))
+    rec = np.zeros(len(levels), dtype=nv.ZOOM_LEVEL_DTYPE)
+    for i, (sx, sy, up, left) in enumerate(levels):
+        rec[i] = (sx, sy, up, left)
+    src = image.dev
+    dst = dv.empty(tuple(src.shape), np.uint8)
+    rec_dev = dv.upload_structs(rec) if len(levels) else None
+    nv.check(nv.lib().vkb_zoom_in_blur_u8(dv.ptr(src), dv.ptr(dst), height, width,
+                                          image.num_channels or 1, dv.ptr(rec_dev), len(levels),
+                                          float(config.alpha), dv.stream_ptr()),
+             'vkb_zoom_in_blur_u8')
+    image = attrs.evolve(image, mat=dst)
+    return to_original_image(image, mode)
+
+
 zoom_in_blur = Distortion(config_cls=ZoomInBlurConfig,
                           state_cls=DistortionNopState[ZoomInBlurConfig],
-                          func_image=_next_row('zoom_in_blur'))
+                          func_image=zoom_in_blur_image)
