@@ -334,6 +334,11 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
 
+/* dst = src > threshold ? high : low -- the two binarisations of Mask.to_resized_mask
+ * (element/mask.py:454-479: mask * 255 before cv.resize, > threshold after).  In place allowed. */
+int vkb_threshold_u8(const uint8_t* src, uint8_t* dst, int64_t n, int32_t threshold, int32_t low,
+                     int32_t high, void* stream);
+
 /* zoom_in_blur (photometric/blur.py:278-330): the page averaged with n_levels cubic enlargements
  * of itself (centre crops), blended with the page by alpha.  levels: device array; the level's
  * enlargement has (src dims / scale) pixels and the crop starts at (up, left). */

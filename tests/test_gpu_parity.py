@@ -999,3 +999,23 @@ def test_cubic_resize_and_zoom_in_blur(vk, case):
     ref = chain_array(case, 'image')
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1 and (diff > 0).mean() <= limit, _diff_report(got, ref)
+
+
+def test_mask_to_resized_mask(vk):
+    """Mask.to_resized_mask: (mask > 0) * 255 -> cv.resize -> > threshold, against the oracle's
+    cv.resize models (NEAREST / LINEAR pinned to cv2 bit for bit, CUBIC = cv2's non-IPP path)."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    _, mask, _ = make_inputs(91, (100, 133))
+    m = element.Mask(mat=mask)
+    full = (mask > 0).astype(np.uint8) * 255
+    for (h, w) in ((37, 200), (150, 61)):
+        for inter, model in ((0, lambda: port.resize_u8(full, (w, h), nearest=True)),
+                             (1, lambda: port.resize_u8(full, (w, h))),
+                             (2, lambda: port.resize_cubic_u8(full, (w, h)))):
+            for thr in (0, 127):
+                got = m.to_resized_mask(resized_height=h, resized_width=w,
+                                        cv_resize_interpolation=inter,
+                                        binarization_threshold=thr).mat
+                assert np.array_equal(got, (model() > thr).astype(np.uint8)), (h, w, inter, thr)

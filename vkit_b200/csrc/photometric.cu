@@ -801,6 +801,14 @@ __global__ void __launch_bounds__(256) zoom_in_blur_kernel(const uint8_t* __rest
     }
 }
 
+// dst = src > threshold ? high : low (Mask.to_resized_mask: element/mask.py:454-479)
+__global__ void __launch_bounds__(256) threshold_u8_kernel(const uint8_t* __restrict__ src,
+                                                           uint8_t* __restrict__ dst, long long n,
+                                                           int threshold, int low, int high) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (uint8_t)((int)src[i] > threshold ? high : low);
+}
+
 // ============================================================================================
 // Batched photometric chain: Gaussian blur (optional) followed by a per-pixel op list, one pass
 // over a ragged batch of pages (per-page shapes, taps and op lists).  The chained form of
@@ -1410,4 +1418,13 @@ extern "C" int vkb_zoom_in_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, 
     else if (channels == 3) zoom_in_blur_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, dst, h, w, levels_dev, n_levels, alpha);
     else zoom_in_blur_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, dst, h, w, levels_dev, n_levels, alpha);
     return check_launch("zoom_in_blur_kernel");
+}
+
+extern "C" int vkb_threshold_u8(const uint8_t* src, uint8_t* dst, int64_t n, int32_t threshold,
+                                int32_t low, int32_t high, void* stream) {
+    VKB_REQUIRE(src && dst && n >= 0, "bad arguments");
+    if (n == 0) return VKB_OK;
+    threshold_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, n, threshold, low, high);
+    return check_launch("threshold_u8_kernel");
 }

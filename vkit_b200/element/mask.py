@@ -4,6 +4,7 @@ from typing import Iterable, Optional, Tuple, Union
 import attrs
 import numpy as np
 
+from .. import _native
 from .. import device as dv
 from ._storage import DualStorage
 from .type import ElementSetOperationMode, Shapable
@@ -179,6 +180,35 @@ class Mask(DualStorage, Shapable):
         if self.on_device:
             return attrs.evolve(self, mat=(self.dev == 0).to(self.dev.dtype))
         return attrs.evolve(self, mat=(~self.np_mask).astype(np.uint8))
+
+    def to_resized_mask(self, resized_height: Optional[int] = None,
+                        resized_width: Optional[int] = None, cv_resize_interpolation: int = 2,
+                        binarization_threshold: int = 0):
+        """element/mask.py:454-479: (mask > 0) * 255 -> cv.resize -> > threshold.  NEAREST (0) and
+        LINEAR (1) are bit exact, CUBIC (2, the default) is cv2's own fixed-point cubic (the
+        wheel's IPP cubic differs by +-1 before the threshold)."""
+        from .opt import generate_resized_shape
+        assert not self.box
+        resized_height, resized_width = generate_resized_shape(self.height, self.width,
+                                                               resized_height, resized_width)
+        if cv_resize_interpolation not in (0, 1, 2):
+            raise NotImplementedError(
+                'to_resized_mask: cv.INTER_NEAREST, INTER_LINEAR and INTER_CUBIC have device '
+                'kernels (AREA / LANCZOS4 / *_EXACT are "next" rows)')
+        lib = _native.lib()
+        src = self.dev
+        n = self.height * self.width
+        full = dv.empty((self.height, self.width), np.uint8)
+        _native.check(lib.vkb_threshold_u8(dv.ptr(src), dv.ptr(full), n, 0, 0, 255,
+                                           dv.stream_ptr()), 'vkb_threshold_u8')
+        dst = dv.empty((resized_height, resized_width), np.uint8)
+        _native.check(lib.vkb_resize_u8(dv.ptr(full), self.height, self.width, dv.ptr(dst),
+                                        resized_height, resized_width, 1, cv_resize_interpolation,
+                                        dv.stream_ptr()), 'vkb_resize_u8')
+        _native.check(lib.vkb_threshold_u8(dv.ptr(dst), dv.ptr(dst), resized_height * resized_width,
+                                           int(binarization_threshold), 0, 1, dv.stream_ptr()),
+                      'vkb_threshold_u8')
+        return Mask(mat=dst)
 
     def to_shifted_mask(self, offset_y: int = 0, offset_x: int = 0):
         assert self.box
