@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 
 BASE_SEED = 133700  # the reference pool's default rng seed (vkit/utility/pool.py:53)
 PAGE_SHAPE = (1024, 1024)
+# BASELINE.json: "synthesized 1024x1024 OCR pages/sec at 1/2/4/8 B200; remap HBM GB/s vs peak"
+METRIC = 'synthesized_1024x1024_ocr_pages_per_s'
 BATCH = 256
 CAMERA_OPS = ('camera_plane_only', 'camera_cubic_curve', 'camera_plane_line_fold',
               'camera_plane_line_curve')
@@ -277,7 +279,7 @@ def run_reference(args, rank: int, world: int):
     total_pages = pages_per_step * args.steps
     value = total_pages / sum(walls)
     line = {
-        'impl': 'reference', 'metric': 'pages_per_s', 'value': value, 'unit': 'pages/s',
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pages/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1000.0 * sum(walls) / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
@@ -439,7 +441,7 @@ def main():
         achieved = algorithmic_bytes / (remap_mean_ms * 1e-3) / 1e9
         value = pages_done / (elapsed_ms * 1e-3)
         line = {
-            'metric': 'pages_per_s', 'value': value, 'unit': 'pages/s', 'n_gpus': world,
+            'metric': METRIC, 'value': value, 'unit': 'pages/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic', 'config': workload_config(world),
