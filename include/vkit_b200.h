@@ -325,12 +325,16 @@ int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
 int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
                     const float* taps_dev, int32_t kh, int32_t kw, void* stream);
 
-/* cv.resize(uint8) for INTER_NEAREST and INTER_LINEAR (pixelation, photometric/effect.py:58-79;
- * Image.to_resized_image with those interpolations, element/image.py:836-852): bit exact
- * (11-bit fixed-point coefficients and cv2's 8-bit vertical pass). */
+/* cv.resize(uint8): INTER_NEAREST, INTER_LINEAR (11-bit fixed-point coefficients and cv2's 8-bit
+ * vertical pass), INTER_NEAREST_EXACT, INTER_LINEAR_EXACT -- all bit exact -- and INTER_CUBIC
+ * (pixelation, photometric/effect.py:58-79; Image.to_resized_image element/image.py:836-852;
+ * Mask.to_resized_mask element/mask.py:454-479; the interpolations page_resizing samples from,
+ * utility/opt.py:125-148, except LANCZOS4 / AREA). */
 #define VKB_INTER_NEAREST 0
 #define VKB_INTER_LINEAR 1
 #define VKB_INTER_CUBIC 2 /* cv2's own fixed-point path; the wheel's IPP default differs by +-1 on ~5 % of pixels */
+#define VKB_INTER_LINEAR_EXACT 5  /* cv2's codes: bit exact */
+#define VKB_INTER_NEAREST_EXACT 6
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
 

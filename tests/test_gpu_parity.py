@@ -965,11 +965,15 @@ def test_image_to_resized_image_linear_and_nearest(vk):
     port.use_cv2(False)
     image, _, _ = make_inputs(77, (100, 133))
     img = element.Image(mat=image)
-    for (h, w) in ((37, 200), (150, 61), (100, 133)):
+    for (h, w) in ((37, 200), (150, 61), (100, 133), (150, 200), (231, 140)):
         got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=1).mat
         assert np.array_equal(got, port.resize_u8(image, (w, h)))
         got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=0).mat
         assert np.array_equal(got, port.resize_u8(image, (w, h), nearest=True))
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=5).mat
+        assert np.array_equal(got, port.resize_exact_u8(image, (w, h)))  # INTER_LINEAR_EXACT
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=6).mat
+        assert np.array_equal(got, port.resize_exact_u8(image, (w, h), nearest=True))
     with pytest.raises(NotImplementedError):
         img.to_resized_image(resized_height=50, cv_resize_interpolation=3)  # cv.INTER_AREA
 
@@ -1013,7 +1017,9 @@ def test_mask_to_resized_mask(vk):
     for (h, w) in ((37, 200), (150, 61)):
         for inter, model in ((0, lambda: port.resize_u8(full, (w, h), nearest=True)),
                              (1, lambda: port.resize_u8(full, (w, h))),
-                             (2, lambda: port.resize_cubic_u8(full, (w, h)))):
+                             (2, lambda: port.resize_cubic_u8(full, (w, h))),
+                             (5, lambda: port.resize_exact_u8(full, (w, h))),
+                             (6, lambda: port.resize_exact_u8(full, (w, h), nearest=True))):
             for thr in (0, 127):
                 got = m.to_resized_mask(resized_height=h, resized_width=w,
                                         cv_resize_interpolation=inter,

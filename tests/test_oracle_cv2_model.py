@@ -111,3 +111,32 @@ def test_camera_functions(rng):
         p = pts.astype(dtype)
         ref, _ = cv.projectPoints(p, rvec, tvec, K, np.zeros(5))
         assert _same(cm.project_points(p, rvec, tvec, K), ref.reshape(-1, 2))
+
+
+@pytest.mark.parametrize('shape', [(64, 96), (100, 133), (77, 50)])
+def test_resize_models_vs_cv2(shape):
+    """The oracle's cv.resize restatements against the cv2 wheel: NEAREST, LINEAR, NEAREST_EXACT
+    and LINEAR_EXACT bit for bit; CUBIC against cv2 with IPP switched off (its own fixed-point
+    path, <= 0.2 % of the pixels off by one where cv2's SIMD vertical pass rounds in float)."""
+    import cv2 as cv
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    for ratio in (0.13, 0.37, 0.5, 0.8, 1.07, 1.5, 2.3):
+        dsize = (max(1, round(shape[1] * ratio)), max(1, round(shape[0] * ratio)))
+        assert np.array_equal(port.resize_u8(img, dsize), cv.resize(img, dsize, interpolation=cv.INTER_LINEAR))
+        assert np.array_equal(port.resize_u8(img, dsize, nearest=True),
+                              cv.resize(img, dsize, interpolation=cv.INTER_NEAREST))
+        assert np.array_equal(port.resize_exact_u8(img, dsize),
+                              cv.resize(img, dsize, interpolation=cv.INTER_LINEAR_EXACT))
+        assert np.array_equal(port.resize_exact_u8(img, dsize, nearest=True),
+                              cv.resize(img, dsize, interpolation=cv.INTER_NEAREST_EXACT))
+        use_ipp = cv.ipp.useIPP()
+        cv.ipp.setUseIPP(False)
+        try:
+            ref = cv.resize(img, dsize, interpolation=cv.INTER_CUBIC)
+        finally:
+            cv.ipp.setUseIPP(use_ipp)
+        diff = np.abs(port.resize_cubic_u8(img, dsize).astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3

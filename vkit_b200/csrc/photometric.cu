@@ -646,17 +646,37 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const uint8_t* __restrict
 // ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2) and INTER_NEAREST (floor(x / scale)).
 // pixelation (photometric/effect.py:58-79) = linear down + nearest up.  Thread per dst pixel.
 // ============================================================================================
+// Columns outside the source get fraction 0; rows keep their fraction and clip the two row
+// indices (cv2's vertical pass then splits one row over both coefficients, which matters to the
+// last bit when the horizontal pass interpolated).
+template <bool ROWS>
 __device__ __forceinline__ void resize_lin_coef(int d, double scale, int sn, int& s0, int& s1,
                                                 int& a0, int& a1) {
     float f = (float)(((double)d + 0.5) * scale - 0.5);
     int si = (int)floorf(f);
     f -= (float)si;
-    if (si < 0) { si = 0; f = 0.f; }
-    if (si >= sn - 1) { si = sn - 1; f = 0.f; }
-    s0 = si;
-    s1 = min(si + 1, sn - 1);
+    if (!ROWS) {
+        if (si < 0) { si = 0; f = 0.f; }
+        if (si >= sn - 1) { si = sn - 1; f = 0.f; }
+    }
+    s0 = min(max(si, 0), sn - 1);
+    s1 = min(max(si + 1, 0), sn - 1);
     a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
     a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// cv.INTER_LINEAR_EXACT (bit-exact by design in cv2): double source position, 8-bit coefficients
+// rint(frac * 256), 8.8 horizontal pass, vertical pass (v + 2^15) >> 16
+__device__ __forceinline__ void resize_lin_exact_coef(int d, double scale, int sn, int& s0, int& s1,
+                                                      int& c1) {
+    const double pos = ((double)d + 0.5) * scale - 0.5;
+    int si = (int)floor(pos);
+    double fr = pos - (double)si;
+    if (si < 0) { si = 0; fr = 0.0; }
+    if (si >= sn - 1) { si = sn - 1; fr = 0.0; }
+    s0 = si;
+    s1 = min(si + 1, sn - 1);
+    c1 = (int)rint(fr * 256.0);
 }
 
 template <int C>
@@ -667,6 +687,31 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
     uint8_t* d = dst + ((long long)y * dw + x) * C;
+    if (nearest == 2) {
+        // cv.INTER_NEAREST_EXACT: 16.16 fixed point on pixel centres (resizeNN_bitexact)
+        const int ifx = ((sw << 16) + dw / 2) / dw, ifx0 = ifx / 2 - (sw % 2);
+        const int ify = ((sh << 16) + dh / 2) / dh, ify0 = ify / 2 - (sh % 2);
+        const int sx = min((ifx0 + ifx * x) >> 16, sw - 1);
+        const int sy = min((ify0 + ify * y) >> 16, sh - 1);
+        const uint8_t* p = src + ((long long)sy * sw + sx) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) d[c] = p[c];
+        return;
+    }
+    if (nearest == 3) {
+        int x0, x1, cx, y0, y1, cy;
+        resize_lin_exact_coef(x, scale_x, sw, x0, x1, cx);
+        resize_lin_exact_coef(y, scale_y, sh, y0, y1, cy);
+        const uint8_t* r0 = src + (long long)y0 * sw * C;
+        const uint8_t* r1 = src + (long long)y1 * sw * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int h0 = (int)r0[x0 * C + c] * (256 - cx) + (int)r0[x1 * C + c] * cx;
+            const int h1 = (int)r1[x0 * C + c] * (256 - cx) + (int)r1[x1 * C + c] * cx;
+            d[c] = (uint8_t)min(max((h0 * (256 - cy) + h1 * cy + 32768) >> 16, 0), 255);
+        }
+        return;
+    }
     if (nearest) {
         const int sx = min((int)floor((double)x * scale_x), sw - 1);
         const int sy = min((int)floor((double)y * scale_y), sh - 1);
@@ -676,8 +721,8 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         return;
     }
     int x0, x1, ax0, ax1, y0, y1, by0, by1;
-    resize_lin_coef(x, scale_x, sw, x0, x1, ax0, ax1);
-    resize_lin_coef(y, scale_y, sh, y0, y1, by0, by1);
+    resize_lin_coef<false>(x, scale_x, sw, x0, x1, ax0, ax1);
+    resize_lin_coef<true>(y, scale_y, sh, y0, y1, by0, by1);
     const uint8_t* r0 = src + (long long)y0 * sw * C;
     const uint8_t* r1 = src + (long long)y1 * sw * C;
 #pragma unroll
@@ -1356,8 +1401,11 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
-                    || interpolation == VKB_INTER_CUBIC,
-                "interpolation must be VKB_INTER_NEAREST, VKB_INTER_LINEAR or VKB_INTER_CUBIC");
+                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LINEAR_EXACT
+                    || interpolation == VKB_INTER_NEAREST_EXACT,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LINEAR_EXACT / NEAREST_EXACT");
+    VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
+                "planes of at most 32767 pixels per side");
     // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
     const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
@@ -1372,7 +1420,9 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
             resize_cubic_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
         return check_launch("resize_cubic_u8_kernel");
     }
-    const int nearest = interpolation == VKB_INTER_NEAREST;
+    const int nearest = interpolation == VKB_INTER_NEAREST ? 1
+                        : interpolation == VKB_INTER_NEAREST_EXACT ? 2
+                        : interpolation == VKB_INTER_LINEAR_EXACT ? 3 : 0;
     if (channels == 1)
         resize_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
     else if (channels == 3)

@@ -191,10 +191,10 @@ class Mask(DualStorage, Shapable):
         assert not self.box
         resized_height, resized_width = generate_resized_shape(self.height, self.width,
                                                                resized_height, resized_width)
-        if cv_resize_interpolation not in (0, 1, 2):
+        if cv_resize_interpolation not in (0, 1, 2, 5, 6):
             raise NotImplementedError(
-                'to_resized_mask: cv.INTER_NEAREST, INTER_LINEAR and INTER_CUBIC have device '
-                'kernels (AREA / LANCZOS4 / *_EXACT are "next" rows)')
+                'to_resized_mask: cv.INTER_NEAREST / LINEAR / CUBIC / LINEAR_EXACT / NEAREST_EXACT '
+                'have device kernels (AREA / LANCZOS4 are "next" rows)')
         lib = _native.lib()
         src = self.dev
         n = self.height * self.width
