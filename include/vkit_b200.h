@@ -338,6 +338,13 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
 
+/* cv.resize(float32, one channel): ScoreMap.to_resized_score_map (element/score_map.py:616-637).
+ * cv2's float path restated with every product and sum rounded to float32 in tap order; cv2's
+ * own result depends on its backend (Intel IPP by default) and agrees to ~5e-6.  clip01 != 0
+ * fuses the np.clip(mat, 0, 1) the reference applies to probability maps. */
+int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
+                   int32_t dst_w, int32_t interpolation, int32_t clip01, void* stream);
+
 /* dst = src > threshold ? high : low -- the two binarisations of Mask.to_resized_mask
  * (element/mask.py:454-479: mask * 255 before cv.resize, > threshold after).  In place allowed. */
 int vkb_threshold_u8(const uint8_t* src, uint8_t* dst, int64_t n, int32_t threshold, int32_t low,

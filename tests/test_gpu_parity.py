@@ -978,6 +978,36 @@ def test_image_to_resized_image_linear_and_nearest(vk):
         img.to_resized_image(resized_height=50, cv_resize_interpolation=3)  # cv.INTER_AREA
 
 
+def test_score_map_to_resized_score_map(vk):
+    """ScoreMap.to_resized_score_map / to_conducted_resized_score_map == the oracle's float32
+    restatement of cv.resize bit for bit (pinned against cv2 in test_oracle_cv2_model.py), with
+    the probability clip fused."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    rng = np.random.default_rng(5)
+    mat = rng.random((100, 133), dtype=np.float32)
+    for is_prob in (True, False):
+        src = mat if is_prob else (mat * 7 - 3).astype(np.float32)
+        score_map = element.ScoreMap(mat=src, is_prob=is_prob)
+        for (h, w) in ((37, 200), (150, 61), (100, 133), (150, 200), (231, 140)):
+            for inter in (0, 1, 2):
+                got = score_map.to_resized_score_map(resized_height=h, resized_width=w,
+                                                     cv_resize_interpolation=inter)
+                assert got.is_prob == is_prob and got.shape == (h, w)
+                want = port.resize_f32(src, (w, h), inter, clip01=is_prob)
+                assert np.array_equal(got.mat, want), (is_prob, h, w, inter)
+    # default = INTER_CUBIC, one side given keeps the aspect ratio
+    got = element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50)
+    assert got.shape == (50, round(133 * 50 / 100))
+    boxed = element.ScoreMap(mat=mat[10:40, 20:90].copy(), box=element.Box(up=10, down=39, left=20, right=89))
+    resized = boxed.to_conducted_resized_score_map((100, 133), resized_height=200, resized_width=266)
+    assert resized.box.shape == resized.shape
+    assert np.array_equal(resized.mat, port.resize_f32(mat[10:40, 20:90], (resized.width, resized.height), 2, clip01=True))
+    with pytest.raises(NotImplementedError):
+        element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=4)
+
+
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")
 def test_cubic_resize_and_zoom_in_blur(vk, case):
     """INTER_CUBIC on the device == the oracle's restatement of cv2's own fixed-point cubic, bit

@@ -140,3 +140,33 @@ def test_resize_models_vs_cv2(shape):
             cv.ipp.setUseIPP(use_ipp)
         diff = np.abs(port.resize_cubic_u8(img, dsize).astype(int) - ref.astype(int))
         assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3
+
+
+@pytest.mark.parametrize('shape', [(67, 91), (40, 33)])
+def test_resize_f32_model_vs_cv2(shape):
+    """ScoreMap resize (float32): the oracle's plain-float32 restatement against cv2.  Without IPP
+    NEAREST and LINEAR are bit identical and CUBIC is within 1 ulp (cv2 contracts to FMA); the
+    wheel's default IPP backend agrees to 1e-5."""
+    import cv2 as cv
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    rng = np.random.default_rng(shape[1])
+    mat = rng.random(shape, dtype=np.float32)
+    use_ipp = cv.ipp.useIPP()
+    try:
+        for dsize in ((40, 30), (200, 150), (91, 120), (133, 67), (300, 300)):
+            for inter in (0, 1, 2):
+                got = port.resize_f32(mat, dsize, inter)
+                cv.ipp.setUseIPP(False)
+                own = cv.resize(mat, dsize, interpolation=inter)
+                cv.ipp.setUseIPP(True)
+                ipp = cv.resize(mat, dsize, interpolation=inter)
+                if inter < 2:
+                    assert np.array_equal(got, own)
+                else:
+                    assert np.abs(got - own).max() <= 2.4e-7
+                assert np.abs(got - ipp).max() <= 1e-5
+                clipped = port.resize_f32(mat, dsize, inter, clip01=True)
+                assert np.array_equal(clipped, np.clip(got, 0.0, 1.0))
+    finally:
+        cv.ipp.setUseIPP(use_ipp)

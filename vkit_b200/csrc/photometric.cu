@@ -735,6 +735,75 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
 }
 
 // ============================================================================================
+// cv.resize(float32) for ScoreMap.to_resized_score_map (element/score_map.py:616-637): cv2's
+// float path -- float32 coefficients, horizontal pass then vertical pass, every product and sum
+// rounded to float32 in tap order (no contraction, so the CPU restatement is bit identical),
+// replicated borders; `clip01` fuses the np.clip(mat, 0, 1) of probability maps.
+// mode 0 NEAREST, 1 LINEAR, 2 CUBIC.
+// ============================================================================================
+__device__ __forceinline__ void resize_cubic_coef_f32(int d, double scale, int& si, float* c) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    si = (int)floorf(f);
+    f = __fsub_rn(f, (float)si);
+    const float A = -0.75f;
+    const float f1 = __fadd_rn(f, 1.f), g = __fsub_rn(1.f, f);
+    c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, f1), 5.f * A), f1), 8.f * A), f1), 4.f * A);
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, f), A + 3.f), f), f), 1.f);
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, g), A + 3.f), g), g), 1.f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict__ src, int sh, int sw,
+                                                         float* __restrict__ dst, int dh, int dw,
+                                                         double scale_x, double scale_y, int clip01) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    float v;
+    if (K == 1) {
+        const int sx = min((int)floor((double)x * scale_x), sw - 1);
+        const int sy = min((int)floor((double)y * scale_y), sh - 1);
+        v = src[(long long)sy * sw + sx];
+    } else {
+        int x0, y0;
+        float cx[4], cy[4];
+        if (K == 4) {
+            resize_cubic_coef_f32(x, scale_x, x0, cx);
+            resize_cubic_coef_f32(y, scale_y, y0, cy);
+            x0 -= 1;
+            y0 -= 1;
+        } else {
+            float fx = (float)(((double)x + 0.5) * scale_x - 0.5);
+            x0 = (int)floorf(fx);
+            fx = __fsub_rn(fx, (float)x0);
+            if (x0 < 0) { x0 = 0; fx = 0.f; }  // columns: fraction 0 at the border; rows clip
+            if (x0 >= sw - 1) { x0 = sw - 1; fx = 0.f; }
+            float fy = (float)(((double)y + 0.5) * scale_y - 0.5);
+            y0 = (int)floorf(fy);
+            fy = __fsub_rn(fy, (float)y0);
+            cx[0] = __fsub_rn(1.f, fx); cx[1] = fx;
+            cy[0] = __fsub_rn(1.f, fy); cy[1] = fy;
+        }
+        int xs[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) xs[i] = min(max(x0 + i, 0), sw - 1);
+        v = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw;
+            float hsum = __fmul_rn(row[xs[0]], cx[0]);
+#pragma unroll
+            for (int i = 1; i < K; ++i) hsum = __fadd_rn(hsum, __fmul_rn(row[xs[i]], cx[i]));
+            const float t = __fmul_rn(hsum, cy[j]);
+            v = j ? __fadd_rn(v, t) : t;
+        }
+    }
+    if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+    dst[(long long)y * dw + x] = v;
+}
+
+// ============================================================================================
 // mat[pos_y, pos_x]: the pixel permutation of glass_blur (photometric/blur.py:216-264).
 // ============================================================================================
 template <int C>
@@ -1430,6 +1499,28 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     else
         resize_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
     return check_launch("resize_u8_kernel");
+}
+
+extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst,
+                              int32_t dst_h, int32_t dst_w, int32_t interpolation, int32_t clip01,
+                              void* stream) {
+    VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
+    VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
+                    || interpolation == VKB_INTER_CUBIC,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC");
+    VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
+                "planes of at most 32767 pixels per side");
+    const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
+    const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
+    dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (interpolation == VKB_INTER_NEAREST)
+        resize_f32_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
+    else if (interpolation == VKB_INTER_LINEAR)
+        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
+    else
+        resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
+    return check_launch("resize_f32_kernel");
 }
 
 extern "C" int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,

@@ -107,6 +107,43 @@ class ScoreMap(DualStorage, Shapable):
         return attrs.evolve(self, box=self.box.to_shifted_box(offset_y=offset_y, offset_x=offset_x),
                             skip_prob_check=True)
 
+    _CV_INTER = {0: 0, 1: 1, 2: 2}  # cv.INTER_NEAREST / INTER_LINEAR / INTER_CUBIC
+
+    def to_conducted_resized_score_map(self, shapable_or_shape, resized_height: Optional[int] = None,
+                                       resized_width: Optional[int] = None,
+                                       cv_resize_interpolation: int = 2):
+        """element/score_map.py:594-614: resize the box and the scores it holds together."""
+        assert self.box
+        resized_box = self.box.to_conducted_resized_box(
+            shapable_or_shape=shapable_or_shape, resized_height=resized_height,
+            resized_width=resized_width)
+        resized = self.to_box_detached().to_resized_score_map(
+            resized_height=resized_box.height, resized_width=resized_box.width,
+            cv_resize_interpolation=cv_resize_interpolation)
+        return resized.to_box_attached(resized_box)
+
+    def to_resized_score_map(self, resized_height: Optional[int] = None,
+                             resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
+        """element/score_map.py:616-637: cv.resize of the float32 map (INTER_CUBIC by default),
+        clipped to [0, 1] when it is a probability map -- the clip is fused into the kernel.
+        The device restates cv2's float path in plain float32 (vkb_resize_f32); cv2's own result
+        depends on its backend (IPP by default) and agrees to about 5e-6."""
+        from .. import _native
+        from .opt import generate_shape_and_resized_shape
+        assert not self.box
+        _, _, resized_height, resized_width = generate_shape_and_resized_shape(
+            self, resized_height, resized_width)
+        if cv_resize_interpolation not in self._CV_INTER:
+            raise NotImplementedError(
+                'to_resized_score_map: cv.INTER_NEAREST / LINEAR / CUBIC have device kernels')
+        src = self.dev
+        dst = dv.empty((resized_height, resized_width), np.float32)
+        _native.check(_native.lib().vkb_resize_f32(
+            dv.ptr(src), self.height, self.width, dv.ptr(dst), resized_height, resized_width,
+            self._CV_INTER[cv_resize_interpolation], int(self.is_prob), dv.stream_ptr()),
+            'vkb_resize_f32')
+        return attrs.evolve(self, mat=dst, skip_prob_check=True)
+
     def to_cropped_score_map(self, up=None, down=None, left=None, right=None):
         assert not self.box
         up = up or 0
