@@ -333,6 +333,7 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
 #define VKB_INTER_NEAREST 0
 #define VKB_INTER_LINEAR 1
 #define VKB_INTER_CUBIC 2 /* cv2's own fixed-point path; the wheel's IPP default differs by +-1 on ~5 % of pixels */
+#define VKB_INTER_LANCZOS4 4 /* bit exact (uint8) */
 #define VKB_INTER_LINEAR_EXACT 5  /* cv2's codes: bit exact */
 #define VKB_INTER_NEAREST_EXACT 6
 int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,

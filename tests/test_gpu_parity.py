@@ -974,6 +974,11 @@ def test_image_to_resized_image_linear_and_nearest(vk):
         assert np.array_equal(got, port.resize_exact_u8(image, (w, h)))  # INTER_LINEAR_EXACT
         got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=6).mat
         assert np.array_equal(got, port.resize_exact_u8(image, (w, h), nearest=True))
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=4).mat
+        assert np.array_equal(got, port.resize_lanczos4_u8(image, (w, h)))  # INTER_LANCZOS4
+        gray = element.Image(mat=np.ascontiguousarray(image[:, :, 1]), mode=element.ImageMode.GRAYSCALE)
+        got = gray.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=4).mat
+        assert np.array_equal(got, port.resize_lanczos4_u8(image[:, :, 1], (w, h)))
     with pytest.raises(NotImplementedError):
         img.to_resized_image(resized_height=50, cv_resize_interpolation=3)  # cv.INTER_AREA
 
@@ -991,7 +996,7 @@ def test_score_map_to_resized_score_map(vk):
         src = mat if is_prob else (mat * 7 - 3).astype(np.float32)
         score_map = element.ScoreMap(mat=src, is_prob=is_prob)
         for (h, w) in ((37, 200), (150, 61), (100, 133), (150, 200), (231, 140)):
-            for inter in (0, 1, 2):
+            for inter in (0, 1, 2, 4, 5, 6):
                 got = score_map.to_resized_score_map(resized_height=h, resized_width=w,
                                                      cv_resize_interpolation=inter)
                 assert got.is_prob == is_prob and got.shape == (h, w)
@@ -1005,7 +1010,7 @@ def test_score_map_to_resized_score_map(vk):
     assert resized.box.shape == resized.shape
     assert np.array_equal(resized.mat, port.resize_f32(mat[10:40, 20:90], (resized.width, resized.height), 2, clip01=True))
     with pytest.raises(NotImplementedError):
-        element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=4)
+        element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=3)
 
 
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")
@@ -1048,6 +1053,7 @@ def test_mask_to_resized_mask(vk):
         for inter, model in ((0, lambda: port.resize_u8(full, (w, h), nearest=True)),
                              (1, lambda: port.resize_u8(full, (w, h))),
                              (2, lambda: port.resize_cubic_u8(full, (w, h))),
+                             (4, lambda: port.resize_lanczos4_u8(full, (w, h))),
                              (5, lambda: port.resize_exact_u8(full, (w, h))),
                              (6, lambda: port.resize_exact_u8(full, (w, h), nearest=True))):
             for thr in (0, 127):

@@ -762,8 +762,16 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
     if (x >= dw || y >= dh) return;
     float v;
     if (K == 1) {
-        const int sx = min((int)floor((double)x * scale_x), sw - 1);
-        const int sy = min((int)floor((double)y * scale_y), sh - 1);
+        int sx, sy;
+        if (clip01 & 2) {  // cv.INTER_NEAREST_EXACT: 16.16 fixed point on pixel centres
+            const int ifx = ((sw << 16) + dw / 2) / dw, ifx0 = ifx / 2 - (sw % 2);
+            const int ify = ((sh << 16) + dh / 2) / dh, ify0 = ify / 2 - (sh % 2);
+            sx = min((ifx0 + ifx * x) >> 16, sw - 1);
+            sy = min((ify0 + ify * y) >> 16, sh - 1);
+        } else {
+            sx = min((int)floor((double)x * scale_x), sw - 1);
+            sy = min((int)floor((double)y * scale_y), sh - 1);
+        }
         v = src[(long long)sy * sw + sx];
     } else {
         int x0, y0;
@@ -799,8 +807,113 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
             v = j ? __fadd_rn(v, t) : t;
         }
     }
-    if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+    if (clip01 & 1) v = fminf(fmaxf(v, 0.f), 1.f);
     dst[(long long)y * dw + x] = v;
+}
+
+// ============================================================================================
+// cv.resize(INTER_LANCZOS4), uint8 (C channels) and float32 (one channel): the 8 taps of
+// cv::interpolateLanczos4 (double sin / cos of -(frac + 3) pi / 4 rotated by multiples of 45
+// degrees, divided by y^2, normalised in float32).  A 32 x 8 block needs 32 column and 8 row tap
+// sets: 40 threads compute them into shared memory, then every thread gathers its 8 x 8
+// neighbourhood with replicated borders.  uint8: taps rounded to 11 bits, integer passes,
+// (sum + 2^21) >> 22 (bit identical to cv2, IPP or not); float32: products and sums rounded to
+// float32 in tap order.
+// ============================================================================================
+__device__ __forceinline__ void lanczos4_taps(float frac, float* c) {
+    const double s45 = 0.70710678118654752440084436210485;
+    const double rot_s[8] = {1.0, -s45, 0.0, s45, -1.0, s45, 0.0, -s45};
+    const double rot_c[8] = {0.0, -s45, 1.0, -s45, 0.0, s45, -1.0, s45};
+    const double pi = 3.1415926535897932384626433832795;
+    const float x3 = __fadd_rn(frac, 3.f);
+    const double y0 = __dmul_rn(__dmul_rn(-(double)x3, pi), 0.25);
+    double s0, c0;
+    sincos(y0, &s0, &c0);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float d = __fsub_rn(x3, (float)i);
+        if (fabsf(d) >= 1e-6f) {
+            const double y = __dmul_rn(__dmul_rn(-(double)d, pi), 0.25);
+            const double num = __dadd_rn(__dmul_rn(rot_s[i], s0), __dmul_rn(rot_c[i], c0));
+            c[i] = (float)__ddiv_rn(num, __dmul_rn(y, y));
+        } else {
+            c[i] = 1e30f;
+        }
+        sum = __fadd_rn(sum, c[i]);
+    }
+    sum = __fdiv_rn(1.f, sum);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __fmul_rn(c[i], sum);
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restrict__ src, int sh, int sw,
+                                                              T* __restrict__ dst, int dh, int dw,
+                                                              double scale_x, double scale_y, int clip01) {
+    __shared__ float taps[40][8];
+    __shared__ int first[40];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 40) {
+        const bool col = tid < 32;
+        const int d = col ? blockIdx.x * 32 + tid : blockIdx.y * 8 + (tid - 32);
+        float f = (float)(((double)d + 0.5) * (col ? scale_x : scale_y) - 0.5);
+        const int si = (int)floorf(f);
+        f = __fsub_rn(f, (float)si);
+        float c[8];
+        lanczos4_taps(f, c);
+        first[tid] = si - 3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) taps[tid][k] = c[k];
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float* cx = taps[threadIdx.x];
+    const float* cy = taps[32 + threadIdx.y];
+    const int x0 = first[threadIdx.x], y0 = first[32 + threadIdx.y];
+    int xs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xs[k] = min(max(x0 + k, 0), sw - 1) * C;
+    if constexpr (sizeof(T) == 1) {
+        int ax[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ax[k] = __float2int_rn(__fmul_rn(cx[k], 2048.f));
+        long long acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const T* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw * C;
+            const int ay = __float2int_rn(__fmul_rn(cy[j], 2048.f));
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                int hsum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hsum += (int)row[xs[k] + c] * ax[k];
+                acc[c] += (long long)hsum * ay;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const long long v = (acc[c] + (1 << 21)) >> 22;
+            dst[((long long)y * dw + x) * C + c] = (T)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    } else {
+        float v = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const T* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw;
+            float hsum = __fmul_rn(row[xs[0]], cx[0]);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) hsum = __fadd_rn(hsum, __fmul_rn(row[xs[k]], cx[k]));
+            const float t = __fmul_rn(hsum, cy[j]);
+            v = j ? __fadd_rn(v, t) : t;
+        }
+        if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+        dst[(long long)y * dw + x] = v;
+    }
 }
 
 // ============================================================================================
@@ -1470,9 +1583,9 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
-                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LINEAR_EXACT
-                    || interpolation == VKB_INTER_NEAREST_EXACT,
-                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LINEAR_EXACT / NEAREST_EXACT");
+                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LANCZOS4
+                    || interpolation == VKB_INTER_LINEAR_EXACT || interpolation == VKB_INTER_NEAREST_EXACT,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
@@ -1488,6 +1601,15 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
         else
             resize_cubic_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
         return check_launch("resize_cubic_u8_kernel");
+    }
+    if (interpolation == VKB_INTER_LANCZOS4) {
+        if (channels == 1)
+            resize_lanczos4_kernel<uint8_t, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
+        else if (channels == 3)
+            resize_lanczos4_kernel<uint8_t, 3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
+        else
+            resize_lanczos4_kernel<uint8_t, 4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
+        return check_launch("resize_lanczos4_kernel");
     }
     const int nearest = interpolation == VKB_INTER_NEAREST ? 1
                         : interpolation == VKB_INTER_NEAREST_EXACT ? 2
@@ -1506,20 +1628,27 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
                               void* stream) {
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
-                    || interpolation == VKB_INTER_CUBIC,
-                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC");
+                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LANCZOS4
+                    || interpolation == VKB_INTER_LINEAR_EXACT || interpolation == VKB_INTER_NEAREST_EXACT,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
     const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
     dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    if (interpolation == VKB_INTER_NEAREST)
-        resize_f32_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
-    else if (interpolation == VKB_INTER_LINEAR)
-        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
+    const int clip = clip01 ? 1 : 0;
+    if (interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_NEAREST_EXACT)
+        resize_f32_kernel<1><<<grid, dim3(32, 8), 0, st>>>(
+            src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y,
+            clip | (interpolation == VKB_INTER_NEAREST_EXACT ? 2 : 0));
+    else if (interpolation == VKB_INTER_LINEAR || interpolation == VKB_INTER_LINEAR_EXACT)
+        // cv::resize runs INTER_LINEAR for float data when INTER_LINEAR_EXACT is asked for
+        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+    else if (interpolation == VKB_INTER_CUBIC)
+        resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     else
-        resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip01);
+        resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     return check_launch("resize_f32_kernel");
 }
 
