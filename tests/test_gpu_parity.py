@@ -980,7 +980,7 @@ def test_image_to_resized_image_linear_and_nearest(vk):
         got = gray.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=4).mat
         assert np.array_equal(got, port.resize_lanczos4_u8(image[:, :, 1], (w, h)))
     with pytest.raises(NotImplementedError):
-        img.to_resized_image(resized_height=50, cv_resize_interpolation=3)  # cv.INTER_AREA
+        img.to_resized_image(resized_height=50, cv_resize_interpolation=7)  # cv.INTER_MAX
 
 
 def test_score_map_to_resized_score_map(vk):
@@ -1010,7 +1010,39 @@ def test_score_map_to_resized_score_map(vk):
     assert resized.box.shape == resized.shape
     assert np.array_equal(resized.mat, port.resize_f32(mat[10:40, 20:90], (resized.width, resized.height), 2, clip01=True))
     with pytest.raises(NotImplementedError):
-        element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=3)
+        element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=7)
+
+
+def test_inter_area_shrinking(vk):
+    """cv.INTER_AREA (page_resizing samples it when shrinking): Image, Mask and ScoreMap resizes ==
+    the oracle restatement bit for bit -- integer ratios (box sums, the 2x2 special case) and
+    fractional ratios (weight tables); enlarging raises."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    image, mask, score = make_inputs(31, (120, 180))
+    img, gray = element.Image(mat=image), element.Image(mat=np.ascontiguousarray(image[:, :, 2]),
+                                                         mode=element.ImageMode.GRAYSCALE)
+    msk, scm = element.Mask(mat=mask), element.ScoreMap(mat=score)
+    raw = element.ScoreMap(mat=(score * 9 - 4).astype(np.float32), is_prob=False)
+    full = (mask > 0).astype(np.uint8) * 255
+    for (h, w) in ((60, 90), (40, 60), (30, 45), (60, 180), (53, 77), (119, 100), (120, 179), (17, 31),
+                   (30, 60), (120, 180)):
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(image, (w, h))), (h, w)
+        got = gray.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(image[:, :, 2], (w, h))), (h, w)
+        got = msk.to_resized_mask(resized_height=h, resized_width=w, cv_resize_interpolation=3,
+                                  binarization_threshold=127).mat
+        assert np.array_equal(got, (port.resize_area(full, (w, h)) > 127).astype(np.uint8)), (h, w)
+        got = scm.to_resized_score_map(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(score, (w, h), clip01=True)), (h, w)
+        got = raw.to_resized_score_map(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(raw.mat, (w, h))), (h, w)
+    for element_obj, call in ((img, 'to_resized_image'), (msk, 'to_resized_mask'),
+                              (scm, 'to_resized_score_map')):
+        with pytest.raises(NotImplementedError):
+            getattr(element_obj, call)(resized_height=121, resized_width=180, cv_resize_interpolation=3)
 
 
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")

@@ -173,3 +173,37 @@ def test_resize_f32_model_vs_cv2(shape):
                 assert np.array_equal(clipped, np.clip(got, 0.0, 1.0))
     finally:
         cv.ipp.setUseIPP(use_ipp)
+
+
+@pytest.mark.parametrize('shape', [(120, 180), (97, 131)])
+def test_resize_area_model_vs_cv2(shape):
+    """INTER_AREA when shrinking (page_resizing's fifth interpolation): the oracle's restatement of
+    cv2's box-sum and weight-table paths.  uint8 bit for bit with and without IPP; float32 bit for
+    bit without IPP, within 1e-5 with it."""
+    import cv2 as cv
+    from oracle import vkit_port as port
+    port.use_cv2(False)
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    mat = rng.random(shape, dtype=np.float32)
+    h, w = shape
+    sizes = [(w // 2, h // 2), (w // 3, h // 3), (w // 4, h // 4), (w, h // 2), (77, 53), (100, 89),
+             (w - 1, h), (31, 17), (w // 3, h // 4), (w, h)]
+    use_ipp = cv.ipp.useIPP()
+    try:
+        for dsize in sizes:
+            for ipp in (False, True):
+                cv.ipp.setUseIPP(ipp)
+                assert np.array_equal(port.resize_area(img, dsize),
+                                      cv.resize(img, dsize, interpolation=cv.INTER_AREA)), dsize
+                assert np.array_equal(port.resize_area(img[:, :, 0], dsize),
+                                      cv.resize(img[:, :, 0], dsize, interpolation=cv.INTER_AREA))
+                got, ref = port.resize_area(mat, dsize), cv.resize(mat, dsize, interpolation=cv.INTER_AREA)
+                if ipp:
+                    assert np.abs(got - ref).max() <= 1e-5
+                else:
+                    assert np.array_equal(got, ref), dsize
+    finally:
+        cv.ipp.setUseIPP(use_ipp)
+    with pytest.raises(NotImplementedError):
+        port.resize_area(img, (w + 1, h))

@@ -115,7 +115,7 @@ class Rect(ctypes.Structure):
  OP_COLOR_BALANCE, OP_PERMUTE, OP_BOUNDARY_EQ, OP_NOISE, OP_LINE_STREAK) = range(11)
 MAX_COLOR_OPS = 8
 INTER_NEAREST, INTER_LINEAR, INTER_CUBIC = 0, 1, 2
-INTER_LANCZOS4, INTER_LINEAR_EXACT, INTER_NEAREST_EXACT = 4, 5, 6
+INTER_AREA, INTER_LANCZOS4, INTER_LINEAR_EXACT, INTER_NEAREST_EXACT = 3, 4, 5, 6
 NOISE_GAUSSIAN, NOISE_POISSON, NOISE_IMPULSE, NOISE_SPECKLE = range(4)
 
 

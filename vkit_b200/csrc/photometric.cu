@@ -917,6 +917,142 @@ __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restric
 }
 
 // ============================================================================================
+// cv.resize(INTER_AREA) when shrinking on both axes (what page_resizing samples), uint8 with C
+// channels and float32 with one.  Thread per destination pixel.
+//   FAST (integer ratios): box sum; uint8 2x2 -> (sum + 2) >> 2, otherwise
+//   round(float(sum) * float(1 / area)); float32 adds in cv2's unrolled order (groups of four in
+//   row-major tap order; the vector part of 2x2 rows pairs the two rows first).
+//   Otherwise: the weights of cv::computeResizeAreaTab recomputed per pixel in double (head /
+//   full / tail source pixels of the cell), horizontal accumulation then vertical accumulation in
+//   table order, all in float32 without contraction.
+// ============================================================================================
+struct AreaSpan {
+    int s0, n;
+    float a_head, a_mid, a_tail;
+    bool has_head, has_tail;
+    __device__ __forceinline__ float weight(int i) const {
+        return (has_head && i == 0) ? a_head : ((has_tail && i == n - 1) ? a_tail : a_mid);
+    }
+};
+
+__device__ __forceinline__ AreaSpan area_span(int d, double scale, int ssize) {
+    const double f1 = __dmul_rn((double)d, scale);
+    const double f2 = __dadd_rn(f1, scale);
+    const double cell = fmin(scale, __dsub_rn((double)ssize, f1));
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    AreaSpan r;
+    const double head = __dsub_rn((double)s1, f1), tail = __dsub_rn(f2, (double)s2);
+    r.has_head = head > 1e-3;
+    r.has_tail = tail > 1e-3;
+    r.a_head = (float)__ddiv_rn(head, cell);
+    r.a_mid = (float)__ddiv_rn(1.0, cell);
+    r.a_tail = (float)__ddiv_rn(fmin(fmin(tail, 1.0), cell), cell);
+    r.s0 = s1 - (r.has_head ? 1 : 0);
+    r.n = (r.has_head ? 1 : 0) + (s2 - s1) + (r.has_tail ? 1 : 0);
+    return r;
+}
+
+template <typename T, int C, bool FAST>
+__global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ src, int sh, int sw,
+                                                          T* __restrict__ dst, int dh, int dw,
+                                                          double scale_x, double scale_y, int isx,
+                                                          int isy, int clip01) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    T* d = dst + ((long long)y * dw + x) * C;
+    if constexpr (FAST) {
+        const int area = isx * isy;
+        const T* base = src + ((long long)y * isy * sw + (long long)x * isx) * C;
+        if constexpr (sizeof(T) == 1) {
+            const float scale = __fdiv_rn(1.f, (float)area);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                int sum = 0;
+                for (int ky = 0; ky < isy; ++ky)
+                    for (int kx = 0; kx < isx; ++kx) sum += base[((long long)ky * sw + kx) * C + c];
+                const int v = (isx == 2 && isy == 2) ? (sum + 2) >> 2
+                                                     : __float2int_rn(__fmul_rn((float)sum, scale));
+                d[c] = (T)min(max(v, 0), 255);
+            }
+        } else {
+            const float scale = __fdiv_rn(1.f, (float)area);
+            float v;
+            if (isx == 2 && isy == 2 && x < (dw & ~3)) {
+                v = __fadd_rn(__fadd_rn(base[0], base[1]), __fadd_rn(base[sw], base[sw + 1]));
+            } else {
+                v = 0.f;
+                int k = 0, ky = 0, kx = 0;
+                auto tap = [&]() {
+                    const float t = base[(long long)ky * sw + kx];
+                    if (++kx == isx) { kx = 0; ++ky; }
+                    return t;
+                };
+                for (; k + 4 <= area; k += 4) {
+                    float g = tap();  // one tap per statement: argument evaluation order is unspecified
+                    g = __fadd_rn(g, tap());
+                    g = __fadd_rn(g, tap());
+                    g = __fadd_rn(g, tap());
+                    v = k ? __fadd_rn(v, g) : g;
+                }
+                for (; k < area; ++k) {
+                    const float t = tap();
+                    v = k ? __fadd_rn(v, t) : t;
+                }
+            }
+            v = __fmul_rn(v, scale);
+            if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+            d[0] = v;
+        }
+    } else {
+        const AreaSpan xs = area_span(x, scale_x, sw);
+        const AreaSpan ys = area_span(y, scale_y, sh);
+        float acc[C];
+        for (int j = 0; j < ys.n; ++j) {
+            const T* row = src + ((long long)(ys.s0 + j) * sw + xs.s0) * C;
+            const float beta = ys.weight(j);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float h = __fmul_rn((float)row[c], xs.weight(0));
+                for (int i = 1; i < xs.n; ++i) h = __fadd_rn(h, __fmul_rn((float)row[i * C + c], xs.weight(i)));
+                const float t = __fmul_rn(beta, h);
+                acc[c] = j ? __fadd_rn(acc[c], t) : t;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if constexpr (sizeof(T) == 1) {
+                d[c] = (T)min(max(__float2int_rn(acc[c]), 0), 255);
+            } else {
+                float v = acc[c];
+                if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+                d[c] = v;
+            }
+        }
+    }
+}
+
+// cv::resize's choice between the integer-ratio box sum and the weight tables
+static bool area_is_fast(double scale_x, double scale_y, int& isx, int& isy) {
+    isx = (int)nearbyint(scale_x);
+    isy = (int)nearbyint(scale_y);
+    return fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
+}
+
+template <typename T, int C>
+static void launch_resize_area(const T* src, int sh, int sw, T* dst, int dh, int dw, double scale_x,
+                               double scale_y, int clip01, cudaStream_t st) {
+    int isx, isy;
+    dim3 grid((dw + 31) / 32, (dh + 7) / 8);
+    if (area_is_fast(scale_x, scale_y, isx, isy))
+        resize_area_kernel<T, C, true><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01);
+    else
+        resize_area_kernel<T, C, false><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01);
+}
+
+// ============================================================================================
 // mat[pos_y, pos_x]: the pixel permutation of glass_blur (photometric/blur.py:216-264).
 // ============================================================================================
 template <int C>
@@ -1583,9 +1719,12 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
-                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LANCZOS4
-                    || interpolation == VKB_INTER_LINEAR_EXACT || interpolation == VKB_INTER_NEAREST_EXACT,
-                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
+                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_AREA
+                    || interpolation == VKB_INTER_LANCZOS4 || interpolation == VKB_INTER_LINEAR_EXACT
+                    || interpolation == VKB_INTER_NEAREST_EXACT,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
+    VKB_REQUIRE(interpolation != VKB_INTER_AREA || (dst_h <= src_h && dst_w <= src_w),
+                "VKB_INTER_AREA is provided for shrinking on both axes");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
@@ -1601,6 +1740,12 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
         else
             resize_cubic_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
         return check_launch("resize_cubic_u8_kernel");
+    }
+    if (interpolation == VKB_INTER_AREA) {
+        if (channels == 1) launch_resize_area<uint8_t, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
+        else if (channels == 3) launch_resize_area<uint8_t, 3>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
+        else launch_resize_area<uint8_t, 4>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
+        return check_launch("resize_area_kernel");
     }
     if (interpolation == VKB_INTER_LANCZOS4) {
         if (channels == 1)
@@ -1628,9 +1773,12 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
                               void* stream) {
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
-                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_LANCZOS4
-                    || interpolation == VKB_INTER_LINEAR_EXACT || interpolation == VKB_INTER_NEAREST_EXACT,
-                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
+                    || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_AREA
+                    || interpolation == VKB_INTER_LANCZOS4 || interpolation == VKB_INTER_LINEAR_EXACT
+                    || interpolation == VKB_INTER_NEAREST_EXACT,
+                "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
+    VKB_REQUIRE(interpolation != VKB_INTER_AREA || (dst_h <= src_h && dst_w <= src_w),
+                "VKB_INTER_AREA is provided for shrinking on both axes");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
@@ -1647,6 +1795,8 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
         resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     else if (interpolation == VKB_INTER_CUBIC)
         resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+    else if (interpolation == VKB_INTER_AREA)
+        launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, st);
     else
         resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     return check_launch("resize_f32_kernel");

@@ -281,12 +281,12 @@ class Image(DualStorage, Shapable):
 
     # cv2 interpolation codes (cv.INTER_NEAREST / INTER_LINEAR / INTER_CUBIC)
     _CV_INTER = {0: _native.INTER_NEAREST, 1: _native.INTER_LINEAR, 2: _native.INTER_CUBIC,
-                 4: _native.INTER_LANCZOS4, 5: _native.INTER_LINEAR_EXACT, 6: _native.INTER_NEAREST_EXACT}
+                 3: _native.INTER_AREA, 4: _native.INTER_LANCZOS4, 5: _native.INTER_LINEAR_EXACT, 6: _native.INTER_NEAREST_EXACT}
 
     def to_resized_image(self, resized_height: Optional[int] = None,
                          resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
         """element/image.py:836-852.  The device resize reproduces cv.resize bit for bit for
-        INTER_NEAREST (0), INTER_LINEAR (1), INTER_LANCZOS4 (4), INTER_LINEAR_EXACT (5) and
+        INTER_NEAREST (0), INTER_LINEAR (1), INTER_AREA (3, shrinking only), INTER_LANCZOS4 (4), INTER_LINEAR_EXACT (5) and
         INTER_NEAREST_EXACT (6).
         INTER_CUBIC (2, the reference's default) follows
         cv2's own fixed-point path; the cv2 wheel routes cubic through Intel IPP, whose result
@@ -296,8 +296,12 @@ class Image(DualStorage, Shapable):
             self, resized_height, resized_width)
         if cv_resize_interpolation not in self._CV_INTER:
             raise NotImplementedError(
-                'to_resized_image: cv.INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / '
-                'NEAREST_EXACT have device kernels (INTER_AREA is a "next" row)')
+                'to_resized_image: cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT '
+                '/ NEAREST_EXACT have device kernels')
+        if cv_resize_interpolation == 3 and (resized_height > self.height
+                                             or resized_width > self.width):
+            raise NotImplementedError('to_resized_image: cv.INTER_AREA is provided for shrinking '
+                                      '(page_resizing samples it only then)')
         if self.mat_dtype != np.uint8:
             raise NotImplementedError('to_resized_image is provided for uint8 images')
         src = self.dev

@@ -107,8 +107,8 @@ class ScoreMap(DualStorage, Shapable):
         return attrs.evolve(self, box=self.box.to_shifted_box(offset_y=offset_y, offset_x=offset_x),
                             skip_prob_check=True)
 
-    # cv.INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT (= LINEAR for float) / NEAREST_EXACT
-    _CV_INTER = {0: 0, 1: 1, 2: 2, 4: 4, 5: 5, 6: 6}
+    # cv.INTER_NEAREST / LINEAR / CUBIC / AREA (shrinking) / LANCZOS4 / LINEAR_EXACT (= LINEAR for float) / NEAREST_EXACT
+    _CV_INTER = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6}
 
     def to_conducted_resized_score_map(self, shapable_or_shape, resized_height: Optional[int] = None,
                                        resized_width: Optional[int] = None,
@@ -136,8 +136,12 @@ class ScoreMap(DualStorage, Shapable):
             self, resized_height, resized_width)
         if cv_resize_interpolation not in self._CV_INTER:
             raise NotImplementedError(
-                'to_resized_score_map: cv.INTER_NEAREST / LINEAR / CUBIC / LANCZOS4 / LINEAR_EXACT / '
-                'NEAREST_EXACT have device kernels (INTER_AREA is a "next" row)')
+                'to_resized_score_map: cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / '
+                'LINEAR_EXACT / NEAREST_EXACT have device kernels')
+        if cv_resize_interpolation == 3 and (resized_height > self.height
+                                             or resized_width > self.width):
+            raise NotImplementedError('to_resized_score_map: cv.INTER_AREA is provided for '
+                                      'shrinking (page_resizing samples it only then)')
         src = self.dev
         dst = dv.empty((resized_height, resized_width), np.float32)
         _native.check(_native.lib().vkb_resize_f32(
