@@ -1045,6 +1045,37 @@ def test_inter_area_shrinking(vk):
             getattr(element_obj, call)(resized_height=121, resized_width=180, cv_resize_interpolation=3)
 
 
+@pytest.mark.parametrize('ratio', [0.6, 0.5, 1.3])
+def test_resize_page_elements(vk, ratio):
+    """compositing.resize_page_elements == PageResizingStep.run's seven resamples restated with the
+    oracle's cv.resize models, for every interpolation the step samples (AREA when shrinking)."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    from vkit_b200 import compositing
+    port.use_cv2(False)
+    image, mask, score = make_inputs(17, (150, 210))
+    _, mask2, score2 = make_inputs(18, (150, 210))
+    heights = [(score * 40).astype(np.float32), (score2 * 25).astype(np.float32)]
+    u8_models = {6: lambda m, d: port.resize_exact_u8(m, d, nearest=True),
+                 5: port.resize_exact_u8, 2: port.resize_cubic_u8, 4: port.resize_lanczos4_u8,
+                 3: port.resize_area}
+    codes = (6, 5, 2, 4, 3) if ratio < 1 else (6, 5, 2, 4)
+    rh, rw = round(ratio * 150), round(ratio * 210)
+    for code in codes:
+        got_image, got_masks, got_maps = compositing.resize_page_elements(
+            element.Image(mat=image), [element.Mask(mat=mask), element.Mask(mat=mask2)],
+            [element.ScoreMap(mat=h, is_prob=False) for h in heights], ratio, code)
+        assert got_image.shape == (rh, rw)
+        assert np.array_equal(got_image.mat, u8_models[code](image, (rw, rh))), code
+        for got, src in zip(got_masks, (mask, mask2)):
+            want = u8_models[code]((src > 0).astype(np.uint8) * 255, (rw, rh)) > 0
+            assert np.array_equal(got.mat, want.astype(np.uint8)), code
+        for got, src in zip(got_maps, heights):
+            want = port.resize_area(src, (rw, rh)) if code == 3 else port.resize_f32(src, (rw, rh), code)
+            assert np.array_equal(got.mat, want * np.float32(ratio)), code
+            assert not got.is_prob
+
+
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")
 def test_cubic_resize_and_zoom_in_blur(vk, case):
     """INTER_CUBIC on the device == the oracle's restatement of cv2's own fixed-point cubic, bit

@@ -192,13 +192,13 @@ def test_resize_area_model_vs_cv2(shape):
     use_ipp = cv.ipp.useIPP()
     try:
         for dsize in sizes:
+            got_rgb, got_gray = port.resize_area(img, dsize), port.resize_area(img[:, :, 0], dsize)
+            got = port.resize_area(mat, dsize)
             for ipp in (False, True):
                 cv.ipp.setUseIPP(ipp)
-                assert np.array_equal(port.resize_area(img, dsize),
-                                      cv.resize(img, dsize, interpolation=cv.INTER_AREA)), dsize
-                assert np.array_equal(port.resize_area(img[:, :, 0], dsize),
-                                      cv.resize(img[:, :, 0], dsize, interpolation=cv.INTER_AREA))
-                got, ref = port.resize_area(mat, dsize), cv.resize(mat, dsize, interpolation=cv.INTER_AREA)
+                assert np.array_equal(got_rgb, cv.resize(img, dsize, interpolation=cv.INTER_AREA)), dsize
+                assert np.array_equal(got_gray, cv.resize(img[:, :, 0], dsize, interpolation=cv.INTER_AREA))
+                ref = cv.resize(mat, dsize, interpolation=cv.INTER_AREA)
                 if ipp:
                     assert np.abs(got - ref).max() <= 1e-5
                 else:

@@ -240,3 +240,38 @@ def fill_polygons(target: Union[Mask, ScoreMap], polygons, value=1, keep_max_val
             dv.stream_ptr()), 'vkb_fill_polygons')
     target._after_device_write()
     return target
+
+
+# =============================================================================================
+# page_resizing
+# =============================================================================================
+def resize_page_elements(page_image: Image, masks: Sequence[Mask], height_score_maps: Sequence[ScoreMap],
+                         resize_ratio: float, cv_resize_interpolation: int):
+    """The data path of PageResizingStep.run (pipeline/text_detection/page_resizing.py:112-180):
+    the page image, its masks (active / char / seal-impression char / text-line) and its height
+    score maps (char / text-line) resized to round(ratio * shape) with ONE sampled cv2
+    interpolation (NEAREST_EXACT, LINEAR_EXACT, CUBIC, LANCZOS4, or AREA when shrinking --
+    utility/opt.py:125-148), the height scores multiplied by the ratio afterwards
+    (page_resizing.py:160-161, 177-180).  Seven device resamples, no host copy.
+    Returns (image, [masks], [score maps])."""
+    height, width = page_image.shape
+    resized_height = round(resize_ratio * height)
+    resized_width = round(resize_ratio * width)
+    image = page_image.to_resized_image(resized_height=resized_height, resized_width=resized_width,
+                                        cv_resize_interpolation=cv_resize_interpolation)
+    resized_masks = []
+    for mask in masks:
+        assert mask.shape == (height, width)
+        resized_masks.append(mask.to_resized_mask(resized_height=resized_height,
+                                                  resized_width=resized_width,
+                                                  cv_resize_interpolation=cv_resize_interpolation))
+    resized_score_maps = []
+    for score_map in height_score_maps:
+        assert score_map.shape == (height, width)
+        resized = score_map.to_resized_score_map(resized_height=resized_height,
+                                                 resized_width=resized_width,
+                                                 cv_resize_interpolation=cv_resize_interpolation)
+        # "Scores are resized as well": float32 map times the Python float ratio, as NumPy does
+        resized.assign_mat(resized.dev * float(np.float32(resize_ratio)))
+        resized_score_maps.append(resized)
+    return image, resized_masks, resized_score_maps
