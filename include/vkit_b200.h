@@ -349,6 +349,13 @@ int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst
 int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
                    int32_t dst_w, int32_t interpolation, int32_t clip01, void* stream);
 
+/* Mask.to_resized_mask (element/mask.py:454-479) in ONE pass: the source reads as (v > 0) * 255,
+ * cv.resize with `interpolation` (same codes and exactness as vkb_resize_u8), the result is stored
+ * as (resized > binarization_threshold) in {0, 1}. */
+int vkb_resize_mask_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst, int32_t dst_h,
+                       int32_t dst_w, int32_t interpolation, int32_t binarization_threshold,
+                       void* stream);
+
 /* dst = src > threshold ? high : low -- the two binarisations of Mask.to_resized_mask
  * (element/mask.py:454-479: mask * 255 before cv.resize, > threshold after).  In place allowed. */
 int vkb_threshold_u8(const uint8_t* src, uint8_t* dst, int64_t n, int32_t threshold, int32_t low,

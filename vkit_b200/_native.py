@@ -193,6 +193,7 @@ def _declare(lib):
     lib.vkb_gather_pixels_u8.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.vkb_resize_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
+    lib.vkb_resize_mask_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_filter2d_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
     lib.vkb_fill_polygons.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]
     lib.vkb_photo_chain_batched.argtypes = [vp, vp, i32, i32, vp]
@@ -208,7 +209,7 @@ EXPORTS = (
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_streak_masks', 'vkb_photo_chain_batched',
-    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
+    'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_resize_mask_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
 )
 
 

@@ -646,6 +646,17 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const uint8_t* __restrict
 // ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2) and INTER_NEAREST (floor(x / scale)).
 // pixelation (photometric/effect.py:58-79) = linear down + nearest up.  Thread per dst pixel.
 // ============================================================================================
+// Mask.to_resized_mask (element/mask.py:454-479) fused into the resize kernels: with
+// mask_thr >= 0 a source pixel reads as (v > 0) * 255 and the result is stored as (v > mask_thr),
+// which removes the two threshold passes around cv.resize.  mask_thr < 0: plain pixels.
+__device__ __forceinline__ int px_in(uint8_t v, int mask_thr) {
+    return mask_thr >= 0 ? (v ? 255 : 0) : (int)v;
+}
+__device__ __forceinline__ float px_in(float v, int) { return v; }
+__device__ __forceinline__ uint8_t px_out(int v, int mask_thr) {
+    return (uint8_t)(mask_thr >= 0 ? (int)(v > mask_thr) : v);
+}
+
 // Columns outside the source get fraction 0; rows keep their fraction and clip the two row
 // indices (cv2's vertical pass then splits one row over both coefficients, which matters to the
 // last bit when the horizontal pass interpolated).
@@ -682,7 +693,8 @@ __device__ __forceinline__ void resize_lin_exact_coef(int d, double scale, int s
 template <int C>
 __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw,
                                                         uint8_t* __restrict__ dst, int dh, int dw,
-                                                        double scale_x, double scale_y, int nearest) {
+                                                        double scale_x, double scale_y, int nearest,
+                                                        int mask_thr) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         const int sy = min((ify0 + ify * y) >> 16, sh - 1);
         const uint8_t* p = src + ((long long)sy * sw + sx) * C;
 #pragma unroll
-        for (int c = 0; c < C; ++c) d[c] = p[c];
+        for (int c = 0; c < C; ++c) d[c] = px_out(px_in(p[c], mask_thr), mask_thr);
         return;
     }
     if (nearest == 3) {
@@ -706,9 +718,9 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         const uint8_t* r1 = src + (long long)y1 * sw * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const int h0 = (int)r0[x0 * C + c] * (256 - cx) + (int)r0[x1 * C + c] * cx;
-            const int h1 = (int)r1[x0 * C + c] * (256 - cx) + (int)r1[x1 * C + c] * cx;
-            d[c] = (uint8_t)min(max((h0 * (256 - cy) + h1 * cy + 32768) >> 16, 0), 255);
+            const int h0 = px_in(r0[x0 * C + c], mask_thr) * (256 - cx) + px_in(r0[x1 * C + c], mask_thr) * cx;
+            const int h1 = px_in(r1[x0 * C + c], mask_thr) * (256 - cx) + px_in(r1[x1 * C + c], mask_thr) * cx;
+            d[c] = px_out(min(max((h0 * (256 - cy) + h1 * cy + 32768) >> 16, 0), 255), mask_thr);
         }
         return;
     }
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         const int sy = min((int)floor((double)y * scale_y), sh - 1);
         const uint8_t* p = src + ((long long)sy * sw + sx) * C;
 #pragma unroll
-        for (int c = 0; c < C; ++c) d[c] = p[c];
+        for (int c = 0; c < C; ++c) d[c] = px_out(px_in(p[c], mask_thr), mask_thr);
         return;
     }
     int x0, x1, ax0, ax1, y0, y1, by0, by1;
@@ -727,10 +739,10 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
     const uint8_t* r1 = src + (long long)y1 * sw * C;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int s0 = (int)r0[x0 * C + c] * ax0 + (int)r0[x1 * C + c] * ax1;
-        const int s1 = (int)r1[x0 * C + c] * ax0 + (int)r1[x1 * C + c] * ax1;
+        const int s0 = px_in(r0[x0 * C + c], mask_thr) * ax0 + px_in(r0[x1 * C + c], mask_thr) * ax1;
+        const int s1 = px_in(r1[x0 * C + c], mask_thr) * ax0 + px_in(r1[x1 * C + c], mask_thr) * ax1;
         const int v = (((by0 * (s0 >> 4)) >> 16) + ((by1 * (s1 >> 4)) >> 16) + 2) >> 2;
-        d[c] = (uint8_t)min(max(v, 0), 255);
+        d[c] = px_out(min(max(v, 0), 255), mask_thr);
     }
 }
 
@@ -850,7 +862,8 @@ __device__ __forceinline__ void lanczos4_taps(float frac, float* c) {
 template <typename T, int C>
 __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restrict__ src, int sh, int sw,
                                                               T* __restrict__ dst, int dh, int dw,
-                                                              double scale_x, double scale_y, int clip01) {
+                                                              double scale_x, double scale_y, int clip01,
+                                                              int mask_thr) {
     __shared__ float taps[40][8];
     __shared__ int first[40];
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -891,14 +904,14 @@ __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restric
             for (int c = 0; c < C; ++c) {
                 int hsum = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) hsum += (int)row[xs[k] + c] * ax[k];
+                for (int k = 0; k < 8; ++k) hsum += px_in(row[xs[k] + c], mask_thr) * ax[k];
                 acc[c] += (long long)hsum * ay;
             }
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const long long v = (acc[c] + (1 << 21)) >> 22;
-            dst[((long long)y * dw + x) * C + c] = (T)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            dst[((long long)y * dw + x) * C + c] = px_out((int)(v < 0 ? 0 : (v > 255 ? 255 : v)), mask_thr);
         }
     } else {
         float v = 0.f;
@@ -958,7 +971,7 @@ template <typename T, int C, bool FAST>
 __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ src, int sh, int sw,
                                                           T* __restrict__ dst, int dh, int dw,
                                                           double scale_x, double scale_y, int isx,
-                                                          int isy, int clip01) {
+                                                          int isy, int clip01, int mask_thr) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -972,10 +985,10 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ 
             for (int c = 0; c < C; ++c) {
                 int sum = 0;
                 for (int ky = 0; ky < isy; ++ky)
-                    for (int kx = 0; kx < isx; ++kx) sum += base[((long long)ky * sw + kx) * C + c];
+                    for (int kx = 0; kx < isx; ++kx) sum += px_in(base[((long long)ky * sw + kx) * C + c], mask_thr);
                 const int v = (isx == 2 && isy == 2) ? (sum + 2) >> 2
                                                      : __float2int_rn(__fmul_rn((float)sum, scale));
-                d[c] = (T)min(max(v, 0), 255);
+                d[c] = px_out(min(max(v, 0), 255), mask_thr);
             }
         } else {
             const float scale = __fdiv_rn(1.f, (float)area);
@@ -1015,8 +1028,9 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ 
             const float beta = ys.weight(j);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float h = __fmul_rn((float)row[c], xs.weight(0));
-                for (int i = 1; i < xs.n; ++i) h = __fadd_rn(h, __fmul_rn((float)row[i * C + c], xs.weight(i)));
+                float h = __fmul_rn((float)px_in(row[c], mask_thr), xs.weight(0));
+                for (int i = 1; i < xs.n; ++i)
+                    h = __fadd_rn(h, __fmul_rn((float)px_in(row[i * C + c], mask_thr), xs.weight(i)));
                 const float t = __fmul_rn(beta, h);
                 acc[c] = j ? __fadd_rn(acc[c], t) : t;
             }
@@ -1024,7 +1038,7 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ 
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             if constexpr (sizeof(T) == 1) {
-                d[c] = (T)min(max(__float2int_rn(acc[c]), 0), 255);
+                d[c] = px_out(min(max(__float2int_rn(acc[c]), 0), 255), mask_thr);
             } else {
                 float v = acc[c];
                 if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
@@ -1043,13 +1057,13 @@ static bool area_is_fast(double scale_x, double scale_y, int& isx, int& isy) {
 
 template <typename T, int C>
 static void launch_resize_area(const T* src, int sh, int sw, T* dst, int dh, int dw, double scale_x,
-                               double scale_y, int clip01, cudaStream_t st) {
+                               double scale_y, int clip01, int mask_thr, cudaStream_t st) {
     int isx, isy;
     dim3 grid((dw + 31) / 32, (dh + 7) / 8);
     if (area_is_fast(scale_x, scale_y, isx, isy))
-        resize_area_kernel<T, C, true><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01);
+        resize_area_kernel<T, C, true><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr);
     else
-        resize_area_kernel<T, C, false><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01);
+        resize_area_kernel<T, C, false><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr);
 }
 
 // ============================================================================================
@@ -1094,7 +1108,7 @@ __device__ __forceinline__ void resize_cubic_coef(int d, double scale, int& s0, 
 template <int C>
 __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ src, int sh, int sw,
                                                    int x, int y, double scale_x, double scale_y,
-                                                   int* out) {
+                                                   int* out, int mask_thr = -1) {
     int sx, sy, ax[4], ay[4];
     resize_cubic_coef(x, scale_x, sx, ax);
     resize_cubic_coef(y, scale_y, sy, ay);
@@ -1112,7 +1126,7 @@ __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ s
         for (int k = 0; k < 4; ++k) {
             const int xx = min(max(sx - 1 + k, 0), sw - 1);
 #pragma unroll
-            for (int c = 0; c < C; ++c) hsum[c] += (int)row[xx * C + c] * ax[k];
+            for (int c = 0; c < C; ++c) hsum[c] += px_in(row[xx * C + c], mask_thr) * ax[k];
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] += hsum[c] * ay[j];
@@ -1124,14 +1138,14 @@ __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ s
 template <int C>
 __global__ void __launch_bounds__(256) resize_cubic_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw,
                                                               uint8_t* __restrict__ dst, int dh, int dw,
-                                                              double scale_x, double scale_y) {
+                                                              double scale_x, double scale_y, int mask_thr) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
     int px[C];
-    resize_cubic_pixel<C>(src, sh, sw, x, y, scale_x, scale_y, px);
+    resize_cubic_pixel<C>(src, sh, sw, x, y, scale_x, scale_y, px, mask_thr);
 #pragma unroll
-    for (int c = 0; c < C; ++c) dst[((long long)y * dw + x) * C + c] = (uint8_t)px[c];
+    for (int c = 0; c < C; ++c) dst[((long long)y * dw + x) * C + c] = px_out(px[c], mask_thr);
 }
 
 // zoom_in_blur (photometric/blur.py:278-330): the page plus its cubic enlargements (centre
@@ -1713,9 +1727,9 @@ extern "C" int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int3
     return check_launch("filter2d_kernel");
 }
 
-extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst,
-                             int32_t dst_h, int32_t dst_w, int32_t channels, int32_t interpolation,
-                             void* stream) {
+static int resize_u8_impl(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst,
+                          int32_t dst_h, int32_t dst_w, int32_t channels, int32_t interpolation,
+                          int mask_thr, void* stream) {
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
@@ -1731,41 +1745,55 @@ extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, u
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
     const double scale_y = 1.0 / ((double)dst_h / (double)src_h);
     dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8);
+    const dim3 block(32, 8);
     cudaStream_t st = (cudaStream_t)stream;
+#define VKB_BY_CHANNELS(LAUNCH)             \
+    do {                                    \
+        if (channels == 1) { LAUNCH(1); }   \
+        else if (channels == 3) { LAUNCH(3); } \
+        else { LAUNCH(4); }                 \
+    } while (0)
     if (interpolation == VKB_INTER_CUBIC) {
-        if (channels == 1)
-            resize_cubic_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
-        else if (channels == 3)
-            resize_cubic_u8_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
-        else
-            resize_cubic_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y);
+#define VKB_L(CH) resize_cubic_u8_kernel<CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, mask_thr)
+        VKB_BY_CHANNELS(VKB_L);
+#undef VKB_L
         return check_launch("resize_cubic_u8_kernel");
     }
     if (interpolation == VKB_INTER_AREA) {
-        if (channels == 1) launch_resize_area<uint8_t, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
-        else if (channels == 3) launch_resize_area<uint8_t, 3>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
-        else launch_resize_area<uint8_t, 4>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, st);
+#define VKB_L(CH) launch_resize_area<uint8_t, CH>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, mask_thr, st)
+        VKB_BY_CHANNELS(VKB_L);
+#undef VKB_L
         return check_launch("resize_area_kernel");
     }
     if (interpolation == VKB_INTER_LANCZOS4) {
-        if (channels == 1)
-            resize_lanczos4_kernel<uint8_t, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
-        else if (channels == 3)
-            resize_lanczos4_kernel<uint8_t, 3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
-        else
-            resize_lanczos4_kernel<uint8_t, 4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0);
+#define VKB_L(CH) resize_lanczos4_kernel<uint8_t, CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, mask_thr)
+        VKB_BY_CHANNELS(VKB_L);
+#undef VKB_L
         return check_launch("resize_lanczos4_kernel");
     }
     const int nearest = interpolation == VKB_INTER_NEAREST ? 1
                         : interpolation == VKB_INTER_NEAREST_EXACT ? 2
                         : interpolation == VKB_INTER_LINEAR_EXACT ? 3 : 0;
-    if (channels == 1)
-        resize_u8_kernel<1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
-    else if (channels == 3)
-        resize_u8_kernel<3><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
-    else
-        resize_u8_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest);
+#define VKB_L(CH) resize_u8_kernel<CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest, mask_thr)
+    VKB_BY_CHANNELS(VKB_L);
+#undef VKB_L
+#undef VKB_BY_CHANNELS
     return check_launch("resize_u8_kernel");
+}
+
+extern "C" int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst,
+                             int32_t dst_h, int32_t dst_w, int32_t channels, int32_t interpolation,
+                             void* stream) {
+    return resize_u8_impl(src, src_h, src_w, dst, dst_h, dst_w, channels, interpolation, -1, stream);
+}
+
+extern "C" int vkb_resize_mask_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst,
+                                  int32_t dst_h, int32_t dst_w, int32_t interpolation,
+                                  int32_t binarization_threshold, void* stream) {
+    VKB_REQUIRE(binarization_threshold >= 0 && binarization_threshold <= 255,
+                "binarization_threshold must be in 0..255");
+    return resize_u8_impl(src, src_h, src_w, dst, dst_h, dst_w, 1, interpolation,
+                          binarization_threshold, stream);
 }
 
 extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst,
@@ -1796,9 +1824,9 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
     else if (interpolation == VKB_INTER_CUBIC)
         resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     else if (interpolation == VKB_INTER_AREA)
-        launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, st);
+        launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1, st);
     else
-        resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+        resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1);
     return check_launch("resize_f32_kernel");
 }
 
