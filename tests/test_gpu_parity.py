@@ -1076,6 +1076,30 @@ def test_resize_page_elements(vk, ratio):
             assert not got.is_prob
 
 
+@pytest.mark.parametrize('code', [6, 5, 2, 4, 3])
+def test_resize_full_size_page(vk, code):
+    """BASELINE page size: a 1024 x 1024 page (image, mask, height map) resized to 461 x 461 with
+    each interpolation page_resizing samples == the oracle, every pixel."""
+    element, _ = vk
+    from oracle import vkit_port as port
+    from vkit_b200 import compositing
+    port.use_cv2(False)
+    image, mask, score = make_inputs(1024 + code, (1024, 1024))
+    heights = (score * 48).astype(np.float32)
+    ratio = 0.45
+    got_image, (got_mask,), (got_map,) = compositing.resize_page_elements(
+        element.Image(mat=image), [element.Mask(mat=mask)],
+        [element.ScoreMap(mat=heights, is_prob=False)], ratio, code)
+    side = round(ratio * 1024)
+    u8_model = {6: lambda m, d: port.resize_exact_u8(m, d, nearest=True), 5: port.resize_exact_u8,
+                2: port.resize_cubic_u8, 4: port.resize_lanczos4_u8, 3: port.resize_area}[code]
+    assert np.array_equal(got_image.mat, u8_model(image, (side, side)))
+    want_mask = u8_model((mask > 0).astype(np.uint8) * 255, (side, side)) > 0
+    assert np.array_equal(got_mask.mat, want_mask.astype(np.uint8))
+    want_map = port.resize_area(heights, (side, side)) if code == 3 else port.resize_f32(heights, (side, side), code)
+    assert np.array_equal(got_map.mat, want_map * np.float32(ratio))
+
+
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")
 def test_cubic_resize_and_zoom_in_blur(vk, case):
     """INTER_CUBIC on the device == the oracle's restatement of cv2's own fixed-point cubic, bit
