@@ -979,6 +979,20 @@ def test_image_to_resized_image_linear_and_nearest(vk):
         gray = element.Image(mat=np.ascontiguousarray(image[:, :, 1]), mode=element.ImageMode.GRAYSCALE)
         got = gray.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=4).mat
         assert np.array_equal(got, port.resize_lanczos4_u8(image[:, :, 1], (w, h)))
+    # box-attached forms (element/image.py:854-873, mask.py:481-503, score_map.py:594-614)
+    box = element.Box(up=10, down=59, left=20, right=99)
+    crop = np.ascontiguousarray(image[10:60, 20:100])
+    boxed = element.Image(mat=crop, box=box).to_conducted_resized_image(
+        (100, 133), resized_height=150, resized_width=200, cv_resize_interpolation=1)
+    assert boxed.box == box.to_conducted_resized_box((100, 133), 150, 200)
+    assert np.array_equal(boxed.mat, port.resize_u8(crop, (boxed.box.width, boxed.box.height)))
+    mask_crop = (crop[:, :, 0] > 128).astype(np.uint8)
+    boxed_mask = element.Mask(mat=mask_crop, box=box).to_conducted_resized_mask(
+        (100, 133), resized_height=150, resized_width=200, cv_resize_interpolation=1,
+        binarization_threshold=100)
+    assert boxed_mask.box == boxed.box
+    assert np.array_equal(boxed_mask.mat, (port.resize_u8(mask_crop * 255, (boxed.box.width, boxed.box.height)) > 100).astype(np.uint8))
+    assert element.ScoreMap.to_conducted_resized_polygon is element.ScoreMap.to_conducted_resized_score_map
     with pytest.raises(NotImplementedError):
         img.to_resized_image(resized_height=50, cv_resize_interpolation=7)  # cv.INTER_MAX
 

@@ -313,6 +313,19 @@ class Image(DualStorage, Shapable):
             channels, self._CV_INTER[cv_resize_interpolation], dv.stream_ptr()), 'vkb_resize_u8')
         return attrs.evolve(self, mat=dst)
 
+    def to_conducted_resized_image(self, shapable_or_shape, resized_height: Optional[int] = None,
+                                   resized_width: Optional[int] = None,
+                                   cv_resize_interpolation: int = 2):
+        """element/image.py:854-873: resize the attached box and the pixels it holds together."""
+        assert self.box
+        resized_box = self.box.to_conducted_resized_box(
+            shapable_or_shape=shapable_or_shape, resized_height=resized_height,
+            resized_width=resized_width)
+        resized = self.to_box_detached().to_resized_image(
+            resized_height=resized_box.height, resized_width=resized_box.width,
+            cv_resize_interpolation=cv_resize_interpolation)
+        return resized.to_box_attached(resized_box)
+
 
 from .box import Box, generate_fill_by_boxes_mask  # noqa: E402
 from .polygon import Polygon, generate_fill_by_polygons_mask  # noqa: E402

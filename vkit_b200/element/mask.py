@@ -207,6 +207,20 @@ class Mask(DualStorage, Shapable):
             'vkb_resize_mask_u8')
         return Mask(mat=dst)
 
+    def to_conducted_resized_mask(self, shapable_or_shape, resized_height: Optional[int] = None,
+                                  resized_width: Optional[int] = None,
+                                  cv_resize_interpolation: int = 2, binarization_threshold: int = 0):
+        """element/mask.py:481-503: resize the attached box and the mask it holds together."""
+        assert self.box
+        resized_box = self.box.to_conducted_resized_box(
+            shapable_or_shape=shapable_or_shape, resized_height=resized_height,
+            resized_width=resized_width)
+        resized = self.to_box_detached().to_resized_mask(
+            resized_height=resized_box.height, resized_width=resized_box.width,
+            cv_resize_interpolation=cv_resize_interpolation,
+            binarization_threshold=binarization_threshold)
+        return resized.to_box_attached(resized_box)
+
     def to_shifted_mask(self, offset_y: int = 0, offset_x: int = 0):
         assert self.box
         return attrs.evolve(self, box=self.box.to_shifted_box(offset_y=offset_y,

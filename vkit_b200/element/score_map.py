@@ -123,6 +123,9 @@ class ScoreMap(DualStorage, Shapable):
             cv_resize_interpolation=cv_resize_interpolation)
         return resized.to_box_attached(resized_box)
 
+    # the reference spells this method `to_conducted_resized_polygon` (element/score_map.py:595)
+    to_conducted_resized_polygon = to_conducted_resized_score_map
+
     def to_resized_score_map(self, resized_height: Optional[int] = None,
                              resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
         """element/score_map.py:616-637: cv.resize of the float32 map (INTER_CUBIC by default),
