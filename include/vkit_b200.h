@@ -326,7 +326,8 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
                     const float* taps_dev, int32_t kh, int32_t kw, void* stream);
 
 /* cv.resize(uint8): INTER_NEAREST, INTER_LINEAR (11-bit fixed-point coefficients and cv2's 8-bit
- * vertical pass), INTER_AREA when shrinking on both axes (box sums / computeResizeAreaTab weights),
+ * vertical pass), INTER_AREA (box sums / computeResizeAreaTab weights when shrinking on both axes,
+ * the bilinear passes with "area mode" fractions as soon as one axis enlarges),
  * INTER_LANCZOS4, INTER_NEAREST_EXACT, INTER_LINEAR_EXACT -- all bit exact -- and INTER_CUBIC
  * (pixelation, photometric/effect.py:58-79; Image.to_resized_image element/image.py:836-852;
  * Mask.to_resized_mask element/mask.py:454-479; every interpolation page_resizing samples,
@@ -334,7 +335,7 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
 #define VKB_INTER_NEAREST 0
 #define VKB_INTER_LINEAR 1
 #define VKB_INTER_CUBIC 2 /* cv2's own fixed-point path; the wheel's IPP default differs by +-1 on ~5 % of pixels */
-#define VKB_INTER_AREA 3     /* shrinking on both axes only; bit exact (uint8) */
+#define VKB_INTER_AREA 3     /* bit exact (uint8) */
 #define VKB_INTER_LANCZOS4 4 /* bit exact (uint8) */
 #define VKB_INTER_LINEAR_EXACT 5  /* cv2's codes: bit exact */
 #define VKB_INTER_NEAREST_EXACT 6
@@ -342,7 +343,7 @@ int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst
                   int32_t dst_w, int32_t channels, int32_t interpolation, void* stream);
 
 /* cv.resize(float32, one channel): ScoreMap.to_resized_score_map (element/score_map.py:616-637).
- * cv2's float paths (NEAREST, LINEAR, CUBIC, AREA when shrinking, LANCZOS4, the two EXACT codes)
+ * cv2's float paths (NEAREST, LINEAR, CUBIC, AREA, LANCZOS4, the two EXACT codes)
  * restated with every product and sum rounded to float32 in cv2's order; cv2's own result
  * depends on its backend (Intel IPP by default) and agrees to ~5e-6.  clip01 != 0
  * fuses the np.clip(mat, 0, 1) the reference applies to probability maps. */

@@ -1027,10 +1027,10 @@ def test_score_map_to_resized_score_map(vk):
         element.ScoreMap(mat=mat).to_resized_score_map(resized_height=50, cv_resize_interpolation=7)
 
 
-def test_inter_area_shrinking(vk):
+def test_inter_area(vk):
     """cv.INTER_AREA (page_resizing samples it when shrinking): Image, Mask and ScoreMap resizes ==
     the oracle restatement bit for bit -- integer ratios (box sums, the 2x2 special case) and
-    fractional ratios (weight tables); enlarging raises."""
+    fractional ratios (weight tables), and enlarging axes ("area mode" bilinear)."""
     element, _ = vk
     from oracle import vkit_port as port
     port.use_cv2(False)
@@ -1053,10 +1053,15 @@ def test_inter_area_shrinking(vk):
         assert np.array_equal(got, port.resize_area(score, (w, h), clip01=True)), (h, w)
         got = raw.to_resized_score_map(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
         assert np.array_equal(got, port.resize_area(raw.mat, (w, h))), (h, w)
-    for element_obj, call in ((img, 'to_resized_image'), (msk, 'to_resized_mask'),
-                              (scm, 'to_resized_score_map')):
-        with pytest.raises(NotImplementedError):
-            getattr(element_obj, call)(resized_height=121, resized_width=180, cv_resize_interpolation=3)
+    # an enlarging axis: cv2 switches to the bilinear passes with "area mode" fractions
+    for (h, w) in ((121, 180), (240, 360), (164, 247), (240, 90), (40, 540)):
+        got = img.to_resized_image(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(image, (w, h))), (h, w)
+        got = msk.to_resized_mask(resized_height=h, resized_width=w, cv_resize_interpolation=3,
+                                  binarization_threshold=127).mat
+        assert np.array_equal(got, (port.resize_area(full, (w, h)) > 127).astype(np.uint8)), (h, w)
+        got = scm.to_resized_score_map(resized_height=h, resized_width=w, cv_resize_interpolation=3).mat
+        assert np.array_equal(got, port.resize_area(score, (w, h), clip01=True)), (h, w)
 
 
 @pytest.mark.parametrize('ratio', [0.6, 0.5, 1.3])

@@ -177,8 +177,9 @@ def test_resize_f32_model_vs_cv2(shape):
 
 @pytest.mark.parametrize('shape', [(120, 180), (97, 131)])
 def test_resize_area_model_vs_cv2(shape):
-    """INTER_AREA when shrinking (page_resizing's fifth interpolation): the oracle's restatement of
-    cv2's box-sum and weight-table paths.  uint8 bit for bit with and without IPP; float32 bit for
+    """INTER_AREA (page_resizing's fifth interpolation, sampled when shrinking): the oracle's
+    restatement of cv2's box-sum and weight-table paths, and of the "area mode" bilinear passes
+    cv2 runs when an axis enlarges.  uint8 bit for bit with and without IPP; float32 bit for
     bit without IPP, within 1e-5 with it."""
     import cv2 as cv
     from oracle import vkit_port as port
@@ -205,5 +206,15 @@ def test_resize_area_model_vs_cv2(shape):
                     assert np.array_equal(got, ref), dsize
     finally:
         cv.ipp.setUseIPP(use_ipp)
-    with pytest.raises(NotImplementedError):
-        port.resize_area(img, (w + 1, h))
+    # an enlarging axis: cv2 runs the bilinear passes with "area mode" fractions
+    try:
+        for dsize in ((w + 1, h), (w * 2, h * 2), (round(w * 1.37), round(h * 1.37)), (w // 2, h * 2),
+                      (w * 3, h // 3)):
+            for ipp in (False, True):
+                cv.ipp.setUseIPP(ipp)
+                assert np.array_equal(port.resize_area(img, dsize),
+                                      cv.resize(img, dsize, interpolation=cv.INTER_AREA)), dsize
+                assert np.array_equal(port.resize_area(mat, dsize),
+                                      cv.resize(mat, dsize, interpolation=cv.INTER_AREA)), dsize
+    finally:
+        cv.ipp.setUseIPP(use_ipp)

@@ -660,12 +660,28 @@ __device__ __forceinline__ uint8_t px_out(int v, int mask_thr) {
 // Columns outside the source get fraction 0; rows keep their fraction and clip the two row
 // indices (cv2's vertical pass then splits one row over both coefficients, which matters to the
 // last bit when the horizontal pass interpolated).
+// cv::resize "area mode" (INTER_AREA with an enlarging axis): the bilinear passes with
+// sx = floor(dx * scale), fx = (dx + 1) - (sx + 1) * inv_scale, 0 if <= 0, else its fractional part.
+__device__ __forceinline__ void resize_area_mode_frac(int d, double scale, int dn, int sn, int& si,
+                                                      float& f) {
+    const double inv_scale = (double)dn / (double)sn;
+    si = (int)floor(__dmul_rn((double)d, scale));
+    f = (float)__dsub_rn((double)(d + 1), __dmul_rn((double)(si + 1), inv_scale));
+    f = f <= 0.f ? 0.f : __fsub_rn(f, floorf(f));
+}
+
 template <bool ROWS>
 __device__ __forceinline__ void resize_lin_coef(int d, double scale, int sn, int& s0, int& s1,
-                                                int& a0, int& a1) {
-    float f = (float)(((double)d + 0.5) * scale - 0.5);
-    int si = (int)floorf(f);
-    f -= (float)si;
+                                                int& a0, int& a1, int area_dn = 0) {
+    float f;
+    int si;
+    if (area_dn > 0) {
+        resize_area_mode_frac(d, scale, area_dn, sn, si, f);
+    } else {
+        f = (float)(((double)d + 0.5) * scale - 0.5);
+        si = (int)floorf(f);
+        f -= (float)si;
+    }
     if (!ROWS) {
         if (si < 0) { si = 0; f = 0.f; }
         if (si >= sn - 1) { si = sn - 1; f = 0.f; }
@@ -724,7 +740,7 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         }
         return;
     }
-    if (nearest) {
+    if (nearest == 1) {
         const int sx = min((int)floor((double)x * scale_x), sw - 1);
         const int sy = min((int)floor((double)y * scale_y), sh - 1);
         const uint8_t* p = src + ((long long)sy * sw + sx) * C;
@@ -733,8 +749,9 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
         return;
     }
     int x0, x1, ax0, ax1, y0, y1, by0, by1;
-    resize_lin_coef<false>(x, scale_x, sw, x0, x1, ax0, ax1);
-    resize_lin_coef<true>(y, scale_y, sh, y0, y1, by0, by1);
+    const bool area_mode = nearest == 4;  // INTER_AREA with an enlarging axis
+    resize_lin_coef<false>(x, scale_x, sw, x0, x1, ax0, ax1, area_mode ? dw : 0);
+    resize_lin_coef<true>(y, scale_y, sh, y0, y1, by0, by1, area_mode ? dh : 0);
     const uint8_t* r0 = src + (long long)y0 * sw * C;
     const uint8_t* r1 = src + (long long)y1 * sw * C;
 #pragma unroll
@@ -794,14 +811,20 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
             x0 -= 1;
             y0 -= 1;
         } else {
-            float fx = (float)(((double)x + 0.5) * scale_x - 0.5);
-            x0 = (int)floorf(fx);
-            fx = __fsub_rn(fx, (float)x0);
+            float fx, fy;
+            if (clip01 & 4) {  // INTER_AREA with an enlarging axis
+                resize_area_mode_frac(x, scale_x, dw, sw, x0, fx);
+                resize_area_mode_frac(y, scale_y, dh, sh, y0, fy);
+            } else {
+                fx = (float)(((double)x + 0.5) * scale_x - 0.5);
+                x0 = (int)floorf(fx);
+                fx = __fsub_rn(fx, (float)x0);
+                fy = (float)(((double)y + 0.5) * scale_y - 0.5);
+                y0 = (int)floorf(fy);
+                fy = __fsub_rn(fy, (float)y0);
+            }
             if (x0 < 0) { x0 = 0; fx = 0.f; }  // columns: fraction 0 at the border; rows clip
             if (x0 >= sw - 1) { x0 = sw - 1; fx = 0.f; }
-            float fy = (float)(((double)y + 0.5) * scale_y - 0.5);
-            y0 = (int)floorf(fy);
-            fy = __fsub_rn(fy, (float)y0);
             cx[0] = __fsub_rn(1.f, fx); cx[1] = fx;
             cy[0] = __fsub_rn(1.f, fy); cy[1] = fy;
         }
@@ -1737,8 +1760,6 @@ static int resize_u8_impl(const uint8_t* src, int32_t src_h, int32_t src_w, uint
                     || interpolation == VKB_INTER_LANCZOS4 || interpolation == VKB_INTER_LINEAR_EXACT
                     || interpolation == VKB_INTER_NEAREST_EXACT,
                 "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
-    VKB_REQUIRE(interpolation != VKB_INTER_AREA || (dst_h <= src_h && dst_w <= src_w),
-                "VKB_INTER_AREA is provided for shrinking on both axes");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale (both double)
@@ -1759,7 +1780,7 @@ static int resize_u8_impl(const uint8_t* src, int32_t src_h, int32_t src_w, uint
 #undef VKB_L
         return check_launch("resize_cubic_u8_kernel");
     }
-    if (interpolation == VKB_INTER_AREA) {
+    if (interpolation == VKB_INTER_AREA && dst_h <= src_h && dst_w <= src_w) {
 #define VKB_L(CH) launch_resize_area<uint8_t, CH>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, mask_thr, st)
         VKB_BY_CHANNELS(VKB_L);
 #undef VKB_L
@@ -1773,7 +1794,8 @@ static int resize_u8_impl(const uint8_t* src, int32_t src_h, int32_t src_w, uint
     }
     const int nearest = interpolation == VKB_INTER_NEAREST ? 1
                         : interpolation == VKB_INTER_NEAREST_EXACT ? 2
-                        : interpolation == VKB_INTER_LINEAR_EXACT ? 3 : 0;
+                        : interpolation == VKB_INTER_LINEAR_EXACT ? 3
+                        : interpolation == VKB_INTER_AREA ? 4 : 0;  // 4: an enlarging axis
 #define VKB_L(CH) resize_u8_kernel<CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, nearest, mask_thr)
     VKB_BY_CHANNELS(VKB_L);
 #undef VKB_L
@@ -1805,8 +1827,6 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
                     || interpolation == VKB_INTER_LANCZOS4 || interpolation == VKB_INTER_LINEAR_EXACT
                     || interpolation == VKB_INTER_NEAREST_EXACT,
                 "interpolation must be VKB_INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT / NEAREST_EXACT");
-    VKB_REQUIRE(interpolation != VKB_INTER_AREA || (dst_h <= src_h && dst_w <= src_w),
-                "VKB_INTER_AREA is provided for shrinking on both axes");
     VKB_REQUIRE(src_h < 32768 && src_w < 32768 && dst_h < 32768 && dst_w < 32768,
                 "planes of at most 32767 pixels per side");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w);
@@ -1823,6 +1843,9 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
         resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
     else if (interpolation == VKB_INTER_CUBIC)
         resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+    else if (interpolation == VKB_INTER_AREA && !(dst_h <= src_h && dst_w <= src_w))
+        // an enlarging axis: the bilinear passes with "area mode" fractions
+        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip | 4);
     else if (interpolation == VKB_INTER_AREA)
         launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1, st);
     else

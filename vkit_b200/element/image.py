@@ -286,7 +286,7 @@ class Image(DualStorage, Shapable):
     def to_resized_image(self, resized_height: Optional[int] = None,
                          resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
         """element/image.py:836-852.  The device resize reproduces cv.resize bit for bit for
-        INTER_NEAREST (0), INTER_LINEAR (1), INTER_AREA (3, shrinking only), INTER_LANCZOS4 (4), INTER_LINEAR_EXACT (5) and
+        INTER_NEAREST (0), INTER_LINEAR (1), INTER_AREA (3), INTER_LANCZOS4 (4), INTER_LINEAR_EXACT (5) and
         INTER_NEAREST_EXACT (6).
         INTER_CUBIC (2, the reference's default) follows
         cv2's own fixed-point path; the cv2 wheel routes cubic through Intel IPP, whose result
@@ -298,10 +298,6 @@ class Image(DualStorage, Shapable):
             raise NotImplementedError(
                 'to_resized_image: cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT '
                 '/ NEAREST_EXACT have device kernels')
-        if cv_resize_interpolation == 3 and (resized_height > self.height
-                                             or resized_width > self.width):
-            raise NotImplementedError('to_resized_image: cv.INTER_AREA is provided for shrinking '
-                                      '(page_resizing samples it only then)')
         if self.mat_dtype != np.uint8:
             raise NotImplementedError('to_resized_image is provided for uint8 images')
         src = self.dev

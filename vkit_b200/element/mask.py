@@ -185,7 +185,7 @@ class Mask(DualStorage, Shapable):
                         resized_width: Optional[int] = None, cv_resize_interpolation: int = 2,
                         binarization_threshold: int = 0):
         """element/mask.py:454-479: (mask > 0) * 255 -> cv.resize -> > threshold.  NEAREST (0),
-        LINEAR (1), AREA (3, shrinking only), LANCZOS4 (4), LINEAR_EXACT (5), NEAREST_EXACT (6) are bit exact, CUBIC (2, the default) is cv2's own fixed-point cubic (the
+        LINEAR (1), AREA (3), LANCZOS4 (4), LINEAR_EXACT (5), NEAREST_EXACT (6) are bit exact, CUBIC (2, the default) is cv2's own fixed-point cubic (the
         wheel's IPP cubic differs by +-1 before the threshold)."""
         from .opt import generate_resized_shape
         assert not self.box
@@ -195,9 +195,6 @@ class Mask(DualStorage, Shapable):
             raise NotImplementedError(
                 'to_resized_mask: cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT / '
                 'NEAREST_EXACT have device kernels')
-        if cv_resize_interpolation == 3 and (resized_height > self.height
-                                             or resized_width > self.width):
-            raise NotImplementedError('to_resized_mask: cv.INTER_AREA is provided for shrinking')
         src = self.dev
         dst = dv.empty((resized_height, resized_width), np.uint8)
         # both binarisations are fused into the resize kernel (one launch instead of three)

@@ -107,7 +107,7 @@ class ScoreMap(DualStorage, Shapable):
         return attrs.evolve(self, box=self.box.to_shifted_box(offset_y=offset_y, offset_x=offset_x),
                             skip_prob_check=True)
 
-    # cv.INTER_NEAREST / LINEAR / CUBIC / AREA (shrinking) / LANCZOS4 / LINEAR_EXACT (= LINEAR for float) / NEAREST_EXACT
+    # cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / LINEAR_EXACT (= LINEAR for float) / NEAREST_EXACT
     _CV_INTER = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6}
 
     def to_conducted_resized_score_map(self, shapable_or_shape, resized_height: Optional[int] = None,
@@ -141,10 +141,6 @@ class ScoreMap(DualStorage, Shapable):
             raise NotImplementedError(
                 'to_resized_score_map: cv.INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4 / '
                 'LINEAR_EXACT / NEAREST_EXACT have device kernels')
-        if cv_resize_interpolation == 3 and (resized_height > self.height
-                                             or resized_width > self.width):
-            raise NotImplementedError('to_resized_score_map: cv.INTER_AREA is provided for '
-                                      'shrinking (page_resizing samples it only then)')
         src = self.dev
         dst = dv.empty((resized_height, resized_width), np.float32)
         _native.check(_native.lib().vkb_resize_f32(
