@@ -1105,9 +1105,9 @@ __global__ void __launch_bounds__(256) gather_pixels_kernel(const uint8_t* __res
 }
 
 // ============================================================================================
-// cv.resize(uint8, INTER_CUBIC) -- cv2's own (non-IPP) fixed-point path: float32 coefficients
-// (A = -0.75) rounded to 11 bits, integer horizontal pass, vertical pass (sum + 2^21) >> 22,
-// replicated borders.  The cv2 wheel routes cubic through Intel IPP by default, which differs
+// cv.resize(uint8, INTER_CUBIC) -- cv2's own (non-IPP) path: float32 coefficients (A = -0.75)
+// rounded to 11 bits, integer horizontal pass, float32 vertical pass (cv2's vector code: taps
+// times 2^-22, summed last to first, rounded half to even), replicated borders.  The cv2 wheel routes cubic through Intel IPP by default, which differs
 // from this by +-1 on ~5 % of the pixels of a random image (measured; cv.ipp.setUseIPP(False)
 // gives this path).  Used by Image.to_resized_image and zoom_in_blur
 // (photometric/blur.py:278-330).
@@ -1135,11 +1135,11 @@ __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ s
     int sx, sy, ax[4], ay[4];
     resize_cubic_coef(x, scale_x, sx, ax);
     resize_cubic_coef(y, scale_y, sy, ay);
-    int acc[C];
+    // cv2's vertical pass (VResizeCubicVec_32s8u) is float32: taps scaled by 2^-22 (exact), the
+    // four products added from the last row to the first without FMA, rounded half to even
+    float acc[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 1 << 21;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 3; j >= 0; --j) {
         const int yy = min(max(sy - 1 + j, 0), sh - 1);
         const uint8_t* row = src + (long long)yy * sw * C;
         int hsum[C];
@@ -1151,11 +1151,15 @@ __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ s
 #pragma unroll
             for (int c = 0; c < C; ++c) hsum[c] += px_in(row[xx * C + c], mask_thr) * ax[k];
         }
+        const float beta = __fmul_rn((float)ay[j], 2.384185791015625e-07f);  // 2^-22
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] += hsum[c] * ay[j];
+        for (int c = 0; c < C; ++c) {
+            const float term = __fmul_rn((float)hsum[c], beta);
+            acc[c] = j == 3 ? term : __fadd_rn(term, acc[c]);
+        }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[c] = min(max(acc[c] >> 22, 0), 255);
+    for (int c = 0; c < C; ++c) out[c] = min(max(__float2int_rn(acc[c]), 0), 255);
 }
 
 template <int C>
