@@ -344,8 +344,8 @@ int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst
 
 /* cv.resize(float32, one channel): ScoreMap.to_resized_score_map (element/score_map.py:616-637).
  * cv2's float paths (NEAREST, LINEAR, CUBIC, AREA, LANCZOS4, the two EXACT codes)
- * restated with every product and sum rounded to float32 in cv2's order; cv2's own result
- * depends on its backend (Intel IPP by default) and agrees to ~5e-6.  clip01 != 0
+ * restated with every product and sum rounded to float32 in cv2's order: bit identical to cv2
+ * with IPP switched off; the wheel's default IPP backend agrees to ~5e-6.  clip01 != 0
  * fuses the np.clip(mat, 0, 1) the reference applies to probability maps. */
 int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
                    int32_t dst_w, int32_t interpolation, int32_t clip01, void* stream);

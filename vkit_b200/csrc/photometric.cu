@@ -831,15 +831,25 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
         int xs[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) xs[i] = min(max(x0 + i, 0), sw - 1);
-        v = 0.f;
+        float t[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const float* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw;
             float hsum = __fmul_rn(row[xs[0]], cx[0]);
 #pragma unroll
             for (int i = 1; i < K; ++i) hsum = __fadd_rn(hsum, __fmul_rn(row[xs[i]], cx[i]));
-            const float t = __fmul_rn(hsum, cy[j]);
-            v = j ? __fadd_rn(v, t) : t;
+            t[j] = __fmul_rn(hsum, cy[j]);
+        }
+        // cv2's vector code (4 columns at a time) adds the rows from the last to the first, its
+        // scalar tail (the last dw % 4 columns) from the first to the last
+        if (x < (dw & ~3)) {
+            v = t[K - 1];
+#pragma unroll
+            for (int j = K - 2; j >= 0; --j) v = __fadd_rn(t[j], v);
+        } else {
+            v = t[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) v = __fadd_rn(v, t[j]);
         }
     }
     if (clip01 & 1) v = fminf(fmaxf(v, 0.f), 1.f);
@@ -937,15 +947,25 @@ __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restric
             dst[((long long)y * dw + x) * C + c] = px_out((int)(v < 0 ? 0 : (v > 255 ? 255 : v)), mask_thr);
         }
     } else {
-        float v = 0.f;
-#pragma unroll 1
+        float t[8];
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
             const T* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw;
             float hsum = __fmul_rn(row[xs[0]], cx[0]);
 #pragma unroll
             for (int k = 1; k < 8; ++k) hsum = __fadd_rn(hsum, __fmul_rn(row[xs[k]], cx[k]));
-            const float t = __fmul_rn(hsum, cy[j]);
-            v = j ? __fadd_rn(v, t) : t;
+            t[j] = __fmul_rn(hsum, cy[j]);
+        }
+        // rows added last to first in cv2's vector code, first to last in its scalar tail
+        float v;
+        if (x < (dw & ~3)) {
+            v = t[7];
+#pragma unroll
+            for (int j = 6; j >= 0; --j) v = __fadd_rn(t[j], v);
+        } else {
+            v = t[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) v = __fadd_rn(v, t[j]);
         }
         if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
         dst[(long long)y * dw + x] = v;
