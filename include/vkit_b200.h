@@ -334,7 +334,7 @@ int vkb_filter2d_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int3
  * utility/opt.py:125-148, pipeline/text_detection/page_resizing.py:118-121). */
 #define VKB_INTER_NEAREST 0
 #define VKB_INTER_LINEAR 1
-#define VKB_INTER_CUBIC 2 /* bit exact vs cv2's own path (IPP off); the wheel's IPP default differs by +-1 on ~5 % of pixels */
+#define VKB_INTER_CUBIC 2 /* the wheel's IPP cubic (float64 bicubic; +-1 on < 3e-4 of the pixels); sources below 4x4: cv2's own path, bit exact */
 #define VKB_INTER_AREA 3     /* bit exact (uint8) */
 #define VKB_INTER_LANCZOS4 4 /* bit exact (uint8) */
 #define VKB_INTER_LINEAR_EXACT 5  /* cv2's codes: bit exact */

@@ -117,7 +117,8 @@ def test_camera_functions(rng):
 def test_resize_models_vs_cv2(shape):
     """The oracle's cv.resize restatements against the cv2 wheel: NEAREST, LINEAR, NEAREST_EXACT
     and LINEAR_EXACT bit for bit; CUBIC bit for bit against cv2 with IPP switched off (its own path:
-    integer horizontal pass, float32 vertical pass)."""
+    integer horizontal pass, float32 vertical pass) and, for the wheel's default, the float64
+    bicubic against IPP (+-1 on < 3e-4 of the pixels)."""
     import cv2 as cv
     from oracle import vkit_port as port
     port.use_cv2(False)
@@ -140,14 +141,24 @@ def test_resize_models_vs_cv2(shape):
             ref = cv.resize(img, dsize, interpolation=cv.INTER_CUBIC)
         finally:
             cv.ipp.setUseIPP(use_ipp)
-        assert np.array_equal(port.resize_cubic_u8(img, dsize), ref)
+        assert np.array_equal(port.resize_cubic_u8(img, dsize, ipp=False), ref)
         gray = np.ascontiguousarray(img[:, :, 0])
         cv.ipp.setUseIPP(False)
         try:
             ref = cv.resize(gray, dsize, interpolation=cv.INTER_CUBIC)
         finally:
             cv.ipp.setUseIPP(use_ipp)
-        assert np.array_equal(port.resize_cubic_u8(gray, dsize), ref)
+        assert np.array_equal(port.resize_cubic_u8(gray, dsize, ipp=False), ref)
+        if use_ipp:
+            # the wheel's default (Intel IPP for sources of at least 4 x 4): the float64 bicubic
+            for src in (img, gray):
+                diff = np.abs(port.resize_cubic_u8(src, dsize).astype(int)
+                              - cv.resize(src, dsize, interpolation=cv.INTER_CUBIC).astype(int))
+                assert diff.max() <= 1 and (diff > 0).mean() <= 3e-4, (dsize, (diff > 0).mean())
+    tiny = img[:3, :9]  # below 4 x 4 the wheel takes cv2's own path even with IPP
+    for dsize in ((14, 4), (30, 10), (7, 2)):
+        assert np.array_equal(port.resize_cubic_u8(tiny, dsize),
+                              cv.resize(tiny, dsize, interpolation=cv.INTER_CUBIC))
 
 
 @pytest.mark.parametrize('shape', [(67, 91), (40, 33)])

@@ -327,7 +327,7 @@ def test_effect_oracle(case):
 
 
 # ---------------------------------------------------------------------------------------------
-# INTER_CUBIC resize / zoom_in_blur: the reference's cv2 runs cubic in Intel IPP -> tolerance
+# INTER_CUBIC resize / zoom_in_blur: the reference's cv2 runs cubic in Intel IPP -> near-tie tolerance
 # ---------------------------------------------------------------------------------------------
 def _cubic_oracle(case):
     image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
@@ -339,15 +339,14 @@ def _cubic_oracle(case):
 
 @pytest.mark.parametrize('case', chain_cases('cubic'), ids=lambda c: f"{c['id']}-{c['op']}")
 def test_cubic_oracle(case):
-    """NumPy model = cv2's own fixed-point cubic; the reference fixture was produced with the
-    wheel's IPP cubic: +-1 grey level on <= 8 % of the pixels of a random image (<= 4 % after
-    zoom_in_blur's averaging); with the cv2 backend the oracle is exact."""
+    """NumPy model = the float64 bicubic that the wheel's IPP cubic evaluates; the reference
+    fixture was produced with the wheel: +-1 grey level on <= 5e-4 of the pixels (near ties, where
+    IPP's own arithmetic rounds the other way); with the cv2 backend the oracle is exact."""
     port.use_cv2(False)
     got = _cubic_oracle(case)
     ref = chain_array(case, 'image')
     diff = np.abs(got.astype(int) - ref.astype(int))
-    limit = 0.08 if case["op"] == "to_resized_image" else 0.04
-    assert diff.max() <= 1 and (diff > 0).mean() <= limit, (case['id'], diff.max(), (diff > 0).mean())
+    assert diff.max() <= 1 and (diff > 0).mean() <= 5e-4, (case['id'], diff.max(), (diff > 0).mean())
     if _cv2_available():
         port.use_cv2(True)
         try:

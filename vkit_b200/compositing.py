@@ -185,7 +185,7 @@ def fill_page_inactive_region(page_image: Image, page_active_mask: Mask,
     """PageDistortionStep.fill_page_inactive_region (page_distortion.py:146-161), in place."""
     assert page_image.shape == page_active_mask.shape
     if page_bottom_layer_image.shape != page_image.shape:
-        # cv.resize INTER_CUBIC like the reference (cv2's own non-IPP cubic bit for bit, see DESIGN.md)
+        # cv.resize INTER_CUBIC like the reference (the wheel's IPP cubic, see DESIGN.md section 5)
         page_bottom_layer_image = page_bottom_layer_image.to_resized_image(
             resized_height=page_image.height, resized_width=page_image.width)
     page_active_mask.to_inverted_mask().fill_image(page_image, page_bottom_layer_image)

@@ -1125,7 +1125,8 @@ __global__ void __launch_bounds__(256) gather_pixels_kernel(const uint8_t* __res
 }
 
 // ============================================================================================
-// cv.resize(uint8, INTER_CUBIC) -- cv2's own (non-IPP) path: float32 coefficients (A = -0.75)
+// cv.resize(uint8, INTER_CUBIC), sources below 4 x 4 pixels (above that the wheel runs IPP, see
+// resize_cubic_pixel_ideal) -- cv2's own path: float32 coefficients (A = -0.75)
 // rounded to 11 bits, integer horizontal pass, float32 vertical pass (cv2's vector code: taps
 // times 2^-22, summed last to first, rounded half to even), replicated borders.  The cv2 wheel routes cubic through Intel IPP by default, which differs
 // from this by +-1 on ~5 % of the pixels of a random image (measured; cv.ipp.setUseIPP(False)
@@ -1148,10 +1149,59 @@ __device__ __forceinline__ void resize_cubic_coef(int d, double scale, int& s0, 
     for (int k = 0; k < 4; ++k) a[k] = min(max(__float2int_rn(__fmul_rn(c[k], 2048.f)), -32768), 32767);
 }
 
+// Intel IPP's cubic (what the cv2 wheel runs by default for sources of at least 4 x 4 pixels): the
+// bicubic (A = -0.75) without coefficient quantisation.  Restated in float64 -- taps, horizontal
+// then vertical sums in tap order, no contraction -- and rounded half to even; the wheel differs
+// from this on < 1e-4 of the pixels (+-1 at near ties).
+__device__ __forceinline__ void resize_cubic_coef_f64(int d, double scale, int& s0, double* c) {
+    double f = __dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+    const double fl = floor(f);
+    s0 = (int)fl - 1;
+    f = __dsub_rn(f, fl);
+    const double f1 = __dadd_rn(f, 1.0), g = __dsub_rn(1.0, f);
+    c[0] = __dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(__dmul_rn(-0.75, f1), -3.75), f1), -6.0), f1), -3.0);
+    c[1] = __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.25, f), 2.25), f), f), 1.0);
+    c[2] = __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.25, g), 2.25), g), g), 1.0);
+    c[3] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, c[0]), c[1]), c[2]);
+}
+
+template <int C>
+__device__ __forceinline__ void resize_cubic_pixel_ideal(const uint8_t* __restrict__ src, int sh,
+                                                         int sw, int x, int y, double scale_x,
+                                                         double scale_y, int* out, int mask_thr) {
+    int sx, sy;
+    double ax[4], ay[4];
+    resize_cubic_coef_f64(x, scale_x, sx, ax);
+    resize_cubic_coef_f64(y, scale_y, sy, ay);
+    int xs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = min(max(sx + k, 0), sw - 1) * C;
+    double acc[C];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint8_t* row = src + (long long)min(max(sy + j, 0), sh - 1) * sw * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            double hsum = __dmul_rn((double)px_in(row[xs[0] + c], mask_thr), ax[0]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                hsum = __dadd_rn(hsum, __dmul_rn((double)px_in(row[xs[k] + c], mask_thr), ax[k]));
+            const double term = __dmul_rn(hsum, ay[j]);
+            acc[c] = j ? __dadd_rn(acc[c], term) : term;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = min(max(__double2int_rn(acc[c]), 0), 255);
+}
+
 template <int C>
 __device__ __forceinline__ void resize_cubic_pixel(const uint8_t* __restrict__ src, int sh, int sw,
                                                    int x, int y, double scale_x, double scale_y,
                                                    int* out, int mask_thr = -1) {
+    if (sh >= 4 && sw >= 4) {  // the wheel's IPP path; smaller sources take cv2's own (below)
+        resize_cubic_pixel_ideal<C>(src, sh, sw, x, y, scale_x, scale_y, out, mask_thr);
+        return;
+    }
     int sx, sy, ax[4], ay[4];
     resize_cubic_coef(x, scale_x, sx, ax);
     resize_cubic_coef(y, scale_y, sy, ay);

@@ -288,9 +288,9 @@ class Image(DualStorage, Shapable):
         """element/image.py:836-852.  The device resize reproduces cv.resize bit for bit for
         INTER_NEAREST (0), INTER_LINEAR (1), INTER_AREA (3), INTER_LANCZOS4 (4), INTER_LINEAR_EXACT (5) and
         INTER_NEAREST_EXACT (6).
-        INTER_CUBIC (2, the reference's default) follows
-        cv2's own fixed-point path; the cv2 wheel routes cubic through Intel IPP, whose result
-        differs from it by +-1 on about 5 % of the pixels."""
+        INTER_CUBIC (2, the reference's default) follows the cv2 wheel: Intel IPP's cubic for
+        sources of at least 4 x 4 pixels (the float64 bicubic; +-1 on < 3e-4 of the pixels at near
+        ties), cv2's own path below that, bit for bit."""
         from .opt import generate_shape_and_resized_shape
         _, _, resized_height, resized_width = generate_shape_and_resized_shape(
             self, resized_height, resized_width)

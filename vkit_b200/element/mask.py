@@ -185,8 +185,8 @@ class Mask(DualStorage, Shapable):
                         resized_width: Optional[int] = None, cv_resize_interpolation: int = 2,
                         binarization_threshold: int = 0):
         """element/mask.py:454-479: (mask > 0) * 255 -> cv.resize -> > threshold.  NEAREST (0),
-        LINEAR (1), AREA (3), LANCZOS4 (4), LINEAR_EXACT (5), NEAREST_EXACT (6) are bit exact, CUBIC (2, the default) is cv2's own (non-IPP) cubic bit for bit (the
-        wheel's IPP cubic differs by +-1 before the threshold)."""
+        LINEAR (1), AREA (3), LANCZOS4 (4), LINEAR_EXACT (5), NEAREST_EXACT (6) are bit exact, CUBIC (2, the default)
+        follows the wheel's IPP cubic (see Image.to_resized_image)."""
         from .opt import generate_resized_shape
         assert not self.box
         resized_height, resized_width = generate_resized_shape(self.height, self.width,
