@@ -344,8 +344,10 @@ int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst
 
 /* cv.resize(float32, one channel): ScoreMap.to_resized_score_map (element/score_map.py:616-637).
  * cv2's float paths (NEAREST, LINEAR, CUBIC, AREA, LANCZOS4, the two EXACT codes)
- * restated with every product and sum rounded to float32 in cv2's order: bit identical to cv2
- * with IPP switched off; the wheel's default IPP backend agrees to ~5e-6.  clip01 != 0
+ * LINEAR / LINEAR_EXACT (sources of at least 2 x 2) and CUBIC (4 x 4) follow the wheel's default
+ * backend, Intel IPP (coordinates and taps in double; restated in float64, within 5e-7 of the
+ * wheel); the other codes and smaller sources restate cv2's own path in float32, products and sums
+ * in cv2's order: bit identical to cv2.  clip01 != 0
  * fuses the np.clip(mat, 0, 1) the reference applies to probability maps. */
 int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
                    int32_t dst_w, int32_t interpolation, int32_t clip01, void* stream);

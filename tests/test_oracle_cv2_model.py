@@ -176,14 +176,17 @@ def test_resize_f32_model_vs_cv2(shape):
     try:
         for dsize in ((40, 30), (200, 150), (91, 120), (133, 67), (300, 300), (93, 50), (94, 77)):
             for inter in (0, 1, 2, 4, 5, 6):
-                got = port.resize_f32(mat, dsize, inter)
+                got = port.resize_f32(mat, dsize, inter, ipp=False)
                 cv.ipp.setUseIPP(False)
                 own = cv.resize(mat, dsize, interpolation=inter)
                 cv.ipp.setUseIPP(True)
                 ipp = cv.resize(mat, dsize, interpolation=inter)
                 assert np.array_equal(got, own), (dsize, inter)
                 assert np.abs(got - ipp).max() <= 1e-5
-                clipped = port.resize_f32(mat, dsize, inter, clip01=True)
+                if use_ipp:
+                    # the default model follows the wheel's backend (IPP: double coordinates)
+                    assert np.abs(port.resize_f32(mat, dsize, inter) - ipp).max() <= 5e-7, (dsize, inter)
+                clipped = port.resize_f32(mat, dsize, inter, clip01=True, ipp=False)
                 assert np.array_equal(clipped, np.clip(got, 0.0, 1.0))
     finally:
         cv.ipp.setUseIPP(use_ipp)

@@ -770,6 +770,8 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
 // replicated borders; `clip01` fuses the np.clip(mat, 0, 1) of probability maps.
 // mode 0 NEAREST, 1 LINEAR, 2 CUBIC.
 // ============================================================================================
+__device__ __forceinline__ void resize_cubic_coef_f64(int d, double scale, int& s0, double* c);
+
 __device__ __forceinline__ void resize_cubic_coef_f32(int d, double scale, int& si, float* c) {
     float f = (float)(((double)d + 0.5) * scale - 0.5);
     si = (int)floorf(f);
@@ -790,7 +792,43 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
     float v;
-    if (K == 1) {
+    // Intel IPP (the cv2 wheel's default) serves LINEAR for sources of at least 2 x 2 pixels and
+    // CUBIC for 4 x 4: coordinates and taps in double.  Restated in float64, taps in order,
+    // rounded to float32 once.  (clip01 & 8 keeps cv2's own float32 path.)
+    const bool ipp_form = !(clip01 & (4 | 8)) && ((K == 2 && sh >= 2 && sw >= 2) || (K == 4 && sh >= 4 && sw >= 4));
+    if (K > 1 && ipp_form) {
+        int x0, y0;
+        double cx[4], cy[4];
+        if (K == 4) {
+            resize_cubic_coef_f64(x, scale_x, x0, cx);
+            resize_cubic_coef_f64(y, scale_y, y0, cy);
+        } else {
+            double fx = __dsub_rn(__dmul_rn((double)x + 0.5, scale_x), 0.5);
+            double fl = floor(fx);
+            x0 = (int)fl;
+            fx = __dsub_rn(fx, fl);
+            cx[0] = __dsub_rn(1.0, fx); cx[1] = fx;
+            double fy = __dsub_rn(__dmul_rn((double)y + 0.5, scale_y), 0.5);
+            fl = floor(fy);
+            y0 = (int)fl;
+            fy = __dsub_rn(fy, fl);
+            cy[0] = __dsub_rn(1.0, fy); cy[1] = fy;
+        }
+        int xs[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) xs[i] = min(max(x0 + i, 0), sw - 1);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float* row = src + (long long)min(max(y0 + j, 0), sh - 1) * sw;
+            double hsum = __dmul_rn((double)row[xs[0]], cx[0]);
+#pragma unroll
+            for (int i = 1; i < K; ++i) hsum = __dadd_rn(hsum, __dmul_rn((double)row[xs[i]], cx[i]));
+            const double term = __dmul_rn(hsum, cy[j]);
+            acc = j ? __dadd_rn(acc, term) : term;
+        }
+        v = (float)acc;
+    } else if (K == 1) {
         int sx, sy;
         if (clip01 & 2) {  // cv.INTER_NEAREST_EXACT: 16.16 fixed point on pixel centres
             const int ifx = ((sw << 16) + dw / 2) / dw, ifx0 = ifx / 2 - (sw % 2);

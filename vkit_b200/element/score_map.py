@@ -130,9 +130,9 @@ class ScoreMap(DualStorage, Shapable):
                              resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
         """element/score_map.py:616-637: cv.resize of the float32 map (INTER_CUBIC by default),
         clipped to [0, 1] when it is a probability map -- the clip is fused into the kernel.
-        The device restates cv2's float path in float32, products and sums in cv2's order
-        (vkb_resize_f32): bit identical to cv2 with IPP switched off; the wheel's default IPP
-        backend agrees to about 5e-6."""
+        LINEAR / LINEAR_EXACT / CUBIC follow the wheel's default backend (Intel IPP: coordinates and
+        taps in double, within 5e-7 of the wheel); the other codes restate cv2's own float32 path
+        bit for bit (vkb_resize_f32)."""
         from .. import _native
         from .opt import generate_shape_and_resized_shape
         assert not self.box
