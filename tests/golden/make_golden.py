@@ -111,8 +111,9 @@ def geometric_case(name, config, shape, seed, keep_arrays, with_labels=True):
     # pixel arrays are pinned by sha256 only; lattices / points / polygons are stored (small)
     add_case(case, cid_arrays, False)
     if name.startswith('skew'):
-        # skew ops are compared with a tie tolerance, so the image is stored
-        ARRAYS[f"{case['id']}/image"] = arrays['image']
+        # skew ops are compared with a tie tolerance, so the pixels are stored
+        for key in ('image', 'mask', 'score_map'):
+            ARRAYS[f"{case['id']}/{key}"] = arrays[key]
     if 'lattice' in small:
         ARRAYS[f"{case['id']}/lattice"] = small['lattice']
     if with_labels:

@@ -215,9 +215,11 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             const double* H = &hinv[(size_t)o * 9];
             const double den = H[6] * x + H[7] * y + H[8];
             const double ux = (H[0] * x + H[1] * y + H[2]) / den, uy = (H[3] * x + H[4] * y + H[5]) / den;
-            const float d = (float)((double)L.g * xr + ((double)L.h * yr + 1.0));
-            const float nx = (float)((double)L.a0 * xr + ((double)L.a1 * yr + (double)L.a2));
-            const float ny = (float)((double)L.b0 * xr + ((double)L.b1 * yr + (double)L.b2));
+            CellColumn col;
+            cell_column(L, xr, col);
+            const float d = fma_rn_f32(L.h, yr, col.d);
+            const float nx = fma_rn_f32(L.a1, yr, col.nx);
+            const float ny = fma_rn_f32(L.b1, yr, col.ny);
             const float r = 1.0f / d;
             const double ex = fabs((double)(nx * r) - 32.0 * (ux - sx[o]));
             const double ey = fabs((double)(ny * r) - 32.0 * (uy - sy[o]));

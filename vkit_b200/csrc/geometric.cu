@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "vkb_math.cuh"
 #include "vkb_lattice.cuh"
+#include "vkb_grid.cuh"
+#include "vkb_gather.cuh"
 
 namespace vkb {
 
@@ -418,32 +420,6 @@ __global__ void __launch_bounds__(128) grid_masks_kernel(
 //                             float32 form of the cell's inverse homography re-centred on the
 //                             tile origin (CellLocal, built here from the float64 matrix).
 // ============================================================================================
-struct __align__(16) TileSlot {
-    CellLocal loc;
-    int x0, y0, nr, cellf;  // bbox origin, rows - 1, cell | (over mask budget ? 1 << 31 : 0)
-    int xm, ym;             // 32 * (src corner of the cell) - kRoundMagicBits: base of the fast path
-    int info;               // slot | cell column << 6 | cell row << 16
-    int pad;
-};
-static_assert(sizeof(TileSlot) == VKB_TILE_SLOT_BYTES, "TileSlot layout is part of the ABI");
-
-// Tiles with at most this many candidates resolve their owners once per tile (lane = row, four
-// bit planes); the others go on a separate work list.
-constexpr int kPlaneCands = 15;
-
-// One work item of the persistent remap kernel: a 32 x 32 dst tile (uniform across a warp).
-struct __align__(16) RemapTile {
-    int page, tx0, ty0;
-    int count;  // candidate records; -1: the tile takes the slow exact path
-    int rec;    // index of the first record
-    int pad[3];
-};
-static_assert(sizeof(RemapTile) == VKB_TILE_HEADER_BYTES, "RemapTile layout is part of the ABI");
-
-__device__ __forceinline__ int page_tiles(const vkb_grid_meta& m) {
-    return ((m.dst_w + VKB_TILE - 1) / VKB_TILE) * ((m.dst_h + VKB_TILE - 1) / VKB_TILE);
-}
-
 // exclusive scan of v over the block (1024 threads); returns the exclusive prefix, adds the
 // block total to `carry` (shared).
 __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* warp_sums, int* carry) {
@@ -594,191 +570,6 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
 }
 
 // ============================================================================================
-// Fused remap.  Block = 32 x (32 / R) threads on one 32 x 32 dst tile; warp w owns rows
-// R*w .. R*w + R-1, lane = column.
-//
-//   prologue  the tile's candidate cells (<= VKB_TILE_CAP, ascending cell order) are staged in
-//             shared memory: bbox + packed (slot, cell column, cell row), and the float32 form
-//             of the cell's inverse homography re-centred on the tile origin (CellLocal, built
-//             here from the float64 matrix);
-//   owner     lane-parallel: lane i fetches candidate i's coverage words for the warp's R rows
-//             (shifted to the tile's columns), a ballot keeps the candidates that touch the
-//             band, and each survivor is broadcast with shuffles in ascending order; a pixel
-//             whose coverage bit is set takes the survivor's key, so the last (= largest) cell
-//             wins, exactly like the reference's cell-by-cell map writes;
-//   coords    float32 fast path with a proven acceptance test, float64 path for the pixels that
-//             sit next to a rounding boundary (vkb_math.cuh);
-//   gather    cv::remap's fixed-point bilinear for Image (C channels), Mask and ScoreMap.  The
-//             L1 data pipe is the scarce resource here, so the RGB taps of a row (6 contiguous
-//             bytes at any alignment) come in as 2-3 aligned 32-bit loads, are aligned with
-//             PRMT and blended horizontally with IDP.4A (byte weights) instead of 6 byte loads.
-// ============================================================================================
-#ifndef VKB_REMAP_ROWS
-#define VKB_REMAP_ROWS 4  // dst rows per thread of the remap kernel (4 or 8)
-#endif
-#ifndef VKB_REMAP_BLOCKS
-// resident blocks per SM = the register cap: 3 x 256 threads leaves 85 registers (78 used, no
-// spills); 4 blocks spill and measured 2 % slower, 2 blocks 19 % slower
-#define VKB_REMAP_BLOCKS ((VKB_REMAP_ROWS == 4) ? 3 : 4)
-#endif
-
-
-// Rare paths are kept out of line so the hot loop stays small (instruction cache).
-__device__ __noinline__ int2 cell_coord_exact(const double* __restrict__ H, int x, int y) {
-    int X, Y;
-    cell_coord(H, x, y, X, Y);
-    return make_int2(X, Y);
-}
-
-// coverage of one over-budget cell on row y, restricted to the 32 columns starting at tx0
-__device__ __noinline__ uint32_t cell_row_window_slow(const int32_t* __restrict__ lat, int cols,
-                                                      int cell, int y, int tx0) {
-    const int ccols = cols - 1;
-    const int r = cell / ccols, c = cell - r * ccols;
-    const int i00 = r * cols + c, i01 = i00 + 1, i11 = i00 + cols + 1, i10 = i00 + cols;
-    const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
-    const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
-    uint32_t bits = 0;
-    poly_row_mask<4>(px, py, y, tx0, &bits, 1);
-    return bits;
-}
-
-// ---- bilinear taps ---------------------------------------------------------------------------
-// (sum p*w + 2^14) >> 15 with w = (32-fy)(32-fx)*32 ...: all weights share the factor 32, so it
-// equals (gy*a + fy*b + 512) >> 10 with a, b the horizontally blended rows (gx*p0 + fx*p1).
-
-// One row of an RGB pixel pair: the 6 bytes at `p` (any alignment) as two words
-// lo = R0 G0 B0 R1, hi = G1 B1 . .  (2 aligned 32-bit loads, a third when the bytes straddle).
-struct RowRgb {
-    uint32_t w0, w1, w2, off;
-};
-
-__device__ __forceinline__ RowRgb row_rgb_load(const uint8_t* __restrict__ p) {
-    RowRgb r;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    r.off = (uint32_t)addr & 3u;
-    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-    r.w0 = __ldg(q);
-    r.w1 = __ldg(q + 1);
-    r.w2 = 0;
-    if (r.off == 3u) r.w2 = __ldg(q + 2);  // only then do the 6 bytes reach into a third word
-    return r;
-}
-
-// horizontal blend with IDP.4A: wr / wg0,wg1 / wb0,wb1 are byte-weight words on (lo, hi)
-__device__ __forceinline__ void row_rgb_blend(const RowRgb& row, uint32_t wr, uint32_t wg0,
-                                              uint32_t wg1, uint32_t wb0, uint32_t wb1, int& r,
-                                              int& g, int& b) {
-    const uint32_t sel = 0x3210u + row.off * 0x1111u;
-    const uint32_t lo = __byte_perm(row.w0, row.w1, sel);
-    const uint32_t hi = __byte_perm(row.w1, row.w2, sel);
-    r = (int)__dp4a(lo, wr, 0u);
-    g = (int)__dp4a(hi, wg1, __dp4a(lo, wg0, 0u));
-    b = (int)__dp4a(hi, wb1, __dp4a(lo, wb0, 0u));
-}
-
-// Branch-free taps.  The 2 x 2 footprint at (x0, y0) is read from the in-image window that
-// starts at xs = clamp(x0, 0, w-2), ys = clamp(y0, 0, h-2); taps that fall outside the image
-// (BORDER_CONSTANT 0) get weight 0 and the surviving tap keeps its own weight:
-//   x0 == xs: (32-fx, fx)   x0 == xs-1: (fx, 0)   x0 == xs+1: (0, 32-fx)   otherwise (0, 0).
-// No divergent border branch, so the loads of all pixels of a thread can be in flight together.
-// Needs w >= 2 and h >= 2 (the kernel routes smaller planes to sample_u8_small).
-struct TapWeights {
-    int xs, ys;
-    int wx0, wx1, wy0, wy1;
-};
-
-__device__ __forceinline__ TapWeights tap_weights_plain(int X, int Y) {
-    TapWeights t;
-    t.xs = X >> kInterBits;
-    t.ys = Y >> kInterBits;
-    t.wx1 = X & (kInterTab - 1);
-    t.wy1 = Y & (kInterTab - 1);
-    t.wx0 = kInterTab - t.wx1;
-    t.wy0 = kInterTab - t.wy1;
-    return t;
-}
-
-// true when the 2 x 2 footprint leaves the image (sizes are below 32768, checked by the caller,
-// so cv's saturate_cast<short> of the integer coordinates cannot turn an outside tap into an
-// inside one)
-__device__ __forceinline__ bool tap_outside(const TapWeights& t, int h, int w) {
-    return (unsigned)t.xs > (unsigned)(w - 2) || (unsigned)t.ys > (unsigned)(h - 2);
-}
-
-__device__ __forceinline__ void tap_border_fix(TapWeights& t, int h, int w) {
-    const int x0 = t.xs, y0 = t.ys, fx = t.wx1, fy = t.wy1;
-    t.xs = min(max(x0, 0), w - 2);
-    t.ys = min(max(y0, 0), h - 2);
-    const int dx = x0 - t.xs, dy = y0 - t.ys;
-    t.wx0 = dx == 0 ? kInterTab - fx : (dx == -1 ? fx : 0);
-    t.wx1 = dx == 0 ? fx : (dx == 1 ? kInterTab - fx : 0);
-    t.wy0 = dy == 0 ? kInterTab - fy : (dy == -1 ? fy : 0);
-    t.wy1 = dy == 0 ? fy : (dy == 1 ? kInterTab - fy : 0);
-}
-
-
-// Taps of one pixel, requested now and blended later (so a thread keeps the loads of all its
-// pixels in flight).
-template <int C>
-struct Taps {
-    TapWeights t;
-    RowRgb rgb[2];                // C == 3
-    int p[C == 3 ? 1 : 4 * C];    // C != 3: p00, p01, p10, p11 per channel
-};
-
-template <int C>
-__device__ __forceinline__ void taps_load(const uint8_t* __restrict__ src, int w, Taps<C>& k) {
-    const int pitch = w * C;  // a page plane is < 2 GiB (checked by the caller)
-    const uint8_t* r0 = src + (k.t.ys * pitch + k.t.xs * C);
-    const uint8_t* r1 = r0 + pitch;
-    if (C == 3) {
-        k.rgb[0] = row_rgb_load(r0);
-        k.rgb[1] = row_rgb_load(r1);
-    } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            k.p[(4 * c + 0) % (C == 3 ? 1 : 4 * C)] = __ldg(r0 + c);
-            k.p[(4 * c + 1) % (C == 3 ? 1 : 4 * C)] = __ldg(r0 + C + c);
-            k.p[(4 * c + 2) % (C == 3 ? 1 : 4 * C)] = __ldg(r1 + c);
-            k.p[(4 * c + 3) % (C == 3 ? 1 : 4 * C)] = __ldg(r1 + C + c);
-        }
-    }
-}
-
-template <int C>
-__device__ __forceinline__ void taps_blend(const Taps<C>& k, uint8_t* __restrict__ out) {
-    const TapWeights& t = k.t;
-    if (C == 3) {
-        const uint32_t wr = (uint32_t)t.wx0 | ((uint32_t)t.wx1 << 24);
-        const uint32_t wg0 = (uint32_t)t.wx0 << 8, wg1 = (uint32_t)t.wx1;
-        const uint32_t wb0 = (uint32_t)t.wx0 << 16, wb1 = (uint32_t)t.wx1 << 8;
-        int a[3], b[3];
-        row_rgb_blend(k.rgb[0], wr, wg0, wg1, wb0, wb1, a[0], a[1], a[2]);
-        row_rgb_blend(k.rgb[1], wr, wg0, wg1, wb0, wb1, b[0], b[1], b[2]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) out[c % C] = (uint8_t)((t.wy0 * a[c] + t.wy1 * b[c] + 512) >> 10);
-    } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            constexpr int M = C == 3 ? 1 : 4 * C;
-            const int a = t.wx0 * k.p[(4 * c + 0) % M] + t.wx1 * k.p[(4 * c + 1) % M];
-            const int b = t.wx0 * k.p[(4 * c + 2) % M] + t.wx1 * k.p[(4 * c + 3) % M];
-            out[c] = (uint8_t)((t.wy0 * a + t.wy1 * b + 512) >> 10);
-        }
-    }
-}
-
-// planes narrower or shorter than 2 px: plain per-tap bounds checks
-template <int C>
-__device__ __noinline__ uint32_t sample_u8_small(const uint8_t* __restrict__ src, int h, int w,
-                                                 int X, int Y) {
-    uint8_t out[4] = {0, 0, 0, 0};
-    bilinear_u8<C>(src, h, w, (long long)w * C, X, Y, out);
-    return out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-}
-
-// ============================================================================================
 // Affine / perspective warp (rotate / shear / skew: affine.py:38-43, 416-456).  Block (32, 8)
 // covers a 32 x 32 dst tile, 4 rows per thread.  The coordinates follow cv::warpAffine /
 // cv::warpPerspective (double arithmetic, 10-bit / 5-bit fixed point); the gather is the remap's:
@@ -910,363 +701,6 @@ __global__ void __launch_bounds__(256) warp_fused_kernel(const vkb_warp_page* __
             pl.dst_score[(long long)y * pl.dst_w + x] =
                 bilinear_f32(pl.src_score, src_h, src_w, src_w, X[k], Y[k]);
         }
-    }
-}
-
-// ---- cp.async plumbing of the persistent remap kernel -----------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// Persistent kernel, WARP-private work items: a block owns a contiguous share of the flat tile
-// list and its warps take the tiles of that share round robin (neighbouring tiles at the same
-// time, so their source rows meet in L1); a warp walks the R-row bands of its 32 x 32 tile by
-// itself.  No block-level synchronisation exists: every warp stages the candidate records of its
-// next tile with cp.async into its own half of a 2 x 32-record shared-memory buffer while it
-// works on the current one (a tile with 33..64 records takes both halves and is loaded when it
-// starts), so a warp never waits for another warp.
-constexpr int kWarpSlots = 64;
-
-// LARGE = false: the tiles with at most kPlaneCands candidates (99.8 % of them), owners resolved
-// once per tile with lane = row; LARGE = true: the remaining tiles (more candidates, or the exact
-// slow path), owners resolved band by band.  Two launches over the same tile list, each skipping
-// the other's tiles, keep both kernels inside the register budget.
-template <int C, bool MASK, bool SCORE, int R, bool LARGE>
-__global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_remap_kernel(
-    const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
-    int c_max, int p_max, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
-    const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
-    const RemapTile* __restrict__ headers, const TileSlot* __restrict__ slots,
-    const int32_t* __restrict__ lattice_i, const int32_t* __restrict__ large) {
-    constexpr int kWarps = VKB_TILE / R;
-    __shared__ __align__(16) TileSlot sm_all[kWarps][kWarpSlots];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    TileSlot* __restrict__ sm = sm_all[warp];
-
-    // LARGE = false: contiguous share of the flat tile list per block, round robin over its
-    // warps.  LARGE = true: the (short, clustered) list of large tiles, strided over all warps.
-    const int total = LARGE ? large[0] : tile_base[n_pages];
-    const int per = (total + gridDim.x - 1) / gridDim.x;
-    const int w_begin = LARGE ? 0 : blockIdx.x * per;
-    const int n_block = LARGE ? total : min(total, w_begin + per) - w_begin;
-    const int first = LARGE ? blockIdx.x * kWarps + warp : warp;
-    const int stride = LARGE ? gridDim.x * kWarps : kWarps;
-    const int n_tiles = n_block > first ? (n_block - first + stride - 1) / stride : 0;  // of this warp
-    if (n_tiles <= 0) return;
-
-    auto load_header = [&](int k) {
-        RemapTile t;
-        int index = w_begin + first + stride * min(k, n_tiles - 1);
-        if (LARGE) index = large[1 + index];
-        const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
-        const int4 a = __ldg(src), b = __ldg(src + 1);
-        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
-        return t;
-    };
-    auto stage = [&](const RemapTile& t, int base) {  // this warp's copies of one tile's records
-        const int chunks = t.count * (VKB_TILE_SLOT_BYTES / 16);  // <= 256; negative on the slow path
-        const char* g = reinterpret_cast<const char*>(slots + t.rec);
-        char* d = reinterpret_cast<char*>(sm + base);
-        for (int i = lane; i < chunks; i += 32) cp_async_16(d + i * 16, g + i * 16);
-        cp_async_commit();
-    };
-
-    RemapTile h0 = load_header(0), h1 = load_header(1);
-    int cur_base = 0;
-    bool cur_staged = false;
-
-    // per-page state, reloaded when the page changes
-    int ctx_page = -1;
-    int dst_h = 0, dst_w = 0, src_h = 0, src_w = 0, cols = 0;
-    float t_odd = 0.f, t_even = 0.f;
-    const uint8_t* __restrict__ src_image = nullptr;
-    uint8_t* __restrict__ dst_image = nullptr;
-    const uint8_t* __restrict__ src_mask = nullptr;
-    uint8_t* __restrict__ dst_mask = nullptr;
-    const float* __restrict__ src_score = nullptr;
-    float* __restrict__ dst_score = nullptr;
-
-    auto mine = [](const RemapTile& t) {
-        return ((unsigned)t.count <= (unsigned)kPlaneCands) != LARGE;
-    };
-    for (int k = 0; k < n_tiles; ++k) {
-        const RemapTile cur = h0;
-        if (!mine(cur)) {  // the other launch's tile (never staged ahead)
-            h0 = h1;
-            h1 = load_header(k + 2);
-            continue;
-        }
-        if (!cur_staged) {
-            cur_base = 0;
-            stage(cur, 0);
-        }
-        // the next tile's records go to the other half when both tiles fit a half
-        const bool ahead = k + 1 < n_tiles && mine(h1) && cur.count <= kWarpSlots / 2
-                           && h1.count <= kWarpSlots / 2;
-        const int next_base = cur_base ? 0 : kWarpSlots / 2;
-        if (ahead) {
-            stage(h1, next_base);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncwarp();
-
-        const int page = cur.page;
-        if (page != ctx_page) {
-            const vkb_planes* __restrict__ pl = planes + page;
-            dst_h = pl->dst_h; dst_w = pl->dst_w; src_h = pl->src_h; src_w = pl->src_w;
-            src_image = pl->src_image; dst_image = pl->dst_image;
-            src_mask = pl->src_mask; dst_mask = pl->dst_mask;
-            src_score = pl->src_score; dst_score = pl->dst_score;
-            cols = pages[page].cols;
-            fast_thresholds(max(src_h, src_w), t_odd, t_even);
-            ctx_page = page;
-        }
-        const TileSlot* __restrict__ S = sm + cur_base;
-        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
-        const bool fast = count >= 0;
-        const size_t page_cell0 = (size_t)page * c_max;
-        const int x = tx0 + lane;
-
-        // ---- owner, whole tile at once: lane = dst row ------------------------------------
-        // Bit plane b of a row holds bit b of (slot + 1) of every pixel's owner (0 = uncovered).
-        // Candidates come in ascending cell order and later ones overwrite earlier ones, exactly
-        // like the reference's cell-by-cell map writes; one coverage word per candidate and row.
-        // Four planes cover tiles with up to 15 candidates (mean 8.7).
-        uint32_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0;
-        constexpr bool planes_ok = !LARGE;
-        if (planes_ok) {
-            const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
-            const int row_y = ty0 + lane;
-            for (int s = 0; s < count; ++s) {
-                const int4 b = *reinterpret_cast<const int4*>(&S[s].x0);  // same for all lanes
-                const int r = row_y - b.y;
-                uint32_t win = 0u;
-                if ((unsigned)r <= (unsigned)b.z) {
-                    if (b.w >= 0) {
-                        const uint32_t wd = __ldg(page_masks + (b.w * VKB_CELL_MASK_WORDS + r));
-                        const int rel = tx0 - b.x;  // |rel| < 32: the bbox overlaps the tile
-                        win = rel >= 0 ? (wd >> rel) : (wd << (-rel));
-                    } else {
-                        win = cell_row_window_slow(lattice_i + (size_t)page * p_max * 2, cols,
-                                                   b.w & 0x7FFFFFFF, row_y, tx0);
-                    }
-                }
-                const uint32_t id = (uint32_t)s + 1u;
-                pl0 = (pl0 & ~win) | (win & (0u - (id & 1u)));
-                pl1 = (pl1 & ~win) | (win & (0u - ((id >> 1) & 1u)));
-                pl2 = (pl2 & ~win) | (win & (0u - ((id >> 2) & 1u)));
-                pl3 = (pl3 & ~win) | (win & (0u - ((id >> 3) & 1u)));
-            }
-        }
-
-#pragma unroll 1
-        for (int band = 0; band < kWarps; ++band) {
-        const int ry0 = ty0 + band * R;
-        if (ry0 >= dst_h) break;
-
-        int X[R], Y[R];
-        if (ry0 < dst_h) {
-            const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
-            // ---- owner ---------------------------------------------------------------------
-            // key: fast mode -> info of the owning slot; overflow mode -> cell index; -1 = none
-            int key[R];
-#pragma unroll
-            for (int j = 0; j < R; ++j) key[j] = -1;
-            if (planes_ok) {
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int row = band * R + j;
-                    uint32_t id = (__shfl_sync(0xffffffffu, pl0, row) >> lane) & 1u;
-                    id |= ((__shfl_sync(0xffffffffu, pl1, row) >> lane) & 1u) << 1;
-                    id |= ((__shfl_sync(0xffffffffu, pl2, row) >> lane) & 1u) << 2;
-                    id |= ((__shfl_sync(0xffffffffu, pl3, row) >> lane) & 1u) << 3;
-                    key[j] = (int)id - 1;
-                }
-            }
-            const int n_cand = planes_ok ? 0 : (fast ? count : (pages[page].rows - 1) * (cols - 1));
-            for (int base = 0; base < n_cand; base += 32) {
-                const int s = base + lane;
-                uint32_t win[R];
-#pragma unroll
-                for (int j = 0; j < R; ++j) win[j] = 0u;
-                int my_key = s;
-                if (s < n_cand) {
-                    int4 b;
-                    if (fast) {
-                        b = *reinterpret_cast<const int4*>(&S[s].x0);  // records sit in rank order: key = s
-                    } else {
-                        const int4 g = cell_box[page_cell0 + s];
-                        b = make_int4(g.x, g.y, g.w - g.y, s | ((g.z & 0x40000000) ? (int)0x80000000 : 0));
-                    }
-                    const int r = ry0 - b.y;    // band row 0 relative to the bbox
-                    const int rel = tx0 - b.x;  // tile column 0 relative to the bbox
-                    if (r + (R - 1) >= 0 && r <= b.z) {
-                        if (b.w >= 0) {
-                            if (fast || (rel > -32 && rel < 32)) {
-                                const uint32_t* __restrict__ m = page_masks + (b.w * VKB_CELL_MASK_WORDS + r);
-#pragma unroll
-                                for (int j = 0; j < R; ++j) {
-                                    if ((unsigned)(r + j) <= (unsigned)b.z) {
-                                        const uint32_t wd = __ldg(m + j);
-                                        win[j] = rel >= 0 ? (wd >> rel) : (wd << (-rel));
-                                    }
-                                }
-                            }
-                        } else {
-                            const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
-#pragma unroll
-                            for (int j = 0; j < R; ++j)
-                                win[j] = cell_row_window_slow(lat, cols, b.w & 0x7FFFFFFF, ry0 + j, tx0);
-                        }
-                    }
-                }
-                uint32_t any = win[0];
-#pragma unroll
-                for (int j = 1; j < R; ++j) any |= win[j];
-                unsigned active = __ballot_sync(0xffffffffu, any != 0u);
-                while (active) {
-                    const int src_lane = __ffs(active) - 1;
-                    active &= active - 1;
-                    const int kk = __shfl_sync(0xffffffffu, my_key, src_lane);
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const uint32_t wd = __shfl_sync(0xffffffffu, win[j], src_lane);
-                        if ((wd >> lane) & 1u) key[j] = kk;
-                    }
-                }
-            }
-
-            {
-                // ---- coordinates -----------------------------------------------------------
-                // uncovered pixels keep map value (0, 0); the fast path is evaluated for every
-                // pixel (slot 0 for uncovered ones) and the result selected afterwards
-                const float xr = (float)lane;
-                const float yr0 = (float)(band * R);
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const bool covered = key[j] >= 0;
-                    if (fast) {
-                        const int slot = covered ? key[j] : 0;
-                        const int2 base = *reinterpret_cast<const int2*>(&S[slot].xm);
-                        const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j, base.x, base.y,
-                                                        t_odd, t_even, X[j], Y[j]);
-                        if (covered && !ok) {
-                            const int cell = S[slot].cellf & 0x7FFFFFFF;
-                            const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
-                            X[j] = e.x;
-                            Y[j] = e.y;
-                        }
-                    } else if (covered) {
-                        const int2 e = cell_coord_exact(hinv + (page_cell0 + key[j]) * 9, x, ry0 + j);
-                        X[j] = e.x;
-                        Y[j] = e.y;
-                    }
-                    if (!covered) {
-                        X[j] = 0;
-                        Y[j] = 0;
-                    }
-                }
-            }
-        }
-        if (ry0 < dst_h) {
-            if (x < dst_w) {
-                // ---- gather ----------------------------------------------------------------
-                const int di0 = ry0 * dst_w + x;
-                const bool tiny = src_h < 2 || src_w < 2;
-                // tap weights of the R pixels, shared by Image and Mask; footprints that leave
-                // the image are rare, so all of them are fixed up behind ONE branch
-                TapWeights tw[R];
-                bool outside = false;
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    tw[j] = tap_weights_plain(X[j], Y[j]);
-                    outside |= tap_outside(tw[j], src_h, src_w);
-                }
-                if (outside && !tiny) {
-#pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if (tap_outside(tw[j], src_h, src_w)) tap_border_fix(tw[j], src_h, src_w);
-                }
-                if (C > 0) {
-                    constexpr int CC = C > 0 ? C : 1;
-                    uint8_t px[R][CC];
-                    if (tiny) {
-#pragma unroll
-                        for (int j = 0; j < R; ++j) {
-                            const uint32_t v = sample_u8_small<CC>(src_image, src_h, src_w, X[j], Y[j]);
-#pragma unroll
-                            for (int c = 0; c < CC; ++c) px[j][c] = (uint8_t)(v >> (8 * c));
-                        }
-                    } else {
-                        Taps<CC> taps[R];
-#pragma unroll
-                        for (int j = 0; j < R; ++j) {
-                            taps[j].t = tw[j];
-                            taps_load<CC>(src_image, src_w, taps[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < R; ++j) taps_blend<CC>(taps[j], px[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        if (ry0 + j < dst_h) {
-                            uint8_t* d = dst_image + (di0 + j * dst_w) * CC;
-                            if (CC == 4) {
-                                *reinterpret_cast<uchar4*>(d) =
-                                    make_uchar4(px[j][0], px[j][1 % CC], px[j][2 % CC], px[j][3 % CC]);
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < CC; ++c) d[c] = px[j][c];
-                            }
-                        }
-                    }
-                }
-                if (MASK) {
-                    uint8_t m[R][1];
-                    if (tiny) {
-#pragma unroll
-                        for (int j = 0; j < R; ++j)
-                            m[j][0] = (uint8_t)sample_u8_small<1>(src_mask, src_h, src_w, X[j], Y[j]);
-                    } else {
-                        Taps<1> taps[R];
-#pragma unroll
-                        for (int j = 0; j < R; ++j) {
-                            taps[j].t = tw[j];
-                            taps_load<1>(src_mask, src_w, taps[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < R; ++j) taps_blend<1>(taps[j], m[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if (ry0 + j < dst_h) dst_mask[di0 + j * dst_w] = m[j][0];
-                }
-                if (SCORE) {
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const float v = bilinear_f32(src_score, src_h, src_w, src_w, X[j], Y[j]);
-                        if (ry0 + j < dst_h) dst_score[di0 + j * dst_w] = v;
-                    }
-                }
-            }
-        }
-        }  // band
-        __syncwarp();  // every lane is done with this tile's records before their half is reused
-        cur_staged = ahead;
-        cur_base = next_base;
-        h0 = h1;
-        h1 = load_header(k + 2);  // one exposed L2 latency per tile (~1 % of a tile's time)
     }
 }
 
@@ -1588,113 +1022,6 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
         tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
         reinterpret_cast<RemapTile*>(tile_headers), large);
     return check_launch("grid_tile_records_kernel");
-}
-
-static int remap_grid_blocks(int blocks_per_sm) {
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess
-            || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess
-            || sm_count <= 0)
-            sm_count = 148;
-    }
-    return sm_count * blocks_per_sm;
-}
-
-// One side stream + fork / join events per device, created on first use (the only state the
-// library keeps besides the colour tables; work submitted through it is ordered with the
-// caller's stream by the two events, so the call stays stream-ordered for the caller).
-struct RemapSide {
-    cudaStream_t stream;
-    cudaEvent_t fork, join;
-};
-static RemapSide* remap_side() {
-    static RemapSide sides[64];
-    static bool ready[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!ready[dev]) {
-        RemapSide s;
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        sides[dev] = s;
-        ready[dev] = true;
-    }
-    return &sides[dev];
-}
-
-extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t n_pages,
-                              int32_t p_max, int32_t c_max, int32_t t_max, int32_t s_cap,
-                              const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
-                              const uint32_t* cell_masks, const int32_t* tile_count,
-                              const int32_t* tile_off, const int32_t* tile_base,
-                              const void* tile_slots, const void* tile_headers,
-                              int32_t image_channels, int32_t has_mask, int32_t has_score,
-                              void* stream) {
-    VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
-                    && tile_off && tile_base && tile_slots && tile_headers, "bad arguments");
-    (void)s_cap;
-    const int32_t* large = reinterpret_cast<const int32_t*>(
-        reinterpret_cast<const char*>(tile_headers) + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
-    VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
-    VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
-                    || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
-    VKB_REQUIRE(image_channels || has_mask || has_score, "nothing to remap");
-    cudaStream_t st = (cudaStream_t)stream;
-    constexpr int R = VKB_REMAP_ROWS;
-    constexpr int kBlocksPerSm = VKB_REMAP_BLOCKS;
-    const int grid = remap_grid_blocks(kBlocksPerSm);
-#define VKB_LAUNCH_REMAP_1(CH, M, S, LARGE)                                                     \
-    grid_remap_kernel<CH, M, S, R, LARGE><<<grid, 32 * (VKB_TILE / R), 0, st>>>(               \
-        planes, pages, n_pages, c_max, p_max, hinv, reinterpret_cast<const int4*>(cell_box),   \
-        cell_masks, tile_base, reinterpret_cast<const RemapTile*>(tile_headers),               \
-        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, large)
-    // The few large tiles run on a side stream next to the main launch (disjoint dst tiles):
-    // alone they are a latency-bound tail of ~30 us.
-    RemapSide* side = remap_side();
-    cudaStream_t main_st = st;
-    // fork / launch / join are issued under a lock: the events are shared by all callers
-    static std::mutex side_mutex;
-    std::lock_guard<std::mutex> side_lock(side_mutex);
-    if (side) {
-        VKB_CUDA(cudaEventRecord(side->fork, main_st));
-        VKB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    }
-#define VKB_LAUNCH_REMAP(CH, M, S)                \
-    do {                                          \
-        st = side ? side->stream : main_st;       \
-        VKB_LAUNCH_REMAP_1(CH, M, S, true);       \
-        st = main_st;                             \
-        VKB_LAUNCH_REMAP_1(CH, M, S, false);      \
-    } while (0)
-    const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
-    switch (key) {
-        case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;
-        case 0 * 4 + 2: VKB_LAUNCH_REMAP(0, true, false); break;
-        case 0 * 4 + 3: VKB_LAUNCH_REMAP(0, true, true); break;
-        case 1 * 4 + 0: VKB_LAUNCH_REMAP(1, false, false); break;
-        case 1 * 4 + 1: VKB_LAUNCH_REMAP(1, false, true); break;
-        case 1 * 4 + 2: VKB_LAUNCH_REMAP(1, true, false); break;
-        case 1 * 4 + 3: VKB_LAUNCH_REMAP(1, true, true); break;
-        case 3 * 4 + 0: VKB_LAUNCH_REMAP(3, false, false); break;
-        case 3 * 4 + 1: VKB_LAUNCH_REMAP(3, false, true); break;
-        case 3 * 4 + 2: VKB_LAUNCH_REMAP(3, true, false); break;
-        case 3 * 4 + 3: VKB_LAUNCH_REMAP(3, true, true); break;
-        case 4 * 4 + 0: VKB_LAUNCH_REMAP(4, false, false); break;
-        case 4 * 4 + 1: VKB_LAUNCH_REMAP(4, false, true); break;
-        case 4 * 4 + 2: VKB_LAUNCH_REMAP(4, true, false); break;
-        case 4 * 4 + 3: VKB_LAUNCH_REMAP(4, true, true); break;
-        default: VKB_REQUIRE(false, "unsupported container combination");
-    }
-#undef VKB_LAUNCH_REMAP
-#undef VKB_LAUNCH_REMAP_1
-    if (side) {
-        VKB_CUDA(cudaEventRecord(side->join, side->stream));
-        VKB_CUDA(cudaStreamWaitEvent(main_st, side->join, 0));
-    }
-    return check_launch("grid_remap_kernel");
 }
 
 extern "C" int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double* xy_in,

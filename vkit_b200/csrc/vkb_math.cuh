@@ -254,19 +254,37 @@ VKB_HD bool fast_axis(float f, int base_m, float t_odd, float t_even, int& X) {
     return fabsf(d) < ((v.i & 1) ? t_odd : t_even);
 }
 
-// (xr, yr): pixel - tile origin as floats (exact small integers).
-VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int x0m, int y0m, float t_odd,
-                            float t_even, int& X, int& Y) {
+VKB_HD float fma_rn_f32(float a, float b, float c) {
 #if defined(__CUDA_ARCH__)
-    const float d = __fmaf_rn(L.g, xr, __fmaf_rn(L.h, yr, 1.0f));
-    const float nx = __fmaf_rn(L.a0, xr, __fmaf_rn(L.a1, yr, L.a2));
-    const float ny = __fmaf_rn(L.b0, xr, __fmaf_rn(L.b1, yr, L.b2));
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);  // correctly rounded on the host as well
+#endif
+}
+
+// The three linear forms are evaluated column part first: the part that depends on the pixel's
+// column only (CellColumn) is shared by every row a thread visits inside one cell, a row then
+// costs three FMAs.  Two roundings per form, like the row-first order.
+struct CellColumn {
+    float nx, ny, d;  // a0*x' + a2, b0*x' + b2, g*x' + 1
+};
+
+VKB_HD void cell_column(const CellLocal& L, float xr, CellColumn& c) {
+    c.nx = fma_rn_f32(L.a0, xr, L.a2);
+    c.ny = fma_rn_f32(L.b0, xr, L.b2);
+    c.d = fma_rn_f32(L.g, xr, 1.0f);
+}
+
+// one row of a prepared column: (a1, b1, h) = L.a1, L.b1, L.h
+VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h, float yr, int x0m,
+                                int y0m, float t_odd, float t_even, int& X, int& Y) {
+    const float d = fma_rn_f32(h, yr, c.d);
+    const float nx = fma_rn_f32(a1, yr, c.nx);
+    const float ny = fma_rn_f32(b1, yr, c.ny);
+#if defined(__CUDA_ARCH__)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));  // one MUFU.RCP, <= 1 ulp
 #else
-    const float d = (float)((double)L.g * xr + ((double)L.h * yr + 1.0));
-    const float nx = (float)((double)L.a0 * xr + ((double)L.a1 * yr + (double)L.a2));
-    const float ny = (float)((double)L.b0 * xr + ((double)L.b1 * yr + (double)L.b2));
     const float r = 1.0f / d;
 #endif
     const float fx = VKB_FMUL(nx, r), fy = VKB_FMUL(ny, r);
@@ -274,6 +292,14 @@ VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int x0m, int
     const bool oky = fast_axis(fy, y0m, t_odd, t_even, Y);
     // NaN / inf anywhere -> false (every comparison fails)
     return okx && oky && fmaxf(fabsf(fx), fabsf(fy)) < kFastRange;
+}
+
+// (xr, yr): pixel - tile origin as floats (exact small integers).
+VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int x0m, int y0m, float t_odd,
+                            float t_even, int& X, int& Y) {
+    CellColumn c;
+    cell_column(L, xr, c);
+    return cell_coord_fast_row(c, L.a1, L.b1, L.h, yr, x0m, y0m, t_odd, t_even, X, Y);
 }
 
 // ---------------------------------------------------------------------------------------
