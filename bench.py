@@ -317,6 +317,8 @@ def main():
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     parser.add_argument('--batch', type=int, default=BATCH)
     parser.add_argument('--skip-cpu-baseline', action='store_true')
+    parser.add_argument('--kernel-only', action='store_true',
+                        help='kernel experiments: no e2e leg, no CPU baseline (not a bench line)')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -411,13 +413,16 @@ def main():
         return int(offsets[-1])
 
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        d2h = e2e_step()
-    barrier()
-    e2e_ms = 1000.0 * (time.perf_counter() - t0) / e2e_steps
+    if args.kernel_only:
+        d2h, e2e_ms = 0, float('nan')
+    else:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d2h = e2e_step()
+        barrier()
+        e2e_ms = 1000.0 * (time.perf_counter() - t0) / e2e_steps
 
     # ---- reduce over ranks (max time, summed counters) --------------------------------------
     stats = torch.tensor([elapsed_ms, e2e_ms, float(np.mean(remap_ms))], dtype=torch.float64,
@@ -465,7 +470,7 @@ def main():
             },
         }
         line['config']['numa_local_cpus'] = numa_cpus
-        if not args.skip_cpu_baseline:
+        if not (args.skip_cpu_baseline or args.kernel_only):
             unbind_cpus()
             cores = max(1, min(os.cpu_count() or 1, 64))
             n_pages = cores * CPU_PAGES_PER_WORKER

@@ -233,6 +233,7 @@ int vkb_fill_polygons(void* dst, int32_t dst_f32, int32_t h, int32_t w, const in
  *   alpha array  : out = trunc((1 - a) * f32(dst) + a * f32(value))   (float32, no FMA)
  *   alpha scalar : 1 -> assign (or keep max / keep min), (0,1) -> same blend with a = f32(alpha)
  * ------------------------------------------------------------------------------------- */
+#define VKB_BLEND_FLOAT_CONST 4
 typedef struct vkb_blend_item {
     void* dst;             /* full destination plane, HWC uint8 or HW float32 */
     const void* value_arr; /* NULL: value_const; else same dtype as dst, origin at region */
@@ -245,7 +246,9 @@ typedef struct vkb_blend_item {
     int32_t value_pitch; /* pixels per row of value_arr */
     int32_t mask_pitch;
     int32_t alpha_pitch;
-    int32_t keep_mode; /* 0 none, 1 keep max, 2 keep min */
+    int32_t keep_mode; /* 0 none, 1 keep max, 2 keep min; | VKB_BLEND_FLOAT_CONST: an alpha blend into a
+                          uint8 plane uses value_const as float32 instead of casting it to uint8
+                          first (fog on a GRAYSCALE page, effect.py:194-197) */
     float alpha;
     float value_const[4];
 } vkb_blend_item;

@@ -148,6 +148,20 @@ extern "C" void hs_fill_poly4(const int32_t* pts, int h, int w, uint8_t* out) {
     // masks kernel uses; a pixel on which they disagree is reported as 7
     EdgeConst E[4];
     for (int i = 0; i < 4; ++i) edge_setup(px[(i + 3) & 3], py[(i + 3) & 3], px[i], py[i], E[i]);
+    // third form (grid_masks_kernel): outline walked per edge + per-row scan fill, for polygons
+    // that fit one 32-bit window per row
+    std::vector<uint32_t> walked(h, 0u);
+    EdgeScan ES[4];
+    const bool one_word = w <= 32;
+    if (one_word) {
+        for (int i = 0; i < 4; ++i) {
+            const int ax = px[(i + 3) & 3], ay = py[(i + 3) & 3], bx = px[i], by = py[i];
+            edge_scan_setup(ax, ay, bx, by, ES[i]);
+            edge_walk(ax, ay, bx, by, [&](int x, int y) {
+                if (y >= 0 && y < h && x >= 0 && x < 32) walked[y] |= 1u << x;
+            });
+        }
+    }
     for (int y = 0; y < h; ++y) {
         std::fill(words.begin(), words.end(), 0u);
         std::fill(words2.begin(), words2.end(), 0u);
@@ -163,6 +177,8 @@ extern "C" void hs_fill_poly4(const int32_t* pts, int h, int w, uint8_t* out) {
                 if (quad_row_mask_fast(E, y, 32 * wd) != words[wd])
                     for (int x = 32 * wd; x < w && x < 32 * wd + 32; ++x) out[(size_t)y * w + x] = 9;
         }
+        if (one_word && (walked[y] | quad_fill_row(ES, y, 0)) != words[0])
+            for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = 11;
     }
 }
 

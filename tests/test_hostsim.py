@@ -161,6 +161,25 @@ def test_fill_poly_rows_random_quads(hs):
         pts = np.ascontiguousarray(quad.astype(np.int32))
         hs.hs_fill_poly4(pts.ctypes.data, h, w, out.ctypes.data)
         assert np.array_equal(out, ref), quad.tolist()
+    # quads that fit one 32-bit window per row: also through the walked-outline + row-fill form of
+    # the masks kernel (hs_fill_poly4 marks a row on which that form disagrees with 11)
+    for it in range(3000):
+        if it % 3 == 0:
+            quad = rng.integers(0, 32, (4, 2))  # arbitrary, incl. self-intersecting / degenerate
+        else:
+            side = int(rng.integers(1, 24))
+            jitter = int(rng.integers(0, 5))
+            quad = np.array([[0, 0], [side, 0], [side, side], [0, side]]) + rng.integers(
+                -jitter, jitter + 1, (4, 2))
+        quad -= quad.min(axis=0)
+        w, h = int(quad[:, 0].max() + 1), int(quad[:, 1].max() + 1)
+        if w > 32:
+            continue
+        ref = cm.fill_poly((h, w), quad)
+        out = np.zeros((h, w), np.uint8)
+        pts = np.ascontiguousarray(quad.astype(np.int32))
+        hs.hs_fill_poly4(pts.ctypes.data, h, w, out.ctypes.data)
+        assert np.array_equal(out, ref), quad.tolist()
 
 
 def test_homography_closed_form(hs):

@@ -3,7 +3,8 @@ by the live reference (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from common import (AFFINE_OPS, golden_array, golden_cases, make_inputs, oracle_geometric, sha)
+from common import (AFFINE_OPS, assert_skew_close, golden_array, golden_cases, make_inputs,
+                    oracle_geometric, sha)
 from oracle import vkit_port as port
 
 
@@ -33,9 +34,7 @@ def test_geometric_small_numpy_models(case):
     if case['op'].startswith('skew'):
         # closed-form homography vs cv2's LAPACK SVD solve: identical except at exact 1/64 px
         # rounding ties (DESIGN.md "skew ties"); bounded, not bit-exact.
-        ref = golden_array(case, 'image')
-        diff = np.abs(out['image'].astype(int) - ref.astype(int)).max(axis=-1)
-        assert (diff > 0).mean() <= 0.005 and diff.max() <= 16
+        assert_skew_close(case, out, 'oracle ')
         return
     for key in ('image', 'mask', 'score_map'):
         assert sha(out[key]) == case['sha'][key], key

@@ -20,6 +20,7 @@ TILE_CAP = 64
 TILE_SLOT_BYTES = 64
 TILE_HEADER_BYTES = 32
 
+BLEND_FLOAT_CONST = 4
 WARP_AFFINE = 0
 WARP_PERSPECTIVE = 1
 PROJ_CAMERA = 0

@@ -226,7 +226,9 @@ class AffineBatch:
         total = int(offsets[-1])
         src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
         src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
-        planes = self.records['planes']
+        # a fresh block of container pointers per call: a second run() with other containers must
+        # not see the (possibly freed) arenas of the previous one
+        planes = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
         planes['src_h'] = [s[0] for s in self.shapes]
         planes['src_w'] = [s[1] for s in self.shapes]
         planes['dst_h'] = [s[0] for s in shapes]
@@ -238,6 +240,8 @@ class AffineBatch:
                                                         else None)
             if channels is None:
                 raise ValueError('flat image arenas need `channels`')
+            if int(images.numel()) != int(src_pixels.sum()) * channels:
+                raise ValueError('images do not hold the pages of this batch')
             image_arena = dv.empty((total * channels,), np.uint8)
             planes['src_image'] = np.uint64(images.data_ptr()) + src_offsets * np.uint64(channels)
             planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
@@ -246,15 +250,22 @@ class AffineBatch:
         else:
             channels = 0
         if masks is not None:
+            if int(masks.numel()) != int(src_pixels.sum()):
+                raise ValueError('masks do not hold the pages of this batch')
             mask_arena = dv.empty((total,), np.uint8)
             planes['src_mask'] = np.uint64(masks.data_ptr()) + src_offsets
             planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
         if score_maps is not None:
+            if int(score_maps.numel()) != int(src_pixels.sum()):
+                raise ValueError('score maps do not hold the pages of this batch')
             score_arena = dv.empty((total,), np.float32)
             planes['src_score'] = np.uint64(score_maps.data_ptr()) + src_offsets * np.uint64(4)
             planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
-        self.records['planes'] = planes
-        pages_dev = dv.upload_structs(self.records)
+        if images is None and masks is None and score_maps is None:
+            raise ValueError('nothing to warp')
+        records = self.records.copy()
+        records['planes'] = planes
+        pages_dev = dv.upload_structs(records)
         nv.check(nv.lib().vkb_warp_fused(dv.ptr(pages_dev), self.n,
                                          max(s[0] for s in shapes), max(s[1] for s in shapes),
                                          dv.stream_ptr()), 'vkb_warp_fused')

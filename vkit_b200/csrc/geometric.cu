@@ -353,56 +353,97 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
 }
 
 // ============================================================================================
-// Coverage masks: warp per cell, lane per row of the cell's bounding box.  The four edges are
-// prepared once per cell (lane e sets up edge e: end point order, deltas, the 16.16 scan slope
-// and the reciprocal of the Bresenham divisor) and shared through shared memory; a row then only
-// evaluates the closed forms.  (Half a warp per cell was measured 1.5x SLOWER.)
+// Coverage masks (cv.fillPoly of every lattice cell, type.py:199-207).  A warp takes EIGHT cells at
+// a time:
+//
+//   outline   lane = (cell, edge): the lane walks its edge like cv::LineIterator (edge_walk: one
+//             add and one compare per pixel) and ORs the pixels into the cell's row words in
+//             shared memory; the four scan-edge records of the cell are set up on the way;
+//   fill      lane = (cell, row), the rows of the eight cells back to back: crossings of the four
+//             scan edges, 5-exchange sort, spans, OR with the outline word, one store per row.
+//
+// ~100 warp instructions per cell; the first generation (warp per cell, lane per row, closed-form
+// outline per row) spent ~500 and was the second most expensive kernel of the step.
 // ============================================================================================
-__global__ void __launch_bounds__(128) grid_masks_kernel(
+constexpr int kMaskWarps = 4;
+constexpr int kMaskCells = 8;  // cells per warp and step
+
+__global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max,
     const int32_t* __restrict__ lattice_i, int32_t* __restrict__ cell_box,
     uint32_t* __restrict__ cell_masks) {
+    __shared__ uint32_t sm_rows[kMaskWarps][kMaskCells][VKB_CELL_MASK_WORDS];
+    __shared__ EdgeScan sm_scan[kMaskWarps][kMaskCells][4];
+    __shared__ int2 sm_org[kMaskWarps][kMaskCells];  // bbox origin (x0, y0)
     const int page = blockIdx.y;
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
     const int C = (pg.rows - 1) * ccols;
-    const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (cell >= C) return;
-    const int lane = threadIdx.x & 31;
-    const int r = floor_div_small(cell, ccols, __fdividef(1.0f, (float)ccols));
-    const int c = cell - r * ccols;
-    const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
-    const int i00 = r * pg.cols + c, i01 = i00 + 1, i11 = i00 + pg.cols + 1, i10 = i00 + pg.cols;
-    const int px[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
-    const int py[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
-    const int x0 = min(min(px[0], px[1]), min(px[2], px[3]));
-    const int x1 = max(max(px[0], px[1]), max(px[2], px[3]));
-    const int y0 = min(min(py[0], py[1]), min(py[2], py[3]));
-    const int y1 = max(max(py[0], py[1]), max(py[2], py[3]));
-    const int nrows = y1 - y0 + 1;
-    const int nwords = (x1 - x0 + 32) / 32;
-    uint32_t* out = cell_masks + ((size_t)page * c_max + cell) * VKB_CELL_MASK_WORDS;
-    if (nwords != 1 || nrows > VKB_CELL_MASK_WORDS) {
-        // too large for the fixed budget: the remap kernel rasterises this cell on the fly.
-        if (lane == 0) cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
-        return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell0 = (blockIdx.x * kMaskWarps + warp) * kMaskCells;
+    if (cell0 >= C) return;
+#pragma unroll
+    for (int k = 0; k < kMaskCells; ++k) sm_rows[warp][k][lane] = 0u;
+
+    // ---- lane = (cell, edge): edge e runs from vertex e - 1 to vertex e of the clockwise quad
+    //      (r,c) (r,c+1) (r+1,c+1) (r+1,c)   (type.py:107-116)
+    const int k8 = lane >> 2, e = lane & 3;
+    const int cell = cell0 + k8;
+    const bool valid = cell < C;
+    int vx = 0, vy = 0;
+    if (valid) {
+        const int r = floor_div_small(cell, ccols, __fdividef(1.0f, (float)ccols));
+        const int c = cell - r * ccols;
+        const int idx = (r + (e >> 1)) * pg.cols + c + ((e == 1 || e == 2) ? 1 : 0);
+        const int2 v = *reinterpret_cast<const int2*>(lattice_i + ((size_t)page * p_max + idx) * 2);
+        vx = v.x;
+        vy = v.y;
     }
-    __shared__ EdgeConst edges[4][4];  // [warp][edge]
-    EdgeConst* E = edges[threadIdx.x >> 5];
-    if (lane < 4) {
-        // edge e runs from vertex e-1 to vertex e (selects, not indexed registers)
-        const int ex1 = lane == 0 ? px[0] : lane == 1 ? px[1] : lane == 2 ? px[2] : px[3];
-        const int ey1 = lane == 0 ? py[0] : lane == 1 ? py[1] : lane == 2 ? py[2] : py[3];
-        const int ex0 = lane == 0 ? px[3] : lane == 1 ? px[0] : lane == 2 ? px[1] : px[2];
-        const int ey0 = lane == 0 ? py[3] : lane == 1 ? py[0] : lane == 2 ? py[1] : py[2];
-        edge_setup(ex0, ey0, ex1, ey1, E[lane]);
+    const int prev = (lane & ~3) | ((e + 3) & 3);
+    const int ux = __shfl_sync(0xffffffffu, vx, prev), uy = __shfl_sync(0xffffffffu, vy, prev);
+    int x0 = min(vx, __shfl_xor_sync(0xffffffffu, vx, 1)), x1 = max(vx, __shfl_xor_sync(0xffffffffu, vx, 1));
+    int y0 = min(vy, __shfl_xor_sync(0xffffffffu, vy, 1)), y1 = max(vy, __shfl_xor_sync(0xffffffffu, vy, 1));
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, 2));
+    y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, 2));
+    int nrows = y1 - y0 + 1;
+    const bool big = (x1 - x0 + 32) / 32 != 1 || nrows > VKB_CELL_MASK_WORDS;
+    if (valid && big && e == 0) {
+        // too large for the fixed budget: the remap kernel rasterises this cell on the fly
+        cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
+    }
+    if (!valid || big) nrows = 0;
+    if (nrows) {
+        EdgeScan es;
+        edge_scan_setup(ux, uy, vx, vy, es);
+        sm_scan[warp][k8][e] = es;
+        if (e == 0) sm_org[warp][k8] = make_int2(x0, y0);
+    }
+    __syncwarp();  // the zeroed rows are visible before the first OR
+    if (nrows) {
+        uint32_t* rows = sm_rows[warp][k8];
+        edge_walk(ux, uy, vx, vy, [&](int x, int y) { atomicOr(rows + (y - y0), 1u << (x - x0)); });
     }
     __syncwarp();
-    if (lane < nrows) {
-        uint32_t word = 0;
-        if (edges_fast_ok(E)) word = quad_row_mask_fast(E, y0 + lane, x0);  // branch-free form
-        else poly_row_mask_edges<4>(E, y0 + lane, x0, &word, 1);
-        out[lane] = word;
+
+    // ---- lane = (cell, row): the rows of the eight cells back to back -------------------------
+    int first[kMaskCells + 1];  // first[k]: rows before cell k
+    first[0] = 0;
+#pragma unroll
+    for (int k = 0; k < kMaskCells; ++k) first[k + 1] = first[k] + __shfl_sync(0xffffffffu, nrows, 4 * k);
+    const int total = first[kMaskCells];
+    for (int p = lane; p < total; p += 32) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < kMaskCells; ++i) k += p >= first[i] ? 1 : 0;
+        int before = 0;
+#pragma unroll
+        for (int i = 1; i < kMaskCells; ++i) before = (i <= k) ? first[i] : before;
+        const int row = p - before;
+        const int2 org = sm_org[warp][k];
+        const uint32_t word = sm_rows[warp][k][row] | quad_fill_row(sm_scan[warp][k], org.y + row, org.x);
+        cell_masks[((size_t)page * c_max + cell0 + k) * VKB_CELL_MASK_WORDS + row] = word;
     }
 }
 
@@ -1009,8 +1050,8 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     int rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
-    grid_masks_kernel<<<dim3((c_max + 3) / 4, n_pages), 128, 0, st>>>(pages, p_max, c_max, lattice_i,
-                                                                     cell_box, cell_masks);
+    grid_masks_kernel<<<dim3((c_max + kMaskWarps * kMaskCells - 1) / (kMaskWarps * kMaskCells), n_pages),
+                        32 * kMaskWarps, 0, st>>>(pages, p_max, c_max, lattice_i, cell_box, cell_masks);
     rc = check_launch("grid_masks_kernel");
     if (rc) return rc;
     grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);

@@ -11,6 +11,7 @@
 // All of it is byte-stream work bound by HBM bandwidth: one read and one write per pixel,
 // no tensor cores.
 #include <curand_kernel.h>
+#include <mutex>
 #include "common.cuh"
 #include "vkb_color.cuh"
 
@@ -20,15 +21,26 @@ namespace vkb {
 // (coalesced staging into shared memory per block), not in the constant bank, whose reads
 // serialise when the lanes of a warp use different addresses.
 __device__ HsvTables c_hsv;
-static bool g_hsv_ready = false;
 
+// `c_hsv` exists once per device: every device gets its own upload, under a lock (first calls
+// from several threads / several devices of one process).
 static int ensure_tables(cudaStream_t st) {
-    if (!g_hsv_ready) {
-        static HsvTables host;
-        fill_hsv_tables(host);
+    static std::mutex mutex;
+    static bool ready[64] = {};
+    static HsvTables host;
+    static bool host_ready = false;
+    int dev = 0;
+    VKB_CUDA(cudaGetDevice(&dev));
+    VKB_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(mutex);
+    if (!ready[dev]) {
+        if (!host_ready) {
+            fill_hsv_tables(host);
+            host_ready = true;
+        }
         VKB_CUDA(cudaMemcpyToSymbolAsync(c_hsv, &host, sizeof(host), 0, cudaMemcpyHostToDevice, st));
         VKB_CUDA(cudaStreamSynchronize(st));
-        g_hsv_ready = true;
+        ready[dev] = true;
     }
     return VKB_OK;
 }
@@ -54,16 +66,21 @@ __device__ __forceinline__ void blend_pixel(const vkb_blend_item& it, int ry, in
             const float v = it.value_arr ? reinterpret_cast<const float*>(it.value_arr)[vi + c]
                                          : it.value_const[c];
             if (do_blend) *d = blend_f32(*d, v, a);
-            else if (it.keep_mode == 1) { if (*d < v) *d = v; }
-            else if (it.keep_mode == 2) { if (*d > v) *d = v; }
+            else if ((it.keep_mode & 3) == 1) { if (*d < v) *d = v; }
+            else if ((it.keep_mode & 3) == 2) { if (*d > v) *d = v; }
             else *d = v;
         } else {
             uint8_t* d = reinterpret_cast<uint8_t*>(it.dst) + di + c;
+            // a constant value is cast to the destination dtype first (prep_value's np.full_like,
+            // element/opt.py:96-115) unless the caller blends with its own float constant
+            // (VKB_BLEND_FLOAT_CONST: fog on a GRAYSCALE page, effect.py:194-197)
             const int v = it.value_arr ? (int)reinterpret_cast<const uint8_t*>(it.value_arr)[vi + c]
                                        : (int)it.value_const[c];
-            if (do_blend) *d = (uint8_t)(int)blend_f32((float)*d, (float)v, a);  // truncation
-            else if (it.keep_mode == 1) { if (*d < v) *d = (uint8_t)v; }
-            else if (it.keep_mode == 2) { if (*d > v) *d = (uint8_t)v; }
+            const float vf = (!it.value_arr && (it.keep_mode & VKB_BLEND_FLOAT_CONST))
+                                 ? it.value_const[c] : (float)v;
+            if (do_blend) *d = (uint8_t)(int)blend_f32((float)*d, vf, a);  // truncation
+            else if ((it.keep_mode & 3) == 1) { if (*d < v) *d = (uint8_t)v; }
+            else if ((it.keep_mode & 3) == 2) { if (*d > v) *d = (uint8_t)v; }
             else *d = (uint8_t)v;
         }
     }

@@ -662,24 +662,37 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
         {
             const uint32_t* __restrict__ page_masks = cell_masks + page_cell0 * VKB_CELL_MASK_WORDS;
             const int row_y = ty0 + lane;
-            for (int s = 1; s <= count; ++s) {
-                const int4 b = *reinterpret_cast<const int4*>(&S[s].x0);  // same for all lanes
-                const int r = row_y - b.y;
-                uint32_t win = 0u;
-                if ((unsigned)r <= (unsigned)b.z) {
-                    if (b.w >= 0) {
-                        const uint32_t wd = __ldg(page_masks + (b.w * VKB_CELL_MASK_WORDS + r));
-                        const int rel = tx0 - b.x;  // |rel| < 32: the bbox overlaps the tile
-                        win = rel >= 0 ? (wd >> rel) : (wd << (-rel));
-                    } else {
-                        win = cell_row_window_slow(lattice_i + (size_t)page * p_max * 2, cols,
-                                                   b.w & 0x7FFFFFFF, row_y, tx0);
+            // four candidates per step: their coverage words are requested together, so a tile
+            // pays ~count / 4 exposed memory latencies instead of count (1.99 -> 1.89 ms)
+            for (int s0 = 1; s0 <= count; s0 += 4) {
+                uint32_t wd[4];
+                int rel[4], cellf[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    wd[u] = 0u;
+                    rel[u] = 0;
+                    cellf[u] = 0;
+                    if (s0 + u <= count) {
+                        const int4 b = *reinterpret_cast<const int4*>(&S[s0 + u].x0);  // same for all lanes
+                        const int r = row_y - b.y;
+                        rel[u] = tx0 - b.x;  // |rel| < 32: the bbox overlaps the tile
+                        cellf[u] = b.w;
+                        if ((unsigned)r <= (unsigned)b.z && b.w >= 0)
+                            wd[u] = __ldg(page_masks + (b.w * VKB_CELL_MASK_WORDS + r));
                     }
                 }
-                q0 = (q0 & ~win) | (win & (0u - ((uint32_t)s & 1u)));
-                q1 = (q1 & ~win) | (win & (0u - (((uint32_t)s >> 1) & 1u)));
-                q2 = (q2 & ~win) | (win & (0u - (((uint32_t)s >> 2) & 1u)));
-                q3 = (q3 & ~win) | (win & (0u - (((uint32_t)s >> 3) & 1u)));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t s = (uint32_t)(s0 + u);  // past `count`: wd = 0, nothing changes
+                    uint32_t win = rel[u] >= 0 ? (wd[u] >> rel[u]) : (wd[u] << (-rel[u]));
+                    if (cellf[u] < 0)  // over-budget cell (rare, uniform): rasterised here
+                        win = cell_row_window_slow(lattice_i + (size_t)page * p_max * 2, cols,
+                                                   cellf[u] & 0x7FFFFFFF, row_y, tx0);
+                    q0 = (q0 & ~win) | (win & (0u - (s & 1u)));
+                    q1 = (q1 & ~win) | (win & (0u - ((s >> 1) & 1u)));
+                    q2 = (q2 & ~win) | (win & (0u - ((s >> 2) & 1u)));
+                    q3 = (q3 & ~win) | (win & (0u - ((s >> 3) & 1u)));
+                }
             }
         }
         // ---- lane = dst column from here on -------------------------------------------------
@@ -901,6 +914,11 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     } while (0)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);
     switch (key) {
+#ifdef VKB_REMAP_ONLY_RGB  // kernel experiments (tools/build_variants.py): one instantiation
+        case 3 * 4 + 0: VKB_LAUNCH_REMAP(3, false, false); break;
+        default: VKB_REQUIRE(false, "experiment build: RGB image only");
+    }
+#else
         case 0 * 4 + 1: VKB_LAUNCH_REMAP(0, false, true); break;
         case 0 * 4 + 2: VKB_LAUNCH_REMAP(0, true, false); break;
         case 0 * 4 + 3: VKB_LAUNCH_REMAP(0, true, true); break;
@@ -918,6 +936,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
         case 4 * 4 + 3: VKB_LAUNCH_REMAP(4, true, true); break;
         default: VKB_REQUIRE(false, "unsupported container combination");
     }
+#endif
 #undef VKB_LAUNCH_REMAP
 #undef VKB_LAUNCH_REMAP_1
     if (side) {

@@ -687,6 +687,81 @@ VKB_HD uint32_t quad_row_mask_fast(const EdgeConst* E, int y, int bx0) {
     return word;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same coverage split the other way round (grid_masks_kernel, second generation): the outline
+// is WALKED once per edge (cv::LineIterator step by step, a few integer operations per pixel)
+// instead of being solved per row in closed form, and only the scan fill is evaluated per row.
+//
+//   edge_walk    visits the pixels of the 8-connected line from the LEFT end point: after j major
+//                steps the minor coordinate is floor((2*minor*j + major - 1) / (2*major)), kept
+//                incrementally as (quotient, remainder) -- one add, one compare per step;
+//   EdgeScan     the 16.16 scan edge of cv::FillEdgeCollection for rows [ya, yb);
+//   quad_fill_row  the spans of one row from the four scan edges (crossings sorted by a
+//                5-exchange network, pairs filled from ceil(xl) to floor(xr)).
+// coverage(row) = outline bits | quad_fill_row: same bits as poly_row_mask<4> (checked on the host
+// against cv.fillPoly's model, tests/test_hostsim.py).
+// ---------------------------------------------------------------------------------------
+template <typename Plot>
+VKB_HD void edge_walk(int x0, int y0, int x1, int y1, Plot plot) {
+    if (x0 > x1) {  // left to right
+        int t = x0; x0 = x1; x1 = t;
+        t = y0; y0 = y1; y1 = t;
+    }
+    const int dx = x1 - x0;
+    const int dys = y1 - y0;
+    const int sy = dys >= 0 ? 1 : -1;
+    const int dy = dys >= 0 ? dys : -dys;
+    const bool steep = dy > dx;
+    const int major = steep ? dy : dx, minor_ext = steep ? dx : dy;
+    int rem = major - 1, minor = 0;  // (2*minor_ext*j + major - 1) = 2*major*minor + rem
+    for (int j = 0; j <= major; ++j) {
+        const int x = steep ? x0 + minor : x0 + j;
+        const int y = steep ? y0 + sy * j : y0 + sy * minor;
+        plot(x, y);
+        rem += 2 * minor_ext;
+        if (rem >= 2 * major) {  // minor_ext <= major: at most one step
+            rem -= 2 * major;
+            ++minor;
+        }
+    }
+}
+
+struct alignas(16) EdgeScan {
+    int ya, yb;  // active rows [ya, yb); ya == yb: horizontal, takes no part in the fill
+    int base;    // x << 16 at row ya
+    int dxf;     // trunc(((x1 - x0) << 16) / (y1 - y0)) per row
+};
+
+// |x1 - x0| < 16384 and 0 <= x < 32768 (every lattice cell the masks kernel accepts)
+VKB_HD void edge_scan_setup(int x0, int y0, int x1, int y1, EdgeScan& e) {
+    e.ya = y0 < y1 ? y0 : y1;
+    e.yb = y0 < y1 ? y1 : y0;
+    e.base = (y0 < y1 ? x0 : x1) * 65536;
+    e.dxf = y0 != y1 ? ((x1 - x0) * 65536) / (y1 - y0) : 0;
+}
+
+VKB_HD uint32_t quad_fill_row(const EdgeScan* e, int y, int bx0) {
+    int c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        c[i] = (y >= e[i].ya && y < e[i].yb) ? e[i].base + e[i].dxf * (y - e[i].ya) : kNoCross;
+#define VKB_CSWAP(a, b) { const int lo_ = a < b ? a : b, hi_ = a < b ? b : a; a = lo_; b = hi_; }
+    VKB_CSWAP(c[0], c[1]) VKB_CSWAP(c[2], c[3]) VKB_CSWAP(c[0], c[2]) VKB_CSWAP(c[1], c[3]) VKB_CSWAP(c[1], c[2])
+#undef VKB_CSWAP
+    uint32_t word = 0;
+    {
+        const int xl = (int)(((long long)c[0] + 65535) >> 16), xr = c[1] >> 16;
+        const uint32_t m = bits_lo_hi(xl - bx0, xr - bx0);
+        word |= (c[1] != kNoCross && xl <= xr) ? m : 0u;
+    }
+    {
+        const int xl = (int)(((long long)c[2] + 65535) >> 16), xr = c[3] >> 16;
+        const uint32_t m = bits_lo_hi(xl - bx0, xr - bx0);
+        word |= (c[3] != kNoCross && xl <= xr) ? m : 0u;
+    }
+    return word;
+}
+
 // Direct form (no per-edge state): used where a single row of a polygon is needed once
 // (over-budget cells in the remap's slow path); same results as poly_row_mask_edges.
 template <int N>

@@ -18,9 +18,15 @@ def _as_device(arr, dtype=None):
         if dtype is not None and arr.dtype != dtype:
             arr = arr.astype(dtype)
         return dv.to_device(arr)
+    if not arr.is_cuda:
+        raise _native.NativeError('blend operands must be NumPy arrays or CUDA tensors '
+                                  '(a CPU tensor was given)')
     if dtype is not None:
         arr = arr.to(dv._torch_dtype(dtype))
-    return arr
+    # the kernel addresses operands as dense rows (pitch = width): sliced / strided views are
+    # copied.  (Views produced by Box.extract_* are copies already -- unlike the reference's NumPy
+    # views, filling an extracted element does not write through to its parent.)
+    return arr.contiguous()
 
 
 def fill_region(

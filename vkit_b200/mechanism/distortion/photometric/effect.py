@@ -170,7 +170,7 @@ def fog_image(config: FogConfig, state, image: Image, rng: Optional[RandomGenera
     item.mask = None
     item.alpha_arr = alpha.data_ptr()
     item.alpha_pitch = image.width
-    item.keep_mode = 0
+    item.keep_mode = nv.BLEND_FLOAT_CONST  # the GRAYSCALE fog value is fractional
     item.alpha = 1.0
     nv.check(nv.lib().vkb_blend_fill(ctypes.byref(item), dv.stream_ptr()), 'vkb_blend_fill')
     image = attrs.evolve(image, mat=dst)
