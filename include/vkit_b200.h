@@ -168,8 +168,9 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
  *               float32 tile-centred inverse map of every candidate, ascending cell order)
  *   tile_headers: n_pages x t_max x VKB_TILE_HEADER_BYTES bytes (the flat work list of the
  *               remap: page, tile origin, record count, first record) followed by
- *               (n_pages x t_max + 1) int32 (the list of tiles that take the remap's second
- *               launch: more than 15 candidates or the exact slow path); opaque */
+ *               (n_pages x t_max + 2) int32: the list of tiles that take the remap's second
+ *               launch (count + entries: more than 15 candidates or the exact slow path) and, last,
+ *               the work counter vkb_grid_remap resets and its small-tile kernel draws from; opaque */
 #define VKB_TILE_SLOT_BYTES 64
 #define VKB_TILE_HEADER_BYTES 32
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
@@ -181,8 +182,9 @@ int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, i
 /* Phase 2b: the fused remap -- owner cell per dst pixel (last cell in row-major order whose
  * cv.fillPoly coverage contains it), per-pixel inverse homography in double, float32 map
  * value, 1/32 px quantisation, bilinear gather of Image + Mask + ScoreMap in one pass.
- * A persistent kernel: every block walks a contiguous share of the flat tile list and
- * prefetches the next tile's records while it works on the current one.
+ * Persistent kernels: every warp draws 32 x 32 dst tiles from the flat tile list (a work counter
+ * in the tile_headers workspace) and prefetches the next tile's records while it works on the
+ * current one.  Concurrent calls need separate workspaces.
  * The kernel is specialised at compile time on the containers present, so every page of one
  * call carries the same set: image_channels (0 = no image), has_mask, has_score.
  * planes[i].dst_h / dst_w must be the result shape in meta[i]; src planes below 32768 px. */
@@ -191,7 +193,7 @@ int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t
                    const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
                    const uint32_t* cell_masks, const int32_t* tile_count,
                    const int32_t* tile_off, const int32_t* tile_base, const void* tile_slots,
-                   const void* tile_headers, int32_t image_channels, int32_t has_mask,
+                   void* tile_headers, int32_t image_channels, int32_t has_mask,
                    int32_t has_score, void* stream);
 
 /* Points through the forward homography of the source cell that contains the ROUNDED point

@@ -452,6 +452,10 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 constexpr int kTilesWarps = 8;
 constexpr int kTilesHalf = 16;                  // records per half: [0] = the zero map, 1..15 candidates
 constexpr int kTilesSlots = 2 * kTilesHalf;
+#ifndef VKB_TILES_CHUNK
+#define VKB_TILES_CHUNK 1
+#endif
+constexpr int kTilesChunk = VKB_TILES_CHUNK;  // consecutive tiles per draw from the work counter
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t v, int s) { return __funnelshift_r(v, v, s); }
 
@@ -516,20 +520,30 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
     int c_max, int p_max, const double* __restrict__ hinv, const uint32_t* __restrict__ cell_masks,
     const int32_t* __restrict__ tile_base, const RemapTile* __restrict__ headers,
-    const TileSlot* __restrict__ slots, const int32_t* __restrict__ lattice_i) {
+    const TileSlot* __restrict__ slots, const int32_t* __restrict__ lattice_i,
+    int32_t* __restrict__ work_counter) {
     constexpr int CC = C > 0 ? C : 1;
     __shared__ __align__(16) TileSlot sm_all[kTilesWarps][kTilesSlots];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     TileSlot* __restrict__ sm = sm_all[warp];
 
-    // contiguous share of the flat tile list per block, round robin over its warps
+    // Dynamic work distribution: a warp draws chunks of kTilesChunk consecutive tiles from a
+    // global counter (tiles without owners cost a fraction of a full tile, so static shares end
+    // unevenly: 13 % of a 64-page launch was tail).  Two chunks are always in hand, so the next
+    // tile and the one after it are known for the header / record prefetch.
     const int total = tile_base[n_pages];
-    const int per = (total + gridDim.x - 1) / gridDim.x;
-    const int w_begin = blockIdx.x * per;
-    const int n_block = min(total, w_begin + per) - w_begin;
-    const int n_tiles = n_block > warp ? (n_block - warp + kTilesWarps - 1) / kTilesWarps : 0;
-    if (n_tiles <= 0) return;
+    auto grab = [&]() {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(work_counter, kTilesChunk);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    int chunk0 = grab(), chunk1 = grab(), pos = 0;
+    if (chunk0 >= total) return;
+    auto tile_at = [&](int ahead) {  // ahead <= kTilesChunk
+        const int p = pos + ahead;
+        return p < kTilesChunk ? chunk0 + p : chunk1 + (p - kTilesChunk);
+    };
 
     // record 0 of both halves: the map of uncovered pixels, (0, 0) for every pixel, always exact
     if (lane < 2) {
@@ -540,9 +554,9 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
     }
     __syncwarp();
 
-    auto load_header = [&](int k) {
+    auto load_header = [&](int index) {
         RemapTile t;
-        const int index = w_begin + warp + kTilesWarps * min(k, n_tiles - 1);
+        index = min(index, total - 1);
         const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
         t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
@@ -557,9 +571,18 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
         cp_async_commit();
     };
 
-    RemapTile h0 = load_header(0), h1 = load_header(1);
+    RemapTile h0 = load_header(tile_at(0)), h1 = load_header(tile_at(1));
     int cur_base = 0;
     bool cur_staged = false;
+    auto advance = [&]() {  // next tile of this warp's sequence
+        if (++pos == kTilesChunk) {
+            pos = 0;
+            chunk0 = chunk1;
+            chunk1 = grab();
+        }
+        h0 = h1;
+        h1 = load_header(tile_at(1));
+    };
 
     // per-page state, reloaded when the page changes
     int ctx_page = -1;
@@ -574,18 +597,17 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
     uint32_t fill_mask = 0;
     float fill_score = 0.f;
 
-    for (int k = 0; k < n_tiles; ++k) {
+    while (tile_at(0) < total) {
         const RemapTile cur = h0;
         if (!mine(cur)) {  // the large-tile launch's tile (never staged ahead)
-            h0 = h1;
-            h1 = load_header(k + 2);
+            advance();
             continue;
         }
         if (!cur_staged) {
             cur_base = 0;
             stage(cur, 0);
         }
-        const bool ahead = k + 1 < n_tiles && mine(h1);
+        const bool ahead = tile_at(1) < total && mine(h1);
         const int next_base = cur_base ? 0 : kTilesHalf;
         if (ahead) {
             stage(h1, next_base);
@@ -814,8 +836,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
         __syncwarp();  // every lane is done with this tile's records before their half is reused
         cur_staged = ahead;
         cur_base = next_base;
-        h0 = h1;
-        h1 = load_header(k + 2);
+        advance();
     }
 }
 
@@ -863,7 +884,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               const int32_t* lattice_i, const double* hinv, const int32_t* cell_box,
                               const uint32_t* cell_masks, const int32_t* tile_count,
                               const int32_t* tile_off, const int32_t* tile_base,
-                              const void* tile_slots, const void* tile_headers,
+                              const void* tile_slots, void* tile_headers,
                               int32_t image_channels, int32_t has_mask, int32_t has_score,
                               void* stream) {
     VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
@@ -872,6 +893,9 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     const int32_t* large = reinterpret_cast<const int32_t*>(
         reinterpret_cast<const char*>(tile_headers) + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
+    // the work counter of the small-tile kernel lives behind the list of large tiles
+    int32_t* work_counter = const_cast<int32_t*>(large) + (size_t)n_pages * t_max + 1;
+    VKB_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), (cudaStream_t)stream));
     VKB_REQUIRE(image_channels == 0 || image_channels == 1 || image_channels == 3
                     || image_channels == 4, "image_channels must be 0, 1, 3 or 4");
     VKB_REQUIRE(image_channels || has_mask || has_score, "nothing to remap");
@@ -909,7 +933,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
             grid_remap_tiles_kernel<CH, M, S><<<tiles_grid, 32 * kTilesWarps, 0, st>>>(         \
                 planes, pages, n_pages, c_max, p_max, hinv, cell_masks, tile_base,              \
                 reinterpret_cast<const RemapTile*>(tile_headers),                               \
-                reinterpret_cast<const TileSlot*>(tile_slots), lattice_i);                      \
+                reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, work_counter);        \
         }                                                                                       \
     } while (0)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);

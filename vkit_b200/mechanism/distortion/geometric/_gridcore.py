@@ -106,7 +106,7 @@ class GridBatch:
         self.tile_base = dv.empty((self.n + 1,), np.int32)
         self.tile_slots = dv.empty((self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
         self.tile_headers = dv.empty(
-            (self.n * self.t_max * nv.TILE_HEADER_BYTES + (self.n * self.t_max + 1) * 4,), np.uint8)
+            (self.n * self.t_max * nv.TILE_HEADER_BYTES + (self.n * self.t_max + 2) * 4,), np.uint8)
         nv.check(self.lib.vkb_grid_build(
             dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max, self.s_cap,
             dv.ptr(self.lattice_i), dv.ptr(self.meta_dev), dv.ptr(self.hinv), dv.ptr(self.hfwd),
