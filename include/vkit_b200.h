@@ -151,6 +151,21 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
                       const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
                       vkb_grid_meta* meta_mirror, void* stream);
 
+/* Phase 1c (batches, optional): the output layout on the device, so that no host round trip
+ * sits between the projection and the remap.  `planes` (device, n_pages records) arrives with
+ * the source fields filled and dst_image / dst_mask / dst_score = the BASE of the respective
+ * output arena (NULL when absent); the call adds every page's offset (exclusive scan of
+ * dst_h * dst_w over the pages, in pixels) and writes dst_h / dst_w from `meta`.
+ *   layout:        n_pages + 2 int64: pixel offset per page, total pixels, status
+ *   layout_mirror: NULL or the same in mapped pinned host memory (read after a synchronise)
+ *   status:        0 ok; bit 0: the batch needs more than cap_pixels; bit 1: some page has more
+ *                  than t_max 32 x 32 tiles.  On a non-zero status every result shape in `meta`
+ *                  and `planes` is zeroed (vkb_grid_build / vkb_grid_remap then do nothing; the
+ *                  true shapes stay in vkb_grid_finalize's meta_mirror) and the caller runs the
+ *                  batch again with exact capacities. */
+int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes, int64_t cap_pixels,
+                    int32_t t_max, int64_t* layout, int64_t* layout_mirror, void* stream);
+
 /* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage masks; per dst
  * tile the candidate cells and their records for the remap kernel.
  * c_max >= (rows-1)*(cols-1); t_max >= 32x32 tiles per page; s_cap = candidate records kept

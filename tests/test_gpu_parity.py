@@ -1172,3 +1172,58 @@ def test_mask_to_resized_mask(vk):
                                         cv_resize_interpolation=inter,
                                         binarization_threshold=thr).mat
                 assert np.array_equal(got, (model() > thr).astype(np.uint8)), (h, w, inter, thr)
+
+
+# ---------------------------------------------------------------------------------------------
+# Optimistic batches: output layout on the device, no host round trip inside run()
+# ---------------------------------------------------------------------------------------------
+def _camera_batch(n, shape=(200, 264)):
+    import torch
+    rng = np.random.default_rng(77)
+    names, configs = [], []
+    from vkit_b200.mechanism.distortion_policy.geometric import camera as cam_policy
+    factories = [cam_policy.camera_plane_only_policy_factory, cam_policy.camera_cubic_curve_policy_factory,
+                 cam_policy.camera_plane_line_fold_policy_factory,
+                 cam_policy.camera_plane_line_curve_policy_factory]
+    for i in range(n):
+        policy = factories[i % 4].create()
+        gen = policy.config_generator_cls(policy.config_for_config_generator, int(rng.integers(1, 11)))
+        names.append(factories[i % 4].name)
+        configs.append(gen(shape, rng))
+    images = torch.from_numpy(rng.integers(0, 256, (n,) + shape + (3,), dtype=np.uint8)).cuda()
+    masks = torch.from_numpy((rng.random((n,) + shape) > 0.5).astype(np.uint8)).cuda()
+    scores = torch.from_numpy(rng.random((n,) + shape).astype(np.float32)).cuda()
+    return names, configs, shape, images, masks, scores
+
+
+def test_optimistic_batch_equals_exact(vk):
+    from vkit_b200.batch import GeometricBatch
+    names, configs, shape, images, masks, scores = _camera_batch(12)
+    exact = GeometricBatch(names, configs, shape).run(images, masks, scores)
+    opt = GeometricBatch(names, configs, shape).run(images, masks, scores, optimistic=True)
+    assert opt.shapes == exact.shapes
+    assert np.array_equal(opt.pixel_offsets, exact.pixel_offsets)
+    for i in range(len(names)):
+        assert np.array_equal(opt.image(i).cpu().numpy(), exact.image(i).cpu().numpy()), i
+        assert np.array_equal(opt.mask(i).cpu().numpy(), exact.mask(i).cpu().numpy()), i
+        assert np.array_equal(opt.score_map(i).cpu().numpy(), exact.score_map(i).cpu().numpy()), i
+    assert opt.packed(opt.image_arena, 3).numel() == exact.image_arena.numel()
+
+
+@pytest.mark.parametrize('which', ['pixels', 'tiles'])
+def test_optimistic_batch_overflow_falls_back(vk, which, monkeypatch):
+    """Bounds that are too small are detected on the device (nothing is written out of bounds)
+    and the batch is run again with exact sizes."""
+    from vkit_b200 import batch as vb
+    names, configs, shape, images, masks, scores = _camera_batch(6)
+    exact = vb.GeometricBatch(names, configs, shape).run(images)
+    if which == 'pixels':
+        monkeypatch.setattr(vb, 'PIXELS_BOUND_FACTOR', 0.5)
+    else:
+        monkeypatch.setattr(vb, 'DIMS_BOUND_FACTOR', 0.5)
+    engine = vb.GeometricBatch(names, configs, shape)
+    opt = engine.run(images, optimistic=True)
+    assert opt.shapes == exact.shapes
+    assert not engine.plan.deferred  # the exact re-run replaced the optimistic plan
+    for i in range(len(names)):
+        assert np.array_equal(opt.image(i).cpu().numpy(), exact.image(i).cpu().numpy()), i

@@ -20,9 +20,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 names, configs = bench.sample_page_configs(0, n, 256)
 pages = torch.randint(0, 256, (n, 1024, 1024, 3), dtype=torch.uint8, device='cuda')
 eng = GeometricBatch(names, configs, (1024, 1024))
+OPT = os.environ.get('PROBE_EXACT') is None
 for _ in range(3):
-    eng.plan_batch()
-    out = eng.run(pages, replan=False)
+    out = eng.run(pages, optimistic=OPT)
 torch.cuda.synchronize()
 
 marks = []
@@ -62,8 +62,7 @@ rows = {}
 for rep in range(reps):
     marks.clear()
     torch.cuda.synchronize()
-    eng.plan_batch()
-    out = eng.run(pages, replan=False)
+    out = eng.run(pages, optimistic=OPT)
     mark('end')
     torch.cuda.synchronize()
     for (l0, e0, t0), (l1, e1, t1) in zip(marks, marks[1:]):

@@ -46,15 +46,42 @@ def grid_page_record(op_name: str, config, shape: Tuple[int, int], out=None, han
 
 
 class BatchOutput:
-    """Ragged outputs of one batch: flat arenas + per-page offsets."""
+    """Ragged outputs of one batch: flat arenas + per-page offsets.  For an optimistic batch the
+    shapes and offsets are read from the device when they are first asked for (`resolve`)."""
 
-    def __init__(self, shapes, channels, image_arena, mask_arena, score_arena, pixel_offsets):
-        self.shapes = shapes
+    def __init__(self, shapes, channels, image_arena, mask_arena, score_arena, pixel_offsets,
+                 resolve=None):
+        self._shapes = shapes
         self.channels = channels
         self.image_arena = image_arena
         self.mask_arena = mask_arena
         self.score_arena = score_arena
-        self.pixel_offsets = pixel_offsets
+        self._pixel_offsets = pixel_offsets
+        self._resolve = resolve
+
+    def _ready(self):
+        if self._resolve is not None:
+            resolve, self._resolve = self._resolve, None
+            resolve(self)
+
+    @property
+    def shapes(self):
+        self._ready()
+        return self._shapes
+
+    @property
+    def pixel_offsets(self):
+        self._ready()
+        return self._pixel_offsets
+
+    @property
+    def total_pixels(self):
+        return int(self.pixel_offsets[-1])
+
+    def packed(self, arena, per_pixel: int = 1):
+        """The used part of an arena (optimistic batches allocate by a bound): what the next
+        batched stage takes as its flat input."""
+        return arena[:self.total_pixels * per_pixel]
 
     def _view(self, arena, i, per_pixel):
         h, w = self.shapes[i]
@@ -70,6 +97,13 @@ class BatchOutput:
 
     def score_map(self, i):
         return self._view(self.score_arena, i, 1)
+
+
+# Optimistic batches: result canvases are assumed to stay within these factors of the source
+# (side lengths / total pixels); a batch that does not is detected on the device and run again
+# with exact sizes.  The reference's policies reach ~1.3 x per side at the strongest levels.
+DIMS_BOUND_FACTOR = 1.5
+PIXELS_BOUND_FACTOR = 1.5
 
 
 class GeometricBatch:
@@ -100,60 +134,118 @@ class GeometricBatch:
         self.keepalive = keepalive
         self.plan: Optional[GridBatch] = None
 
-    def plan_batch(self):
-        """Phase 1 + 2a: lattices, result shapes (one D2H), cell homographies, masks, bins."""
-        self.plan = GridBatch(self.pages, keepalive=self.keepalive)
-        self.plan.build()
+    def plan_batch(self, optimistic: bool = False):
+        """Phase 1 + 2a: lattices, result shapes, cell homographies, masks, bins.  The exact form
+        waits for the result shapes (one stream synchronise); the optimistic form sizes the
+        workspaces from DIMS_BOUND_FACTOR and never waits (see GridBatch)."""
+        bound = None
+        if optimistic:
+            bound = (int(max(s[0] for s in self.shapes) * DIMS_BOUND_FACTOR) + 1,
+                     int(max(s[1] for s in self.shapes) * DIMS_BOUND_FACTOR) + 1)
+        self.plan = GridBatch(self.pages, keepalive=self.keepalive, dims_bound=bound)
+        if not optimistic:
+            self.plan.build()
         return self.plan
 
     def run(self, images=None, masks=None, score_maps=None, replan: bool = True,
-            launch_events=None, channels: Optional[int] = None) -> BatchOutput:
+            launch_events=None, channels: Optional[int] = None,
+            optimistic: bool = False) -> BatchOutput:
         """images: (B, H, W, C) uint8, masks: (B, H, W) uint8, score_maps: (B, H, W) float32 --
         CUDA tensors (any subset); or, for ragged pages, flat arenas that hold the pages back to
         back in page order (`channels` then names the image's channel count).  Returns ragged
         outputs in fresh arenas.
         `launch_events`: optional list; a (start, end) pair of CUDA events recorded immediately
-        around the fused remap launch is appended (kernel time without host work)."""
-        if replan or self.plan is None:
+        around the fused remap launch is appended (kernel time without host work).
+        `optimistic`: no host round trip inside the call -- arenas sized by PIXELS_BOUND_FACTOR,
+        output layout computed on the device, shapes read when the BatchOutput is first asked
+        for them (a batch that does not fit the bounds is then run again the exact way)."""
+        if optimistic:
+            return self._run_optimistic(images, masks, score_maps, launch_events, channels)
+        if replan or self.plan is None or self.plan.deferred:
             self.plan_batch()
         plan = self.plan
         shapes = [plan.result_shape(i) for i in range(self.n)]
         pixels = np.asarray([h * w for h, w in shapes], dtype=np.int64)
         offsets = np.concatenate([[0], np.cumsum(pixels)])
         total = int(offsets[-1])
-        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
-        src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
-        planes = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
-        planes['src_h'] = [s[0] for s in self.shapes]
-        planes['src_w'] = [s[1] for s in self.shapes]
+        planes, channels = self._source_planes(images, masks, score_maps, channels)
         planes['dst_h'] = [s[0] for s in shapes]
         planes['dst_w'] = [s[1] for s in shapes]
         image_arena = mask_arena = score_arena = None
+        if images is not None:
+            image_arena = dv.empty((total * channels,), np.uint8)
+            planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
+                np.uint64)
+        if masks is not None:
+            mask_arena = dv.empty((total,), np.uint8)
+            planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
+        if score_maps is not None:
+            score_arena = dv.empty((total,), np.float32)
+            planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
+        plan.remap(planes, launch_events=launch_events)
+        return BatchOutput(shapes, channels, image_arena, mask_arena, score_arena, offsets)
+
+    def _source_planes(self, images, masks, score_maps, channels):
+        """Plane records with the source side filled in (+ validation of the inputs)."""
+        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
+        src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
+        n_src = int(src_pixels.sum())
+        planes = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
+        planes['src_h'] = [s[0] for s in self.shapes]
+        planes['src_w'] = [s[1] for s in self.shapes]
         if images is not None:
             if channels is None:
                 channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
                                                         else None)
             if channels is None:
                 raise ValueError('flat image arenas need `channels`')
-            if int(images.numel()) != int(src_pixels.sum()) * channels:
+            if int(images.numel()) != n_src * channels:
                 raise ValueError('images do not hold the pages of this batch')
-            image_arena = dv.empty((total * channels,), np.uint8)
             planes['src_image'] = np.uint64(images.data_ptr()) + src_offsets * np.uint64(channels)
-            planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
-                np.uint64)
             planes['image_channels'] = channels
         else:
             channels = 0
         if masks is not None:
-            mask_arena = dv.empty((total,), np.uint8)
+            if int(masks.numel()) != n_src:
+                raise ValueError('masks do not hold the pages of this batch')
             planes['src_mask'] = np.uint64(masks.data_ptr()) + src_offsets
-            planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
         if score_maps is not None:
-            score_arena = dv.empty((total,), np.float32)
+            if int(score_maps.numel()) != n_src:
+                raise ValueError('score maps do not hold the pages of this batch')
             planes['src_score'] = np.uint64(score_maps.data_ptr()) + src_offsets * np.uint64(4)
-            planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
-        plan.remap(planes, launch_events=launch_events)
-        return BatchOutput(shapes, channels, image_arena, mask_arena, score_arena, offsets)
+        return planes, channels
+
+    def _run_optimistic(self, images, masks, score_maps, launch_events, channels):
+        plan = self.plan_batch(optimistic=True)
+        planes, channels = self._source_planes(images, masks, score_maps, channels)
+        cap = int(sum(h * w for h, w in self.shapes) * PIXELS_BOUND_FACTOR) + 1
+        image_arena = mask_arena = score_arena = None
+        if images is not None:
+            image_arena = dv.empty((cap * channels,), np.uint8)
+            planes['dst_image'] = image_arena.data_ptr()
+        if masks is not None:
+            mask_arena = dv.empty((cap,), np.uint8)
+            planes['dst_mask'] = mask_arena.data_ptr()
+        if score_maps is not None:
+            score_arena = dv.empty((cap,), np.float32)
+            planes['dst_score'] = score_arena.data_ptr()
+        planes_dev = plan.layout(planes, cap)
+        plan.build()
+        plan.remap(planes, launch_events=launch_events, planes_dev=planes_dev)
+        inputs = (images, masks, score_maps)
+
+        def resolve(out: BatchOutput):
+            if plan.finish():
+                out._shapes = [plan.result_shape(i) for i in range(self.n)]
+                out._pixel_offsets = plan.pixel_offsets
+                return
+            # the bounds were too small for this batch: once more, exactly sized
+            exact = self.run(*inputs, channels=channels or None)
+            out._shapes, out._pixel_offsets = exact._shapes, exact._pixel_offsets
+            out.image_arena, out.mask_arena, out.score_arena = (exact.image_arena, exact.mask_arena,
+                                                                exact.score_arena)
+
+        return BatchOutput(None, channels, image_arena, mask_arena, score_arena, None, resolve)
 
     def algorithmic_bytes(self, channels: int = 3, with_mask: bool = False,
                           with_score: bool = False) -> int:
@@ -365,13 +457,14 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
             out = sub.run(staging[a:b], replan=False)
             done = t.cuda.Event()
             done.record()
-        n_bytes = int(out.image_arena.numel())
+        n_bytes = out.total_pixels * channels
         start = offsets[-1]
         if start + n_bytes > host_out.numel():
             raise ValueError('host_out is too small for the distorted pages')
         with t.cuda.stream(state['d2h']):
             state['d2h'].wait_event(done)
-            host_out[start:start + n_bytes].copy_(out.image_arena, non_blocking=True)
+            host_out[start:start + n_bytes].copy_(out.packed(out.image_arena, channels),
+                                                  non_blocking=True)
         for k, (h, w) in enumerate(out.shapes):
             shapes.append((h, w))
             offsets.append(start + int(out.pixel_offsets[k + 1]) * channels)

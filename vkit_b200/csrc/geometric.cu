@@ -291,6 +291,91 @@ __global__ void __launch_bounds__(1024) grid_finalize_kernel(
 }
 
 // ============================================================================================
+// Output layout on the device: exclusive scan of the pages' result pixels, destination pointers
+// and result shapes written into the plane records -- so a batch needs no host round trip between
+// the lattice projection and the remap (the host reads shapes and offsets when the batch is done).
+// Capacities are the caller's bet; when a page needs more tiles than the workspaces hold or the
+// batch more pixels than the arenas, every result shape is zeroed (all later kernels then have
+// nothing to do) and the status word tells the host to run again with exact sizes.
+// ============================================================================================
+__global__ void __launch_bounds__(1024) grid_layout_kernel(
+    vkb_grid_meta* __restrict__ meta, int n_pages, vkb_planes* __restrict__ planes,
+    long long cap_pixels, int t_max, long long* __restrict__ layout,
+    long long* __restrict__ layout_mirror) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry;
+    __shared__ int bad;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        bad = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_pages; base += 1024) {
+        const int page = base + threadIdx.x;
+        long long v = 0;
+        if (page < n_pages) {
+            v = (long long)meta[page].dst_h * meta[page].dst_w;
+            if (page_tiles(meta[page]) > t_max) atomicOr(&bad, 2);
+        }
+        long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long ws = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long o = __shfl_up_sync(0xffffffffu, ws, d);
+                if (lane >= d) ws += o;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const long long ex = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + inc - v;
+        const long long total = warp_sums[31];
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        if (page < n_pages) {
+            layout[page] = ex;
+            if (layout_mirror) layout_mirror[page] = ex;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && carry > cap_pixels) bad |= 1;
+    __syncthreads();
+    const int status = bad;
+    if (threadIdx.x == 0) {
+        layout[n_pages] = carry;
+        layout[n_pages + 1] = status;
+        if (layout_mirror) {
+            layout_mirror[n_pages] = carry;
+            layout_mirror[n_pages + 1] = status;
+        }
+    }
+    for (int page = threadIdx.x; page < n_pages; page += 1024) {
+        vkb_planes& pl = planes[page];
+        if (status) {  // nothing downstream may touch the (too small) buffers
+            meta[page].dst_h = 0;
+            meta[page].dst_w = 0;
+            pl.dst_h = 0;
+            pl.dst_w = 0;
+            continue;
+        }
+        const long long off = layout[page];
+        pl.dst_h = meta[page].dst_h;
+        pl.dst_w = meta[page].dst_w;
+        if (pl.dst_image) pl.dst_image += off * pl.image_channels;
+        if (pl.dst_mask) pl.dst_mask += off;
+        if (pl.dst_score) pl.dst_score += off;
+    }
+}
+
+// ============================================================================================
 // Cells: inverse (and optionally forward) homography, bbox, tile binning.  Thread per cell.
 // ============================================================================================
 __global__ void __launch_bounds__(128) grid_cells_kernel(
@@ -1024,6 +1109,17 @@ extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, in
     grid_finalize_kernel<<<n_pages, 1024, 0, (cudaStream_t)stream>>>(pages, p_max, lattice_f,
                                                                     lattice_i, meta, meta_mirror);
     return check_launch("grid_finalize_kernel");
+}
+
+extern "C" int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes,
+                               int64_t cap_pixels, int32_t t_max, int64_t* layout,
+                               int64_t* layout_mirror, void* stream) {
+    VKB_REQUIRE(meta && planes && layout && n_pages > 0, "bad arguments");
+    VKB_REQUIRE(cap_pixels > 0 && t_max > 0, "empty capacities");
+    grid_layout_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+        meta, n_pages, planes, (long long)cap_pixels, t_max, reinterpret_cast<long long*>(layout),
+        reinterpret_cast<long long*>(layout_mirror));
+    return check_launch("grid_layout_kernel");
 }
 
 extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,

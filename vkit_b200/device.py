@@ -93,10 +93,15 @@ def _torch_dtype(dtype):
 
 
 def upload_structs(records: np.ndarray):
-    """Structured NumPy array (parameter blocks) -> uint8 device tensor."""
+    """Structured NumPy array (parameter blocks) -> uint8 device tensor.  Staged through pinned
+    memory and copied asynchronously: a pageable source makes cudaMemcpyAsync wait for the stream,
+    which would put a host round trip into every batch.  (The caching host allocator keeps the
+    pinned block alive until the copy has run.)"""
     t = require_cuda()
     raw = np.frombuffer(records.tobytes(), dtype=np.uint8)
-    return t.from_numpy(raw.copy()).to(device())
+    host = t.empty((raw.size,), dtype=t.uint8, pin_memory=True)
+    host.numpy()[:] = raw
+    return host.to(device(), non_blocking=True)
 
 
 def ptr(tensor):

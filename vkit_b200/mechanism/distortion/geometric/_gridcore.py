@@ -40,9 +40,16 @@ def new_grid_page(height: int, width: int, grid_size: int, out=None):
 
 
 class GridBatch:
+    """`dims_bound` = None: the constructor waits for the result shapes (one stream synchronise)
+    and sizes every workspace exactly -- what the per-page `Distortion.distort` needs.
+
+    `dims_bound` = (max_dst_h, max_dst_w): the OPTIMISTIC form for batches.  Workspaces are sized
+    from the bound, the output layout is computed on the device (`vkb_grid_layout`) and nothing
+    waits for the GPU until `finish()`; a batch that does not fit reports it there (`fits`) and is
+    run again with exact sizes by the caller."""
 
     def __init__(self, pages: np.ndarray, keepalive: Sequence = (),
-                 given_lattice: Optional[np.ndarray] = None):
+                 given_lattice: Optional[np.ndarray] = None, dims_bound=None):
         dv.require_cuda()
         self.lib = nv.lib()
         self.pages = np.ascontiguousarray(pages, dtype=nv.GRID_PAGE_DTYPE).reshape(-1)
@@ -76,15 +83,42 @@ class GridBatch:
                                             dv.ptr(self.meta_dev),
                                             ctypes.c_void_p(meta_host.data_ptr()), stream),
                  'vkb_grid_finalize')
-        t.cuda.current_stream().synchronize()
-        self.meta = np.frombuffer(meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
-        self.max_dst_h = int(self.meta['dst_h'].max())
-        self.max_dst_w = int(self.meta['dst_w'].max())
+        self.meta_host = meta_host
+        self.stream = t.cuda.current_stream()
+        self.layout_host = None
+        self._meta = None
+        self.fits = True
+        self.deferred = dims_bound is not None
+        if self.deferred:
+            self.max_dst_h, self.max_dst_w = int(dims_bound[0]), int(dims_bound[1])
+        else:
+            t.cuda.current_stream().synchronize()
+            self._meta = np.frombuffer(meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
+            self.max_dst_h = int(self._meta['dst_h'].max())
+            self.max_dst_w = int(self._meta['dst_w'].max())
         self.tiles_x = (self.max_dst_w + nv.TILE - 1) // nv.TILE
         self.tiles_y = (self.max_dst_h + nv.TILE - 1) // nv.TILE
         self.t_max = self.tiles_x * self.tiles_y
         self.hinv = None
         self.hfwd = None
+
+    @property
+    def meta(self):
+        if self._meta is None:
+            self.finish()
+        return self._meta
+
+    def finish(self):
+        """Optimistic plans: wait for the stream, read the result shapes (and the layout status)
+        from the pinned mirrors.  Returns `fits`."""
+        if self._meta is None:
+            self.stream.synchronize()
+            self._meta = np.frombuffer(self.meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
+            if self.layout_host is not None:
+                layout = self.layout_host.numpy()
+                self.fits = int(layout[self.n + 1]) == 0
+                self.pixel_offsets = np.array(layout[:self.n + 1], dtype=np.int64)
+        return self.fits
 
     def result_shape(self, i: int = 0):
         return int(self.meta['dst_h'][i]), int(self.meta['dst_w'][i])
@@ -114,10 +148,26 @@ class GridBatch:
             dv.ptr(self.tile_cells), dv.ptr(self.tile_off), dv.ptr(self.tile_base),
             dv.ptr(self.tile_slots), dv.ptr(self.tile_headers), dv.stream_ptr()), 'vkb_grid_build')
 
-    def remap(self, planes: np.ndarray, launch_events=None):
+    def layout(self, planes: np.ndarray, cap_pixels: int):
+        """Optimistic plans: `planes` carries the source fields and the arena BASES in its dst
+        pointers; offsets and result shapes are filled in on the device.  Returns the device copy
+        of the records for `remap(planes_dev=...)`."""
+        t = dv.torch()
+        planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
+        planes_dev = dv.upload_structs(planes)
+        self.layout_dev = dv.empty((self.n + 2,), np.int64)
+        self.layout_host = t.empty((self.n + 2,), dtype=t.int64, pin_memory=True)
+        nv.check(self.lib.vkb_grid_layout(
+            dv.ptr(self.meta_dev), self.n, dv.ptr(planes_dev), int(cap_pixels), self.t_max,
+            dv.ptr(self.layout_dev), ctypes.c_void_p(self.layout_host.data_ptr()), dv.stream_ptr()),
+            'vkb_grid_layout')
+        return planes_dev
+
+    def remap(self, planes: np.ndarray, launch_events=None, planes_dev=None):
         """planes: structured array (PLANES_DTYPE), one record per page, device pointers.
         `launch_events`: optional list that receives a (start, end) CUDA event pair recorded
-        immediately around the kernel launch."""
+        immediately around the kernel launch.  `planes_dev`: the records already on the device
+        (from `layout`); `planes` then only names the containers."""
         self.build()
         planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
         channels = int(planes['image_channels'][0])
@@ -129,9 +179,11 @@ class GridBatch:
             raise ValueError('all pages of one remap call must carry the same containers')
         if int(planes['src_h'].max()) >= 32768 or int(planes['src_w'].max()) >= 32768:
             raise ValueError('source planes larger than 32767 px are not supported (cv.remap limit)')
-        planes_dev = dv.upload_structs(planes)
-        if (planes['dst_h'] != self.meta['dst_h']).any() or (planes['dst_w'] != self.meta['dst_w']).any():
-            raise ValueError('planes.dst_h / dst_w must be the result shapes of the plan')
+        if planes_dev is None:
+            planes_dev = dv.upload_structs(planes)
+            if ((planes['dst_h'] != self.meta['dst_h']).any()
+                    or (planes['dst_w'] != self.meta['dst_w']).any()):
+                raise ValueError('planes.dst_h / dst_w must be the result shapes of the plan')
         if launch_events is not None:
             t = dv.torch()
             ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
