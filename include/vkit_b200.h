@@ -151,6 +151,12 @@ int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max
                       const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
                       vkb_grid_meta* meta_mirror, void* stream);
 
+/* Parameter blocks (vkb_grid_page / vkb_planes / ... arrays) from mapped pinned HOST memory to
+ * device memory through a kernel instead of the copy engine, where a small copy would queue
+ * behind the caller's bulk page copies.  nbytes: a multiple of 16; src_host: pinned host memory
+ * (device accessible under unified addressing); stream ordered like every other call. */
+int vkb_stage_params(void* dst, const void* src_host, int64_t nbytes, void* stream);
+
 /* Phase 1c (batches, optional): the output layout on the device, so that no host round trip
  * sits between the projection and the remap.  `planes` (device, n_pages records) arrives with
  * the source fields filled and dst_image / dst_mask / dst_score = the BASE of the respective

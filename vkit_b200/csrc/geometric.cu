@@ -1111,6 +1111,25 @@ extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, in
     return check_launch("grid_finalize_kernel");
 }
 
+// Parameter blocks from (mapped, pinned) host memory into device memory by a KERNEL: a
+// cudaMemcpyAsync of a few kilobytes would wait on the copy engine behind whatever bulk page
+// copies the caller has queued there (the end-to-end pipeline keeps ~100 MB in flight).
+__global__ void __launch_bounds__(256) stage_params_kernel(uint4* __restrict__ dst,
+                                                           const uint4* __restrict__ src, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+extern "C" int vkb_stage_params(void* dst, const void* src_host, int64_t nbytes, void* stream) {
+    VKB_REQUIRE(dst && src_host && nbytes > 0 && nbytes % 16 == 0, "bad arguments (16-byte units)");
+    VKB_REQUIRE(nbytes < (1ll << 30), "parameter blocks only");
+    const int n16 = (int)(nbytes / 16);
+    const int blocks = n16 < 256 * 64 ? (n16 + 255) / 256 : 64;
+    stage_params_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src_host), n16);
+    return check_launch("stage_params_kernel");
+}
+
 extern "C" int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes,
                                int64_t cap_pixels, int32_t t_max, int64_t* layout,
                                int64_t* layout_mirror, void* stream) {

@@ -92,16 +92,64 @@ def _torch_dtype(dtype):
     return table[dtype]
 
 
+# Pinned staging blocks, reused: cudaHostAlloc costs ~1 ms and torch's caching host allocator hands
+# a block back only after the copy that used it has run, which under a deep queue of work means a
+# fresh cudaHostAlloc per upload.  Blocks are kept per (device, size class) with the event of their
+# last copy; a block is reused when that event has completed.
+_PINNED = {}
+
+
+def _pinned_block(nbytes: int):
+    t = torch()
+    size = 4096
+    while size < nbytes:
+        size *= 2
+    pool = _PINNED.setdefault((t.cuda.current_device(), size), [])
+    for entry in pool:
+        if entry[1] is None or entry[1].query():
+            return entry
+    entry = [t.empty((size,), dtype=t.uint8, pin_memory=True), None]
+    pool.append(entry)
+    return entry
+
+
 def upload_structs(records: np.ndarray):
     """Structured NumPy array (parameter blocks) -> uint8 device tensor.  Staged through pinned
-    memory and copied asynchronously: a pageable source makes cudaMemcpyAsync wait for the stream,
-    which would put a host round trip into every batch.  (The caching host allocator keeps the
-    pinned block alive until the copy has run.)"""
+    memory and copied asynchronously BY A KERNEL: a pageable source makes cudaMemcpyAsync wait for
+    the stream (a host round trip in every batch), and any cudaMemcpyAsync queues on the copy
+    engine behind the bulk page copies of the end-to-end pipeline."""
     t = require_cuda()
     raw = np.frombuffer(records.tobytes(), dtype=np.uint8)
-    host = t.empty((raw.size,), dtype=t.uint8, pin_memory=True)
-    host.numpy()[:] = raw
-    return host.to(device(), non_blocking=True)
+    entry = _pinned_block(raw.size)
+    entry[0].numpy()[:raw.size] = raw
+    padded = (raw.size + 15) // 16 * 16
+    out = t.empty((padded,), dtype=t.uint8, device=device())
+    # a kernel copies the block (vkb_stage_params): the copy engine may be busy with page copies
+    _native.check(_native.lib().vkb_stage_params(ptr(out), ctypes.c_void_p(entry[0].data_ptr()),
+                                                 padded, stream_ptr()), 'vkb_stage_params')
+    out = out[:raw.size]
+    event = t.cuda.Event()
+    event.record()
+    entry[1] = event
+    return out
+
+
+def pinned_mirror(nbytes: int):
+    """A pinned host block a kernel mirrors small results into (result shapes, layouts); the
+    caller hands it back with `release_mirror` once it has read it."""
+    t = require_cuda()
+    size = 4096
+    while size < nbytes:
+        size *= 2
+    pool = _PINNED.setdefault((t.cuda.current_device(), 'mirror', size), [])
+    if pool:
+        return pool.pop()
+    return t.empty((size,), dtype=t.uint8, pin_memory=True)
+
+
+def release_mirror(block):
+    t = torch()
+    _PINNED.setdefault((t.cuda.current_device(), 'mirror', int(block.numel())), []).append(block)
 
 
 def ptr(tensor):

@@ -76,8 +76,8 @@ class GridBatch:
         # into pinned host memory (device accessible under UVA), so one stream synchronise is
         # enough -- a D2H copy would wait behind bulk copies queued on the copy engine
         t = dv.torch()
-        meta_host = t.empty((self.n * nv.GRID_META_DTYPE.itemsize,), dtype=t.uint8,
-                            pin_memory=True)
+        self._meta_bytes = self.n * nv.GRID_META_DTYPE.itemsize
+        meta_host = dv.pinned_mirror(self._meta_bytes)
         nv.check(self.lib.vkb_grid_finalize(dv.ptr(self.pages_dev), self.n, self.p_max,
                                             dv.ptr(self.lattice_f), dv.ptr(self.lattice_i),
                                             dv.ptr(self.meta_dev),
@@ -93,7 +93,7 @@ class GridBatch:
             self.max_dst_h, self.max_dst_w = int(dims_bound[0]), int(dims_bound[1])
         else:
             t.cuda.current_stream().synchronize()
-            self._meta = np.frombuffer(meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
+            self._read_meta()
             self.max_dst_h = int(self._meta['dst_h'].max())
             self.max_dst_w = int(self._meta['dst_w'].max())
         self.tiles_x = (self.max_dst_w + nv.TILE - 1) // nv.TILE
@@ -113,12 +113,21 @@ class GridBatch:
         from the pinned mirrors.  Returns `fits`."""
         if self._meta is None:
             self.stream.synchronize()
-            self._meta = np.frombuffer(self.meta_host.numpy().tobytes(), dtype=nv.GRID_META_DTYPE)
+            self._read_meta()
             if self.layout_host is not None:
-                layout = self.layout_host.numpy()
+                layout = self.layout_host.numpy()[:(self.n + 2) * 8].view(np.int64)
                 self.fits = int(layout[self.n + 1]) == 0
                 self.pixel_offsets = np.array(layout[:self.n + 1], dtype=np.int64)
+                dv.release_mirror(self.layout_host)
+                self.layout_host = None
         return self.fits
+
+    def _read_meta(self):
+        """(after a synchronise) result shapes out of the pinned mirror; the block goes back."""
+        raw = self.meta_host.numpy()[:self._meta_bytes].tobytes()
+        self._meta = np.frombuffer(raw, dtype=nv.GRID_META_DTYPE)
+        dv.release_mirror(self.meta_host)
+        self.meta_host = None
 
     def result_shape(self, i: int = 0):
         return int(self.meta['dst_h'][i]), int(self.meta['dst_w'][i])
@@ -156,7 +165,7 @@ class GridBatch:
         planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
         planes_dev = dv.upload_structs(planes)
         self.layout_dev = dv.empty((self.n + 2,), np.int64)
-        self.layout_host = t.empty((self.n + 2,), dtype=t.int64, pin_memory=True)
+        self.layout_host = dv.pinned_mirror((self.n + 2) * 8)
         nv.check(self.lib.vkb_grid_layout(
             dv.ptr(self.meta_dev), self.n, dv.ptr(planes_dev), int(cap_pixels), self.t_max,
             dv.ptr(self.layout_dev), ctypes.c_void_p(self.layout_host.data_ptr()), dv.stream_ptr()),
