@@ -420,6 +420,17 @@ int vkb_noise_field(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t 
 /* Streaks (photometric/streak.py:44-337).  line: analytic periodic masks; rect: the masks are
  * rasterised from the host-computed bar lists; both blend `color` with `alpha`, vertical mask
  * first, horizontal second (crossings get alpha twice, streak.py:96-98). In place on `image`. */
+/* ellipse_streak (vkit/mechanism/distortion/photometric/streak.py:282-337): cv.ellipse(mask,
+ * center, axes, 0, 0, 360, 1, thickness) for a list of ellipses, ORed into a uint8 h x w mask
+ * (caller zeroes it).  ellipses_host: n x 4 int32 (center x, center y, half axis x, half axis y)
+ * on the HOST: the vertex lists of OpenCV's EllipseEx / ellipse2Poly are prepared there, the
+ * pixels (Bresenham thin lines; for thickness > 1 convex quads with Line2 outlines + round caps,
+ * all bit exact vs cv2 4.13) are drawn on the device, one thread per polyline segment.
+ * seg_workspace: device scratch of at least 74 * 40 bytes per ellipse. */
+int vkb_draw_ellipses(uint8_t* mask, int32_t h, int32_t w, const int32_t* ellipses_host,
+                      int32_t n_ellipses, int32_t thickness, void* seg_workspace,
+                      int64_t workspace_bytes, void* stream);
+
 typedef struct vkb_rect { int32_t up, down, left, right; } vkb_rect;
 int vkb_streak_line(uint8_t* image, int32_t h, int32_t w, int32_t channels, int32_t thickness,
                     int32_t gap, int32_t dash_thickness, int32_t dash_gap, int32_t enable_vert,

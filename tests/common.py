@@ -186,3 +186,35 @@ def plain_config(obj):
 
 def product_config_for(op, config):
     return product_config({'op': op, 'config': config})
+
+
+# ---------------------------------------------------------------------------------------------
+# Round-2 fixtures (tests/golden/make_golden_r2.py): ellipse_streak, fog on GRAYSCALE, jpeg_quality
+# ---------------------------------------------------------------------------------------------
+_R2 = None
+
+
+def r2_golden():
+    global _R2
+    if _R2 is None:
+        with open(os.path.join(GOLDEN_DIR, 'r2_cases.json')) as fin:
+            meta = json.load(fin)
+        _R2 = (meta['cases'], np.load(os.path.join(GOLDEN_DIR, 'r2_arrays.npz')))
+    return _R2
+
+
+def r2_cases(kind):
+    return [c for c in r2_golden()[0] if c['kind'] == kind]
+
+
+def r2_array(case, key):
+    arrays = r2_golden()[1]
+    name = f"{case['id']}/{key}"
+    return arrays[name] if name in arrays.files else None
+
+
+def rgb_to_gray(rgb):
+    """cv.cvtColor(RGB2GRAY) on uint8 (Image.to_target_mode_image, image.py:771-814), through the
+    oracle's pinned model."""
+    from oracle import cv2_model
+    return cv2_model.cvt_rgb2gray(rgb)

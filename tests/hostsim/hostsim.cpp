@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../vkit_b200/csrc/vkb_math.cuh"
 #include "../../vkit_b200/csrc/vkb_lattice.cuh"
+#include "../../vkit_b200/csrc/vkb_draw_host.h"
 
 using namespace vkb;
 
@@ -243,4 +244,15 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             const long long e = (long long)(fmax(ex, ey) * 1e9);
             if (e > stats[3]) stats[3] = e;
         }
+}
+
+
+// cv.ellipse(img, center, axes, 0, 0, 360, 1, thickness) through the product's drawing code
+// (vkb_draw_host.h vertices + vkb_draw.cuh primitives), one segment after the other
+extern "C" void hs_ellipse(int h, int w, int cx, int cy, int ax, int ay, int thickness, uint8_t* out) {
+    std::vector<DrawSegment> segs;
+    ellipse_segments(cx, cy, ax, ay, segs);
+    auto plot = [&](int x, int y) { out[(size_t)y * w + x] = 1; };
+    auto hline = [&](int y, int xa, int xb) { for (int x = xa; x <= xb; ++x) out[(size_t)y * w + x] = 1; };
+    for (const DrawSegment& sg : segs) draw_thick_segment(w, h, sg.p0, sg.p1, thickness, sg.flags, plot, hline);
 }

@@ -1227,3 +1227,33 @@ def test_optimistic_batch_overflow_falls_back(vk, which, monkeypatch):
     assert not engine.plan.deferred  # the exact re-run replaced the optimistic plan
     for i in range(len(names)):
         assert np.array_equal(opt.image(i).cpu().numpy(), exact.image(i).cpu().numpy()), i
+
+
+# ---------------------------------------------------------------------------------------------
+# Round-2 fixtures: ellipse_streak, fog on a GRAYSCALE page
+# ---------------------------------------------------------------------------------------------
+from common import r2_cases  # noqa: E402
+
+
+@pytest.mark.parametrize('case', r2_cases('ellipse_streak'), ids=lambda c: f"{c['id']}-{c['shape'][0]}")
+def test_ellipse_streak_vs_golden(vk, case):
+    """cv.ellipse outlines (thin Bresenham polylines; thick: convex quads + round caps) drawn on the
+    device, one blend: sha256-equal to the live reference."""
+    element, distortion = vk
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    r = distortion.ellipse_streak.distort(product_config_for('ellipse_streak', case['config']),
+                                          image=element.Image(mat=image))
+    if sha(r.image.mat) != case['sha']['image']:
+        from oracle import vkit_port as port
+        ref = port.ellipse_streak(image, **case['config'])
+        raise AssertionError(_diff_report(r.image.mat, ref))
+
+
+@pytest.mark.parametrize('case', r2_cases('fog_gray'), ids=lambda c: c['id'])
+def test_fog_grayscale_vs_golden(vk, case):
+    element, distortion = vk
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    gray = element.Image(mat=image).to_target_mode_image(element.ImageMode.GRAYSCALE)
+    r = distortion.fog.distort(product_config_for('fog', case['config']), image=gray,
+                               rng=np.random.default_rng(case['rng_seed']))
+    assert sha(r.image.mat) == case['sha']['image']

@@ -21,6 +21,7 @@ def hs(hostsim):
     hostsim.hs_grid_remap.argtypes = [vp, vp, vp, vp, vp]
     hostsim.hs_fast_path_stats.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
     hostsim.hs_fill_poly4.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    hostsim.hs_ellipse.argtypes = [ctypes.c_int] * 7 + [vp]
     hostsim.hs_homography.argtypes = [vp, vp, vp]
     assert hostsim.hs_sizeof_grid_page() == ctypes.sizeof(nv.GridPage)
     assert hostsim.hs_sizeof_warp_page() == ctypes.sizeof(nv.WarpPage)
@@ -199,3 +200,28 @@ def test_homography_closed_form(hs):
         # the SVD solve (what cv2 runs) to ~1e-6
         np.testing.assert_allclose(a[:2] / a[2], src.T, rtol=0, atol=1e-9)
         np.testing.assert_allclose(b[:2] / b[2], src.T, rtol=0, atol=1e-4)
+
+
+def test_ellipse_drawing_vs_oracle(hs):
+    """The product's drawing code (vkb_draw_host.h vertices + vkb_draw.cuh primitives, host build)
+    against the oracle's restatement of cv.ellipse -- and against cv2 itself where importable."""
+    from oracle import cv2_draw as cd
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    rng = np.random.default_rng(5)
+    for it in range(400 if cv2 is None else 1500):
+        h, w = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+        axes = (int(rng.integers(0, 260)), int(rng.integers(0, 260)))
+        t = int(rng.integers(1, 4))
+        got = np.zeros((h, w), np.uint8)
+        hs.hs_ellipse(h, w, w // 2, h // 2, axes[0], axes[1], t, got.ctypes.data)
+        if cv2 is not None:
+            ref = np.zeros((h, w), np.uint8)
+            cv2.ellipse(ref, (w // 2, h // 2), axes, 0, 0, 360, 1, t)
+        else:
+            ref = cd.ellipse(np.zeros((h, w), np.uint8), (w // 2, h // 2), axes, t)
+        assert np.array_equal(got, ref), (h, w, axes, t)
+        if cv2 is not None and it % 10 == 0:
+            assert np.array_equal(cd.ellipse(np.zeros((h, w), np.uint8), (w // 2, h // 2), axes, t), ref)

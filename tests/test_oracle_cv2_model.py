@@ -235,3 +235,36 @@ def test_resize_area_model_vs_cv2(shape):
                                       cv.resize(mat, dsize, interpolation=cv.INTER_AREA)), dsize
     finally:
         cv.ipp.setUseIPP(use_ipp)
+
+
+def test_draw_models_vs_cv2():
+    """oracle/cv2_draw.py (what ellipse_streak's restatement draws with) against the wheel: thin and
+    thick lines with a 16-bit shift, filled circles, convex quads and whole ellipses, clipped by
+    the canvas in every direction."""
+    from oracle import cv2_draw as cd
+    rng = np.random.default_rng(20261017)
+    one = 65536
+    for _ in range(300):
+        h, w = int(rng.integers(5, 80)), int(rng.integers(5, 80))
+        p1 = (int(rng.integers(-20 * one, (w + 20) * one)), int(rng.integers(-20 * one, (h + 20) * one)))
+        p2 = (int(rng.integers(-20 * one, (w + 20) * one)), int(rng.integers(-20 * one, (h + 20) * one)))
+        t = int(rng.integers(1, 5))
+        ref = np.zeros((h, w), np.uint8)
+        cv.line(ref, p1, p2, 1, t, 8, 16)
+        got = np.zeros((h, w), np.uint8)
+        cd.thick_line(got, p1, p2, t, 3)
+        assert np.array_equal(ref, got), ('line', h, w, p1, p2, t)
+        c, r = (int(rng.integers(-5, w + 5)), int(rng.integers(-5, h + 5))), int(rng.integers(0, 12))
+        ref = np.zeros((h, w), np.uint8)
+        cv.circle(ref, c, r, 1, -1)
+        got = np.zeros((h, w), np.uint8)
+        cd.circle_fill(got, c[0], c[1], r)
+        assert np.array_equal(ref, got), ('circle', h, w, c, r)
+    for _ in range(400):
+        h, w = int(rng.integers(8, 300)), int(rng.integers(8, 300))
+        axes = (int(rng.integers(0, 320)), int(rng.integers(0, 320)))
+        t = int(rng.integers(1, 4))
+        ref = np.zeros((h, w), np.uint8)
+        cv.ellipse(ref, (w // 2, h // 2), axes, 0, 0, 360, 1, t)
+        got = cd.ellipse(np.zeros((h, w), np.uint8), (w // 2, h // 2), axes, t)
+        assert np.array_equal(ref, got), ('ellipse', h, w, axes, t)

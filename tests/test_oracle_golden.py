@@ -352,3 +352,34 @@ def test_cubic_oracle(case):
             assert sha(_cubic_oracle(case)) == case['sha']['image']
         finally:
             port.use_cv2(False)
+
+
+# ---------------------------------------------------------------------------------------------
+# Round-2 fixtures: ellipse_streak (cv.ellipse restated in oracle/cv2_draw.py), fog on GRAYSCALE
+# ---------------------------------------------------------------------------------------------
+from common import r2_cases, rgb_to_gray  # noqa: E402
+
+
+@pytest.mark.parametrize('backend', ['numpy', 'cv2'])
+@pytest.mark.parametrize('case', r2_cases('ellipse_streak'), ids=lambda c: c['id'])
+def test_ellipse_streak_oracle(case, backend):
+    if backend == 'cv2' and not _cv2_available():
+        pytest.skip('cv2 not importable')
+    if backend == 'numpy' and case['shape'][0] > 512:
+        pytest.skip('pure-Python drawing of a 1024^2 page: covered by the cv2 backend')
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    port.use_cv2(backend == 'cv2')
+    try:
+        got = port.ellipse_streak(image, **case['config'])
+    finally:
+        port.use_cv2(False)
+    assert sha(got) == case['sha']['image']
+
+
+@pytest.mark.parametrize('case', r2_cases('fog_gray'), ids=lambda c: c['id'])
+def test_fog_grayscale_oracle(case):
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    cfg = case['config']
+    got = port.fog(rgb_to_gray(image), cfg['roughness'], np.random.default_rng(case['rng_seed']),
+                   tuple(cfg['fog_rgb']), cfg['ratio_max'], cfg['ratio_min'])
+    assert sha(got) == case['sha']['image']

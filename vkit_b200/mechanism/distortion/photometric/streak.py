@@ -180,8 +180,39 @@ class EllipseStreakConfig(DistortionConfig):
     alpha: float = 1.0
 
 
-# The reference's ellipse_streak raises inside cv.ellipse under cv2 >= 4.13 (read-only array,
-# streak.py:316), so there is no oracle to pin a kernel against yet.
+def ellipse_streak_image(config: EllipseStreakConfig, state, image: Image,
+                         rng: Optional[RandomGenerator]):
+    # streak.py:292-330.  (Under cv2 >= 4.13 the reference itself raises inside cv.ellipse because
+    # Mask.mat is read-only; the fixtures come from the reference with that array made writable.)
+    aspect_ratio = config.aspect_ratio
+    if aspect_ratio is None:
+        aspect_ratio = image.width / image.height
+    boxes = generate_centered_boxes(image.height, image.width, aspect_ratio,
+                                    config.short_side_min, config.short_side_step)
+    if config.thickness < 1:
+        raise NotImplementedError('ellipse_streak: filled ellipses (thickness < 1) are not provided')
+    image = image.copy()
+    alpha = _check_alpha(config.alpha)
+    if alpha == 0.0 or not boxes:
+        return image
+    height, width = image.height, image.width
+    ellipses = np.asarray([(width // 2, height // 2, box.width // 2, box.height // 2)
+                           for box in boxes], dtype=np.int32)
+    mask = dv.zeros((height, width), np.uint8)
+    workspace = dv.empty((int(ellipses.shape[0]) * 74 * 40,), np.uint8)
+    nv.check(nv.lib().vkb_draw_ellipses(
+        dv.ptr(mask), height, width, ellipses.ctypes.data_as(ctypes.c_void_p),
+        int(ellipses.shape[0]), int(config.thickness), dv.ptr(workspace),
+        int(workspace.numel()), dv.stream_ptr()), 'vkb_draw_ellipses')
+    # mask.fill_image(image, color, alpha): one blend over the drawn pixels
+    no_mask = ctypes.c_void_p(0)
+    nv.check(nv.lib().vkb_streak_masks(
+        dv.ptr(image.dev), height, width, image.num_channels or 1, dv.ptr(mask), no_mask, 0, 0,
+        _color_array(image, config.color), alpha, dv.stream_ptr()), 'vkb_streak_masks')
+    image._after_device_write()
+    return image
+
+
 ellipse_streak = Distortion(config_cls=EllipseStreakConfig,
                             state_cls=DistortionNopState[EllipseStreakConfig],
-                            func_image=_next_row('ellipse_streak'))
+                            func_image=ellipse_streak_image)
