@@ -133,6 +133,15 @@ class GeometricBatch:
             keepalive.append(handles)
         self.keepalive = keepalive
         self.plan: Optional[GridBatch] = None
+        # what successive plans of this engine share (device copy of the parameter blocks,
+        # workspaces): see GridBatch.  One stream at a time per engine.
+        self._shared = {}
+        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
+        self._n_src = int(src_pixels.sum())
+        self._src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
+        self._planes_template = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
+        self._planes_template['src_h'] = [s[0] for s in self.shapes]
+        self._planes_template['src_w'] = [s[1] for s in self.shapes]
 
     def plan_batch(self, optimistic: bool = False):
         """Phase 1 + 2a: lattices, result shapes, cell homographies, masks, bins.  The exact form
@@ -142,7 +151,8 @@ class GeometricBatch:
         if optimistic:
             bound = (int(max(s[0] for s in self.shapes) * DIMS_BOUND_FACTOR) + 1,
                      int(max(s[1] for s in self.shapes) * DIMS_BOUND_FACTOR) + 1)
-        self.plan = GridBatch(self.pages, keepalive=self.keepalive, dims_bound=bound)
+        self.plan = GridBatch(self.pages, keepalive=self.keepalive, dims_bound=bound,
+                              shared=self._shared)
         if not optimistic:
             self.plan.build()
         return self.plan
@@ -187,12 +197,8 @@ class GeometricBatch:
 
     def _source_planes(self, images, masks, score_maps, channels):
         """Plane records with the source side filled in (+ validation of the inputs)."""
-        src_pixels = np.asarray([h * w for h, w in self.shapes], dtype=np.int64)
-        src_offsets = np.concatenate([[0], np.cumsum(src_pixels)])[:-1].astype(np.uint64)
-        n_src = int(src_pixels.sum())
-        planes = np.zeros(self.n, dtype=nv.PLANES_DTYPE)
-        planes['src_h'] = [s[0] for s in self.shapes]
-        planes['src_w'] = [s[1] for s in self.shapes]
+        src_offsets, n_src = self._src_offsets, self._n_src
+        planes = self._planes_template.copy()
         if images is not None:
             if channels is None:
                 channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
@@ -218,7 +224,7 @@ class GeometricBatch:
     def _run_optimistic(self, images, masks, score_maps, launch_events, channels):
         plan = self.plan_batch(optimistic=True)
         planes, channels = self._source_planes(images, masks, score_maps, channels)
-        cap = int(sum(h * w for h, w in self.shapes) * PIXELS_BOUND_FACTOR) + 1
+        cap = int(self._n_src * PIXELS_BOUND_FACTOR) + 1
         image_arena = mask_arena = score_arena = None
         if images is not None:
             image_arena = dv.empty((cap * channels,), np.uint8)

@@ -49,26 +49,41 @@ class GridBatch:
     run again with exact sizes by the caller."""
 
     def __init__(self, pages: np.ndarray, keepalive: Sequence = (),
-                 given_lattice: Optional[np.ndarray] = None, dims_bound=None):
+                 given_lattice: Optional[np.ndarray] = None, dims_bound=None, shared=None):
+        """`shared`: a dict owned by the caller (one per batch engine) in which the plan keeps what
+        does not change between the plans of that engine -- the device copy of the parameter
+        blocks and the workspaces.  Successive plans of one engine then cost launches only; they
+        must run on one stream at a time (stream order protects the reuse), and the workspaces
+        always belong to the LATEST plan."""
         dv.require_cuda()
         self.lib = nv.lib()
         self.pages = np.ascontiguousarray(pages, dtype=nv.GRID_PAGE_DTYPE).reshape(-1)
         self.n = int(self.pages.shape[0])
         self.keepalive = list(keepalive)
-        self.p_max = int((self.pages['rows'] * self.pages['cols']).max())
-        self.c_max = int(((self.pages['rows'] - 1) * (self.pages['cols'] - 1)).max())
-        self.pages_dev = dv.upload_structs(self.pages)
-        self.lattice_f = dv.empty((self.n, self.p_max, 2), np.float64)
-        self.lattice_i = dv.empty((self.n, self.p_max, 2), np.int32)
-        self.meta_dev = dv.empty((self.n * nv.GRID_META_DTYPE.itemsize,), np.uint8)
+        self.shared = shared if shared is not None else {}
+        static = self.shared.get('static')
+        if static is None:
+            projectors = 0
+            for kind in np.unique(self.pages['projector']):
+                projectors |= 1 << int(kind)
+            static = {
+                'p_max': int((self.pages['rows'] * self.pages['cols']).max()),
+                'c_max': int(((self.pages['rows'] - 1) * (self.pages['cols'] - 1)).max()),
+                'projectors': projectors,
+                'pages_dev': dv.upload_structs(self.pages),
+            }
+            self.shared['static'] = static
+        self.p_max, self.c_max = static['p_max'], static['c_max']
+        self.pages_dev = static['pages_dev']
+        projectors = static['projectors']
+        self.lattice_f = self._ws('lattice_f', (self.n, self.p_max, 2), np.float64)
+        self.lattice_i = self._ws('lattice_i', (self.n, self.p_max, 2), np.int32)
+        self.meta_dev = self._ws('meta_dev', (self.n * nv.GRID_META_DTYPE.itemsize,), np.uint8)
         stream = dv.stream_ptr()
         if given_lattice is not None:
             lat = np.zeros((self.n, self.p_max, 2), dtype=np.float64)
             lat[:, :given_lattice.shape[1]] = given_lattice
             self.lattice_f.copy_(dv.to_device(lat))
-        projectors = 0
-        for kind in np.unique(self.pages['projector']):
-            projectors |= 1 << int(kind)
         nv.check(self.lib.vkb_grid_project(dv.ptr(self.pages_dev), self.n, self.p_max,
                                            dv.ptr(self.lattice_f), projectors, stream),
                  'vkb_grid_project')
@@ -101,6 +116,15 @@ class GridBatch:
         self.t_max = self.tiles_x * self.tiles_y
         self.hinv = None
         self.hfwd = None
+
+    def _ws(self, name, shape, dtype):
+        """A workspace tensor: from the engine's shared dict when the shape still fits, else new."""
+        key = ('ws', name)
+        t = self.shared.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = dv.empty(shape, dtype)
+            self.shared[key] = t
+        return t
 
     @property
     def meta(self):
@@ -135,20 +159,21 @@ class GridBatch:
     def build(self, need_forward: bool = False):
         if self.hinv is not None and (self.hfwd is not None or not need_forward):
             return
-        self.hinv = dv.empty((self.n, self.c_max, 9), np.float64)
+        self.hinv = self._ws('hinv', (self.n, self.c_max, 9), np.float64)
         if need_forward:
-            self.hfwd = dv.empty((self.n, self.c_max, 9), np.float64)
-        self.cell_box = dv.empty((self.n, self.c_max, 4), np.int32)
-        self.cell_masks = dv.empty((self.n, self.c_max, nv.CELL_MASK_WORDS), np.uint32)
-        self.tile_count = dv.empty((self.n, self.t_max), np.int32)
-        self.tile_cells = dv.empty((self.n, self.t_max, nv.TILE_CAP), np.uint16)
+            self.hfwd = self._ws('hfwd', (self.n, self.c_max, 9), np.float64)
+        self.cell_box = self._ws('cell_box', (self.n, self.c_max, 4), np.int32)
+        self.cell_masks = self._ws('cell_masks', (self.n, self.c_max, nv.CELL_MASK_WORDS), np.uint32)
+        self.tile_count = self._ws('tile_count', (self.n, self.t_max), np.int32)
+        self.tile_cells = self._ws('tile_cells', (self.n, self.t_max, nv.TILE_CAP), np.uint16)
         # candidate records of the remap kernel: 16 per tile on average is ample (typical 8-10);
         # a page that needs more falls back to the kernel's slow exact path for the excess tiles
         self.s_cap = 16 * self.t_max
-        self.tile_off = dv.empty((self.n, self.t_max), np.int32)
-        self.tile_base = dv.empty((self.n + 1,), np.int32)
-        self.tile_slots = dv.empty((self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
-        self.tile_headers = dv.empty(
+        self.tile_off = self._ws('tile_off', (self.n, self.t_max), np.int32)
+        self.tile_base = self._ws('tile_base', (self.n + 1,), np.int32)
+        self.tile_slots = self._ws('tile_slots', (self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
+        self.tile_headers = self._ws(
+            'tile_headers',
             (self.n * self.t_max * nv.TILE_HEADER_BYTES + (self.n * self.t_max + 2) * 4,), np.uint8)
         nv.check(self.lib.vkb_grid_build(
             dv.ptr(self.pages_dev), self.n, self.p_max, self.c_max, self.t_max, self.s_cap,
@@ -164,7 +189,7 @@ class GridBatch:
         t = dv.torch()
         planes = np.ascontiguousarray(planes, dtype=nv.PLANES_DTYPE).reshape(-1)
         planes_dev = dv.upload_structs(planes)
-        self.layout_dev = dv.empty((self.n + 2,), np.int64)
+        self.layout_dev = self._ws('layout_dev', (self.n + 2,), np.int64)
         self.layout_host = dv.pinned_mirror((self.n + 2) * 8)
         nv.check(self.lib.vkb_grid_layout(
             dv.ptr(self.meta_dev), self.n, dv.ptr(planes_dev), int(cap_pixels), self.t_max,
