@@ -420,6 +420,16 @@ int vkb_noise_field(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t 
 /* Streaks (photometric/streak.py:44-337).  line: analytic periodic masks; rect: the masks are
  * rasterised from the host-computed bar lists; both blend `color` with `alpha`, vertical mask
  * first, horizontal second (crossings get alpha twice, streak.py:96-98). In place on `image`. */
+/* jpeg_quality (vkit/mechanism/distortion/photometric/effect.py:26-55): the pixels of
+ * cv.imdecode(cv.imencode('.jpeg', mat, [IMWRITE_JPEG_QUALITY, quality])) without the (lossless)
+ * entropy coding: libjpeg's RGB -> YCbCr, 4:2:0 downsampling, islow DCT, quantisation with the
+ * quality-scaled Annex K tables, dequantisation, islow IDCT, fancy upsampling, YCbCr -> RGB, all in
+ * libjpeg's integer arithmetic -- bit exact vs cv2 4.13 / libjpeg-turbo.  src / dst: dense h x w x
+ * channels uint8 (channels 3: channel 0 plays blue like in cv2; channels 1: GRAYSCALE);
+ * planes: device workspace, 16-byte aligned, 1.5 bytes per pixel of the page padded to 16 x 16. */
+int vkb_jpeg_round_trip_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                           int32_t quality, uint8_t* planes, int64_t planes_bytes, void* stream);
+
 /* ellipse_streak (vkit/mechanism/distortion/photometric/streak.py:282-337): cv.ellipse(mask,
  * center, axes, 0, 0, 360, 1, thickness) for a list of ellipses, ORed into a uint8 h x w mask
  * (caller zeroes it).  ellipses_host: n x 4 int32 (center x, center y, half axis x, half axis y)

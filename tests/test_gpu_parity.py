@@ -1257,3 +1257,55 @@ def test_fog_grayscale_vs_golden(vk, case):
     r = distortion.fog.distort(product_config_for('fog', case['config']), image=gray,
                                rng=np.random.default_rng(case['rng_seed']))
     assert sha(r.image.mat) == case['sha']['image']
+
+
+@pytest.mark.parametrize('case', r2_cases('jpeg_quality'), ids=lambda c: f"{c['id']}-q{c['config']['quality']}")
+def test_jpeg_quality_vs_golden(vk, case):
+    """The JPEG round trip on the device (libjpeg's integer colour conversion, 4:2:0 sampling,
+    islow DCT / IDCT, quality-scaled tables; no entropy coding): sha256-equal to the reference's
+    cv.imencode + cv.imdecode."""
+    element, distortion = vk
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    if case['smooth']:
+        import cv2
+        image = cv2.GaussianBlur(image, (0, 0), 3.0)
+    r = distortion.jpeg_quality.distort({'quality': case['config']['quality']},
+                                        image=element.Image(mat=image))
+    if sha(r.image.mat) != case['sha']['image']:
+        from oracle import jpeg_model
+        raise AssertionError(_diff_report(r.image.mat, jpeg_model.jpeg_round_trip(image, case['config']['quality'])))
+
+
+def test_jpeg_quality_ragged_and_gray_vs_oracle(vk):
+    """Sides that are not multiples of 16 / 8 / 2, chroma planes of one or two samples, GRAYSCALE
+    pages: device == oracle (the oracle is pinned against cv2)."""
+    element, distortion = vk
+    from oracle import jpeg_model
+    rng = np.random.default_rng(9)
+    for h, w, q in [(1, 1, 50), (3, 2, 10), (7, 4, 90), (16, 5, 35), (17, 31, 1), (33, 47, 100),
+                    (50, 77, 20), (96, 64, 75), (255, 129, 5)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = distortion.jpeg_quality.distort({'quality': q}, image=element.Image(mat=img)).image.mat
+        assert np.array_equal(got, jpeg_model.jpeg_round_trip(img, q)), (h, w, q)
+        gray = element.Image(mat=img).to_target_mode_image(element.ImageMode.GRAYSCALE)
+        got = distortion.jpeg_quality.distort({'quality': q}, image=gray).image.mat
+        assert np.array_equal(got, jpeg_model.jpeg_round_trip(gray.mat, q)), ('gray', h, w, q)
+
+
+def test_default_random_distortion_config_runs(vk):
+    """The pipeline's default RandomDistortion config (page_distortion.py:53-64 disables only
+    defocus_blur / zoom_in_blur) selects every other op, ellipse_streak and jpeg_quality included:
+    no seed may raise."""
+    element, _ = vk
+    from vkit_b200.mechanism.distortion_policy import random_distortion_factory
+    rd = random_distortion_factory.create({'disabled_policy_names': ['defocus_blur', 'zoom_in_blur']})
+    names = set()
+    from vkit_b200.mechanism.distortion_policy.random_distortion import RandomDistortionDebug
+    for seed in range(160):
+        image, mask, _ = make_inputs(3000 + seed, (96, 128))
+        debug = RandomDistortionDebug()
+        r = rd.distort(np.random.default_rng(seed), image=element.Image(mat=image),
+                       mask=element.Mask(mat=mask), debug=debug)
+        assert r.image.mat.dtype == np.uint8
+        names.update(debug.distortion_names)
+    assert {'ellipse_streak', 'jpeg_quality'} <= names, sorted(names)

@@ -268,3 +268,29 @@ def test_draw_models_vs_cv2():
         cv.ellipse(ref, (w // 2, h // 2), axes, 0, 0, 360, 1, t)
         got = cd.ellipse(np.zeros((h, w), np.uint8), (w // 2, h // 2), axes, t)
         assert np.array_equal(ref, got), ('ellipse', h, w, axes, t)
+
+
+def test_jpeg_model_vs_cv2():
+    """oracle/jpeg_model.py against cv.imencode / cv.imdecode: every quality, sides from 1 px up
+    (ragged MCUs, chroma planes of 1 - 2 samples), noise / smooth / structured content, RGB and
+    GRAYSCALE."""
+    from oracle import jpeg_model as jm
+    rng = np.random.default_rng(20261017)
+
+    def round_trip(mat, q):
+        _, buf = cv.imencode('.jpeg', mat, [cv.IMWRITE_JPEG_QUALITY, q])
+        return cv.imdecode(buf, cv.IMREAD_UNCHANGED)
+
+    for it in range(500):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        q = int(rng.integers(0, 101))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if it % 3 == 1:
+            img = cv.GaussianBlur(img, (0, 0), 2.5)
+        if it % 3 == 2:
+            img = (np.indices((h, w)).sum(0)[..., None] * np.array([3, 5, 7]) % 256).astype(np.uint8)
+        assert np.array_equal(round_trip(img, q), jm.jpeg_round_trip(img, q)), ('rgb', h, w, q)
+        gray = np.ascontiguousarray(img[..., 0])
+        assert np.array_equal(round_trip(gray, q), jm.jpeg_round_trip(gray, q)), ('gray', h, w, q)
+    img = cv.GaussianBlur(rng.integers(0, 256, (512, 640, 3), dtype=np.uint8), (0, 0), 4.0)
+    assert np.array_equal(round_trip(img, 12), jm.jpeg_round_trip(img, 12))

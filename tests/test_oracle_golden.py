@@ -383,3 +383,28 @@ def test_fog_grayscale_oracle(case):
     got = port.fog(rgb_to_gray(image), cfg['roughness'], np.random.default_rng(case['rng_seed']),
                    tuple(cfg['fog_rgb']), cfg['ratio_max'], cfg['ratio_min'])
     assert sha(got) == case['sha']['image']
+
+
+@pytest.mark.parametrize('backend', ['numpy', 'cv2'])
+@pytest.mark.parametrize('case', r2_cases('jpeg_quality'), ids=lambda c: c['id'])
+def test_jpeg_quality_oracle(case, backend):
+    """oracle/jpeg_model.py (libjpeg's integer pipeline, no entropy coding) reproduces the
+    reference's cv.imencode / cv.imdecode round trip bit for bit."""
+    if backend == 'cv2' and not _cv2_available():
+        pytest.skip('cv2 not importable')
+    image, _, _ = make_inputs(case['seed'], tuple(case['shape']))
+    if case['smooth']:
+        image = _smooth(image)
+    port.use_cv2(backend == 'cv2')
+    try:
+        got = port.jpeg_quality(image, case['config']['quality'])
+    finally:
+        port.use_cv2(False)
+    assert sha(got) == case['sha']['image']
+
+
+def _smooth(image):
+    """The smooth pages of the jpeg fixtures: cv.GaussianBlur(image, (0, 0), 3.0) of the seeded
+    noise (generator side); needs cv2, like the generator."""
+    cv2 = pytest.importorskip('cv2')
+    return cv2.GaussianBlur(image, (0, 0), 3.0)

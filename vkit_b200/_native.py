@@ -190,6 +190,7 @@ def _declare(lib):
                                     POINTER(c_float), c_float, vp]
     lib.vkb_fill_rects.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.vkb_draw_ellipses.argtypes = [vp, i32, i32, vp, i32, i32, vp, i64, vp]
+    lib.vkb_jpeg_round_trip_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, i64, vp]
     lib.vkb_streak_masks.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, POINTER(c_float),
                                      c_float, vp]
     lib.vkb_threshold_u8.argtypes = [vp, vp, i64, i32, i32, i32, vp]
@@ -212,7 +213,7 @@ EXPORTS = (
     'vkb_grid_layout', 'vkb_stage_params', 'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon',
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
-    'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_streak_masks', 'vkb_photo_chain_batched',
+    'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_jpeg_round_trip_u8', 'vkb_streak_masks', 'vkb_photo_chain_batched',
     'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_resize_mask_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
 )
 

@@ -1,9 +1,10 @@
 """Effect ops (vkit/mechanism/distortion/photometric/effect.py): jpeg_quality, pixelation, fog.
 
+jpeg_quality: the JPEG round trip without entropy coding, libjpeg's integer arithmetic (csrc/jpeg.cu).
 pixelation: cv.resize INTER_LINEAR down + INTER_NEAREST up, both bit exact on the device.
 fog: the diamond-square field is drawn on the host from the caller's NumPy generator (it is the
 random field the reference would draw, a few vector operations per level), the blend runs on the
-device.  jpeg_quality stays a "next" row (libjpeg codec)."""
+device."""
 import ctypes
 from typing import Any, Mapping, Optional, Tuple
 
@@ -16,7 +17,6 @@ from vkit_b200 import device as dv
 from vkit_b200.element import Image, ImageMode
 
 from ..interface import Distortion, DistortionConfig, DistortionNopState
-from .blur import _next_row
 from .opt import to_original_image, to_rgb_image
 
 
@@ -25,9 +25,32 @@ class JpegQualityConfig(DistortionConfig):
     quality: int
 
 
+def jpeg_quality_image(config: JpegQualityConfig, state, image: Image,
+                       rng: Optional[RandomGenerator]):
+    # effect.py:35-48: cv.imencode('.jpeg', mat, quality) + cv.imdecode.  The round trip runs on
+    # the device without the (lossless) entropy coding, in libjpeg's integer arithmetic.
+    mode = image.mode
+    image = to_rgb_image(image, mode)
+    assert 0 <= config.quality <= 100
+    if image.mat_dtype != np.uint8:
+        raise NotImplementedError('jpeg_quality is provided for uint8 images')
+    channels = image.num_channels or 1
+    height, width = image.height, image.width
+    padded = ((height + 15) // 16 * 16) * ((width + 15) // 16 * 16)
+    planes = dv.empty((padded + padded // 2,), np.uint8)
+    shape = (height, width) if image.num_channels == 0 else (height, width, channels)
+    dst = dv.empty(shape, np.uint8)
+    nv.check(nv.lib().vkb_jpeg_round_trip_u8(dv.ptr(image.dev), dv.ptr(dst), height, width, channels,
+                                             int(config.quality), dv.ptr(planes),
+                                             int(planes.numel()), dv.stream_ptr()),
+             'vkb_jpeg_round_trip_u8')
+    image = attrs.evolve(image, mat=dst)
+    return to_original_image(image, mode)
+
+
 jpeg_quality = Distortion(config_cls=JpegQualityConfig,
                           state_cls=DistortionNopState[JpegQualityConfig],
-                          func_image=_next_row('jpeg_quality'))
+                          func_image=jpeg_quality_image)
 
 
 @attrs.define

@@ -16,7 +16,6 @@ from vkit_b200 import device as dv
 from vkit_b200.element import Box, Image
 
 from ..interface import Distortion, DistortionConfig, DistortionNopState
-from .blur import _next_row
 
 
 def _color_array(image: Image, color):
