@@ -1309,3 +1309,21 @@ def test_default_random_distortion_config_runs(vk):
         assert r.image.mat.dtype == np.uint8
         names.update(debug.distortion_names)
     assert {'ellipse_streak', 'jpeg_quality'} <= names, sorted(names)
+
+
+def test_optimistic_batch_host_runs_ahead(vk):
+    """Many optimistic steps queued without a synchronise (the host runs several steps ahead of
+    the device, abandoned plans are collected while their kernels are still queued): the pinned
+    blocks the kernels mirror shapes into must not be reused under them.  Regression test: a late
+    mirror write once landed in a staging block and corrupted the plane records of a later step."""
+    import torch
+    from vkit_b200.batch import GeometricBatch
+    names, configs, shape, images, _, _ = _camera_batch(8)
+    exact = GeometricBatch(names, configs, shape).run(images)
+    engine = GeometricBatch(names, configs, shape)
+    for _ in range(80):
+        out = engine.run(images, optimistic=True)
+    torch.cuda.synchronize()
+    assert out.shapes == exact.shapes
+    for i in range(len(names)):
+        assert np.array_equal(out.image(i).cpu().numpy(), exact.image(i).cpu().numpy()), i

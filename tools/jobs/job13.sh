@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/r2_sweep.log
+for v in cur nopar; do
+  echo "== $v" >> gpurun_out/r2_sweep.log
+  for b in 256 32; do
+  VKB_LIB=$PWD/variants/libvkit_$v.so timeout 120 python bench.py --steps 20 --warmup 3 --kernel-only --batch $b 2>&1 | python -c "
+import sys,json
+for line in sys.stdin:
+    if line.startswith('{'):
+        d=json.loads(line); print('batch $b value %.0f pages/s  step %.3f ms  remap %.3f ms' % (d['value'], d['ms_per_step'], d['roofline']['launch_ms']))
+    else: print(line.rstrip())
+" >> gpurun_out/r2_sweep.log 2>&1
+  done
+done
+cat gpurun_out/r2_sweep.log
+VKB_LIB=$PWD/variants/libvkit_cur.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "geometric or fuzz or batch or full_size" 2>&1 | tail -3

@@ -452,6 +452,9 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 constexpr int kTilesWarps = 8;
 constexpr int kTilesHalf = 16;                  // records per half: [0] = the zero map, 1..15 candidates
 constexpr int kTilesSlots = 2 * kTilesHalf;
+#ifndef VKB_TILES_FREE_STORE
+#define VKB_TILES_FREE_STORE 1
+#endif
 #ifndef VKB_TILES_CHUNK
 #define VKB_TILES_CHUNK 1
 #endif
@@ -533,12 +536,13 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
     // unevenly: 13 % of a 64-page launch was tail).  Two chunks are always in hand, so the next
     // tile and the one after it are known for the header / record prefetch.
     const int total = tile_base[n_pages];
-    auto grab = [&]() {
-        int v = 0;
-        if (lane == 0) v = atomicAdd(work_counter, kTilesChunk);
-        return __shfl_sync(0xffffffffu, v, 0);
-    };
-    int chunk0 = grab(), chunk1 = grab(), pos = 0;
+    // The counter is drawn one chunk further ahead than it is needed: lane 0 keeps the raw result
+    // of its atomicAdd (`pending`) and broadcasts it only when the chunk after next is due, a whole
+    // tile later -- the warp never waits for the atomic (8 % of the stall samples before).
+    auto draw = [&]() { return lane == 0 ? atomicAdd(work_counter, kTilesChunk) : 0; };
+    int chunk0 = __shfl_sync(0xffffffffu, draw(), 0);
+    int chunk1 = __shfl_sync(0xffffffffu, draw(), 0);
+    int pending = draw(), pos = 0;
     if (chunk0 >= total) return;
     auto tile_at = [&](int ahead) {  // ahead <= kTilesChunk
         const int p = pos + ahead;
@@ -578,7 +582,8 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
         if (++pos == kTilesChunk) {
             pos = 0;
             chunk0 = chunk1;
-            chunk1 = grab();
+            chunk1 = __shfl_sync(0xffffffffu, pending, 0);
+            pending = draw();
         }
         h0 = h1;
         h1 = load_header(tile_at(1));
@@ -654,6 +659,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
         const bool x_in = x < pg.dst_w;
+        const bool tile_in_x = tx0 + VKB_TILE <= pg.dst_w;
 
         // stores of one finished pixel
         auto store_px = [&](int di, const uint32_t* v) {
@@ -756,9 +762,19 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
                 fail4 |= ok ? 0u : (1u << j);
             }
             failbits |= fail4 << (band * 4);
-            // rows of the band this thread stores: inside the page, not waiting for the exact path
+            // rows of the band this thread stores: the ones inside the page.  (A pixel that waits
+            // for the exact path is stored here all the same and overwritten after the band loop
+            // by this very thread, in program order: no predicate per pixel for it.)  Bands that
+            // lie inside the page completely -- warp uniform, nearly all of them -- store
+            // without any predicate.
             const int rows_in = pg.dst_h - ry0;  // >= 1
+#if VKB_TILES_FREE_STORE
+            const bool interior = tile_in_x && rows_in >= 4;
+            const uint32_t live = x_in ? (rows_in >= 4 ? 0xFu : ((1u << rows_in) - 1u)) : 0u;
+#else
+            const bool interior = false;
             const uint32_t live = x_in ? (~fail4 & (rows_in >= 4 ? 0xFu : ((1u << rows_in) - 1u))) : 0u;
+#endif
             // ---- gather -------------------------------------------------------------------
             const int di0 = ry0 * pg.dst_w + x;
             if (tiny) {
@@ -794,11 +810,16 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
                 Fetch2<CC> f[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) fetch2_request<CC>(img_words, img_mis, img_pitch, tap[j], f[j]);
+                uint32_t v[4][CC];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t v[CC];
-                    fetch2_blend<CC>(f[j], tap[j], v);
-                    if ((live >> j) & 1u) store_px(di0 + j * pg.dst_w, v);
+                for (int j = 0; j < 4; ++j) fetch2_blend<CC>(f[j], tap[j], v[j]);
+                if (interior) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) store_px(di0 + j * pg.dst_w, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((live >> j) & 1u) store_px(di0 + j * pg.dst_w, v[j]);
                 }
             }
             if (MASK) {

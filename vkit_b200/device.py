@@ -134,22 +134,48 @@ def upload_structs(records: np.ndarray):
     return out
 
 
-def pinned_mirror(nbytes: int):
-    """A pinned host block a kernel mirrors small results into (result shapes, layouts); the
-    caller hands it back with `release_mirror` once it has read it."""
+class MirrorBlock:
+    """A pinned host block that kernels mirror small results into (result shapes, layouts).  The
+    block never goes back to torch's allocator: an abandoned plan's kernels may still be queued,
+    and a block handed to somebody else meanwhile would be overwritten under them (parameter
+    blocks corrupted by a late shape mirror: an illegal address in the remap).  `written()` is
+    called right after the launch of the last kernel that writes the block; the pool reuses a
+    block only when that point of the stream has been passed."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.event = None
+
+    def written(self):
+        t = torch()
+        self.event = t.cuda.Event()
+        self.event.record()
+
+    def data_ptr(self):
+        return self.tensor.data_ptr()
+
+    def numpy(self):
+        return self.tensor.numpy()
+
+    def release(self):
+        t = torch()
+        _PINNED.setdefault((t.cuda.current_device(), 'mirror', int(self.tensor.numel())), []).append(self)
+
+
+def pinned_mirror(nbytes: int) -> MirrorBlock:
     t = require_cuda()
     size = 4096
     while size < nbytes:
         size *= 2
     pool = _PINNED.setdefault((t.cuda.current_device(), 'mirror', size), [])
-    if pool:
-        return pool.pop()
-    return t.empty((size,), dtype=t.uint8, pin_memory=True)
+    for i, block in enumerate(pool):
+        if block.event is None or block.event.query():
+            return pool.pop(i)
+    return MirrorBlock(t.empty((size,), dtype=t.uint8, pin_memory=True))
 
 
-def release_mirror(block):
-    t = torch()
-    _PINNED.setdefault((t.cuda.current_device(), 'mirror', int(block.numel())), []).append(block)
+def release_mirror(block: MirrorBlock):
+    block.release()
 
 
 def ptr(tensor):

@@ -98,6 +98,7 @@ class GridBatch:
                                             dv.ptr(self.meta_dev),
                                             ctypes.c_void_p(meta_host.data_ptr()), stream),
                  'vkb_grid_finalize')
+        meta_host.written()
         self.meta_host = meta_host
         self.stream = t.cuda.current_stream()
         self.layout_host = None
@@ -116,6 +117,17 @@ class GridBatch:
         self.t_max = self.tiles_x * self.tiles_y
         self.hinv = None
         self.hfwd = None
+
+    def __del__(self):
+        # a plan nobody asked for its shapes: the mirrors go back to the pool, guarded by the
+        # events of their writers
+        for name in ('meta_host', 'layout_host'):
+            block = getattr(self, name, None)
+            if block is not None:
+                try:
+                    block.release()
+                except Exception:
+                    pass
 
     def _ws(self, name, shape, dtype):
         """A workspace tensor: from the engine's shared dict when the shape still fits, else new."""
@@ -195,6 +207,7 @@ class GridBatch:
             dv.ptr(self.meta_dev), self.n, dv.ptr(planes_dev), int(cap_pixels), self.t_max,
             dv.ptr(self.layout_dev), ctypes.c_void_p(self.layout_host.data_ptr()), dv.stream_ptr()),
             'vkb_grid_layout')
+        self.layout_host.written()
         return planes_dev
 
     def remap(self, planes: np.ndarray, launch_events=None, planes_dev=None):
