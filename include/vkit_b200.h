@@ -223,6 +223,18 @@ int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* planes, int32_t
 int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double* xy_in,
                     const int32_t* cell_rc, double* xy_out, int32_t n, void* stream);
 
+/* The same for the points of MANY pages in one launch (RandomDistortionBatch): page_cell: n x 3
+ * int32 (page, polygon_row, polygon_col); hfwd: the n_pages x c_max x 9 array of vkb_grid_build. */
+int vkb_grid_points_batched(const vkb_grid_page* pages, const double* hfwd, int32_t c_max,
+                            const double* xy_in, const int32_t* page_cell, double* xy_out,
+                            int32_t n, void* stream);
+
+/* affine_np_points (affine.py:46-64) for the points of many pages: mats: n_pages x 9 doubles
+ * (forward matrices, row major); rows_f32[page]: 2 or 3 rows, | 4 = float32 arithmetic (the 2 x 3
+ * ops); page_of: the page of every point.  All device pointers. */
+int vkb_affine_points_batched(const double* mats, const int32_t* rows_f32, const int32_t* page_of,
+                              const double* xy_in, double* xy_out, int32_t n, void* stream);
+
 /* Active mask: cv.fillPoly of one polygon (the dst lattice border, interface.py:177-192)
  * on a zeroed uint8 canvas.  poly_xy: n_pts x 2 int32 (x, y). */
 int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32_t* poly_xy, int32_t n_pts,

@@ -1327,3 +1327,63 @@ def test_optimistic_batch_host_runs_ahead(vk):
     assert out.shapes == exact.shapes
     for i in range(len(names)):
         assert np.array_equal(out.image(i).cpu().numpy(), exact.image(i).cpu().numpy()), i
+
+
+# ---------------------------------------------------------------------------------------------
+# RandomDistortionBatch: the reference fixtures through the BATCHED path
+# ---------------------------------------------------------------------------------------------
+def _rd_groups():
+    groups = {}
+    for case in chain_cases('random_distortion'):
+        groups.setdefault(tuple(case.get('disabled', NOT_YET)), []).append(case)
+    return list(groups.items())
+
+
+@pytest.mark.parametrize('disabled,cases', _rd_groups(), ids=lambda v: str(len(v)) if isinstance(v, list) else 'set')
+def test_random_distortion_batch_vs_reference(vk, disabled, cases):
+    """All fixture pages of one policy set in ONE RandomDistortionBatch.distort call: the chains
+    drawn on the host equal the reference's (names, levels, configs, rng stream), and pixels /
+    points / polygons meet the same bars as the per-page path."""
+    import torch
+    from vkit_b200.mechanism.distortion.photometric import noise as noise_mod
+    from vkit_b200.mechanism.distortion_policy import random_distortion_factory
+    from vkit_b200.mechanism.distortion_policy.random_distortion_batch import RandomDistortionBatch
+    rd = random_distortion_factory.create({'disabled_policy_names': list(disabled),
+                                           'force_post_rotate': True})
+    shape = tuple(cases[0]['shape'])
+    assert all(tuple(c['shape']) == shape for c in cases)
+    inputs = [make_inputs(c['seed'], shape) for c in cases]
+    images = torch.from_numpy(np.stack([x[0] for x in inputs])).cuda()
+    masks = torch.from_numpy(np.stack([x[1] for x in inputs])).cuda()
+    points = [np.asarray(make_points(c['seed'], shape, 16), dtype=np.float64) for c in cases]
+    polygons = [[np.asarray(p, dtype=np.float64) for p in make_polygons(c['seed'], shape, 4)]
+                for c in cases]
+    rngs = [np.random.default_rng(c['rng_seed']) for c in cases]
+    noise_mod.use_host_field(True)
+    try:
+        results = RandomDistortionBatch(rd).distort(rngs, images, masks, points, polygons)
+    finally:
+        noise_mod.use_host_field(False)
+    for case, rng, r in zip(cases, rngs, results):
+        chain = r.chain
+        assert chain.names == case['names'], case['id']
+        assert chain.levels == case['levels'], case['id']
+        assert _json_round([plain_config(c) for c in chain.configs]) == case['configs'], case['id']
+        assert float(rng.random()) == case['rng_after'], case['id']
+        assert list(r.shape) == case['result_shape'], case['id']
+        got, ref = r.image.cpu().numpy(), chain_array(case, 'image')
+        got_mask, ref_mask = r.mask.cpu().numpy(), chain_array(case, 'mask')
+        report = (case['id'], case['names'], _diff_report(got, ref), _diff_report(got_mask, ref_mask))
+        if not (set(case['names']) & INEXACT):
+            assert sha(got) == case['sha']['image'], report
+            assert sha(got_mask) == case['sha']['mask'], report
+        else:
+            diff = np.abs(got.astype(int) - ref.astype(int))
+            stretched = {'histogram_equalization', 'boundary_equalization'} & set(case['names'])
+            assert (diff > 0).mean() <= 0.03 and (stretched or diff.max() <= 16), report
+            if not ({'skew_hori', 'skew_vert', 'similarity_mls'} & set(case['names'])):
+                assert sha(got_mask) == case['sha']['mask'], report
+            else:
+                assert (got_mask != ref_mask).mean() <= 0.01, report
+        assert np.abs(r.points - chain_array(case, 'points')).max() <= 1e-3, report
+        assert np.abs(np.stack(r.polygons) - chain_array(case, 'polygons')).max() <= 1e-3, report

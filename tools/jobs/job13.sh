@@ -13,4 +13,3 @@ for line in sys.stdin:
   done
 done
 cat gpurun_out/r2_sweep.log
-VKB_LIB=$PWD/variants/libvkit_cur.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "geometric or fuzz or batch or full_size" 2>&1 | tail -3

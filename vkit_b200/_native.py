@@ -172,6 +172,8 @@ def _declare(lib):
     lib.vkb_grid_remap.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                    vp, i32, i32, i32, vp]
     lib.vkb_grid_points.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.vkb_grid_points_batched.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
+    lib.vkb_affine_points_batched.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.vkb_grid_layout.argtypes = [vp, i32, vp, ctypes.c_int64, i32, vp, vp, vp]
     lib.vkb_stage_params.argtypes = [vp, vp, ctypes.c_int64, vp]
     lib.vkb_fill_polygon.argtypes = [vp, i32, i32, vp, i32, c_uint8, vp]
@@ -210,7 +212,7 @@ def _declare(lib):
 
 EXPORTS = (
     'vkb_warp_fused', 'vkb_affine_points', 'vkb_grid_project', 'vkb_grid_finalize',
-    'vkb_grid_layout', 'vkb_stage_params', 'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_fill_polygon',
+    'vkb_grid_layout', 'vkb_stage_params', 'vkb_grid_build', 'vkb_grid_remap', 'vkb_grid_points', 'vkb_grid_points_batched', 'vkb_affine_points_batched', 'vkb_fill_polygon',
     'vkb_blend_fill', 'vkb_blend_draw_list', 'vkb_cvt_color', 'vkb_color_ops',
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_jpeg_round_trip_u8', 'vkb_streak_masks', 'vkb_photo_chain_batched',

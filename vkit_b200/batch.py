@@ -106,6 +106,35 @@ DIMS_BOUND_FACTOR = 1.5
 PIXELS_BOUND_FACTOR = 1.5
 
 
+def _planes_from_lists(planes, shapes, images, masks, score_maps, channels):
+    """Source side of the plane records when every page is its own tensor (pages that went
+    through different ops before): one pointer per page."""
+    n = len(shapes)
+    keep = []
+    if images is not None:
+        if channels is None:
+            channels = 1 if images[0].dim() == 2 else int(images[0].shape[2])
+        for i, (t, (h, w)) in enumerate(zip(images, shapes)):
+            t = t if t.is_contiguous() else t.contiguous()
+            if int(t.numel()) != h * w * channels:
+                raise ValueError(f'image {i} does not match its page shape')
+            keep.append(t)
+            planes['src_image'][i] = t.data_ptr()
+        planes['image_channels'] = channels
+    else:
+        channels = 0
+    for name, tensors in (('src_mask', masks), ('src_score', score_maps)):
+        if tensors is None:
+            continue
+        for i, (t, (h, w)) in enumerate(zip(tensors, shapes)):
+            t = t if t.is_contiguous() else t.contiguous()
+            if int(t.numel()) != h * w:
+                raise ValueError(f'{name[4:]} {i} does not match its page shape')
+            keep.append(t)
+            planes[name][i] = t.data_ptr()
+    return planes, channels, keep
+
+
 class GeometricBatch:
     """A batch of same-size pages, each with its own grid-op config."""
 
@@ -199,6 +228,11 @@ class GeometricBatch:
         """Plane records with the source side filled in (+ validation of the inputs)."""
         src_offsets, n_src = self._src_offsets, self._n_src
         planes = self._planes_template.copy()
+        if isinstance(images, (list, tuple)) or isinstance(masks, (list, tuple)) \
+                or isinstance(score_maps, (list, tuple)):
+            planes, channels, self._keep_sources = _planes_from_lists(
+                planes, self.shapes, images, masks, score_maps, channels)
+            return planes, channels
         if images is not None:
             if channels is None:
                 channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
@@ -295,6 +329,7 @@ class AffineBatch:
         self.records = np.zeros(self.n, dtype=nv.WARP_PAGE_DTYPE)
         self.result_shapes = []
         self.identity = []
+        self.forward = []  # forward matrix per page (None: identity), for the points
         for i, (name, config) in enumerate(zip(op_names, configs)):
             config_cls, state_cls = _affine_states()[name]
             config = dyn_structure(config, config_cls)
@@ -302,11 +337,13 @@ class AffineBatch:
             trans_mat, dsize = state.trans_mat, state.dsize
             if trans_mat is None or getattr(config, 'is_nop', False):
                 self.identity.append(True)
+                self.forward.append(None)
                 self.result_shapes.append(self.shapes[i])
                 self.records['kind'][i] = nv.WARP_AFFINE
                 self.records['inv'][i, :6] = [1, 0, 0, 0, 1, 0]
                 continue
             self.identity.append(False)
+            self.forward.append(trans_mat)
             self.result_shapes.append((int(dsize[1]), int(dsize[0])))
             if trans_mat.shape[0] == 2:
                 self.records['kind'][i] = nv.WARP_AFFINE
@@ -332,6 +369,24 @@ class AffineBatch:
         planes['dst_h'] = [s[0] for s in shapes]
         planes['dst_w'] = [s[1] for s in shapes]
         image_arena = mask_arena = score_arena = None
+        if isinstance(images, (list, tuple)) or isinstance(masks, (list, tuple)) \
+                or isinstance(score_maps, (list, tuple)):
+            planes, channels, self._keep_sources = _planes_from_lists(
+                planes, self.shapes, images, masks, score_maps, channels)
+            if images is not None:
+                image_arena = dv.empty((total * channels,), np.uint8)
+                planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
+                    np.uint64)
+            if masks is not None:
+                mask_arena = dv.empty((total,), np.uint8)
+                planes['dst_mask'] = mask_arena.data_ptr() + offsets[:-1].astype(np.uint64)
+            if score_maps is not None:
+                score_arena = dv.empty((total,), np.float32)
+                planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
+            images = masks = score_maps = None
+            from_lists = True
+        else:
+            from_lists = False
         if images is not None:
             if channels is None:
                 channels = 1 if images.dim() == 3 else (int(images.shape[3]) if images.dim() == 4
@@ -345,7 +400,7 @@ class AffineBatch:
             planes['dst_image'] = image_arena.data_ptr() + (offsets[:-1] * channels).astype(
                 np.uint64)
             planes['image_channels'] = channels
-        else:
+        elif not from_lists:
             channels = 0
         if masks is not None:
             if int(masks.numel()) != int(src_pixels.sum()):
@@ -359,8 +414,10 @@ class AffineBatch:
             score_arena = dv.empty((total,), np.float32)
             planes['src_score'] = np.uint64(score_maps.data_ptr()) + src_offsets * np.uint64(4)
             planes['dst_score'] = score_arena.data_ptr() + (offsets[:-1] * 4).astype(np.uint64)
-        if images is None and masks is None and score_maps is None:
+        if images is None and masks is None and score_maps is None and not from_lists:
             raise ValueError('nothing to warp')
+        if from_lists and image_arena is None:
+            channels = 0
         records = self.records.copy()
         records['planes'] = planes
         pages_dev = dv.upload_structs(records)

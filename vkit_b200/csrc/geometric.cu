@@ -849,6 +849,57 @@ __global__ void grid_points_kernel(const double* __restrict__ hfwd, int ccols,
     xy_out[2 * i + 1] = __ddiv_rn(ty, t);
 }
 
+// Batched forms for RandomDistortionBatch: every point carries its page.
+__global__ void grid_points_batched_kernel(const vkb_grid_page* __restrict__ pages,
+                                           const double* __restrict__ hfwd, int c_max,
+                                           const double* __restrict__ xy_in,
+                                           const int32_t* __restrict__ page_cell,
+                                           double* __restrict__ xy_out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int page = page_cell[3 * i];
+    const int ccols = pages[page].cols - 1;
+    const double* H = hfwd + ((size_t)page * c_max + (size_t)page_cell[3 * i + 1] * ccols
+                              + page_cell[3 * i + 2]) * 9;
+    const double x = xy_in[2 * i], y = xy_in[2 * i + 1];
+    const double tx = __dadd_rn(__dadd_rn(__dmul_rn(H[0], x), __dmul_rn(H[1], y)), H[2]);
+    const double ty = __dadd_rn(__dadd_rn(__dmul_rn(H[3], x), __dmul_rn(H[4], y)), H[5]);
+    const double t = __dadd_rn(__dadd_rn(__dmul_rn(H[6], x), __dmul_rn(H[7], y)), H[8]);
+    xy_out[2 * i] = __ddiv_rn(tx, t);
+    xy_out[2 * i + 1] = __ddiv_rn(ty, t);
+}
+
+// mats: per page 9 doubles (row major, 2 x 3 matrices in the first six) + kind in `rows_f32`
+// (bits 0-1: rows 2 / 3, bit 2: float32 arithmetic like affine_np_points with a 2 x 3 matrix)
+__global__ void affine_points_batched_kernel(const double* __restrict__ mats,
+                                             const int32_t* __restrict__ rows_f32,
+                                             const int32_t* __restrict__ page_of,
+                                             const double* __restrict__ xy_in,
+                                             double* __restrict__ xy_out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int page = page_of[i];
+    const double* M = mats + (size_t)page * 9;
+    const int rows = rows_f32[page] & 3;
+    if (rows_f32[page] & 4) {
+        const float x = (float)xy_in[2 * i], y = (float)xy_in[2 * i + 1];
+        xy_out[2 * i] = (double)__fmaf_rn((float)M[2], 1.0f, __fmaf_rn((float)M[1], y, __fmul_rn((float)M[0], x)));
+        xy_out[2 * i + 1] = (double)__fmaf_rn((float)M[5], 1.0f, __fmaf_rn((float)M[4], y, __fmul_rn((float)M[3], x)));
+        return;
+    }
+    const double x = xy_in[2 * i], y = xy_in[2 * i + 1];
+    const double tx = fma(M[2], 1.0, fma(M[1], y, __dmul_rn(M[0], x)));
+    const double ty = fma(M[5], 1.0, fma(M[4], y, __dmul_rn(M[3], x)));
+    if (rows == 2) {
+        xy_out[2 * i] = tx;
+        xy_out[2 * i + 1] = ty;
+        return;
+    }
+    const double t = fma(M[8], 1.0, fma(M[7], y, __dmul_rn(M[6], x)));
+    xy_out[2 * i] = __ddiv_rn(tx, t);
+    xy_out[2 * i + 1] = __ddiv_rn(ty, t);
+}
+
 struct Mat9 {
     double m[9];
 };
@@ -1187,6 +1238,26 @@ extern "C" int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, co
     grid_points_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(hfwd_page, cols_minus_1,
                                                                           xy_in, cell_rc, xy_out, n);
     return check_launch("grid_points_kernel");
+}
+
+extern "C" int vkb_grid_points_batched(const vkb_grid_page* pages, const double* hfwd, int32_t c_max,
+                                       const double* xy_in, const int32_t* page_cell,
+                                       double* xy_out, int32_t n, void* stream) {
+    VKB_REQUIRE(pages && hfwd && xy_in && page_cell && xy_out && c_max > 0, "bad arguments");
+    if (n <= 0) return VKB_OK;
+    grid_points_batched_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        pages, hfwd, c_max, xy_in, page_cell, xy_out, n);
+    return check_launch("grid_points_batched_kernel");
+}
+
+extern "C" int vkb_affine_points_batched(const double* mats, const int32_t* rows_f32,
+                                         const int32_t* page_of, const double* xy_in,
+                                         double* xy_out, int32_t n, void* stream) {
+    VKB_REQUIRE(mats && rows_f32 && page_of && xy_in && xy_out, "bad arguments");
+    if (n <= 0) return VKB_OK;
+    affine_points_batched_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        mats, rows_f32, page_of, xy_in, xy_out, n);
+    return check_launch("affine_points_batched_kernel");
 }
 
 extern "C" int vkb_fill_polygon(uint8_t* mask, int32_t h, int32_t w, const int32_t* poly_xy,
