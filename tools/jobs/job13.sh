@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/r2_sweep.log
-for v in cur nopar; do
+for v in cur il; do
   echo "== $v" >> gpurun_out/r2_sweep.log
   for b in 256 32; do
   VKB_LIB=$PWD/variants/libvkit_$v.so timeout 120 python bench.py --steps 20 --warmup 3 --kernel-only --batch $b 2>&1 | python -c "

@@ -418,9 +418,12 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     const int y0 = min(min(dy[0], dy[1]), min(dy[2], dy[3]));
     const int y1 = max(max(dy[0], dy[1]), max(dy[2], dy[3]));
     int32_t* box = cell_box + ((size_t)page * c_max + cell) * 4;
+    // bit 30 of x1: the coverage of this cell exceeds the fixed mask budget (one 32-bit word per
+    // row, VKB_CELL_MASK_WORDS rows): the masks kernel skips it, the remap rasterises it on the fly
+    const bool big = (x1 - x0 + 32) / 32 != 1 || y1 - y0 + 1 > VKB_CELL_MASK_WORDS;
     box[0] = x0;
     box[1] = y0;
-    box[2] = x1;
+    box[2] = x1 | (big ? 0x40000000 : 0);
     box[3] = y1;
     // bin into dst tiles
     const int tiles_x = (meta[page].dst_w + VKB_TILE - 1) / VKB_TILE;
@@ -455,8 +458,7 @@ constexpr int kMaskCells = 8;  // cells per warp and step
 
 __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max,
-    const int32_t* __restrict__ lattice_i, int32_t* __restrict__ cell_box,
-    uint32_t* __restrict__ cell_masks) {
+    const int32_t* __restrict__ lattice_i, uint32_t* __restrict__ cell_masks) {
     __shared__ uint32_t sm_rows[kMaskWarps][kMaskCells][VKB_CELL_MASK_WORDS];
     __shared__ EdgeScan sm_scan[kMaskWarps][kMaskCells][4];
     __shared__ int2 sm_org[kMaskWarps][kMaskCells];  // bbox origin (x0, y0)
@@ -493,11 +495,8 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
     y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, 2));
     y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, 2));
     int nrows = y1 - y0 + 1;
+    // too large for the fixed budget: flagged by grid_cells_kernel, rasterised by the remap
     const bool big = (x1 - x0 + 32) / 32 != 1 || nrows > VKB_CELL_MASK_WORDS;
-    if (valid && big && e == 0) {
-        // too large for the fixed budget: the remap kernel rasterises this cell on the fly
-        cell_box[((size_t)page * c_max + cell) * 4 + 2] |= 0x40000000;
-    }
     if (!valid || big) nrows = 0;
     if (nrows) {
         EdgeScan es;
@@ -618,9 +617,12 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
     const int32_t* __restrict__ tile_off, const int32_t* __restrict__ tile_base,
     TileSlot* __restrict__ slots, RemapTile* __restrict__ headers, int32_t* __restrict__ large) {
+    // HALF a warp per tile (a tile has 8.7 candidates on average, 64 at most): lane l of the half
+    // takes candidates l, l + 16, ...; a candidate's rank = the number of smaller cell indices in
+    // the tile's list (read back from L1, the same address for the whole half warp).
     const int page = blockIdx.y;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 4);
+    const int lane = threadIdx.x & 15;
     const int dst_w = meta[page].dst_w;
     const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
     if (t >= min(page_tiles(meta[page]), t_max)) return;
@@ -647,29 +649,13 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     }
     if (!usable) return;  // the remap takes its slow path
     const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
-    const int ca = lane < count ? (int)cells[lane] : 0x7fffffff;
-    const int cb = lane + 32 < count ? (int)cells[lane + 32] : 0x7fffffff;
-    int rank_a = 0, rank_b = 0;
-    const int na = min(count, 32), nb = max(count - 32, 0);
-    for (int i = 0; i < na; ++i) {
-        const int o = __shfl_sync(0xffffffffu, ca, i);
-        rank_a += o < ca;
-        rank_b += o < cb;
-    }
-    for (int i = 0; i < nb; ++i) {
-        const int o = __shfl_sync(0xffffffffu, cb, i);
-        rank_a += o < ca;
-        rank_b += o < cb;
-    }
     const int ccols = pages[page].cols - 1;
     const int gs = pages[page].grid_size;
     const size_t page_cell0 = (size_t)page * c_max;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int s = lane + 32 * half;
-        if (s >= count) break;
-        const int cell = half ? cb : ca;
-        const int rank = half ? rank_b : rank_a;
+    for (int s = lane; s < count; s += 16) {
+        const int cell = (int)cells[s];
+        int rank = 0;
+        for (int j = 0; j < count; ++j) rank += (int)cells[j] < cell;
         const int4 b = cell_box[page_cell0 + cell];
         const int r = cell / ccols, c = cell - r * ccols;
         double H[9];
@@ -1192,6 +1178,30 @@ extern "C" int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes*
     return check_launch("grid_layout_kernel");
 }
 
+// One side stream + fork / join events per device for vkb_grid_build (created on first use; work
+// submitted through it is ordered with the caller's stream by the two events).
+struct BuildSide {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static BuildSide* build_side() {
+    static BuildSide sides[64];
+    static bool ready[64] = {};
+    static std::mutex mutex;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mutex);
+    if (!ready[dev]) {
+        BuildSide s;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sides[dev] = s;
+        ready[dev] = true;
+    }
+    return &sides[dev];
+}
+
 extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                               int32_t c_max, int32_t t_max, int32_t s_cap, const int32_t* lattice_i,
                               vkb_grid_meta* meta, double* hinv, double* hfwd, int32_t* cell_box,
@@ -1212,19 +1222,33 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     int32_t* large = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(tile_headers)
                                                 + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
     VKB_CUDA(cudaMemsetAsync(large, 0, sizeof(int32_t), st));
+    // cells (fp64 latency bound) and masks (integer issue bound) only share their input: the
+    // masks run on a side stream next to the cells
+    BuildSide* side = build_side();
+    static std::mutex side_mutex;  // the fork / join events are shared by all callers
+    std::lock_guard<std::mutex> side_lock(side_mutex);
+    if (side) {
+        VKB_CUDA(cudaEventRecord(side->fork, st));
+        VKB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
+    grid_masks_kernel<<<dim3((c_max + kMaskWarps * kMaskCells - 1) / (kMaskWarps * kMaskCells), n_pages),
+                        32 * kMaskWarps, 0, side ? side->stream : st>>>(pages, p_max, c_max, lattice_i,
+                                                                       cell_masks);
+    int rc = check_launch("grid_masks_kernel");
+    if (rc) return rc;
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
-    int rc = check_launch("grid_cells_kernel");
+    rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
-    grid_masks_kernel<<<dim3((c_max + kMaskWarps * kMaskCells - 1) / (kMaskWarps * kMaskCells), n_pages),
-                        32 * kMaskWarps, 0, st>>>(pages, p_max, c_max, lattice_i, cell_box, cell_masks);
-    rc = check_launch("grid_masks_kernel");
-    if (rc) return rc;
+    if (side) {
+        VKB_CUDA(cudaEventRecord(side->join, side->stream));
+        VKB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    }
     grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);
     grid_tile_offsets_kernel<<<n_pages, 1024, 0, st>>>(meta, t_max, tile_count, tile_off);
     rc = check_launch("grid_tile_offsets_kernel");
     if (rc) return rc;
-    grid_tile_records_kernel<<<dim3((t_max + 3) / 4, n_pages), 128, 0, st>>>(
+    grid_tile_records_kernel<<<dim3((t_max + 7) / 8, n_pages), 128, 0, st>>>(
         pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
         tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
         reinterpret_cast<RemapTile*>(tile_headers), large);

@@ -251,11 +251,7 @@ VKB_HD bool fast_axis(float f, int base_m, float t_odd, float t_even, int& X) {
     v.f = VKB_FADD(f, kRoundMagic);                 // low mantissa bits = rint(f), half to even
     const float d = VKB_FSUB(f, VKB_FSUB(v.f, kRoundMagic));  // exact
     X = base_m + v.i;
-#ifdef VKB_FAST_NO_PARITY  // experiment: one (the stricter) threshold for both parities
-    return fabsf(d) < t_odd;
-#else
     return fabsf(d) < ((v.i & 1) ? t_odd : t_even);
-#endif
 }
 
 VKB_HD float fma_rn_f32(float a, float b, float c) {
