@@ -389,6 +389,12 @@ int vkb_resize_u8(const uint8_t* src, int32_t src_h, int32_t src_w, uint8_t* dst
  * fuses the np.clip(mat, 0, 1) the reference applies to probability maps. */
 int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
                    int32_t dst_w, int32_t interpolation, int32_t clip01, void* stream);
+/* The same with every resized value multiplied by `post_scale` (one float32 product, after the
+ * clip) before it is stored: PageResizingStep scales its height score maps by the resize ratio
+ * right after resizing them (pipeline/text_detection/page_resizing.py:160-161, 177-180). */
+int vkb_resize_f32_scaled(const float* src, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
+                          int32_t dst_w, int32_t interpolation, int32_t clip01, float post_scale,
+                          void* stream);
 
 /* Mask.to_resized_mask (element/mask.py:454-479) in ONE pass: the source reads as (v > 0) * 255,
  * cv.resize with `interpolation` (same codes and exactness as vkb_resize_u8), the result is stored
@@ -491,6 +497,48 @@ int vkb_noise_philox_batched(const vkb_photo_page* pages, int32_t n_pages, int32
  * out (device): per page 3 x uint64 sums, then 3 x uint32 mins, 3 x uint32 maxs (48 bytes). */
 int vkb_channel_stats_batched(const vkb_photo_page* pages, int32_t n_pages, int32_t channels,
                               void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The step before compositing.
+ *
+ * Background synthesis -- ImageCombinerEngine.synthesize_image
+ * (vkit/engine/image/combiner.py:178-333): texture segments pasted into an h x w canvas in list
+ * order (later segments overwrite earlier ones, uncovered pixels stay 0), then the pixels inside
+ * the edge bands of every segment (fill_np_edge_mask, combiner.py:147-176; `band` =
+ * gaussian_blur_kernel_size // 2 + 1) are replaced by cv.GaussianBlur(canvas, (ksize, ksize),
+ * sigma) with BORDER_REFLECT_101 -- `kernel_host`: the ksize 8.8 fixed-point taps (sum 256) cv2
+ * derives for uint8.  One pass, one launch; the canvas is written once.  items: device array;
+ * `src` of an item points at the texture pixel that lands on (up, left), src_pitch in pixels.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vkb_paste_item {
+    const uint8_t* src;
+    int32_t src_pitch;
+    int32_t up, down, left, right; /* inclusive canvas rectangle */
+    int32_t pad_;
+} vkb_paste_item;
+int vkb_background_compose(uint8_t* dst, int32_t h, int32_t w, int32_t channels,
+                           const vkb_paste_item* items, int32_t n_items, int32_t band,
+                           const int32_t* kernel_host, int32_t ksize, void* stream);
+
+/* Glyph atlas -- the planes render_char_glyphs_in_text_line blends from
+ * (vkit/engine/font/freetype.py:136-221 build_char_glyph, :314-380 the renderer,
+ * engine/font/type.py:423-451 get_glyph_mask), derived on the device from FreeType coverage
+ * bitmaps uploaded once:  mask = bitmap > 0 (any channel for H x W x 3 LCD bitmaps);
+ * alpha = alpha_lut[bitmap] (float32; the caller evaluates np.power(v / 255, gamma) for the 256
+ * byte values, so the numbers are NumPy's own); lcd_image = lcd_lut[bitmap] per channel.
+ * One block per glyph.  items: device array, items_host: the same records for validation. */
+typedef struct vkb_glyph_item {
+    const uint8_t* bitmap; /* n_pixels x channels */
+    uint8_t* mask;         /* n_pixels */
+    float* alpha;          /* n_pixels or NULL (LCD glyphs have no score map) */
+    uint8_t* lcd_image;    /* n_pixels x 3 or NULL */
+    const float* alpha_lut; /* 256 float32 */
+    const uint8_t* lcd_lut; /* 256 uint8 */
+    int32_t n_pixels;
+    int32_t channels; /* 1 or 3 */
+} vkb_glyph_item;
+int vkb_glyph_prepare(const vkb_glyph_item* items, const vkb_glyph_item* items_host,
+                      int32_t n_items, void* stream);
 
 #ifdef __cplusplus
 }

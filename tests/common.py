@@ -218,3 +218,72 @@ def rgb_to_gray(rgb):
     oracle's pinned model."""
     from oracle import cv2_model
     return cv2_model.cvt_rgb2gray(rgb)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fixtures of the step before compositing (tests/golden/make_golden_f4.py): background
+# synthesis, glyph preparation, LCD / default text-line rendering
+# ---------------------------------------------------------------------------------------------
+_F4 = None
+
+
+def f4_golden():
+    global _F4
+    if _F4 is None:
+        with open(os.path.join(GOLDEN_DIR, 'f4_cases.json')) as fin:
+            meta = json.load(fin)
+        _F4 = (meta['cases'], np.load(os.path.join(GOLDEN_DIR, 'f4_arrays.npz')))
+    return _F4
+
+
+def f4_cases(kind):
+    return [c for c in f4_golden()[0] if c['kind'] == kind]
+
+
+def f4_array(case, key):
+    arrays = f4_golden()[1]
+    name = f"{case['id']}/{key}"
+    return arrays[name] if name in arrays.files else None
+
+
+def f4_textures(seed, count, size_min, size_max):
+    """Synthetic background textures: smooth colour ramps + noise, each with its own size and
+    brightness so the grayscale-mean ordering and the sigma window of the combiner matter.
+    Returns [(name, HxWx3 uint8, grayscale_mean, grayscale_std)]; the statistics are rounded to
+    three decimals so JSON and both sides see the same numbers."""
+    rng = np.random.default_rng(seed)
+    textures = []
+    for k in range(count):
+        h, w = (int(v) for v in rng.integers(size_min, size_max + 1, 2))
+        base = rng.integers(20, 236, 3)
+        yy, xx = np.mgrid[0:h, 0:w]
+        ramp = (yy * int(rng.integers(-3, 4)) + xx * int(rng.integers(-3, 4))) // 4
+        mat = base[None, None, :] + ramp[:, :, None] + rng.integers(-12, 13, (h, w, 3))
+        mat = np.clip(mat, 0, 255).astype(np.uint8)
+        gray = mat.mean(axis=2)
+        textures.append((f'tex{k:02d}.png', mat, round(float(gray.mean()), 3),
+                         round(float(gray.std()), 3)))
+    return textures
+
+
+def f4_glyph_bitmaps(seed, count, lcd):
+    """Synthetic FreeType-like coverage bitmaps with empty margins (so trimming has work to do):
+    [(bitmap, bitmap_top, bitmap_left, advance_x)]."""
+    rng = np.random.default_rng(seed)
+    glyphs = []
+    for _ in range(count):
+        h, w = int(rng.integers(6, 30)), int(rng.integers(4, 24))
+        shape = (h, w, 3) if lcd else (h, w)
+        body = rng.integers(0, 256, shape)
+        body[rng.random(shape) < 0.45] = 0
+        pad = [int(v) for v in rng.integers(0, 4, 4)]
+        full = np.zeros((h + pad[0] + pad[1], w + pad[2] + pad[3]) + shape[2:], dtype=np.uint8)
+        full[pad[0]:pad[0] + h, pad[2]:pad[2] + w] = body
+        # one certainly covered pixel per border row / column of the body keeps the trim exact
+        full[pad[0], pad[2]] = 255
+        full[pad[0] + h - 1, pad[2] + w - 1] = 255
+        bitmap_top = int(rng.integers(-2, h + 4))
+        bitmap_left = int(rng.integers(-2, 4))
+        advance_x = int(rng.integers(1, (full.shape[1] + 6) * 64))
+        glyphs.append((full, bitmap_top, bitmap_left, advance_x))
+    return glyphs

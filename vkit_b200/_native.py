@@ -106,6 +106,17 @@ class ZoomLevel(ctypes.Structure):
     _fields_ = [('scale_x', c_double), ('scale_y', c_double), ('up', c_int32), ('left', c_int32)]
 
 
+class PasteItem(ctypes.Structure):
+    _fields_ = [('src', c_void_p), ('src_pitch', c_int32), ('up', c_int32), ('down', c_int32),
+                ('left', c_int32), ('right', c_int32), ('pad_', c_int32)]
+
+
+class GlyphItem(ctypes.Structure):
+    _fields_ = [('bitmap', c_void_p), ('mask', c_void_p), ('alpha', c_void_p),
+                ('lcd_image', c_void_p), ('alpha_lut', c_void_p), ('lcd_lut', c_void_p),
+                ('n_pixels', c_int32), ('channels', c_int32)]
+
+
 class Rect(ctypes.Structure):
     _fields_ = [('up', c_int32), ('down', c_int32), ('left', c_int32), ('right', c_int32)]
 
@@ -149,6 +160,8 @@ COLOR_OP_DTYPE = _np_dtype(ColorOp)
 WARP_PAGE_DTYPE = _np_dtype(WarpPage)
 GRID_PAGE_DTYPE = _np_dtype(GridPage)
 GRID_META_DTYPE = _np_dtype(GridMeta)
+PASTE_ITEM_DTYPE = _np_dtype(PasteItem)
+GLYPH_ITEM_DTYPE = _np_dtype(GlyphItem)
 
 
 class NativeError(RuntimeError):
@@ -200,12 +213,16 @@ def _declare(lib):
     lib.vkb_gather_pixels_u8.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.vkb_resize_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
+    lib.vkb_resize_f32_scaled.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, c_float, vp]
     lib.vkb_resize_mask_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_filter2d_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
     lib.vkb_fill_polygons.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp]
     lib.vkb_photo_chain_batched.argtypes = [vp, vp, i32, i32, vp]
     lib.vkb_channel_stats_batched.argtypes = [vp, i32, i32, vp, vp]
     lib.vkb_noise_philox_batched.argtypes = [vp, i32, i32, i32, vp]
+    lib.vkb_background_compose.argtypes = [vp, i32, i32, i32, vp, i32, i32, POINTER(c_int32), i32,
+                                           vp]
+    lib.vkb_glyph_prepare.argtypes = [vp, vp, i32, vp]
     for name in EXPORTS:
         getattr(lib, name).restype = c_int32
 
@@ -217,6 +234,7 @@ EXPORTS = (
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_jpeg_round_trip_u8', 'vkb_streak_masks', 'vkb_photo_chain_batched',
     'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_resize_mask_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
+    'vkb_background_compose', 'vkb_glyph_prepare', 'vkb_resize_f32_scaled',
 )
 
 

@@ -9,8 +9,9 @@ as ONE upload + ONE launch (`vkb_blend_draw_list`), applying overlapping items i
 the result is identical to the sequential calls.
 """
 import ctypes
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Dict, Hashable, List, Optional, Sequence, Tuple, Union
 
+import attrs
 import numpy as np
 
 from . import _native as nv
@@ -20,6 +21,29 @@ from .element import Box, Image, Mask, ScoreMap
 
 def _align(n: int, a: int = 16) -> int:
     return (n + a - 1) // a * a
+
+
+@attrs.define(eq=False)
+class DeviceBlob:
+    """A region-shaped array that already lives in HBM (a glyph plane of the atlas, a texture):
+    draw-list items point at it instead of uploading a copy per fill."""
+    tensor: object  # the CUDA tensor that owns the bytes (kept alive by whoever holds the blob)
+    offset: int  # bytes from tensor.data_ptr()
+    shape: Tuple[int, ...]  # (h, w) or (h, w, channels)
+    pitch: int  # pixels per row
+    dtype: np.dtype
+
+    @property
+    def ptr(self) -> int:
+        return self.tensor.data_ptr() + self.offset
+
+    def to_host(self) -> np.ndarray:
+        """Download (tests / debugging)."""
+        count = int(np.prod(self.shape))
+        nbytes = count * np.dtype(self.dtype).itemsize
+        assert self.pitch == self.shape[1]
+        raw = dv.to_host(self.tensor.view(dv.torch().uint8).reshape(-1)[self.offset:self.offset + nbytes])
+        return raw.view(self.dtype).reshape(self.shape).copy()
 
 
 class DrawList:
@@ -55,9 +79,17 @@ class DrawList:
         item['box_h'], item['box_w'] = rel.height, rel.width
         idx = len(self.items)
 
-        if isinstance(value, (Image, Mask, ScoreMap)):
+        if isinstance(value, DeviceBlob):
+            if tuple(value.shape[:2]) != rel.shape or np.dtype(value.dtype) != self.np_dtype:
+                raise RuntimeError('device value does not match the box / destination dtype.')
+            item['value_arr'] = value.ptr
+            item['value_pitch'] = value.pitch
+            self.device_refs.append(value.tensor)
+        elif isinstance(value, (Image, Mask, ScoreMap)):
             value = value.mat
-        if isinstance(value, np.ndarray):
+        if isinstance(value, DeviceBlob):
+            pass
+        elif isinstance(value, np.ndarray):
             if value.shape[:2] == self.target.shape and rel.shape != self.target.shape:
                 value = value[rel.up:rel.down + 1, rel.left:rel.right + 1]
             if value.shape[:2] != rel.shape:
@@ -77,7 +109,14 @@ class DrawList:
         if isinstance(alpha, ScoreMap):
             assert alpha.is_prob
             alpha = alpha.mat
-        if isinstance(alpha, np.ndarray):
+        if isinstance(alpha, DeviceBlob):
+            if tuple(alpha.shape) != rel.shape or np.dtype(alpha.dtype) != np.float32:
+                raise RuntimeError('device alpha does not match the box.')
+            item['alpha_arr'] = alpha.ptr
+            item['alpha_pitch'] = alpha.pitch
+            item['alpha'] = 1.0
+            self.device_refs.append(alpha.tensor)
+        elif isinstance(alpha, np.ndarray):
             if alpha.shape != rel.shape:
                 raise RuntimeError('alpha array shape does not match the box.')
             self.blobs.append((idx, 'alpha_arr', np.ascontiguousarray(alpha, dtype=np.float32)))
@@ -92,7 +131,13 @@ class DrawList:
                 return
             item['alpha'] = alpha
 
-        if mask is not None:
+        if isinstance(mask, DeviceBlob):
+            if tuple(mask.shape) != rel.shape or np.dtype(mask.dtype) != np.uint8:
+                raise RuntimeError('device mask does not match the box.')
+            item['mask'] = mask.ptr
+            item['mask_pitch'] = mask.pitch
+            self.device_refs.append(mask.tensor)
+        elif mask is not None:
             if isinstance(mask, Mask):
                 mask = mask.mat
             if mask.shape != rel.shape:
@@ -147,13 +192,233 @@ class DrawList:
         return self.target
 
 
+# =============================================================================================
+# Glyph atlas: FreeType coverage bitmaps uploaded once, their
+# blend planes derived on the device, text lines rendered from device pointers
+# =============================================================================================
+def trim_glyph_bitmap(bitmap: np.ndarray):
+    """Rows / columns without coverage removed (trim_char_np_image_vert / _hori,
+    freetype.py:100-134): returns (trimmed, pad_up, pad_down, pad_left, pad_right)."""
+    covered = bitmap if bitmap.ndim == 2 else bitmap.max(axis=2)
+    rows = np.flatnonzero(covered.max(axis=1))
+    cols = np.flatnonzero(covered.max(axis=0))
+    if rows.size == 0 or cols.size == 0:
+        raise RuntimeError('trim_glyph_bitmap: empty bitmap.')
+    up, down, left, right = int(rows[0]), int(rows[-1]), int(cols[0]), int(cols[-1])
+    height, width = covered.shape
+    return (bitmap[up:down + 1, left:right + 1], up, height - 1 - down, left, width - 1 - right)
+
+
+@attrs.define(eq=False)
+class AtlasGlyph:
+    """One cached glyph: the metrics build_char_glyph derives (freetype.py:136-221) and, once the
+    atlas is committed, the device planes the renderer blends from."""
+    key: Hashable
+    height: int
+    width: int
+    channels: int  # 1: default / monochrome, 3: LCD
+    gamma: float
+    ascent: int
+    pad_up: int
+    pad_down: int
+    pad_left: int
+    pad_right: int
+    bitmap: Optional[DeviceBlob] = None
+    mask: Optional[DeviceBlob] = None
+    alpha: Optional[DeviceBlob] = None  # float32 score map (default / monochrome glyphs)
+    lcd_image: Optional[DeviceBlob] = None  # uint8 H x W x 3 (LCD glyphs)
+
+    @property
+    def shape(self):
+        return self.height, self.width
+
+
+class GlyphAtlas:
+    """Device-resident glyph cache.  `add` registers a FreeType bitmap under a key (font, char,
+    size ...), `commit` uploads everything added since the last commit in ONE copy and derives
+    the mask / alpha / LCD planes with ONE launch (`vkb_glyph_prepare`).  Arena pages are never
+    moved, so blobs handed out stay valid for the life of the atlas."""
+
+    def __init__(self, page_bytes: int = 8 << 20):
+        self.page_bytes = page_bytes
+        self.pages: List[object] = []
+        self.cursor = 0
+        self.glyphs: Dict[Hashable, AtlasGlyph] = {}
+        self._pending: List[Tuple[AtlasGlyph, np.ndarray]] = []
+        self._luts: Dict[float, Tuple[DeviceBlob, DeviceBlob]] = {}
+
+    def __contains__(self, key):
+        return key in self.glyphs
+
+    def __getitem__(self, key) -> AtlasGlyph:
+        return self.glyphs[key]
+
+    @staticmethod
+    def gamma_tables(gamma: float):
+        """The two functions of a coverage byte the reference evaluates per glyph pixel, tabulated
+        with the same NumPy expressions: float32 alpha `np.power(v.astype(float32) / 255.0, gamma)`
+        (freetype.py:176-180) and the LCD image `((1 - np.power(v / 255.0, gamma)) * 255)
+        .astype(uint8)` (freetype.py:361-366)."""
+        v = np.arange(256, dtype=np.uint8)
+        alpha = np.power(v.astype(np.float32) / 255.0, gamma)
+        lcd = ((1 - np.power(v / 255.0, gamma)) * 255).astype(np.uint8)
+        return np.ascontiguousarray(alpha, dtype=np.float32), lcd
+
+    def add(self, key: Hashable, bitmap: np.ndarray, gamma: float = 1.0, bitmap_top: int = 0,
+            bitmap_left: int = 0, advance_x: Optional[int] = None) -> AtlasGlyph:
+        """Register the bitmap FreeType rendered for one char (H x W, or H x W x 3 in LCD mode).
+        `bitmap_top`, `bitmap_left`, `advance_x` (26.6 fixed point) are the glyph-slot fields
+        build_char_glyph reads; the paddings and the ascent follow freetype.py:150-173."""
+        if key in self.glyphs:
+            return self.glyphs[key]
+        bitmap = np.asarray(bitmap, dtype=np.uint8)
+        assert bitmap.ndim == 2 or (bitmap.ndim == 3 and bitmap.shape[2] == 3)
+        full_width = bitmap.shape[1]
+        trimmed, pad_up, pad_down, pad_left_inc, pad_right_inc = trim_glyph_bitmap(bitmap)
+        # vertical trim first, then the bearings, then the horizontal trim, like the reference
+        pad_left = max(0, bitmap_left)
+        if advance_x is None:
+            pad_right = 0
+        else:
+            pad_right = max(0, round(advance_x / 64) - pad_left - full_width)
+        glyph = AtlasGlyph(key=key, height=trimmed.shape[0], width=trimmed.shape[1],
+                           channels=1 if trimmed.ndim == 2 else 3, gamma=float(gamma),
+                           ascent=bitmap_top - pad_up, pad_up=pad_up, pad_down=pad_down,
+                           pad_left=pad_left + pad_left_inc, pad_right=pad_right + pad_right_inc)
+        self.glyphs[key] = glyph
+        self._pending.append((glyph, np.ascontiguousarray(trimmed)))
+        return glyph
+
+    def _reserve(self, nbytes: int):
+        nbytes = _align(nbytes)
+        if not self.pages or self.cursor + nbytes > self.pages[-1].numel():
+            self.pages.append(dv.empty((max(self.page_bytes, nbytes),), np.uint8))
+            self.cursor = 0
+        page, offset = self.pages[-1], self.cursor
+        self.cursor += nbytes
+        return page, offset
+
+    def commit(self):
+        if not self._pending:
+            return
+        new_gammas = sorted({glyph.gamma for glyph, _ in self._pending} - set(self._luts))
+        # chunk layout: [tables][bitmaps] uploaded, then [masks][alphas][lcd images] derived
+        upload_size = 0
+        lut_at = {}
+        for gamma in new_gammas:
+            lut_at[gamma] = upload_size
+            upload_size += 1024 + 256
+        bitmap_at = []
+        for glyph, bitmap in self._pending:
+            bitmap_at.append(upload_size)
+            upload_size = _align(upload_size + bitmap.nbytes)
+        total = upload_size
+        mask_at, alpha_at, lcd_at = [], [], []
+        for glyph, bitmap in self._pending:
+            pixels = glyph.height * glyph.width
+            mask_at.append(total)
+            total = _align(total + pixels)
+            if glyph.channels == 1:
+                alpha_at.append(total)
+                lcd_at.append(None)
+                total = _align(total + pixels * 4)
+            else:
+                alpha_at.append(None)
+                lcd_at.append(total)
+                total = _align(total + pixels * 3)
+        page, base = self._reserve(total)
+        staging = np.zeros(upload_size, dtype=np.uint8)
+        for gamma in new_gammas:
+            alpha_lut, lcd_lut = self.gamma_tables(gamma)
+            at = lut_at[gamma]
+            staging[at:at + 1024] = alpha_lut.view(np.uint8)
+            staging[at + 1024:at + 1280] = lcd_lut
+            self._luts[gamma] = (DeviceBlob(page, base + at, (1, 256), 256, np.float32),
+                                 DeviceBlob(page, base + at + 1024, (1, 256), 256, np.uint8))
+        for at, (glyph, bitmap) in zip(bitmap_at, self._pending):
+            staging[at:at + bitmap.nbytes] = bitmap.reshape(-1)
+        page[base:base + upload_size].copy_(dv.torch().from_numpy(staging))
+        items = np.zeros(len(self._pending), dtype=nv.GLYPH_ITEM_DTYPE)
+        origin = page.data_ptr() + base
+        for i, (glyph, bitmap) in enumerate(self._pending):
+            shape2 = (glyph.height, glyph.width)
+            shape = shape2 if glyph.channels == 1 else shape2 + (3,)
+            glyph.bitmap = DeviceBlob(page, base + bitmap_at[i], shape, glyph.width, np.uint8)
+            glyph.mask = DeviceBlob(page, base + mask_at[i], shape2, glyph.width, np.uint8)
+            alpha_lut, lcd_lut = self._luts[glyph.gamma]
+            items['bitmap'][i] = origin + bitmap_at[i]
+            items['mask'][i] = origin + mask_at[i]
+            items['n_pixels'][i] = glyph.height * glyph.width
+            items['channels'][i] = glyph.channels
+            if glyph.channels == 1:
+                glyph.alpha = DeviceBlob(page, base + alpha_at[i], shape2, glyph.width, np.float32)
+                items['alpha'][i] = origin + alpha_at[i]
+                items['alpha_lut'][i] = alpha_lut.ptr
+            else:
+                glyph.lcd_image = DeviceBlob(page, base + lcd_at[i], shape, glyph.width, np.uint8)
+                items['lcd_image'][i] = origin + lcd_at[i]
+                items['lcd_lut'][i] = lcd_lut.ptr
+        table = dv.upload_structs(items)
+        nv.check(nv.lib().vkb_glyph_prepare(dv.ptr(table), items.ctypes.data_as(ctypes.c_void_p),
+                                            len(items), dv.stream_ptr()), 'vkb_glyph_prepare')
+        self._pending = []
+
+
+def render_atlas_glyphs_in_text_line(glyph_color: Tuple[int, int, int], text_line_height: int,
+                                     text_line_width: int, glyphs: Sequence[AtlasGlyph],
+                                     char_boxes: Sequence[Box]):
+    """render_char_glyphs_in_text_line (freetype.py:314-380) from atlas glyphs: white line image;
+    default / monochrome glyphs paint `glyph_color` under the glyph mask and merge their alpha
+    into the score map with keep-max; LCD glyphs (H x W x 3 bitmaps) paste their gamma-corrected
+    inverted image under the mask, ignore `glyph_color` and yield no score map.  No glyph pixel
+    crosses the bus: the draw-list items point into the atlas."""
+    assert glyphs and len(glyphs) == len(char_boxes)
+    image = Image(mat=np.full((text_line_height, text_line_width, 3), 255, dtype=np.uint8))
+    mask = Mask(mat=np.zeros((text_line_height, text_line_width), dtype=np.uint8))
+    lcd = glyphs[0].channels == 3
+    score_map = None if lcd else ScoreMap.from_shape((text_line_height, text_line_width))
+    dl_image, dl_mask = DrawList(image), DrawList(mask)
+    dl_score = None if lcd else DrawList(score_map)
+    for glyph, box in zip(glyphs, char_boxes):
+        if glyph.mask is None:
+            raise RuntimeError('GlyphAtlas.commit() has not run for this glyph.')
+        assert (glyph.channels == 3) == lcd and box.shape == glyph.shape
+        if lcd:
+            dl_image.fill(box, glyph.lcd_image, mask=glyph.mask)
+        else:
+            dl_image.fill(box, tuple(glyph_color), mask=glyph.mask)
+            dl_score.fill(box, glyph.alpha, keep_max_value=True)
+        dl_mask.fill(box, 1, mask=glyph.mask)
+    dl_image.flush()
+    dl_mask.flush()
+    if dl_score is not None:
+        dl_score.flush()
+    return image, mask, score_map
+
+
 def render_char_glyphs_in_text_line(glyph_color: Tuple[int, int, int], text_line_height: int,
                                     text_line_width: int, glyph_images: Sequence[np.ndarray],
-                                    glyph_score_maps: Sequence[np.ndarray],
-                                    char_boxes: Sequence[Box]):
-    """Default / monochrome branch of render_char_glyphs_in_text_line (freetype.py:314-353):
-    white line image, glyph colour where the glyph bitmap is non-zero, mask = 1 there, score map
-    merged with keep-max.  Three draw lists, three launches, whatever the number of glyphs."""
+                                    glyph_score_maps: Optional[Sequence[np.ndarray]],
+                                    char_boxes: Sequence[Box], glyph_color_gamma: float = 1.0):
+    """render_char_glyphs_in_text_line (freetype.py:314-380) from host glyph arrays.
+    Default / monochrome branch (2-D glyph images): white line image, glyph colour where the glyph
+    bitmap is non-zero, mask = 1 there, score map merged with keep-max -- three draw lists, three
+    launches, whatever the number of glyphs.  LCD branch (H x W x 3 glyph images,
+    freetype.py:355-370): the glyphs go through a throw-away GlyphAtlas."""
+    if glyph_images[0].ndim == 3:
+        atlas = GlyphAtlas(page_bytes=1 << 20)
+        glyphs = []
+        for i, glyph_image in enumerate(glyph_images):
+            # no trimming here: the caller's char boxes fit the arrays as they are
+            glyph = AtlasGlyph(key=i, height=glyph_image.shape[0], width=glyph_image.shape[1],
+                               channels=3, gamma=float(glyph_color_gamma), ascent=0, pad_up=0,
+                               pad_down=0, pad_left=0, pad_right=0)
+            atlas.glyphs[i] = glyph
+            atlas._pending.append((glyph, np.ascontiguousarray(glyph_image, dtype=np.uint8)))
+            glyphs.append(glyph)
+        atlas.commit()
+        return render_atlas_glyphs_in_text_line(glyph_color, text_line_height, text_line_width,
+                                                glyphs, char_boxes)
     image = Image(mat=np.full((text_line_height, text_line_width, 3), 255, dtype=np.uint8))
     mask = Mask(mat=np.zeros((text_line_height, text_line_width), dtype=np.uint8))
     score_map = ScoreMap.from_shape((text_line_height, text_line_width))
@@ -252,7 +517,7 @@ def resize_page_elements(page_image: Image, masks: Sequence[Mask], height_score_
     score maps (char / text-line) resized to round(ratio * shape) with ONE sampled cv2
     interpolation (NEAREST_EXACT, LINEAR_EXACT, CUBIC, LANCZOS4, or AREA when shrinking --
     utility/opt.py:125-148), the height scores multiplied by the ratio afterwards
-    (page_resizing.py:160-161, 177-180).  Seven device resamples, no host copy.
+    (page_resizing.py:160-161, 177-180).  Seven device resamples (the score scaling inside them), no host copy.
     Returns (image, [masks], [score maps])."""
     height, width = page_image.shape
     resized_height = round(resize_ratio * height)
@@ -268,10 +533,10 @@ def resize_page_elements(page_image: Image, masks: Sequence[Mask], height_score_
     resized_score_maps = []
     for score_map in height_score_maps:
         assert score_map.shape == (height, width)
-        resized = score_map.to_resized_score_map(resized_height=resized_height,
-                                                 resized_width=resized_width,
-                                                 cv_resize_interpolation=cv_resize_interpolation)
-        # "Scores are resized as well": float32 map times the Python float ratio, as NumPy does
-        resized.assign_mat(resized.dev * float(np.float32(resize_ratio)))
-        resized_score_maps.append(resized)
+        # "Scores are resized as well": float32 map times the Python float ratio as NumPy does it
+        # (one float32 product with float32(ratio)), inside the resize kernel
+        resized_score_maps.append(score_map.to_resized_score_map(
+            resized_height=resized_height, resized_width=resized_width,
+            cv_resize_interpolation=cv_resize_interpolation,
+            post_scale=float(np.float32(resize_ratio))))
     return image, resized_masks, resized_score_maps

@@ -804,7 +804,8 @@ __device__ __forceinline__ void resize_cubic_coef_f32(int d, double scale, int& 
 template <int K>
 __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict__ src, int sh, int sw,
                                                          float* __restrict__ dst, int dh, int dw,
-                                                         double scale_x, double scale_y, int clip01) {
+                                                         double scale_x, double scale_y, int clip01,
+                                                         float post) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
         }
     }
     if (clip01 & 1) v = fminf(fmaxf(v, 0.f), 1.f);
-    dst[(long long)y * dw + x] = v;
+    dst[(long long)y * dw + x] = __fmul_rn(v, post);  // post = 1: exact no-op
 }
 
 // ============================================================================================
@@ -951,7 +952,7 @@ template <typename T, int C>
 __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restrict__ src, int sh, int sw,
                                                               T* __restrict__ dst, int dh, int dw,
                                                               double scale_x, double scale_y, int clip01,
-                                                              int mask_thr) {
+                                                              int mask_thr, float post) {
     __shared__ float taps[40][8];
     __shared__ int first[40];
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -1023,7 +1024,7 @@ __global__ void __launch_bounds__(256) resize_lanczos4_kernel(const T* __restric
             for (int j = 1; j < 8; ++j) v = __fadd_rn(v, t[j]);
         }
         if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-        dst[(long long)y * dw + x] = v;
+        dst[(long long)y * dw + x] = __fmul_rn(v, post);
     }
 }
 
@@ -1069,7 +1070,7 @@ template <typename T, int C, bool FAST>
 __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ src, int sh, int sw,
                                                           T* __restrict__ dst, int dh, int dw,
                                                           double scale_x, double scale_y, int isx,
-                                                          int isy, int clip01, int mask_thr) {
+                                                          int isy, int clip01, int mask_thr, float post) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -1115,7 +1116,7 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ 
             }
             v = __fmul_rn(v, scale);
             if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-            d[0] = v;
+            d[0] = __fmul_rn(v, post);
         }
     } else {
         const AreaSpan xs = area_span(x, scale_x, sw);
@@ -1140,7 +1141,7 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const T* __restrict__ 
             } else {
                 float v = acc[c];
                 if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-                d[c] = v;
+                d[c] = __fmul_rn(v, post);
             }
         }
     }
@@ -1155,13 +1156,14 @@ static bool area_is_fast(double scale_x, double scale_y, int& isx, int& isy) {
 
 template <typename T, int C>
 static void launch_resize_area(const T* src, int sh, int sw, T* dst, int dh, int dw, double scale_x,
-                               double scale_y, int clip01, int mask_thr, cudaStream_t st) {
+                               double scale_y, int clip01, int mask_thr, cudaStream_t st,
+                               float post = 1.f) {
     int isx, isy;
     dim3 grid((dw + 31) / 32, (dh + 7) / 8);
     if (area_is_fast(scale_x, scale_y, isx, isy))
-        resize_area_kernel<T, C, true><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr);
+        resize_area_kernel<T, C, true><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr, post);
     else
-        resize_area_kernel<T, C, false><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr);
+        resize_area_kernel<T, C, false><<<grid, dim3(32, 8), 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, isx, isy, clip01, mask_thr, post);
 }
 
 // ============================================================================================
@@ -1916,7 +1918,7 @@ static int resize_u8_impl(const uint8_t* src, int32_t src_h, int32_t src_w, uint
         return check_launch("resize_area_kernel");
     }
     if (interpolation == VKB_INTER_LANCZOS4) {
-#define VKB_L(CH) resize_lanczos4_kernel<uint8_t, CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, mask_thr)
+#define VKB_L(CH) resize_lanczos4_kernel<uint8_t, CH><<<grid, block, 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, 0, mask_thr, 1.f)
         VKB_BY_CHANNELS(VKB_L);
 #undef VKB_L
         return check_launch("resize_lanczos4_kernel");
@@ -1947,9 +1949,9 @@ extern "C" int vkb_resize_mask_u8(const uint8_t* src, int32_t src_h, int32_t src
                           binarization_threshold, stream);
 }
 
-extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst,
-                              int32_t dst_h, int32_t dst_w, int32_t interpolation, int32_t clip01,
-                              void* stream) {
+extern "C" int vkb_resize_f32_scaled(const float* src, int32_t src_h, int32_t src_w, float* dst,
+                                     int32_t dst_h, int32_t dst_w, int32_t interpolation,
+                                     int32_t clip01, float post_scale, void* stream) {
     VKB_REQUIRE(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     VKB_REQUIRE(interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_LINEAR
                     || interpolation == VKB_INTER_CUBIC || interpolation == VKB_INTER_AREA
@@ -1966,20 +1968,27 @@ extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, fl
     if (interpolation == VKB_INTER_NEAREST || interpolation == VKB_INTER_NEAREST_EXACT)
         resize_f32_kernel<1><<<grid, dim3(32, 8), 0, st>>>(
             src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y,
-            clip | (interpolation == VKB_INTER_NEAREST_EXACT ? 2 : 0));
+            clip | (interpolation == VKB_INTER_NEAREST_EXACT ? 2 : 0), post_scale);
     else if (interpolation == VKB_INTER_LINEAR || interpolation == VKB_INTER_LINEAR_EXACT)
         // cv::resize runs INTER_LINEAR for float data when INTER_LINEAR_EXACT is asked for
-        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, post_scale);
     else if (interpolation == VKB_INTER_CUBIC)
-        resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip);
+        resize_f32_kernel<4><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, post_scale);
     else if (interpolation == VKB_INTER_AREA && !(dst_h <= src_h && dst_w <= src_w))
         // an enlarging axis: the bilinear passes with "area mode" fractions
-        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip | 4);
+        resize_f32_kernel<2><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip | 4, post_scale);
     else if (interpolation == VKB_INTER_AREA)
-        launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1, st);
+        launch_resize_area<float, 1>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1, st, post_scale);
     else
-        resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1);
+        resize_lanczos4_kernel<float, 1><<<grid, dim3(32, 8), 0, st>>>(src, src_h, src_w, dst, dst_h, dst_w, scale_x, scale_y, clip, -1, post_scale);
     return check_launch("resize_f32_kernel");
+}
+
+extern "C" int vkb_resize_f32(const float* src, int32_t src_h, int32_t src_w, float* dst,
+                              int32_t dst_h, int32_t dst_w, int32_t interpolation, int32_t clip01,
+                              void* stream) {
+    return vkb_resize_f32_scaled(src, src_h, src_w, dst, dst_h, dst_w, interpolation, clip01, 1.f,
+                                 stream);
 }
 
 extern "C" int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,

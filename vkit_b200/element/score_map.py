@@ -127,12 +127,15 @@ class ScoreMap(DualStorage, Shapable):
     to_conducted_resized_polygon = to_conducted_resized_score_map
 
     def to_resized_score_map(self, resized_height: Optional[int] = None,
-                             resized_width: Optional[int] = None, cv_resize_interpolation: int = 2):
+                             resized_width: Optional[int] = None, cv_resize_interpolation: int = 2,
+                             post_scale: float = 1.0):
         """element/score_map.py:616-637: cv.resize of the float32 map (INTER_CUBIC by default),
         clipped to [0, 1] when it is a probability map -- the clip is fused into the kernel.
         LINEAR / LINEAR_EXACT / CUBIC follow the wheel's default backend (Intel IPP: coordinates and
         taps in double, within 5e-7 of the wheel); the other codes restate cv2's own float32 path
-        bit for bit (vkb_resize_f32)."""
+        bit for bit (vkb_resize_f32).  `post_scale` (not in the reference
+        signature) multiplies the resized float32 values in the same kernel -- page_resizing scales
+        its height maps by the resize ratio right after resizing them (page_resizing.py:160-161)."""
         from .. import _native
         from .opt import generate_shape_and_resized_shape
         assert not self.box
@@ -144,10 +147,10 @@ class ScoreMap(DualStorage, Shapable):
                 'LINEAR_EXACT / NEAREST_EXACT have device kernels')
         src = self.dev
         dst = dv.empty((resized_height, resized_width), np.float32)
-        _native.check(_native.lib().vkb_resize_f32(
+        _native.check(_native.lib().vkb_resize_f32_scaled(
             dv.ptr(src), self.height, self.width, dv.ptr(dst), resized_height, resized_width,
-            self._CV_INTER[cv_resize_interpolation], int(self.is_prob), dv.stream_ptr()),
-            'vkb_resize_f32')
+            self._CV_INTER[cv_resize_interpolation], int(self.is_prob), float(post_scale),
+            dv.stream_ptr()), 'vkb_resize_f32_scaled')
         return attrs.evolve(self, mat=dst, skip_prob_check=True)
 
     def to_cropped_score_map(self, up=None, down=None, left=None, right=None):
