@@ -1387,3 +1387,33 @@ def test_random_distortion_batch_vs_reference(vk, disabled, cases):
                 assert (got_mask != ref_mask).mean() <= 0.01, report
         assert np.abs(r.points - chain_array(case, 'points')).max() <= 1e-3, report
         assert np.abs(np.stack(r.polygons) - chain_array(case, 'polygons')).max() <= 1e-3, report
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('channels', [1, 3, 4])
+def test_gaussian_blur_tma_staging_matches_loop_and_oracle(vk, channels, monkeypatch):
+    """vkb_gaussian_blur_u8 stages interior tiles with a TMA box load when base and pitch are
+    16-byte aligned (VKB_BLUR_NO_TMA=1 keeps the per-thread loop): both forms equal the oracle."""
+    import ctypes
+    import torch
+    from oracle import cv2_model
+    from vkit_b200 import _native as nv, device as dv
+    from vkit_b200.mechanism.distortion.photometric.blur import gaussian_kernel_u8
+    rng = np.random.default_rng(5)
+    for (h, w), (ksize, sigma) in (((96, 64), (3, 0.8)), ((200, 256), (5, 1.0)),
+                                   ((131, 176), (17, 5.0)), ((70, 48), (9, 2.2))):
+        shape = (h, w) if channels == 1 else (h, w, channels)
+        assert (w * channels) % 16 == 0
+        page = rng.integers(0, 256, shape, dtype=np.uint8)
+        src = dv.to_device(page)
+        taps = gaussian_kernel_u8(ksize, sigma)
+        arr = (ctypes.c_int32 * ksize)(*taps)
+        outs = []
+        for flag in ('0', '1'):
+            monkeypatch.setenv('VKB_BLUR_NO_TMA', flag)
+            dst = torch.zeros_like(src)
+            nv.check(nv.lib().vkb_gaussian_blur_u8(dv.ptr(src), dv.ptr(dst), h, w, channels, arr,
+                                                   ksize, dv.stream_ptr()), 'vkb_gaussian_blur_u8')
+            outs.append(dv.to_host(dst))
+        ref = cv2_model.gaussian_blur_u8(page, ksize, sigma)
+        assert np.array_equal(outs[0], ref) and np.array_equal(outs[1], ref), (h, w, ksize)

@@ -10,7 +10,9 @@
 //
 // All of it is byte-stream work bound by HBM bandwidth: one read and one write per pixel,
 // no tensor cores.
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is looked up at run time
 #include <curand_kernel.h>
+#include <cstdlib>
 #include <mutex>
 #include "common.cuh"
 #include "vkb_color.cuh"
@@ -473,6 +475,147 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const uint8_t* __res
             dst[((long long)y * w + x) * C + c] = (uint8_t)min((acc + (1 << 15)) >> 16, 255);
         }
     }
+}
+
+// --------------------------------------------------------------------------------------------
+// The same blur with the tile + halo of INTERIOR tiles staged by one TMA box load
+// (cp.async.bulk.tensor.2d, SASS UTMALDG): the page is described to the copy engine as a 2-D
+// byte tensor [h][w * C]; one elected thread posts the expected byte count on an mbarrier and
+// issues the copy, the other 255 threads skip the per-element reflect-101 / byte-load loop
+// entirely.  Tiles that touch the page border keep the loop (TMA fills out-of-range bytes with
+// zeros, cv2 wants BORDER_REFLECT_101).  Needs a 16-byte aligned base and row pitch; other pages
+// take gaussian_blur_kernel.  The first byte of a box must be 16-byte aligned as well (measured:
+// UTMALDG raises "illegal instruction" otherwise, tools/ubench/tma_probe.cu), and a tile + halo
+// starts at byte (x0 - r) * C: the box therefore starts MIS = (-r * C) mod 16 bytes earlier -- the
+// same for every tile because 32 * C is a multiple of 16 -- and the passes read at that constant
+// offset.  PITCH = bytes per shared-memory tile row = box width = roundup16(MIS + (32 + 2r) * C).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) gaussian_blur_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                const uint8_t* __restrict__ src,
+                                                                uint8_t* __restrict__ dst, int h, int w,
+                                                                const GaussKernel gk, int PITCH, int MIS) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int r = gk.r;
+    const int TW = 32 + 2 * r, TH = 32 + 2 * r;
+    const uint8_t* tile = smem + MIS;                                                // TH x PITCH
+    unsigned short* rows = reinterpret_cast<unsigned short*>(smem + ((TH * PITCH + 15) & ~15));  // TH x 32 x C
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const bool interior = x0 - r >= 0 && y0 - r >= 0 && x0 + 32 + r <= w && y0 + 32 + r <= h;
+    if (interior) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
+                         "r"(TH * PITCH)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+                "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&bar)), "r"((x0 - r) * C - MIS), "r"(y0 - r)
+                : "memory");
+        }
+        __syncthreads();  // the barrier is initialised before anybody polls it
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(smem_u32(&bar)), "r"(0)
+                : "memory");
+        }
+    } else {
+        for (int i = tid; i < TH * TW; i += 256) {
+            const int ty = i / TW, tx = i - ty * TW;
+            const int sy = reflect101(y0 + ty - r, h), sx = reflect101(x0 + tx - r, w);
+            const uint8_t* p = src + ((long long)sy * w + sx) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) smem[MIS + ty * PITCH + tx * C + c] = p[c];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < TH * 32; i += 256) {
+        const int ty = i >> 5, tx = i & 31;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k) acc += (int)tile[ty * PITCH + (tx + k) * C + c] * gk.k[k];
+            rows[i * C + c] = (unsigned short)min(acc, 65535);
+        }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= w) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ly = threadIdx.y + 8 * j;
+        const int y = y0 + ly;
+        if (y >= h) break;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int acc = 0;
+            for (int k = 0; k <= 2 * r; ++k) acc += (int)rows[((ly + k) * 32 + threadIdx.x) * C + c] * gk.k[k];
+            dst[((long long)y * w + x) * C + c] = (uint8_t)min((acc + (1 << 15)) >> 16, 255);
+        }
+    }
+}
+
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                           const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: the library keeps no link
+// dependency on libcuda.so (it must load on machines without a driver for the symbol checks).
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<TensorMapEncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// Returns 1 when the TMA form was launched, 0 when the page does not qualify, < 0 on error.
+static int gaussian_blur_tma(const uint8_t* src, uint8_t* dst, int h, int w, int channels,
+                             const GaussKernel& gk, cudaStream_t st) {
+    const char* off = getenv("VKB_BLUR_NO_TMA");
+    if (off && off[0] == '1') return 0;
+    const long long pitch = (long long)w * channels;
+    if ((pitch & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) return 0;
+    TensorMapEncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return 0;
+    const int TW = 32 + 2 * gk.r;
+    const int mis = (16 - (gk.r * channels) % 16) % 16;
+    const int box_w = (mis + TW * channels + 15) & ~15;
+    if (box_w > 256 || TW > 256) return 0;
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)TW};
+    const cuuint32_t elem[2] = {1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(src), dims, strides, box, elem,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    const size_t smem = (((size_t)TW * box_w + 15) & ~(size_t)15) + (size_t)TW * 32 * channels * 2;
+    dim3 grid((w + 31) / 32, (h + 31) / 32);
+    if (channels == 1) gaussian_blur_tma_kernel<1><<<grid, dim3(32, 8), smem, st>>>(tmap, src, dst, h, w, gk, box_w, mis);
+    else if (channels == 3) gaussian_blur_tma_kernel<3><<<grid, dim3(32, 8), smem, st>>>(tmap, src, dst, h, w, gk, box_w, mis);
+    else gaussian_blur_tma_kernel<4><<<grid, dim3(32, 8), smem, st>>>(tmap, src, dst, h, w, gk, box_w, mis);
+    const int rc = check_launch("gaussian_blur_tma_kernel");
+    return rc == VKB_OK ? 1 : rc;
 }
 
 // ============================================================================================
@@ -1738,10 +1881,12 @@ extern "C" int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h,
     GaussKernel gk;
     gk.r = ksize / 2;
     for (int i = 0; i < ksize; ++i) gk.k[i] = kernel_host[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tma = gaussian_blur_tma(src, dst, h, w, channels, gk, st);
+    if (tma != 0) return tma > 0 ? VKB_OK : tma;
     const int TW = 32 + 2 * gk.r;
     const size_t smem = ((size_t)(TW * TW * channels + 3) & ~(size_t)3) + (size_t)TW * 32 * channels * 2;
     dim3 grid((w + 31) / 32, (h + 31) / 32);
-    cudaStream_t st = (cudaStream_t)stream;
     if (channels == 1) gaussian_blur_kernel<1><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
     else if (channels == 3) gaussian_blur_kernel<3><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
     else gaussian_blur_kernel<4><<<grid, dim3(32, 8), smem, st>>>(src, dst, h, w, gk);
