@@ -371,11 +371,58 @@ def cvt_hsv2rgb_full(hsv):
     return np.clip(np.rint(rgb * f32(255.0)), 0, 255).astype(np.uint8)
 
 
+# RCPPS(d), d = 1..255: x86's 12-bit hardware reciprocal approximation (Intel's table; the values
+# _mm_rcp_ss returns -- generator: oracle/ipp_rcp_table.c).  IPP's RGB -> HLS divides with it.
+IPP_RCP = np.array([
+    0.0,
+    0.999755859, 0.49987793, 0.333251953, 0.249938965, 0.199951172, 0.166625977, 0.142822266,
+    0.124969482, 0.111083984, 0.0999755859, 0.0908966064, 0.0833129883, 0.0769042969, 0.0714111328,
+    0.0666503906, 0.0624847412, 0.058807373, 0.0555419922, 0.0526199341, 0.049987793, 0.0476074219,
+    0.0454483032, 0.04347229, 0.0416564941, 0.0399932861, 0.0384521484, 0.0370330811, 0.0357055664,
+    0.0344772339, 0.0333251953, 0.0322570801, 0.0312423706, 0.0302963257, 0.0294036865, 0.0285644531,
+    0.0277709961, 0.0270195007, 0.026309967, 0.0256347656, 0.0249938965, 0.0243873596, 0.0238037109,
+    0.0232505798, 0.0227241516, 0.0222167969, 0.021736145, 0.0212745667, 0.0208282471, 0.0204048157,
+    0.0199966431, 0.0196037292, 0.0192260742, 0.018863678, 0.0185165405, 0.0181808472, 0.0178527832,
+    0.017539978, 0.0172386169, 0.0169487, 0.0166625977, 0.0163917542, 0.01612854, 0.0158691406,
+    0.0156211853, 0.0153808594, 0.0151481628, 0.0149211884, 0.0147018433, 0.0144901276, 0.0142822266,
+    0.014081955, 0.013885498, 0.0136947632, 0.0135097504, 0.0133304596, 0.0131549835, 0.0129852295,
+    0.0128173828, 0.0126552582, 0.0124969482, 0.012342453, 0.0121936798, 0.012046814, 0.0119018555,
+    0.011762619, 0.0116252899, 0.0114917755, 0.0113620758, 0.0112342834, 0.0111083984, 0.0109863281,
+    0.0108680725, 0.0107517242, 0.0106372833, 0.0105247498, 0.0104141235, 0.010307312, 0.0102024078,
+    0.010099411, 0.00999832153, 0.0098991394, 0.00980186462, 0.00970649719, 0.00961303711, 0.00952148438,
+    0.00943183899, 0.00934410095, 0.00925827026, 0.00917243958, 0.00909042358, 0.00900840759, 0.0089263916,
+    0.00884819031, 0.00876998901, 0.00869369507, 0.00861930847, 0.00854492188, 0.00847434998, 0.00840187073,
+    0.00833129883, 0.00826263428, 0.00819587708, 0.00812911987, 0.00806427002, 0.00799942017, 0.00793457031,
+    0.00787353516, 0.00781059265, 0.00775051117, 0.00769042969, 0.00763130188, 0.00757408142, 0.00751686096,
+    0.00746059418, 0.00740528107, 0.00735092163, 0.00729751587, 0.00724506378, 0.00719261169, 0.00714111328,
+    0.00709056854, 0.00704097748, 0.00699138641, 0.00694274902, 0.00689506531, 0.00684738159, 0.00680160522,
+    0.00675487518, 0.00671005249, 0.0066652298, 0.00662136078, 0.00657749176, 0.00653457642, 0.00649261475,
+    0.00645065308, 0.00640869141, 0.00636768341, 0.00632762909, 0.00628852844, 0.00624847412, 0.00621032715,
+    0.0061712265, 0.0061340332, 0.0060968399, 0.00605964661, 0.00602340698, 0.00598716736, 0.00595092773,
+    0.00591564178, 0.00588130951, 0.00584697723, 0.00581264496, 0.00577926636, 0.00574588776, 0.00571346283,
+    0.0056810379, 0.00564861298, 0.00561714172, 0.00558567047, 0.00555419922, 0.00552368164, 0.00549316406,
+    0.00546360016, 0.00543403625, 0.00540447235, 0.00537586212, 0.00534629822, 0.00531864166, 0.00529003143,
+    0.00526237488, 0.00523471832, 0.00520706177, 0.00518035889, 0.00515365601, 0.00512695312, 0.00510120392,
+    0.00507545471, 0.00504970551, 0.0050239563, 0.00499916077, 0.00497436523, 0.0049495697, 0.00492572784,
+    0.00490093231, 0.00487709045, 0.0048532486, 0.00483036041, 0.00480651855, 0.00478363037, 0.00476074219,
+    0.00473880768, 0.00471591949, 0.00469398499, 0.00467205048, 0.00465011597, 0.00462913513, 0.00460720062,
+    0.00458621979, 0.00456523895, 0.00454521179, 0.00452423096, 0.0045042038, 0.00448322296, 0.0044631958,
+    0.00444412231, 0.00442409515, 0.00440502167, 0.00438499451, 0.00436592102, 0.00434684753, 0.00432872772,
+    0.00430965424, 0.00429153442, 0.00427246094, 0.00425434113, 0.00423717499, 0.00421905518, 0.00420093536,
+    0.00418376923, 0.00416564941, 0.00414848328, 0.00413131714, 0.00411510468, 0.00409793854, 0.0040807724,
+    0.00406455994, 0.00404834747, 0.00403213501, 0.00401592255, 0.00399971008, 0.00398349762, 0.00396728516,
+    0.00395202637, 0.00393676758, 0.00392150879,
+], dtype=np.float32)
+
+
 def cvt_rgb2hls_full(rgb):
     """cv.cvtColor(uint8, COLOR_RGB2HLS_FULL) as the default (IPP) backend of the 4.13 wheel
-    computes it: hue scale 255/360; L = round_half_even((max + min) / 2) EXACTLY (all 32 896
-    (max, min) pairs); H and S through float32, within +-1 of cv2 (whose own result depends on
-    the IPP / SIMD / scalar backend)."""
+    computes it, bit exact on all 2^24 colours (test_cvt_hls_full_colour_cube):
+      L = round_half_even((max + min) / 2);
+      S = rint(diff * RCPPS(den) * 255) with den = max + min when <= 255, else 510 - (max + min);
+      H = rint(h * 42.5), h = (g - b) * RCPPS(diff) (+ 2 / + 4 when green / blue is the maximum,
+          tested in the order R, G, B), + 6 when negative, 256 wraps to 0; float32 products.
+    (OpenCV's own path -- cv.ipp.setUseIPP(False) -- differs from this on 60 % of the colours.)"""
     f32 = np.float32
     ri = rgb[..., 0].astype(np.int64)
     gi = rgb[..., 1].astype(np.int64)
@@ -383,30 +430,28 @@ def cvt_rgb2hls_full(rgb):
     imax = np.maximum(np.maximum(ri, gi), bi)
     imin = np.minimum(np.minimum(ri, gi), bi)
     isum = imax + imin
+    diff = imax - imin
     half = isum >> 1
     l_int = np.where((isum & 1) == 0, half, half + (half & 1))
-    x = rgb.astype(f32) * f32(1.0 / 255.0)
-    r, g, b = x[..., 0], x[..., 1], x[..., 2]
-    vmax = np.maximum(np.maximum(r, g), b)
-    vmin = np.minimum(np.minimum(r, g), b)
-    diff = vmax - vmin
-    l = (vmax + vmin) * f32(0.5)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        s = np.where(l < f32(0.5), diff / (vmax + vmin), diff / (f32(2.0) - vmax - vmin))
-        d = f32(60.0) / diff
-        h = np.where(vmax == r, (g - b) * d,
-                     np.where(vmax == g, (b - r) * d + f32(120.0), (r - g) * d + f32(240.0)))
-    h = np.where(h < 0, h + f32(360.0), h)
-    zero = diff <= np.finfo(f32).eps
-    h = np.where(zero, f32(0), h)
-    s = np.where(zero, f32(0), s)
-    hs = np.stack([h * f32(255.0 / 360.0), s * f32(255.0)], axis=-1)
-    hs = np.clip(np.rint(hs), 0, 255).astype(np.int64)
-    return np.stack([hs[..., 0], l_int, hs[..., 1]], axis=-1).astype(np.uint8)
+    den = np.where(isum <= 255, isum, 510 - isum)
+    s_int = np.rint((diff.astype(f32) * IPP_RCP[den]) * f32(255.0)).astype(np.int64)
+    rd = IPP_RCP[diff]
+    h = np.where(imax == ri, (gi - bi).astype(f32) * rd,
+                 np.where(imax == gi, (bi - ri).astype(f32) * rd + f32(2.0),
+                          (ri - gi).astype(f32) * rd + f32(4.0))).astype(f32)
+    h = np.where(h < 0, h + f32(6.0), h).astype(f32)
+    h_int = np.rint(h * f32(42.5)).astype(np.int64)
+    h_int = np.where(h_int >= 256, h_int - 256, h_int)
+    zero = diff == 0
+    h_int = np.where(zero, 0, h_int)
+    s_int = np.where(zero, 0, s_int)
+    return np.stack([h_int, l_int, s_int], axis=-1).astype(np.uint8)
 
 
 def cvt_hls2rgb_full(hls):
-    """cv.cvtColor(uint8, COLOR_HLS2RGB_FULL): float32 path, hue scale 6/255."""
+    """cv.cvtColor(uint8, COLOR_HLS2RGB_FULL): float32 path, hue scale 6/255.  Equal to OpenCV's own
+    path on all 2^24 HLS triples and to the wheel's default (IPP) on all but 20 of them (+-1 in
+    one channel, float32 ties)."""
     f32 = np.float32
     h = hls[..., 0].astype(f32) * f32(6.0 / 255.0)
     l = hls[..., 1].astype(f32) * f32(1.0 / 255.0)

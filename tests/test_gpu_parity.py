@@ -215,7 +215,8 @@ def test_photometric_vs_golden(vk, case):
         ref = golden_array(case, 'image')
         diff = np.abs(got.astype(int) - ref.astype(int))
         if case['op'] == 'brightness_shift' and case['config']['intermediate_image_mode'] == 'hsl':
-            assert (diff > 0).mean() <= 0.03 and (diff > 1).mean() <= 0.006 and diff.max() <= 8
+            # RGB -> HLS exact (IPP's RCPPS form), HLS -> RGB off on 20 of 2^24 triples
+            assert diff.max() <= 1 and (diff > 0).mean() <= 2e-5
         else:
             assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3
     elif case['op'] == 'std_shift':

@@ -90,13 +90,12 @@ def test_colour_conversions_all_colours():
     assert _same(cm.cvt_rgb2hsv_full(grid), cv.cvtColor(grid, cv.COLOR_RGB2HSV_FULL))
     assert _same(cm.cvt_rgb2gray(grid), cv.cvtColor(grid, cv.COLOR_RGB2GRAY))
     for model, code, max_bad in ((cm.cvt_hsv2rgb_full, cv.COLOR_HSV2RGB_FULL, 200),
-                                 (cm.cvt_hls2rgb_full, cv.COLOR_HLS2RGB_FULL, 200)):
+                                 (cm.cvt_hls2rgb_full, cv.COLOR_HLS2RGB_FULL, 32)):
         diff = np.abs(model(grid).astype(int) - cv.cvtColor(grid, code).astype(int))
         assert diff.max() <= 1 and (diff > 0).any(axis=-1).sum() <= max_bad
-    got = cm.cvt_rgb2hls_full(grid).astype(int)
-    ref = cv.cvtColor(grid, cv.COLOR_RGB2HLS_FULL).astype(int)
-    assert np.array_equal(got[..., 1], ref[..., 1])  # L exact
-    assert np.abs(got - ref).max() <= 1  # H, S within 1 (IPP backend)
+    # RGB -> HLS_FULL: the wheel's IPP routine, reciprocals by RCPPS -- all 2^24 colours exact
+    # (needs the x86 host the fixtures were made on: Intel's RCPPS table is part of the model)
+    assert _same(cm.cvt_rgb2hls_full(grid), cv.cvtColor(grid, cv.COLOR_RGB2HLS_FULL))
 
 
 def test_camera_functions(rng):

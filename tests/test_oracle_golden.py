@@ -157,9 +157,9 @@ def test_photometric(case):
         diff = np.abs(got.astype(int) - ref.astype(int))
         via_hls = case['op'] == 'brightness_shift' and case['config']['intermediate_image_mode'] == 'hsl'
         if via_hls:
-            # RGB<->HLS goes through Intel IPP inside cv2 (closed source, backend dependent):
-            # L is exact, H/S +-1, which the inverse conversion can amplify on dark pixels.
-            assert (diff > 0).mean() <= 0.03 and (diff > 1).mean() <= 0.006 and diff.max() <= 8
+            # RGB -> HLS is IPP's routine (reciprocals by RCPPS), modelled exactly; HLS -> RGB
+            # differs from the wheel on 20 of the 2^24 HLS triples (float32 ties, +-1)
+            assert diff.max() <= 1 and (diff > 0).mean() <= 2e-5, f'max diff {diff.max()}' 
         else:
             assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3, f'max diff {diff.max()}'
     else:
