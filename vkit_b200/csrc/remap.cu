@@ -447,13 +447,23 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 //   Tiles without candidates and bands without owners are filled with the value of map (0, 0).
 // ============================================================================================
 #ifndef VKB_TILES_BLOCKS
-#define VKB_TILES_BLOCKS 3
+#define VKB_TILES_BLOCKS 4
 #endif
+// Resident blocks per SM: 4 x 8 warps at <= 64 registers (measured 1.503 -> 1.447 ms per 256 pages
+// against 3 blocks at 80 registers: the extra warps hide more of the tap-load latency); the
+// image + mask + score map variants would spill at 64 registers and keep 3.
+template <int C, bool MASK, bool SCORE>
+constexpr int tiles_blocks_per_sm() {
+    return (C >= 3 && MASK && SCORE) ? 3 : VKB_TILES_BLOCKS;
+}
 constexpr int kTilesWarps = 8;
 constexpr int kTilesHalf = 16;                  // records per half: [0] = the zero map, 1..15 candidates
 constexpr int kTilesSlots = 2 * kTilesHalf;
 #ifndef VKB_TILES_FREE_STORE
 #define VKB_TILES_FREE_STORE 1
+#endif
+#ifndef VKB_TILES_ROWS
+#define VKB_TILES_ROWS 4  // rows of a band one lane carries through coordinates -> gather together (4 or 2)
 #endif
 #ifndef VKB_TILES_CHUNK
 #define VKB_TILES_CHUNK 1
@@ -519,7 +529,7 @@ __device__ __noinline__ void remap_pixel_exact(const RemapPage pg, const double*
 }
 
 template <int C, bool MASK, bool SCORE>
-__global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap_tiles_kernel(
+__global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK, SCORE>())) grid_remap_tiles_kernel(
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
     int c_max, int p_max, const double* __restrict__ hinv, const uint32_t* __restrict__ cell_masks,
     const int32_t* __restrict__ tile_base, const RemapTile* __restrict__ headers,
@@ -747,39 +757,46 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
                 continue;
             }
             // ---- coordinates ------------------------------------------------------------
-            int X[4], Y[4];
+            constexpr int R = VKB_TILES_ROWS;
+            static_assert(R == 4 || R == 2, "VKB_TILES_ROWS must be 4 or 2");
+#pragma unroll 1
+            for (int sub = 0; sub < 4 / R; ++sub) {
+            const int jb = sub * R;  // first row of the sub-band inside the band
+            if (R < 4 && ry0 + jb >= pg.dst_h) break;
+            int X[R], Y[R];
             uint32_t fail4 = 0;
-            const float yr0 = (float)(band * 4);
+            const float yr0 = (float)(band * 4 + jb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < R; ++j) {
                 // bits j, j+4, j+8, j+12 of `own` -> a 4-bit number (the partial products of
                 // the multiplication land on distinct bits: no carries)
-                const uint32_t id = (((own >> j) & 0x1111u) * 0x12480000u) >> 28;
+                const uint32_t id = (((own >> (jb + j)) & 0x1111u) * 0x12480000u) >> 28;
                 const TileSlot* __restrict__ sp = S + id;
                 const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
                 const bool ok = cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y, t_odd,
                                                 t_even, X[j], Y[j]);
                 fail4 |= ok ? 0u : (1u << j);
             }
-            failbits |= fail4 << (band * 4);
+            failbits |= fail4 << (band * 4 + jb);
             // rows of the band this thread stores: the ones inside the page.  (A pixel that waits
             // for the exact path is stored here all the same and overwritten after the band loop
             // by this very thread, in program order: no predicate per pixel for it.)  Bands that
             // lie inside the page completely -- warp uniform, nearly all of them -- store
             // without any predicate.
-            const int rows_in = pg.dst_h - ry0;  // >= 1
+            const int rows_in = pg.dst_h - (ry0 + jb);  // >= 1
+            constexpr uint32_t kAllRows = (1u << R) - 1u;
 #if VKB_TILES_FREE_STORE
-            const bool interior = tile_in_x && rows_in >= 4;
-            const uint32_t live = x_in ? (rows_in >= 4 ? 0xFu : ((1u << rows_in) - 1u)) : 0u;
+            const bool interior = tile_in_x && rows_in >= R;
+            const uint32_t live = x_in ? (rows_in >= R ? kAllRows : ((1u << rows_in) - 1u)) : 0u;
 #else
             const bool interior = false;
-            const uint32_t live = x_in ? (~fail4 & (rows_in >= 4 ? 0xFu : ((1u << rows_in) - 1u))) : 0u;
+            const uint32_t live = x_in ? (~fail4 & (rows_in >= R ? kAllRows : ((1u << rows_in) - 1u))) : 0u;
 #endif
             // ---- gather -------------------------------------------------------------------
-            const int di0 = ry0 * pg.dst_w + x;
+            const int di0 = (ry0 + jb) * pg.dst_w + x;
             if (tiny) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < R; ++j) {
                     if (!((live >> j) & 1u)) continue;
                     const int di = di0 + j * pg.dst_w;
                     if (C > 0) {
@@ -794,40 +811,40 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
                 }
                 continue;
             }
-            Tap2 tap[4];
+            Tap2 tap[R];
             bool outside = false;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < R; ++j) {
                 tap[j] = tap2_plain(X[j], Y[j]);
                 outside |= tap2_outside(tap[j], pg.src_h, pg.src_w);
             }
             if (outside) {  // rare: footprints that leave the image, all behind one branch
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < R; ++j)
                     if (tap2_outside(tap[j], pg.src_h, pg.src_w)) tap[j] = tap2_border(X[j], Y[j], pg.src_h, pg.src_w);
             }
             if (C > 0) {
-                Fetch2<CC> f[4];
+                Fetch2<CC> f[R];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fetch2_request<CC>(img_words, img_mis, img_pitch, tap[j], f[j]);
-                uint32_t v[4][CC];
+                for (int j = 0; j < R; ++j) fetch2_request<CC>(img_words, img_mis, img_pitch, tap[j], f[j]);
+                uint32_t v[R][CC];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fetch2_blend<CC>(f[j], tap[j], v[j]);
+                for (int j = 0; j < R; ++j) fetch2_blend<CC>(f[j], tap[j], v[j]);
                 if (interior) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) store_px(di0 + j * pg.dst_w, v[j]);
+                    for (int j = 0; j < R; ++j) store_px(di0 + j * pg.dst_w, v[j]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < R; ++j)
                         if ((live >> j) & 1u) store_px(di0 + j * pg.dst_w, v[j]);
                 }
             }
             if (MASK) {
-                Fetch2<1> f[4];
+                Fetch2<1> f[R];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fetch2_request<1>(mask_words, mask_mis, pg.src_w, tap[j], f[j]);
+                for (int j = 0; j < R; ++j) fetch2_request<1>(mask_words, mask_mis, pg.src_w, tap[j], f[j]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < R; ++j) {
                     uint32_t v[1];
                     fetch2_blend<1>(f[j], tap[j], v);
                     if ((live >> j) & 1u) pg.dst_mask[di0 + j * pg.dst_w] = (uint8_t)v[0];
@@ -835,11 +852,12 @@ __global__ void __launch_bounds__(32 * kTilesWarps, VKB_TILES_BLOCKS) grid_remap
             }
             if (SCORE) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < R; ++j) {
                     const float v = bilinear_f32(pg.src_score, pg.src_h, pg.src_w, pg.src_w, X[j], Y[j]);
                     if ((live >> j) & 1u) pg.dst_score[di0 + j * pg.dst_w] = v;
                 }
             }
+            }  // sub-band
         }  // band
 
         // ---- the flagged pixels, float64 coordinates (q0 .. q3 are back in place: 8 x 4 bits) ----
@@ -924,7 +942,6 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     constexpr int R = VKB_REMAP_ROWS;
     constexpr int kBlocksPerSm = VKB_REMAP_BLOCKS;
     const int grid = remap_grid_blocks(kBlocksPerSm);
-    const int tiles_grid = remap_grid_blocks(VKB_TILES_BLOCKS);
     // VKB_REMAP_V1=1 keeps the first-generation small-tile kernel (A/B measurements only)
     static const bool use_v1 = getenv("VKB_REMAP_V1") != nullptr && getenv("VKB_REMAP_V1")[0] == '1';
 #define VKB_LAUNCH_REMAP_1(CH, M, S, LARGE)                                                     \
@@ -951,7 +968,8 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
         if (use_v1) {                                                                           \
             VKB_LAUNCH_REMAP_1(CH, M, S, false);                                                \
         } else {                                                                                \
-            grid_remap_tiles_kernel<CH, M, S><<<tiles_grid, 32 * kTilesWarps, 0, st>>>(         \
+            grid_remap_tiles_kernel<CH, M, S><<<remap_grid_blocks(tiles_blocks_per_sm<CH, M, S>()), \
+                                              32 * kTilesWarps, 0, st>>>(                       \
                 planes, pages, n_pages, c_max, p_max, hinv, cell_masks, tile_base,              \
                 reinterpret_cast<const RemapTile*>(tile_headers),                               \
                 reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, work_counter);        \
