@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
 //   outline   lane = (cell, edge): the lane walks its edge like cv::LineIterator (edge_walk: one
 //             add and one compare per pixel) and ORs the pixels into the cell's row words in
 //             shared memory; the four scan-edge records of the cell are set up on the way;
-//   fill      lane = (cell, row), the rows of the eight cells back to back: crossings of the four
-//             scan edges, 5-exchange sort, spans, OR with the outline word, one store per row.
+//   fill      lane = (cell, row mod 4): crossings of the four scan edges (kept in registers),
+//             5-exchange sort, spans, OR with the outline word, one store per row.
 //
 // ~100 warp instructions per cell; the first generation (warp per cell, lane per row, closed-form
 // outline per row) spent ~500 and was the second most expensive kernel of the step.
@@ -461,7 +461,6 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
     const int32_t* __restrict__ lattice_i, uint32_t* __restrict__ cell_masks) {
     __shared__ uint32_t sm_rows[kMaskWarps][kMaskCells][VKB_CELL_MASK_WORDS];
     __shared__ EdgeScan sm_scan[kMaskWarps][kMaskCells][4];
-    __shared__ int2 sm_org[kMaskWarps][kMaskCells];  // bbox origin (x0, y0)
     const int page = blockIdx.y;
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
@@ -502,7 +501,6 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
         EdgeScan es;
         edge_scan_setup(ux, uy, vx, vy, es);
         sm_scan[warp][k8][e] = es;
-        if (e == 0) sm_org[warp][k8] = make_int2(x0, y0);
     }
     __syncwarp();  // the zeroed rows are visible before the first OR
     if (nrows) {
@@ -511,23 +509,16 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
     }
     __syncwarp();
 
-    // ---- lane = (cell, row): the rows of the eight cells back to back -------------------------
-    int first[kMaskCells + 1];  // first[k]: rows before cell k
-    first[0] = 0;
+    // ---- lane = (cell, row mod 4): the four lanes of a cell take its rows in turn; the cell's scan
+    //      edges stay in registers for all of them (a linearised (cell, row) list balanced the lanes
+    //      better but paid 17 % of the kernel's instructions for finding its cell per row)
+    if (nrows) {
+        EdgeScan es4[4];
 #pragma unroll
-    for (int k = 0; k < kMaskCells; ++k) first[k + 1] = first[k] + __shfl_sync(0xffffffffu, nrows, 4 * k);
-    const int total = first[kMaskCells];
-    for (int p = lane; p < total; p += 32) {
-        int k = 0;
-#pragma unroll
-        for (int i = 1; i < kMaskCells; ++i) k += p >= first[i] ? 1 : 0;
-        int before = 0;
-#pragma unroll
-        for (int i = 1; i < kMaskCells; ++i) before = (i <= k) ? first[i] : before;
-        const int row = p - before;
-        const int2 org = sm_org[warp][k];
-        const uint32_t word = sm_rows[warp][k][row] | quad_fill_row(sm_scan[warp][k], org.y + row, org.x);
-        cell_masks[((size_t)page * c_max + cell0 + k) * VKB_CELL_MASK_WORDS + row] = word;
+        for (int i = 0; i < 4; ++i) es4[i] = sm_scan[warp][k8][i];
+        const uint32_t* rows = sm_rows[warp][k8];
+        uint32_t* out = cell_masks + ((size_t)page * c_max + cell) * VKB_CELL_MASK_WORDS;
+        for (int row = e; row < nrows; row += 4) out[row] = rows[row] | quad_fill_row(es4, y0 + row, x0);
     }
 }
 
