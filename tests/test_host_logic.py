@@ -270,3 +270,18 @@ def test_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_vectorised_gaussian_taps_equal_scalar():
+    """PhotometricBatch builds the 8.8 fixed-point taps of all pages at once: same integers as the
+    per-page form for every kernel size."""
+    from vkit_b200.mechanism.distortion.photometric import blur
+    rng = np.random.default_rng(3)
+    sigmas = np.concatenate([rng.uniform(0.3, 5.6, 4000), [0.5, 1.0, 1.5, 2.5, 5.0]])
+    ksizes, taps = blur.gaussian_kernels_u8(sigmas)
+    for i, sigma in enumerate(sigmas):
+        ksize = blur._estimate_gaussian_kernel_size(float(sigma))
+        assert ksizes[i] == ksize
+        if ksize <= 17:
+            assert list(taps[i, :ksize]) == blur.gaussian_kernel_u8(ksize, float(sigma))
+            assert not taps[i, ksize:].any()

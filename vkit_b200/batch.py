@@ -774,14 +774,12 @@ class PhotometricBatch:
                 continue
             if name == 'gaussian_blur':
                 flush()
-                for i, config in enumerate(configs):
-                    config = dyn_structure(config, _blur.GaussianBlurConfig)
-                    ksize = _blur._estimate_gaussian_kernel_size(config.sigma)
-                    if ksize > 17:
-                        raise NotImplementedError('gaussian_blur kernels wider than 17 taps')
-                    taps = _blur.gaussian_kernel_u8(ksize, config.sigma)
-                    rec['blur_radius'][i] = ksize // 2
-                    rec['blur_taps'][i, :ksize] = taps
+                sigmas = [dyn_structure(config, _blur.GaussianBlurConfig).sigma for config in configs]
+                ksizes, taps = _blur.gaussian_kernels_u8(sigmas)  # all pages at once
+                if (ksizes > 17).any():
+                    raise NotImplementedError('gaussian_blur kernels wider than 17 taps')
+                rec['blur_radius'] = ksizes // 2
+                rec['blur_taps'] = taps
                 dirty = True
                 continue
             stats = None

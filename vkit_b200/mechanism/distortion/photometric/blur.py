@@ -1,7 +1,7 @@
 """Blur ops (vkit/mechanism/distortion/photometric/blur.py).  gaussian_blur runs as a separable
 8.8 fixed-point shared-memory stencil that reproduces cv.GaussianBlur on uint8 bit-exactly."""
 import ctypes
-from typing import Any, Mapping, Optional
+from typing import Tuple, Any, Mapping, Optional
 
 import attrs
 import numpy as np
@@ -38,6 +38,35 @@ def gaussian_kernel_u8(ksize: int, sigma: float):
         taps[i] = taps[ksize - 1 - i] = int(v)
     taps[r] = 256 - sum(taps)
     return taps
+
+
+def gaussian_kernels_u8(sigmas) -> Tuple[np.ndarray, np.ndarray]:
+    """gaussian_kernel_u8 for many pages at once (batched chains build one tap row per page):
+    returns (ksizes, taps) with taps[i, :ksizes[i]] the integer taps of page i.  Same float64
+    operations per element as the scalar form, vectorised over the pages of each kernel size
+    (tests/test_host_logic.py compares the two on random sigmas)."""
+    sigmas = np.asarray(sigmas, dtype=np.float64)
+    ksizes = np.asarray([_estimate_gaussian_kernel_size(float(s)) for s in sigmas], dtype=np.int64)
+    taps = np.zeros((sigmas.shape[0], 17), dtype=np.int32)
+    for ksize in np.unique(ksizes):
+        ksize = int(ksize)
+        if ksize > 17:
+            continue  # the caller rejects these
+        sel = np.flatnonzero(ksizes == ksize)
+        r = ksize // 2
+        xs = np.arange(ksize, dtype=np.float64) - r
+        k = np.exp(-(xs * xs)[None, :] / (2.0 * sigmas[sel] * sigmas[sel])[:, None])
+        k = k / k.sum(axis=1)[:, None]
+        out = np.zeros((sel.shape[0], ksize), dtype=np.int64)
+        err = np.zeros(sel.shape[0], dtype=np.float64)
+        for i in range(r):
+            adj = k[:, i] * 256.0 + err
+            v = np.rint(adj)
+            err = adj - v
+            out[:, i] = out[:, ksize - 1 - i] = v.astype(np.int64)
+        out[:, r] = 256 - out.sum(axis=1)
+        taps[sel, :ksize] = out
+    return ksizes, taps
 
 
 def gaussian_blur_device(image: Image, sigma: float) -> Image:
