@@ -1418,3 +1418,28 @@ def test_gaussian_blur_tma_staging_matches_loop_and_oracle(vk, channels, monkeyp
             outs.append(dv.to_host(dst))
         ref = cv2_model.gaussian_blur_u8(page, ksize, sigma)
         assert np.array_equal(outs[0], ref) and np.array_equal(outs[1], ref), (h, w, ksize)
+
+
+def test_mls_projection_generations_agree(vk, monkeypatch):
+    """The thread-per-point MLS projection reduces the handles in the same order as the
+    warp-per-point one (butterfly tree): the float64 lattice values must be bit-identical, on the
+    policy's configs at several levels, on odd page shapes and on an exact handle hit."""
+    import torch
+    from vkit_b200.batch import GeometricBatch
+    from vkit_b200.mechanism.distortion_policy.geometric.mls import similarity_mls_policy_factory
+    policy = similarity_mls_policy_factory.create()
+    for shape, seed in (((1024, 1024), 1), ((600, 337), 2), ((136, 176), 3)):
+        rng = np.random.default_rng(seed)
+        configs = []
+        for level in (1, 3, 5, 8, 10, 10):
+            generator = policy.config_generator_cls(policy.config_for_config_generator, level)
+            configs.append(generator(shape, rng))
+        lattices = []
+        for flag in ('1', '0'):
+            monkeypatch.setenv('VKB_MLS_V1', flag)
+            engine = GeometricBatch(['similarity_mls'] * len(configs), configs, shape)
+            plan = engine.plan_batch()
+            torch.cuda.synchronize()
+            lattices.append(plan.lattice_f.cpu().numpy().copy())
+        assert lattices[0].shape == lattices[1].shape
+        assert np.array_equal(lattices[0].view(np.uint64), lattices[1].view(np.uint64)), shape

@@ -12,6 +12,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
+#include <cstdlib>
 #include "common.cuh"
 #include "vkb_math.cuh"
 #include "vkb_lattice.cuh"
@@ -203,6 +204,139 @@ __global__ void __launch_bounds__(256) grid_project_mls_kernel(
         out[0] = (double)__fadd_rn(sx / mu, qcx);
         out[1] = (double)__fadd_rn(sy / mu, qcy);
     }
+}
+
+// The same projection with ONE THREAD per lattice point (second generation, the default).  The
+// warp-per-point form above spends ~415 warp instructions per point, most of them on lanes without
+// a handle and on 8 x 5 shuffle steps; here a thread walks the handles itself and reduces them in
+// the SAME order as the butterfly did, so the float32 results are bit-identical
+// (tests/test_gpu_parity.py::test_mls_projection_generations_agree): lane L of the old kernel
+// accumulated handles L, L + 32, ... and the xor butterfly then added the 32 lane values as a
+// perfect binary tree over the lanes in bit-reversed order -- that tree is evaluated with a
+// five-level merge stack while the slots are visited in bit-reversed order.
+constexpr int kMlsSmemHandles = 64;
+
+template <int R>
+struct MlsTree {
+    float st[R][5];
+    float total[R];
+    // slot number `k` of the bit-reversed visit carries the values v[0..R-1]
+    __device__ __forceinline__ void push(int k, const float* v) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            float x = v[q];
+            bool placed = false;
+#pragma unroll
+            for (int lev = 0; lev < 5; ++lev) {
+                if (placed) continue;
+                if ((k >> lev) & 1) {
+                    x = st[q][lev] + x;
+                } else {
+                    st[q][lev] = x;
+                    placed = true;
+                }
+            }
+            if (!placed) total[q] = x;  // k == 31
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) grid_project_mls_points_kernel(
+    const vkb_grid_page* __restrict__ pages, int p_max, double* __restrict__ lattice_f) {
+    __shared__ float s_hs[2 * kMlsSmemHandles], s_hd[2 * kMlsSmemHandles];
+    const vkb_grid_page& pg = pages[blockIdx.y];
+    if (pg.projector != VKB_PROJ_MLS) return;  // block uniform
+    const int n = pg.n_handles;
+    for (int i = threadIdx.x; i < 2 * min(n, kMlsSmemHandles); i += blockDim.x) {
+        s_hs[i] = pg.handles_src[i];
+        s_hd[i] = pg.handles_dst[i];
+    }
+    __syncthreads();
+    const int P = pg.rows * pg.cols;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= P) return;
+    const float* __restrict__ g_hs = pg.handles_src;
+    const float* __restrict__ g_hd = pg.handles_dst;
+    auto hs = [&](int j) { return j < 2 * kMlsSmemHandles ? s_hs[j] : g_hs[j]; };
+    auto hd = [&](int j) { return j < 2 * kMlsSmemHandles ? s_hd[j] : g_hd[j]; };
+    const int r = pt / pg.cols, c = pt - r * pg.cols;
+    const float vx = (float)lattice_coord(c, pg.src_w, pg.grid_size);
+    const float vy = (float)lattice_coord(r, pg.src_h, pg.grid_size);
+    double* out = lattice_f + ((size_t)blockIdx.y * p_max + pt) * 2;
+
+    // pass 0: sum of the inverse squared distances; an exact hit returns the handle's target
+    // (the lowest slot with a hit wins, inside a slot the last one: the old kernel's ballot)
+    int hit = -1;
+    MlsTree<1> t0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int L = (int)(__brev((unsigned)k) >> 27);
+        float sum_inv = 0.f;
+        int slot_hit = -1;
+        for (int i = L; i < n; i += 32) {
+            const float dx = hs(2 * i) - vx, dy = hs(2 * i + 1) - vy;
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (d2 == 0.f) slot_hit = i;
+            else sum_inv += 1.0f / d2;
+        }
+        if (slot_hit >= 0 && (hit < 0 || L < (hit & 31))) hit = slot_hit;
+        t0.push(k, &sum_inv);
+    }
+    if (hit >= 0) {
+        out[0] = (double)hd(2 * hit);
+        out[1] = (double)hd(2 * hit + 1);
+        return;
+    }
+    const float sum_inv = t0.total[0];
+
+    // pass 1: weighted centroids of the source and target handles
+    MlsTree<4> t1;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int L = (int)(__brev((unsigned)k) >> 27);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = L; i < n; i += 32) {
+            const float px = hs(2 * i), py = hs(2 * i + 1);
+            const float dx = px - vx, dy = py - vy;
+            const float inv = 1.0f / __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const float w = inv / sum_inv;
+            v[0] = __fmaf_rn(w, px, v[0]);
+            v[1] = __fmaf_rn(w, py, v[1]);
+            v[2] = __fmaf_rn(w, hd(2 * i), v[2]);
+            v[3] = __fmaf_rn(w, hd(2 * i + 1), v[3]);
+        }
+        t1.push(k, v);
+    }
+    const float pcx = t1.total[0], pcy = t1.total[1], qcx = t1.total[2], qcy = t1.total[3];
+    const float ax = __fsub_rn(vx, pcx), ay = __fsub_rn(vy, pcy);
+
+    // pass 2: mu and the 2-vector sum
+    MlsTree<3> t2;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int L = (int)(__brev((unsigned)k) >> 27);
+        float v[3] = {0.f, 0.f, 0.f};  // sx, sy, mu
+        for (int i = L; i < n; i += 32) {
+            const float px = hs(2 * i), py = hs(2 * i + 1);
+            const float dx = px - vx, dy = py - vy;
+            const float inv = 1.0f / __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const float hx = __fsub_rn(px, pcx), hy = __fsub_rn(py, pcy);
+            const float qx = __fsub_rn(hd(2 * i), qcx), qy = __fsub_rn(hd(2 * i + 1), qcy);
+            const float r00 = __fmaf_rn(hy, ay, __fmul_rn(hx, ax));
+            const float r01 = __fmaf_rn(hy, -ax, __fmul_rn(hx, ay));
+            const float r10 = __fmaf_rn(-hx, ay, __fmul_rn(hy, ax));
+            const float r11 = __fmaf_rn(-hx, -ax, __fmul_rn(hy, ay));
+            const float m00 = __fmul_rn(inv, r00), m01 = __fmul_rn(inv, r01);
+            const float m10 = __fmul_rn(inv, r10), m11 = __fmul_rn(inv, r11);
+            v[0] += __fadd_rn(__fmul_rn(qx, m00), __fmul_rn(qy, m10));
+            v[1] += __fadd_rn(__fmul_rn(qx, m01), __fmul_rn(qy, m11));
+            v[2] += __fmul_rn(inv, __fadd_rn(__fmul_rn(hx, hx), __fmul_rn(hy, hy)));
+        }
+        t2.push(k, v);
+    }
+    const float sx = t2.total[0], sy = t2.total[1], mu = t2.total[2];
+    out[0] = (double)__fadd_rn(sx / mu, qcx);
+    out[1] = (double)__fadd_rn(sy / mu, qcy);
 }
 
 // ============================================================================================
@@ -1123,9 +1257,16 @@ extern "C" int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int
         if (rc) return rc;
     }
     if (projectors & (1 << VKB_PROJ_MLS)) {
-        grid_project_mls_kernel<<<dim3((p_max + 7) / 8, n_pages), 256, 0, (cudaStream_t)stream>>>(
-            pages, p_max, lattice_f);
-        return check_launch("grid_project_mls_kernel");
+        // VKB_MLS_V1=1 keeps the warp-per-point generation (A/B tests)
+        const char* v1 = getenv("VKB_MLS_V1");
+        if (v1 && v1[0] == '1') {
+            grid_project_mls_kernel<<<dim3((p_max + 7) / 8, n_pages), 256, 0, (cudaStream_t)stream>>>(
+                pages, p_max, lattice_f);
+            return check_launch("grid_project_mls_kernel");
+        }
+        grid_project_mls_points_kernel<<<dim3((p_max + 127) / 128, n_pages), 128, 0,
+                                         (cudaStream_t)stream>>>(pages, p_max, lattice_f);
+        return check_launch("grid_project_mls_points_kernel");
     }
     return VKB_OK;
 }
