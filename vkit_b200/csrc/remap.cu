@@ -456,6 +456,22 @@ template <int C, bool MASK, bool SCORE>
 constexpr int tiles_blocks_per_sm() {
     return (C >= 3 && MASK && SCORE) ? 3 : VKB_TILES_BLOCKS;
 }
+// Blocks per SM the launch actually uses (VKB_TILES_GRID_BLOCKS or the environment variable of the
+// same name, experiments): fewer than the resident limit leaves block slots to kernels of other
+// streams that run next to this persistent one.
+#ifndef VKB_TILES_GRID_BLOCKS
+#define VKB_TILES_GRID_BLOCKS 0
+#endif
+template <int C, bool MASK, bool SCORE>
+static int tiles_grid_blocks_per_sm() {
+    static const int from_env = [] {
+        const char* e = getenv("VKB_TILES_GRID_BLOCKS");
+        return e ? atoi(e) : 0;
+    }();
+    const int cap = tiles_blocks_per_sm<C, MASK, SCORE>();
+    const int want = from_env > 0 ? from_env : (VKB_TILES_GRID_BLOCKS > 0 ? VKB_TILES_GRID_BLOCKS : cap);
+    return want < cap ? want : cap;
+}
 constexpr int kTilesWarps = 8;
 constexpr int kTilesHalf = 16;                  // records per half: [0] = the zero map, 1..15 candidates
 constexpr int kTilesSlots = 2 * kTilesHalf;
@@ -968,7 +984,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
         if (use_v1) {                                                                           \
             VKB_LAUNCH_REMAP_1(CH, M, S, false);                                                \
         } else {                                                                                \
-            grid_remap_tiles_kernel<CH, M, S><<<remap_grid_blocks(tiles_blocks_per_sm<CH, M, S>()), \
+            grid_remap_tiles_kernel<CH, M, S><<<remap_grid_blocks(tiles_grid_blocks_per_sm<CH, M, S>()), \
                                               32 * kTilesWarps, 0, st>>>(                       \
                 planes, pages, n_pages, c_max, p_max, hinv, cell_masks, tile_base,              \
                 reinterpret_cast<const RemapTile*>(tile_headers),                               \
