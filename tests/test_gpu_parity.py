@@ -1443,3 +1443,56 @@ def test_mls_projection_generations_agree(vk, monkeypatch):
             lattices.append(plan.lattice_f.cpu().numpy().copy())
         assert lattices[0].shape == lattices[1].shape
         assert np.array_equal(lattices[0].view(np.uint64), lattices[1].view(np.uint64)), shape
+
+
+@pytest.mark.parametrize('op', ['camera_cubic_curve', 'camera_plane_line_fold'])
+def test_remap_container_and_channel_variants_vs_oracle(vk, op):
+    """Every instantiation of the fused remap (image with 1 / 3 / 4 channels, mask, score map and
+    their combinations -- 4 resident blocks per SM, 3 for the three-container variants) against
+    the oracle on a page whose sides are no multiples of the tile size."""
+    from oracle import vkit_port as port
+    element, distortion = vk
+    shape = (203, 245)
+    rng = np.random.default_rng(77)
+    config = {'curve_alpha': 22.0, 'curve_beta': -14.0, 'curve_direction': 25.0, 'curve_scale': 1.0,
+              'camera_model_config': {'rotation_unit_vec': [0.9, 0.4, 0.15], 'rotation_theta': 21},
+              'grid_size': 12}
+    if op == 'camera_plane_line_fold':
+        config = {'fold_point': [120.0, 90.0], 'fold_direction': 35.0, 'fold_perturb_vec': [0.4, 0.2, 60.0],
+                  'fold_alpha': 0.9,
+                  'camera_model_config': {'rotation_unit_vec': [0.3, 0.9, 0.2], 'rotation_theta': 17},
+                  'grid_size': 12}
+    gray = rng.integers(0, 256, shape, dtype=np.uint8)
+    rgb = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    rgba = rng.integers(0, 256, shape + (4,), dtype=np.uint8)
+    mask = (rng.random(shape) > 0.5).astype(np.uint8)
+    score = rng.random(shape).astype(np.float32)
+    port.use_cv2(False)
+    ref_cache = {}
+
+    def ref_of(key, mat):
+        if key not in ref_cache:
+            kind = 'score_map' if mat.dtype == np.float32 else ('mask' if key == 'mask' else 'image')
+            ref_cache[key] = port.grid_distort(op, config, shape, **{kind: mat})[kind]
+        return ref_cache[key]
+
+    images = {'gray': gray, 'rgb': rgb, 'rgba': rgba}
+    combos = [(img, use_mask, use_score) for img in (None, 'gray', 'rgb', 'rgba')
+              for use_mask in (False, True) for use_score in (False, True)
+              if img or use_mask or use_score]
+    for img, use_mask, use_score in combos:
+        kwargs = {}
+        if img:
+            kwargs['image'] = element.Image(mat=images[img])
+        if use_mask:
+            kwargs['mask'] = element.Mask(mat=mask)
+        if use_score:
+            kwargs['score_map'] = element.ScoreMap(mat=score)
+        r = getattr(distortion, op).distort(dict(config), **kwargs)
+        where = (op, img, use_mask, use_score)
+        if img:
+            assert np.array_equal(r.image.mat, ref_of(img, images[img])), where
+        if use_mask:
+            assert np.array_equal(r.mask.mat, ref_of('mask', mask)), where
+        if use_score:
+            assert np.array_equal(r.score_map.mat, ref_of('score', score)), where
