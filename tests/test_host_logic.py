@@ -285,3 +285,98 @@ def test_vectorised_gaussian_taps_equal_scalar():
         if ksize <= 17:
             assert list(taps[i, :ksize]) == blur.gaussian_kernel_u8(ksize, float(sigma))
             assert not taps[i, ksize:].any()
+
+
+def test_glass_swap_maps_equal_plain_restatement():
+    """The strided-view form of the glass_blur permutation against a literal restatement of the
+    reference's loop (vkit/mechanism/distortion/photometric/blur.py:232-262): same maps, same
+    generator state afterwards."""
+    from vkit_b200.mechanism.distortion.photometric.blur import glass_swap_maps
+
+    def plain(shape, delta, loop, rng):
+        height, width = shape
+        pos_x, pos_y = np.meshgrid(np.arange(width), np.arange(height))
+        period = 2 * delta + 1
+        for _ in range(loop):
+            rows = np.arange(rng.integers(0, period), height - delta, period).reshape(-1, 1)
+            cols = np.arange(rng.integers(0, period), width - delta, period).reshape(1, -1)
+            grid_shape = (rows.shape[0], cols.shape[1])
+            shift_y = rng.integers(-delta, delta + 1, grid_shape)
+            shift_x = rng.integers(-delta, delta + 1, grid_shape)
+            target_y = np.clip(pos_y[rows, cols] + shift_y, 0, height - 1)
+            target_x = np.clip(pos_x[rows, cols] + shift_x, 0, width - 1)
+            for pos in (pos_y, pos_x):
+                at_centre, at_target = pos[rows, cols], pos[target_y, target_x]
+                pos[rows, cols] = at_target
+                pos[target_y, target_x] = at_centre
+        return pos_y, pos_x
+
+    for shape, delta, loop in (((257, 300), 1, 5), ((64, 64), 3, 4), ((5, 7), 1, 2),
+                               ((33, 500), 2, 6), ((1, 9), 1, 3)):
+        a_rng, b_rng = np.random.default_rng(5), np.random.default_rng(5)
+        ref = plain(shape, delta, loop, a_rng)
+        got = glass_swap_maps(shape, delta, loop, b_rng)
+        assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1]), shape
+        assert a_rng.integers(0, 1 << 30) == b_rng.integers(0, 1 << 30)
+
+
+def test_diamond_square_mask_equals_plain_restatement():
+    """The slice-based fog field against the literal np.roll restatement of the reference
+    (vkit/mechanism/distortion/photometric/effect.py:89-146): same float32 field, same generator
+    state afterwards."""
+    from vkit_b200.mechanism.distortion.photometric.effect import generate_diamond_square_mask
+
+    def _midpoint_level(sums, weight, rng):
+        """One displacement level: mean of the four neighbours damped by (1 - weight) plus
+        weight * U(0, 1).  The dtype sequence is the reference's (float32 sums, float64 draws)."""
+        return (1 - weight) * sums / 4 + weight * rng.uniform(0, 1, sums.shape)
+
+
+    def plain_mask(shape, roughness, rng):
+        """Diamond-square plasma field cropped to `shape` (effect.py:89-146); consumes `rng` exactly
+        like the reference: 4 corner draws, then per level the diamond draw, the two square draws,
+        and finally the crop offsets."""
+        assert 0.0 <= roughness <= 1.0
+        height, width = shape
+        size = int(2**np.ceil(np.log2(max(height, width))) + 1)
+        field = np.zeros((size, size), dtype=np.float32)
+        for corner in ((0, 0), (0, -1), (-1, -1), (-1, 0)):
+            field[corner] = rng.uniform(0.0, 1.0)
+
+        step, level = size - 1, 0
+        while step >= 2:
+            weight = roughness**level
+            half = step // 2
+            corners = field[0:size:step, 0:size:step]
+            down_pairs = corners + np.roll(corners, shift=-1, axis=0)
+            right_pairs = corners + np.roll(corners, shift=-1, axis=1)
+
+            # centres of the squares
+            centres = _midpoint_level((down_pairs + right_pairs)[:-1, :-1], weight, rng)
+            field[half:size:step, half:size:step] = centres
+
+            # edge midpoints on the corner rows: left/right corners + centres above/below (wrapping)
+            above_below = centres + np.roll(centres, shift=1, axis=0)
+            above_below = np.vstack([above_below, above_below[0]])
+            field[0:size:step, half:size:step] = _midpoint_level(right_pairs[:, :-1] + above_below,
+                                                                 weight, rng)
+
+            # edge midpoints on the corner columns
+            left_right = centres + np.roll(centres, shift=1, axis=1)
+            left_right = np.hstack([left_right, left_right[0].reshape(-1, 1)])
+            field[half:size:step, 0:size:step] = _midpoint_level(down_pairs[:-1] + left_right, weight,
+                                                                 rng)
+            level += 1
+            step = half
+
+        up = rng.integers(0, size - height + 1)
+        left = rng.integers(0, size - width + 1)
+        return field[up:up + height, left:left + width]
+
+    for shape, roughness in (((257, 300), 0.6), ((64, 96), 0.9), ((100, 133), 0.3), ((5, 3), 0.7),
+                             ((2, 2), 0.5), ((1, 1), 0.5), ((513, 40), 0.0), ((40, 513), 1.0)):
+        a_rng, b_rng = np.random.default_rng(11), np.random.default_rng(11)
+        ref = plain_mask(shape, roughness, a_rng)
+        got = generate_diamond_square_mask(shape, roughness, b_rng)
+        assert ref.dtype == got.dtype and np.array_equal(ref, got), shape
+        assert a_rng.integers(0, 1 << 30) == b_rng.integers(0, 1 << 30)

@@ -282,24 +282,28 @@ class GlassBlurConfig(DistortionConfig):
 
 
 def glass_swap_maps(shape, delta: int, loop: int, rng: RandomGenerator):
-    """The pixel permutation of glass_blur as two index maps (blur.py:232-262): `loop` rounds in
-    which every (2*delta+1)-th pixel trades places with a random neighbour.  Drawn on the host from
-    the caller's generator -- it is the random field of the op; duplicates among the targets
-    resolve like NumPy's fancy assignment (the last writer in C order wins)."""
+    """The pixel permutation of glass_blur as two int32 index maps (blur.py:232-262): `loop` rounds
+    in which every (2*delta+1)-th pixel trades places with a random neighbour OF THE PIXEL THAT
+    CURRENTLY SITS THERE.  Drawn on the host from the caller's generator -- it is the random field
+    of the op; duplicates among the targets resolve like NumPy's fancy assignment (the last writer
+    in C order wins).  The centres form a regular sub-grid, so they are strided views; only the
+    ~(H / period) x (W / period) targets go through fancy indexing."""
     height, width = shape
-    pos_x, pos_y = np.meshgrid(np.arange(width), np.arange(height))
+    pos_y = np.broadcast_to(np.arange(height, dtype=np.int32)[:, None], (height, width)).copy()
+    pos_x = np.broadcast_to(np.arange(width, dtype=np.int32)[None, :], (height, width)).copy()
     period = 2 * delta + 1
     for _ in range(loop):
-        rows = np.arange(rng.integers(0, period), height - delta, period).reshape(-1, 1)
-        cols = np.arange(rng.integers(0, period), width - delta, period).reshape(1, -1)
-        grid_shape = (rows.shape[0], cols.shape[1])
+        row0 = int(rng.integers(0, period))
+        col0 = int(rng.integers(0, period))
+        centres = (slice(row0, height - delta, period), slice(col0, width - delta, period))
+        grid_shape = pos_y[centres].shape
         shift_y = rng.integers(-delta, delta + 1, grid_shape)
         shift_x = rng.integers(-delta, delta + 1, grid_shape)
-        target_y = np.clip(pos_y[rows, cols] + shift_y, 0, height - 1)
-        target_x = np.clip(pos_x[rows, cols] + shift_x, 0, width - 1)
+        target_y = np.clip(pos_y[centres] + shift_y, 0, height - 1)
+        target_x = np.clip(pos_x[centres] + shift_x, 0, width - 1)
         for pos in (pos_y, pos_x):
-            at_centre, at_target = pos[rows, cols], pos[target_y, target_x]
-            pos[rows, cols] = at_target
+            at_centre, at_target = pos[centres].copy(), pos[target_y, target_x]
+            pos[centres] = at_target
             pos[target_y, target_x] = at_centre
     return pos_y, pos_x
 

@@ -86,16 +86,14 @@ pixelation = Distortion(config_cls=PixelationConfig,
                         func_image=pixelation_image)
 
 
-def _midpoint_level(sums: np.ndarray, weight: float, rng: RandomGenerator) -> np.ndarray:
-    """One displacement level: mean of the four neighbours damped by (1 - weight) plus
-    weight * U(0, 1).  The dtype sequence is the reference's (float32 sums, float64 draws)."""
-    return (1 - weight) * sums / 4 + weight * rng.uniform(0, 1, sums.shape)
-
-
 def generate_diamond_square_mask(shape: Tuple[int, int], roughness: float, rng: RandomGenerator):
     """Diamond-square plasma field cropped to `shape` (effect.py:89-146); consumes `rng` exactly
     like the reference: 4 corner draws, then per level the diamond draw, the two square draws,
-    and finally the crop offsets."""
+    and finally the crop offsets.  Every displacement is `(1 - weight) * sums / 4 + weight * U(0, 1)`
+    with the reference's dtype sequence (float32 corner sums, float64 centres and draws, float32
+    field); the neighbour sums are slices instead of np.roll copies, same additions.  One quirk is
+    kept on purpose: for the column midpoints the reference closes the wrapped sums with the first
+    ROW of `left_right` (`left_right[0].reshape(-1, 1)`, effect.py:131-133), not its first column."""
     assert 0.0 <= roughness <= 1.0
     height, width = shape
     size = int(2**np.ceil(np.log2(max(height, width))) + 1)
@@ -106,26 +104,32 @@ def generate_diamond_square_mask(shape: Tuple[int, int], roughness: float, rng: 
     step, level = size - 1, 0
     while step >= 2:
         weight = roughness**level
+        keep = 1 - weight
         half = step // 2
         corners = field[0:size:step, 0:size:step]
-        down_pairs = corners + np.roll(corners, shift=-1, axis=0)
-        right_pairs = corners + np.roll(corners, shift=-1, axis=1)
+        down = corners[:-1] + corners[1:]          # corner + the corner below
+        right = corners[:, :-1] + corners[:, 1:]   # corner + the corner to the right
+        m = down.shape[0]
 
         # centres of the squares
-        centres = _midpoint_level((down_pairs + right_pairs)[:-1, :-1], weight, rng)
+        centres = keep * (down[:, :-1] + right[:-1]) / 4 + weight * rng.uniform(0, 1, (m, m))
         field[half:size:step, half:size:step] = centres
 
-        # edge midpoints on the corner rows: left/right corners + centres above/below (wrapping)
-        above_below = centres + np.roll(centres, shift=1, axis=0)
-        above_below = np.vstack([above_below, above_below[0]])
-        field[0:size:step, half:size:step] = _midpoint_level(right_pairs[:, :-1] + above_below,
-                                                             weight, rng)
+        # edge midpoints on the corner rows: left / right corners + centres above / below (wrapping)
+        above_below = np.empty((m + 1, m), dtype=centres.dtype)
+        above_below[1:m] = centres[1:] + centres[:-1]
+        above_below[0] = centres[0] + centres[-1]
+        above_below[m] = above_below[0]
+        field[0:size:step, half:size:step] = (keep * (right + above_below) / 4
+                                              + weight * rng.uniform(0, 1, above_below.shape))
 
         # edge midpoints on the corner columns
-        left_right = centres + np.roll(centres, shift=1, axis=1)
-        left_right = np.hstack([left_right, left_right[0].reshape(-1, 1)])
-        field[half:size:step, 0:size:step] = _midpoint_level(down_pairs[:-1] + left_right, weight,
-                                                             rng)
+        left_right = np.empty((m, m + 1), dtype=centres.dtype)
+        left_right[:, 1:m] = centres[:, 1:] + centres[:, :-1]
+        left_right[:, 0] = centres[:, 0] + centres[:, -1]
+        left_right[:, m] = left_right[0, :m]  # (sic) the first row, see the docstring
+        field[half:size:step, 0:size:step] = (keep * (down + left_right) / 4
+                                              + weight * rng.uniform(0, 1, left_right.shape))
         level += 1
         step = half
 
