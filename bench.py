@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- synthesized 1024x1024 pages/s through the B200 distortion path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
 --config 2 (default; BASELINE.json configs[1], the configuration the metric is quoted on):
     batch = 256 pages of 1024x1024 RGB per GPU, one camera_* op per page cycling plane_only /
@@ -9,6 +9,8 @@
     output layout -> per-cell homographies + coverage masks + tile bins + candidate records ->
     fused remap.
 --config 3 (configs[2]): similarity_mls -> gaussian_blur -> color_shift, batch = 1024 pages per GPU.
+--config 4 (configs[3]): page pipeline -- background synthesis, atlas glyph text lines, alpha blend,
+    RandomDistortion over the batch, label rasterisation (host bound; wall-clock timed).
 --config 5 (configs[4]): mixed-resolution sweep 256 .. 4096 px, fixed 10-op chain, batch sharded.
 
 Configs come from the reference's policy generators with the per-page generator
@@ -403,6 +405,17 @@ def workload_config(config_id: int, world: int, batch: int):
             'l2': f'inputs ({batch * 3} MB per batch) larger than L2 (126 MB); no flush needed',
             'seed': BASE_SEED,
         }
+    if config_id == 4:
+        return {
+            'workload': 'text-detection page pipeline: background synthesis + 16 text lines x 24 '
+                        'atlas glyphs rendered and alpha-blended + RandomDistortion (default policy '
+                        'set, post rotate) on image, mask, 256 points, 16 polygons + label '
+                        f'rasterisation, 1024x1024 RGB uint8, batch {batch} pages per GPU',
+            'batch_per_gpu': batch, 'page_shape': list(PAGE_SHAPE),
+            'parallelism': f'page-sharded x{world} (no data-path collective)',
+            'l2': 'pages are produced and consumed on the device; every stage streams them once',
+            'seed': BASE_SEED,
+        }
     if config_id == 5:
         return {
             'workload': 'mixed-resolution sweep 256..4096 px, 10-op chain ' + ' -> '.join(CHAIN5_OPS)
@@ -647,6 +660,153 @@ class Workload3:
         return stats, len(tasks) / wall, wall, per_page, len(tasks)
 
 
+def run_config4(args, rank, world, local_rank, dist):
+    """config 4 (BASELINE configs[3]): the text-detection page pipeline around the distortion
+    path, per page -- background synthesis (ImageCombiner: skyline walk on the host, one fused
+    launch), 16 text lines of 24 glyphs each rendered from the device glyph atlas, blended onto the
+    page through their score maps (one draw-list launch), then RandomDistortion (the pipeline's
+    default policy set, post-rotate forced) over the whole batch of image + mask + 256 points +
+    16 text-line polygons, and the label rasterisation of the distorted polygons (text-line mask
+    and height score map).  FreeType itself is not available here: the atlas is filled with
+    synthetic coverage bitmaps once, outside the timed region.  Host bound by design of the
+    workload (a few hundred small launches and Python objects per page)."""
+    import torch
+    from vkit_b200 import compositing as comp
+    from vkit_b200.background import ImageCombiner, ImageCombinerConfig, Texture
+    from vkit_b200.element import Image, Mask, ScoreMap
+    from vkit_b200.mechanism.distortion_policy import random_distortion_factory
+    from vkit_b200.mechanism.distortion_policy.random_distortion_batch import RandomDistortionBatch
+
+    batch = args.batch or 64
+    n_lines, n_glyphs, n_points = 16, 24, 256
+    height, width = PAGE_SHAPE
+    gen = np.random.default_rng(BASE_SEED + 4)
+    # textures of the background combiner (device resident after the first use)
+    textures = []
+    for k in range(12):
+        th, tw = (int(v) for v in gen.integers(160, 420, 2))
+        base = gen.integers(120, 250, 3)
+        mat = np.clip(base[None, None, :] + gen.integers(-10, 11, (th, tw, 3)), 0, 255).astype(np.uint8)
+        gray = mat.mean(axis=2)
+        textures.append(Texture(f'tex{k}', Image(mat=mat), float(gray.mean()), float(gray.std())))
+    combiner = ImageCombiner(textures, ImageCombinerConfig(prob_use_only_the_anchor_image=0.5))
+    # glyph atlas: 96 synthetic coverage bitmaps, 20 - 28 px tall
+    atlas = comp.GlyphAtlas()
+    glyph_keys = []
+    for k in range(96):
+        gh, gw = int(gen.integers(20, 29)), int(gen.integers(10, 22))
+        bitmap = gen.integers(0, 256, (gh, gw))
+        bitmap[gen.random((gh, gw)) < 0.45] = 0
+        bitmap[0, 0] = bitmap[-1, -1] = 255
+        atlas.add(k, bitmap.astype(np.uint8), gamma=1.0)
+        glyph_keys.append(k)
+    atlas.commit()
+    rd = random_distortion_factory.create({'disabled_policy_names': ['defocus_blur', 'zoom_in_blur'],
+                                           'force_post_rotate': True})
+    engine = RandomDistortionBatch(rd)
+    masks = torch.ones((batch, height, width), dtype=torch.uint8, device='cuda')
+    seqs = np.random.SeedSequence(BASE_SEED + 40).spawn(batch * world * 64)
+    counters = {'launch_groups': 0}
+
+    def step(k):
+        rngs = [np.random.default_rng(s)
+                for s in seqs[(k * world + rank) * batch:(k * world + rank + 1) * batch]]
+        page_images, points, polygons = [], [], []
+        for rng in rngs:
+            page = combiner.run(height, width, rng)
+            line_boxes = np.empty((n_lines, 4), dtype=np.int64)
+            alpha_ptrs = np.empty(n_lines, dtype=np.uint64)
+            colors = rng.integers(0, 160, (n_lines, 3))
+            keep, polys = [], []
+            line_specs = []
+            for li in range(n_lines):
+                picks = rng.integers(0, len(glyph_keys), n_glyphs)
+                glyphs = [atlas[glyph_keys[int(p)]] for p in picks]
+                line_h = 32
+                ups = rng.integers(0, [line_h - g.height + 1 for g in glyphs])
+                widths = np.asarray([g.width for g in glyphs])
+                lefts = 1 + np.concatenate([[0], np.cumsum(widths[:-1] + 1)])
+                line_w = int(lefts[-1] + widths[-1] + 2)
+                line_specs.append((tuple(int(c) for c in colors[li]), line_h, line_w, glyphs,
+                                   np.stack([ups, lefts], axis=1)))
+            # all lines of the page: three launches (image, score map, mask planes)
+            rendered = comp.render_atlas_text_lines(line_specs)
+            for li, (_, line_h, line_w, _, _) in enumerate(line_specs):
+                score_map = rendered[li][2]
+                up = 16 + li * 62
+                left = int(rng.integers(8, max(9, width - line_w - 8)))
+                line_boxes[li] = (up, left, line_h, line_w)
+                alpha_ptrs[li] = score_map.dev.data_ptr()
+                keep.append(score_map)
+                polys.append(np.asarray([(left, up), (left + line_w - 1, up),
+                                         (left + line_w - 1, up + line_h - 1),
+                                         (left, up + line_h - 1)], dtype=np.float64))
+            # the text lines onto the page: alpha = their score maps, one ordered launch
+            keep.append(comp._launch_glyph_items(page, line_boxes, value_const=colors,
+                                                 alpha_ptrs=alpha_ptrs,
+                                                 alpha_pitches=line_boxes[:, 3]))
+            page_images.append(page.dev)
+            points.append(rng.uniform(0, height - 1, (n_points, 2)))
+            polygons.append(polys)
+        images = torch.stack(page_images)
+        results = engine.distort(rngs, images, masks, points, polygons)
+        labels = []
+        for r in results:
+            line_mask = comp.fill_polygons(Mask(mat=torch.zeros(r.shape, dtype=torch.uint8,
+                                                                 device='cuda')), r.polygons, 1)
+            heights = [float(10 + j % 30) for j in range(len(r.polygons))]
+            height_map = comp.fill_polygons(
+                ScoreMap(mat=torch.zeros(r.shape, dtype=torch.float32, device='cuda'),
+                         is_prob=False), r.polygons, heights)
+            labels.append((line_mask, height_map))
+        return results, labels
+
+    for k in range(max(1, min(args.warmup, 2))):
+        step(k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        results, labels = step(8 + k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = 1000.0 * (time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
+    stats = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms = float(stats.cpu()[0])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        out_px = sum(r.shape[0] * r.shape[1] for r in results)
+        # page written once, read + written by the text blend, image + mask through two
+        # geometric stages (read + write each), two label planes written
+        alg = batch * height * width * (3 + 6 + 2 * 8) + out_px * (1 + 4)
+        line = {
+            'metric': METRIC, 'value': batch * world / (ms * 1e-3), 'unit': 'pages/s',
+            'n_gpus': world, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)),
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u8', 'data': 'synthetic', 'config': workload_config(4, world, batch),
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'whole page pipeline (host bound)',
+                         'achieved': alg / ms / 1e6, 'peak': peak, 'unit': 'GB/s',
+                         'frac': alg / ms / 1e6 / peak, 'traffic': None, 'peak_source': peak_src,
+                         'note': 'algorithmic bytes of the page pipeline / wall time of a step; the '
+                                 'step is bound by the host (Python objects and a few hundred small '
+                                 'launches per page), not by HBM'},
+            'e2e': None, 'cpu_baseline': None,
+            'note': 'timed with the wall clock around whole steps (host bound); glyph bitmaps are '
+                    'synthetic (no FreeType in this image); pinned by tests/test_pre_compositing.py '
+                    '(background, atlas, text lines) and the RandomDistortion fixtures, not gated here',
+        }
+        print(json.dumps(line), flush=True)
+
+
 def run_config5(args, rank, world, local_rank, dist):
     """config 5: per-size batched 10-op chain; one JSON line, per-size numbers inside."""
     import torch
@@ -760,7 +920,7 @@ def main():
     parser.add_argument('--steps', type=int, default=20)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    parser.add_argument('--config', type=int, default=2, choices=[2, 3, 5])
+    parser.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5])
     parser.add_argument('--batch', type=int, default=None)
     parser.add_argument('--skip-cpu-baseline', action='store_true',
                         help='no oracle leg: neither the parity gate nor the CPU baseline')
@@ -789,6 +949,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
+    if args.config == 4:
+        run_config4(args, rank, world, local_rank, dist)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if args.config == 5:
         run_config5(args, rank, world, local_rank, dist)
         if dist is not None:

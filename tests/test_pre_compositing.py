@@ -176,3 +176,35 @@ def test_lcd_text_line_from_host_arrays():
         glyph_color_gamma=case['gamma'])
     assert score_map is None
     assert sha(image.mat) == case['sha']['image'] and sha(mask.mat) == case['sha']['mask']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('lcd', [False, True])
+def test_batched_text_lines_match_reference(lcd):
+    """All text lines of a page through three launches (render_atlas_text_lines): every line equals
+    the live-reference fixture of its case."""
+    from vkit_b200.compositing import GlyphAtlas, render_atlas_text_lines
+    from vkit_b200.element import Box
+    cases = [c for c in TEXT_LINES if c['lcd'] == lcd]
+    atlas = GlyphAtlas(page_bytes=1 << 18)
+    lines = []
+    for case in cases:
+        bitmaps = f4_glyph_bitmaps(case['seed'], case['count'], case['lcd'])
+        glyphs = [atlas.add((case['id'], j), bitmap, gamma=case['gamma'], bitmap_top=top,
+                            bitmap_left=left, advance_x=advance_x)
+                  for j, (bitmap, top, left, advance_x) in enumerate(bitmaps)]
+        boxes = [Box(up=b[0], down=b[1], left=b[2], right=b[3]) for b in case['boxes']]
+        if case is cases[-1]:  # the array form of the boxes: (up, left) per glyph
+            boxes = np.asarray([(b[0], b[2]) for b in case['boxes']])
+        height, width = case['line_shape']
+        lines.append((tuple(case['glyph_color']), height, width, glyphs, boxes))
+    atlas.commit()
+    rendered = render_atlas_text_lines(lines)
+    assert len(rendered) == len(cases)
+    for case, (image, mask, score_map) in zip(cases, rendered):
+        assert sha(image.mat) == case['sha']['image'], case['id']
+        assert sha(mask.mat) == case['sha']['mask'], case['id']
+        if lcd:
+            assert score_map is None
+        else:
+            assert sha(score_map.mat) == case['sha']['score_map'], case['id']

@@ -364,6 +364,38 @@ class GlyphAtlas:
         self._pending = []
 
 
+def _launch_glyph_items(target, boxes_yxhw: np.ndarray, *, value_const=None, value_ptrs=None,
+                        value_pitches=None, mask_ptrs=None, mask_pitches=None, alpha_ptrs=None,
+                        alpha_pitches=None, keep_max: bool = False):
+    """One ordered draw-list launch whose items all point at device-resident planes: the item table
+    is filled column by column (no per-item Python objects)."""
+    n = boxes_yxhw.shape[0]
+    items = np.zeros(n, dtype=nv.BLEND_ITEM_DTYPE)
+    dst = target.dev
+    items['dst'] = dst.data_ptr()
+    items['dst_f32'] = int(target.mat_dtype == np.float32)
+    items['channels'] = 1 if target.mat_ndim == 2 else target.mat_shape[2]
+    items['dst_w'] = target.width
+    items['box_y'], items['box_x'] = boxes_yxhw[:, 0], boxes_yxhw[:, 1]
+    items['box_h'], items['box_w'] = boxes_yxhw[:, 2], boxes_yxhw[:, 3]
+    items['alpha'] = 1.0
+    if value_const is not None:  # one tuple for all items or one row per item
+        consts = np.asarray(value_const).astype(np.float32 if items['dst_f32'][0] else np.uint8)
+        items['value_const'][:, :consts.shape[-1]] = consts.astype(np.float32)
+    if value_ptrs is not None:
+        items['value_arr'], items['value_pitch'] = value_ptrs, value_pitches
+    if mask_ptrs is not None:
+        items['mask'], items['mask_pitch'] = mask_ptrs, mask_pitches
+    if alpha_ptrs is not None:
+        items['alpha_arr'], items['alpha_pitch'] = alpha_ptrs, alpha_pitches
+    items['keep_mode'] = 1 if keep_max else 0
+    table = dv.upload_structs(items)
+    nv.check(nv.lib().vkb_blend_draw_list(dv.ptr(table), n, target.height, target.width,
+                                          dv.stream_ptr()), 'vkb_blend_draw_list')
+    target._after_device_write()
+    return table
+
+
 def render_atlas_glyphs_in_text_line(glyph_color: Tuple[int, int, int], text_line_height: int,
                                      text_line_width: int, glyphs: Sequence[AtlasGlyph],
                                      char_boxes: Sequence[Box]):
@@ -371,29 +403,136 @@ def render_atlas_glyphs_in_text_line(glyph_color: Tuple[int, int, int], text_lin
     default / monochrome glyphs paint `glyph_color` under the glyph mask and merge their alpha
     into the score map with keep-max; LCD glyphs (H x W x 3 bitmaps) paste their gamma-corrected
     inverted image under the mask, ignore `glyph_color` and yield no score map.  No glyph pixel
-    crosses the bus: the draw-list items point into the atlas."""
+    crosses the bus: the draw-list items point into the atlas; three launches per line (two for
+    LCD), their item tables built as arrays."""
     assert glyphs and len(glyphs) == len(char_boxes)
-    image = Image(mat=np.full((text_line_height, text_line_width, 3), 255, dtype=np.uint8))
-    mask = Mask(mat=np.zeros((text_line_height, text_line_width), dtype=np.uint8))
+    t = dv.require_cuda()
+    device = dv.device()
+    image = Image(mat=t.full((text_line_height, text_line_width, 3), 255, dtype=t.uint8,
+                             device=device))
+    mask = Mask(mat=t.zeros((text_line_height, text_line_width), dtype=t.uint8, device=device))
     lcd = glyphs[0].channels == 3
-    score_map = None if lcd else ScoreMap.from_shape((text_line_height, text_line_width))
-    dl_image, dl_mask = DrawList(image), DrawList(mask)
-    dl_score = None if lcd else DrawList(score_map)
-    for glyph, box in zip(glyphs, char_boxes):
+    score_map = None
+    if not lcd:
+        score_map = ScoreMap(mat=t.zeros((text_line_height, text_line_width), dtype=t.float32,
+                                         device=device), skip_prob_check=True)
+    n = len(glyphs)
+    boxes = np.empty((n, 4), dtype=np.int64)
+    mask_ptrs = np.empty(n, dtype=np.uint64)
+    plane_ptrs = np.empty(n, dtype=np.uint64)
+    pitches = np.empty(n, dtype=np.int64)
+    for i, (glyph, box) in enumerate(zip(glyphs, char_boxes)):
         if glyph.mask is None:
             raise RuntimeError('GlyphAtlas.commit() has not run for this glyph.')
         assert (glyph.channels == 3) == lcd and box.shape == glyph.shape
-        if lcd:
-            dl_image.fill(box, glyph.lcd_image, mask=glyph.mask)
-        else:
-            dl_image.fill(box, tuple(glyph_color), mask=glyph.mask)
-            dl_score.fill(box, glyph.alpha, keep_max_value=True)
-        dl_mask.fill(box, 1, mask=glyph.mask)
-    dl_image.flush()
-    dl_mask.flush()
-    if dl_score is not None:
-        dl_score.flush()
+        if box.up < 0 or box.left < 0 or box.down >= text_line_height \
+                or box.right >= text_line_width:
+            raise RuntimeError('char box outside the text line.')
+        boxes[i] = (box.up, box.left, glyph.height, glyph.width)
+        mask_ptrs[i] = glyph.mask.ptr
+        plane_ptrs[i] = glyph.lcd_image.ptr if lcd else glyph.alpha.ptr
+        pitches[i] = glyph.width
+    keep = []
+    if lcd:
+        keep.append(_launch_glyph_items(image, boxes, value_ptrs=plane_ptrs, value_pitches=pitches,
+                                        mask_ptrs=mask_ptrs, mask_pitches=pitches))
+    else:
+        keep.append(_launch_glyph_items(image, boxes, value_const=tuple(glyph_color),
+                                        mask_ptrs=mask_ptrs, mask_pitches=pitches))
+        keep.append(_launch_glyph_items(score_map, boxes, value_ptrs=plane_ptrs,
+                                        value_pitches=pitches, keep_max=True))
+    keep.append(_launch_glyph_items(mask, boxes, value_const=(1,), mask_ptrs=mask_ptrs,
+                                    mask_pitches=pitches))
     return image, mask, score_map
+
+
+def render_atlas_text_lines(lines):
+    """Many text lines at once: `lines` = [(glyph_color, height, width, glyphs, boxes)] with `boxes`
+    a list of Box or an (n, 2) integer array of (up, left) per glyph.  Same result per line as
+    render_atlas_glyphs_in_text_line, but the lines of a page (or of a batch of pages) share three
+    launches: every draw-list item carries its own destination pointer and pitch, so one ordered
+    list can paint into many line images.  Returns [(Image, Mask, ScoreMap or None)]."""
+    t = dv.require_cuda()
+    device = dv.device()
+    if not lines:
+        return []
+    lcd = lines[0][3][0].channels == 3
+    sizes = np.asarray([(int(h), int(w)) for _, h, w, _, _ in lines], dtype=np.int64)
+    pixels = sizes[:, 0] * sizes[:, 1]
+    offsets = np.concatenate([[0], np.cumsum(pixels)])
+    total = int(offsets[-1])
+    image_arena = t.full((total * 3,), 255, dtype=t.uint8, device=device)
+    mask_arena = t.zeros((total,), dtype=t.uint8, device=device)
+    score_arena = None if lcd else t.zeros((total,), dtype=t.float32, device=device)
+    n_items = sum(len(glyphs) for _, _, _, glyphs, _ in lines)
+    boxes = np.empty((n_items, 4), dtype=np.int64)
+    line_of = np.empty(n_items, dtype=np.int64)
+    mask_ptrs = np.empty(n_items, dtype=np.uint64)
+    plane_ptrs = np.empty(n_items, dtype=np.uint64)
+    pitches = np.empty(n_items, dtype=np.int64)
+    colors = np.zeros((n_items, 3), dtype=np.int64)
+    k = 0
+    for li, (color, height, width, glyphs, glyph_boxes) in enumerate(lines):
+        for gi, glyph in enumerate(glyphs):
+            if glyph.mask is None:
+                raise RuntimeError('GlyphAtlas.commit() has not run for this glyph.')
+            assert (glyph.channels == 3) == lcd
+            box = glyph_boxes[gi]
+            up, left = (box.up, box.left) if isinstance(box, Box) else (int(box[0]), int(box[1]))
+            if up < 0 or left < 0 or up + glyph.height > height or left + glyph.width > width:
+                raise RuntimeError('char box outside the text line.')
+            boxes[k] = (up, left, glyph.height, glyph.width)
+            line_of[k] = li
+            mask_ptrs[k] = glyph.mask.ptr
+            plane_ptrs[k] = glyph.lcd_image.ptr if lcd else glyph.alpha.ptr
+            pitches[k] = glyph.width
+            colors[k] = color
+            k += 1
+    max_h, max_w = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+    line_w = sizes[line_of, 1]
+
+    def launch(arena, bytes_per_pixel, channels, dst_f32, **fields):
+        items = np.zeros(n_items, dtype=nv.BLEND_ITEM_DTYPE)
+        items['dst'] = np.uint64(arena.data_ptr()) + (offsets[line_of] * bytes_per_pixel).astype(np.uint64)
+        items['dst_f32'] = int(dst_f32)
+        items['channels'] = channels
+        items['dst_w'] = line_w
+        items['box_y'], items['box_x'] = boxes[:, 0], boxes[:, 1]
+        items['box_h'], items['box_w'] = boxes[:, 2], boxes[:, 3]
+        items['alpha'] = 1.0
+        for name, value in fields.items():
+            if name == 'value_const':
+                items['value_const'][:, :value.shape[1]] = value
+            else:
+                items[name] = value
+        table = dv.upload_structs(items)
+        nv.check(nv.lib().vkb_blend_draw_list(dv.ptr(table), n_items, max_h, max_w, dv.stream_ptr()),
+                 'vkb_blend_draw_list')
+        return table
+
+    keep = []
+    if lcd:
+        keep.append(launch(image_arena, 3, 3, False, value_arr=plane_ptrs, value_pitch=pitches,
+                           mask=mask_ptrs, mask_pitch=pitches))
+    else:
+        keep.append(launch(image_arena, 3, 3, False,
+                           value_const=colors.astype(np.uint8).astype(np.float32),
+                           mask=mask_ptrs, mask_pitch=pitches))
+        keep.append(launch(score_arena, 4, 1, True, value_arr=plane_ptrs, value_pitch=pitches,
+                           keep_mode=1))
+    keep.append(launch(mask_arena, 1, 1, False, value_const=np.ones((n_items, 1), np.float32),
+                       mask=mask_ptrs, mask_pitch=pitches))
+    out = []
+    for li, (height, width) in enumerate(sizes):
+        height, width = int(height), int(width)
+        a, b = int(offsets[li]), int(offsets[li + 1])
+        image = Image(mat=image_arena[a * 3:b * 3].view(height, width, 3))
+        mask = Mask(mat=mask_arena[a:b].view(height, width))
+        score_map = None
+        if not lcd:
+            score_map = ScoreMap(mat=score_arena[a:b].view(height, width), skip_prob_check=True)
+        out.append((image, mask, score_map))
+    return out
 
 
 def render_char_glyphs_in_text_line(glyph_color: Tuple[int, int, int], text_line_height: int,
@@ -479,7 +618,12 @@ def fill_polygons(target: Union[Mask, ScoreMap], polygons, value=1, keep_max_val
     pts = []
     first = 0
     for i, (polygon, v) in enumerate(zip(polygons, values)):
-        xy = np.asarray(polygon.to_np_array(), dtype=np.int32).reshape(-1, 2)
+        if isinstance(polygon, np.ndarray):
+            # smooth (x, y) vertices, e.g. from RandomDistortionBatch: the rounded twins of
+            # Point.create (Python round, half to even) like Polygon.to_np_array
+            xy = np.rint(polygon).astype(np.int32).reshape(-1, 2)
+        else:
+            xy = np.asarray(polygon.to_np_array(), dtype=np.int32).reshape(-1, 2)
         items['first_pt'][i] = first
         items['n_pts'][i] = xy.shape[0]
         items['y_min'][i] = int(xy[:, 1].min())
@@ -488,7 +632,9 @@ def fill_polygons(target: Union[Mask, ScoreMap], polygons, value=1, keep_max_val
         first += xy.shape[0]
         pts.append(xy)
     dst_f32 = target.mat_dtype == np.float32
-    pts_dev = dv.to_device(np.ascontiguousarray(np.concatenate(pts)))
+    # staged like the item tables (pinned block + copy kernel): a pageable cudaMemcpy would wait
+    # for everything queued on the stream
+    pts_dev = dv.upload_structs(np.ascontiguousarray(np.concatenate(pts)))
     items_dev = dv.upload_structs(items)
     height, width = target.shape
     keys = dv.empty((height, width), np.int32)
