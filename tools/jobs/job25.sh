@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out; : > gpurun_out/r2_sweep2.log
-for v in r4b4 b5 b4c2 b6w5; do
+for v in base share; do
   echo "== $v" >> gpurun_out/r2_sweep2.log
   for b in 256; do
   VKB_LIB=$PWD/variants/libvkit_$v.so timeout 120 python bench.py --steps 20 --warmup 3 --kernel-only --batch $b 2>&1 | python -c "

@@ -481,6 +481,9 @@ constexpr int kTilesSlots = 2 * kTilesHalf;
 #ifndef VKB_TILES_ROWS
 #define VKB_TILES_ROWS 4  // rows of a band one lane carries through coordinates -> gather together (4 or 2)
 #endif
+#ifndef VKB_TILES_SHARE_COLUMN
+#define VKB_TILES_SHARE_COLUMN 1
+#endif
 #ifndef VKB_TILES_CHUNK
 #define VKB_TILES_CHUNK 1
 #endif
@@ -782,6 +785,26 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
             int X[R], Y[R];
             uint32_t fail4 = 0;
             const float yr0 = (float)(band * 4 + jb);
+#if VKB_TILES_SHARE_COLUMN
+            // Nearly every band lies inside one row of cells: every lane then has ONE owner for its
+            // four rows (each plane's nibble is 0 or F), and the column part of the cell's three
+            // linear forms, its record pointer and its bases are computed once per lane.
+            if (R == 4 && __all_sync(0xffffffffu, ((own & 0x1111u) * 0xFu) == own)) {
+                const uint32_t id = ((own & 0x1111u) * 0x12480000u) >> 28;
+                const TileSlot* __restrict__ sp = S + id;
+                const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
+                CellColumn col;
+                cell_column(sp->loc, xr, col);
+                const float a1 = sp->loc.a1, b1 = sp->loc.b1, hh = sp->loc.h;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const bool ok = cell_coord_fast_row(col, a1, b1, hh, yr0 + (float)j, base.x, base.y,
+                                                        t_odd, t_even, X[j], Y[j]);
+                    fail4 |= ok ? 0u : (1u << j);
+                }
+            } else
+#endif
+            {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 // bits j, j+4, j+8, j+12 of `own` -> a 4-bit number (the partial products of
@@ -792,6 +815,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 const bool ok = cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y, t_odd,
                                                 t_even, X[j], Y[j]);
                 fail4 |= ok ? 0u : (1u << j);
+            }
             }
             failbits |= fail4 << (band * 4 + jb);
             // rows of the band this thread stores: the ones inside the page.  (A pixel that waits
