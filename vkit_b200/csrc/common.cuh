@@ -1,6 +1,7 @@
 // common.cuh -- error plumbing shared by the translation units of libvkit_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header only: resolves the tool's injection library at run time, no link dependency
 #include <stdio.h>
 #include "../../include/vkit_b200.h"
 
@@ -15,7 +16,17 @@ inline int check_launch(const char* what) {
     }
     return VKB_OK;
 }
+// NVTX range over one C-ABI call (visible in Nsight Systems / compute timelines; a no-op costing
+// one pointer test when no tool is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 }  // namespace vkb
+
+#define VKB_NVTX(name) vkb::NvtxRange vkb_nvtx_range_(name)
 
 #define VKB_REQUIRE(cond, msg)                  \
     do {                                        \

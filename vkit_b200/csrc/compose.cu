@@ -172,6 +172,7 @@ using namespace vkb;
 extern "C" int vkb_background_compose(uint8_t* dst, int32_t h, int32_t w, int32_t channels,
                                       const vkb_paste_item* items, int32_t n_items, int32_t band,
                                       const int32_t* kernel_host, int32_t ksize, void* stream) {
+    VKB_NVTX("vkb_background_compose");
     VKB_REQUIRE(dst && items && kernel_host && h > 0 && w > 0, "bad arguments");
     VKB_REQUIRE(n_items >= 0 && n_items <= kComposeMaxItems, "at most 4096 segments per canvas");
     VKB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 2 * kComposeMaxR + 1, "ksize must be odd and <= 17");
@@ -195,6 +196,7 @@ extern "C" int vkb_background_compose(uint8_t* dst, int32_t h, int32_t w, int32_
 
 extern "C" int vkb_glyph_prepare(const vkb_glyph_item* items, const vkb_glyph_item* items_host,
                                  int32_t n_items, void* stream) {
+    VKB_NVTX("vkb_glyph_prepare");
     VKB_REQUIRE(items && items_host && n_items >= 0, "bad arguments");
     for (int i = 0; i < n_items; ++i) {
         const vkb_glyph_item& it = items_host[i];

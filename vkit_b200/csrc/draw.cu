@@ -31,6 +31,7 @@ using namespace vkb;
 extern "C" int vkb_draw_ellipses(uint8_t* mask, int32_t h, int32_t w, const int32_t* ellipses_host,
                                  int32_t n_ellipses, int32_t thickness, void* seg_workspace,
                                  int64_t workspace_bytes, void* stream) {
+    VKB_NVTX("vkb_draw_ellipses");
     VKB_REQUIRE(mask && ellipses_host && seg_workspace && h > 0 && w > 0, "bad arguments");
     VKB_REQUIRE(thickness >= 1 && thickness <= 255, "thickness must be 1..255 (outlines only)");
     VKB_REQUIRE(h < 16384 && w < 16384, "canvases below 16384 px");

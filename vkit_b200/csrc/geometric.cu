@@ -1227,6 +1227,7 @@ extern "C" const char* vkb_last_error(void) { return g_error; }
 
 extern "C" int vkb_warp_fused(const vkb_warp_page* pages, int32_t n_pages, int32_t max_dst_h,
                               int32_t max_dst_w, void* stream) {
+    VKB_NVTX("vkb_warp_fused");
     VKB_REQUIRE(pages != nullptr && n_pages > 0, "no pages");
     VKB_REQUIRE(n_pages <= 65535, "at most 65535 pages per launch");
     VKB_REQUIRE(max_dst_h > 0 && max_dst_w > 0, "empty destination");
@@ -1248,6 +1249,7 @@ extern "C" int vkb_affine_points(const double* mat_host, int32_t rows, const dou
 
 extern "C" int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                                 double* lattice_f, int32_t projectors, void* stream) {
+    VKB_NVTX("vkb_grid_project");
     VKB_REQUIRE(pages && lattice_f && n_pages > 0 && p_max > 0, "bad arguments");
     VKB_REQUIRE(n_pages <= 65535, "at most 65535 pages per launch");
     // every kernel skips the pages of the other projector; a kernel no page needs is not launched
@@ -1274,6 +1276,7 @@ extern "C" int vkb_grid_project(const vkb_grid_page* pages, int32_t n_pages, int
 extern "C" int vkb_grid_finalize(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max,
                                  const double* lattice_f, int32_t* lattice_i, vkb_grid_meta* meta,
                                  vkb_grid_meta* meta_mirror, void* stream) {
+    VKB_NVTX("vkb_grid_finalize");
     VKB_REQUIRE(pages && lattice_f && lattice_i && meta && n_pages > 0, "bad arguments");
     grid_finalize_kernel<<<n_pages, 1024, 0, (cudaStream_t)stream>>>(pages, p_max, lattice_f,
                                                                     lattice_i, meta, meta_mirror);
@@ -1302,6 +1305,7 @@ extern "C" int vkb_stage_params(void* dst, const void* src_host, int64_t nbytes,
 extern "C" int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes,
                                int64_t cap_pixels, int32_t t_max, int64_t* layout,
                                int64_t* layout_mirror, void* stream) {
+    VKB_NVTX("vkb_grid_layout");
     VKB_REQUIRE(meta && planes && layout && n_pages > 0, "bad arguments");
     VKB_REQUIRE(cap_pixels > 0 && t_max > 0, "empty capacities");
     grid_layout_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
@@ -1340,6 +1344,7 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
                               uint32_t* cell_masks, int32_t* tile_count, uint16_t* tile_cells,
                               int32_t* tile_off, int32_t* tile_base, void* tile_slots,
                               void* tile_headers, void* stream) {
+    VKB_NVTX("vkb_grid_build");
     VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_masks && tile_count
                     && tile_cells && tile_off && tile_base && tile_slots && tile_headers,
                 "bad arguments");
@@ -1399,6 +1404,7 @@ extern "C" int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, co
 extern "C" int vkb_grid_points_batched(const vkb_grid_page* pages, const double* hfwd, int32_t c_max,
                                        const double* xy_in, const int32_t* page_cell,
                                        double* xy_out, int32_t n, void* stream) {
+    VKB_NVTX("vkb_grid_points_batched");
     VKB_REQUIRE(pages && hfwd && xy_in && page_cell && xy_out && c_max > 0, "bad arguments");
     if (n <= 0) return VKB_OK;
     grid_points_batched_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
@@ -1409,6 +1415,7 @@ extern "C" int vkb_grid_points_batched(const vkb_grid_page* pages, const double*
 extern "C" int vkb_affine_points_batched(const double* mats, const int32_t* rows_f32,
                                          const int32_t* page_of, const double* xy_in,
                                          double* xy_out, int32_t n, void* stream) {
+    VKB_NVTX("vkb_affine_points_batched");
     VKB_REQUIRE(mats && rows_f32 && page_of && xy_in && xy_out, "bad arguments");
     if (n <= 0) return VKB_OK;
     affine_points_batched_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
@@ -1431,6 +1438,7 @@ extern "C" int vkb_fill_polygons(void* dst, int32_t dst_f32, int32_t h, int32_t 
                                  const int32_t* pts_xy, const vkb_poly_item* items,
                                  const vkb_poly_item* items_host, int32_t n_items, int32_t mode,
                                  int32_t* keys, void* stream) {
+    VKB_NVTX("vkb_fill_polygons");
     VKB_REQUIRE(dst && pts_xy && items && items_host && keys && h > 0 && w > 0, "bad arguments");
     VKB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (assign), 1 (keep max) or 2 (keep min)");
     VKB_REQUIRE(n_items >= 0 && n_items <= 65535, "at most 65535 polygons per launch");

@@ -260,6 +260,7 @@ static void fill_quant(const int* base, int quality, uint16_t* out) {
 extern "C" int vkb_jpeg_round_trip_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
                                       int32_t channels, int32_t quality, uint8_t* planes,
                                       int64_t planes_bytes, void* stream) {
+    VKB_NVTX("vkb_jpeg_round_trip_u8");
     static const int kLuma[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55,
                                   14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
                                   18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,

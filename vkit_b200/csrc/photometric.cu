@@ -1793,6 +1793,7 @@ extern "C" int vkb_blend_fill(const vkb_blend_item* item_host, void* stream) {
 
 extern "C" int vkb_blend_draw_list(const vkb_blend_item* items, int32_t n_items, int32_t dst_h,
                                    int32_t dst_w, void* stream) {
+    VKB_NVTX("vkb_blend_draw_list");
     VKB_REQUIRE(items && n_items >= 0 && dst_h > 0 && dst_w > 0, "bad arguments");
     if (n_items == 0) return VKB_OK;
     dim3 grid((dst_w + 31) / 32, (dst_h + 31) / 32);
@@ -1813,6 +1814,7 @@ extern "C" int vkb_cvt_color(const uint8_t* src, uint8_t* dst, int64_t n_pixels,
 
 extern "C" int vkb_color_ops(const uint8_t* src, uint8_t* dst, int64_t n_pixels, int32_t channels,
                              const vkb_color_op* ops_host, int32_t n_ops, void* stream) {
+    VKB_NVTX("vkb_color_ops");
     VKB_REQUIRE(src && dst && ops_host, "bad arguments");
     VKB_REQUIRE(n_ops >= 0 && n_ops <= VKB_MAX_COLOR_OPS, "too many ops");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
@@ -1875,6 +1877,7 @@ extern "C" int vkb_apply_lut(const uint8_t* src, uint8_t* dst, int64_t n_pixels,
 extern "C" int vkb_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w,
                                     int32_t channels, const int32_t* kernel_host, int32_t ksize,
                                     void* stream) {
+    VKB_NVTX("vkb_gaussian_blur_u8");
     VKB_REQUIRE(src && dst && kernel_host && h > 0 && w > 0, "bad arguments");
     VKB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 2 * kGaussMaxR + 1, "ksize must be odd and <= 17");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
@@ -1952,6 +1955,7 @@ extern "C" int vkb_streak_masks(uint8_t* image, int32_t h, int32_t w, int32_t ch
 
 extern "C" int vkb_photo_chain_batched(const vkb_photo_page* pages, const vkb_photo_page* pages_host,
                                        int32_t n_pages, int32_t channels, void* stream) {
+    VKB_NVTX("vkb_photo_chain_batched");
     VKB_REQUIRE(pages && pages_host && n_pages > 0 && n_pages <= 65535, "bad arguments");
     VKB_REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
     int max_h = 0, max_w = 0, max_r = 0;

@@ -966,6 +966,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               const void* tile_slots, void* tile_headers,
                               int32_t image_channels, int32_t has_mask, int32_t has_score,
                               void* stream) {
+    VKB_NVTX("vkb_grid_remap");
     VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
                     && tile_off && tile_base && tile_slots && tile_headers, "bad arguments");
     (void)s_cap;
