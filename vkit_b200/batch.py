@@ -465,8 +465,17 @@ def distort_pages_host(op_names: Sequence[str], configs: Sequence, shape: Tuple[
     n = len(op_names)
     # a short first chunk gets the D2H engine going early (the pipeline is PCIe-bound: the fill
     # time before the first copy-out is pure loss)
+    # ... and the chunks then grow by 1.5 x up to `chunk_pages`: a chunk's result must be ready
+    # when the copy-out of the chunk before it ends, and D2H moves a page ~1.3 x slower than H2D
+    # brings the next one in (measured with tools/e2e_timeline_probe.py: a full-size second chunk
+    # left the copy-out engine idle for 0.9 ms)
     first = min(n, max(1, chunk_pages // 4))
-    bounds = [(0, first)] + [(a, min(a + chunk_pages, n)) for a in range(first, n, chunk_pages)]
+    bounds, a, size = [], 0, first
+    while a < n:
+        b = min(a + size, n)
+        bounds.append((a, b))
+        a = b
+        size = min(chunk_pages, max(size + 1, (size * 3) // 2))
     # ... and a short last chunk keeps the drain (its kernels + its D2H, nothing to overlap) short
     a, b = bounds[-1]
     if b - a > first:
