@@ -514,8 +514,8 @@ class Workload2:
 
     def e2e_note(self):
         return ('vkit_b200.batch.distort_pages_host(configs, pinned host pages) incl. '
-                'parameter-block build, H2D, kernels, D2H (32-page chunks; copy-in, two work and '
-                'copy-out streams); wall clock, max over ranks')
+                'parameter-block build, H2D, kernels, D2H (chunks of 8, 12, 18, 27, 32 ... pages; '
+                'copy-in, two work and copy-out streams); wall clock, max over ranks')
 
     def parity(self, cores, n_cpu_pages):
         """GPU pages 0 .. PARITY_PAGES-1 of the timed batch against the oracle; the same pool
