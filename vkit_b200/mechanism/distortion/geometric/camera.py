@@ -64,13 +64,14 @@ def fill_camera_model(rec: np.ndarray, config: CameraModelConfig):
     pp = config.principal_point
     principal_point = np.array((pp[0], pp[1], pp[2] if len(pp) > 2 else 0), dtype=_F32)
 
-    rotation_mat = rodrigues(rotation_vec).astype(_F32)  # cv.Rodrigues(float32) -> float32
+    rotation_mat64 = rodrigues(rotation_vec)  # double, as cv.projectPoints recomputes it below
+    rotation_mat = rotation_mat64.astype(_F32)  # cv.Rodrigues(float32) -> float32
     wc_shifted_original_vec = rotation_mat[2] * _F32(config.camera_distance)
     wc_shifted_principal_point_vec = wc_shifted_original_vec - principal_point
     translation_vec = np.matmul(rotation_mat, wc_shifted_principal_point_vec.reshape(3, 1))
 
     # cv.projectPoints converts rvec / tvec / K to double and recomputes Rodrigues in double
-    rec['R'] = rodrigues(rotation_vec).reshape(-1)
+    rec['R'] = rotation_mat64.reshape(-1)
     rec['t'] = translation_vec.reshape(-1)
     rec['focal'] = float(_F32(config.focal_length))
     rec['projector'] = nv.PROJ_CAMERA
