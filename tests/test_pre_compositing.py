@@ -208,3 +208,34 @@ def test_batched_text_lines_match_reference(lcd):
             assert score_map is None
         else:
             assert sha(score_map.mat) == case['sha']['score_map'], case['id']
+
+
+def test_textures_from_folder_match_in_memory_textures(tmp_path):
+    """`<folder>/metas.json` + `<folder>/image/*` (the layout ImageCombinerEngine reads,
+    combiner.py:48-69): same pixels, same walk as textures handed over in memory."""
+    import json
+    from PIL import Image as PilImage
+    from vkit_b200.background import ImageCombiner, load_textures_from_folder
+    case = COMBINER[0]
+    textures = f4_textures(case['textures_seed'], case['textures_count'], *case['size_range'])
+    (tmp_path / 'image').mkdir()
+    metas = []
+    for name, mat, mean, std in textures:
+        PilImage.fromarray(mat).save(tmp_path / 'image' / name)
+        metas.append({'image_file': name, 'grayscale_mean': mean, 'grayscale_std': std})
+    (tmp_path / 'metas.json').write_text(json.dumps(metas))
+    loaded = load_textures_from_folder(str(tmp_path))
+    assert len(loaded) == len(textures)
+    for texture, (name, mat, mean, std) in zip(loaded, textures):
+        assert texture.name.endswith(name) and np.array_equal(texture.image.mat, mat)
+        assert texture.grayscale_mean == mean and texture.grayscale_std == std
+    from_folder = ImageCombiner(loaded)
+    in_memory, _ = _combiner_for(case)
+    height, width = case['canvas']
+    run = case['runs'][0]
+    plans = []
+    for combiner in (from_folder, in_memory):
+        rng = np.random.default_rng(run['rng_seed'])
+        placements = combiner.plan(height, width, combiner.sample_candidates(rng), rng)
+        plans.append([[p.up, p.down, p.left, p.right] for p in placements])
+    assert plans[0] == plans[1] == run['rects']
