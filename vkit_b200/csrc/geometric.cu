@@ -517,48 +517,74 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     const int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta,
     double* __restrict__ hinv, double* __restrict__ hfwd, int32_t* __restrict__ cell_box,
     int32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_cells) {
+    // The 72-byte homographies of a block's 128 consecutive cells are contiguous in global memory:
+    // they go through shared memory and leave as coalesced 8-byte stores (one thread storing its own
+    // nine doubles touches nine sectors per instruction and throttled the load / store unit).
+    __shared__ double s_h[128 * 9];
     const int page = blockIdx.y;
     const vkb_grid_page& pg = pages[page];
     const int ccols = pg.cols - 1;
     const int C = (pg.rows - 1) * ccols;
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= C) return;
-    const int r = cell / ccols, c = cell - r * ccols;
-    const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
-    const int i00 = r * pg.cols + c, i01 = i00 + 1, i11 = i00 + pg.cols + 1, i10 = i00 + pg.cols;
-    // clockwise: (r,c) (r,c+1) (r+1,c+1) (r+1,c)   (type.py:107-116)
-    int dx[4] = {lat[2 * i00], lat[2 * i01], lat[2 * i11], lat[2 * i10]};
-    int dy[4] = {lat[2 * i00 + 1], lat[2 * i01 + 1], lat[2 * i11 + 1], lat[2 * i10 + 1]};
-    const double sx0 = lattice_coord(c, pg.src_w, pg.grid_size);
-    const double sx1 = lattice_coord(c + 1, pg.src_w, pg.grid_size);
-    const double sy0 = lattice_coord(r, pg.src_h, pg.grid_size);
-    const double sy1 = lattice_coord(r + 1, pg.src_h, pg.grid_size);
-    const double sq[8] = {sx0, sy0, sx1, sy0, sx1, sy1, sx0, sy1};
-    const double dq[8] = {(double)dx[0], (double)dy[0], (double)dx[1], (double)dy[1],
-                          (double)dx[2], (double)dy[2], (double)dx[3], (double)dy[3]};
-    double H[9];
-    homography_4pt(dq, sq, H);
-    double* ho = hinv + ((size_t)page * c_max + cell) * 9;
+    const int cell0 = blockIdx.x * blockDim.x;
+    if (cell0 >= C) return;  // block uniform
+    const int cell = cell0 + threadIdx.x;
+    const bool valid = cell < C;
+    const int n_valid = min((int)blockDim.x, C - cell0);
+    int dx[4] = {0, 0, 0, 0}, dy[4] = {0, 0, 0, 0};
+    double sq[8] = {}, dq[8] = {};
+    if (valid) {
+        const int r = cell / ccols, c = cell - r * ccols;
+        const int32_t* lat = lattice_i + (size_t)page * p_max * 2;
+        const int i00 = r * pg.cols + c, i01 = i00 + 1, i11 = i00 + pg.cols + 1, i10 = i00 + pg.cols;
+        // clockwise: (r,c) (r,c+1) (r+1,c+1) (r+1,c)   (type.py:107-116)
+        const int2 p00 = *reinterpret_cast<const int2*>(lat + 2 * i00);
+        const int2 p01 = *reinterpret_cast<const int2*>(lat + 2 * i01);
+        const int2 p11 = *reinterpret_cast<const int2*>(lat + 2 * i11);
+        const int2 p10 = *reinterpret_cast<const int2*>(lat + 2 * i10);
+        dx[0] = p00.x; dx[1] = p01.x; dx[2] = p11.x; dx[3] = p10.x;
+        dy[0] = p00.y; dy[1] = p01.y; dy[2] = p11.y; dy[3] = p10.y;
+        const double sx0 = lattice_coord(c, pg.src_w, pg.grid_size);
+        const double sx1 = lattice_coord(c + 1, pg.src_w, pg.grid_size);
+        const double sy0 = lattice_coord(r, pg.src_h, pg.grid_size);
+        const double sy1 = lattice_coord(r + 1, pg.src_h, pg.grid_size);
+        sq[0] = sx0; sq[1] = sy0; sq[2] = sx1; sq[3] = sy0; sq[4] = sx1; sq[5] = sy1; sq[6] = sx0; sq[7] = sy1;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) ho[i] = H[i];
-    if (hfwd) {
-        homography_4pt(sq, dq, H);
-        double* hf = hfwd + ((size_t)page * c_max + cell) * 9;
+        for (int k = 0; k < 4; ++k) {
+            dq[2 * k] = (double)dx[k];
+            dq[2 * k + 1] = (double)dy[k];
+        }
+        double H[9];
+        homography_4pt(dq, sq, H);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) hf[i] = H[i];
+        for (int i = 0; i < 9; ++i) s_h[threadIdx.x * 9 + i] = H[i];
     }
+    __syncthreads();
+    {
+        double* __restrict__ ho = hinv + ((size_t)page * c_max + cell0) * 9;
+        for (int k = threadIdx.x; k < n_valid * 9; k += blockDim.x) ho[k] = s_h[k];
+    }
+    if (hfwd) {
+        __syncthreads();
+        if (valid) {
+            double H[9];
+            homography_4pt(sq, dq, H);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s_h[threadIdx.x * 9 + i] = H[i];
+        }
+        __syncthreads();
+        double* __restrict__ hf = hfwd + ((size_t)page * c_max + cell0) * 9;
+        for (int k = threadIdx.x; k < n_valid * 9; k += blockDim.x) hf[k] = s_h[k];
+    }
+    if (!valid) return;
     const int x0 = min(min(dx[0], dx[1]), min(dx[2], dx[3]));
     const int x1 = max(max(dx[0], dx[1]), max(dx[2], dx[3]));
     const int y0 = min(min(dy[0], dy[1]), min(dy[2], dy[3]));
     const int y1 = max(max(dy[0], dy[1]), max(dy[2], dy[3]));
-    int32_t* box = cell_box + ((size_t)page * c_max + cell) * 4;
     // bit 30 of x1: the coverage of this cell exceeds the fixed mask budget (one 32-bit word per
     // row, VKB_CELL_MASK_WORDS rows): the masks kernel skips it, the remap rasterises it on the fly
     const bool big = (x1 - x0 + 32) / 32 != 1 || y1 - y0 + 1 > VKB_CELL_MASK_WORDS;
-    box[0] = x0;
-    box[1] = y0;
-    box[2] = x1 | (big ? 0x40000000 : 0);
-    box[3] = y1;
+    *reinterpret_cast<int4*>(cell_box + ((size_t)page * c_max + cell) * 4) =
+        make_int4(x0, y0, x1 | (big ? 0x40000000 : 0), y1);
     // bin into dst tiles
     const int tiles_x = (meta[page].dst_w + VKB_TILE - 1) / VKB_TILE;
     const int tx0 = x0 / VKB_TILE, tx1 = x1 / VKB_TILE, ty0 = y0 / VKB_TILE, ty1 = y1 / VKB_TILE;
