@@ -805,14 +805,16 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     const size_t page_cell0 = (size_t)page * c_max;
     for (int s = lane; s < count; s += 16) {
         const int cell = (int)cells[s];
-        int rank = 0;
-        for (int j = 0; j < count; ++j) rank += (int)cells[j] < cell;
+        // the cell's box and homography are requested first: their (L2) latency then runs under
+        // the ranking loop instead of after it
         const int4 b = cell_box[page_cell0 + cell];
-        const int r = cell / ccols, c = cell - r * ccols;
         double H[9];
         const double* __restrict__ hp = hinv + (page_cell0 + cell) * 9;
 #pragma unroll
         for (int i = 0; i < 9; ++i) H[i] = hp[i];
+        int rank = 0;
+        for (int j = 0; j < count; ++j) rank += (int)cells[j] < cell;
+        const int r = cell / ccols, c = cell - r * ccols;
         TileSlot rec;
         make_cell_local(H, c * gs, r * gs, tx * VKB_TILE, ty * VKB_TILE, rec.loc);
         rec.x0 = b.x;
