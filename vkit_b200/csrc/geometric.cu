@@ -682,18 +682,17 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
             // A row of an ordinary (convex) cell meets exactly two scan edges: one span between
             // them, no sorting.  Other counts (folded cells) take the general routine.
             const int y = y0 + row;
-            int lo = kNoCross, sum = 0, n_cross = 0;
+            int lo = kNoCross, hi = -kNoCross, n_cross = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const bool active = y >= es4[i].ya && y < es4[i].yb;
                 const int c = es4[i].base + es4[i].dxf * (y - es4[i].ya);
                 lo = active ? min(lo, c) : lo;
-                sum += active ? c : 0;
+                hi = active ? max(hi, c) : hi;
                 n_cross += active ? 1 : 0;
             }
             uint32_t fill;
             if (n_cross == 2) {
-                const int hi = sum - lo;
                 const int xl = (int)(((long long)lo + 65535) >> 16), xr = hi >> 16;
                 fill = xl <= xr ? bits_lo_hi(xl - x0, xr - x0) : 0u;
             } else {
