@@ -122,6 +122,12 @@ class Box(Shapable):
         return mat[self.up:self.down + 1, self.left:self.right + 1]
 
     def _extract_element(self, element):
+        """The part of `element` under this box as a new element (box.py:239-275).
+        Difference to the reference: a device-resident crop is a COPY (`.contiguous()`: the
+        kernels take dense planes), not a view into its parent, and a host-backed crop becomes a
+        private device copy the first time a kernel writes into it.  Filling an extracted element
+        therefore never changes the element it was cut from; fill the parent through the box
+        (`box.fill_image(parent, ...)`) instead -- the reference's own pipeline does exactly that."""
         relative_box, new_box = self.get_boxes_for_box_attached_opt(element.box)
         if relative_box.shape == element.shape:
             return element
