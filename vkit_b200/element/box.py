@@ -127,7 +127,7 @@ class Box(Shapable):
         kernels take dense planes), not a view into its parent, and a host-backed crop becomes a
         private device copy the first time a kernel writes into it.  Filling an extracted element
         therefore never changes the element it was cut from; fill the parent through the box
-        (`box.fill_image(parent, ...)`) instead -- the reference's own pipeline does exactly that."""
+        (`box.fill_image(parent, ...)`) instead."""
         relative_box, new_box = self.get_boxes_for_box_attached_opt(element.box)
         if relative_box.shape == element.shape:
             return element
