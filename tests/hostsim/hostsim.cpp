@@ -210,8 +210,7 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
         sx[cell] = sx0;
         sy[cell] = sy0;
     }
-    float t_odd, t_even;
-    fast_thresholds(pg->src_w > pg->src_h ? pg->src_w : pg->src_h, t_odd, t_even);
+    const int extent = pg->src_w > pg->src_h ? pg->src_w : pg->src_h;
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
     for (int y = 0; y < Hh; ++y)
         for (int x = 0; x < W; ++x) {
@@ -225,8 +224,13 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             int Xe, Ye, Xf, Yf;
             cell_coord(&hinv[(size_t)o * 9], x, y, Xe, Ye);
             const float xr = (float)(x - ox), yr = (float)(y - oy);
-            const bool ok = cell_coord_fast(L, xr, yr, sx[o] * 32 - kRoundMagicBits,
-                                            sy[o] * 32 - kRoundMagicBits, t_odd, t_even, Xf, Yf);
+            // The kernel takes the margin from the largest source corner among the cells that
+            // touch the pixel's tile; the owner is one of them, so the owner's own corner gives
+            // the narrowest margin (= the largest accepted set) any tile can use for this pixel.
+            const int margin = fast_margin(sx[o] > sy[o] ? sx[o] : sy[o]), limit = fast_limit(margin);
+            const bool ok = fast_page_ok(extent)
+                            && cell_coord_fast(L, xr, yr, fast_base(sx[o], margin),
+                                               fast_base(sy[o], margin), limit, Xf, Yf);
             if (ok) { stats[1]++; if (Xf != Xe || Yf != Ye) stats[2]++; }
             // error of the float32 evaluation itself
             const double* H = &hinv[(size_t)o * 9];
@@ -238,9 +242,12 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             const float nx = fma_rn_f32(L.a1, yr, col.nx);
             const float ny = fma_rn_f32(L.b1, yr, col.ny);
             const float r = 1.0f / d;
-            const double ex = fabs((double)(nx * r) - 32.0 * (ux - sx[o]));
-            const double ey = fabs((double)(ny * r) - 32.0 * (uy - sy[o]));
-            if (fmax(fabs((double)(nx * r)), fabs((double)(ny * r))) >= kFastRange) continue;
+            // what the kernel's test sees: the sums rounded to whole fast-path units
+            const double fx = rint((double)fma_rn_f32(nx, r, kRoundMagic) - (double)kRoundMagic) / kFastUnits;
+            const double fy = rint((double)fma_rn_f32(ny, r, kRoundMagic) - (double)kRoundMagic) / kFastUnits;
+            const double ex = fabs(fx - 32.0 * (ux - sx[o]));
+            const double ey = fabs(fy - 32.0 * (uy - sy[o]));
+            if (!(fmax(fabs((double)nx * r), fabs((double)ny * r)) < kFastRange * kFastUnits)) continue;
             const long long e = (long long)(fmax(ex, ey) * 1e9);
             if (e > stats[3]) stats[3] = e;
         }

@@ -140,8 +140,10 @@ def test_remap_numerics_given_reference_lattice(hs, case):
                           owner.ctypes.data, stats)
     pixels, ok, wrong, max_err = list(stats)
     assert wrong == 0
-    assert ok / pixels > 0.99
-    assert max_err / 1e9 < 1.0e-3 / 4  # kFastSlack with a 4x margin
+    assert ok / pixels > 0.985
+    # kFastSlack with a 3x margin; the error includes the rounding of the estimate to whole
+    # fast-path units (2^-12 of 1/32 px: up to 1.2e-4)
+    assert max_err / 1e9 < 1.0e-3 / 3
     print(f'fast path: {ok / pixels:.5f} accepted, max error {max_err / 1e9:.2e}')
 
 

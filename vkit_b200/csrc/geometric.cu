@@ -803,6 +803,23 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
     const int off = tile_off[pt];
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const bool usable = count <= VKB_TILE_CAP && off + count <= s_cap;
+    const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
+    const int ccols = pages[page].cols - 1;
+    const int gs = pages[page].grid_size;
+    // acceptance margin of the fast path: from the largest source corner among the tile's cells
+    int margin = 0;
+    if (usable) {
+        int reach = 0;
+        for (int s = lane; s < count; s += 16) {
+            const int cell = (int)cells[s];
+            const int r = cell / ccols, c = cell - r * ccols;
+            reach = max(reach, max(r, c));
+        }
+        const unsigned half = 0xFFFFu << (threadIdx.x & 16);
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) reach = max(reach, __shfl_xor_sync(half, reach, d));
+        margin = fast_margin(reach * gs);
+    }
     if (lane == 0) {
         RemapTile h;
         h.page = page;
@@ -810,7 +827,8 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         h.ty0 = ty * VKB_TILE;
         h.count = usable ? count : -1;
         h.rec = page * s_cap + off;
-        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        h.lim = fast_limit(margin);
+        h.pad[0] = h.pad[1] = 0;
         const int index = tile_base[page] + t;
         int4* __restrict__ dst = reinterpret_cast<int4*>(headers + index);
         const int4* src = reinterpret_cast<const int4*>(&h);
@@ -820,10 +838,8 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         if ((unsigned)h.count > (unsigned)kPlaneCands) large[1 + atomicAdd(large, 1)] = index;
     }
     if (!usable) return;  // the remap takes its slow path
-    const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
-    const int ccols = pages[page].cols - 1;
-    const int gs = pages[page].grid_size;
     const size_t page_cell0 = (size_t)page * c_max;
+    const bool fast_ok = fast_page_ok(max(pages[page].src_h, pages[page].src_w));
     for (int s = lane; s < count; s += 16) {
         const int cell = (int)cells[s];
         // the cell's box and homography are requested first: their (L2) latency then runs under
@@ -842,8 +858,9 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         rec.y0 = b.y;
         rec.nr = b.w - b.y;
         rec.cellf = cell | ((b.z & 0x40000000) ? (int)0x80000000 : 0);
-        rec.xm = c * gs * 32 - kRoundMagicBits;
-        rec.ym = r * gs * 32 - kRoundMagicBits;
+        if (!fast_ok) rec.loc.a2 = __int_as_float(0x7fc00000);  // NaN: every pixel takes the exact path
+        rec.xm = fast_base(c * gs, margin);
+        rec.ym = fast_base(r * gs, margin);
         rec.info = rank | (c << 6) | (r << 16);
         rec.pad = 0;
         int4* __restrict__ dst = reinterpret_cast<int4*>(slots + ((size_t)page * s_cap + off + rank));

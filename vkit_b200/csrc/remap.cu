@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
         if (LARGE) index = large[1 + index];
         const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
-        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
+        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x; t.lim = b.y;
         return t;
     };
     auto stage = [&](const RemapTile& t, int base) {  // this warp's copies of one tile's records
@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
     // per-page state, reloaded when the page changes
     int ctx_page = -1;
     int dst_h = 0, dst_w = 0, src_h = 0, src_w = 0, cols = 0;
-    float t_odd = 0.f, t_even = 0.f;
     const uint8_t* __restrict__ src_image = nullptr;
     uint8_t* __restrict__ dst_image = nullptr;
     const uint8_t* __restrict__ src_mask = nullptr;
@@ -183,11 +182,10 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
             src_mask = pl->src_mask; dst_mask = pl->dst_mask;
             src_score = pl->src_score; dst_score = pl->dst_score;
             cols = pages[page].cols;
-            fast_thresholds(max(src_h, src_w), t_odd, t_even);
             ctx_page = page;
         }
         const TileSlot* __restrict__ S = sm + cur_base;
-        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
+        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count, fast_lim = cur.lim;
         const bool fast = count >= 0;
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
@@ -314,7 +312,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                         const int slot = covered ? key[j] : 0;
                         const int2 base = *reinterpret_cast<const int2*>(&S[slot].xm);
                         const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j, base.x, base.y,
-                                                        t_odd, t_even, X[j], Y[j]);
+                                                        fast_lim, X[j], Y[j]);
                         if (covered && !ok) {
                             const int cell = S[slot].cellf & 0x7FFFFFFF;
                             const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
@@ -581,8 +579,8 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
     // record 0 of both halves: the map of uncovered pixels, (0, 0) for every pixel, always exact
     if (lane < 2) {
         TileSlot z = {};
-        z.xm = -kRoundMagicBits;
-        z.ym = -kRoundMagicBits;
+        z.xm = kFastBaseZero;
+        z.ym = kFastBaseZero;
         sm[lane * kTilesHalf] = z;
     }
     __syncwarp();
@@ -592,7 +590,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
         index = min(index, total - 1);
         const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
-        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x;
+        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x; t.lim = b.y;
         return t;
     };
     auto mine = [](const RemapTile& t) { return (unsigned)t.count <= (unsigned)kPlaneCands; };
@@ -622,7 +620,6 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
     int ctx_page = -1;
     RemapPage pg = {};
     int cols = 0;
-    float t_odd = 0.f, t_even = 0.f;
     const uint32_t* __restrict__ img_words = nullptr;   // image base rounded down to 4 bytes
     const uint32_t* __restrict__ mask_words = nullptr;  // mask base rounded down to 4 bytes
     int img_mis = 0, mask_mis = 0, img_pitch = 0;
@@ -659,7 +656,6 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
             pg.src_mask = pl->src_mask; pg.dst_mask = pl->dst_mask;
             pg.src_score = pl->src_score; pg.dst_score = pl->dst_score;
             cols = pages[page].cols;
-            fast_thresholds(max(pg.src_h, pg.src_w), t_odd, t_even);
             tiny = pg.src_h < 2 || pg.src_w < 2;
             if (C > 0) {
                 const uintptr_t a = reinterpret_cast<uintptr_t>(pg.src_image);
@@ -684,7 +680,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
             ctx_page = page;
         }
         const TileSlot* __restrict__ S = sm + cur_base;  // S[0]: zero map, S[1 ..]: candidates
-        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count;
+        const int tx0 = cur.tx0, ty0 = cur.ty0, count = cur.count, fast_lim = cur.lim;
         const size_t page_cell0 = (size_t)page * c_max;
         const int x = tx0 + lane;
         const bool x_in = x < pg.dst_w;
@@ -799,7 +795,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const bool ok = cell_coord_fast_row(col, a1, b1, hh, yr0 + (float)j, base.x, base.y,
-                                                        t_odd, t_even, X[j], Y[j]);
+                                                        fast_lim, X[j], Y[j]);
                     fail4 |= ok ? 0u : (1u << j);
                 }
             } else
@@ -812,8 +808,8 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 const uint32_t id = (((own >> (jb + j)) & 0x1111u) * 0x12480000u) >> 28;
                 const TileSlot* __restrict__ sp = S + id;
                 const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
-                const bool ok = cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y, t_odd,
-                                                t_even, X[j], Y[j]);
+                const bool ok = cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y, fast_lim,
+                                                X[j], Y[j]);
                 fail4 |= ok ? 0u : (1u << j);
             }
             }

@@ -10,7 +10,7 @@ namespace vkb {
 struct __align__(16) TileSlot {
     CellLocal loc;
     int x0, y0, nr, cellf;  // bbox origin, rows - 1, cell | (over mask budget ? 1 << 31 : 0)
-    int xm, ym;             // 32 * (src corner of the cell) - kRoundMagicBits: base of the fast path
+    int xm, ym;             // fast_base(src corner of the cell, margin of the page): base of the fast path
     int info;               // slot | cell column << 6 | cell row << 16
     int pad;
 };
@@ -25,7 +25,8 @@ struct __align__(16) RemapTile {
     int page, tx0, ty0;
     int count;  // candidate records; -1: the tile takes the slow exact path
     int rec;    // index of the first record
-    int pad[3];
+    int lim;    // fast_limit of the tile's acceptance margin (the records' bases hold the margin)
+    int pad[2];
 };
 static_assert(sizeof(RemapTile) == VKB_TILE_HEADER_BYTES, "RemapTile layout is part of the ABI");
 

@@ -183,31 +183,43 @@ VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& 
 // The source lattice is integer, so inside a cell the source coordinate is  u = sx0 + du  with
 // du in roughly [-2, g+2].  f = 32*du is evaluated in float32 from the homography re-centred on
 // the origin of the 32 x 32 dst tile the pixel lies in (tile origin -> offset from the cell's
-// src corner, numerators pre-scaled by 32): magnitudes stay in the low thousands, so the
-// absolute error of f is far below the 1/32 px quantum.
+// src corner): magnitudes stay in the low thousands, so the absolute error of f is far below the
+// 1/32 px quantum.
 //
 // The reference rounds twice: u (float64) -> float32 map value m, then X = rint(32 * m), half
 // to even.  With t = 32 * u, K an integer and T = K + 0.5: every t within h = 32 * halfulp32(u)
 // of T rounds to the float32 value T itself, which rint() then sends to the EVEN neighbour.
-// So the set of t that produce an odd X is (X - 0.5 + h, X + 0.5 - h) and the set that produce
-// an even X is [X - 0.5 - h, X + 0.5 + h].  With Xi = nearest integer of the float32 estimate
-// and d = f - Xi, the estimate therefore IS the reference's result whenever
-//     |d| < 0.5 - h - eps   (Xi odd)        |d| < 0.5 + h - eps   (Xi even)
-// where eps (kFastSlack) bounds the float32 evaluation error of f; otherwise the caller takes
-// the float64 path.  The kernel uses one pair of thresholds per page: h_max of the largest
-// source coordinate for odd results, h = 0 for even ones (both conservative).
-// tests/test_hostsim.py audits all of this on every golden grid case (observed evaluation
-// error is > 4x below kFastSlack; 0 wrong results among accepted pixels).
+// So whatever the parity of the neighbours, a t farther than h from every tie rounds like
+// rint(t), and an estimate of t with error below eps (kFastSlack) gives the reference's X
+// whenever it keeps a distance of h + eps from every tie; otherwise the caller takes the
+// float64 path.
+//
+// The test runs on integers.  The numerators are pre-scaled by 32 * 2^kFastBits, the last FMA of
+// an axis adds 1.5 * 2^23 to numerator * reciprocal, so the low mantissa bits of the sum are
+// I = rint(2^kFastBits * f) (the rounding, at most half a unit = 1.2e-4, is part of eps).  With
+// the cell's base  B = 2^kFastBits * 32 * s0 + 2^(kFastBits-1) - margin - (bits of the magic)
+// t = bits + B  has  X = t >> kFastBits  and  p = t & (2^kFastBits - 1)  = distance of the estimate
+// from the tie below minus `margin`: accepted when p <= 2^kFastBits - 1 - 2 * margin.  One FMA,
+// one add, one shift, one AND and one compare per axis (the float form of the same test -- two
+// parities, two thresholds -- cost eight).  margin = ceil((h_max + eps) * 2^kFastBits) for the
+// largest source coordinate of the page.  tests/test_hostsim.py audits all of this on every
+// golden grid case (observed evaluation error incl. the rounding is > 3x below kFastSlack;
+// 0 wrong results among accepted pixels).
 // ---------------------------------------------------------------------------------------
 struct CellLocal {
-    float a0, a1, a2, g;  // 32 * numerator of du_x = a0*x' + a1*y' + a2 ; denominator g*x' + h*y' + 1
-    float b0, b1, b2, h;  // 32 * numerator of du_y          (x', y') = pixel - tile origin
+    float a0, a1, a2, g;  // kFastUnits * 32 * numerator of du_x = a0*x' + a1*y' + a2 ; denominator g*x' + h*y' + 1
+    float b0, b1, b2, h;  // kFastUnits * 32 * numerator of du_y          (x', y') = pixel - tile origin
 };
 
 constexpr float kFastSlack = 1.0e-3f;          // in units of 1/32 px
 constexpr float kFastRange = 1024.0f;          // |32*du| accepted by the fast path (32 px)
+constexpr int kFastBits = 12;                  // fraction bits of the fast path's fixed point
+constexpr int kFastOne = 1 << kFastBits;
+constexpr float kFastUnits = (float)kFastOne;
 constexpr float kRoundMagic = 12582912.0f;     // 1.5 * 2^23: (v + magic) rounds v half to even
 constexpr int kRoundMagicBits = 0x4B400000;    // bit pattern of kRoundMagic
+constexpr int kFastMaxExtent = 16000;          // 32 * extent * 2^kFastBits must fit an int32
+static_assert(kFastRange * kFastUnits <= 4194304.0f, "the magic-number rounding holds below 2^22");
 
 // 2^(e-19) for |u| in [2^e, 2^(e+1)): 32 * half ulp of float32(u); 0 for tiny |u|.
 VKB_HD float half_ulp_times_32(float u) {
@@ -218,12 +230,26 @@ VKB_HD float half_ulp_times_32(float u) {
     return v.f;
 }
 
-// acceptance thresholds for a page whose source coordinates stay below `extent` pixels
-VKB_HD void fast_thresholds(int extent, float& t_odd, float& t_even) {
-    const float reach = (float)extent + kFastRange / 32.0f + 1.0f;
-    t_odd = 0.5f - half_ulp_times_32(reach) - kFastSlack;
-    t_even = 0.5f - kFastSlack;
+// Acceptance window for source coordinates that start below `extent` pixels (a page's size, or
+// the largest source corner among the cells of one dst tile -- the half ulp of the float32 map
+// value grows with the coordinate, so tiles near the origin get a narrower window): distance
+// (in fast-path units) an estimate keeps from every tie.  < kFastOne / 4 for every extent
+// below kFastMaxExtent; pages beyond that never take the fast path (fast_page_ok).
+VKB_HD int fast_margin(int extent) {
+    const float reach = (float)(extent < kFastMaxExtent ? extent : kFastMaxExtent) + kFastRange / 32.0f + 1.0f;
+    const float w = (half_ulp_times_32(reach) + kFastSlack) * kFastUnits;
+    const int m = (int)w;
+    return (float)m < w ? m + 1 : m;
 }
+VKB_HD int fast_limit(int margin) { return kFastOne - 1 - 2 * margin; }
+VKB_HD bool fast_page_ok(int extent) { return extent < kFastMaxExtent; }
+
+// base of a cell whose source corner is s0 (pixels), for a page with acceptance margin `margin`
+VKB_HD int fast_base(int s0, int margin) {
+    return s0 * 32 * kFastOne + kFastOne / 2 - margin - kRoundMagicBits;
+}
+// base of the zero map (uncovered pixels): accepted under every margin, X = 0
+constexpr int kFastBaseZero = kFastOne / 2 - kRoundMagicBits;
 
 // H: inverse homography of the cell (dst -> src); (sx0, sy0): its src corner; (ox, oy): origin
 // of the dst tile the form is valid for.
@@ -233,25 +259,15 @@ VKB_HD void make_cell_local(const double* __restrict__ H, int sx0, int sy0, int 
     const double ay0 = H[3] - sy0 * H[6], ay1 = H[4] - sy0 * H[7], ay2 = H[5] - sy0 * H[8];
     const double d0 = H[6] * ox + H[7] * oy + H[8];
     const double inv = 1.0 / d0;  // inf / nan when degenerate: the fast path then always fails
-    const double inv32 = 32.0 * inv;
-    L.a0 = (float)(ax0 * inv32);
-    L.a1 = (float)(ax1 * inv32);
-    L.a2 = (float)((ax0 * ox + ax1 * oy + ax2) * inv32);
-    L.b0 = (float)(ay0 * inv32);
-    L.b1 = (float)(ay1 * inv32);
-    L.b2 = (float)((ay0 * ox + ay1 * oy + ay2) * inv32);
+    const double invs = (32.0 * kFastOne) * inv;
+    L.a0 = (float)(ax0 * invs);
+    L.a1 = (float)(ax1 * invs);
+    L.a2 = (float)((ax0 * ox + ax1 * oy + ax2) * invs);
+    L.b0 = (float)(ay0 * invs);
+    L.b1 = (float)(ay1 * invs);
+    L.b2 = (float)((ay0 * ox + ay1 * oy + ay2) * invs);
     L.g = (float)(H[6] * inv);
     L.h = (float)(H[7] * inv);
-}
-
-// one axis: f = float32 estimate of 32*du, base_m = 32*s0 - kRoundMagicBits.
-// Returns the acceptance test; X = 32*s0 + rint(f).
-VKB_HD bool fast_axis(float f, int base_m, float t_odd, float t_even, int& X) {
-    union { float f; int i; } v;
-    v.f = VKB_FADD(f, kRoundMagic);                 // low mantissa bits = rint(f), half to even
-    const float d = VKB_FSUB(f, VKB_FSUB(v.f, kRoundMagic));  // exact
-    X = base_m + v.i;
-    return fabsf(d) < ((v.i & 1) ? t_odd : t_even);
 }
 
 VKB_HD float fma_rn_f32(float a, float b, float c) {
@@ -260,6 +276,22 @@ VKB_HD float fma_rn_f32(float a, float b, float c) {
 #else
     return fmaf(a, b, c);  // correctly rounded on the host as well
 #endif
+}
+
+// one axis: n * r = float32 estimate of kFastUnits * 32 * du, base = fast_base(s0, margin).
+// Returns the acceptance test; X = 32 * s0 + rint(32 * du) when it holds.  (A sum outside
+// [2^23, 2^24) -- |32*du| >= kFastRange, inf, nan -- is caught by fast_pair_in_range.)
+VKB_HD bool fast_axis(float n, float r, int base, int limit, int& X, int& bits) {
+    union { float f; int i; } v;
+    v.f = fma_rn_f32(n, r, kRoundMagic);  // low mantissa bits = rint(n * r), half to even
+    bits = v.i;
+    const int t = v.i + base;
+    X = t >> kFastBits;
+    return (t & (kFastOne - 1)) <= limit;
+}
+// both sums have the exponent of the magic number
+VKB_HD bool fast_pair_in_range(int bits_x, int bits_y) {
+    return (uint32_t)((bits_x ^ 0x4B000000) | (bits_y ^ 0x4B000000)) < 0x00800000u;
 }
 
 // The three linear forms are evaluated column part first: the part that depends on the pixel's
@@ -276,8 +308,8 @@ VKB_HD void cell_column(const CellLocal& L, float xr, CellColumn& c) {
 }
 
 // one row of a prepared column: (a1, b1, h) = L.a1, L.b1, L.h
-VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h, float yr, int x0m,
-                                int y0m, float t_odd, float t_even, int& X, int& Y) {
+VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h, float yr, int xb,
+                                int yb, int limit, int& X, int& Y) {
     const float d = fma_rn_f32(h, yr, c.d);
     const float nx = fma_rn_f32(a1, yr, c.nx);
     const float ny = fma_rn_f32(b1, yr, c.ny);
@@ -287,19 +319,19 @@ VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h
 #else
     const float r = 1.0f / d;
 #endif
-    const float fx = VKB_FMUL(nx, r), fy = VKB_FMUL(ny, r);
-    const bool okx = fast_axis(fx, x0m, t_odd, t_even, X);
-    const bool oky = fast_axis(fy, y0m, t_odd, t_even, Y);
-    // NaN / inf anywhere -> false (every comparison fails)
-    return okx && oky && fmaxf(fabsf(fx), fabsf(fy)) < kFastRange;
+    int bx, by;
+    const bool okx = fast_axis(nx, r, xb, limit, X, bx);
+    const bool oky = fast_axis(ny, r, yb, limit, Y, by);
+    // NaN / inf anywhere -> false (the exponent test fails)
+    return okx && oky && fast_pair_in_range(bx, by);
 }
 
 // (xr, yr): pixel - tile origin as floats (exact small integers).
-VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int x0m, int y0m, float t_odd,
-                            float t_even, int& X, int& Y) {
+VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int xb, int yb, int limit,
+                            int& X, int& Y) {
     CellColumn c;
     cell_column(L, xr, c);
-    return cell_coord_fast_row(c, L.a1, L.b1, L.h, yr, x0m, y0m, t_odd, t_even, X, Y);
+    return cell_coord_fast_row(c, L.a1, L.b1, L.h, yr, xb, yb, limit, X, Y);
 }
 
 // ---------------------------------------------------------------------------------------
