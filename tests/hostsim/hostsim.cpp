@@ -230,7 +230,7 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             const int margin = fast_margin(sx[o] > sy[o] ? sx[o] : sy[o]), limit = fast_limit(margin);
             const bool ok = fast_page_ok(extent)
                             && cell_coord_fast(L, xr, yr, fast_base(sx[o], margin),
-                                               fast_base(sy[o], margin), limit, Xf, Yf);
+                                               fast_base(sy[o], margin), limit, Xf, Yf) >= 0;
             if (ok) { stats[1]++; if (Xf != Xe || Yf != Ye) stats[2]++; }
             // error of the float32 evaluation itself
             const double* H = &hinv[(size_t)o * 9];

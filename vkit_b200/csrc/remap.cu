@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                         const int slot = covered ? key[j] : 0;
                         const int2 base = *reinterpret_cast<const int2*>(&S[slot].xm);
                         const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j, base.x, base.y,
-                                                        fast_lim, X[j], Y[j]);
+                                                        fast_lim, X[j], Y[j]) >= 0;
                         if (covered && !ok) {
                             const int cell = S[slot].cellf & 0x7FFFFFFF;
                             const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
@@ -663,8 +663,13 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 img_words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
                 img_pitch = pg.src_w * CC;
                 if (CC == 4 && img_mis) tiny = true;  // unaligned RGBA: the plain per-tap path
+                if (CC == 3) {  // RGB taps are addressed in bits (fetch2_request_rgb_bits)
+                    if ((long long)img_pitch * pg.src_h >= (1ll << 28)) tiny = true;  // plain per-tap path
+                    img_mis *= 8;
+                    img_pitch *= 8;
+                }
                 uint8_t px[CC];
-                bilinear_u8<CC>(pg.src_image, pg.src_h, pg.src_w, (long long)img_pitch, 0, 0, px);
+                bilinear_u8<CC>(pg.src_image, pg.src_h, pg.src_w, (long long)pg.src_w * CC, 0, 0, px);
 #pragma unroll
                 for (int c = 0; c < CC; ++c) fill_px[c] = px[c];
             }
@@ -792,25 +797,23 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 CellColumn col;
                 cell_column(sp->loc, xr, col);
                 const float a1 = sp->loc.a1, b1 = sp->loc.b1, hh = sp->loc.h;
+                // verdicts collected from the last row down: bit j of fail4 = row j rejected
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const bool ok = cell_coord_fast_row(col, a1, b1, hh, yr0 + (float)j, base.x, base.y,
-                                                        fast_lim, X[j], Y[j]);
-                    fail4 |= ok ? 0u : (1u << j);
-                }
+                for (int j = R - 1; j >= 0; --j)
+                    fail4 = fast_collect(fail4, cell_coord_fast_row(col, a1, b1, hh, yr0 + (float)j,
+                                                                    base.x, base.y, fast_lim, X[j], Y[j]));
             } else
 #endif
             {
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
+            for (int j = R - 1; j >= 0; --j) {
                 // bits j, j+4, j+8, j+12 of `own` -> a 4-bit number (the partial products of
                 // the multiplication land on distinct bits: no carries)
                 const uint32_t id = (((own >> (jb + j)) & 0x1111u) * 0x12480000u) >> 28;
                 const TileSlot* __restrict__ sp = S + id;
                 const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
-                const bool ok = cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y, fast_lim,
-                                                X[j], Y[j]);
-                fail4 |= ok ? 0u : (1u << j);
+                fail4 = fast_collect(fail4, cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y,
+                                                            fast_lim, X[j], Y[j]));
             }
             }
             failbits |= fail4 << (band * 4 + jb);
@@ -847,6 +850,46 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 }
                 continue;
             }
+            // taps -> loads -> blend -> stores of the band's R rows, for a given set of taps
+            auto emit = [&](const Tap2 (&tap)[R]) {
+                if (C > 0) {
+                    Fetch2<CC> f[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        if constexpr (CC == 3) fetch2_request_rgb_bits(img_words, img_mis, img_pitch, tap[j], f[j]);
+                        else fetch2_request<CC>(img_words, img_mis, img_pitch, tap[j], f[j]);
+                    }
+                    uint32_t v[R][CC];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) fetch2_blend<CC>(f[j], tap[j], v[j]);
+                    if (interior) {
+#pragma unroll
+                        for (int j = 0; j < R; ++j) store_px(di0 + j * pg.dst_w, v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            if ((live >> j) & 1u) store_px(di0 + j * pg.dst_w, v[j]);
+                    }
+                }
+                if (MASK) {
+                    Fetch2<1> f[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) fetch2_request<1>(mask_words, mask_mis, pg.src_w, tap[j], f[j]);
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        uint32_t v[1];
+                        fetch2_blend<1>(f[j], tap[j], v);
+                        if ((live >> j) & 1u) pg.dst_mask[di0 + j * pg.dst_w] = (uint8_t)v[0];
+                    }
+                }
+                if (SCORE) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const float v = bilinear_f32(pg.src_score, pg.src_h, pg.src_w, pg.src_w, X[j], Y[j]);
+                        if ((live >> j) & 1u) pg.dst_score[di0 + j * pg.dst_w] = v;
+                    }
+                }
+            };
             Tap2 tap[R];
             bool outside = false;
 #pragma unroll
@@ -854,44 +897,16 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 tap[j] = tap2_plain(X[j], Y[j]);
                 outside |= tap2_outside(tap[j], pg.src_h, pg.src_w);
             }
-            if (outside) {  // rare: footprints that leave the image, all behind one branch
+            if (outside) {  // rare: footprints that leave the image; its own copy of the band's
+                            // code, so that the common path carries no merged values
+                Tap2 tb[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if (tap2_outside(tap[j], pg.src_h, pg.src_w)) tap[j] = tap2_border(X[j], Y[j], pg.src_h, pg.src_w);
-            }
-            if (C > 0) {
-                Fetch2<CC> f[R];
-#pragma unroll
-                for (int j = 0; j < R; ++j) fetch2_request<CC>(img_words, img_mis, img_pitch, tap[j], f[j]);
-                uint32_t v[R][CC];
-#pragma unroll
-                for (int j = 0; j < R; ++j) fetch2_blend<CC>(f[j], tap[j], v[j]);
-                if (interior) {
-#pragma unroll
-                    for (int j = 0; j < R; ++j) store_px(di0 + j * pg.dst_w, v[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if ((live >> j) & 1u) store_px(di0 + j * pg.dst_w, v[j]);
-                }
-            }
-            if (MASK) {
-                Fetch2<1> f[R];
-#pragma unroll
-                for (int j = 0; j < R; ++j) fetch2_request<1>(mask_words, mask_mis, pg.src_w, tap[j], f[j]);
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    uint32_t v[1];
-                    fetch2_blend<1>(f[j], tap[j], v);
-                    if ((live >> j) & 1u) pg.dst_mask[di0 + j * pg.dst_w] = (uint8_t)v[0];
-                }
-            }
-            if (SCORE) {
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const float v = bilinear_f32(pg.src_score, pg.src_h, pg.src_w, pg.src_w, X[j], Y[j]);
-                    if ((live >> j) & 1u) pg.dst_score[di0 + j * pg.dst_w] = v;
-                }
+                    tb[j] = tap2_outside(tap[j], pg.src_h, pg.src_w) ? tap2_border(X[j], Y[j], pg.src_h, pg.src_w)
+                                                                     : tap[j];
+                emit(tb);
+            } else {
+                emit(tap);
             }
             }  // sub-band
         }  // band

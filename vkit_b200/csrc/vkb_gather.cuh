@@ -206,8 +206,8 @@ __device__ __forceinline__ void fetch2_request(const uint32_t* __restrict__ base
     if (C == 3) {
         const uint32_t* __restrict__ q0 = base + (o0 >> 2);
         const uint32_t* __restrict__ q1 = base + (o1 >> 2);
-        f.a[3 % (C == 3 ? 4 : 2)] = (uint32_t)o0 & 3u;
-        f.b[3 % (C == 3 ? 4 : 2)] = (uint32_t)o1 & 3u;
+        f.a[3 % (C == 3 ? 4 : 2)] = ((uint32_t)o0 & 3u) * 8u;
+        f.b[3 % (C == 3 ? 4 : 2)] = ((uint32_t)o1 & 3u) * 8u;
         f.a[0] = __ldg(q0);
         f.a[1] = __ldg(q0 + 1);
         f.b[0] = __ldg(q1);
@@ -234,10 +234,32 @@ __device__ __forceinline__ void fetch2_request(const uint32_t* __restrict__ base
     }
 }
 
-// RGB row: align the 6 bytes (funnel shifts), pair the channels (PRMT):
+// RGB taps addressed in BITS: `pitch8` = 8 * pitch, `mis8` = 8 * (base & 3); the word index is
+// the bit offset >> 5 and the funnel shift takes its low five bits by itself, so a row costs
+// no separate shift amount.  For planes below 2^28 bytes (the caller checks).
+__device__ __forceinline__ void fetch2_request_rgb_bits(const uint32_t* __restrict__ base, int mis8,
+                                                        int pitch8, const Tap2& t, Fetch2<3>& f) {
+    const int o0 = t.ys * pitch8 + (t.xs * 24 + mis8);
+    const int o1 = o0 + pitch8;
+    const uint32_t* __restrict__ q0 = base + (o0 >> 5);
+    const uint32_t* __restrict__ q1 = base + (o1 >> 5);
+    f.a[3] = (uint32_t)o0;
+    f.b[3] = (uint32_t)o1;
+    f.a[0] = __ldg(q0);
+    f.a[1] = __ldg(q0 + 1);
+    f.b[0] = __ldg(q1);
+    f.b[1] = __ldg(q1 + 1);
+    f.a[2] = 0u;
+    f.b[2] = 0u;
+    // only a byte offset of 3 pushes the 6 bytes into a third word
+    if ((~(uint32_t)o0 & 24u) == 0u) f.a[2] = __ldg(q0 + 2);
+    if ((~(uint32_t)o1 & 24u) == 0u) f.b[2] = __ldg(q1 + 2);
+}
+
+// RGB row: align the 6 bytes (funnel shifts by w[3] mod 32 bits), pair the channels (PRMT):
 //   rg = R0 R1 G0 G1,  bb = B0 B1 . .
 __device__ __forceinline__ void rgb_row_pairs(const uint32_t* w, uint32_t& rg, uint32_t& bb) {
-    const uint32_t sh = w[3] * 8u;
+    const uint32_t sh = w[3];
     const uint32_t lo = __funnelshift_r(w[0], w[1], sh);  // R0 G0 B0 R1
     const uint32_t hi = __funnelshift_r(w[1], w[2], sh);  // G1 B1 .  .
     rg = __byte_perm(lo, hi, 0x4130);

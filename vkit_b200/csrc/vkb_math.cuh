@@ -200,8 +200,9 @@ VKB_HD void cell_coord(const double* __restrict__ H, int x, int y, int& X, int& 
 // the cell's base  B = 2^kFastBits * 32 * s0 + 2^(kFastBits-1) - margin - (bits of the magic)
 // t = bits + B  has  X = t >> kFastBits  and  p = t & (2^kFastBits - 1)  = distance of the estimate
 // from the tie below minus `margin`: accepted when p <= 2^kFastBits - 1 - 2 * margin.  One FMA,
-// one add, one shift, one AND and one compare per axis (the float form of the same test -- two
-// parities, two thresholds -- cost eight).  margin = ceil((h_max + eps) * 2^kFastBits) for the
+// one add, one shift and one AND per axis, one max, two logic ops and a subtraction per pixel
+// whose sign is the verdict (the float form of the same test -- two parities, two thresholds,
+// a range test -- cost twenty per pixel).  margin = ceil((h_max + eps) * 2^kFastBits) for the
 // largest source coordinate of the page.  tests/test_hostsim.py audits all of this on every
 // golden grid case (observed evaluation error incl. the rounding is > 3x below kFastSlack;
 // 0 wrong results among accepted pixels).
@@ -279,19 +280,22 @@ VKB_HD float fma_rn_f32(float a, float b, float c) {
 }
 
 // one axis: n * r = float32 estimate of kFastUnits * 32 * du, base = fast_base(s0, margin).
-// Returns the acceptance test; X = 32 * s0 + rint(32 * du) when it holds.  (A sum outside
-// [2^23, 2^24) -- |32*du| >= kFastRange, inf, nan -- is caught by fast_pair_in_range.)
-VKB_HD bool fast_axis(float n, float r, int base, int limit, int& X, int& bits) {
+// X = 32 * s0 + rint(32 * du) when the axis is accepted; returns p, the position inside the
+// acceptance window (accepted: p <= limit); bits = the sum itself for the range test.
+VKB_HD int fast_axis(float n, float r, int base, int& X, int& bits) {
     union { float f; int i; } v;
     v.f = fma_rn_f32(n, r, kRoundMagic);  // low mantissa bits = rint(n * r), half to even
     bits = v.i;
     const int t = v.i + base;
     X = t >> kFastBits;
-    return (t & (kFastOne - 1)) <= limit;
+    return t & (kFastOne - 1);
 }
-// both sums have the exponent of the magic number
-VKB_HD bool fast_pair_in_range(int bits_x, int bits_y) {
-    return (uint32_t)((bits_x ^ 0x4B000000) | (bits_y ^ 0x4B000000)) < 0x00800000u;
+// Verdict of a pixel from both axes: >= 0 accepted, < 0 rejected.  A sum whose exponent is not
+// the magic number's (|32*du| >= kFastRange, inf, nan) sets a bit above the window positions.
+VKB_HD int fast_verdict(int px, int py, int bits_x, int bits_y, int limit) {
+    const int p = px > py ? px : py;
+    const int c = p | (((bits_x ^ 0x4B000000) | (bits_y ^ 0x4B000000)) & 0x7F800000);  // < 2^31
+    return limit - c;
 }
 
 // The three linear forms are evaluated column part first: the part that depends on the pixel's
@@ -307,9 +311,10 @@ VKB_HD void cell_column(const CellLocal& L, float xr, CellColumn& c) {
     c.d = fma_rn_f32(L.g, xr, 1.0f);
 }
 
-// one row of a prepared column: (a1, b1, h) = L.a1, L.b1, L.h
-VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h, float yr, int xb,
-                                int yb, int limit, int& X, int& Y) {
+// one row of a prepared column: (a1, b1, h) = L.a1, L.b1, L.h.  Returns the verdict (>= 0:
+// accepted, the sign bit marks a pixel for the float64 path).
+VKB_HD int cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h, float yr, int xb,
+                               int yb, int limit, int& X, int& Y) {
     const float d = fma_rn_f32(h, yr, c.d);
     const float nx = fma_rn_f32(a1, yr, c.nx);
     const float ny = fma_rn_f32(b1, yr, c.ny);
@@ -320,18 +325,26 @@ VKB_HD bool cell_coord_fast_row(const CellColumn& c, float a1, float b1, float h
     const float r = 1.0f / d;
 #endif
     int bx, by;
-    const bool okx = fast_axis(nx, r, xb, limit, X, bx);
-    const bool oky = fast_axis(ny, r, yb, limit, Y, by);
-    // NaN / inf anywhere -> false (the exponent test fails)
-    return okx && oky && fast_pair_in_range(bx, by);
+    const int px = fast_axis(nx, r, xb, X, bx);
+    const int py = fast_axis(ny, r, yb, Y, by);
+    return fast_verdict(px, py, bx, by, limit);
 }
 
-// (xr, yr): pixel - tile origin as floats (exact small integers).
-VKB_HD bool cell_coord_fast(const CellLocal& L, float xr, float yr, int xb, int yb, int limit,
-                            int& X, int& Y) {
+// (xr, yr): pixel - tile origin as floats (exact small integers).  Verdict as above.
+VKB_HD int cell_coord_fast(const CellLocal& L, float xr, float yr, int xb, int yb, int limit,
+                           int& X, int& Y) {
     CellColumn c;
     cell_column(L, xr, c);
     return cell_coord_fast_row(c, L.a1, L.b1, L.h, yr, xb, yb, limit, X, Y);
+}
+
+// collects the sign bit of a verdict: acc = acc << 1 | (verdict < 0)
+VKB_HD uint32_t fast_collect(uint32_t acc, int verdict) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l((uint32_t)verdict, acc, 1);
+#else
+    return (acc << 1) | ((uint32_t)verdict >> 31);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
