@@ -1443,10 +1443,8 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
         pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
     rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
-    if (side) {
-        VKB_CUDA(cudaEventRecord(side->join, side->stream));
-        VKB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    }
+    // (the caller's stream joins the masks after the tile lists: only the remap reads them)
+    if (side) VKB_CUDA(cudaEventRecord(side->join, side->stream));
     grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);
     grid_tile_offsets_kernel<<<n_pages, 1024, 0, st>>>(meta, t_max, tile_count, tile_off);
     rc = check_launch("grid_tile_offsets_kernel");
@@ -1455,7 +1453,10 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
         pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
         tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
         reinterpret_cast<RemapTile*>(tile_headers), large);
-    return check_launch("grid_tile_records_kernel");
+    rc = check_launch("grid_tile_records_kernel");
+    if (rc) return rc;
+    if (side) VKB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return VKB_OK;
 }
 
 extern "C" int vkb_grid_points(const double* hfwd_page, int32_t cols_minus_1, const double* xy_in,
