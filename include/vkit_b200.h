@@ -193,7 +193,7 @@ int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes, in
  *               launch (count + entries: more than 15 candidates or the exact slow path) and, last,
  *               the work counter vkb_grid_remap resets and its small-tile kernel draws from; opaque */
 #define VKB_TILE_SLOT_BYTES 64
-#define VKB_TILE_HEADER_BYTES 32
+#define VKB_TILE_HEADER_BYTES 64
 int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32_t p_max, int32_t c_max,
                    int32_t t_max, int32_t s_cap, const int32_t* lattice_i, vkb_grid_meta* meta,
                    double* hinv, double* hfwd, int32_t* cell_box, uint32_t* cell_masks,

@@ -196,7 +196,7 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
                                    const int32_t* owner, long long* stats) {
     const int ccols = pg->cols - 1, C = (pg->rows - 1) * ccols;
     std::vector<double> hinv((size_t)C * 9);
-    std::vector<int> sx(C), sy(C);
+    std::vector<int> sx(C), sy(C), bx0(C), by0(C), big(C);
     for (int cell = 0; cell < C; ++cell) {
         const int r = cell / ccols, c = cell % ccols;
         const int i00 = r * pg->cols + c, i01 = i00 + 1, i11 = i00 + pg->cols + 1, i10 = i00 + pg->cols;
@@ -209,6 +209,15 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
         homography_4pt(dq, sq, &hinv[(size_t)cell * 9]);
         sx[cell] = sx0;
         sy[cell] = sy0;
+        // bbox of the dst cell: the origin its float32 form is re-centred on (grid_cells_kernel)
+        int x0 = px[0], x1 = px[0], y0 = py[0], y1 = py[0];
+        for (int k = 1; k < 4; ++k) {
+            x0 = px[k] < x0 ? px[k] : x0; x1 = px[k] > x1 ? px[k] : x1;
+            y0 = py[k] < y0 ? py[k] : y0; y1 = py[k] > y1 ? py[k] : y1;
+        }
+        bx0[cell] = x0;
+        by0[cell] = y0;
+        big[cell] = (x1 - x0 + 32) / 32 != 1 || y1 - y0 + 1 > VKB_CELL_MASK_WORDS;  // float64 path only
     }
     const int extent = pg->src_w > pg->src_h ? pg->src_w : pg->src_h;
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
@@ -217,8 +226,9 @@ extern "C" void hs_fast_path_stats(const vkb_grid_page* pg, const int32_t* lat, 
             const int o = owner[(size_t)y * W + x];
             if (o < 0) continue;
             stats[0]++;
-            // the kernel's form: re-centred on the origin of the pixel's 32 x 32 tile
-            const int ox = x & ~31, oy = y & ~31;
+            // the kernel's form: re-centred on the origin of the owner's bbox
+            if (big[o]) continue;
+            const int ox = bx0[o], oy = by0[o];
             CellLocal L;
             make_cell_local(&hinv[(size_t)o * 9], sx[o], sy[o], ox, oy, L);
             int Xe, Ye, Xf, Yf;

@@ -18,7 +18,7 @@ CELL_MASK_WORDS = 32
 TILE = 32
 TILE_CAP = 64
 TILE_SLOT_BYTES = 64
-TILE_HEADER_BYTES = 32
+TILE_HEADER_BYTES = 64
 
 BLEND_FLOAT_CONST = 4
 WARP_AFFINE = 0

@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     const vkb_grid_page* __restrict__ pages, int p_max, int c_max, int t_max,
     const int32_t* __restrict__ lattice_i, vkb_grid_meta* __restrict__ meta,
     double* __restrict__ hinv, double* __restrict__ hfwd, int32_t* __restrict__ cell_box,
-    int32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_cells) {
+    int32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_cells,
+    TileSlot* __restrict__ slots, int s_cap) {
     // The 72-byte homographies of a block's 128 consecutive cells are contiguous in global memory:
     // they go through shared memory and leave as coalesced 8-byte stores (one thread storing its own
     // nine doubles touches nine sectors per instruction and throttled the load / store unit).
@@ -562,6 +563,39 @@ __global__ void __launch_bounds__(128) grid_cells_kernel(
     {
         double* __restrict__ ho = hinv + ((size_t)page * c_max + cell0) * 9;
         for (int k = threadIdx.x; k < n_valid * 9; k += blockDim.x) ho[k] = s_h[k];
+    }
+    // the cell's record for the remap (needs the inverse map, still in shared memory here)
+    if (valid) {
+        const int x0 = min(min(dx[0], dx[1]), min(dx[2], dx[3]));
+        const int x1 = max(max(dx[0], dx[1]), max(dx[2], dx[3]));
+        const int y0 = min(min(dy[0], dy[1]), min(dy[2], dy[3]));
+        const int y1 = max(max(dy[0], dy[1]), max(dy[2], dy[3]));
+        const bool big = (x1 - x0 + 32) / 32 != 1 || y1 - y0 + 1 > VKB_CELL_MASK_WORDS;
+        const int r = cell / ccols, c = cell - r * ccols;
+        const int gs = pg.grid_size;
+        double H[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = s_h[threadIdx.x * 9 + i];
+        TileSlot rec;
+        make_cell_local(H, c * gs, r * gs, x0, y0, rec.loc);
+        // The float32 form is audited for arguments up to one mask window (tests/hostsim); larger
+        // cells and pages whose coordinates overflow the fixed point take the float64 path (NaN).
+        if (big || !fast_page_ok(max(pg.src_h, pg.src_w))) rec.loc.a2 = __int_as_float(0x7fc00000);
+        const int margin = fast_margin(max(r, c) * gs);
+        rec.x0 = x0;
+        rec.y0 = y0;
+        rec.nr = y1 - y0;
+        rec.cellf = cell | (big ? (int)0x80000000 : 0);
+        rec.xm = fast_base(c * gs, margin);
+        rec.ym = fast_base(r * gs, margin);
+        rec.nox = (float)(-x0);
+        rec.noy = (float)(-y0);
+        int4* __restrict__ dst = reinterpret_cast<int4*>(slots + ((size_t)page * s_cap + cell));
+        const int4* src = reinterpret_cast<const int4*>(&rec);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+        dst[3] = src[3];
     }
     if (hfwd) {
         __syncthreads();
@@ -704,18 +738,17 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
 }
 
 // ============================================================================================
-// Per-tile candidate records for the remap kernel.
+// Per-tile candidate lists for the remap kernel.
 //
 //   grid_tile_base_kernel     prefix sum over pages of the number of 32 x 32 dst tiles: the
 //                             remap's flat work list (tile_base[n_pages] = all tiles);
-//   grid_tile_offsets_kernel  block per page: exclusive scan of the candidate counts of the
-//                             page's tiles -> where each tile's records start;
-//   grid_tile_records_kernel  warp per tile, lane per candidate: rank the candidates by cell
-//                             index (the remap resolves "last writer wins" by letting later
-//                             records overwrite earlier ones) and write one 64-byte record per
-//                             candidate: bbox, packed (slot, cell column, cell row) and the
-//                             float32 form of the cell's inverse homography re-centred on the
-//                             tile origin (CellLocal, built here from the float64 matrix).
+//   grid_tile_lists_kernel    half a warp per tile: the tile's candidates in ascending cell order
+//                             and its header.  (The 64-byte record of a candidate -- bbox and the
+//                             float32 form of the cell's inverse homography, CellLocal -- exists
+//                             once per CELL, written by grid_cells_kernel and re-centred on the
+//                             cell's bbox origin; round 2's first version wrote one per
+//                             (tile, cell) pair, re-centred on the tile: 2.2 x the float64 work
+//                             and 280 MB per 256 pages, 119 us.)
 // ============================================================================================
 // exclusive scan of v over the block (1024 threads); returns the exclusive prefix, adds the
 // block total to `carry` (shared).
@@ -762,63 +795,62 @@ __global__ void __launch_bounds__(1024) grid_tile_base_kernel(const vkb_grid_met
     if (threadIdx.x == 0) tile_base[n_pages] = carry;
 }
 
-__global__ void __launch_bounds__(1024) grid_tile_offsets_kernel(
-    const vkb_grid_meta* __restrict__ meta, int t_max, const int32_t* __restrict__ tile_count,
-    int32_t* __restrict__ tile_off) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
-    const int page = blockIdx.x;
-    const int tiles = min(page_tiles(meta[page]), t_max);
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < tiles; base += 1024) {
-        const int t = base + threadIdx.x;
-        int v = 0;
-        if (t < tiles) {
-            v = tile_count[(size_t)page * t_max + t];
-            if (v > VKB_TILE_CAP) v = 0;  // overflowing tiles keep no records (slow path)
-        }
-        const int ex = block_exclusive_scan_1024(v, warp_sums, &carry);
-        if (t < tiles) tile_off[(size_t)page * t_max + t] = ex;
-    }
-}
-
-__global__ void __launch_bounds__(128) grid_tile_records_kernel(
+// Half a warp per tile: ranks the tile's candidate cells by cell index (the remap resolves "last
+// writer wins" by letting later candidates overwrite earlier ones), writes the sorted list behind
+// the page's cell records and the tile's header: page, origin, count, the acceptance limit of
+// the fast path and the first 16 sorted candidates packed for the small-tile kernel.
+__global__ void __launch_bounds__(128) grid_tile_lists_kernel(
     const vkb_grid_page* __restrict__ pages, const vkb_grid_meta* __restrict__ meta, int c_max,
-    int t_max, int s_cap, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
-    const int32_t* __restrict__ tile_count, const uint16_t* __restrict__ tile_cells,
-    const int32_t* __restrict__ tile_off, const int32_t* __restrict__ tile_base,
+    int t_max, int s_cap, const int32_t* __restrict__ tile_count,
+    const uint16_t* __restrict__ tile_cells, const int32_t* __restrict__ tile_base,
     TileSlot* __restrict__ slots, RemapTile* __restrict__ headers, int32_t* __restrict__ large) {
-    // HALF a warp per tile (a tile has 8.7 candidates on average, 64 at most): lane l of the half
-    // takes candidates l, l + 16, ...; a candidate's rank = the number of smaller cell indices in
-    // the tile's list (read back from L1, the same address for the whole half warp).
+    __shared__ uint16_t s_sorted[8][VKB_TILE_CAP];
+    __shared__ uint16_t s_raw[8][VKB_TILE_CAP];
     const int page = blockIdx.y;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 4);
+    const int half = threadIdx.x >> 4;
+    const int t = blockIdx.x * 8 + half;
     const int lane = threadIdx.x & 15;
     const int dst_w = meta[page].dst_w;
     const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
     if (t >= min(page_tiles(meta[page]), t_max)) return;
     const size_t pt = (size_t)page * t_max + t;
     const int count = tile_count[pt];
-    const int off = tile_off[pt];
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    const bool usable = count <= VKB_TILE_CAP && off + count <= s_cap;
+    const bool usable = count <= VKB_TILE_CAP;
+    const unsigned half_mask = 0xFFFFu << (threadIdx.x & 16);
     const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
-    const int ccols = pages[page].cols - 1;
-    const int gs = pages[page].grid_size;
-    // acceptance margin of the fast path: from the largest source corner among the tile's cells
-    int margin = 0;
+    uint16_t* sorted = s_sorted[half];
+    uint16_t* raw = s_raw[half];
+    int reach = 0;
     if (usable) {
-        int reach = 0;
+        // the bin goes through shared memory (one coalesced read); ranks come from broadcast reads
+        for (int s = lane; s < count; s += 16) raw[s] = cells[s];
+        __syncwarp(half_mask);
+        const int ccols = pages[page].cols - 1;
         for (int s = lane; s < count; s += 16) {
-            const int cell = (int)cells[s];
+            const int cell = (int)raw[s];
+            int rank = 0;
+            for (int j = 0; j < count; ++j) rank += (int)raw[j] < cell;
+            sorted[rank] = (uint16_t)cell;
             const int r = cell / ccols, c = cell - r * ccols;
             reach = max(reach, max(r, c));
         }
-        const unsigned half = 0xFFFFu << (threadIdx.x & 16);
 #pragma unroll
-        for (int d = 8; d >= 1; d >>= 1) reach = max(reach, __shfl_xor_sync(half, reach, d));
-        margin = fast_margin(reach * gs);
+        for (int d = 8; d >= 1; d >>= 1) reach = max(reach, __shfl_xor_sync(half_mask, reach, d));
+    }
+    __syncwarp(half_mask);
+    RemapTile* __restrict__ hd = headers + (tile_base[page] + t);
+    if (usable) {
+        // the sorted list: behind the page's cell records (tile_list), two 16-bit entries per lane and step
+        uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(
+            const_cast<uint16_t*>(tile_list(slots, page, s_cap, c_max, t)));
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(sorted);
+        for (int w = lane; 2 * w < count; w += 16) out[w] = sw[w];  // (an odd count copies one stale entry)
+        if (lane < 8) {
+            const uint32_t lo = lane < count ? sorted[lane] : 0u;
+            const uint32_t hi = lane + 8 < count ? sorted[lane + 8] : 0u;
+            hd->ids[lane] = lo | (hi << 16);
+        }
     }
     if (lane == 0) {
         RemapTile h;
@@ -826,49 +858,15 @@ __global__ void __launch_bounds__(128) grid_tile_records_kernel(
         h.tx0 = tx * VKB_TILE;
         h.ty0 = ty * VKB_TILE;
         h.count = usable ? count : -1;
-        h.rec = page * s_cap + off;
-        h.lim = fast_limit(margin);
+        h.tile = t;
+        h.lim = fast_limit(fast_margin(reach * pages[page].grid_size));
         h.pad[0] = h.pad[1] = 0;
-        const int index = tile_base[page] + t;
-        int4* __restrict__ dst = reinterpret_cast<int4*>(headers + index);
+        int4* __restrict__ dst = reinterpret_cast<int4*>(hd);
         const int4* src = reinterpret_cast<const int4*>(&h);
         dst[0] = src[0];
         dst[1] = src[1];
         // tiles outside the lane-per-row owner path go on the second launch's work list
-        if ((unsigned)h.count > (unsigned)kPlaneCands) large[1 + atomicAdd(large, 1)] = index;
-    }
-    if (!usable) return;  // the remap takes its slow path
-    const size_t page_cell0 = (size_t)page * c_max;
-    const bool fast_ok = fast_page_ok(max(pages[page].src_h, pages[page].src_w));
-    for (int s = lane; s < count; s += 16) {
-        const int cell = (int)cells[s];
-        // the cell's box and homography are requested first: their (L2) latency then runs under
-        // the ranking loop instead of after it
-        const int4 b = cell_box[page_cell0 + cell];
-        double H[9];
-        const double* __restrict__ hp = hinv + (page_cell0 + cell) * 9;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) H[i] = hp[i];
-        int rank = 0;
-        for (int j = 0; j < count; ++j) rank += (int)cells[j] < cell;
-        const int r = cell / ccols, c = cell - r * ccols;
-        TileSlot rec;
-        make_cell_local(H, c * gs, r * gs, tx * VKB_TILE, ty * VKB_TILE, rec.loc);
-        rec.x0 = b.x;
-        rec.y0 = b.y;
-        rec.nr = b.w - b.y;
-        rec.cellf = cell | ((b.z & 0x40000000) ? (int)0x80000000 : 0);
-        if (!fast_ok) rec.loc.a2 = __int_as_float(0x7fc00000);  // NaN: every pixel takes the exact path
-        rec.xm = fast_base(c * gs, margin);
-        rec.ym = fast_base(r * gs, margin);
-        rec.info = rank | (c << 6) | (r << 16);
-        rec.pad = 0;
-        int4* __restrict__ dst = reinterpret_cast<int4*>(slots + ((size_t)page * s_cap + off + rank));
-        const int4* src = reinterpret_cast<const int4*>(&rec);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
-        dst[3] = src[3];
+        if ((unsigned)h.count > (unsigned)kPlaneCands) large[1 + atomicAdd(large, 1)] = tile_base[page] + t;
     }
 }
 
@@ -1412,13 +1410,15 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
                               void* tile_headers, void* stream) {
     VKB_NVTX("vkb_grid_build");
     VKB_REQUIRE(pages && lattice_i && meta && hinv && cell_box && cell_masks && tile_count
-                    && tile_cells && tile_off && tile_base && tile_slots && tile_headers,
+                    && tile_cells && tile_base && tile_slots && tile_headers,
                 "bad arguments");
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
     VKB_REQUIRE(c_max > 0 && c_max <= 65535, "at most 65535 cells per page");
     VKB_REQUIRE(t_max > 0 && s_cap > 0, "empty tile workspace");
     VKB_REQUIRE((long long)n_pages * t_max < (1ll << 31), "too many tiles in one launch");
     VKB_REQUIRE((long long)n_pages * s_cap < (1ll << 31), "too many tile records in one launch");
+    VKB_REQUIRE(s_cap >= c_max + 2 * t_max, "s_cap holds the cell records and the tile lists: >= c_max + 2 * t_max");
+    (void)tile_off;  // (kept in the signature: earlier layouts kept per-tile record offsets here)
     cudaStream_t st = (cudaStream_t)stream;
     VKB_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * (size_t)n_pages * t_max, st));
     // the list of large tiles lives behind the headers: [count, tile index ...]
@@ -1440,20 +1440,17 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     int rc = check_launch("grid_masks_kernel");
     if (rc) return rc;
     grid_cells_kernel<<<dim3((c_max + 127) / 128, n_pages), 128, 0, st>>>(
-        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells);
+        pages, p_max, c_max, t_max, lattice_i, meta, hinv, hfwd, cell_box, tile_count, tile_cells,
+        reinterpret_cast<TileSlot*>(tile_slots), s_cap);
     rc = check_launch("grid_cells_kernel");
     if (rc) return rc;
     // (the caller's stream joins the masks after the tile lists: only the remap reads them)
     if (side) VKB_CUDA(cudaEventRecord(side->join, side->stream));
     grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);
-    grid_tile_offsets_kernel<<<n_pages, 1024, 0, st>>>(meta, t_max, tile_count, tile_off);
-    rc = check_launch("grid_tile_offsets_kernel");
-    if (rc) return rc;
-    grid_tile_records_kernel<<<dim3((t_max + 7) / 8, n_pages), 128, 0, st>>>(
-        pages, meta, c_max, t_max, s_cap, hinv, reinterpret_cast<const int4*>(cell_box), tile_count,
-        tile_cells, tile_off, tile_base, reinterpret_cast<TileSlot*>(tile_slots),
-        reinterpret_cast<RemapTile*>(tile_headers), large);
-    rc = check_launch("grid_tile_records_kernel");
+    grid_tile_lists_kernel<<<dim3((t_max + 7) / 8, n_pages), 128, 0, st>>>(
+        pages, meta, c_max, t_max, s_cap, tile_count, tile_cells, tile_base,
+        reinterpret_cast<TileSlot*>(tile_slots), reinterpret_cast<RemapTile*>(tile_headers), large);
+    rc = check_launch("grid_tile_lists_kernel");
     if (rc) return rc;
     if (side) VKB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     return VKB_OK;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
     int c_max, int p_max, const double* __restrict__ hinv, const int4* __restrict__ cell_box,
     const uint32_t* __restrict__ cell_masks, const int32_t* __restrict__ tile_base,
     const RemapTile* __restrict__ headers, const TileSlot* __restrict__ slots,
-    const int32_t* __restrict__ lattice_i, const int32_t* __restrict__ large) {
+    const int32_t* __restrict__ lattice_i, const int32_t* __restrict__ large, int s_cap) {
     constexpr int kWarps = VKB_TILE / R;
     __shared__ __align__(16) TileSlot sm_all[kWarps][kWarpSlots];
     const int tid = threadIdx.x;
@@ -123,14 +123,20 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
         if (LARGE) index = large[1 + index];
         const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
-        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x; t.lim = b.y;
+        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.tile = b.x; t.lim = b.y;
         return t;
     };
-    auto stage = [&](const RemapTile& t, int base) {  // this warp's copies of one tile's records
+    // this warp's copies of the records of one tile's candidate cells, in the order of the
+    // tile's sorted list (four 16-byte pieces per record)
+    auto stage = [&](const RemapTile& t, int base) {
         const int chunks = t.count * (VKB_TILE_SLOT_BYTES / 16);  // <= 256; negative on the slow path
-        const char* g = reinterpret_cast<const char*>(slots + t.rec);
+        const uint16_t* __restrict__ list = tile_list(slots, t.page, s_cap, c_max, t.tile);
+        const char* g = reinterpret_cast<const char*>(slots + (size_t)t.page * s_cap);
         char* d = reinterpret_cast<char*>(sm + base);
-        for (int i = lane; i < chunks; i += 32) cp_async_16(d + i * 16, g + i * 16);
+        for (int i = lane; i < chunks; i += 32) {
+            const int cell = (int)__ldg(list + (i >> 2));
+            cp_async_16(d + i * 16, g + (size_t)cell * VKB_TILE_SLOT_BYTES + (i & 3) * 16);
+        }
         cp_async_commit();
     };
 
@@ -303,16 +309,17 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
                 // ---- coordinates -----------------------------------------------------------
                 // uncovered pixels keep map value (0, 0); the fast path is evaluated for every
                 // pixel (slot 0 for uncovered ones) and the result selected afterwards
-                const float xr = (float)lane;
-                const float yr0 = (float)(band * R);
+                const float xr = (float)x;
+                const float yr0 = (float)ry0;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const bool covered = key[j] >= 0;
-                    if (fast) {
-                        const int slot = covered ? key[j] : 0;
+                    if (fast && covered) {
+                        const int slot = key[j];
                         const int2 base = *reinterpret_cast<const int2*>(&S[slot].xm);
-                        const bool ok = cell_coord_fast(S[slot].loc, xr, yr0 + (float)j, base.x, base.y,
-                                                        fast_lim, X[j], Y[j]) >= 0;
+                        const float2 no = *reinterpret_cast<const float2*>(&S[slot].nox);
+                        const bool ok = cell_coord_fast(S[slot].loc, xr + no.x, yr0 + (float)j + no.y,
+                                                        base.x, base.y, fast_lim, X[j], Y[j]) >= 0;
                         if (covered && !ok) {
                             const int cell = S[slot].cellf & 0x7FFFFFFF;
                             const int2 e = cell_coord_exact(hinv + (page_cell0 + cell) * 9, x, ry0 + j);
@@ -545,13 +552,19 @@ __device__ __noinline__ void remap_pixel_exact(const RemapPage pg, const double*
     if (SCORE) pg.dst_score[di] = bilinear_f32(pg.src_score, pg.src_h, pg.src_w, pg.src_w, X, Y);
 }
 
+// a tile header as the small-tile kernel carries it (uniform across the warp but `ids`)
+struct TileHead {
+    int page, tx0, ty0, count, lim;
+    uint32_t ids;  // the lane's two candidate cells
+};
+
 template <int C, bool MASK, bool SCORE>
 __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK, SCORE>())) grid_remap_tiles_kernel(
     const vkb_planes* __restrict__ planes, const vkb_grid_page* __restrict__ pages, int n_pages,
     int c_max, int p_max, const double* __restrict__ hinv, const uint32_t* __restrict__ cell_masks,
     const int32_t* __restrict__ tile_base, const RemapTile* __restrict__ headers,
     const TileSlot* __restrict__ slots, const int32_t* __restrict__ lattice_i,
-    int32_t* __restrict__ work_counter) {
+    int32_t* __restrict__ work_counter, int s_cap) {
     constexpr int CC = C > 0 ? C : 1;
     __shared__ __align__(16) TileSlot sm_all[kTilesWarps][kTilesSlots];
     const int tid = threadIdx.x;
@@ -581,28 +594,36 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
         TileSlot z = {};
         z.xm = kFastBaseZero;
         z.ym = kFastBaseZero;
+        z.nox = z.noy = 0.f;
         sm[lane * kTilesHalf] = z;
     }
     __syncwarp();
 
     auto load_header = [&](int index) {
-        RemapTile t;
+        TileHead t;
         index = min(index, total - 1);
         const int4* __restrict__ src = reinterpret_cast<const int4*>(headers + index);
         const int4 a = __ldg(src), b = __ldg(src + 1);
-        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.rec = b.x; t.lim = b.y;
+        t.page = a.x; t.tx0 = a.y; t.ty0 = a.z; t.count = a.w; t.lim = b.y;
+        // the lane's two candidates (lane / 4 and lane / 4 + 8 of the sorted list), requested with
+        // the header: staging needs no second trip to memory
+        t.ids = __ldg(reinterpret_cast<const uint32_t*>(src + 2) + (lane >> 2));
         return t;
     };
-    auto mine = [](const RemapTile& t) { return (unsigned)t.count <= (unsigned)kPlaneCands; };
-    auto stage = [&](const RemapTile& t, int base) {  // candidates go behind the half's record 0
-        const int chunks = t.count * (VKB_TILE_SLOT_BYTES / 16);  // <= 60
-        const char* g = reinterpret_cast<const char*>(slots + t.rec);
-        char* d = reinterpret_cast<char*>(sm + base + 1);
-        for (int i = lane; i < chunks; i += 32) cp_async_16(d + i * 16, g + i * 16);
+    auto mine = [](const TileHead& t) { return (unsigned)t.count <= (unsigned)kPlaneCands; };
+    // The records of the tile's candidate cells go behind the half's record 0, in list order:
+    // four lanes copy one 64-byte record, two rounds cover the 15 candidates.
+    auto stage = [&](const TileHead& t, int base) {
+        const char* g = reinterpret_cast<const char*>(slots + (size_t)t.page * s_cap) + (lane & 3) * 16;
+        char* d = reinterpret_cast<char*>(sm + base + 1) + lane * 16;
+        if ((lane >> 2) < t.count)
+            cp_async_16(d, g + (size_t)(t.ids & 0xFFFFu) * VKB_TILE_SLOT_BYTES);
+        if ((lane >> 2) + 8 < t.count)
+            cp_async_16(d + 8 * VKB_TILE_SLOT_BYTES, g + (size_t)(t.ids >> 16) * VKB_TILE_SLOT_BYTES);
         cp_async_commit();
     };
 
-    RemapTile h0 = load_header(tile_at(0)), h1 = load_header(tile_at(1));
+    TileHead h0 = load_header(tile_at(0)), h1 = load_header(tile_at(1));
     int cur_base = 0;
     bool cur_staged = false;
     auto advance = [&]() {  // next tile of this warp's sequence
@@ -629,7 +650,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
     float fill_score = 0.f;
 
     while (tile_at(0) < total) {
-        const RemapTile cur = h0;
+        const TileHead cur = h0;
         if (!mine(cur)) {  // the large-tile launch's tile (never staged ahead)
             advance();
             continue;
@@ -760,7 +781,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
         q2 = rotr32(q2, 24);
         q3 = rotr32(q3, 20);
         uint32_t failbits = 0;  // rows of this column left to the float64 path
-        const float xr = (float)lane;
+        const float xr = (float)x;  // absolute column: a cell's form takes pixel - bbox origin
 
 #pragma unroll 1
         for (int band = 0; band < VKB_TILE / 4; ++band) {
@@ -785,7 +806,7 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
             if (R < 4 && ry0 + jb >= pg.dst_h) break;
             int X[R], Y[R];
             uint32_t fail4 = 0;
-            const float yr0 = (float)(band * 4 + jb);
+            const float yr0 = (float)(ry0 + jb);
 #if VKB_TILES_SHARE_COLUMN
             // Nearly every band lies inside one row of cells: every lane then has ONE owner for its
             // four rows (each plane's nibble is 0 or F), and the column part of the cell's three
@@ -793,14 +814,15 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
             if (R == 4 && __all_sync(0xffffffffu, ((own & 0x1111u) * 0xFu) == own)) {
                 const uint32_t id = ((own & 0x1111u) * 0x12480000u) >> 28;
                 const TileSlot* __restrict__ sp = S + id;
-                const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
+                const int4 base = *reinterpret_cast<const int4*>(&sp->xm);  // xm, ym, nox, noy
                 CellColumn col;
-                cell_column(sp->loc, xr, col);
+                cell_column(sp->loc, xr + __int_as_float(base.z), col);
                 const float a1 = sp->loc.a1, b1 = sp->loc.b1, hh = sp->loc.h;
+                const float yc = yr0 + __int_as_float(base.w);
                 // verdicts collected from the last row down: bit j of fail4 = row j rejected
 #pragma unroll
                 for (int j = R - 1; j >= 0; --j)
-                    fail4 = fast_collect(fail4, cell_coord_fast_row(col, a1, b1, hh, yr0 + (float)j,
+                    fail4 = fast_collect(fail4, cell_coord_fast_row(col, a1, b1, hh, yc + (float)j,
                                                                     base.x, base.y, fast_lim, X[j], Y[j]));
             } else
 #endif
@@ -811,9 +833,10 @@ __global__ void __launch_bounds__(32 * kTilesWarps, (tiles_blocks_per_sm<C, MASK
                 // the multiplication land on distinct bits: no carries)
                 const uint32_t id = (((own >> (jb + j)) & 0x1111u) * 0x12480000u) >> 28;
                 const TileSlot* __restrict__ sp = S + id;
-                const int2 base = *reinterpret_cast<const int2*>(&sp->xm);
-                fail4 = fast_collect(fail4, cell_coord_fast(sp->loc, xr, yr0 + (float)j, base.x, base.y,
-                                                            fast_lim, X[j], Y[j]));
+                const int4 base = *reinterpret_cast<const int4*>(&sp->xm);  // xm, ym, nox, noy
+                fail4 = fast_collect(fail4, cell_coord_fast(sp->loc, xr + __int_as_float(base.z),
+                                                            yr0 + (float)j + __int_as_float(base.w),
+                                                            base.x, base.y, fast_lim, X[j], Y[j]));
             }
             }
             failbits |= fail4 << (band * 4 + jb);
@@ -979,8 +1002,8 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                               void* stream) {
     VKB_NVTX("vkb_grid_remap");
     VKB_REQUIRE(pages && planes && lattice_i && hinv && cell_box && cell_masks && tile_count
-                    && tile_off && tile_base && tile_slots && tile_headers, "bad arguments");
-    (void)s_cap;
+                    && tile_base && tile_slots && tile_headers, "bad arguments");
+    (void)tile_off;
     const int32_t* large = reinterpret_cast<const int32_t*>(
         reinterpret_cast<const char*>(tile_headers) + (size_t)n_pages * t_max * VKB_TILE_HEADER_BYTES);
     VKB_REQUIRE(n_pages > 0 && n_pages <= 65535, "1..65535 pages per launch");
@@ -1000,7 +1023,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
     grid_remap_kernel<CH, M, S, R, LARGE><<<grid, 32 * (VKB_TILE / R), 0, st>>>(               \
         planes, pages, n_pages, c_max, p_max, hinv, reinterpret_cast<const int4*>(cell_box),   \
         cell_masks, tile_base, reinterpret_cast<const RemapTile*>(tile_headers),               \
-        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, large)
+        reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, large, s_cap)
     // The few large tiles run on a side stream next to the main launch (disjoint dst tiles):
     // alone they are a latency-bound tail of ~30 us.
     RemapSide* side = remap_side();
@@ -1024,7 +1047,7 @@ extern "C" int vkb_grid_remap(const vkb_grid_page* pages, const vkb_planes* plan
                                               32 * kTilesWarps, 0, st>>>(                       \
                 planes, pages, n_pages, c_max, p_max, hinv, cell_masks, tile_base,              \
                 reinterpret_cast<const RemapTile*>(tile_headers),                               \
-                reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, work_counter);        \
+                reinterpret_cast<const TileSlot*>(tile_slots), lattice_i, work_counter, s_cap); \
         }                                                                                       \
     } while (0)
     const int key = image_channels * 4 + (has_mask ? 2 : 0) + (has_score ? 1 : 0);

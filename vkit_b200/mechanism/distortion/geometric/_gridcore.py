@@ -180,7 +180,8 @@ class GridBatch:
         self.tile_cells = self._ws('tile_cells', (self.n, self.t_max, nv.TILE_CAP), np.uint16)
         # candidate records of the remap kernel: 16 per tile on average is ample (typical 8-10);
         # a page that needs more falls back to the kernel's slow exact path for the excess tiles
-        self.s_cap = 16 * self.t_max
+        # records of the page: one per cell, then the sorted candidate lists of the tiles
+        self.s_cap = max(16 * self.t_max, self.c_max + 2 * self.t_max)
         self.tile_off = self._ws('tile_off', (self.n, self.t_max), np.int32)
         self.tile_base = self._ws('tile_base', (self.n + 1,), np.int32)
         self.tile_slots = self._ws('tile_slots', (self.n, self.s_cap, nv.TILE_SLOT_BYTES), np.uint8)
