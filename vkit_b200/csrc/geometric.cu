@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(32 * kMaskWarps) grid_masks_kernel(
 //
 //   grid_tile_base_kernel     prefix sum over pages of the number of 32 x 32 dst tiles: the
 //                             remap's flat work list (tile_base[n_pages] = all tiles);
-//   grid_tile_lists_kernel    half a warp per tile: the tile's candidates in ascending cell order
+//   grid_tile_lists_kernel    eight lanes per tile: the tile's candidates in ascending cell order
 //                             and its header.  (The 64-byte record of a candidate -- bbox and the
 //                             float32 form of the cell's inverse homography, CellLocal -- exists
 //                             once per CELL, written by grid_cells_kernel and re-centred on the
@@ -795,21 +795,26 @@ __global__ void __launch_bounds__(1024) grid_tile_base_kernel(const vkb_grid_met
     if (threadIdx.x == 0) tile_base[n_pages] = carry;
 }
 
-// Half a warp per tile: ranks the tile's candidate cells by cell index (the remap resolves "last
-// writer wins" by letting later candidates overwrite earlier ones), writes the sorted list behind
+// Eight lanes per tile: rank the tile's candidate cells by cell index (the remap resolves "last
+// writer wins" by letting later candidates overwrite earlier ones), write the sorted list behind
 // the page's cell records and the tile's header: page, origin, count, the acceptance limit of
-// the fast path and the first 16 sorted candidates packed for the small-tile kernel.
+// the fast path and the first 16 sorted candidates packed for the small-tile kernel.  The kernel
+// is a chain of dependent loads per tile (count -> bin -> stores); what matters is how many tiles
+// are in flight, hence the narrow groups.
+constexpr int kListLanes = 8;
+constexpr int kListTiles = 128 / kListLanes;  // tiles per block
+
 __global__ void __launch_bounds__(128) grid_tile_lists_kernel(
     const vkb_grid_page* __restrict__ pages, const vkb_grid_meta* __restrict__ meta, int c_max,
     int t_max, int s_cap, const int32_t* __restrict__ tile_count,
     const uint16_t* __restrict__ tile_cells, const int32_t* __restrict__ tile_base,
     TileSlot* __restrict__ slots, RemapTile* __restrict__ headers, int32_t* __restrict__ large) {
-    __shared__ uint16_t s_sorted[8][VKB_TILE_CAP];
-    __shared__ uint16_t s_raw[8][VKB_TILE_CAP];
+    __shared__ __align__(4) uint16_t s_sorted[kListTiles][VKB_TILE_CAP];
+    __shared__ __align__(4) uint16_t s_raw[kListTiles][VKB_TILE_CAP];
     const int page = blockIdx.y;
-    const int half = threadIdx.x >> 4;
-    const int t = blockIdx.x * 8 + half;
-    const int lane = threadIdx.x & 15;
+    const int group = threadIdx.x / kListLanes;
+    const int t = blockIdx.x * kListTiles + group;
+    const int lane = threadIdx.x % kListLanes;
     const int dst_w = meta[page].dst_w;
     const int tiles_x = (dst_w + VKB_TILE - 1) / VKB_TILE;
     if (t >= min(page_tiles(meta[page]), t_max)) return;
@@ -817,17 +822,17 @@ __global__ void __launch_bounds__(128) grid_tile_lists_kernel(
     const int count = tile_count[pt];
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const bool usable = count <= VKB_TILE_CAP;
-    const unsigned half_mask = 0xFFFFu << (threadIdx.x & 16);
+    const unsigned group_mask = ((1u << kListLanes) - 1u) << (threadIdx.x & 31 & ~(kListLanes - 1));
     const uint16_t* __restrict__ cells = tile_cells + pt * VKB_TILE_CAP;
-    uint16_t* sorted = s_sorted[half];
-    uint16_t* raw = s_raw[half];
+    uint16_t* sorted = s_sorted[group];
+    uint16_t* raw = s_raw[group];
     int reach = 0;
     if (usable) {
         // the bin goes through shared memory (one coalesced read); ranks come from broadcast reads
-        for (int s = lane; s < count; s += 16) raw[s] = cells[s];
-        __syncwarp(half_mask);
+        for (int s = lane; s < count; s += kListLanes) raw[s] = cells[s];
+        __syncwarp(group_mask);
         const int ccols = pages[page].cols - 1;
-        for (int s = lane; s < count; s += 16) {
+        for (int s = lane; s < count; s += kListLanes) {
             const int cell = (int)raw[s];
             int rank = 0;
             for (int j = 0; j < count; ++j) rank += (int)raw[j] < cell;
@@ -836,21 +841,19 @@ __global__ void __launch_bounds__(128) grid_tile_lists_kernel(
             reach = max(reach, max(r, c));
         }
 #pragma unroll
-        for (int d = 8; d >= 1; d >>= 1) reach = max(reach, __shfl_xor_sync(half_mask, reach, d));
+        for (int d = kListLanes / 2; d >= 1; d >>= 1) reach = max(reach, __shfl_xor_sync(group_mask, reach, d));
     }
-    __syncwarp(half_mask);
+    __syncwarp(group_mask);
     RemapTile* __restrict__ hd = headers + (tile_base[page] + t);
     if (usable) {
         // the sorted list: behind the page's cell records (tile_list), two 16-bit entries per lane and step
         uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(
             const_cast<uint16_t*>(tile_list(slots, page, s_cap, c_max, t)));
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(sorted);
-        for (int w = lane; 2 * w < count; w += 16) out[w] = sw[w];  // (an odd count copies one stale entry)
-        if (lane < 8) {
-            const uint32_t lo = lane < count ? sorted[lane] : 0u;
-            const uint32_t hi = lane + 8 < count ? sorted[lane + 8] : 0u;
-            hd->ids[lane] = lo | (hi << 16);
-        }
+        for (int w = lane; 2 * w < count; w += kListLanes) out[w] = sw[w];  // (an odd count copies one stale entry)
+        const uint32_t lo = lane < count ? sorted[lane] : 0u;
+        const uint32_t hi = lane + 8 < count ? sorted[lane + 8] : 0u;
+        hd->ids[lane] = lo | (hi << 16);
     }
     if (lane == 0) {
         RemapTile h;
@@ -1447,7 +1450,7 @@ extern "C" int vkb_grid_build(const vkb_grid_page* pages, int32_t n_pages, int32
     // (the caller's stream joins the masks after the tile lists: only the remap reads them)
     if (side) VKB_CUDA(cudaEventRecord(side->join, side->stream));
     grid_tile_base_kernel<<<1, 1024, 0, st>>>(meta, n_pages, tile_base);
-    grid_tile_lists_kernel<<<dim3((t_max + 7) / 8, n_pages), 128, 0, st>>>(
+    grid_tile_lists_kernel<<<dim3((t_max + kListTiles - 1) / kListTiles, n_pages), 128, 0, st>>>(
         pages, meta, c_max, t_max, s_cap, tile_count, tile_cells, tile_base,
         reinterpret_cast<TileSlot*>(tile_slots), reinterpret_cast<RemapTile*>(tile_headers), large);
     rc = check_launch("grid_tile_lists_kernel");
