@@ -470,8 +470,8 @@ class Workload2:
     """config 2: one camera op per page."""
     config_id = 2
     kernel = 'grid_remap_tiles_kernel'
-    # project_camera (no page uses the MLS projector: not launched), finalize, layout, cells,
-    # masks, tile_base, tile_offsets, tile_records, remap (small-tile + large-tile launch)
+    # project_camera (no page uses the MLS projector: not launched), finalize, stage_params,
+    # layout, cells, masks, tile_base, tile_lists, remap (small-tile + large-tile launch)
     launches_per_step = 10
 
     def __init__(self, batch, first, total, seeds):
@@ -541,9 +541,9 @@ class Workload3:
     the colour op run as ONE pass of the fused chain kernel."""
     config_id = 3
     kernel = 'photo_chain_kernel'
-    # project_mls, finalize, cells, masks, tile_base, tile_offsets, tile_records, remap x2,
-    # fused gaussian_blur + color_shift
-    launches_per_step = 10
+    # project_mls, finalize, stage_params, cells, masks, tile_base, tile_lists, remap x2,
+    # stage_params, fused gaussian_blur + color_shift (ncu launch list: profiles/r02_launches_bench_config3.csv)
+    launches_per_step = 11
 
     def __init__(self, batch, first, total, seeds):
         import torch

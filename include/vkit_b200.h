@@ -172,23 +172,26 @@ int vkb_stage_params(void* dst, const void* src_host, int64_t nbytes, void* stre
 int vkb_grid_layout(vkb_grid_meta* meta, int32_t n_pages, vkb_planes* planes, int64_t cap_pixels,
                     int32_t t_max, int64_t* layout, int64_t* layout_mirror, void* stream);
 
-/* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage masks; per dst
- * tile the candidate cells and their records for the remap kernel.
- * c_max >= (rows-1)*(cols-1); t_max >= 32x32 tiles per page; s_cap = candidate records kept
- * per page (16 * t_max is ample; tiles that do not fit are handled by a slow exact path).
+/* Phase 2a: per cell inverse homography (dst -> src), bounding box, coverage mask and the
+ * float32 record the remap evaluates; per dst tile the sorted list of candidate cells.
+ * c_max >= (rows-1)*(cols-1); t_max >= 32x32 tiles per page; s_cap >= c_max + 2 * t_max records
+ * per page (the cells' records, then the tiles' candidate lists).
  *   hinv:       n_pages x c_max x 9 doubles
  *   hfwd:       n_pages x c_max x 9 doubles or NULL (forward maps, needed by vkb_grid_points)
  *   cell_box:   n_pages x c_max x 4 int32 (x0, y0, x1, y1); bit 30 of x1 set = coverage of
  *               this cell exceeds the mask budget and is rasterised on the fly by the remap
  *   cell_masks: n_pages x c_max x VKB_CELL_MASK_WORDS uint32
  *   tile_count: n_pages x t_max int32 (zeroed by this call)
- *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16
- *   tile_off:   n_pages x t_max int32, first record of each tile within its page
+ *   tile_cells: n_pages x t_max x VKB_TILE_CAP uint16 (unordered bins)
+ *   tile_off:   n_pages x t_max int32; unused since the records became per cell (kept so that
+ *               the signature of the call did not change)
  *   tile_base:  n_pages + 1 int32, prefix sum of tiles per page (the remap's flat work list)
- *   tile_slots: n_pages x s_cap x VKB_TILE_SLOT_BYTES bytes, opaque (bbox, cell id and the
- *               float32 tile-centred inverse map of every candidate, ascending cell order)
+ *   tile_slots: n_pages x s_cap x VKB_TILE_SLOT_BYTES bytes, opaque: per page one record per
+ *               cell (bbox, mask flag, float32 inverse map re-centred on the bbox origin), then
+ *               per tile VKB_TILE_CAP uint16 with its candidate cells in ascending order
  *   tile_headers: n_pages x t_max x VKB_TILE_HEADER_BYTES bytes (the flat work list of the
- *               remap: page, tile origin, record count, first record) followed by
+ *               remap: page, tile origin, candidate count, acceptance limit of the float32
+ *               coordinates, the first 16 sorted candidates) followed by
  *               (n_pages x t_max + 2) int32: the list of tiles that take the remap's second
  *               launch (count + entries: more than 15 candidates or the exact slow path) and, last,
  *               the work counter vkb_grid_remap resets and its small-tile kernel draws from; opaque */

@@ -801,7 +801,10 @@ __global__ void __launch_bounds__(1024) grid_tile_base_kernel(const vkb_grid_met
 // the fast path and the first 16 sorted candidates packed for the small-tile kernel.  The kernel
 // is a chain of dependent loads per tile (count -> bin -> stores); what matters is how many tiles
 // are in flight, hence the narrow groups.
-constexpr int kListLanes = 8;
+#ifndef VKB_LIST_LANES
+#define VKB_LIST_LANES 8
+#endif
+constexpr int kListLanes = VKB_LIST_LANES;
 constexpr int kListTiles = 128 / kListLanes;  // tiles per block
 
 __global__ void __launch_bounds__(128) grid_tile_lists_kernel(
@@ -851,9 +854,11 @@ __global__ void __launch_bounds__(128) grid_tile_lists_kernel(
             const_cast<uint16_t*>(tile_list(slots, page, s_cap, c_max, t)));
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(sorted);
         for (int w = lane; 2 * w < count; w += kListLanes) out[w] = sw[w];  // (an odd count copies one stale entry)
-        const uint32_t lo = lane < count ? sorted[lane] : 0u;
-        const uint32_t hi = lane + 8 < count ? sorted[lane + 8] : 0u;
-        hd->ids[lane] = lo | (hi << 16);
+        for (int w = lane; w < 8; w += kListLanes) {
+            const uint32_t lo = w < count ? sorted[w] : 0u;
+            const uint32_t hi = w + 8 < count ? sorted[w + 8] : 0u;
+            hd->ids[w] = lo | (hi << 16);
+        }
     }
     if (lane == 0) {
         RemapTile h;
