@@ -221,6 +221,10 @@ class ClockSampler:
             nvml.nvmlInit()
             handle = nvml.nvmlDeviceGetHandleByIndex(self._visible_index())
             self.max_mhz = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+            # the first queries of a process can take tens of milliseconds inside the driver (and
+            # kernel launches wait behind them): make them here, before the timed region starts
+            nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)
+            nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
             self.thread = threading.Thread(target=self._poll_nvml, args=(nvml, handle), daemon=True)
             self.thread.start()
             return
