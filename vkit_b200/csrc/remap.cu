@@ -21,10 +21,10 @@ namespace vkb {
 // Fused remap.  Block = 32 x (32 / R) threads on one 32 x 32 dst tile; warp w owns rows
 // R*w .. R*w + R-1, lane = column.
 //
-//   prologue  the tile's candidate cells (<= VKB_TILE_CAP, ascending cell order) are staged in
-//             shared memory: bbox + packed (slot, cell column, cell row), and the float32 form
-//             of the cell's inverse homography re-centred on the tile origin (CellLocal, built
-//             here from the float64 matrix);
+//   prologue  the records of the tile's candidate cells (<= VKB_TILE_CAP, ascending cell order,
+//             read from the tile's sorted list) are staged in shared memory: bbox and the
+//             float32 form of the cell's inverse homography re-centred on the cell's bbox
+//             origin (CellLocal, one record per cell, written by grid_cells_kernel);
 //   owner     lane-parallel: lane i fetches candidate i's coverage words for the warp's R rows
 //             (shifted to the tile's columns), a ballot keeps the candidates that touch the
 //             band, and each survivor is broadcast with shuffles in ascending order; a pixel
@@ -431,8 +431,9 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 
 // ============================================================================================
 // Small-tile kernel (second generation).  One WARP per 32 x 32 dst tile, persistent blocks, the
-// candidate records of the next tile staged with cp.async while the current one is processed
-// (as in grid_remap_kernel).  Per tile:
+// records of the next tile's candidate cells staged with cp.async while the current one is
+// processed (each lane reads its two candidate ids with the tile's header, four lanes copy one
+// 64-byte cell record).  Per tile:
 //
 //   owner     lane = dst ROW: for every candidate (ascending cell order) the lane loads the
 //             candidate's coverage word of its row and overwrites four bit planes of
@@ -442,11 +443,11 @@ __global__ void __launch_bounds__(32 * (VKB_TILE / R), VKB_REMAP_BLOCKS) grid_re
 //             of its 32 rows; a band's four owners come out of one 16-bit word with a multiply
 //             (no per-pixel shuffles).  Owner 0 = uncovered = record 0 of the warp's buffer,
 //             a constant record whose map is (0, 0): uncovered pixels need no special case.
-//   coords    float32 fast path per pixel (vkb_math.cuh); a pixel whose result sits next to a
-//             rounding boundary is NOT resolved on the spot: it is flagged in a per-thread row
-//             mask, skipped by the stores, and resolved after the band loop by the float64 path
-//             (0.1 - 0.6 % of the pixels; on the spot the whole warp paid for it in every other
-//             row).
+//   coords    float32 fast path per pixel with an integer acceptance test (vkb_math.cuh); a
+//             pixel whose result sits next to a rounding boundary is NOT resolved on the spot:
+//             it is flagged in a per-thread row mask and resolved after the band loop by the
+//             float64 path (0.1 - 0.7 % of the pixels; on the spot the whole warp paid for it in
+//             every other row).
 //   gather    cv::remap's fixed-point bilinear with both blend directions folded into IDP.2A
 //             (vkb_gather.cuh), loads of the band's four pixels in flight together.
 //   Tiles without candidates and bands without owners are filled with the value of map (0, 0).
