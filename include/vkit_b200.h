@@ -422,6 +422,28 @@ int vkb_zoom_in_blur_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, 
                         const vkb_zoom_level* levels_dev, int32_t n_levels, double alpha,
                         void* stream);
 
+/* The alpha field of `fog` (photometric/effect.py:89-208: generate_diamond_square_mask and the
+ * normalisation of fog_image) computed on the device FROM THE CALLER'S NumPy GENERATOR STREAM:
+ * (state, inc) is the PCG64 state after the four scalar corner draws; the array draws of the
+ * levels are regenerated on the device (draw i = one 64-bit output, reached by jump-ahead), the
+ * host advances its generator by the `count` of vkb_fog_draws(size, &count) outputs and then draws the crop offsets.
+ * weight[l] = roughness ** l as the host's Python float computes it.  Workspaces: field
+ * size x size float32, centres ((size - 1) / 2)^2 doubles, draws `count` doubles,
+ * minmax 2 x uint32.  alpha: height x width float32 = the blend weights of the fog colour. */
+#define VKB_FOG_MAX_LEVELS 16
+typedef struct vkb_fog_params {
+    uint64_t state_hi, state_lo, inc_hi, inc_lo;
+    double weight[VKB_FOG_MAX_LEVELS];
+    float corners[4]; /* field[0][0], field[0][-1], field[-1][-1], field[-1][0] */
+    int32_t size;     /* 2^k + 1 */
+    int32_t up, left, height, width;
+    float ratio_span, ratio_min; /* float32(ratio_max - ratio_min), float32(ratio_min) */
+    int32_t _pad;
+} vkb_fog_params;
+int vkb_fog_draws(int32_t size, int64_t* count);
+int vkb_fog_mask(const vkb_fog_params* p, float* field, double* centres, double* draws,
+                 uint32_t* minmax, float* alpha, void* stream);
+
 /* dst[y, x] = src[pos_y[y, x], pos_x[y, x]] (uint8 HWC): the pixel permutation of glass_blur
  * (photometric/blur.py:216-264); the index maps are the host-drawn random field. */
 int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,

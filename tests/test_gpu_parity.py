@@ -1274,6 +1274,38 @@ def test_fog_grayscale_vs_golden(vk, case):
     assert sha(r.image.mat) == case['sha']['image']
 
 
+@pytest.mark.parametrize('shape,roughness,ratios,seed', [
+    ((64, 64), 0.5, (0.0, 1.0), 1), ((65, 129), 0.3, (0.1, 0.8), 2), ((200, 137), 0.9, (0.0, 0.6), 3),
+    ((3, 2), 0.7, (0.2, 0.9), 4), ((1024, 1024), 0.45, (0.0, 1.0), 5), ((513, 700), 0.0, (0.0, 1.0), 6),
+    ((300, 300), 1.0, (0.3, 0.7), 7),
+])
+def test_fog_field_on_device_equals_host_field(vk, shape, roughness, ratios, seed):
+    """The fog alpha computed on the device from the generator's PCG64 stream (jump-ahead draws,
+    diamond-square levels, normalisation) == the host restatement of the reference's
+    generate_diamond_square_mask + fog_image normalisation, bit for bit, and the generator ends in
+    the same state (incl. a pending half of a 32-bit draw); other bit generators take the host path."""
+    from vkit_b200 import device as dv
+    from vkit_b200.mechanism.distortion.photometric import effect
+    ratio_min, ratio_max = ratios
+    for pending_uint32 in (False, True):
+        rng_dev, rng_host = np.random.default_rng(seed), np.random.default_rng(seed)
+        if pending_uint32:  # a 32-bit draw leaves the other half of its 64-bit output cached
+            assert rng_dev.integers(0, 10) == rng_host.integers(0, 10)
+        alpha = effect.diamond_square_alpha_device(shape, roughness, ratio_min, ratio_max, rng_dev)
+        mask = effect.generate_diamond_square_mask(shape, roughness, rng_host)
+        mask -= mask.min()
+        mask /= mask.max()
+        mask *= (ratio_max - ratio_min)
+        mask += ratio_min
+        got = dv.to_host(alpha)
+        assert got.dtype == np.float32 and got.shape == tuple(shape)
+        assert np.array_equal(got, mask.astype(np.float32)), float(np.abs(got - mask).max())
+        assert rng_dev.bit_generator.state == rng_host.bit_generator.state
+        assert rng_dev.integers(0, 1 << 30, 5).tolist() == rng_host.integers(0, 1 << 30, 5).tolist()
+    other = np.random.Generator(np.random.MT19937(seed))
+    assert effect.diamond_square_alpha_device(shape, roughness, ratio_min, ratio_max, other) is None
+
+
 @pytest.mark.parametrize('case', r2_cases('jpeg_quality'), ids=lambda c: f"{c['id']}-q{c['config']['quality']}")
 def test_jpeg_quality_vs_golden(vk, case):
     """The JPEG round trip on the device (libjpeg's integer colour conversion, 4:2:0 sampling,

@@ -81,6 +81,17 @@ class BlendItem(ctypes.Structure):
     ]
 
 
+class FogParams(ctypes.Structure):
+    """vkb_fog_params (include/vkit_b200.h)."""
+    _fields_ = [
+        ('state_hi', ctypes.c_uint64), ('state_lo', ctypes.c_uint64),
+        ('inc_hi', ctypes.c_uint64), ('inc_lo', ctypes.c_uint64),
+        ('weight', ctypes.c_double * 16), ('corners', c_float * 4), ('size', c_int32),
+        ('up', c_int32), ('left', c_int32), ('height', c_int32), ('width', c_int32),
+        ('ratio_span', c_float), ('ratio_min', c_float), ('_pad', c_int32),
+    ]
+
+
 class ColorOp(ctypes.Structure):
     _fields_ = [
         ('kind', c_int32), ('i0', c_int32), ('i1', c_int32), ('i2', c_int32), ('i3', c_int32),
@@ -211,6 +222,8 @@ def _declare(lib):
     lib.vkb_threshold_u8.argtypes = [vp, vp, i64, i32, i32, i32, vp]
     lib.vkb_zoom_in_blur_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, c_double, vp]
     lib.vkb_gather_pixels_u8.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.vkb_fog_draws.argtypes = [i32, POINTER(ctypes.c_int64)]
+    lib.vkb_fog_mask.argtypes = [POINTER(FogParams), vp, vp, vp, vp, vp, vp]
     lib.vkb_resize_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32_scaled.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, c_float, vp]
@@ -234,7 +247,7 @@ EXPORTS = (
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_jpeg_round_trip_u8', 'vkb_streak_masks', 'vkb_photo_chain_batched',
     'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_resize_mask_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
-    'vkb_background_compose', 'vkb_glyph_prepare', 'vkb_resize_f32_scaled',
+    'vkb_background_compose', 'vkb_glyph_prepare', 'vkb_resize_f32_scaled', 'vkb_fog_draws', 'vkb_fog_mask',
 )
 
 

@@ -138,6 +138,61 @@ def generate_diamond_square_mask(shape: Tuple[int, int], roughness: float, rng: 
     return field[up:up + height, left:left + width]
 
 
+def diamond_square_alpha_device(shape: Tuple[int, int], roughness: float, ratio_min: float,
+                                ratio_max: float, rng: RandomGenerator):
+    """The fog alpha (generate_diamond_square_mask + fog_image's normalisation, effect.py:89-190) as
+    a float32 CUDA tensor, computed on the device from the caller's generator stream.  NumPy's
+    PCG64 can be advanced by any number of steps and every uniform double of the field is one
+    64-bit output, so the device regenerates the array draws itself (`vkb_fog_mask`); the host makes
+    the four scalar corner draws, advances the generator past the array draws and makes the two
+    crop draws -- the generator ends in the state the reference leaves it in.  Returns None when
+    the generator is not a PCG64 (the caller then draws the field on the host)."""
+    bit_generator = rng.bit_generator
+    if type(bit_generator).__name__ != 'PCG64':
+        return None
+    assert 0.0 <= roughness <= 1.0
+    height, width = shape
+    size = int(2**np.ceil(np.log2(max(height, width))) + 1)
+    if size < 3:
+        return None
+    params = nv.FogParams()
+    for k in range(4):  # (0, 0), (0, -1), (-1, -1), (-1, 0), stored as float32 like the field
+        params.corners[k] = float(np.float32(rng.uniform(0.0, 1.0)))
+    state = bit_generator.state
+    s128, inc128 = state['state']['state'], state['state']['inc']
+    mask64 = (1 << 64) - 1
+    params.state_hi, params.state_lo = s128 >> 64, s128 & mask64
+    params.inc_hi, params.inc_lo = inc128 >> 64, inc128 & mask64
+    step, level = size - 1, 0
+    while step >= 2:
+        params.weight[level] = roughness**level
+        level += 1
+        step //= 2
+    # past the array draws; the cached half of a 32-bit draw survives them in the reference
+    count = ctypes.c_int64(0)
+    nv.check(nv.lib().vkb_fog_draws(size, ctypes.byref(count)), 'vkb_fog_draws')
+    n_draws = int(count.value)
+    bit_generator.advance(n_draws)
+    after = bit_generator.state
+    after['has_uint32'], after['uinteger'] = state['has_uint32'], state['uinteger']
+    bit_generator.state = after
+    params.size = size
+    params.up = int(rng.integers(0, size - height + 1))
+    params.left = int(rng.integers(0, size - width + 1))
+    params.height, params.width = height, width
+    params.ratio_span = float(np.float32(ratio_max - ratio_min))
+    params.ratio_min = float(np.float32(ratio_min))
+    field = dv.empty((size, size), np.float32)
+    centres = dv.empty((max(1, (size - 1) // 2) ** 2,), np.float64)
+    draws = dv.empty((max(1, n_draws),), np.float64)
+    minmax = dv.empty((2,), np.uint32)
+    alpha = dv.empty((height, width), np.float32)
+    nv.check(nv.lib().vkb_fog_mask(ctypes.byref(params), dv.ptr(field), dv.ptr(centres),
+                                   dv.ptr(draws), dv.ptr(minmax), dv.ptr(alpha), dv.stream_ptr()),
+             'vkb_fog_mask')
+    return alpha
+
+
 @attrs.define
 class FogConfig(DistortionConfig):
     roughness: float
@@ -165,14 +220,18 @@ def fog_image(config: FogConfig, state, image: Image, rng: Optional[RandomGenera
     mode = image.mode
     image = to_rgb_image(image, mode)
     assert rng is not None
-    mask = generate_diamond_square_mask(image.shape, config.roughness, rng)
-    mask -= mask.min()
-    mask /= mask.max()
     assert config.ratio_min < config.ratio_max
     if config.ratio_min < 0.0 or config.ratio_max > 1.0:
         raise NotImplementedError('fog ratios outside [0, 1] are not provided')
-    mask *= (config.ratio_max - config.ratio_min)
-    mask += config.ratio_min
+    alpha = diamond_square_alpha_device(image.shape, config.roughness, config.ratio_min,
+                                        config.ratio_max, rng)
+    if alpha is None:  # a bit generator whose stream cannot be split: the field is drawn on the host
+        mask = generate_diamond_square_mask(image.shape, config.roughness, rng)
+        mask -= mask.min()
+        mask /= mask.max()
+        mask *= (config.ratio_max - config.ratio_min)
+        mask += config.ratio_min
+        alpha = dv.to_device(np.ascontiguousarray(mask, dtype=np.float32))
 
     channels = image.num_channels or 1
     if image.mode == ImageMode.GRAYSCALE:
@@ -184,7 +243,6 @@ def fog_image(config: FogConfig, state, image: Image, rng: Optional[RandomGenera
 
     # (1 - mask) * mat + mask * fog in float32, clipped and truncated: the device blend
     dst = image.dev.clone()
-    alpha = dv.to_device(np.ascontiguousarray(mask, dtype=np.float32))
     item = nv.BlendItem()
     item.dst = dst.data_ptr()
     item.dst_f32 = 0
