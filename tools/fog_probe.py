@@ -1,3 +1,8 @@
+"""fog_image per call (host time and host + device time) with the field computed on the device
+(0.25 ms per 1024 x 1024 page on the B200; the host-drawn field took 17 ms) + a cProfile of the call.
+
+    python tools/fog_probe.py
+"""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from vkit_b200 import element
