@@ -444,6 +444,24 @@ int vkb_fog_draws(int32_t size, int64_t* count);
 int vkb_fog_mask(const vkb_fog_params* p, float* field, double* centres, double* draws,
                  uint32_t* minmax, float* alpha, void* stream);
 
+/* The pixel permutation of glass_blur (photometric/blur.py:232-262) built on the device from the
+ * caller's NumPy PCG64 stream.  vkb_glass_init: pos_y / pos_x = identity maps (h x w int32),
+ * owner = -1 (h x w int32 scratch), flag = 0.  vkb_glass_round: one round -- the host has drawn the
+ * round's two offsets (row0, col0) and passes the generator's state after them ((state, inc) and
+ * the pending 32-bit half, if any); the kernel regenerates the round's 2 * n bounded integers
+ * (n = centres of the round; Lemire's method on the 32-bit halves, as NumPy does), swaps every
+ * centre with its target (duplicate targets: the last centre in C order wins, like NumPy's fancy
+ * assignment) and sets *flag when NumPy would have REJECTED a draw (2^-32 per draw): the maps are
+ * then invalid and the caller repeats the call on the host.  target: n int32, at_centre /
+ * at_target: 2 * n int32 scratch (n <= ceil(h / period) * ceil(w / period)). */
+int vkb_glass_init(int32_t* pos_y, int32_t* pos_x, int32_t* owner, int32_t h, int32_t w,
+                   int32_t* flag, void* stream);
+int vkb_glass_round(int32_t* pos_y, int32_t* pos_x, int32_t* owner, int32_t h, int32_t w,
+                    int32_t row0, int32_t col0, int32_t delta, int32_t round, uint64_t state_hi,
+                    uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, int32_t has_cached,
+                    uint32_t cached, int32_t* target, int32_t* at_centre, int32_t* at_target,
+                    int32_t* flag, void* stream);
+
 /* dst[y, x] = src[pos_y[y, x], pos_x[y, x]] (uint8 HWC): the pixel permutation of glass_blur
  * (photometric/blur.py:216-264); the index maps are the host-drawn random field. */
 int vkb_gather_pixels_u8(const uint8_t* src, uint8_t* dst, int32_t h, int32_t w, int32_t channels,

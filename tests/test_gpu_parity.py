@@ -1306,6 +1306,35 @@ def test_fog_field_on_device_equals_host_field(vk, shape, roughness, ratios, see
     assert effect.diamond_square_alpha_device(shape, roughness, ratio_min, ratio_max, other) is None
 
 
+@pytest.mark.parametrize('shape,delta,loop,seed', [
+    ((64, 64), 1, 5, 1), ((65, 130), 1, 5, 2), ((200, 137), 2, 3, 3), ((5, 4), 1, 2, 4),
+    ((1024, 1024), 1, 5, 5), ((301, 517), 3, 4, 6), ((2, 2), 1, 5, 7),
+])
+def test_glass_maps_on_device_equal_host_maps(vk, shape, delta, loop, seed):
+    """glass_blur's pixel permutation built on the device from the generator's PCG64 stream
+    (bounded integers by Lemire's method on the 32-bit halves, swaps with last-writer-wins) == the
+    host restatement of the reference's rounds, and the generator ends in the same state."""
+    from vkit_b200 import device as dv
+    from vkit_b200.mechanism.distortion.photometric import blur
+
+    def meaningful(state):
+        return (state['state'], state['has_uint32'], state['uinteger'] if state['has_uint32'] else None)
+
+    for pending_uint32 in (False, True):
+        rng_dev, rng_host = np.random.default_rng(seed), np.random.default_rng(seed)
+        if pending_uint32:
+            assert rng_dev.integers(0, 10) == rng_host.integers(0, 10)
+        maps = blur.glass_swap_maps_device(shape, delta, loop, rng_dev)
+        assert maps is not None
+        pos_y, pos_x = blur.glass_swap_maps(shape, delta, loop, rng_host)
+        assert np.array_equal(dv.to_host(maps[0]), pos_y)
+        assert np.array_equal(dv.to_host(maps[1]), pos_x)
+        assert meaningful(rng_dev.bit_generator.state) == meaningful(rng_host.bit_generator.state)
+        assert rng_dev.integers(0, 1 << 30, 5).tolist() == rng_host.integers(0, 1 << 30, 5).tolist()
+    other = np.random.Generator(np.random.MT19937(seed))
+    assert blur.glass_swap_maps_device(shape, delta, loop, other) is None
+
+
 @pytest.mark.parametrize('case', r2_cases('jpeg_quality'), ids=lambda c: f"{c['id']}-q{c['config']['quality']}")
 def test_jpeg_quality_vs_golden(vk, case):
     """The JPEG round trip on the device (libjpeg's integer colour conversion, 4:2:0 sampling,

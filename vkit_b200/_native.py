@@ -224,6 +224,10 @@ def _declare(lib):
     lib.vkb_gather_pixels_u8.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.vkb_fog_draws.argtypes = [i32, POINTER(ctypes.c_int64)]
     lib.vkb_fog_mask.argtypes = [POINTER(FogParams), vp, vp, vp, vp, vp, vp]
+    u64 = ctypes.c_uint64
+    lib.vkb_glass_init.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.vkb_glass_round.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, u64, u64, u64, u64, i32,
+                                    ctypes.c_uint32, vp, vp, vp, vp, vp]
     lib.vkb_resize_u8.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
     lib.vkb_resize_f32_scaled.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, c_float, vp]
@@ -247,7 +251,7 @@ EXPORTS = (
     'vkb_channel_stats', 'vkb_histogram_u8', 'vkb_apply_lut', 'vkb_gaussian_blur_u8', 'vkb_noise_philox', 'vkb_noise_field',
     'vkb_streak_line', 'vkb_fill_rects', 'vkb_draw_ellipses', 'vkb_jpeg_round_trip_u8', 'vkb_streak_masks', 'vkb_photo_chain_batched',
     'vkb_channel_stats_batched', 'vkb_fill_polygons', 'vkb_filter2d_u8', 'vkb_resize_u8', 'vkb_resize_f32', 'vkb_resize_mask_u8', 'vkb_gather_pixels_u8', 'vkb_noise_philox_batched', 'vkb_zoom_in_blur_u8', 'vkb_threshold_u8',
-    'vkb_background_compose', 'vkb_glyph_prepare', 'vkb_resize_f32_scaled', 'vkb_fog_draws', 'vkb_fog_mask',
+    'vkb_background_compose', 'vkb_glyph_prepare', 'vkb_resize_f32_scaled', 'vkb_fog_draws', 'vkb_fog_mask', 'vkb_glass_init', 'vkb_glass_round',
 )
 
 

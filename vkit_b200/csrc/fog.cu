@@ -242,3 +242,184 @@ extern "C" int vkb_fog_mask(const vkb_fog_params* p, float* field, double* centr
         field, size, p->up, p->left, p->height, p->width, minmax, p->ratio_span, p->ratio_min, alpha);
     return check_launch("vkb_fog_mask");
 }
+
+// ============================================================================================
+// glass_blur's pixel permutation on the device (photometric/blur.py:232-262).  Per round every
+// (2 * delta + 1)-th pixel ("centre") trades places with a random neighbour of the pixel that
+// currently sits there; the shifts are NumPy bounded integers: Lemire's method on the 32-bit
+// halves of the generator's 64-bit outputs (low half first; a half left over by an earlier draw
+// comes first).  Half number p of the stream is again a pure function of (state, p) -- unless a
+// draw is REJECTED (probability 2^-32 per draw for three values), which shifts everything behind
+// it: the kernel raises a flag then and the caller repeats the call on the host.
+// ============================================================================================
+namespace vkb {
+
+// 32-bit half number p (0-based) of the stream that starts with `cached` when has_cached is set
+struct HalfStream {
+    u128 s;       // state of the output the next half comes from (already stepped when `high`)
+    bool high;    // the next half is the high half of the current output
+};
+
+__device__ __forceinline__ uint32_t half_at_start(u128 state, u128 inc, int has_cached, uint32_t cached,
+                                                  int64_t p, HalfStream& hs, bool& from_cache) {
+    // positions behind the cached half map onto outputs 1, 2, ...: q = p - has_cached
+    from_cache = has_cached && p == 0;
+    if (from_cache) {
+        hs.s = state;  // next: low half of output 1
+        hs.high = false;
+        return cached;
+    }
+    const int64_t q = p - has_cached;
+    u128 s = pcg_advance(state, inc, (uint64_t)(q >> 1) + 1);
+    hs.s = s;
+    const uint64_t hi = (uint64_t)(s >> 64), lo = (uint64_t)s;
+    const uint64_t x = hi ^ lo;
+    const unsigned r = (unsigned)(hi >> 58);
+    const uint64_t o = (x >> r) | (x << ((64u - r) & 63u));
+    hs.high = !(q & 1);  // after a low half comes the high half of the same output
+    return (q & 1) ? (uint32_t)(o >> 32) : (uint32_t)o;
+}
+
+__device__ __forceinline__ uint32_t half_next(HalfStream& hs, u128 inc, bool was_cache) {
+    if (!was_cache && hs.high) {  // high half of the current output
+        const uint64_t hi = (uint64_t)(hs.s >> 64), lo = (uint64_t)hs.s;
+        const uint64_t x = hi ^ lo;
+        const unsigned r = (unsigned)(hi >> 58);
+        const uint64_t o = (x >> r) | (x << ((64u - r) & 63u));
+        hs.high = false;
+        return (uint32_t)(o >> 32);
+    }
+    hs.s = hs.s * pcg_mult() + inc;
+    const uint64_t hi = (uint64_t)(hs.s >> 64), lo = (uint64_t)hs.s;
+    const uint64_t x = hi ^ lo;
+    const unsigned r = (unsigned)(hi >> 58);
+    const uint64_t o = (x >> r) | (x << ((64u - r) & 63u));
+    hs.high = true;
+    return (uint32_t)o;
+}
+
+constexpr int kGlassRun = 8;  // consecutive centres per thread (one jump-ahead per axis)
+
+// bounded integer low + Lemire(u, span); flags a draw NumPy would have rejected
+__device__ __forceinline__ int lemire_bounded(uint32_t u, uint32_t span, uint32_t threshold, int low,
+                                              int32_t* __restrict__ flag) {
+    const uint64_t m = (uint64_t)u * span;
+    const uint32_t leftover = (uint32_t)m;
+    if (leftover < span && leftover < threshold) *flag = 1;
+    return low + (int)(m >> 32);
+}
+
+// phase 1 of a round: shifts, targets, and the values both sides hold BEFORE any write
+__global__ void __launch_bounds__(128) glass_targets_kernel(
+    const int32_t* __restrict__ pos_y, const int32_t* __restrict__ pos_x, int h, int w, int row0,
+    int col0, int period, int delta, int ny, int nx, uint64_t state_hi, uint64_t state_lo,
+    uint64_t inc_hi, uint64_t inc_lo, int has_cached, uint32_t cached, int round,
+    int32_t* __restrict__ target, int32_t* __restrict__ at_centre, int32_t* __restrict__ at_target,
+    int32_t* __restrict__ owner, int32_t* __restrict__ flag) {
+    const int64_t n = (int64_t)ny * nx;
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kGlassRun;
+    if (first >= n) return;
+    const u128 state = make_u128(state_hi, state_lo), inc = make_u128(inc_hi, inc_lo);
+    const uint32_t span = 2u * (uint32_t)delta + 1u;
+    const uint32_t threshold = (uint32_t)((0x100000000ull - span) % span);
+    HalfStream sy, sx;
+    bool cy_cache, cx_cache;
+    uint32_t uy = half_at_start(state, inc, has_cached, cached, first, sy, cy_cache);
+    uint32_t ux = half_at_start(state, inc, has_cached, cached, n + first, sx, cx_cache);
+    const int64_t last = first + kGlassRun < n ? first + kGlassRun : n;
+    for (int64_t k = first; k < last; ++k) {
+        const int shift_y = lemire_bounded(uy, span, threshold, -delta, flag);
+        const int shift_x = lemire_bounded(ux, span, threshold, -delta, flag);
+        const int iy = (int)(k / nx), ix = (int)(k - (int64_t)iy * nx);
+        const int c = (row0 + iy * period) * w + (col0 + ix * period);
+        const int vy = pos_y[c], vx = pos_x[c];
+        const int ty = min(max(vy + shift_y, 0), h - 1), tx = min(max(vx + shift_x, 0), w - 1);
+        const int t = ty * w + tx;
+        target[k] = t;
+        at_centre[2 * k] = vy;
+        at_centre[2 * k + 1] = vx;
+        at_target[2 * k] = pos_y[t];
+        at_target[2 * k + 1] = pos_x[t];
+        // duplicates among the targets: the last centre in C order writes last
+        atomicMax(owner + t, (round << 24) | (int)k);
+        if (k + 1 < last) {
+            uy = half_next(sy, inc, cy_cache);
+            ux = half_next(sx, inc, cx_cache);
+            cy_cache = cx_cache = false;
+        }
+    }
+}
+
+// phase 2: pos[centres] = at_target
+__global__ void __launch_bounds__(256) glass_centres_kernel(int32_t* __restrict__ pos_y, int32_t* __restrict__ pos_x,
+                                                            int w, int row0, int col0, int period, int ny, int nx,
+                                                            const int32_t* __restrict__ at_target) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ny * nx) return;
+    const int iy = k / nx, ix = k - iy * nx;
+    const int c = (row0 + iy * period) * w + (col0 + ix * period);
+    pos_y[c] = at_target[2 * k];
+    pos_x[c] = at_target[2 * k + 1];
+}
+
+// phase 3: pos[targets] = at_centre, the winner of every target only
+__global__ void __launch_bounds__(256) glass_scatter_kernel(int32_t* __restrict__ pos_y, int32_t* __restrict__ pos_x,
+                                                            int n, int round, const int32_t* __restrict__ target,
+                                                            const int32_t* __restrict__ at_centre,
+                                                            const int32_t* __restrict__ owner) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int t = target[k];
+    if (owner[t] != ((round << 24) | k)) return;
+    pos_y[t] = at_centre[2 * k];
+    pos_x[t] = at_centre[2 * k + 1];
+}
+
+__global__ void __launch_bounds__(256) glass_init_kernel(int32_t* __restrict__ pos_y, int32_t* __restrict__ pos_x,
+                                                         int32_t* __restrict__ owner, int h, int w,
+                                                         int32_t* __restrict__ flag) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) *flag = 0;
+    if (p >= (int64_t)h * w) return;
+    const int y = (int)(p / w);
+    pos_y[p] = y;
+    pos_x[p] = (int)(p - (int64_t)y * w);
+    owner[p] = -1;
+}
+
+}  // namespace vkb
+
+extern "C" int vkb_glass_init(int32_t* pos_y, int32_t* pos_x, int32_t* owner, int32_t h, int32_t w,
+                              int32_t* flag, void* stream) {
+    VKB_REQUIRE(pos_y && pos_x && owner && flag && h > 0 && w > 0, "bad arguments");
+    const int64_t n = (int64_t)h * w;
+    glass_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_y, pos_x, owner, h, w, flag);
+    return check_launch("glass_init_kernel");
+}
+
+extern "C" int vkb_glass_round(int32_t* pos_y, int32_t* pos_x, int32_t* owner, int32_t h, int32_t w,
+                               int32_t row0, int32_t col0, int32_t delta, int32_t round,
+                               uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                               int32_t has_cached, uint32_t cached, int32_t* target, int32_t* at_centre,
+                               int32_t* at_target, int32_t* flag, void* stream) {
+    VKB_NVTX("vkb_glass_round");
+    VKB_REQUIRE(pos_y && pos_x && owner && target && at_centre && at_target && flag, "bad arguments");
+    VKB_REQUIRE(delta >= 1 && round >= 0 && round < 127, "delta >= 1, at most 127 rounds");
+    const int period = 2 * delta + 1;
+    VKB_REQUIRE(row0 >= 0 && row0 < period && col0 >= 0 && col0 < period, "bad offsets");
+    const int ny = h - delta > row0 ? (h - delta - row0 + period - 1) / period : 0;
+    const int nx = w - delta > col0 ? (w - delta - col0 + period - 1) / period : 0;
+    const int64_t n = (int64_t)ny * nx;
+    if (n == 0) return VKB_OK;
+    VKB_REQUIRE(n < (1 << 24), "too many centres per round");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t threads = (n + kGlassRun - 1) / kGlassRun;
+    glass_targets_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+        pos_y, pos_x, h, w, row0, col0, period, delta, ny, nx, state_hi, state_lo, inc_hi, inc_lo,
+        has_cached, cached, round, target, at_centre, at_target, owner, flag);
+    glass_centres_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos_y, pos_x, w, row0, col0, period,
+                                                                     ny, nx, at_target);
+    glass_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos_y, pos_x, (int)n, round, target,
+                                                                     at_centre, owner);
+    return check_launch("vkb_glass_round");
+}

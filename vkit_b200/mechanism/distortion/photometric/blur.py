@@ -308,17 +308,80 @@ def glass_swap_maps(shape, delta: int, loop: int, rng: RandomGenerator):
     return pos_y, pos_x
 
 
+def glass_swap_maps_device(shape, delta: int, loop: int, rng: RandomGenerator):
+    """glass_swap_maps on the device, from the caller's generator stream: the host draws the two
+    offsets of every round, the device regenerates the round's bounded integers (`vkb_glass_round`)
+    and the host moves its PCG64 past them (whole 64-bit outputs by `advance`, the last one drawn
+    for the half it may leave pending).  Returns (pos_y, pos_x) as CUDA int32 tensors, or None when
+    the generator is not a PCG64, the page is too large for the round keys, or the device saw a
+    draw NumPy would have rejected (2^-32 per draw) -- the generator is then back in its initial
+    state and the caller draws the maps on the host."""
+    bit_generator = rng.bit_generator
+    height, width = shape
+    period = 2 * delta + 1
+    if (type(bit_generator).__name__ != 'PCG64' or delta < 1 or loop > 100
+            or -(-height // period) * -(-width // period) >= (1 << 24)):
+        return None
+    initial = bit_generator.state
+    lib = nv.lib()
+    n_max = -(-height // period) * -(-width // period)
+    pos_y = dv.empty((height, width), np.int32)
+    pos_x = dv.empty((height, width), np.int32)
+    owner = dv.empty((height, width), np.int32)
+    target = dv.empty((max(1, n_max),), np.int32)
+    at_centre = dv.empty((max(1, 2 * n_max),), np.int32)
+    at_target = dv.empty((max(1, 2 * n_max),), np.int32)
+    flag = dv.empty((1,), np.int32)
+    nv.check(lib.vkb_glass_init(dv.ptr(pos_y), dv.ptr(pos_x), dv.ptr(owner), height, width,
+                                dv.ptr(flag), dv.stream_ptr()), 'vkb_glass_init')
+    mask64 = (1 << 64) - 1
+    for k in range(loop):
+        row0 = int(rng.integers(0, period))
+        col0 = int(rng.integers(0, period))
+        n = len(range(row0, height - delta, period)) * len(range(col0, width - delta, period))
+        state = bit_generator.state
+        s128, inc128 = state['state']['state'], state['state']['inc']
+        pending = int(state['has_uint32'])
+        nv.check(lib.vkb_glass_round(
+            dv.ptr(pos_y), dv.ptr(pos_x), dv.ptr(owner), height, width, row0, col0, delta, k,
+            s128 >> 64, s128 & mask64, inc128 >> 64, inc128 & mask64, pending,
+            int(state['uinteger']) if pending else 0, dv.ptr(target), dv.ptr(at_centre),
+            dv.ptr(at_target), dv.ptr(flag), dv.stream_ptr()), 'vkb_glass_round')
+        # the generator moves past the round's 2 * n halves
+        fresh = 2 * n - pending  # halves taken from new 64-bit outputs
+        if fresh > 0:
+            outputs = (fresh + 1) // 2
+            bit_generator.advance(outputs - 1)  # (resets the pending half)
+            last = int(bit_generator.random_raw())
+            after = bit_generator.state
+            after['has_uint32'] = fresh & 1  # an odd number of halves leaves the high half pending
+            after['uinteger'] = last >> 32   # (NumPy keeps the value after it has been used, too)
+            bit_generator.state = after
+        elif 2 * n > 0:  # the single half of the round was the pending one
+            after = bit_generator.state
+            after['has_uint32'] = 0
+            bit_generator.state = after
+    if int(dv.to_host(flag)[0]):
+        bit_generator.state = initial
+        return None
+    return pos_y, pos_x
+
+
 def glass_blur_image(config: GlassBlurConfig, state, image: Image,
                      rng: Optional[RandomGenerator]):
     mode = image.mode
     image = to_rgb_image(image, mode)
     image = gaussian_blur_device(image, config.sigma)
     assert rng is not None
-    pos_y, pos_x = glass_swap_maps(image.shape, config.delta, config.loop, rng)
+    maps = glass_swap_maps_device(image.shape, config.delta, config.loop, rng)
     src = image.dev
     dst = dv.empty(tuple(src.shape), np.uint8)
-    py = dv.to_device(np.ascontiguousarray(pos_y, dtype=np.int32))
-    px = dv.to_device(np.ascontiguousarray(pos_x, dtype=np.int32))
+    if maps is not None:
+        py, px = maps
+    else:  # a generator whose stream cannot be split, or a rejected draw: the maps come from the host
+        pos_y, pos_x = glass_swap_maps(image.shape, config.delta, config.loop, rng)
+        py = dv.to_device(np.ascontiguousarray(pos_y, dtype=np.int32))
+        px = dv.to_device(np.ascontiguousarray(pos_x, dtype=np.int32))
     nv.check(nv.lib().vkb_gather_pixels_u8(dv.ptr(src), dv.ptr(dst), image.height, image.width,
                                            image.num_channels or 1, dv.ptr(py), dv.ptr(px),
                                            dv.stream_ptr()), 'vkb_gather_pixels_u8')
